@@ -1,0 +1,117 @@
+"""ORACLE (test infrastructure): config trees of the golden / parity cases.
+
+``algorithm_cfg`` builds the full ``cfg.algorithm`` tree the reference reads
+eagerly in BaseVideoAlgo.__init__ (base_pytorch_video_algo.py:37-88) with the
+defaults of configurations/algorithm/dfot_video.yaml; keyword overrides use
+dotted paths ("diffusion.sampling_timesteps").
+"""
+import copy
+from typing import Any, Dict
+
+
+def _set(d: dict, path: str, value: Any) -> None:
+    keys = path.split(".")
+    for k in keys[:-1]:
+        d = d.setdefault(k, {})
+    d[keys[-1]] = value
+
+
+def algorithm_cfg(**overrides) -> Dict[str, Any]:
+    cfg = dict(
+        debug=False, lr=1e-4,
+        external_cond_type=None, external_cond_num_classes=None, external_cond_dim=0,
+        external_cond_stack=False, external_cond_processing=None,
+        backbone=dict(name="dit3d", variant="full", pos_emb_type="rope_3d", patch_size=2, hidden_size=384,
+                      depth=12, num_heads=6, mlp_ratio=4.0, use_gradient_checkpointing=False),
+        x_shape=[4, 16, 16], max_frames=8, n_frames=8, frame_skip=1, context_frames=1,
+        latent=dict(enabled=False, type="pre_sample", suffix=None, downsampling_factor=[1, 8], shape=None,
+                    num_channels=4),
+        data_mean=[[[0.0]]] * 4, data_std=[[[1.0]]] * 4,
+        compile=False, weight_decay=1e-3, optimizer_beta=[0.9, 0.99],
+        lr_scheduler=dict(name="constant_with_warmup", num_warmup_steps=5000),
+        noise_level="random_independent", uniform_future=dict(enabled=False),
+        fixed_context=dict(enabled=False, indices=None, dropout=0),
+        variable_context=dict(enabled=False, prob=0.25, dropout=0.3),
+        chunk_size=-1, scheduling_matrix="full_sequence", replacement="noisy_scale",
+        refinement_sampling=dict(enabled=False, goback_length=20, n_goback=5),
+        save_attn_map=dict(enabled=False, attn_map_dir=""),
+        diffusion=dict(is_continuous=False, timesteps=1000, beta_schedule="cosine",
+                       schedule_fn_kwargs=dict(shift=1.0), use_causal_mask=False, clip_noise=20.0,
+                       objective="pred_v",
+                       loss_weighting=dict(strategy="fused_min_snr", snr_clip=5.0, cum_snr_decay=0.9),
+                       sampling_timesteps=50, ddim_sampling_eta=0.0, reconstruction_guidance=0.0),
+        vae=dict(pretrained_path=None, pretrained_kwargs={}, use_fp16=False, batch_size=2),
+        checkpoint=dict(reset_optimizer=False, strict=True),
+        tasks=dict(
+            prediction=dict(enabled=True, history_guidance=dict(name="conditional", visualize=False),
+                            keyframe_density=None, sliding_context_len=None),
+            interpolation=dict(enabled=False, history_guidance=dict(name="conditional", visualize=False),
+                               max_batch_size=None)),
+        logging=dict(deterministic=0, loss_freq=100, grad_norm_freq=100, max_num_videos=8,
+                     n_metrics_frames=None, metrics=[], metrics_batch_size=16, sanity_generation=False,
+                     raw_dir=None),
+    )
+    for k, v in overrides.items():
+        _set(cfg, k.replace("__", "."), copy.deepcopy(v))
+    return cfg
+
+
+def continuous_overrides() -> Dict[str, Any]:
+    """configurations/shortcut/diffusion/continuous.yaml + the dataset_experiment defaults it is used with."""
+    return {
+        "diffusion.is_continuous": True, "diffusion.precond_scale": 0.125,
+        "diffusion.beta_schedule": "cosine_simple_diffusion",
+        "diffusion.schedule_fn_kwargs": dict(shifted=0.125, interpolated=False),
+        "diffusion.training_schedule": dict(name="cosine", shift=0.125),
+        "diffusion.loss_weighting": dict(strategy="sigmoid", sigmoid_bias=-1.0),
+        "backbone.use_fourier_noise_embedding": True,
+    }
+
+
+def _small(**kw):
+    """golden-sized DiT3D: D=64, 1 head (d=64), depth 2, MLP x2, latents [4,8,8], patch 2 → P=16; 4 tokens/window."""
+    base = {
+        "backbone.hidden_size": 64, "backbone.depth": 2, "backbone.num_heads": 1,
+        "backbone.spatial_mlp_ratio": 2.0, "x_shape": [4, 8, 8], "max_frames": 4, "n_frames": 4,
+        "context_frames": 1, "diffusion.sampling_timesteps": 5,
+    }
+    base.update(kw)
+    return algorithm_cfg(**base)
+
+
+def golden_cases() -> Dict[str, Dict[str, Any]]:
+    """name -> dict(cfg, batch, n_frames, cond_dim, weights)  (weights = which state-dict the case uses)"""
+    act = {"external_cond_type": "action", "external_cond_dim": 3, "external_cond_processing": "mask_first",
+           "backbone.external_cond_dropout": 0.1}
+    cases = {
+        "vanilla": dict(cfg=_small(**{"tasks.prediction.history_guidance":
+                                      dict(name="vanilla", guidance_scale=4.0, visualize=False)}),
+                        batch=2, weights="plain"),
+        "conditional_nomlp": dict(cfg=_small(**{"backbone.spatial_mlp_ratio": None}), batch=2, weights="nomlp"),
+        "stabilized_sliding": dict(cfg=_small(**{
+            "n_frames": 7, "tasks.prediction.sliding_context_len": 2,
+            "tasks.prediction.history_guidance": dict(name="stabilized_vanilla", guidance_scale=2.0,
+                                                      stabilization_level=0.02, visualize=False)}),
+            batch=1, weights="plain"),
+        "pyramid_conditional": dict(cfg=_small(**{"scheduling_matrix": "autoregressive"}), batch=1, weights="plain"),
+        "full_sequence_fractional": dict(cfg=_small(**{
+            "noise_level": "random_uniform", "context_frames": 2,
+            "tasks.prediction.history_guidance": dict(name="fractional", guidance_scale=3.0, freq_scale=0.3,
+                                                      visualize=False)}), batch=1, weights="plain"),
+        "temporal": dict(cfg=_small(**{
+            "context_frames": 2,
+            "tasks.prediction.history_guidance": dict(name="temporal", hist_subsequences=[[0], [1]],
+                                                      hist_weights=[1.5, 1.5], gen_segments=[[0], [1], [0, 1]],
+                                                      visualize=False)}), batch=1, weights="plain"),
+        "continuous_action": dict(cfg=_small(**{**continuous_overrides(), **act,
+                                                "tasks.prediction.history_guidance":
+                                                dict(name="vanilla", guidance_scale=2.5, visualize=False)}),
+                                  batch=2, weights="action"),
+        "keyframes_interp": dict(cfg=_small(**{
+            **continuous_overrides(), **act, "n_frames": 9,
+            "tasks.prediction.keyframe_density": 0.5, "tasks.prediction.sliding_context_len": 1,
+            "tasks.interpolation.enabled": False,
+            "tasks.interpolation.history_guidance": dict(name="vanilla", guidance_scale=1.5, visualize=False),
+            "tasks.interpolation.max_batch_size": 2}), batch=1, weights="action"),
+    }
+    return cases

@@ -1,0 +1,156 @@
+"""ORACLE (test infrastructure): DiT3D backbone forward (variant=full, rope_3d),
+functional over a reference-keyed state dict.
+
+Restates
+  algorithms/dfot/backbones/dit/dit3d.py:153-192           (patchify / unpatchify)
+  algorithms/dfot/backbones/dit/dit_base.py:310-425        (block loop, final layer)
+  algorithms/dfot/backbones/dit/dit_blocks.py:21-44,47-123 (attention), :408-437 (AdaLN-Zero),
+                                              :488-510 (block, residual-on-modulated quirk), :513-542
+  algorithms/dfot/backbones/modules/embeddings.py:67-153   (noise-level embedding), :156-277 (RoPE-ND)
+Third-party pieces restated from their pinned versions (see oracle/ref_shim.py):
+timm PatchEmbed / Mlp, diffusers TimestepEmbedding.
+"""
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+
+def sinusoidal_embedding(k: torch.Tensor, dim: int = 256) -> torch.Tensor:
+    """embeddings.py:112-153 with flip_sin_to_cos=True, downscale_freq_shift=0 → [cos | sin]."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half)
+    ang = k[..., None].float() * freqs
+    return torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1)
+
+
+def fourier_embedding(k: torch.Tensor, freqs: torch.Tensor, phases: torch.Tensor) -> torch.Tensor:
+    """embeddings.py:94-109."""
+    y = k.to(torch.float32)[..., None] * freqs.float() + phases.float()
+    return (y.cos() * math.sqrt(2)).to(k.dtype if k.is_floating_point() else torch.float32)
+
+
+def rope_axis_dims(head_dim: int) -> Tuple[int, int, int]:
+    """embeddings.py:254-277: rotary widths for (t, h, w)."""
+    half = head_dim // 2
+    q, r = divmod(half, 3)
+    dims = {0: (q, q, q), 1: (q + 1, q, q), 2: (q, q + 1, q + 1)}[r]
+    return tuple(2 * d for d in dims)
+
+
+def rope_angles(head_dim: int, sizes: Tuple[int, int, int], theta: float = 10000.0) -> torch.Tensor:
+    """embeddings.py:156-213: angle table [T*H*W, head_dim]; each frequency repeated twice."""
+    T, H, W = sizes
+    parts = []
+    for axis, (dim, n) in enumerate(zip(rope_axis_dims(head_dim), sizes)):
+        inv = 1.0 / (theta ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim))
+        ang = torch.arange(n, dtype=torch.float32)[:, None] * inv[None, :]
+        ang = ang.repeat_interleave(2, dim=-1)                     # [n, dim]
+        shape = [1, 1, 1, dim]
+        shape[axis] = n
+        parts.append(ang.reshape(shape).expand(T, H, W, dim))
+    return torch.cat(parts, dim=-1).reshape(T * H * W, head_dim)
+
+
+def apply_rope(x: torch.Tensor, angles: torch.Tensor) -> torch.Tensor:
+    """embeddings.py:204-215 with interleaved rotate_half: (x0,x1) -> (-x1,x0)."""
+    a = angles[: x.shape[-2]]
+    pairs = x.reshape(*x.shape[:-1], -1, 2)
+    rot = torch.stack((-pairs[..., 1], pairs[..., 0]), dim=-1).reshape(x.shape)
+    return x * a.cos() + rot * a.sin()
+
+
+def _linear(x, sd, prefix):
+    return F.linear(x, sd[prefix + ".weight"], sd.get(prefix + ".bias"))
+
+
+def _adaln(x, c_act, sd, prefix, chunks):
+    mod = _linear(c_act, sd, prefix + ".modulation.1")
+    parts = mod.chunk(chunks, dim=-1)
+    y = F.layer_norm(x, (x.shape[-1],), eps=1e-6) * (1 + parts[1]) + parts[0]
+    return (y, parts[2]) if chunks == 3 else y
+
+
+class DiT3DOracle:
+    """Callable (x[B,T,C,H,W], noise_levels[B,T], external_cond, external_cond_mask) -> like x."""
+
+    def __init__(self, backbone_cfg: dict, x_shape, max_tokens: int, state_dict: Dict[str, torch.Tensor],
+                 external_cond_dim: int = 0):
+        cfg = backbone_cfg
+        assert cfg.get("variant", "full") == "full" and cfg.get("pos_emb_type", "rope_3d") == "rope_3d"
+        self.sd = {k: v.detach().float() for k, v in state_dict.items()}
+        self.p = cfg["patch_size"]
+        self.C, self.H, self.W = x_shape
+        self.gh, self.gw = self.H // self.p, self.W // self.p
+        self.P = self.gh * self.gw
+        self.D = cfg["hidden_size"]
+        self.depth = cfg["depth"]
+        self.heads = cfg["num_heads"]
+        self.dh = self.D // self.heads
+        self.use_fourier = bool(cfg.get("use_fourier_noise_embedding", False))
+        self.external_cond_dim = external_cond_dim
+        self.cond_dropout = cfg.get("external_cond_dropout", 0.0)
+        self.angles = rope_angles(self.dh, (max_tokens, self.gh, self.gw))
+        # dit_base.py:185,192: MLP exists only if spatial_mlp_ratio is set (fork quirk Q2)
+        self.use_mlp = "dit_base.blocks.0.mlp.fc1.weight" in self.sd
+        self.taps = None  # optional dict filled with intermediates for kernel-level parity tests
+
+    def noise_embedding(self, k: torch.Tensor) -> torch.Tensor:
+        sd = self.sd
+        if self.use_fourier:
+            e = fourier_embedding(k, sd["noise_level_pos_embedding.timesteps.freqs"],
+                                  sd["noise_level_pos_embedding.timesteps.phases"])
+        else:
+            e = sinusoidal_embedding(k, 256)
+        e = _linear(e, sd, "noise_level_pos_embedding.embedding.linear_1")
+        return _linear(F.silu(e), sd, "noise_level_pos_embedding.embedding.linear_2")
+
+    def cond_embedding(self, cond: torch.Tensor, cond_mask: Optional[torch.Tensor]) -> torch.Tensor:
+        # embeddings.py:364-387: dropout_prob == 0 → plain TimestepEmbedding that ignores the mask
+        sd = self.sd
+        if self.cond_dropout == 0:
+            e = _linear(cond, sd, "external_cond_embedding.linear_1")
+            return _linear(F.silu(e), sd, "external_cond_embedding.linear_2")
+        e = _linear(cond, sd, "external_cond_embedding.embedding.linear_1")
+        e = _linear(F.silu(e), sd, "external_cond_embedding.embedding.linear_2")
+        if cond_mask is not None:
+            e = torch.where(cond_mask.reshape(-1, *([1] * (e.ndim - 1))), torch.zeros_like(e), e)
+        return e
+
+    def attention(self, y: torch.Tensor, i: int) -> torch.Tensor:
+        B, N, D = y.shape
+        qkv = _linear(y, self.sd, f"dit_base.blocks.{i}.attn.qkv")
+        q, k, v = qkv.reshape(B, N, 3, self.heads, self.dh).permute(2, 0, 3, 1, 4).unbind(0)
+        q, k = apply_rope(q, self.angles), apply_rope(k, self.angles)
+        w = torch.softmax(q @ k.transpose(-2, -1) * (1 / math.sqrt(self.dh)), dim=-1)
+        o = (w @ v).transpose(1, 2).reshape(B, N, D)
+        if self.taps is not None and i == 0:
+            self.taps.update(q0=q, k0=k, v0=v, attn0=o)
+        return _linear(o, self.sd, f"dit_base.blocks.{i}.attn.proj")
+
+    def __call__(self, x, noise_levels, external_cond=None, external_cond_mask=None):
+        B, T = x.shape[:2]
+        sd = self.sd
+        tok = F.conv2d(x.reshape(B * T, self.C, self.H, self.W).float(), sd["patch_embedder.proj.weight"],
+                       sd["patch_embedder.proj.bias"], stride=self.p)
+        tok = tok.flatten(2).transpose(1, 2).reshape(B, T * self.P, self.D)
+        emb = self.noise_embedding(noise_levels)
+        if external_cond is not None:
+            emb = emb + self.cond_embedding(external_cond.float(), external_cond_mask)
+        c_act = F.silu(emb.repeat_interleave(self.P, dim=1))      # per-token copy of a per-frame vector
+        h = tok
+        for i in range(self.depth):
+            pre = f"dit_base.blocks.{i}"
+            y, gate = _adaln(h, c_act, sd, pre + ".norm1", 3)
+            h = y + gate * self.attention(y, i)                    # residual base is the modulated tensor (Q1)
+            if self.use_mlp:
+                z, gate2 = _adaln(h, c_act, sd, pre + ".norm2", 3)
+                m = _linear(F.gelu(_linear(z, sd, pre + ".mlp.fc1"), approximate="tanh"), sd, pre + ".mlp.fc2")
+                h = z + gate2 * m
+            if self.taps is not None and i == 0:
+                self.taps.update(block0=h)
+        h = _adaln(h, c_act, sd, "dit_base.final_layer.norm_final", 2)
+        h = _linear(h, sd, "dit_base.final_layer.linear")           # [B, T*P, p*p*C]
+        h = h.reshape(B, T, self.gh, self.gw, self.p, self.p, self.C)
+        return h.permute(0, 1, 6, 2, 4, 3, 5).reshape(B, T, self.C, self.H, self.W)

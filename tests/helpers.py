@@ -1,0 +1,45 @@
+"""Shared test helpers: golden loading and oracle construction (test infrastructure)."""
+import json
+import os
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def load_case(name):
+    with open(os.path.join(GOLDEN, f"case_{name}.json")) as f:
+        meta = json.load(f)
+    arrays = dict(np.load(os.path.join(GOLDEN, f"case_{name}.npz")))
+    weights = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, f"weights_{meta['weights']}.npz")).items()}
+    return meta, arrays, weights
+
+
+def case_names():
+    return sorted(f[len("case_"):-len(".json")] for f in os.listdir(GOLDEN) if f.startswith("case_") and f.endswith(".json"))
+
+
+def build_oracle(cfg, weights, randn=torch.randn, randn_like=torch.randn_like):
+    from oracle.dit3d import DiT3DOracle
+    from oracle.sampler import SamplerOracle
+    probe = SamplerOracle(cfg, None)
+    model = DiT3DOracle(cfg["backbone"], probe.x_shape, probe.max_tokens, weights,
+                        external_cond_dim=probe.external_cond_dim)
+    return SamplerOracle(cfg, model, randn, randn_like), model
+
+
+class NoiseBank:
+    """Deterministic noise shared by oracle (CPU) and product (GPU): call i of shape s -> randn(seed+i)."""
+
+    def __init__(self, seed=1234, device="cpu"):
+        self.seed, self.i, self.device = seed, 0, device
+
+    def randn(self, shape, **kw):
+        g = torch.Generator().manual_seed(self.seed + self.i)
+        self.i += 1
+        return torch.randn(tuple(shape), generator=g).to(self.device)
+
+    def randn_like(self, x):
+        return self.randn(x.shape)
