@@ -1,0 +1,82 @@
+"""ctypes binding of libdfot_b200.so (the C ABI declared in include/dfot_b200.h)."""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdfot_b200.so")
+
+F32, BF16, I64 = 0, 1, 2
+EPI_F32, EPI_BF16, EPI_GELU_BF16, EPI_SILU_BF16, EPI_GATE_RESID_F32, EPI_QKV_ROPE_BF16 = range(6)
+
+SYMBOLS = [
+    "dfot_abi_version", "dfot_last_error", "dfot_launch_count", "dfot_sampler_step_hg", "dfot_adaln_layernorm",
+    "dfot_gemm_bf16", "dfot_attention", "dfot_noise_features", "dfot_silu_sum_bf16", "dfot_patchify_bf16",
+    "dfot_unpatchify", "dfot_cast_bf16",
+]
+
+
+class FrameUpdate(Structure):
+    _fields_ = [("a", c_float), ("b", c_float), ("sigma", c_float), ("w", c_float), ("clip", c_float),
+                ("generate", c_int32)]
+
+
+class FramePrepare(Structure):
+    _fields_ = [("mode", c_int32), ("noise_row", c_int32), ("qa", c_float), ("qb", c_float)]
+
+
+class GemmEpilogue(Structure):
+    _fields_ = [("bias", c_void_p), ("resid", c_void_p), ("ld_resid", c_int64), ("gate", c_void_p),
+                ("ld_gate", c_int64), ("tokens_per_frame", c_int64), ("rope_cs", c_void_p),
+                ("tokens_per_sample", c_int64), ("model_dim", c_int64), ("head_dim", c_int64),
+                ("q_scale", c_float)]
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load the library; build it first if the sources are newer / it is missing and nvcc exists.
+    Fails loudly — there is no fallback implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from .build import build
+        try:
+            build()
+        except Exception as e:  # noqa: BLE001
+            raise RuntimeError(
+                f"dfot_b200: CUDA extension {LIB_PATH} is missing and could not be built ({e}). "
+                "Run `python __graft_entry__.py build` on a machine with nvcc; there is no CPU fallback.") from e
+    L = ctypes.CDLL(LIB_PATH)
+    L.dfot_abi_version.restype = c_int
+    L.dfot_last_error.restype = c_char_p
+    L.dfot_launch_count.restype = c_int64
+    vp, i64, i = c_void_p, c_int64, c_int
+    L.dfot_sampler_step_hg.argtypes = [vp, vp, i, vp, i, vp, vp, vp, vp, vp, i64, i64, i64, i64, vp]
+    L.dfot_adaln_layernorm.argtypes = [vp, vp, i64, i64, i64, vp, vp, i64, i64, i64, c_float, vp]
+    L.dfot_gemm_bf16.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, i64, i, POINTER(GemmEpilogue), vp]
+    L.dfot_attention.argtypes = [vp, vp, i64, i64, i64, i64, vp]
+    L.dfot_noise_features.argtypes = [vp, i, vp, vp, vp, i64, i64, vp]
+    L.dfot_silu_sum_bf16.argtypes = [vp, vp, vp, i64, vp, i64, i64, vp]
+    L.dfot_patchify_bf16.argtypes = [vp, i, vp, i64, i64, i64, i64, i64, vp]
+    L.dfot_unpatchify.argtypes = [vp, i64, vp, i, i64, i64, i64, i64, i64, vp]
+    L.dfot_cast_bf16.argtypes = [vp, vp, i64, vp]
+    for name in SYMBOLS:
+        if name not in ("dfot_last_error", "dfot_launch_count"):
+            getattr(L, name).restype = c_int
+    if L.dfot_abi_version() != 1:
+        raise RuntimeError("dfot_b200: ABI version mismatch between Python binding and libdfot_b200.so")
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().dfot_last_error().decode(errors="replace")
+        raise RuntimeError(f"dfot_b200 {what} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().dfot_launch_count())

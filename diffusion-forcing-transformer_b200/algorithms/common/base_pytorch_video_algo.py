@@ -1,0 +1,205 @@
+"""BaseVideoAlgo — the slice of the reference's algorithms/common/base_pytorch_video_algo.py that the
+denoising sampling path uses: shape / latent / token bookkeeping (:37-88, :986-1033), model construction
+(:142-174), normalisation (:489-502), condition processing (:635-700), scheduling matrices (:877-947) and
+the validation entry point (:234-264).  Training, VAE encode/decode, metrics and logging are out of scope
+(SURVEY.md §2): the hooks exist where callers need them and raise or no-op explicitly.
+
+It is a plain ``nn.Module`` (Lightning is not a dependency of the sampling path); ``state_dict()`` keys are
+identical to the reference's (``data_mean``, ``data_std``, ``diffusion_model.model.*``).
+"""
+from typing import Callable, Dict, Optional
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+from dfot_b200.config import to_config
+
+
+class BaseVideoAlgo(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        cfg = to_config(cfg)
+        self.cfg = cfg
+        self.debug = cfg.get("debug", False)
+        # 1. shape
+        self.x_shape = list(cfg.x_shape)
+        self.frame_skip = cfg.frame_skip
+        self.chunk_size = cfg.chunk_size
+        self.external_cond_type = cfg.external_cond_type
+        self.external_cond_num_classes = cfg.external_cond_num_classes
+        self.external_cond_dim = cfg.external_cond_dim * (cfg.frame_skip if cfg.external_cond_stack else 1)
+        # 2. latent
+        lat = cfg.latent
+        self.is_latent_diffusion = lat.enabled
+        self.is_latent_online = lat.type == "online"
+        self.temporal_downsampling_factor = lat.downsampling_factor[0]
+        self.is_latent_video_vae = self.temporal_downsampling_factor > 1
+        if self.is_latent_diffusion:
+            self.x_shape = list(lat.shape) if lat.get("shape") is not None else \
+                [lat.num_channels] + [d // lat.downsampling_factor[1] for d in self.x_shape[1:]]
+        # 3. diffusion
+        d = cfg.diffusion
+        self.use_causal_mask = d.use_causal_mask
+        self.timesteps = d.timesteps
+        self.sampling_timesteps = d.sampling_timesteps
+        self.clip_noise = d.clip_noise
+        self.is_full_sequence = (cfg.noise_level == "random_uniform" and not cfg.fixed_context.enabled
+                                 and not cfg.variable_context.enabled)
+        # 4. tasks
+        self.logging = cfg.get("logging")
+        self.tasks = [t for t in ("prediction", "interpolation") if cfg.tasks[t].enabled]
+        self.generator = None
+        self._build_model()
+
+    # ------------------------------------------------------------------ construction
+    def _build_model(self, diffusion_cls: Optional[Callable] = None) -> None:
+        if self.cfg.get("compile", False):
+            raise NotImplementedError("torch.compile is a training-only knob in the reference and is not used here")
+        self.diffusion_model = diffusion_cls(
+            cfg=self.cfg.diffusion, backbone_cfg=self.cfg.backbone, x_shape=self.x_shape, max_tokens=self.max_tokens,
+            external_cond_type=self.external_cond_type, external_cond_num_classes=self.external_cond_num_classes,
+            external_cond_dim=self.external_cond_dim)
+        self.register_buffer("data_mean", torch.tensor(self.cfg.data_mean).float())
+        self.register_buffer("data_std", torch.tensor(self.cfg.data_std).float())
+        self.vae = None
+
+    @property
+    def device(self) -> torch.device:
+        return self.data_mean.device
+
+    # ------------------------------------------------------------------ data plumbing (pre/post-processing, not per step)
+    def on_after_batch_transfer(self, batch: Dict, dataloader_idx: int = 0) -> Dict:
+        if self.is_latent_diffusion:
+            if self.is_latent_online:
+                raise NotImplementedError("online VAE encoding is outside the sampling-path scope; pass `latents`")
+            xs = batch["latents"]
+        else:
+            xs = batch["videos"]
+        gt_videos = batch.get("videos") if self.is_latent_diffusion else None
+        xs = self._normalize_x(xs)
+        if "masks" in batch:
+            assert not self.is_latent_video_vae, "Masks should not be provided from the dataset when using VideoVAE."
+            masks = batch["masks"]
+        else:
+            masks = torch.ones(*xs.shape[:2], dtype=torch.bool, device=xs.device)
+        return {"xs": xs, "conditions": batch.get("conds", None), "masks": masks, "gt_videos": gt_videos}
+
+    def _stat(self, t: Tensor, xs: Tensor) -> Tensor:
+        return t.reshape([1] * (xs.ndim - t.ndim) + list(t.shape))
+
+    def _normalize_x(self, xs: Tensor) -> Tensor:
+        return (xs - self._stat(self.data_mean, xs)) / self._stat(self.data_std, xs)
+
+    def _unnormalize_x(self, xs: Tensor) -> Tensor:
+        return xs * self._stat(self.data_std, xs) + self._stat(self.data_mean, xs)
+
+    @torch.no_grad()
+    def new_validation_step(self, batch, batch_idx, accelerator=None, namespace="validation", validate_sample=True):
+        """(:234-264) — the denoising-loss evaluation is a training diagnostic and returns None here."""
+        all_videos = None
+        if validate_sample:
+            all_videos = self._sample_all_videos(batch, batch_idx, namespace, n_context_tokens=self.n_context_tokens)
+        return None, all_videos
+
+    @torch.no_grad()
+    def validation_step(self, batch, batch_idx, namespace="validation"):
+        return self._sample_all_videos(batch, batch_idx, namespace)
+
+    # ------------------------------------------------------------------ conditions / padding (:635-700)
+    @torch.no_grad()
+    def _process_conditions(self, conditions: Optional[Tensor], noise_levels: Optional[Tensor] = None):
+        if conditions is None:
+            return conditions
+        mode = self.cfg.external_cond_processing
+        if mode is None:
+            return conditions
+        if mode == "mask_first":
+            out = conditions.clone()
+            out[:, :1, : self.external_cond_dim] = 0
+            return out
+        raise NotImplementedError(f"External condition processing {mode} is not implemented.")
+
+    def _pad_to_max_tokens(self, y: Optional[Tensor]) -> Optional[Tensor]:
+        if y is None or y.shape[1] >= self.max_tokens:
+            return y
+        tail = y[:, -1:].expand(-1, self.max_tokens - y.shape[1], *y.shape[2:])
+        return torch.cat([y, tail], dim=1)
+
+    def _extend_x_dim(self, x: Tensor) -> Tensor:
+        return x.reshape(*x.shape, *([1] * len(self.x_shape)))
+
+    # ------------------------------------------------------------------ scheduling matrices (:877-947), host side
+    def _generate_scheduling_matrix(self, horizon: int, padding: int = 0) -> Tensor:
+        kind, S = self.cfg.scheduling_matrix, self.sampling_timesteps
+        if kind in ("full_sequence", "gibbs"):
+            idx = np.repeat(np.arange(S, -1, -1)[:, None], horizon, axis=1)
+        elif kind == "autoregressive":
+            idx = self._generate_pyramid_scheduling_matrix(horizon, S)
+        elif kind == "interleaved":
+            idx = self._generate_interleaved_scheduling_matrix(horizon, 3, S)
+        else:
+            raise ValueError(f"unknown scheduling matrix {kind}")
+        levels = self.diffusion_model.ddim_idx_to_noise_level(torch.from_numpy(idx).long())
+        if kind == "gibbs":   # one frame advances at a time; later frames hold the previous sweep's value
+            sweeps = levels.shape[0]
+            levels = levels.repeat_interleave(horizon, dim=0)
+            for i in range(1, sweeps):
+                prev_last = levels[(i - 1) * horizon + horizon - 1].clone()
+                for j in range(horizon):
+                    levels[i * horizon + j, j + 1:] = prev_last[j + 1:]
+        return torch.nn.functional.pad(levels, (0, padding, 0, 0), value=self.timesteps - 1)
+
+    def _generate_interleaved_scheduling_matrix(self, horizon: int, interleaved_size: int = 2,
+                                                sampling_timesteps: int = 50) -> np.ndarray:
+        S, k = sampling_timesteps, interleaved_size
+        rows = S + k
+        out = np.zeros((rows, horizon), dtype=np.int64)
+        for t in range(horizon):
+            lead = t % k + 1
+            col = [S] * lead
+            j = 0
+            while len(col) < rows:
+                idx = max(S - lead - k * j, 0)
+                col += [idx] * (k if idx > 0 else rows - len(col))
+                j += 1
+            out[:, t] = col[:rows]
+        return out
+
+    def _generate_pyramid_scheduling_matrix(self, horizon: int, sampling_timesteps: int,
+                                            uncertainty_scale: float = 1.0) -> np.ndarray:
+        height = sampling_timesteps + int((horizon - 1) * uncertainty_scale) + 1
+        lag = np.array([int(t * uncertainty_scale) for t in range(horizon)], dtype=np.int64)
+        m = np.arange(height, dtype=np.int64)[:, None]
+        return np.clip(sampling_timesteps + lag[None, :] - m, 0, sampling_timesteps)
+
+    # ------------------------------------------------------------------ frames vs tokens (:986-1033)
+    def _n_frames_to_n_tokens(self, n_frames: int) -> int:
+        return (n_frames - 1) // self.temporal_downsampling_factor + 1
+
+    def _n_tokens_to_n_frames(self, n_tokens: int) -> int:
+        return (n_tokens - 1) * self.temporal_downsampling_factor + 1
+
+    @property
+    def max_frames(self) -> int:
+        return self.cfg.max_frames
+
+    @property
+    def max_tokens(self) -> int:
+        return self._n_frames_to_n_tokens(self.max_frames)
+
+    @property
+    def n_frames(self) -> int:
+        return self.cfg.n_frames
+
+    @property
+    def n_context_frames(self) -> int:
+        return self.cfg.context_frames
+
+    @property
+    def n_tokens(self) -> int:
+        return self._n_frames_to_n_tokens(self.n_frames)
+
+    @property
+    def n_context_tokens(self) -> int:
+        return self._n_frames_to_n_tokens(self.n_context_frames)

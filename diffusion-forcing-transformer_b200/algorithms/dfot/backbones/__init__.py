@@ -1,0 +1,3 @@
+from .dit.dit3d import DiT3D
+
+__all__ = ["DiT3D"]

@@ -1,0 +1,362 @@
+"""DiT3D backbone (variant=full, pos_emb_type=rope_3d) on hand-written sm_100a kernels.
+
+Drop-in for the reference class
+    algorithms/dfot/backbones/dit/dit3d.py:11-192  (DiT3D),
+    algorithms/dfot/backbones/dit/dit_base.py:77-425 (DiTBase), dit_blocks.py:378-542 (blocks)
+same constructor signature, same ``forward(x, noise_levels, external_cond, external_cond_mask)`` and the
+same ``state_dict()`` keys, so a reference checkpoint loads unchanged.  Parameters are kept in fp32
+under the reference's names; kernel-layout copies (bf16, concatenated modulation weights, padded
+patch-embed / condition weights, RoPE cos/sin table) are (re)packed lazily whenever a parameter changes.
+
+Per forward (R rows, T frames, P patches/frame, M = R*T*P tokens, D hidden):
+    K4/patchify → [tcgen05 GEMM] patch-embed → x f32
+    noise features → GEMM(+SiLU) → GEMM → (+cond emb) SiLU → ONE GEMM for the adaLN modulation of all blocks
+        (per *frame*, M = R*T rows — the reference recomputes it per token: 30 % of its FLOPs at K600-XL)
+    per block: K1 adaLN-LN → GEMM qkv (+bias, RoPE-3D, q-scale fused in the epilogue) → K3 attention →
+               GEMM proj (+bias, gate, residual fused) → K1 → GEMM fc1 (+bias, GELU) → GEMM fc2 (+gate, residual)
+    K1 (final) → GEMM final → unpatchify
+"""
+import math
+from typing import Optional
+
+import torch
+from torch import nn
+
+from dfot_b200 import ops
+from dfot_b200.config import to_config
+
+LOG2E = 1.4426950408889634
+
+
+# ------------------------------------------------------------------ parameter containers (reference key names)
+class _TimestepMLP(nn.Module):          # diffusers TimestepEmbedding: linear_1 → SiLU → linear_2
+    def __init__(self, in_dim: int, dim: int):
+        super().__init__()
+        self.linear_1 = nn.Linear(in_dim, dim)
+        self.linear_2 = nn.Linear(dim, dim)
+
+
+class _Fourier(nn.Module):              # embeddings.py:94-109 (persistent random buffers)
+    def __init__(self, dim: int):
+        super().__init__()
+        self.register_buffer("freqs", 2 * math.pi * torch.randn(dim))
+        self.register_buffer("phases", 2 * math.pi * torch.rand(dim))
+
+
+class _NoiseLevelEmbedding(nn.Module):  # embeddings.py:67-91
+    def __init__(self, dim: int, emb_dim: int, use_fourier: bool):
+        super().__init__()
+        if use_fourier:
+            self.timesteps = _Fourier(dim)
+        self.embedding = _TimestepMLP(dim, emb_dim)
+
+
+class _CondEmbeddingDropout(nn.Module):  # embeddings.py:364-387 with dropout_prob > 0
+    def __init__(self, cond_dim: int, emb_dim: int):
+        super().__init__()
+        self.embedding = _TimestepMLP(cond_dim, emb_dim)
+
+
+class _PatchEmbed(nn.Module):           # timm PatchEmbed: Conv2d(k = s = p)
+    def __init__(self, in_chans: int, dim: int, p: int):
+        super().__init__()
+        self.proj = nn.Conv2d(in_chans, dim, kernel_size=p, stride=p, bias=True)
+
+
+class _AdaLN(nn.Module):                # dit_blocks.py:378-437
+    def __init__(self, dim: int, chunks: int):
+        super().__init__()
+        self.modulation = nn.Sequential(nn.SiLU(), nn.Linear(dim, chunks * dim, bias=True))
+        nn.init.zeros_(self.modulation[-1].weight)
+        nn.init.zeros_(self.modulation[-1].bias)
+
+
+class _Attention(nn.Module):            # dit_blocks.py:47-79
+    def __init__(self, dim: int):
+        super().__init__()
+        self.qkv = nn.Linear(dim, 3 * dim, bias=True)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _Mlp(nn.Module):                  # timm Mlp
+    def __init__(self, dim: int, hidden: int):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class _Block(nn.Module):                # dit_blocks.py:440-510
+    def __init__(self, dim: int, mlp_ratio: Optional[float]):
+        super().__init__()
+        self.norm1 = _AdaLN(dim, 3)
+        self.attn = _Attention(dim)
+        self.use_mlp = mlp_ratio is not None and mlp_ratio > 0.0
+        if self.use_mlp:
+            self.norm2 = _AdaLN(dim, 3)
+            self.mlp = _Mlp(dim, int(dim * mlp_ratio))
+        for lin in [self.attn.qkv, self.attn.proj] + ([self.mlp.fc1, self.mlp.fc2] if self.use_mlp else []):
+            nn.init.xavier_uniform_(lin.weight)
+            nn.init.zeros_(lin.bias)
+
+
+class _FinalLayer(nn.Module):           # dit_blocks.py:513-542
+    def __init__(self, dim: int, out_channels: int):
+        super().__init__()
+        self.norm_final = _AdaLN(dim, 2)
+        self.linear = nn.Linear(dim, out_channels, bias=True)
+        nn.init.zeros_(self.linear.weight)
+        nn.init.zeros_(self.linear.bias)
+
+
+class _DiTBase(nn.Module):
+    def __init__(self, dim: int, depth: int, spatial_mlp_ratio: Optional[float], out_channels: int):
+        super().__init__()
+        # dit_base.py:185,192 — "full" blocks take spatial_mlp_ratio (None ⇒ no MLP; fork quirk Q2)
+        self.blocks = nn.ModuleList([_Block(dim, spatial_mlp_ratio) for _ in range(depth)])
+        self.final_layer = _FinalLayer(dim, out_channels)
+
+
+def rope_axis_dims(head_dim: int):
+    """embeddings.py:254-277: rotary widths of the (t, h, w) axes."""
+    half = head_dim // 2
+    q, r = divmod(half, 3)
+    dims = {0: (q, q, q), 1: (q + 1, q, q), 2: (q, q + 1, q + 1)}[r]
+    return tuple(2 * d for d in dims)
+
+
+def rope_cos_sin_table(head_dim: int, sizes, theta: float = 10000.0) -> torch.Tensor:
+    """[T*H*W, head_dim/2, 2] (cos, sin) of the pair angles (embeddings.py:156-213; both elements of an
+    interleaved pair share one angle, so only every second column of the reference table is kept)."""
+    T, H, W = sizes
+    parts = []
+    for axis, (dim, n) in enumerate(zip(rope_axis_dims(head_dim), sizes)):
+        inv = 1.0 / (theta ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim))
+        ang = torch.arange(n, dtype=torch.float32)[:, None] * inv[None, :]
+        shape = [1, 1, 1, dim // 2]
+        shape[axis] = n
+        parts.append(ang.reshape(shape).expand(T, H, W, dim // 2))
+    ang = torch.cat(parts, dim=-1).reshape(T * H * W, head_dim // 2)
+    return torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class DiT3D(nn.Module):
+    def __init__(self, cfg, x_shape, max_tokens: int, external_cond_type: Optional[str] = None,
+                 external_cond_num_classes: Optional[int] = None, external_cond_dim: int = 0,
+                 use_causal_mask: bool = True):
+        if use_causal_mask:
+            raise NotImplementedError("Causal masking is not yet implemented for DiT3D backbone")  # dit3d.py:23-26
+        super().__init__()
+        cfg = to_config(cfg)
+        if cfg.get("variant", "full") != "full" or cfg.get("pos_emb_type", "rope_3d") != "rope_3d":
+            raise NotImplementedError("dfot_b200 DiT3D supports variant=full with pos_emb_type=rope_3d "
+                                      "(the default dit3d.yaml); other variants are fork-only ablations")
+        if external_cond_type == "label" and external_cond_dim:
+            raise NotImplementedError("label conditioning is outside the B200 hot-path scope (SURVEY.md §8)")
+        self.cfg = cfg
+        self.x_shape = list(x_shape)
+        self.max_tokens = max_tokens
+        self.external_cond_type = external_cond_type
+        self.external_cond_num_classes = external_cond_num_classes
+        self.external_cond_dim = external_cond_dim or 0
+        self.use_causal_mask = use_causal_mask
+        self.patch_size = cfg.patch_size
+        C, H, W = self.x_shape
+        self.num_patches_h, self.num_patches_w = H // self.patch_size, W // self.patch_size
+        self.num_patches = self.num_patches_h * self.num_patches_w
+        self.hidden_size = D = cfg.hidden_size
+        self.num_heads = cfg.num_heads
+        self.head_dim = D // self.num_heads
+        self.depth = cfg.depth
+        if D % self.num_heads or self.head_dim not in (64, 72, 128):
+            raise NotImplementedError(f"head_dim {self.head_dim} unsupported by the attention kernel (64, 72, 128)")
+        self.external_cond_dropout = cfg.get("external_cond_dropout", 0.0)
+
+        self.noise_level_pos_embedding = _NoiseLevelEmbedding(256, D, bool(cfg.get("use_fourier_noise_embedding",
+                                                                                  False)))
+        if self.external_cond_dim:
+            self.external_cond_embedding = (_TimestepMLP(self.external_cond_dim, D) if self.external_cond_dropout == 0
+                                            else _CondEmbeddingDropout(self.external_cond_dim, D))
+        else:
+            self.external_cond_embedding = None
+        self.patch_embedder = _PatchEmbed(C, D, self.patch_size)
+        self.dit_base = _DiTBase(D, self.depth, cfg.get("spatial_mlp_ratio", None), self.patch_size ** 2 * C)
+        self.use_mlp = self.dit_base.blocks[0].use_mlp
+        self._init_embedders()
+        self._packed = None
+        self._packed_key = None
+        self._ws = {}
+
+    # dit3d.py:91-108
+    def _init_embedders(self):
+        w = self.patch_embedder.proj.weight.data
+        nn.init.xavier_uniform_(w.view(w.shape[0], -1))
+        nn.init.zeros_(self.patch_embedder.proj.bias)
+        mlps = [self.noise_level_pos_embedding]
+        if self.external_cond_embedding is not None:
+            mlps.append(self.external_cond_embedding)
+        for root in mlps:
+            for m in root.modules():
+                if isinstance(m, nn.Linear):
+                    nn.init.normal_(m.weight, std=0.02)
+                    nn.init.zeros_(m.bias)
+
+    @property
+    def n_tokens_per_frame(self) -> int:
+        return self.num_patches
+
+    # ------------------------------------------------------------------ weight packing
+    def _version_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + \
+               tuple((b.data_ptr(), b._version) for b in self.buffers())
+
+    def packed(self):
+        key = self._version_key()
+        if self._packed is not None and key == self._packed_key:
+            return self._packed
+        dev = self.patch_embedder.proj.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("dfot_b200: DiT3D runs on CUDA only (no CPU fallback); move the module to a B200")
+        D, C, p = self.hidden_size, self.x_shape[0], self.patch_size
+        bf = lambda w: ops.cast_bf16(w.detach().float().contiguous())
+        f32 = lambda b: b.detach().float().contiguous()
+        P = {}
+        te = self.noise_level_pos_embedding.embedding
+        P["t1_w"], P["t1_b"], P["t2_w"], P["t2_b"] = bf(te.linear_1.weight), f32(te.linear_1.bias), \
+            bf(te.linear_2.weight), f32(te.linear_2.bias)
+        if hasattr(self.noise_level_pos_embedding, "timesteps"):
+            P["four_f"] = f32(self.noise_level_pos_embedding.timesteps.freqs)
+            P["four_p"] = f32(self.noise_level_pos_embedding.timesteps.phases)
+        if self.external_cond_embedding is not None:
+            ce = self.external_cond_embedding if self.external_cond_dropout == 0 else self.external_cond_embedding.embedding
+            kc = _pad8(self.external_cond_dim)
+            w1 = torch.zeros((D, kc), device=dev)
+            w1[:, : self.external_cond_dim] = ce.linear_1.weight.detach().float()
+            P["c1_w"], P["c1_b"], P["c2_w"], P["c2_b"] = bf(w1), f32(ce.linear_1.bias), bf(ce.linear_2.weight), \
+                f32(ce.linear_2.bias)
+        kp = _pad8(C * p * p)
+        wp = torch.zeros((D, kp), device=dev)
+        wp[:, : C * p * p] = self.patch_embedder.proj.weight.detach().float().reshape(D, -1)
+        P["pe_w"], P["pe_b"] = bf(wp), f32(self.patch_embedder.proj.bias)
+        mods_w, mods_b = [], []
+        for blk in self.dit_base.blocks:
+            mods_w.append(blk.norm1.modulation[-1].weight)
+            mods_b.append(blk.norm1.modulation[-1].bias)
+            if blk.use_mlp:
+                mods_w.append(blk.norm2.modulation[-1].weight)
+                mods_b.append(blk.norm2.modulation[-1].bias)
+        fl = self.dit_base.final_layer
+        mods_w.append(fl.norm_final.modulation[-1].weight)
+        mods_b.append(fl.norm_final.modulation[-1].bias)
+        P["mod_w"] = bf(torch.cat([w.detach().float() for w in mods_w], 0))
+        P["mod_b"] = torch.cat([b.detach().float() for b in mods_b], 0).contiguous()
+        P["blocks"] = []
+        for blk in self.dit_base.blocks:
+            d = dict(qkv_w=bf(blk.attn.qkv.weight), qkv_b=f32(blk.attn.qkv.bias), proj_w=bf(blk.attn.proj.weight),
+                     proj_b=f32(blk.attn.proj.bias))
+            if blk.use_mlp:
+                d.update(fc1_w=bf(blk.mlp.fc1.weight), fc1_b=f32(blk.mlp.fc1.bias), fc2_w=bf(blk.mlp.fc2.weight),
+                         fc2_b=f32(blk.mlp.fc2.bias))
+            P["blocks"].append(d)
+        no = _pad8(p * p * C)
+        wf = torch.zeros((no, D), device=dev)
+        wf[: p * p * C] = fl.linear.weight.detach().float()
+        bfin = torch.zeros((no,), device=dev)
+        bfin[: p * p * C] = fl.linear.bias.detach().float()
+        P["fin_w"], P["fin_b"] = bf(wf), bfin
+        P["rope"] = rope_cos_sin_table(self.head_dim, (self.max_tokens, self.num_patches_h, self.num_patches_w)).to(dev)
+        self._packed, self._packed_key = P, key
+        return P
+
+    def _workspace(self, R: int, T: int, dev, out_dtype):
+        key = (R, T, str(dev), out_dtype)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        D, C, p = self.hidden_size, self.x_shape[0], self.patch_size
+        M, RT = R * T * self.num_patches, R * T
+        n_mod = (6 if self.use_mlp else 3) * self.depth + 2
+        e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+        bf, f32 = torch.bfloat16, torch.float32
+        ws = dict(feat=e((RT, 256), bf), e1=e((RT, D), bf), emb=e((RT, D), f32), cact=e((RT, D), bf),
+                  mod=e((RT, n_mod * D), f32), patches=torch.zeros((M, _pad8(C * p * p)), dtype=bf, device=dev),
+                  x=e((M, D), f32), y=e((M, D), f32), y16=e((M, D), bf), qkv=e((M, 3 * D), bf), att=e((M, D), bf),
+                  tok=e((M, _pad8(p * p * C)), f32), out=e((R, T, *self.x_shape), out_dtype))
+        if self.use_mlp:
+            ws["h"] = e((M, self.dit_base.blocks[0].mlp.fc1.out_features), bf)
+        if self.external_cond_embedding is not None:
+            ws.update(cin=torch.zeros((RT, _pad8(self.external_cond_dim)), dtype=bf, device=dev), c1=e((RT, D), bf),
+                      cemb=e((RT, D), f32))
+        self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, noise_levels: torch.Tensor, external_cond: Optional[torch.Tensor] = None,
+                external_cond_mask: Optional[torch.Tensor] = None, out_dtype=torch.float32) -> torch.Tensor:
+        """x [R,T,C,H,W] f32|bf16; noise_levels [R,T] int64 (discrete) or f32 (continuous: precond*logsnr).
+        Returns a tensor shaped like x (a workspace buffer that the next call overwrites)."""
+        if not x.is_cuda:
+            raise RuntimeError("dfot_b200: DiT3D.forward needs CUDA tensors (no CPU fallback)")
+        R, T = x.shape[:2]
+        C, H, W = self.x_shape
+        D, p, Pn = self.hidden_size, self.patch_size, self.num_patches
+        if T > self.max_tokens:
+            raise ValueError(f"Input sequence length {T * Pn} exceeds the maximum length {self.max_tokens * Pn}")
+        Pk = self.packed()
+        ws = self._workspace(R, T, x.device, out_dtype)
+        M, RT, Ntok = R * T * Pn, R * T, T * Pn
+        x = x.contiguous()
+        levels = noise_levels.contiguous()
+        if levels.dtype not in (torch.int64, torch.float32):
+            levels = levels.float()
+
+        # --- tokens
+        ops.patchify_bf16(x, ws["patches"], RT, C, H, W, p)
+        ops.gemm_bf16(ws["patches"], Pk["pe_w"], ws["x"], ops.EPI_F32, bias=Pk["pe_b"])
+        # --- per-frame conditioning vector c = silu(noise_emb [+ cond_emb])
+        ops.noise_features(levels, ws["feat"], Pk.get("four_f"), Pk.get("four_p"))
+        ops.gemm_bf16(ws["feat"], Pk["t1_w"], ws["e1"], ops.EPI_SILU_BF16, bias=Pk["t1_b"])
+        ops.gemm_bf16(ws["e1"], Pk["t2_w"], ws["emb"], ops.EPI_F32, bias=Pk["t2_b"])
+        cemb, row_mask = None, None
+        if external_cond is not None:
+            if self.external_cond_embedding is None:
+                raise ValueError("external_cond given but the backbone was built with external_cond_dim=0")
+            ws["cin"][:, : self.external_cond_dim] = external_cond.reshape(RT, -1).to(torch.bfloat16)
+            ops.gemm_bf16(ws["cin"], Pk["c1_w"], ws["c1"], ops.EPI_SILU_BF16, bias=Pk["c1_b"])
+            ops.gemm_bf16(ws["c1"], Pk["c2_w"], ws["cemb"], ops.EPI_F32, bias=Pk["c2_b"])
+            cemb = ws["cemb"]
+            # embeddings.py:364-387: with dropout_prob == 0 the embedding is a plain MLP and ignores the mask
+            if external_cond_mask is not None and self.external_cond_dropout != 0:
+                row_mask = external_cond_mask.to(torch.uint8).contiguous()
+        ops.silu_sum_bf16(ws["emb"], cemb, row_mask, T, ws["cact"])
+        ops.gemm_bf16(ws["cact"], Pk["mod_w"], ws["mod"], ops.EPI_F32, bias=Pk["mod_b"])
+        mod, ldm = ws["mod"], ws["mod"].shape[1]
+
+        # --- blocks
+        q_scale = LOG2E / math.sqrt(self.head_dim)
+        col = 0
+        xa, xb = ws["x"], ws["y"]
+        for bw in Pk["blocks"]:
+            ops.adaln_layernorm(xa, mod, col, col + D, Pn, y_f32=xb, y_bf16=ws["y16"])
+            ops.gemm_bf16(ws["y16"], bw["qkv_w"], ws["qkv"], ops.EPI_QKV_ROPE_BF16, bias=bw["qkv_b"], rope_cs=Pk["rope"],
+                          tokens_per_sample=Ntok, model_dim=D, head_dim=self.head_dim, q_scale=q_scale)
+            ops.attention(ws["qkv"], ws["att"], R, Ntok, self.num_heads, self.head_dim)
+            # x1 = y + gate1 * proj(att)   (residual base is the modulated tensor — reference quirk Q1)
+            ops.gemm_bf16(ws["att"], bw["proj_w"], xa, ops.EPI_GATE_RESID_F32, bias=bw["proj_b"], resid=xb,
+                          gate=mod[:, col + 2 * D:], ld_gate=ldm, tokens_per_frame=Pn)
+            col += 3 * D
+            if self.use_mlp:
+                ops.adaln_layernorm(xa, mod, col, col + D, Pn, y_f32=xb, y_bf16=ws["y16"])
+                ops.gemm_bf16(ws["y16"], bw["fc1_w"], ws["h"], ops.EPI_GELU_BF16, bias=bw["fc1_b"])
+                ops.gemm_bf16(ws["h"], bw["fc2_w"], xa, ops.EPI_GATE_RESID_F32, bias=bw["fc2_b"], resid=xb,
+                              gate=mod[:, col + 2 * D:], ld_gate=ldm, tokens_per_frame=Pn)
+                col += 3 * D
+        # --- final layer + unpatchify
+        ops.adaln_layernorm(xa, mod, col, col + D, Pn, y_bf16=ws["y16"])
+        ops.gemm_bf16(ws["y16"], Pk["fin_w"], ws["tok"], ops.EPI_F32, bias=Pk["fin_b"])
+        ops.unpatchify(ws["tok"], ws["out"], RT, C, H, W, p)
+        return ws["out"]

@@ -1,0 +1,150 @@
+// Glue kernels of the DiT3D backbone: noise-level features, embedding combine,
+// patchify (im2col for the patch-embed GEMM), unpatchify, fp32->bf16 cast.
+#include "common.cuh"
+
+namespace dfot {
+
+// embeddings.py:112-153 (flip_sin_to_cos → [cos | sin], max_period 1e4) and :94-109 (Fourier).
+__global__ void noise_features_kernel(const void* __restrict__ levels, int levels_dtype,
+                                      const float* __restrict__ freqs, const float* __restrict__ phases,
+                                      __nv_bfloat16* __restrict__ out, int64_t n, int dim) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * dim) return;
+  const int64_t r = idx / dim;
+  const int c = (int)(idx % dim);
+  const float k = levels_dtype == DFOT_I64 ? (float)reinterpret_cast<const int64_t*>(levels)[r]
+                                           : reinterpret_cast<const float*>(levels)[r];
+  float v;
+  if (freqs != nullptr) {
+    v = cosf(k * freqs[c] + phases[c]) * 1.4142135623730951f;
+  } else {
+    const int half = dim >> 1;
+    const int i = c < half ? c : c - half;
+    const float f = expf(-9.210340371976184f * (float)i / (float)half);
+    v = c < half ? cosf(k * f) : sinf(k * f);
+  }
+  out[idx] = __float2bfloat16_rn(v);
+}
+
+__global__ void silu_sum_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                     const uint8_t* __restrict__ row_mask, int64_t rows_per_mask,
+                                     __nv_bfloat16* __restrict__ out, int64_t n_rows, int64_t D) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_rows * D) return;
+  float v = a[idx];
+  if (b != nullptr) {
+    const int64_t r = idx / D;
+    const bool masked = row_mask != nullptr && row_mask[r / rows_per_mask] != 0;
+    if (!masked) v += b[idx];
+  }
+  out[idx] = __float2bfloat16_rn(silu_f(v));
+}
+
+// out[token, c*p*p + py*p + px] = x[frame, c, gy*p + py, gx*p + px]; token = (frame, gy, gx)
+template <typename TX>
+__global__ void patchify_kernel(const TX* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t frames, int C,
+                                int H, int W, int p) {
+  const int gw = W / p, gh = H / p, kk = C * p * p;
+  const int64_t total = frames * gh * gw * kk;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int k = (int)(idx % kk);
+  const int64_t tok = idx / kk;
+  const int gx = (int)(tok % gw), gy = (int)((tok / gw) % gh);
+  const int64_t fr = tok / ((int64_t)gw * gh);
+  const int px = k % p, py = (k / p) % p, c = k / (p * p);
+  const float v = (float)x[((fr * C + c) * H + gy * p + py) * W + gx * p + px];
+  out[idx] = __float2bfloat16_rn(v);
+}
+
+// x[frame, c, gy*p + py, gx*p + px] = tok[token, (py*p + px)*C + c]
+template <typename TX>
+__global__ void unpatchify_kernel(const float* __restrict__ tok, int64_t ld, TX* __restrict__ x, int64_t frames,
+                                  int C, int H, int W, int p) {
+  const int64_t total = frames * C * H * W;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int w = (int)(idx % W), h = (int)((idx / W) % H), c = (int)((idx / ((int64_t)W * H)) % C);
+  const int64_t fr = idx / ((int64_t)W * H * C);
+  const int gw = W / p, gh = H / p;
+  const int64_t token = (fr * gh + h / p) * gw + w / p;
+  const int col = ((h % p) * p + (w % p)) * C + c;
+  x[idx] = (TX)tok[token * ld + col];
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+static inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)ceil_div(n, threads); }
+
+}  // namespace dfot
+
+using namespace dfot;
+
+extern "C" int dfot_noise_features(const void* levels, int levels_dtype, const float* fourier_freqs,
+                                   const float* fourier_phases, void* out_bf16, int64_t n, int64_t dim,
+                                   void* stream) {
+  DFOT_REQUIRE(levels && out_bf16 && n > 0 && dim > 0 && dim % 2 == 0, DFOT_ERR_INVALID_ARG,
+               "noise_features: bad arguments");
+  DFOT_REQUIRE(levels_dtype == DFOT_I64 || levels_dtype == DFOT_F32, DFOT_ERR_INVALID_ARG,
+               "noise_features: levels must be int64 or f32");
+  DFOT_REQUIRE((fourier_freqs == nullptr) == (fourier_phases == nullptr), DFOT_ERR_INVALID_ARG,
+               "noise_features: freqs and phases go together");
+  noise_features_kernel<<<blocks_for(n * dim, 256), 256, 0, (cudaStream_t)stream>>>(
+      levels, levels_dtype, fourier_freqs, fourier_phases, (__nv_bfloat16*)out_bf16, n, (int)dim);
+  DFOT_CHECK_LAUNCH("noise_features");
+  return DFOT_OK;
+}
+
+extern "C" int dfot_silu_sum_bf16(const float* a, const float* b, const uint8_t* row_mask, int64_t rows_per_mask,
+                                  void* out_bf16, int64_t n_rows, int64_t D, void* stream) {
+  DFOT_REQUIRE(a && out_bf16 && n_rows > 0 && D > 0, DFOT_ERR_INVALID_ARG, "silu_sum_bf16: bad arguments");
+  DFOT_REQUIRE(row_mask == nullptr || rows_per_mask > 0, DFOT_ERR_INVALID_ARG, "silu_sum_bf16: rows_per_mask");
+  silu_sum_bf16_kernel<<<blocks_for(n_rows * D, 256), 256, 0, (cudaStream_t)stream>>>(
+      a, b, row_mask, rows_per_mask, (__nv_bfloat16*)out_bf16, n_rows, D);
+  DFOT_CHECK_LAUNCH("silu_sum_bf16");
+  return DFOT_OK;
+}
+
+extern "C" int dfot_patchify_bf16(const void* x, int x_dtype, void* out_bf16, int64_t frames, int64_t C, int64_t H,
+                                  int64_t W, int64_t p, void* stream) {
+  DFOT_REQUIRE(x && out_bf16 && frames > 0 && C > 0 && p > 0 && H % p == 0 && W % p == 0, DFOT_ERR_INVALID_ARG,
+               "patchify: bad arguments");
+  const int64_t total = frames * C * H * W;
+  if (x_dtype == DFOT_F32)
+    patchify_kernel<float><<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float*)x, (__nv_bfloat16*)out_bf16, frames, (int)C, (int)H, (int)W, (int)p);
+  else if (x_dtype == DFOT_BF16)
+    patchify_kernel<__nv_bfloat16><<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)out_bf16, frames, (int)C, (int)H, (int)W, (int)p);
+  else
+    DFOT_REQUIRE(false, DFOT_ERR_INVALID_ARG, "patchify: x dtype must be f32 or bf16");
+  DFOT_CHECK_LAUNCH("patchify");
+  return DFOT_OK;
+}
+
+extern "C" int dfot_unpatchify(const float* tok, int64_t ld, void* x, int x_dtype, int64_t frames, int64_t C,
+                               int64_t H, int64_t W, int64_t p, void* stream) {
+  DFOT_REQUIRE(tok && x && frames > 0 && C > 0 && p > 0 && H % p == 0 && W % p == 0 && ld >= C * p * p,
+               DFOT_ERR_INVALID_ARG, "unpatchify: bad arguments");
+  const int64_t total = frames * C * H * W;
+  if (x_dtype == DFOT_F32)
+    unpatchify_kernel<float><<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        tok, ld, (float*)x, frames, (int)C, (int)H, (int)W, (int)p);
+  else if (x_dtype == DFOT_BF16)
+    unpatchify_kernel<__nv_bfloat16><<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        tok, ld, (__nv_bfloat16*)x, frames, (int)C, (int)H, (int)W, (int)p);
+  else
+    DFOT_REQUIRE(false, DFOT_ERR_INVALID_ARG, "unpatchify: x dtype must be f32 or bf16");
+  DFOT_CHECK_LAUNCH("unpatchify");
+  return DFOT_OK;
+}
+
+extern "C" int dfot_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream) {
+  DFOT_REQUIRE(in && out_bf16 && n > 0, DFOT_ERR_INVALID_ARG, "cast_bf16: bad arguments");
+  cast_bf16_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out_bf16, n);
+  DFOT_CHECK_LAUNCH("cast_bf16");
+  return DFOT_OK;
+}

@@ -1,0 +1,471 @@
+// K2 — bf16 GEMM on the 5th-gen tensor cores: C[M,N] = epi(A[M,K] · W[N,K]^T + bias).
+//
+// Persistent, warp-specialised kernel (one CTA per SM):
+//   warp 0   : TMA producer  — cp.async.bulk.tensor 2D loads of A (128x64) and W (BNx64) tiles into a
+//              128B-swizzled shared-memory ring, completion on mbarriers
+//   warp 1   : MMA issuer    — one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (128 x BN x 16),
+//              accumulating in tensor memory; tcgen05.commit releases ring slots / publishes accumulators
+//   warps 2-5: epilogue      — tcgen05.ld (32 lanes x 32 columns per warp) → bias / activation / gated
+//              residual / RoPE → 128-bit global stores.  Two TMEM accumulator stages let the epilogue
+//              of tile i overlap the main loop of tile i+1.
+// Both operands are K-major (A row-major activations, W = nn.Linear.weight), so no transposes exist anywhere.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace dfot {
+namespace gemm {
+
+constexpr int BM = 128;       // UMMA M (cta_group::1)
+constexpr int BK = 64;        // one 128-byte swizzle atom of bf16 along K
+constexpr int UMMA_K = 16;    // K per tcgen05.mma for 16-bit inputs
+constexpr int kThreads = 192; // 6 warps
+
+template <int BN> struct Cfg {
+  static constexpr int kStageBytesA = BM * BK * 2;
+  static constexpr int kStageBytesB = BN * BK * 2;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two >= 32)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct Params {
+  int M, N, K;
+  void* C;
+  int64_t ldc;
+  dfot_gemm_epilogue e;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint64_t t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((spin & 1023u) == 1023u) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {
+        printf("dfot_gemm: mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
+               threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile in shared memory, 128-byte swizzle: rows are 128 B apart, 8-row groups 1024 B apart.
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64))
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;             // leading byte offset (unused for swizzled K-major) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;   // stride byte offset between 8-row core-matrix groups
+  d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: D=f32, A=B=bf16, both K-major, M=128, N=BN
+template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ epilogue math on one 32-column chunk
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (&acc)[32], int m, int n0) {
+  // m < M is guaranteed by the caller; columns beyond N are dropped in groups of 8 (N % 8 == 0).
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  if (p.e.bias != nullptr) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (n0 + 4 * g < p.N) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.e.bias + n0) + g);
+        v[4 * g] += b.x; v[4 * g + 1] += b.y; v[4 * g + 2] += b.z; v[4 * g + 3] += b.w;
+      }
+    }
+  }
+  if constexpr (EPI == DFOT_EPI_GELU_BF16) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+  } else if constexpr (EPI == DFOT_EPI_SILU_BF16) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+  } else if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) {
+    const int64_t f = m / p.e.tokens_per_frame;
+    const float4* gate = reinterpret_cast<const float4*>(p.e.gate + f * p.e.ld_gate + n0);
+    const float4* res = reinterpret_cast<const float4*>(p.e.resid + (int64_t)m * p.e.ld_resid + n0);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (n0 + 4 * g < p.N) {
+        const float4 gt = __ldg(gate + g);
+        const float4 r = res[g];
+        v[4 * g] = r.x + gt.x * v[4 * g];
+        v[4 * g + 1] = r.y + gt.y * v[4 * g + 1];
+        v[4 * g + 2] = r.z + gt.z * v[4 * g + 2];
+        v[4 * g + 3] = r.w + gt.w * v[4 * g + 3];
+      }
+    }
+  } else if constexpr (EPI == DFOT_EPI_QKV_ROPE_BF16) {
+    const int D = (int)p.e.model_dim, dh = (int)p.e.head_dim;
+    if (n0 < 2 * D) {
+      const int tok = m % (int)p.e.tokens_per_sample;
+      const float2* cs = reinterpret_cast<const float2*>(p.e.rope_cs) + (int64_t)tok * (dh >> 1);
+      int dd = n0 % dh;  // column inside the head (even)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int n = n0 + 2 * i;
+        if (n < 2 * D) {
+          const float2 c = __ldg(cs + (dd >> 1));
+          const float x0 = v[2 * i], x1 = v[2 * i + 1];
+          float r0 = x0 * c.x - x1 * c.y;
+          float r1 = x1 * c.x + x0 * c.y;
+          if (n < D) { r0 *= p.e.q_scale; r1 *= p.e.q_scale; }
+          v[2 * i] = r0;
+          v[2 * i + 1] = r1;
+        }
+        dd += 2;
+        if (dd >= dh) dd -= dh;
+      }
+    }
+  }
+  if constexpr (EPI == DFOT_EPI_F32 || EPI == DFOT_EPI_GATE_RESID_F32) {
+    float* out = reinterpret_cast<float*>(p.C) + (int64_t)m * p.ldc + n0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      if (n0 + 4 * g < p.N)
+        *reinterpret_cast<float4*>(out + 4 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+  } else {
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)m * p.ldc + n0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (n0 + 8 * g < p.N)
+        *reinterpret_cast<uint4*>(out + 8 * g) =
+            make_uint4(pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
+                       pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
+  }
+}
+
+// ------------------------------------------------------------------ the kernel
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                         const Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms must start on 1024-byte boundaries
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + C::kStages * C::kStageBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C::kStages + s); };
+  auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * C::kStages + a); };
+  auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * C::kStages + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * C::kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tma_a);
+    prefetch_tmap(&tma_b);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), C::kStageBytes);
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
+          tma_load_2d(sa, &tma_a, full_bar(stage), kb * BK, m_blk * BM);
+          tma_load_2d(sa + C::kStageBytesA, &tma_b, full_bar(stage), kb * BK, n_blk * BN);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);               // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
+          const uint64_t a_desc = make_smem_desc_sw128(sa);
+          const uint64_t b_desc = make_smem_desc_sw128(sa + C::kStageBytesA);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));                   // ring slot reusable once these MMAs retire
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tmem_full_bar(acc));                   // accumulator complete → epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tc_fence_after();
+      const int m = m_blk * BM + q * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_blk * BN + c * 32;
+        if (n0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_x32(t_row + (uint32_t)(c * 32), r);
+        if (m < p.M) epilogue_chunk<EPI>(p, r, m, n0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// 2D bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64], 128B swizzle
+static int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  DFOT_REQUIRE(enc != nullptr, DFOT_ERR_DRIVER, "gemm: cuTensorMapEncodeTiled unavailable from the driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DFOT_REQUIRE(r == CUDA_SUCCESS, DFOT_ERR_DRIVER, "gemm: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return DFOT_OK;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int EPI>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t s) {
+  using C = Cfg<BN>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    DFOT_REQUIRE(e == cudaSuccess, DFOT_ERR_CUDA, "gemm: cannot reserve %d B of shared memory: %s", C::kSmemBytes,
+                 cudaGetErrorString(e));
+    configured = true;
+  }
+  const int tiles = (int)(ceil_div(p.M, BM) * ceil_div(p.N, BN));
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, kThreads, C::kSmemBytes, s>>>(ta, tb, p);
+  DFOT_CHECK_LAUNCH("gemm_bf16_tcgen05");
+  return DFOT_OK;
+}
+
+template <int BN>
+static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t s) {
+  switch (epi) {
+    case DFOT_EPI_F32: return launch<BN, DFOT_EPI_F32>(ta, tb, p, s);
+    case DFOT_EPI_BF16: return launch<BN, DFOT_EPI_BF16>(ta, tb, p, s);
+    case DFOT_EPI_GELU_BF16: return launch<BN, DFOT_EPI_GELU_BF16>(ta, tb, p, s);
+    case DFOT_EPI_SILU_BF16: return launch<BN, DFOT_EPI_SILU_BF16>(ta, tb, p, s);
+    case DFOT_EPI_GATE_RESID_F32: return launch<BN, DFOT_EPI_GATE_RESID_F32>(ta, tb, p, s);
+    case DFOT_EPI_QKV_ROPE_BF16: return launch<BN, DFOT_EPI_QKV_ROPE_BF16>(ta, tb, p, s);
+  }
+  set_error("gemm: unknown epilogue %d", epi);
+  return DFOT_ERR_INVALID_ARG;
+}
+
+}  // namespace gemm
+}  // namespace dfot
+
+extern "C" int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* Cout, int64_t ldc,
+                              int64_t M, int64_t N, int64_t K, int epilogue, const dfot_gemm_epilogue* epi,
+                              void* stream) {
+  using namespace dfot;
+  using namespace dfot::gemm;
+  DFOT_REQUIRE(A && W && Cout && epi, DFOT_ERR_INVALID_ARG, "gemm: null pointer");
+  DFOT_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31),
+               DFOT_ERR_INVALID_ARG, "gemm: bad sizes M=%lld N=%lld K=%lld", (long long)M, (long long)N,
+               (long long)K);
+  DFOT_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K, DFOT_ERR_UNSUPPORTED,
+               "gemm: K, lda, ldw must be multiples of 8 (16-byte TMA strides); got K=%lld lda=%lld ldw=%lld",
+               (long long)K, (long long)lda, (long long)ldw);
+  DFOT_REQUIRE(N % 8 == 0 && ldc % 8 == 0 && ldc >= N, DFOT_ERR_UNSUPPORTED,
+               "gemm: N and ldc must be multiples of 8; got N=%lld ldc=%lld", (long long)N, (long long)ldc);
+  DFOT_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0) && ((uintptr_t)Cout % 16 == 0),
+               DFOT_ERR_UNSUPPORTED, "gemm: A, W, C must be 16-byte aligned");
+  if (epilogue == DFOT_EPI_GATE_RESID_F32)
+    DFOT_REQUIRE(epi->resid && epi->gate && epi->tokens_per_frame > 0 && epi->ld_resid % 4 == 0 &&
+                     epi->ld_gate % 4 == 0,
+                 DFOT_ERR_INVALID_ARG, "gemm: GATE_RESID needs resid, gate, tokens_per_frame and 16-byte rows");
+  if (epilogue == DFOT_EPI_QKV_ROPE_BF16)
+    DFOT_REQUIRE(epi->rope_cs && epi->tokens_per_sample > 0 && epi->head_dim > 0 && epi->head_dim % 2 == 0 &&
+                     epi->model_dim > 0 && epi->model_dim % epi->head_dim == 0 && N == 3 * epi->model_dim,
+                 DFOT_ERR_INVALID_ARG, "gemm: QKV_ROPE needs rope table, tokens_per_sample, head_dim | model_dim, N=3D");
+  Params p;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.C = Cout; p.ldc = ldc; p.e = *epi;
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, A, M, K, lda, BM);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  // widest tile whose last column block is not mostly padding
+  if (N > 128) {
+    rc = make_tmap(&tb, W, N, K, ldw, 256);
+    return rc ? rc : dispatch_epi<256>(epilogue, ta, tb, p, s);
+  } else if (N > 64) {
+    rc = make_tmap(&tb, W, N, K, ldw, 128);
+    return rc ? rc : dispatch_epi<128>(epilogue, ta, tb, p, s);
+  }
+  rc = make_tmap(&tb, W, N, K, ldw, 64);
+  return rc ? rc : dispatch_epi<64>(epilogue, ta, tb, p, s);
+}

@@ -1,0 +1,133 @@
+// K4 — fused per-frame sampler step + history-guidance combine + next-step prepare.
+// One pass over HBM per sampling step; see include/dfot_b200.h for the contract.
+// HBM-bound: algorithmic bytes per latent element = 4 (x_t) + 4 (x_{t+1}) + nfe*s_out + nfe*s_in.
+#include "common.cuh"
+
+namespace dfot {
+
+constexpr int kSamplerThreads = 256;
+constexpr int kMaxNfe = 16;
+
+template <typename T> struct Vec4;  // 4 elements of T
+template <> struct Vec4<float> {
+  static __device__ __forceinline__ float4 load(const float* p) {
+    uint4 u = ld_stream_u4(p);
+    return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+  }
+  static __device__ __forceinline__ void store(float* p, float4 v) {
+    st_stream_u4(p, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
+  }
+};
+template <> struct Vec4<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 load(const __nv_bfloat16* p) {
+    uint2 u = ld_stream_u2(p);
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, float4 v) {
+    st_stream_u2(p, make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w)));
+  }
+};
+
+__device__ __forceinline__ float4 clamp4(float4 v, float c) {
+  return make_float4(fminf(fmaxf(v.x, -c), c), fminf(fmaxf(v.y, -c), c), fminf(fmaxf(v.z, -c), c),
+                     fminf(fmaxf(v.w, -c), c));
+}
+
+// grid = (chunks, T, B); each thread owns 4 consecutive elements per iteration.
+template <typename TOut, typename TIn>
+__global__ void __launch_bounds__(kSamplerThreads)
+sampler_step_hg_kernel(float* __restrict__ x, const TOut* __restrict__ model_out, TIn* __restrict__ model_in_next,
+                       const dfot_frame_update* __restrict__ upd, const dfot_frame_prepare* __restrict__ prep,
+                       const float* __restrict__ noise_ddim, const float* __restrict__ noise_hist,
+                       const float* __restrict__ noise_excl, int nfe, int T, int64_t F) {
+  const int t = blockIdx.y, b = blockIdx.z;
+  __shared__ dfot_frame_update s_upd[kMaxNfe];
+  __shared__ dfot_frame_prepare s_prep[kMaxNfe];
+  if (threadIdx.x < nfe) {
+    const int64_t r = (int64_t)b * nfe + threadIdx.x;
+    if (upd) s_upd[threadIdx.x] = upd[r * T + t];
+    if (prep) s_prep[threadIdx.x] = prep[r * T + t];
+  }
+  __syncthreads();
+  const bool do_update = (model_out != nullptr) && (upd != nullptr) && s_upd[0].generate != 0;
+  const int64_t frame_x = ((int64_t)b * T + t) * F;
+  for (int64_t e = ((int64_t)blockIdx.x * kSamplerThreads + threadIdx.x) * 4; e < F;
+       e += (int64_t)gridDim.x * kSamplerThreads * 4) {
+    // x is updated in place: plain (coherent) load, not the .nc streaming path
+    float4 xv = *reinterpret_cast<const float4*>(x + frame_x + e);
+    if (do_update) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < nfe; ++j) {
+        const dfot_frame_update u = s_upd[j];
+        if (u.w == 0.f) continue;
+        const int64_t off = (((int64_t)b * nfe + j) * T + t) * F + e;
+        float4 o = Vec4<TOut>::load(model_out + off);
+        if (u.clip > 0.f) o = clamp4(o, u.clip);
+        float4 v = make_float4(u.a * xv.x + u.b * o.x, u.a * xv.y + u.b * o.y, u.a * xv.z + u.b * o.z,
+                               u.a * xv.w + u.b * o.w);
+        if (u.sigma != 0.f && noise_ddim != nullptr) {
+          float4 n = Vec4<float>::load(noise_ddim + off);
+          v.x += u.sigma * n.x; v.y += u.sigma * n.y; v.z += u.sigma * n.z; v.w += u.sigma * n.w;
+        }
+        acc.x += u.w * v.x; acc.y += u.w * v.y; acc.z += u.w * v.z; acc.w += u.w * v.w;
+      }
+      xv = acc;
+      Vec4<float>::store(x + frame_x + e, xv);
+    }
+    if (model_in_next != nullptr) {
+      for (int j = 0; j < nfe; ++j) {
+        const dfot_frame_prepare p = s_prep[j];
+        const int64_t off = (((int64_t)b * nfe + j) * T + t) * F + e;
+        float4 v = xv;
+        if (p.mode == 1) {
+          float4 n = Vec4<float>::load(noise_hist + ((int64_t)p.noise_row * T + t) * F + e);
+          v = make_float4(p.qa * xv.x + p.qb * n.x, p.qa * xv.y + p.qb * n.y, p.qa * xv.z + p.qb * n.z,
+                          p.qa * xv.w + p.qb * n.w);
+        } else if (p.mode == 2) {
+          v = Vec4<float>::load(noise_excl + off);
+        }
+        Vec4<TIn>::store(model_in_next + off, v);
+      }
+    }
+  }
+}
+
+}  // namespace dfot
+
+extern "C" int dfot_sampler_step_hg(float* x, const void* model_out, int model_out_dtype, void* model_in_next,
+                                    int model_in_dtype, const dfot_frame_update* upd,
+                                    const dfot_frame_prepare* prep, const float* noise_ddim,
+                                    const float* noise_hist, const float* noise_excl, int64_t B, int64_t nfe,
+                                    int64_t T, int64_t F, void* stream) {
+  using namespace dfot;
+  DFOT_REQUIRE(x != nullptr && B > 0 && T > 0 && F > 0, DFOT_ERR_INVALID_ARG, "sampler_step_hg: bad x/B/T/F");
+  DFOT_REQUIRE(nfe >= 1 && nfe <= kMaxNfe, DFOT_ERR_UNSUPPORTED, "sampler_step_hg: nfe=%lld not in [1,%d]",
+               (long long)nfe, kMaxNfe);
+  DFOT_REQUIRE(F % 4 == 0, DFOT_ERR_UNSUPPORTED, "sampler_step_hg: frame size %lld must be a multiple of 4",
+               (long long)F);
+  DFOT_REQUIRE(T <= 65535 && B <= 65535, DFOT_ERR_UNSUPPORTED, "sampler_step_hg: B/T exceed grid limits");
+  DFOT_REQUIRE(model_out == nullptr || upd != nullptr, DFOT_ERR_INVALID_ARG, "sampler_step_hg: upd is required");
+  DFOT_REQUIRE(model_in_next == nullptr || prep != nullptr, DFOT_ERR_INVALID_ARG,
+               "sampler_step_hg: prep is required");
+  int64_t chunks = ceil_div(F, (int64_t)kSamplerThreads * 4);
+  // keep >= 2 waves of 148 SMs when the problem is large enough, otherwise one block per 1024 elements
+  const int64_t frames = B * T;
+  const int64_t cap = ceil_div(148 * 8, frames);
+  if (chunks > cap) chunks = cap < 1 ? 1 : cap;
+  dim3 grid((unsigned)chunks, (unsigned)T, (unsigned)B), block(kSamplerThreads);
+  cudaStream_t s = (cudaStream_t)stream;
+#define LAUNCH(TO, TI)                                                                                       \
+  sampler_step_hg_kernel<TO, TI><<<grid, block, 0, s>>>(x, (const TO*)model_out, (TI*)model_in_next, upd, prep, \
+                                                        noise_ddim, noise_hist, noise_excl, (int)nfe, (int)T, F)
+  const bool ob = model_out_dtype == DFOT_BF16, ib = model_in_dtype == DFOT_BF16;
+  DFOT_REQUIRE((model_out_dtype == DFOT_F32 || ob) && (model_in_dtype == DFOT_F32 || ib), DFOT_ERR_INVALID_ARG,
+               "sampler_step_hg: dtype tags must be DFOT_F32 or DFOT_BF16");
+  if (ob && ib) LAUNCH(__nv_bfloat16, __nv_bfloat16);
+  else if (ob) LAUNCH(__nv_bfloat16, float);
+  else if (ib) LAUNCH(float, __nv_bfloat16);
+  else LAUNCH(float, float);
+#undef LAUNCH
+  DFOT_CHECK_LAUNCH("sampler_step_hg");
+  return DFOT_OK;
+}

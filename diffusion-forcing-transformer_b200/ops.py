@@ -1,0 +1,165 @@
+"""Tensor-level wrappers over the C ABI (torch is used for device memory and streams only).
+
+Every wrapper checks device / dtype / contiguity, launches on torch's current CUDA stream and
+raises RuntimeError with the library's message on failure.  No op has a CPU implementation.
+"""
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _abi
+from ._abi import (BF16, EPI_BF16, EPI_F32, EPI_GATE_RESID_F32, EPI_GELU_BF16, EPI_QKV_ROPE_BF16,  # noqa: F401
+                   EPI_SILU_BF16, F32, I64)
+
+_DTYPE_TAG = {torch.float32: F32, torch.bfloat16: BF16, torch.int64: I64}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"dfot_b200: `{name}` must be a CUDA tensor (no CPU fallback exists)")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"dfot_b200: `{name}` must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"dfot_b200: `{name}` must be contiguous")
+
+
+def sampler_step_hg(x, model_out, model_in_next, upd, prep, noise_ddim, noise_hist, noise_excl, B, nfe, T):
+    """K4. x [B,T,...] f32 in place; model_out / model_in_next [B*nfe,T,...] f32|bf16 or None;
+    upd / prep: uint8 CUDA tensors holding packed dfot_frame_update / dfot_frame_prepare records."""
+    _need(x, torch.float32, "x")
+    F = x[0, 0].numel()
+    for t, n in ((model_out, "model_out"), (model_in_next, "model_in_next")):
+        if t is not None:
+            _need(t, None, n)
+            if t.dtype not in (torch.float32, torch.bfloat16) or t.numel() != B * nfe * T * F:
+                raise RuntimeError(f"dfot_b200: `{n}` has wrong dtype/size")
+    for t, n in ((noise_ddim, "noise_ddim"), (noise_hist, "noise_hist"), (noise_excl, "noise_excl")):
+        if t is not None:
+            _need(t, torch.float32, n)
+    for t, n, sz in ((upd, "upd", 24), (prep, "prep", 16)):
+        if t is not None:
+            _need(t, torch.uint8, n)
+            if t.numel() != B * nfe * T * sz:
+                raise RuntimeError(f"dfot_b200: `{n}` table has {t.numel()} bytes, expected {B * nfe * T * sz}")
+    rc = _abi.lib().dfot_sampler_step_hg(
+        x.data_ptr(), _ptr(model_out), _DTYPE_TAG[model_out.dtype] if model_out is not None else F32,
+        _ptr(model_in_next), _DTYPE_TAG[model_in_next.dtype] if model_in_next is not None else F32,
+        _ptr(upd), _ptr(prep), _ptr(noise_ddim), _ptr(noise_hist), _ptr(noise_excl), B, nfe, T, F, _stream())
+    _abi.check(rc, "sampler_step_hg")
+
+
+def adaln_layernorm(x, mod, shift_col, scale_col, tokens_per_frame, y_f32=None, y_bf16=None, eps=1e-6):
+    """K1. x [M,D] f32, mod [frames, mod_ld] f32."""
+    _need(x, torch.float32, "x")
+    _need(mod, torch.float32, "mod")
+    M, D = x.shape
+    if y_f32 is not None:
+        _need(y_f32, torch.float32, "y_f32")
+    if y_bf16 is not None:
+        _need(y_bf16, torch.bfloat16, "y_bf16")
+    rc = _abi.lib().dfot_adaln_layernorm(x.data_ptr(), mod.data_ptr(), mod.shape[-1], shift_col, scale_col,
+                                         _ptr(y_f32), _ptr(y_bf16), M, D, tokens_per_frame, eps, _stream())
+    _abi.check(rc, "adaln_layernorm")
+
+
+def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, gate=None, ld_gate=0, tokens_per_frame=1, rope_cs=None,
+              tokens_per_sample=1, model_dim=0, head_dim=0, q_scale=1.0, M=None):
+    """K2. a [M,K] bf16 (row stride may exceed K), w [N,K] bf16, out [M,N] f32|bf16 per epilogue."""
+    _need(w, torch.bfloat16, "w")
+    if not a.is_cuda or a.dtype != torch.bfloat16 or a.stride(-1) != 1:
+        raise RuntimeError("dfot_b200: `a` must be a CUDA bf16 matrix with unit inner stride")
+    if not out.is_cuda or out.stride(-1) != 1:
+        raise RuntimeError("dfot_b200: `out` must be a CUDA matrix with unit inner stride")
+    want = torch.float32 if epilogue in (EPI_F32, EPI_GATE_RESID_F32) else torch.bfloat16
+    if out.dtype != want:
+        raise RuntimeError(f"dfot_b200: epilogue {epilogue} writes {want}, got {out.dtype}")
+    M = a.shape[0] if M is None else M
+    N, K = w.shape
+    if a.shape[1] != K or out.shape[0] < M or out.shape[1] != N:
+        raise RuntimeError(f"dfot_b200: gemm shape mismatch a{tuple(a.shape)} w{tuple(w.shape)} out{tuple(out.shape)}")
+    e = _abi.GemmEpilogue()
+    e.bias = _ptr(bias)
+    if bias is not None:
+        _need(bias, torch.float32, "bias")
+    if resid is not None:
+        _need(resid, torch.float32, "resid")
+        e.resid, e.ld_resid = resid.data_ptr(), resid.stride(0)
+    if gate is not None:
+        if gate.dtype != torch.float32 or not gate.is_cuda:
+            raise RuntimeError("dfot_b200: `gate` must be CUDA f32")
+        e.gate, e.ld_gate = gate.data_ptr(), ld_gate
+    e.tokens_per_frame = tokens_per_frame
+    if rope_cs is not None:
+        _need(rope_cs, torch.float32, "rope_cs")
+        e.rope_cs = rope_cs.data_ptr()
+    e.tokens_per_sample, e.model_dim, e.head_dim, e.q_scale = tokens_per_sample, model_dim, head_dim, q_scale
+    rc = _abi.lib().dfot_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
+                                   out.stride(0), M, N, K, epilogue, ctypes.byref(e), _stream())
+    _abi.check(rc, "gemm_bf16")
+
+
+def attention(qkv, out, R, Ntok, heads, head_dim):
+    """K3. qkv [R*Ntok, 3*D] bf16 (q rotated+scaled, k rotated), out [R*Ntok, D] bf16."""
+    _need(qkv, torch.bfloat16, "qkv")
+    _need(out, torch.bfloat16, "out")
+    rc = _abi.lib().dfot_attention(qkv.data_ptr(), out.data_ptr(), R, Ntok, heads, head_dim, _stream())
+    _abi.check(rc, "attention")
+
+
+def noise_features(levels, out, fourier_freqs=None, fourier_phases=None):
+    _need(levels, None, "levels")
+    _need(out, torch.bfloat16, "out")
+    if levels.dtype not in (torch.int64, torch.float32):
+        raise RuntimeError("dfot_b200: noise levels must be int64 or float32")
+    n, dim = levels.numel(), out.shape[-1]
+    rc = _abi.lib().dfot_noise_features(levels.data_ptr(), _DTYPE_TAG[levels.dtype], _ptr(fourier_freqs),
+                                        _ptr(fourier_phases), out.data_ptr(), n, dim, _stream())
+    _abi.check(rc, "noise_features")
+
+
+def silu_sum_bf16(a, b, row_mask, rows_per_mask, out):
+    _need(a, torch.float32, "a")
+    _need(out, torch.bfloat16, "out")
+    if b is not None:
+        _need(b, torch.float32, "b")
+    if row_mask is not None:
+        _need(row_mask, torch.uint8, "row_mask")
+    n_rows, D = a.shape
+    rc = _abi.lib().dfot_silu_sum_bf16(a.data_ptr(), _ptr(b), _ptr(row_mask), rows_per_mask, out.data_ptr(), n_rows,
+                                       D, _stream())
+    _abi.check(rc, "silu_sum_bf16")
+
+
+def patchify_bf16(x, out, frames, C, H, W, p):
+    _need(x, None, "x")
+    _need(out, torch.bfloat16, "out")
+    rc = _abi.lib().dfot_patchify_bf16(x.data_ptr(), _DTYPE_TAG[x.dtype], out.data_ptr(), frames, C, H, W, p,
+                                       _stream())
+    _abi.check(rc, "patchify_bf16")
+
+
+def unpatchify(tok, x, frames, C, H, W, p):
+    _need(tok, torch.float32, "tok")
+    _need(x, None, "x")
+    rc = _abi.lib().dfot_unpatchify(tok.data_ptr(), tok.stride(0), x.data_ptr(), _DTYPE_TAG[x.dtype], frames, C, H, W,
+                                    p, _stream())
+    _abi.check(rc, "unpatchify")
+
+
+def cast_bf16(src, out=None):
+    _need(src, torch.float32, "src")
+    if out is None:
+        out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    _need(out, torch.bfloat16, "out")
+    rc = _abi.lib().dfot_cast_bf16(src.data_ptr(), out.data_ptr(), src.numel(), _stream())
+    _abi.check(rc, "cast_bf16")
+    return out

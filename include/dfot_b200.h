@@ -1,0 +1,171 @@
+/*
+ * dfot_b200.h — C ABI of the B200-native DFoT denoising-sampling kernels (sm_100a).
+ *
+ * The reference (ktncktnc/diffusion-forcing-transformer) is pure PyTorch and has no FFI;
+ * the boundary it exposes for this path is its Python module API.  These
+ * entry points sit *beneath* that API: each one replaces a group of ATen calls made by the
+ * reference functions cited next to it.  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a CUDA device pointer unless noted;
+ *   - `stream` is a cudaStream_t passed as void*; kernels are launched on it, the call never
+ *     synchronises, never allocates device memory and never throws;
+ *   - return value: 0 = success, negative = error (DFOT_ERR_*); dfot_last_error() returns a
+ *     thread-local, human-readable message for the last failing call;
+ *   - bf16 tensors are raw uint16 storage; "f32" is IEEE float.
+ */
+#ifndef DFOT_B200_H_
+#define DFOT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFOT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DFOT_API __attribute__((visibility("default")))
+#else
+#define DFOT_API
+#endif
+
+#define DFOT_OK 0
+#define DFOT_ERR_INVALID_ARG (-1)
+#define DFOT_ERR_UNSUPPORTED (-2)
+#define DFOT_ERR_CUDA (-3)
+#define DFOT_ERR_DRIVER (-4)
+
+/* dtype tags for arguments that accept either storage type */
+#define DFOT_F32 0
+#define DFOT_BF16 1
+#define DFOT_I64 2
+
+DFOT_API int dfot_abi_version(void);
+DFOT_API const char* dfot_last_error(void);
+/* number of kernel launches issued through this library since load (all threads) */
+DFOT_API int64_t dfot_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K4 — fused per-frame sampler step + history-guidance combine (+ next-step prepare).
+ * Replaces, per sampling step, the ATen elementwise chain of
+ *   algorithms/dfot/dfot_video.py:675-752            (mask update, clone, revert `where`)
+ *   algorithms/dfot/history_guidance.py:446-568, 929-982 (prepare / compose)
+ *   algorithms/dfot/diffusion/discrete_diffusion.py:242-250 (q_sample), 454-538 (DDIM update)
+ * in one pass over HBM.  All per-(row, frame) integers/scalars are precomputed on the host
+ * for the whole window (they depend only on the scheduling matrix and the context mask).
+ *
+ * Layout: a "frame" is F = C*H*W contiguous values.  x: [B, T, F] f32 state (in/out).
+ * Branch rows r = (b, j), j in [0, nfe) ordered as the reference's "(b h g)".
+ *   model_out     [B*nfe, T, F]  backbone output of THIS step (NULL => prepare-only launch)
+ *   model_in_next [B*nfe, T, F]  backbone input for the NEXT step (NULL => do not emit)
+ *   upd  [B*nfe, T] dfot_frame_update  : DDIM/compose coefficients of this step
+ *   prep [B*nfe, T] dfot_frame_prepare : how to build the next step's input per branch frame
+ *   noise_ddim [B*nfe, T, F] f32 or NULL (only read where upd.sigma != 0)
+ *   noise_hist [B*n_hist, T, F] f32 or NULL; prep.noise_row selects the row
+ *   noise_excl [B*nfe, T, F] f32 or NULL
+ * For every frame with upd(b,0,t).generate != 0:
+ *     x' = sum_j w_j * ( a_j * x + b_j * g(out_j) + sigma_j * n_j ),  g = clamp(+-clip) or identity
+ * else x' = x.  Then, per branch frame: mode 0: in = x'; 1: in = qa*x' + qb*noise_hist; 2: in = noise_excl.
+ */
+typedef struct {
+  float a;        /* coefficient of x_t            */
+  float b;        /* coefficient of g(model_out)   */
+  float sigma;    /* coefficient of DDIM noise     */
+  float w;        /* compose weight (0 drops the branch for this frame) */
+  float clip;     /* >0: clamp model_out to +-clip before use (pred_noise) */
+  int32_t generate; /* 1: frame is being generated (context_mask == 0): x is overwritten */
+} dfot_frame_update;
+
+typedef struct {
+  int32_t mode;      /* 0 copy, 1 q_sample re-noise, 2 pure noise (excluded gen token) */
+  int32_t noise_row; /* row of noise_hist to read in mode 1 */
+  float qa;          /* sqrt(alpha_bar[level])     */
+  float qb;          /* sqrt(1 - alpha_bar[level]) */
+} dfot_frame_prepare;
+
+DFOT_API int dfot_sampler_step_hg(float* x, const void* model_out, int model_out_dtype, void* model_in_next,
+                         int model_in_dtype, const dfot_frame_update* upd, const dfot_frame_prepare* prep,
+                         const float* noise_ddim, const float* noise_hist, const float* noise_excl,
+                         int64_t B, int64_t nfe, int64_t T, int64_t F, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1 — fused AdaLN modulate + LayerNorm with per-frame gather.
+ * Replaces algorithms/dfot/backbones/dit/dit_blocks.py:15-16, 378-437 (AdaLayerNorm[Zero]):
+ *   y[m, :] = LN_eps(x[m, :]) * (1 + scale[f(m), :]) + shift[f(m), :],   f(m) = m / tokens_per_frame
+ * shift/scale are read from the per-frame modulation matrix mod[f, shift_col + d] / mod[f, scale_col + d]
+ * (the reference recomputes them per token; only the frame varies).  Writes y as f32 (residual
+ * base, may be NULL) and/or bf16 (GEMM operand, may be NULL).  D % 8 == 0, D <= 8192.
+ */
+DFOT_API int dfot_adaln_layernorm(const float* x, const float* mod, int64_t mod_ld, int64_t shift_col, int64_t scale_col,
+                         float* y_f32, void* y_bf16, int64_t M, int64_t D, int64_t tokens_per_frame, float eps,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2 — tcgen05/TMEM bf16 GEMM fed by TMA:  C[M,N] = epilogue(A[M,K] · W[N,K]^T + bias[N]).
+ * Replaces every nn.Linear on the path (dit_blocks.py:72,76,387,417,525; timm Mlp; the
+ * patch-embed conv dit3d.py:49-55; diffusers TimestepEmbedding): A row-major bf16 (lda elements),
+ * W = nn.Linear.weight row-major bf16 (ldw elements), fp32 accumulation in tensor memory.
+ * K % 8 == 0, lda % 8 == 0, ldw % 8 == 0 (16-byte TMA strides), N % 8 == 0.
+ */
+#define DFOT_EPI_F32 0            /* out f32  = acc + bias                                   */
+#define DFOT_EPI_BF16 1           /* out bf16 = acc + bias                                   */
+#define DFOT_EPI_GELU_BF16 2      /* out bf16 = gelu_tanh(acc + bias)      (timm Mlp fc1)     */
+#define DFOT_EPI_SILU_BF16 3      /* out bf16 = silu(acc + bias)           (TimestepEmbedding) */
+#define DFOT_EPI_GATE_RESID_F32 4 /* out f32  = resid + gate[f(m), n] * (acc + bias)          */
+#define DFOT_EPI_QKV_ROPE_BF16 5  /* out bf16 = rope3d(acc + bias) on q,k columns; q pre-scaled */
+
+typedef struct {
+  const float* bias;          /* [N] or NULL */
+  /* GATE_RESID */
+  const float* resid;         /* [M, ld_resid] f32 */
+  int64_t ld_resid;
+  const float* gate;          /* gate[f * ld_gate + n] */
+  int64_t ld_gate;
+  int64_t tokens_per_frame;   /* f(m) = m / tokens_per_frame */
+  /* QKV_ROPE: columns [0, D) = q, [D, 2D) = k, [2D, 3D) = v; head h owns columns h*head_dim.. */
+  const float* rope_cs;       /* [tokens_per_sample, head_dim/2, 2] = (cos, sin) of the pair angle */
+  int64_t tokens_per_sample;  /* token index = m % tokens_per_sample */
+  int64_t model_dim;          /* D */
+  int64_t head_dim;
+  float q_scale;              /* multiplies q after rotation (softmax scale * log2 e) */
+} dfot_gemm_epilogue;
+
+DFOT_API int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int64_t M,
+                   int64_t N, int64_t K, int epilogue, const dfot_gemm_epilogue* epi, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3 — attention over space-time latent tokens (non-causal, no mask: context frames are
+ * expressed through per-frame noise levels, never an attention mask — SURVEY.md §8a Q9).
+ * Replaces dit_blocks.py:21-44, 100-123.  qkv: [R*Ntok, 3*D] bf16 as written by the
+ * QKV_ROPE epilogue (q already rotated and multiplied by scale*log2e, k rotated);
+ * out: [R*Ntok, D] bf16 (heads concatenated, i.e. "transpose(1,2).reshape(B,N,C)").
+ * Online softmax in fp32 (exp2), row max / sum via warp shuffles.  head_dim in {64, 72, 128}.
+ */
+DFOT_API int dfot_attention(const void* qkv, void* out, int64_t R, int64_t Ntok, int64_t heads, int64_t head_dim,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Small glue kernels of the DiT3D backbone (dit3d.py:153-192, embeddings.py:67-153).
+ */
+/* noise-level features: sinusoidal [cos|sin] (levels int64 or f32) or Fourier cos(k*f+phase)*sqrt2 → bf16 [n, dim] */
+DFOT_API int dfot_noise_features(const void* levels, int levels_dtype, const float* fourier_freqs,
+                        const float* fourier_phases, void* out_bf16, int64_t n, int64_t dim, void* stream);
+/* c_act = silu(a + (row_mask[r] ? 0 : b)) → bf16; a,b f32 [n_rows, D]; b / row_mask may be NULL; rows_per_mask = T */
+DFOT_API int dfot_silu_sum_bf16(const float* a, const float* b, const uint8_t* row_mask, int64_t rows_per_mask,
+                       void* out_bf16, int64_t n_rows, int64_t D, void* stream);
+/* patchify: x [R*T, C, H, W] (f32 or bf16) → tokens [R*T*(H/p)*(W/p), C*p*p] bf16 in conv-weight order (c, py, px) */
+DFOT_API int dfot_patchify_bf16(const void* x, int x_dtype, void* out_bf16, int64_t frames, int64_t C, int64_t H, int64_t W,
+                       int64_t p, void* stream);
+/* unpatchify: tokens [frames*(H/p)*(W/p), ld] f32 with columns (py, px, c) → x [frames, C, H, W] (f32 or bf16) */
+DFOT_API int dfot_unpatchify(const float* tok, int64_t ld, void* x, int x_dtype, int64_t frames, int64_t C, int64_t H,
+                    int64_t W, int64_t p, void* stream);
+/* elementwise f32 → bf16 (weights repack / activations), n % 8 == 0 not required */
+DFOT_API int dfot_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFOT_B200_H_ */

@@ -1,0 +1,146 @@
+"""Host-side logic of the product (no GPU): scheduling matrices, HG branch tables, interpolation plans,
+diffusion tables, state-dict keys — bit-exact against the reference-generated goldens — and the window
+planner driven end-to-end on CPU with the K4 *contract emulation* + the oracle backbone."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from dfot_b200 import ops
+from dfot_b200.algorithms.dfot import DFoTVideo
+from dfot_b200.algorithms.dfot.dfot_video import interpolation_plan
+from dfot_b200.algorithms.dfot.history_guidance import HistoryGuidance
+from helpers import GOLDEN, NoiseBank, build_oracle, case_names, load_case
+from oracle.cases import algorithm_cfg, continuous_overrides
+import k4_emulation
+
+with open(os.path.join(GOLDEN, "integers.json")) as f:
+    INTS = json.load(f)
+
+
+def _tiny(**over):
+    base = {"backbone.hidden_size": 64, "backbone.depth": 1, "backbone.num_heads": 1, "x_shape": [4, 8, 8]}
+    base.update(over)
+    return algorithm_cfg(**base)
+
+
+def test_scheduling_matrices_bit_exact():
+    for rec in INTS["scheduling_matrices"]:
+        algo = DFoTVideo(_tiny(**{"scheduling_matrix": rec["kind"], "diffusion.sampling_timesteps": rec["steps"],
+                                  "max_frames": rec["horizon"] + rec["padding"]}))
+        m = algo._generate_scheduling_matrix(rec["horizon"], rec["padding"])
+        assert m.dtype == torch.int64 and m.tolist() == rec["matrix"], rec["kind"]
+
+
+def test_ddim_levels_bit_exact():
+    for rec in INTS["ddim_levels"]:
+        algo = DFoTVideo(_tiny(**{"diffusion.sampling_timesteps": rec["steps"]}))
+        lv = algo.diffusion_model.ddim_idx_to_noise_level(torch.arange(rec["steps"] + 1))
+        assert lv.tolist() == rec["levels"]
+
+
+def test_hg_branch_tables_bit_exact():
+    for rec in INTS["hg_branch_tables"]:
+        hgd = HistoryGuidance.from_config(dict(rec["scheme"], visualize=False), timesteps=1000)
+        mask = np.array(rec["mask"])
+        if "error" in rec:
+            with pytest.raises((AssertionError, IndexError)):
+                hgd.branch_table(mask)
+            continue
+        assert hgd.is_simple == (rec["manager"] == "SimpleHistoryGuidanceManager")
+        if hgd.is_simple:
+            continue
+        tab = hgd.branch_table(mask)
+        assert tab.num_hist * tab.num_gen == rec["nfe"]
+        assert tab.hist_indices.tolist() == rec["hist_indices"]
+        assert tab.gen_indices.tolist() == rec["gen_indices"]
+        assert tab.gen_mask.astype(int).tolist() == rec["gen_mask"]
+        assert tab.hist_noise_levels.tolist() == rec["hist_noise_levels"], rec
+        assert tab.cond_mask.astype(int).tolist() == rec["cond_mask"]
+        assert tab.weights.tolist() == rec["weights"]
+
+
+def test_interpolation_plans_bit_exact():
+    for rec in INTS["interpolation_calls"]:
+        known = np.zeros(rec["n_frames"], dtype=bool)
+        known[rec["keyframes"]] = True
+        plan = interpolation_plan(known, rec["max_tokens"])
+        assert len(plan) == len(rec["calls"])
+        k = known.copy()
+        for chunks, call in zip(plan, rec["calls"]):
+            rows = []
+            for c in chunks:
+                r = k[c].astype(int).tolist()
+                rows.append(r + [r[-1]] * (rec["max_tokens"] - len(r)))
+            assert rows == call["mask"]
+            for c in chunks:
+                k[c] = True
+
+
+def test_diffusion_buffers_bit_exact():
+    gold = np.load(os.path.join(GOLDEN, "schedules.npz"))
+    for tag, over in [("cosine", {}), ("continuous", continuous_overrides()),
+                      ("sigmoid_zt", {"diffusion.beta_schedule": "sigmoid", "diffusion.schedule_fn_kwargs": {}}),
+                      ("cosine_shift", {"diffusion.schedule_fn_kwargs": dict(shift=0.5)})]:
+        dm = DFoTVideo(_tiny(**over)).diffusion_model
+        for name in ["alphas_cumprod", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "logsnr"]:
+            if f"{tag}.{name}" in gold:
+                assert np.array_equal(getattr(dm, name).numpy(), gold[f"{tag}.{name}"]), (tag, name)
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_state_dict_keys_match_reference(name):
+    meta, _, weights = load_case(name)
+    algo = DFoTVideo(meta["cfg"])
+    sd = {"diffusion_model.model." + k: v for k, v in weights.items()}
+    sd["data_mean"], sd["data_std"] = algo.data_mean, algo.data_std
+    res = algo.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+
+
+def test_ops_fail_loudly_without_cuda():
+    x = torch.zeros(2, 4, 16)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.sampler_step_hg(x, None, None, None, None, None, None, None, 2, 1, 4)
+    algo = DFoTVideo(_tiny())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        algo.diffusion_model.model(torch.zeros(1, 8, 4, 8, 8), torch.zeros(1, 8, dtype=torch.long))
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_planner_end_to_end_on_cpu(name, monkeypatch):
+    """Product host logic + K4 contract emulation + oracle backbone (all fp32 on CPU) must reproduce the
+    reference rollout: per-step levels bit-exact, tensors <= 2e-5 (coefficients are folded in float64)."""
+    meta, arr, weights = load_case(name)
+    cfg = meta["cfg"]
+    algo = DFoTVideo(cfg)
+    algo.model_in_dtype = torch.float32
+    _, backbone = build_oracle(cfg, weights)
+
+    class OracleBackbone(torch.nn.Module):
+        def forward(self, x, k, c=None, cm=None, out_dtype=None):
+            return backbone(x, k, c, cm)
+
+    algo.diffusion_model.model = OracleBackbone()
+    monkeypatch.setattr(ops, "sampler_step_hg", k4_emulation.emulate)
+    torch.manual_seed(meta["sampling_seed"])
+    algo.diffusion_model.noise_source = lambda shape, device: torch.randn(shape)
+    algo.trace = []
+    xs = torch.from_numpy(arr["xs"])
+    conds = torch.from_numpy(arr["conds"]) if "conds" in arr else None
+    out = algo._predict_videos(xs.clone(), cfg["context_frames"], conds)
+    assert len(algo.trace) == int(arr["n_steps"])
+    for i, t in enumerate(algo.trace):
+        p = f"step{i:03d}."
+        assert np.array_equal(t["levels_from"], arr[p + "levels_from"]), (name, i)
+        assert np.array_equal(t["levels_to"], arr[p + "levels_to"]), (name, i)
+        assert (t["cond_mask"] is None) == (p + "cond_mask" not in arr)
+        if t["cond_mask"] is not None:
+            assert np.array_equal(t["cond_mask"], arr[p + "cond_mask"])
+        for k in ["model_in", "model_out"]:
+            err = np.abs(t[k].numpy() - arr[p + k]).max()
+            assert err <= 2e-5, (name, i, k, err)
+    err = np.abs(out.numpy() - arr["prediction"]).max()
+    assert err <= 2e-5, (name, err)
