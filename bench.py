@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — DFoT denoising-sampling throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # CPU baseline arm (reference algorithm on host cores)
+
+Workload (configs[1]): K600-shaped DFoT DiT3D-XL latent sampling — latents [16,16,16], 17 frames = 5 tokens
+(2 context tokens), 50 DDIM steps, conditional history guidance (nfe=1), batch 8 per GPU.  A bench "step" is one
+full sampling pass over one batch (50 denoising steps).  Synthetic latents, random-init weights (zero-initialised
+output layers re-drawn N(0,0.02) so the network is not identically 0).
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+# --------------------------------------------------------------------------------------- workload definition
+def k600_cfg(sampling_timesteps=50, spatial_mlp_ratio=4.0, depth=28, hidden=1152, heads=16):
+    """`dataset=kinetics_600 algorithm=dfot_video @DiT/XL` resolved by hand (kinetics_600.yaml,
+    kinetics_600_video_generation.yaml, shortcut/DiT/XL.yaml, dfot_video.yaml).  spatial_mlp_ratio=4.0 gives the
+    MLP blocks of the published DiT-XL (the fork's dit3d.yaml leaves it unset → no MLP)."""
+    mean = [[[0.0]]] * 16
+    std = [[[1.0]]] * 16
+    return dict(
+        debug=False, lr=1e-4, external_cond_type=None, external_cond_num_classes=None, external_cond_dim=0,
+        external_cond_stack=False, external_cond_processing=None,
+        backbone=dict(name="dit3d", variant="full", pos_emb_type="rope_3d", patch_size=1, hidden_size=hidden,
+                      depth=depth, num_heads=heads, mlp_ratio=4.0, spatial_mlp_ratio=spatial_mlp_ratio,
+                      use_gradient_checkpointing=False),
+        x_shape=[3, 128, 128], max_frames=17, n_frames=17, frame_skip=1, context_frames=5,
+        latent=dict(enabled=True, type="pre_sample", suffix=None, downsampling_factor=[4, 8], shape=None,
+                    num_channels=16),
+        data_mean=mean, data_std=std, compile=False, weight_decay=0, optimizer_beta=[0.9, 0.99],
+        lr_scheduler=dict(name="constant_with_warmup", num_warmup_steps=10000), noise_level="random_independent",
+        uniform_future=dict(enabled=False), fixed_context=dict(enabled=False, indices=None, dropout=0),
+        variable_context=dict(enabled=False, prob=0.25, dropout=0.3), chunk_size=-1,
+        scheduling_matrix="full_sequence", replacement="noisy_scale",
+        refinement_sampling=dict(enabled=False, goback_length=20, n_goback=5),
+        save_attn_map=dict(enabled=False, attn_map_dir=""),
+        diffusion=dict(is_continuous=False, timesteps=1000, beta_schedule="cosine", schedule_fn_kwargs=dict(shift=1.0),
+                       use_causal_mask=False, clip_noise=20.0, objective="pred_v",
+                       loss_weighting=dict(strategy="fused_min_snr", snr_clip=5.0, cum_snr_decay=0.96),
+                       sampling_timesteps=sampling_timesteps, ddim_sampling_eta=0.0, reconstruction_guidance=0.0),
+        vae=dict(pretrained_path=None, pretrained_kwargs={}, use_fp16=False, batch_size=2),
+        checkpoint=dict(reset_optimizer=False, strict=True),
+        tasks=dict(prediction=dict(enabled=True, history_guidance=dict(name="conditional", visualize=False),
+                                   keyframe_density=None, sliding_context_len=None),
+                   interpolation=dict(enabled=False, history_guidance=dict(name="conditional", visualize=False),
+                                      max_batch_size=None)),
+        logging=dict(deterministic=0, loss_freq=100, grad_norm_freq=100, max_num_videos=8, n_metrics_frames=None,
+                     metrics=[], metrics_batch_size=16, sanity_generation=False, raw_dir=None))
+
+
+N_FRAMES, CTX_FRAMES, N_TOKENS, CTX_TOKENS, BATCH = 17, 5, 5, 2, 8
+GEN_FRAMES = N_FRAMES - CTX_FRAMES
+
+
+def forward_row_gflop(cfg):
+    """Algorithmic GFLOP per backbone forward-row: per block per token 8D² + 4·N·D (+ 4·r·D²)."""
+    b = cfg["backbone"]
+    D, depth = b["hidden_size"], b["depth"]
+    r = b.get("spatial_mlp_ratio") or 0
+    P = (16 // b["patch_size"]) ** 2
+    N = N_TOKENS * P
+    per_tok = 8 * D * D + 4 * N * D + 4 * r * D * D
+    return depth * N * per_tok / 1e9
+
+
+def make_weights(cfg, seed=0):
+    import torch
+    from dfot_b200.algorithms.dfot import DFoTVideo
+    torch.manual_seed(seed)
+    algo = DFoTVideo(cfg)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for _, p in algo.named_parameters():
+            if bool((p == 0).all()):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    return algo
+
+
+# --------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_baseline(cfg_full, seconds_budget=25.0):
+    """The reference algorithm restated on the CPU (oracle/, torch fp32, all host threads) on a bounded sample of
+    the same workload: batch 1, 2 sampling steps → 2 forward-rows of the full-size DiT-XL.  NFE/s is step-count
+    independent; frames/s = NFE/s * generated frames / (50 steps * nfe)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle.dit3d import DiT3DOracle
+    from oracle.sampler import SamplerOracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = json.loads(json.dumps(cfg_full))
+    cfg["diffusion"]["sampling_timesteps"] = 2
+    algo = make_weights(cfg, 0)
+    weights = {k[len("diffusion_model.model."):]: v.detach() for k, v in algo.state_dict().items()
+               if k.startswith("diffusion_model.model.")}
+    probe = SamplerOracle(cfg, None)
+    model = DiT3DOracle(cfg["backbone"], probe.x_shape, probe.max_tokens, weights)
+    oracle = SamplerOracle(cfg, model)
+    g = torch.Generator().manual_seed(123)
+    xs = torch.randn((1, N_TOKENS, 16, 16, 16), generator=g)
+    torch.manual_seed(123)
+    t0 = time.perf_counter()
+    rows = 0
+    with torch.no_grad():
+        while True:
+            oracle.predict_videos(xs.clone(), CTX_TOKENS, None)
+            rows += 2
+            if time.perf_counter() - t0 > seconds_budget * 0.5 or rows >= 8:
+                break
+    dt = time.perf_counter() - t0
+    nfe_s = rows / dt
+    return dict(value=nfe_s * GEN_FRAMES / 50.0, unit="generated_frames/s", cores=cores, kind="port",
+                nfe_per_sec=nfe_s,
+                sample=f"oracle (reference algorithm, torch fp32 CPU, {cores} threads): batch 1 x 2 DDIM steps x "
+                       f"{rows // 2} passes = {rows} forward-rows of the full DiT-XL in {dt:.1f}s; "
+                       "frames/s derived as NFE/s*12/50")
+
+
+# --------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dfot_b200", choices=["dfot_b200", "reference"])
+    ap.add_argument("--no-mlp", action="store_true", help="fork default: spatial_mlp_ratio unset (no MLP blocks)")
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--sampling-steps", type=int, default=50)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = k600_cfg(args.sampling_steps, None if args.no_mlp else 4.0)
+    workload = (f"K600-shaped DFoT DiT3D-XL (28x1152, 16 heads d=72, patch 1, "
+                f"{'no MLP (fork default)' if args.no_mlp else 'MLP x4'}) latent sampling: latents 16x16x16, 17 frames = "
+                f"5 tokens (2 context), {args.sampling_steps} DDIM steps, conditional HG (nfe=1), batch {args.batch}/GPU")
+    config = dict(workload=workload, global_batch=args.batch * world, parallelism=f"samples sharded x{world}",
+                  l2="per-step activations (~0.5 GB) and weights (1.3 GB bf16) exceed the 126 MB L2; no flush needed")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_baseline(cfg)
+        line = dict(metric="generated_frames_per_sec", value=cb["value"], unit="generated_frames/s", n_gpus=args.gpus,
+                    steps=args.steps, warmup=args.warmup, ms_per_step=None, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f32", data="synthetic", impl="reference", config=config,
+                    nfe_per_sec=cb["nfe_per_sec"], cpu_baseline=cb,
+                    e2e=dict(value=cb["value"], unit="generated_frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from dfot_b200 import _abi, ops
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product has no CPU path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    algo = make_weights(cfg, 0).to(dev).eval()
+    B = args.batch
+    g = torch.Generator().manual_seed(123 + rank)
+    xs_host = torch.randn((B, N_TOKENS, 16, 16, 16), generator=g).pin_memory()
+    xs_dev = xs_host.to(dev)
+    torch.manual_seed(123 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_resident():
+        return algo._predict_videos(xs_dev, CTX_TOKENS, None)
+
+    gathered = [torch.empty((B, N_TOKENS, 16, 16, 16), device=dev) for _ in range(world)] if world > 1 else None
+
+    def run_e2e():
+        # public API with HOST buffers: H2D of the latents, sampling, (N>1: final sample gather), D2H of the result
+        batch = {"xs": xs_host.to(dev, non_blocking=True), "conditions": None, "gt_videos": None}
+        vids = algo._sample_all_videos(batch, 0)["prediction"]
+        if world > 1:
+            dist.all_gather(gathered, vids.contiguous())
+        return vids.to("cpu")
+
+    def timed(fn, steps):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        run_resident()
+    n0 = _abi.launch_count()
+    with ClockSampler(local_rank) as clocks:
+        ms = timed(run_resident, args.steps)
+    launches = _abi.launch_count() - n0
+    run_e2e()
+    ms_e2e = timed(run_e2e, args.steps)
+
+    # roofline of the dominant kernel (tcgen05 GEMM): instrumented second pass over the same timed region
+    roof = None
+    if rank == 0:
+        ops_gemm = ops.gemm_bf16
+        recs = []
+
+        def timed_gemm(a, w, out, epilogue, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            M = kw.get("M") or a.shape[0]
+            e0.record()
+            ops_gemm(a, w, out, epilogue, **kw)
+            e1.record()
+            recs.append((2.0 * M * w.shape[0] * w.shape[1], e0, e1))
+
+        ops.gemm_bf16 = timed_gemm
+        try:
+            run_resident()
+            torch.cuda.synchronize()
+        finally:
+            ops.gemm_bf16 = ops_gemm
+        big = [(f, a.elapsed_time(b)) for f, a, b in recs if f > 1e9]
+        flops, dur = sum(f for f, _ in big), sum(d for _, d in big)
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        ach = flops / (dur * 1e-3) / 1e12
+        roof = dict(bound="tensor", kernel="gemm_bf16_tcgen05_kernel", achieved=ach, peak=peak, unit="TFLOP/s",
+                    frac=ach / peak, traffic=None, launches=len(big), avg_launch_us=1e3 * dur / max(len(big), 1),
+                    peak_source="MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
+                    gemm_share_of_step=dur / (ms / args.steps))
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        per_step_s = ms / args.steps / 1e3
+        frames = B * world * GEN_FRAMES
+        rows = B * world * args.sampling_steps
+        per_e2e_s = ms_e2e / args.steps / 1e3
+        bytes_in = xs_host.numel() * 4
+        line = dict(metric="generated_frames_per_sec", value=frames / per_step_s, unit="generated_frames/s",
+                    n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                    config=config, nfe_per_sec=rows / per_step_s,
+                    model_tflops=rows * forward_row_gflop(cfg) / per_step_s / 1e3,
+                    e2e=dict(value=frames / per_e2e_s, unit="generated_frames/s", h2d_bytes_per_step=bytes_in,
+                             d2h_bytes_per_step=bytes_in, nfe_per_sec=rows / per_e2e_s),
+                    gpu_launches=int(launches), clocks=clocks.summary(), roofline=roof)
+        if not args.skip_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(cfg)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

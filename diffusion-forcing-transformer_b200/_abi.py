@@ -60,7 +60,7 @@ def lib() -> ctypes.CDLL:
     L.dfot_attention.argtypes = [vp, vp, i64, i64, i64, i64, vp]
     L.dfot_noise_features.argtypes = [vp, i, vp, vp, vp, i64, i64, vp]
     L.dfot_silu_sum_bf16.argtypes = [vp, vp, vp, i64, vp, i64, i64, vp]
-    L.dfot_patchify_bf16.argtypes = [vp, i, vp, i64, i64, i64, i64, i64, vp]
+    L.dfot_patchify_bf16.argtypes = [vp, i, vp, i64, i64, i64, i64, i64, i64, vp]
     L.dfot_unpatchify.argtypes = [vp, i64, vp, i, i64, i64, i64, i64, i64, vp]
     L.dfot_cast_bf16.argtypes = [vp, vp, i64, vp]
     for name in SYMBOLS:

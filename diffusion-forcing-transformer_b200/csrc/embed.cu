@@ -42,8 +42,8 @@ __global__ void silu_sum_bf16_kernel(const float* __restrict__ a, const float* _
 
 // out[token, c*p*p + py*p + px] = x[frame, c, gy*p + py, gx*p + px]; token = (frame, gy, gx)
 template <typename TX>
-__global__ void patchify_kernel(const TX* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t frames, int C,
-                                int H, int W, int p) {
+__global__ void patchify_kernel(const TX* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t ld,
+                                int64_t frames, int C, int H, int W, int p) {
   const int gw = W / p, gh = H / p, kk = C * p * p;
   const int64_t total = frames * gh * gw * kk;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -54,7 +54,7 @@ __global__ void patchify_kernel(const TX* __restrict__ x, __nv_bfloat16* __restr
   const int64_t fr = tok / ((int64_t)gw * gh);
   const int px = k % p, py = (k / p) % p, c = k / (p * p);
   const float v = (float)x[((fr * C + c) * H + gy * p + py) * W + gx * p + px];
-  out[idx] = __float2bfloat16_rn(v);
+  out[tok * ld + k] = __float2bfloat16_rn(v);
 }
 
 // x[frame, c, gy*p + py, gx*p + px] = tok[token, (py*p + px)*C + c]
@@ -108,17 +108,17 @@ extern "C" int dfot_silu_sum_bf16(const float* a, const float* b, const uint8_t*
   return DFOT_OK;
 }
 
-extern "C" int dfot_patchify_bf16(const void* x, int x_dtype, void* out_bf16, int64_t frames, int64_t C, int64_t H,
-                                  int64_t W, int64_t p, void* stream) {
-  DFOT_REQUIRE(x && out_bf16 && frames > 0 && C > 0 && p > 0 && H % p == 0 && W % p == 0, DFOT_ERR_INVALID_ARG,
-               "patchify: bad arguments");
+extern "C" int dfot_patchify_bf16(const void* x, int x_dtype, void* out_bf16, int64_t ld, int64_t frames, int64_t C,
+                                  int64_t H, int64_t W, int64_t p, void* stream) {
+  DFOT_REQUIRE(x && out_bf16 && frames > 0 && C > 0 && p > 0 && H % p == 0 && W % p == 0 && ld >= C * p * p,
+               DFOT_ERR_INVALID_ARG, "patchify: bad arguments");
   const int64_t total = frames * C * H * W;
   if (x_dtype == DFOT_F32)
     patchify_kernel<float><<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const float*)x, (__nv_bfloat16*)out_bf16, frames, (int)C, (int)H, (int)W, (int)p);
+        (const float*)x, (__nv_bfloat16*)out_bf16, ld, frames, (int)C, (int)H, (int)W, (int)p);
   else if (x_dtype == DFOT_BF16)
     patchify_kernel<__nv_bfloat16><<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)out_bf16, frames, (int)C, (int)H, (int)W, (int)p);
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)out_bf16, ld, frames, (int)C, (int)H, (int)W, (int)p);
   else
     DFOT_REQUIRE(false, DFOT_ERR_INVALID_ARG, "patchify: x dtype must be f32 or bf16");
   DFOT_CHECK_LAUNCH("patchify");

@@ -142,8 +142,8 @@ def silu_sum_bf16(a, b, row_mask, rows_per_mask, out):
 def patchify_bf16(x, out, frames, C, H, W, p):
     _need(x, None, "x")
     _need(out, torch.bfloat16, "out")
-    rc = _abi.lib().dfot_patchify_bf16(x.data_ptr(), _DTYPE_TAG[x.dtype], out.data_ptr(), frames, C, H, W, p,
-                                       _stream())
+    rc = _abi.lib().dfot_patchify_bf16(x.data_ptr(), _DTYPE_TAG[x.dtype], out.data_ptr(), out.stride(0), frames, C, H,
+                                       W, p, _stream())
     _abi.check(rc, "patchify_bf16")
 
 

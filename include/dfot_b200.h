@@ -156,9 +156,10 @@ DFOT_API int dfot_noise_features(const void* levels, int levels_dtype, const flo
 /* c_act = silu(a + (row_mask[r] ? 0 : b)) → bf16; a,b f32 [n_rows, D]; b / row_mask may be NULL; rows_per_mask = T */
 DFOT_API int dfot_silu_sum_bf16(const float* a, const float* b, const uint8_t* row_mask, int64_t rows_per_mask,
                        void* out_bf16, int64_t n_rows, int64_t D, void* stream);
-/* patchify: x [R*T, C, H, W] (f32 or bf16) → tokens [R*T*(H/p)*(W/p), C*p*p] bf16 in conv-weight order (c, py, px) */
-DFOT_API int dfot_patchify_bf16(const void* x, int x_dtype, void* out_bf16, int64_t frames, int64_t C, int64_t H, int64_t W,
-                       int64_t p, void* stream);
+/* patchify: x [R*T, C, H, W] (f32 or bf16) → tokens [R*T*(H/p)*(W/p), ld] bf16, columns (c, py, px) = conv-weight order;
+   columns >= C*p*p are left untouched (the caller zero-fills the K padding once) */
+DFOT_API int dfot_patchify_bf16(const void* x, int x_dtype, void* out_bf16, int64_t ld, int64_t frames, int64_t C, int64_t H,
+                       int64_t W, int64_t p, void* stream);
 /* unpatchify: tokens [frames*(H/p)*(W/p), ld] f32 with columns (py, px, c) → x [frames, C, H, W] (f32 or bf16) */
 DFOT_API int dfot_unpatchify(const float* tok, int64_t ld, void* x, int x_dtype, int64_t frames, int64_t C, int64_t H,
                     int64_t W, int64_t p, void* stream);

@@ -1,0 +1,207 @@
+"""-m gpu: every CUDA kernel, called through the C ABI, against a plain PyTorch fp32 reference of the same op
+(inputs rounded to bf16 where the kernel consumes bf16, so only accumulation order / output rounding differ)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from dfot_b200 import ops  # noqa: E402
+from dfot_b200.algorithms.dfot import sampling_plan as sp  # noqa: E402
+from dfot_b200.algorithms.dfot.backbones.dit.dit3d import rope_cos_sin_table  # noqa: E402
+import k4_emulation  # noqa: E402
+
+DEV = "cuda"
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).float()
+
+
+def rel_err(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp(min=1e-12)).item()
+
+
+# ---------------------------------------------------------------- K2 GEMM
+GEMM_SHAPES = [(128, 256, 64), (40, 64, 256), (1000, 192, 64), (333, 1152, 1152), (2560, 3456, 1152),
+               (512, 16, 1152), (40, 4608, 64), (130, 72, 8), (2048, 1152, 4608), (256, 136, 200)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_bias_f32_and_bf16(M, N, K):
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn((M, K), generator=g).to(DEV).to(torch.bfloat16)
+    w = (torch.randn((N, K), generator=g) / math.sqrt(K)).to(DEV).to(torch.bfloat16)
+    bias = torch.randn((N,), generator=g).to(DEV)
+    ref = a.float() @ w.float().t() + bias
+    out = torch.full((M, N), float("nan"), device=DEV)
+    ops.gemm_bf16(a, w, out, ops.EPI_F32, bias=bias)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item()), (out - ref).abs().max()
+    out16 = torch.empty((M, N), device=DEV, dtype=torch.bfloat16)
+    ops.gemm_bf16(a, w, out16, ops.EPI_BF16, bias=bias)
+    assert rel_err(out16, ref) < 5e-3
+
+
+def test_gemm_activations_and_gate_residual():
+    M, N, K, P = 640, 1152, 256, 64
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn((M, K), generator=g).to(DEV).to(torch.bfloat16)
+    w = (torch.randn((N, K), generator=g) / math.sqrt(K)).to(DEV).to(torch.bfloat16)
+    bias = torch.randn((N,), generator=g).to(DEV)
+    pre = a.float() @ w.float().t() + bias
+    o = torch.empty((M, N), device=DEV, dtype=torch.bfloat16)
+    ops.gemm_bf16(a, w, o, ops.EPI_GELU_BF16, bias=bias)
+    assert (o.float() - torch.nn.functional.gelu(pre, approximate="tanh")).abs().max().item() < 2e-2
+    ops.gemm_bf16(a, w, o, ops.EPI_SILU_BF16, bias=bias)
+    assert (o.float() - torch.nn.functional.silu(pre)).abs().max().item() < 2e-2
+    frames = M // P
+    mod = torch.randn((frames, 3 * N), generator=g).to(DEV)
+    resid = torch.randn((M, N), generator=g).to(DEV)
+    of = torch.empty((M, N), device=DEV)
+    ops.gemm_bf16(a, w, of, ops.EPI_GATE_RESID_F32, bias=bias, resid=resid, gate=mod[:, 2 * N:], ld_gate=3 * N,
+                  tokens_per_frame=P)
+    ref = resid + mod[:, 2 * N:].repeat_interleave(P, 0) * pre
+    assert (of - ref).abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize("heads,dh,T,gh,gw", [(4, 64, 8, 8, 8), (16, 72, 5, 16, 16), (2, 128, 3, 4, 4)])
+def test_gemm_qkv_rope_epilogue(heads, dh, T, gh, gw):
+    D, R = heads * dh, 2
+    Ntok = T * gh * gw
+    M = R * Ntok
+    g = torch.Generator().manual_seed(dh)
+    a = torch.randn((M, D), generator=g).to(DEV).to(torch.bfloat16)
+    w = (torch.randn((3 * D, D), generator=g) / math.sqrt(D)).to(DEV).to(torch.bfloat16)
+    bias = torch.randn((3 * D,), generator=g).to(DEV)
+    cs = rope_cos_sin_table(dh, (T, gh, gw)).to(DEV)
+    qs = 0.37
+    out = torch.empty((M, 3 * D), device=DEV, dtype=torch.bfloat16)
+    ops.gemm_bf16(a, w, out, ops.EPI_QKV_ROPE_BF16, bias=bias, rope_cs=cs, tokens_per_sample=Ntok, model_dim=D,
+                  head_dim=dh, q_scale=qs)
+    pre = (a.float() @ w.float().t() + bias).reshape(R, Ntok, 3, heads, dh)
+    cos = cs[..., 0].repeat_interleave(2, -1)[None, :, None, None, :]
+    sin = cs[..., 1].repeat_interleave(2, -1)[None, :, None, None, :]
+    pairs = pre.reshape(*pre.shape[:-1], -1, 2)
+    rot = torch.stack((-pairs[..., 1], pairs[..., 0]), -1).reshape(pre.shape)
+    roped = pre * cos + rot * sin
+    ref = pre.clone()
+    ref[:, :, 0] = roped[:, :, 0] * qs
+    ref[:, :, 1] = roped[:, :, 1]
+    assert (out.float().reshape(ref.shape) - ref).abs().max().item() < 3e-2
+    assert rel_err(out.reshape(ref.shape), ref) < 5e-3
+
+
+# ---------------------------------------------------------------- K3 attention
+@pytest.mark.parametrize("R,heads,dh,N", [(2, 4, 64, 512), (1, 1, 64, 64), (2, 16, 72, 1280), (1, 12, 64, 576),
+                                          (1, 9, 128, 2048), (3, 2, 72, 200), (1, 2, 64, 1)])
+def test_attention_matches_sdpa(R, heads, dh, N):
+    D = heads * dh
+    g = torch.Generator().manual_seed(N + dh)
+    qkv = torch.randn((R * N, 3 * D), generator=g).to(DEV).to(torch.bfloat16)
+    out = torch.full((R * N, D), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.attention(qkv, out, R, N, heads, dh)
+    q, k, v = qkv.float().reshape(R, N, 3, heads, dh).permute(2, 0, 3, 1, 4).unbind(0)
+    # the kernel expects q pre-multiplied by scale*log2(e) and uses exp2: softmax2(q k^T) == softmax(ln2 * q k^T)
+    w = torch.softmax(q @ k.transpose(-1, -2) * math.log(2.0), dim=-1)
+    ref = (w @ v).transpose(1, 2).reshape(R * N, D)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() < 3e-2, (out.float() - ref).abs().max()
+    assert rel_err(out, ref) < 1e-2
+
+
+# ---------------------------------------------------------------- K1 adaLN + LayerNorm
+@pytest.mark.parametrize("M,D,P", [(512, 256, 64), (1280, 1152, 256), (100, 64, 16), (96, 768, 16), (33, 2048, 11)])
+def test_adaln_layernorm(M, D, P):
+    g = torch.Generator().manual_seed(M + D)
+    x = (torch.randn((M, D), generator=g) * 3 + 0.5).to(DEV)
+    frames = (M + P - 1) // P
+    mod = torch.randn((frames, 6 * D), generator=g).to(DEV)
+    y32 = torch.empty((M, D), device=DEV)
+    y16 = torch.empty((M, D), device=DEV, dtype=torch.bfloat16)
+    ops.adaln_layernorm(x, mod, 3 * D, 4 * D, P, y_f32=y32, y_bf16=y16)
+    f = torch.arange(M, device=DEV) // P
+    ref = torch.nn.functional.layer_norm(x, (D,), eps=1e-6) * (1 + mod[f, 4 * D:5 * D]) + mod[f, 3 * D:4 * D]
+    assert (y32 - ref).abs().max().item() < 1e-4
+    assert (y16.float() - ref).abs().max().item() < 5e-2 and rel_err(y16, ref) < 4e-3
+
+
+# ---------------------------------------------------------------- K4 fused sampler step vs contract emulation
+@pytest.mark.parametrize("out_dt,in_dt", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                          (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("B,nfe,T,shape", [(2, 2, 8, (4, 16, 16)), (8, 1, 5, (16, 16, 16)), (1, 6, 4, (4, 8, 8)),
+                                           (1, 2, 8, (3, 64, 64))])
+def test_sampler_step_hg_matches_contract(out_dt, in_dt, B, nfe, T, shape):
+    g = torch.Generator().manual_seed(B * 100 + nfe * 10 + T)
+    rng = np.random.default_rng(B + nfe + T)
+    R = B * nfe
+    x = torch.randn((B, T, *shape), generator=g)
+    mo = torch.randn((R, T, *shape), generator=g).to(out_dt)
+    nd, nh, ne = (torch.randn((R, T, *shape), generator=g) for _ in range(3))
+    upd = np.zeros((R, T), dtype=sp.UPDATE_DTYPE)
+    upd["a"], upd["b"] = rng.normal(size=(R, T)), rng.normal(size=(R, T))
+    upd["sigma"] = np.where(rng.random((R, T)) < 0.5, 0.0, rng.normal(size=(R, T)))
+    upd["w"] = np.where(rng.random((R, T)) < 0.2, 0.0, rng.normal(size=(R, T)))
+    upd["clip"] = np.where(rng.random((R, T)) < 0.5, 0.0, 0.7)
+    gen = (rng.random((B, T)) < 0.6).astype(np.int32)
+    upd["generate"] = np.repeat(gen[:, None], nfe, 1).reshape(R, T)
+    prep = np.zeros((R, T), dtype=sp.PREPARE_DTYPE)
+    prep["mode"] = rng.integers(0, 3, size=(R, T))
+    prep["noise_row"] = rng.integers(0, R, size=(R, T))
+    prep["qa"], prep["qb"] = rng.random((R, T)), rng.random((R, T))
+    x_ref, mi_ref = x.clone(), torch.empty((R, T, *shape), dtype=in_dt)
+    k4_emulation.emulate(x_ref, mo, mi_ref, upd, prep, nd, nh, ne, B, nfe, T)
+    xd, mi = x.to(DEV), torch.full((R, T, *shape), float("nan"), device=DEV, dtype=in_dt)
+    ops.sampler_step_hg(xd, mo.to(DEV), mi, sp.to_device_bytes(upd, DEV), sp.to_device_bytes(prep, DEV), nd.to(DEV),
+                        nh.to(DEV), ne.to(DEV), B, nfe, T)
+    assert (xd.cpu() - x_ref).abs().max().item() < 1e-4
+    tol = 1e-5 if in_dt == torch.float32 else 4e-2
+    assert (mi.float().cpu() - mi_ref.float()).abs().max().item() < tol
+    # prepare-only and update-only launches
+    x2 = x.to(DEV)
+    ops.sampler_step_hg(x2, None, mi, None, sp.to_device_bytes(prep, DEV), None, nh.to(DEV), ne.to(DEV), B, nfe, T)
+    assert torch.equal(x2.cpu(), x)
+    x3 = x.to(DEV)
+    ops.sampler_step_hg(x3, mo.to(DEV), None, sp.to_device_bytes(upd, DEV), None, nd.to(DEV), None, None, B, nfe, T)
+    assert (x3.cpu() - x_ref).abs().max().item() < 1e-4
+
+
+# ---------------------------------------------------------------- glue kernels
+def test_noise_features_patchify_unpatchify_silu():
+    g = torch.Generator().manual_seed(0)
+    lv = torch.randint(0, 1000, (40,), generator=g)
+    out = torch.empty((40, 256), device=DEV, dtype=torch.bfloat16)
+    ops.noise_features(lv.to(DEV), out)
+    fr = torch.exp(-math.log(10000) * torch.arange(128, dtype=torch.float32) / 128)
+    ang = lv[:, None].float() * fr
+    ref = torch.cat([ang.cos(), ang.sin()], -1)
+    assert (out.float().cpu() - ref).abs().max().item() < 1e-2
+    lvf = torch.randn((40,), generator=g) * 2
+    freqs, phases = torch.randn((256,), generator=g) * 6, torch.rand((256,), generator=g) * 6
+    ops.noise_features(lvf.to(DEV), out, freqs.to(DEV), phases.to(DEV))
+    ref = torch.cos(lvf[:, None] * freqs + phases) * math.sqrt(2)
+    assert (out.float().cpu() - ref).abs().max().item() < 1e-2
+    # patchify / unpatchify
+    for C, H, W, p in [(4, 16, 16, 2), (16, 16, 16, 1), (32, 8, 8, 2)]:
+        fr_ = 6
+        x = torch.randn((fr_, C, H, W), generator=g)
+        kk = C * p * p
+        pat = torch.zeros((fr_ * (H // p) * (W // p), (kk + 7) // 8 * 8), device=DEV, dtype=torch.bfloat16)
+        if pat.shape[1] == kk:
+            ops.patchify_bf16(x.to(DEV), pat, fr_, C, H, W, p)
+            ref = torch.nn.functional.unfold(x, p, stride=p).transpose(1, 2).reshape(-1, kk)
+            assert torch.equal(pat.float().cpu(), ref.to(torch.bfloat16).float())
+        tok = torch.randn((fr_ * (H // p) * (W // p), (kk + 7) // 8 * 8), generator=g)
+        xo = torch.empty((fr_, C, H, W), device=DEV)
+        ops.unpatchify(tok.to(DEV), xo, fr_, C, H, W, p)
+        ref = tok[:, :kk].reshape(fr_, H // p, W // p, p, p, C).permute(0, 5, 1, 3, 2, 4).reshape(fr_, C, H, W)
+        assert torch.equal(xo.cpu(), ref)
+    a, b = torch.randn((24, 64), generator=g), torch.randn((24, 64), generator=g)
+    mask = torch.tensor([1, 0, 1], dtype=torch.uint8)
+    o = torch.empty((24, 64), device=DEV, dtype=torch.bfloat16)
+    ops.silu_sum_bf16(a.to(DEV), b.to(DEV), mask.to(DEV), 8, o)
+    keep = (1 - mask.float()).repeat_interleave(8)[:, None]
+    assert (o.float().cpu() - torch.nn.functional.silu(a + keep * b)).abs().max().item() < 2e-2

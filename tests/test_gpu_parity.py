@@ -1,0 +1,161 @@
+"""-m gpu: the CUDA sampling path (through the C ABI) against the oracle and the committed goldens.
+
+Gates (BASELINE.json north_star): scheduling / mask / level integers bit-exact; per-step denoiser output
+max-abs error <= 2e-2 (bf16 kernels vs fp32 reference); final sample PSNR >= 40 dB vs the reference rollout
+(data_range = value range of the reference rollout, non-context frames)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from dfot_b200.algorithms.dfot import DFoTVideo  # noqa: E402
+from helpers import NoiseBank, build_oracle, case_names, load_case  # noqa: E402
+from oracle.cases import algorithm_cfg, continuous_overrides  # noqa: E402
+
+DEV = "cuda"
+STEP_TOL = 2e-2
+PSNR_MIN = 40.0
+
+
+def psnr(pred, ref, n_ctx):
+    p, r = pred[:, n_ctx:].double(), ref[:, n_ctx:].double()
+    rng = (r.max() - r.min()).item()
+    mse = ((p - r) ** 2).mean().item()
+    return 10 * math.log10(rng * rng / max(mse, 1e-30))
+
+
+def load_product(cfg, weights):
+    algo = DFoTVideo(cfg)
+    sd = {"diffusion_model.model." + k: v for k, v in weights.items()}
+    sd["data_mean"], sd["data_std"] = algo.data_mean, algo.data_std
+    algo.load_state_dict(sd, strict=True)
+    return algo.to(DEV).eval()
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_golden_case_on_gpu(name):
+    """GPU rollout vs the fixture produced by executing the reference (same weights, inputs and noise stream)."""
+    meta, arr, weights = load_case(name)
+    cfg = meta["cfg"]
+    algo = load_product(cfg, weights)
+    torch.manual_seed(meta["sampling_seed"])
+    algo.diffusion_model.noise_source = lambda shape, device: torch.randn(shape).to(device)
+    algo.trace = []
+    xs = torch.from_numpy(arr["xs"]).to(DEV)
+    conds = torch.from_numpy(arr["conds"]).to(DEV) if "conds" in arr else None
+    out = algo._predict_videos(xs.clone(), cfg["context_frames"], conds).cpu()
+    assert len(algo.trace) == int(arr["n_steps"])
+    worst = 0.0
+    for i, t in enumerate(algo.trace):
+        p = f"step{i:03d}."
+        assert np.array_equal(t["levels_from"], arr[p + "levels_from"])
+        assert np.array_equal(t["levels_to"], arr[p + "levels_to"])
+        if t["cond_mask"] is not None:
+            assert np.array_equal(t["cond_mask"], arr[p + "cond_mask"])
+        worst = max(worst, np.abs(t["model_out"].cpu().numpy() - arr[p + "model_out"]).max())
+    assert worst <= STEP_TOL, f"per-step denoiser output max-abs error {worst}"
+    ref = torch.from_numpy(arr["prediction"])
+    assert psnr(out, ref, cfg["context_frames"]) >= PSNR_MIN
+    assert torch.equal(out[:, :cfg["context_frames"]], ref[:, :cfg["context_frames"]])  # context untouched
+
+
+def tiny_cfg1(**over):
+    """BASELINE.json configs[0]: tiny DFoT DiT3D (4 layers, hidden 256), 8-frame 16x16 latents, 10 steps, 1 context."""
+    base = {"backbone.hidden_size": 256, "backbone.depth": 4, "backbone.num_heads": 4, "backbone.spatial_mlp_ratio": 4.0,
+            "x_shape": [4, 16, 16], "max_frames": 8, "n_frames": 8, "context_frames": 1,
+            "diffusion.sampling_timesteps": 10,
+            "tasks.prediction.history_guidance": dict(name="vanilla", guidance_scale=4.0, visualize=False)}
+    base.update(over)
+    return algorithm_cfg(**base)
+
+
+def random_weights(cfg, seed):
+    """Reference-shaped random init (zero-initialised outputs re-drawn N(0, 0.02) like the goldens)."""
+    torch.manual_seed(seed)
+    algo = DFoTVideo(cfg)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for _, p in algo.named_parameters():
+            if bool((p == 0).all()):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    return algo
+
+
+@pytest.mark.parametrize("variant", ["vanilla", "stabilized_sliding", "continuous_action", "nomlp_conditional"])
+def test_cfg1_vs_oracle(variant):
+    over = {}
+    n_frames, batch = 8, 2
+    if variant == "stabilized_sliding":
+        over = {"n_frames": 14, "tasks.prediction.history_guidance":
+                dict(name="stabilized_vanilla", guidance_scale=4.0, stabilization_level=0.02, visualize=False)}
+        n_frames, batch = 14, 1
+    elif variant == "continuous_action":
+        over = {**continuous_overrides(), "external_cond_type": "action", "external_cond_dim": 3,
+                "external_cond_processing": "mask_first", "backbone.external_cond_dropout": 0.1}
+    elif variant == "nomlp_conditional":
+        over = {"backbone.spatial_mlp_ratio": None,
+                "tasks.prediction.history_guidance": dict(name="conditional", visualize=False)}
+    cfg = tiny_cfg1(**over)
+    algo = random_weights(cfg, 0)
+    weights = {k[len("diffusion_model.model."):]: v.detach().clone() for k, v in algo.state_dict().items()
+               if k.startswith("diffusion_model.model.")}
+    g = torch.Generator().manual_seed(123)
+    xs = torch.randn((batch, n_frames, 4, 16, 16), generator=g)
+    conds = torch.randn((batch, n_frames, 3), generator=g) if cfg["external_cond_dim"] else None
+    # oracle on the host CPU
+    bank = NoiseBank(7)
+    oracle, _ = build_oracle(cfg, weights, randn=bank.randn, randn_like=bank.randn_like)
+    oracle.trace = []
+    ref = oracle.predict_videos(xs.clone(), 1, conds)
+    # product on the GPU with the same noise stream
+    bank2 = NoiseBank(7)
+    algo = algo.to(DEV).eval()
+    algo.diffusion_model.noise_source = lambda shape, device: bank2.randn(shape).to(device)
+    algo.trace = []
+    out = algo._predict_videos(xs.to(DEV), 1, None if conds is None else conds.to(DEV)).cpu()
+    assert len(algo.trace) == len(oracle.trace)
+    worst = 0.0
+    for t, o in zip(algo.trace, oracle.trace):
+        assert np.array_equal(t["levels_from"], o["levels_from"].numpy())
+        assert np.array_equal(t["levels_to"], o["levels_to"].numpy())
+        assert np.array_equal(t["context_mask"], o["context_mask"].numpy())
+        worst = max(worst, (t["model_out"].cpu() - o["model_out"]).abs().max().item())
+    assert worst <= STEP_TOL, f"per-step denoiser output max-abs error {worst}"
+    assert psnr(out, ref, 1) >= PSNR_MIN
+
+
+def test_api_level_calls():
+    """sample_step / q_sample / HistoryGuidance manager — the reference's per-step API — agree with the oracle."""
+    from oracle import history_guidance as ohg
+    from oracle.diffusion import Diffusion
+    from dfot_b200.algorithms.dfot.history_guidance import HistoryGuidance
+    cfg = tiny_cfg1()
+    algo = random_weights(cfg, 3).to(DEV).eval()
+    dm = algo.diffusion_model
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn((2, 8, 4, 16, 16), generator=g)
+    k = torch.randint(0, 1000, (2, 8), generator=g)
+    noise = torch.randn(x.shape, generator=g)
+    od = Diffusion(cfg["diffusion"], None)
+    assert (dm.q_sample(x.to(DEV), k.to(DEV), noise.to(DEV)).cpu() - od.q_sample(x, k, noise)).abs().max() < 1e-5
+    mask = torch.tensor([[1, 2, 0, 0, 0, 0, -1, -1]] * 2)
+    frm = torch.tensor([[-1, -1, 599, 599, 599, 599, 999, 999]] * 2)
+    to = torch.tensor([[-1, -1, 499, 499, 499, 499, 999, 999]] * 2)
+    scheme_cfg = dict(name="stabilized_vanilla", guidance_scale=3.0, stabilization_level=0.02)
+    bank, bank2 = NoiseBank(11), NoiseBank(11)
+    od = Diffusion(cfg["diffusion"], None, bank.randn_like)
+    sch = ohg.scheme_from_config(scheme_cfg, 1000)
+    tab = ohg.branch_table(sch, mask[0])
+    xr, f, t, cm, excl = ohg.full_prepare(sch, tab, mask, x, frm, to, od.q_sample, False, bank.randn_like)
+    dm.noise_source = lambda shape, device: bank2.randn(shape).to(device)
+    hgd = HistoryGuidance.from_config(scheme_cfg, timesteps=1000)
+    with hgd(mask.to(DEV)) as mgr:
+        assert mgr.nfe == tab.nfe
+        px, pf, pt, pcm = mgr.prepare(x.to(DEV), frm.to(DEV), to.to(DEV), dm.q_sample, False)
+        assert torch.equal(pf.cpu(), f) and torch.equal(pt.cpu(), t) and torch.equal(pcm.cpu(), cm)
+        assert (px.cpu() - xr).abs().max() < 1e-5
+        comp = mgr.compose(px)
+        assert (comp.cpu() - ohg.full_compose(tab, excl, xr)).abs().max() < 1e-4
