@@ -5,9 +5,10 @@
 //              128B-swizzled shared-memory ring, completion on mbarriers
 //   warp 1   : MMA issuer    — one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (128 x BN x 16),
 //              accumulating in tensor memory; tcgen05.commit releases ring slots / publishes accumulators
-//   warps 2-5: epilogue      — tcgen05.ld (32 lanes x 32 columns per warp) → bias / activation / gated
-//              residual / RoPE → 128-bit global stores.  Two TMEM accumulator stages let the epilogue
-//              of tile i overlap the main loop of tile i+1.
+//   warps 2-9: epilogue      — tcgen05.ld (32 lanes x 32 columns per warp) → XOR-swizzled shared-memory
+//              transpose → row-wise pass where a warp touches one contiguous row segment per instruction, so
+//              bias / gate / residual / RoPE-table reads and the output stores are all fully coalesced.
+//              Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
 // Both operands are K-major (A row-major activations, W = nn.Linear.weight), so no transposes exist anywhere.
 #include <cuda.h>
 
@@ -19,7 +20,9 @@ namespace gemm {
 constexpr int BM = 128;       // UMMA M (cta_group::1)
 constexpr int BK = 64;        // one 128-byte swizzle atom of bf16 along K
 constexpr int UMMA_K = 16;    // K per tcgen05.mma for 16-bit inputs
-constexpr int kThreads = 192; // 6 warps
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // TMA warp + MMA warp + epilogue warps
+constexpr int kRasterBand = 16;  // m-blocks per rasterisation band (L2 reuse of A and W among concurrent CTAs)
 
 template <int BN> struct Cfg {
   static constexpr int kStageBytesA = BM * BK * 2;
@@ -27,7 +30,9 @@ template <int BN> struct Cfg {
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two >= 32)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kEpiStageBytes = 32 * 32 * 4;  // per epilogue warp: 32 rows x 32 fp32, swizzled
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct Params {
@@ -148,80 +153,146 @@ template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc() {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-// ------------------------------------------------------------------ epilogue math on one 32-column chunk
+// ------------------------------------------------------------------ epilogue
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float u = x * (0.7978845608028654f + 0.035677408136300125f * x * x);
+  return 0.5f * x * (1.0f + tanh_approx(u));
+}
+__device__ __forceinline__ float silu_fast(float x) { return 0.5f * x * (1.0f + tanh_approx(0.5f * x)); }
+
+// Phase 1: this warp's 32x32 fp32 accumulator chunk (thread = row) → swizzled smem (16-byte unit j of row r
+// lives at unit j ^ (r & 7)): conflict-free for the row-owner writes AND for the row-wise reads below.
+__device__ __forceinline__ void stage_chunk(uint32_t stage, int lane, const uint32_t (&r)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t addr = stage + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+                 "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                 : "memory");
+  }
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+
+// Side inputs of one 32x32 chunk, fetched into registers BEFORE the accumulator is touched so that 32 (or 16)
+// independent coalesced loads per lane are in flight at once (the row-wise pass itself is then load-free).
+template <int EPI> struct ChunkSide {
+  float v[32];   // GATE_RESID: residual of (row i, this lane's column);  QKV_ROPE: (cos, sin) of row 2k + (lane>>4)
+};
+
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (&acc)[32], int m, int n0) {
-  // m < M is guaranteed by the caller; columns beyond N are dropped in groups of 8 (N % 8 == 0).
-  float v[32];
+__device__ __forceinline__ void prefetch_side(const Params& p, ChunkSide<EPI>& sd, int lane, int m0, int n0) {
+  if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) {
+    const int col = n0 + lane;
+    const bool col_ok = col < p.N;
+    const float* res = p.e.resid + (int64_t)m0 * p.e.ld_resid + col;
+    const int rows = p.M - m0;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-  if (p.e.bias != nullptr) {
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      if (n0 + 4 * g < p.N) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.e.bias + n0) + g);
-        v[4 * g] += b.x; v[4 * g + 1] += b.y; v[4 * g + 2] += b.z; v[4 * g + 3] += b.w;
-      }
-    }
-  }
-  if constexpr (EPI == DFOT_EPI_GELU_BF16) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
-  } else if constexpr (EPI == DFOT_EPI_SILU_BF16) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-  } else if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) {
-    const int64_t f = m / p.e.tokens_per_frame;
-    const float4* gate = reinterpret_cast<const float4*>(p.e.gate + f * p.e.ld_gate + n0);
-    const float4* res = reinterpret_cast<const float4*>(p.e.resid + (int64_t)m * p.e.ld_resid + n0);
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      if (n0 + 4 * g < p.N) {
-        const float4 gt = __ldg(gate + g);
-        const float4 r = res[g];
-        v[4 * g] = r.x + gt.x * v[4 * g];
-        v[4 * g + 1] = r.y + gt.y * v[4 * g + 1];
-        v[4 * g + 2] = r.z + gt.z * v[4 * g + 2];
-        v[4 * g + 3] = r.w + gt.w * v[4 * g + 3];
-      }
-    }
+    for (int i = 0; i < 32; ++i) sd.v[i] = (col_ok && i < rows) ? __ldg(res + (int64_t)i * p.e.ld_resid) : 0.f;
   } else if constexpr (EPI == DFOT_EPI_QKV_ROPE_BF16) {
-    const int D = (int)p.e.model_dim, dh = (int)p.e.head_dim;
-    if (n0 < 2 * D) {
-      const int tok = m % (int)p.e.tokens_per_sample;
-      const float2* cs = reinterpret_cast<const float2*>(p.e.rope_cs) + (int64_t)tok * (dh >> 1);
-      int dd = n0 % dh;  // column inside the head (even)
+    const int col = n0 + ((lane & 15) << 1);
+    const int dh = (int)p.e.head_dim, tps = (int)p.e.tokens_per_sample;
+    const bool rotate = col < 2 * (int)p.e.model_dim && col < p.N;
+    const float2* cs = reinterpret_cast<const float2*>(p.e.rope_cs) + ((col % dh) >> 1);
+    const int rows = p.M - m0;
+    const int tok0 = (m0 + (lane >> 4)) % tps;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int n = n0 + 2 * i;
-        if (n < 2 * D) {
-          const float2 c = __ldg(cs + (dd >> 1));
-          const float x0 = v[2 * i], x1 = v[2 * i + 1];
-          float r0 = x0 * c.x - x1 * c.y;
-          float r1 = x1 * c.x + x0 * c.y;
-          if (n < D) { r0 *= p.e.q_scale; r1 *= p.e.q_scale; }
-          v[2 * i] = r0;
-          v[2 * i + 1] = r1;
-        }
-        dd += 2;
-        if (dd >= dh) dd -= dh;
+    for (int k = 0; k < 16; ++k) {
+      int tok = tok0 + 2 * k;
+      if (tok >= tps) tok %= tps;
+      float2 c = make_float2(1.f, 0.f);
+      if (rotate && 2 * k + (lane >> 4) < rows) c = __ldg(cs + (int64_t)tok * (dh >> 1));
+      sd.v[2 * k] = c.x;
+      sd.v[2 * k + 1] = c.y;
+    }
+  }
+}
+
+// Phase 2 for fp32 outputs: lane = column, loop over the 32 rows of the chunk.
+template <int EPI>
+__device__ __forceinline__ void epilogue_rows_f32(const Params& p, const ChunkSide<EPI>& sd, uint32_t stage, int lane,
+                                                  int m0, int n0) {
+  const int col = n0 + lane;
+  const bool col_ok = col < p.N;
+  const float bias = (p.e.bias != nullptr && col_ok) ? __ldg(p.e.bias + col) : 0.f;
+  const int rows = p.M - m0;
+  float* out = reinterpret_cast<float*>(p.C) + (int64_t)m0 * p.ldc + col;
+  const uint32_t sbase = stage + (uint32_t)((lane & 3) << 2);
+  float gate0 = 0.f, gate1 = 0.f;
+  int split = 32;  // rows [0, split) belong to frame f0, the rest to f0 + 1 (a chunk spans at most 2 frames if P >= 32)
+  if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) {
+    const int64_t P = p.e.tokens_per_frame;
+    const int64_t f0 = (int64_t)m0 / P;
+    if (P >= 32) {
+      split = (int)min((int64_t)32, (f0 + 1) * P - m0);
+      if (col_ok) {
+        gate0 = __ldg(p.e.gate + f0 * p.e.ld_gate + col);
+        if (split < 32) gate1 = __ldg(p.e.gate + (f0 + 1) * p.e.ld_gate + col);
       }
     }
   }
-  if constexpr (EPI == DFOT_EPI_F32 || EPI == DFOT_EPI_GATE_RESID_F32) {
-    float* out = reinterpret_cast<float*>(p.C) + (int64_t)m * p.ldc + n0;
 #pragma unroll
-    for (int g = 0; g < 8; ++g)
-      if (n0 + 4 * g < p.N)
-        *reinterpret_cast<float4*>(out + 4 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-  } else {
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)m * p.ldc + n0;
+  for (int i = 0; i < 32; ++i) {
+    const float acc = lds_f32(sbase + (uint32_t)i * 128u + (uint32_t)((((lane >> 2) ^ (i & 7))) << 4));
+    if (col_ok && i < rows) {
+      if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) {
+        float g;
+        if (p.e.tokens_per_frame >= 32) g = i < split ? gate0 : gate1;
+        else g = __ldg(p.e.gate + ((int64_t)(m0 + i) / p.e.tokens_per_frame) * p.e.ld_gate + col);
+        out[(int64_t)i * p.ldc] = sd.v[i] + g * (acc + bias);
+      } else {
+        out[(int64_t)i * p.ldc] = acc + bias;
+      }
+    }
+  }
+}
+
+// Phase 2 for bf16 outputs: a lane owns two adjacent columns (a RoPE pair); lanes 0-15 take row 2k, 16-31 row 2k+1.
+template <int EPI>
+__device__ __forceinline__ void epilogue_rows_bf16(const Params& p, const ChunkSide<EPI>& sd, uint32_t stage, int lane,
+                                                   int m0, int n0) {
+  const int cl = (lane & 15) << 1;
+  const int col = n0 + cl;
+  const bool col_ok = col < p.N;  // N is even
+  float2 bias = make_float2(0.f, 0.f);
+  if (p.e.bias != nullptr && col_ok) bias = __ldg(reinterpret_cast<const float2*>(p.e.bias + col));
+  const int rows = p.M - m0;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)m0 * p.ldc + col;
+  const float qs = (EPI == DFOT_EPI_QKV_ROPE_BF16 && col < (int)p.e.model_dim) ? p.e.q_scale : 1.f;
+  const int half = lane >> 4;
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-      if (n0 + 8 * g < p.N)
-        *reinterpret_cast<uint4*>(out + 8 * g) =
-            make_uint4(pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
-                       pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
+  for (int k = 0; k < 16; ++k) {
+    const int i = 2 * k + half;
+    float2 v = lds_f32x2(stage + (uint32_t)i * 128u + (uint32_t)((((cl >> 2) ^ (i & 7))) << 4) +
+                         (uint32_t)((cl & 3) << 2));
+    v.x += bias.x;
+    v.y += bias.y;
+    if constexpr (EPI == DFOT_EPI_GELU_BF16) {
+      v.x = gelu_tanh_fast(v.x);
+      v.y = gelu_tanh_fast(v.y);
+    } else if constexpr (EPI == DFOT_EPI_SILU_BF16) {
+      v.x = silu_fast(v.x);
+      v.y = silu_fast(v.y);
+    } else if constexpr (EPI == DFOT_EPI_QKV_ROPE_BF16) {
+      const float c = sd.v[2 * k], sn = sd.v[2 * k + 1];   // (1, 0) on v columns
+      const float x0 = v.x, x1 = v.y;
+      v.x = (x0 * c - x1 * sn) * qs;
+      v.y = (x1 * c + x0 * sn) * qs;
+    }
+    if (col_ok && i < rows) *reinterpret_cast<uint32_t*>(out + (int64_t)i * p.ldc) = pack_bf16x2(v.x, v.y);
   }
 }
 
@@ -240,11 +311,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * C::kStages + a); };
   auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * C::kStages + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * C::kStages + 4);
+  const uint32_t epi_stage0 = bars + 256u;  // 8 x 4 KB transpose buffers (16-byte aligned)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + BK - 1) / BK;
+  // banded rasterisation: consecutive tiles walk the n-blocks of a band of kRasterBand m-blocks, so the CTAs
+  // resident at any time share a small set of A and W tiles in L2
+  auto tile_coord = [&](int tile, int& m_blk, int& n_blk) {
+    const int band_tiles = kRasterBand * num_n;
+    const int band = tile / band_tiles, in_band = tile - band * band_tiles;
+    const int band_m0 = band * kRasterBand;
+    const int band_h = min(kRasterBand, num_m - band_m0);
+    m_blk = band_m0 + in_band % band_h;
+    n_blk = in_band / band_h;
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tma_a);
@@ -255,7 +337,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), 4);  // one arrival per epilogue warp
+      mbar_init(tmem_empty_bar(a), kEpiWarps);  // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -272,7 +354,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        int m_blk, n_blk;
+        tile_coord(tile, m_blk, n_blk);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), C::kStageBytes);
@@ -316,23 +399,34 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     }
   } else {
     // ===================== epilogue warps =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;          // TMEM lane quarter this warp may access (hardware rule: warp_id % 4)
+    const int half = (warp - 2) >> 2;  // the two warps of a quarter alternate over the 32-column chunks
+    const uint32_t stage_buf = epi_stage0 + (uint32_t)(warp - 2) * C::kEpiStageBytes;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      int m_blk, n_blk;
+      tile_coord(tile, m_blk, n_blk);
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tmem_full_bar(acc), acc_phase);
       tc_fence_after();
-      const int m = m_blk * BM + q * 32 + lane;
+      const int m0 = m_blk * BM + q * 32;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         const int n0 = n_blk * BN + c * 32;
-        if (n0 >= p.N) break;  // warp-uniform
+        if (n0 >= p.N || m0 >= p.M) break;  // warp-uniform
+        ChunkSide<EPI> side;
+        prefetch_side<EPI>(p, side, lane, m0, n0);   // loads overlap the TMEM read + transpose below
         uint32_t r[32];
         tmem_ld_x32(t_row + (uint32_t)(c * 32), r);
-        if (m < p.M) epilogue_chunk<EPI>(p, r, m, n0);
+        stage_chunk(stage_buf, lane, r);
+        __syncwarp();
+        if constexpr (EPI == DFOT_EPI_F32 || EPI == DFOT_EPI_GATE_RESID_F32)
+          epilogue_rows_f32<EPI>(p, side, stage_buf, lane, m0, n0);
+        else
+          epilogue_rows_bf16<EPI>(p, side, stage_buf, lane, m0, n0);
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
