@@ -1,0 +1,451 @@
+// K3 — attention over space-time latent tokens on the 5th-gen tensor cores (non-causal, unmasked).
+//
+// Persistent, warp-specialised flash attention; one work item = (sample r, head h, 128-query tile):
+//   warp 0    : TMA producer — Q tile once per item, K / V tiles of 128 keys through two 2-stage rings.
+//               q/k/v are read in place from the [tokens, 3, heads, d] QKV matrix via a 3-D tensor map whose
+//               innermost extent is the true head_dim, so head_dim 72 is zero-padded to 80 by TMA OOB fill.
+//   warp 1    : MMA issuer  — S_j = Q·K_jᵀ (128x128xd, both operands K-major) into a double-buffered TMEM
+//               score tile, then PV_j = P_j·V_j (128 x d x 128; P K-major from shared memory, V MN-major
+//               straight from its row-major tile — no transpose) into a double-buffered TMEM tile.
+//   warps 2-5 : softmax + accumulate, one thread per query row (TMEM lane): row max and sum need no
+//               cross-thread reduction, p = exp2(s - m) in fp32 (q is pre-scaled by scale·log2e and RoPE-rotated
+//               in the QKV-GEMM epilogue), P written as bf16 in the UMMA 128B-swizzled layout; the running
+//               output O lives in registers and is updated as O = O·alpha + PV_j one tile behind, so the
+//               PV MMA of tile j overlaps the softmax of tile j+1.
+// The N x N score matrix never leaves the SM (the reference materialises it in HBM: dit_blocks.py:21-44).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace dfot {
+namespace fattn {
+
+constexpr int BQ = 128, BKV = 128;
+constexpr int kThreads = 192;           // TMA warp, MMA warp, 4 softmax warps
+constexpr int kAtomBytes = 128 * 128;   // one 128-row x 128-byte swizzle plane (64 bf16 wide)
+
+// ------------------------------------------------------------------ PTX wrappers (same idioms as the GEMM)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint64_t t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((spin & 1023u) == 1023u) {   // bounded: a protocol bug must trap, never hang the GPU
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {
+        printf("dfot_attention: mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
+               threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// UMMA shared-memory descriptors (cute::UMMA::SmemDescriptor), 128-byte swizzle, version 1.
+//   K-major  operand: 8-row groups 1024 B apart (SBO); LBO unused.
+//   MN-major operand: K rows are 128-byte lines, 8-row groups 1024 B apart (SBO); 64-element MN atoms LBO apart.
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t addr, uint32_t lbo_bytes) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, M=128; b_mn selects MN-major B
+__device__ __forceinline__ constexpr uint32_t make_idesc(int n, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
+}
+
+struct Params {
+  __nv_bfloat16* out;
+  int R, Ntok, heads, q_tiles, kv_tiles, num_items;
+};
+
+// DH: true head dim; DP: head dim padded to a multiple of 16 (MMA K / N granularity)
+template <int DH, int DP>
+__global__ void __launch_bounds__(kThreads, 1)
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+  constexpr int ATOMS = (DP + 63) / 64;              // 64-wide swizzle planes per Q/K/V tile
+  constexpr int TILE_BYTES = ATOMS * kAtomBytes;     // Q, K or V tile
+  constexpr int P_BYTES = 2 * kAtomBytes;            // 128 rows x 128 keys bf16
+  constexpr int KS_QK = DP / 16, KS_PV = BKV / 16;
+  constexpr uint32_t IDESC_S = make_idesc(BKV, false);
+  constexpr uint32_t IDESC_PV = make_idesc(DP, true);
+  constexpr int TMEM_S0 = 0, TMEM_PV0 = 256;         // S: 2 x 128 cols, PV: 2 x 128 cols
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base;
+  const uint32_t sK = sQ + TILE_BYTES;               // 2 stages
+  const uint32_t sV = sK + 2 * TILE_BYTES;           // 2 stages
+  const uint32_t sP = sV + 2 * TILE_BYTES;           // 2 buffers
+  const uint32_t bars = sP + 2 * P_BYTES;
+  enum { Q_FULL = 0, Q_EMPTY = 1, K_FULL = 2, K_EMPTY = 4, V_FULL = 6, V_EMPTY = 8, S_FULL = 10, P_FULL = 12,
+         PV_DONE = 14, O_EMPTY = 16, N_BARS = 18 };
+  auto bar = [&](int id) { return bars + 8u * id; };
+  const uint32_t tmem_slot = bars + 8u * N_BARS;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    for (int i = 0; i < N_BARS; ++i) {
+      const bool from_softmax = (i >= P_FULL && i < P_FULL + 2) || (i >= O_EMPTY && i < O_EMPTY + 2);
+      mbar_init(bar(i), from_softmax ? 4 : 1);       // one arrival per softmax warp, else a single producer
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int n_kv = p.kv_tiles;
+  auto item_coord = [&](int item, int& r, int& h, int& qt) {
+    qt = item % p.q_tiles;                           // consecutive items share (r, h): K/V stay hot in L2
+    const int rh = item / p.q_tiles;
+    h = rh % p.heads;
+    r = rh / p.heads;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t g = 0, it = 0;                        // global KV-tile counter, item counter
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        int r, h, qt;
+        item_coord(item, r, h, qt);
+        const int row0 = r * p.Ntok;
+        mbar_wait(bar(Q_EMPTY), (it & 1u) ^ 1u);
+        mbar_expect_tx(bar(Q_FULL), TILE_BYTES);
+#pragma unroll
+        for (int a = 0; a < ATOMS; ++a) tma_load_3d(sQ + a * kAtomBytes, &tmap, bar(Q_FULL), a * 64, h, row0 + qt * BQ);
+        for (int j = 0; j < n_kv; ++j, ++g) {
+          const uint32_t st = g & 1u, ph = (g >> 1) & 1u;
+          mbar_wait(bar(K_EMPTY + st), ph ^ 1u);
+          mbar_expect_tx(bar(K_FULL + st), TILE_BYTES);
+#pragma unroll
+          for (int a = 0; a < ATOMS; ++a)
+            tma_load_3d(sK + st * TILE_BYTES + a * kAtomBytes, &tmap, bar(K_FULL + st), a * 64, p.heads + h,
+                        row0 + j * BKV);
+          mbar_wait(bar(V_EMPTY + st), ph ^ 1u);
+          mbar_expect_tx(bar(V_FULL + st), TILE_BYTES);
+#pragma unroll
+          for (int a = 0; a < ATOMS; ++a)
+            tma_load_3d(sV + st * TILE_BYTES + a * kAtomBytes, &tmap, bar(V_FULL + st), a * 64, 2 * p.heads + h,
+                        row0 + j * BKV);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t g = 0, it = 0;
+      auto issue_s = [&](uint32_t gt, bool last_of_item) {       // S = Q · K^T for global tile gt
+        const uint32_t st = gt & 1u, ph = (gt >> 1) & 1u;
+        mbar_wait(bar(K_FULL + st), ph);
+        tc_fence_after();
+        const uint32_t d = tmem_base + TMEM_S0 + st * 128u;
+#pragma unroll
+        for (int s = 0; s < KS_QK; ++s) {
+          const uint32_t off = (uint32_t)(s >> 2) * kAtomBytes + (uint32_t)(s & 3) * 32u;
+          umma_bf16(d, desc_kmajor(sQ + off), desc_kmajor(sK + st * TILE_BYTES + off), IDESC_S, s > 0 ? 1u : 0u);
+        }
+        umma_commit(bar(K_EMPTY + st));
+        umma_commit(bar(S_FULL + st));
+        if (last_of_item) umma_commit(bar(Q_EMPTY));
+      };
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        mbar_wait(bar(Q_FULL), it & 1u);
+        tc_fence_after();
+        // S buffer st was last read by the softmax of tile g-2, which preceded the PV MMA issued for it: free.
+        issue_s(g, n_kv == 1);
+        if (n_kv > 1) issue_s(g + 1, n_kv == 2);
+        for (int j = 0; j < n_kv; ++j) {
+          const uint32_t gt = g + j, st = gt & 1u, ph = (gt >> 1) & 1u;
+          mbar_wait(bar(V_FULL + st), ph);
+          mbar_wait(bar(O_EMPTY + st), ph ^ 1u);     // softmax consumed PV of tile gt-2
+          mbar_wait(bar(P_FULL + st), ph);           // P_j is in shared memory (and S_j has been read)
+          tc_fence_after();
+          const uint32_t d = tmem_base + TMEM_PV0 + st * 128u;
+#pragma unroll
+          for (int s = 0; s < KS_PV; ++s) {
+            const uint32_t a_off = (uint32_t)(s >> 2) * kAtomBytes + (uint32_t)(s & 3) * 32u;   // 16 keys along K
+            umma_bf16(d, desc_kmajor(sP + st * P_BYTES + a_off),
+                      desc_mnmajor(sV + st * TILE_BYTES + (uint32_t)s * 2048u, kAtomBytes), IDESC_PV, s > 0 ? 1u : 0u);
+          }
+          umma_commit(bar(V_EMPTY + st));
+          umma_commit(bar(PV_DONE + st));
+          if (j + 2 < n_kv) issue_s(gt + 2, j + 3 == n_kv);
+        }
+        g += n_kv;
+      }
+    }
+  } else {
+    // ===================== softmax + accumulate (thread = query row) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t g = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int r, h, qt;
+      item_coord(item, r, h, qt);
+      float o[DP];
+#pragma unroll
+      for (int c = 0; c < DP; ++c) o[c] = 0.f;
+      float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+
+      auto accumulate = [&](uint32_t gt, float alpha) {          // O = O*alpha + PV(gt)
+        const uint32_t st = gt & 1u, ph = (gt >> 1) & 1u;
+        mbar_wait(bar(PV_DONE + st), ph);
+        tc_fence_after();
+        const uint32_t t_pv = t_lane + TMEM_PV0 + st * 128u;
+#pragma unroll
+        for (int c0 = 0; c0 < DP; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_x16(t_pv + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) o[c0 + c] = o[c0 + c] * alpha + __uint_as_float(v[c]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(O_EMPTY + st));
+      };
+
+      for (int j = 0; j < n_kv; ++j) {
+        const uint32_t gt = g + j, st = gt & 1u, ph = (gt >> 1) & 1u;
+        mbar_wait(bar(S_FULL + st), ph);
+        tc_fence_after();
+        const uint32_t t_s = t_lane + TMEM_S0 + st * 128u;
+        const int valid = p.Ntok - j * BKV;          // keys of this tile that exist (>= 1)
+        // pass 1: row maximum
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BKV; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(t_s + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float s = (c0 + c < valid) ? __uint_as_float(v[c]) : -INFINITY;
+            mx = fmaxf(mx, s);
+          }
+        }
+        const float m_new = fmaxf(m_run, mx);
+        const float alpha = ex2(m_run - m_new);      // 0 on the first tile (m_run = -inf)
+        // pass 2: p = exp2(s - m), row sum, bf16 P in the 128B-swizzled K-major layout
+        float sum = 0.f;
+        const uint32_t p_row = sP + st * P_BYTES + (uint32_t)row * 128u;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BKV; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(t_s + c0, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            const float p0 = (c0 + c < valid) ? ex2(__uint_as_float(v[c]) - m_new) : 0.f;
+            const float p1 = (c0 + c + 1 < valid) ? ex2(__uint_as_float(v[c + 1]) - m_new) : 0.f;
+            sum += p0 + p1;
+            pk[c >> 1] = pack_bf16x2(p0, p1);
+          }
+          // keys c0..c0+31 = four 16-byte units; unit u of this row sits at unit (u ^ (row & 7)) of its plane
+#pragma unroll
+          for (int u4 = 0; u4 < 4; ++u4) {
+            const int u = (c0 >> 3) + u4;            // 16-byte unit index along the 128 keys (0..15)
+            const uint32_t addr = p_row + (uint32_t)(u >> 3) * kAtomBytes + (uint32_t)(((u & 7) ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * u4]), "r"(pk[4 * u4 + 1]),
+                         "r"(pk[4 * u4 + 2]), "r"(pk[4 * u4 + 3])
+                         : "memory");
+          }
+        }
+        l_run = l_run * alpha + sum;
+        m_run = m_new;
+        // make the generic-proxy writes of P visible to the tensor core (async proxy), then signal
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(P_FULL + st));
+        if (j > 0) accumulate(gt - 1, alpha_prev);   // one tile behind: overlaps the PV MMA with this softmax
+        alpha_prev = alpha;
+      }
+      accumulate(g + n_kv - 1, alpha_prev);
+      g += n_kv;
+
+      const int qrow = qt * BQ + row;
+      if (qrow < p.Ntok) {
+        const float inv = 1.f / l_run;
+        __nv_bfloat16* dst = p.out + ((int64_t)r * p.Ntok + qrow) * ((int64_t)p.heads * DH) + (int64_t)h * DH;
+#pragma unroll
+        for (int c = 0; c < DH; c += 8) {
+          uint4 w;
+          w.x = pack_bf16x2(o[c] * inv, o[c + 1] * inv);
+          w.y = pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv);
+          w.z = pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv);
+          w.w = pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv);
+          *reinterpret_cast<uint4*>(dst + c) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+template <int DH, int DP>
+static int launch(const void* qkv, void* out, int64_t R, int64_t Ntok, int64_t heads, cudaStream_t s) {
+  constexpr int ATOMS = (DP + 63) / 64;
+  constexpr int smem_bytes = 5 * ATOMS * kAtomBytes + 2 * 2 * kAtomBytes + 1024 + 256;
+  EncodeTiledFn enc = get_encode_fn();
+  DFOT_REQUIRE(enc != nullptr, DFOT_ERR_DRIVER, "attention: cuTensorMapEncodeTiled unavailable from the driver");
+  // qkv viewed as [tokens][3*heads][DH]: box = 64 (d) x 1 x 128 (tokens); d beyond DH is zero-filled by TMA
+  CUtensorMap tmap;
+  cuuint64_t gdim[3] = {(cuuint64_t)DH, (cuuint64_t)(3 * heads), (cuuint64_t)(R * Ntok)};
+  cuuint64_t gstr[2] = {(cuuint64_t)DH * 2, (cuuint64_t)(3 * heads * DH) * 2};
+  cuuint32_t box[3] = {64, 1, 128};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DFOT_REQUIRE(cr == CUDA_SUCCESS, DFOT_ERR_DRIVER, "attention: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+  auto kern = attention_tcgen05_kernel<DH, DP>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    DFOT_REQUIRE(e == cudaSuccess, DFOT_ERR_CUDA, "attention: cannot reserve %d B shared memory: %s", smem_bytes,
+                 cudaGetErrorString(e));
+    configured = true;
+  }
+  Params p;
+  p.out = (__nv_bfloat16*)out;
+  p.R = (int)R; p.Ntok = (int)Ntok; p.heads = (int)heads;
+  p.q_tiles = (int)ceil_div(Ntok, BQ);
+  p.kv_tiles = (int)ceil_div(Ntok, BKV);
+  p.num_items = (int)(R * heads * p.q_tiles);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.num_items < sms ? p.num_items : sms;
+  kern<<<grid, kThreads, smem_bytes, s>>>(tmap, p);
+  DFOT_CHECK_LAUNCH("attention_tcgen05");
+  return DFOT_OK;
+}
+
+}  // namespace fattn
+}  // namespace dfot
+
+extern "C" int dfot_attention(const void* qkv, void* out, int64_t R, int64_t Ntok, int64_t heads, int64_t head_dim,
+                              void* stream) {
+  using namespace dfot;
+  DFOT_REQUIRE(qkv && out && R > 0 && Ntok > 0 && heads > 0, DFOT_ERR_INVALID_ARG, "attention: bad arguments");
+  DFOT_REQUIRE(R * Ntok < (1ll << 31) && R * heads * ceil_div(Ntok, 128) < (1ll << 31), DFOT_ERR_UNSUPPORTED,
+               "attention: problem too large");
+  DFOT_REQUIRE(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 16 == 0), DFOT_ERR_UNSUPPORTED,
+               "attention: qkv and out must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (head_dim) {
+    case 64: return fattn::launch<64, 64>(qkv, out, R, Ntok, heads, s);
+    case 72: return fattn::launch<72, 80>(qkv, out, R, Ntok, heads, s);
+    case 128: return fattn::launch<128, 128>(qkv, out, R, Ntok, heads, s);
+  }
+  set_error("attention: head_dim %lld unsupported (64, 72, 128)", (long long)head_dim);
+  return DFOT_ERR_UNSUPPORTED;
+}

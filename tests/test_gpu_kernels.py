@@ -97,7 +97,9 @@ def test_gemm_qkv_rope_epilogue(heads, dh, T, gh, gw):
 
 # ---------------------------------------------------------------- K3 attention
 @pytest.mark.parametrize("R,heads,dh,N", [(2, 4, 64, 512), (1, 1, 64, 64), (2, 16, 72, 1280), (1, 12, 64, 576),
-                                          (1, 9, 128, 2048), (3, 2, 72, 200), (1, 2, 64, 1)])
+                                          (1, 9, 128, 2048), (3, 2, 72, 200), (1, 2, 64, 1), (2, 3, 72, 128),
+                                          (3, 2, 128, 129), (1, 2, 64, 256), (5, 7, 72, 384), (1, 2, 64, 8192),
+                                          (8, 16, 72, 1280)])
 def test_attention_matches_sdpa(R, heads, dh, N):
     D = heads * dh
     g = torch.Generator().manual_seed(N + dh)
