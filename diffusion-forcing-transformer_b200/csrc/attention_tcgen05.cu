@@ -7,11 +7,13 @@
 //   warp 1    : MMA issuer  — S_j = Q·K_jᵀ (128x128xd, both operands K-major) into a double-buffered TMEM
 //               score tile, then PV_j = P_j·V_j (128 x d x 128; P K-major from shared memory, V MN-major
 //               straight from its row-major tile — no transpose) into a double-buffered TMEM tile.
-//   warps 2-5 : softmax + accumulate, one thread per query row (TMEM lane): row max and sum need no
-//               cross-thread reduction, p = exp2(s - m) in fp32 (q is pre-scaled by scale·log2e and RoPE-rotated
-//               in the QKV-GEMM epilogue), P written as bf16 in the UMMA 128B-swizzled layout; the running
-//               output O lives in registers and is updated as O = O·alpha + PV_j one tile behind, so the
-//               PV MMA of tile j overlaps the softmax of tile j+1.
+//   warps 2-9 : softmax + accumulate.  Two warpgroups split every 128x128 score tile by key halves; a thread
+//               owns (query row = TMEM lane, 64 keys), so the row max needs ONE exchange with its partner thread
+//               (via shared memory + a 256-thread named barrier) and no shuffles.  p = exp2(s - m) in fp32 (q is
+//               pre-scaled by scale·log2e and RoPE-rotated in the QKV-GEMM epilogue), P written as bf16 in the
+//               UMMA 128B-swizzled layout; the running output O lives in registers (each warpgroup keeps half
+//               of the head_dim columns) and is updated as O = O·alpha + PV_j one tile behind, so the PV MMA of
+//               tile j overlaps the softmax of tile j+1.  Two warps per scheduler hide TMEM/MUFU latency.
 // The N x N score matrix never leaves the SM (the reference materialises it in HBM: dit_blocks.py:21-44).
 #include <cuda.h>
 
@@ -21,8 +23,10 @@ namespace dfot {
 namespace fattn {
 
 constexpr int BQ = 128, BKV = 128;
-constexpr int kThreads = 192;           // TMA warp, MMA warp, 4 softmax warps
+constexpr int kSoftmaxWarps = 8;
+constexpr int kThreads = 64 + 32 * kSoftmaxWarps;   // TMA warp, MMA warp, 2 softmax warpgroups
 constexpr int kAtomBytes = 128 * 128;   // one 128-row x 128-byte swizzle plane (64 bf16 wide)
+constexpr uint32_t kSuspendHintNs = 2000;
 
 // ------------------------------------------------------------------ PTX wrappers (same idioms as the GEMM)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -41,10 +45,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t spin = 0;; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(kSuspendHintNs)   // sleep in hardware instead of spinning on issue slots
         : "memory");
     if (done) return;
     if ((spin & 1023u) == 1023u) {   // bounded: a protocol bug must trap, never hang the GPU
@@ -101,6 +105,12 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -142,8 +152,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params 
   constexpr uint32_t IDESC_PV = make_idesc(DP, true);
   constexpr int TMEM_S0 = 0, TMEM_PV0 = 256;         // S: 2 x 128 cols, PV: 2 x 128 cols
 
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);          // 128B-swizzle atoms need 1024-byte alignment
+  if ((base & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("dfot_attention: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   const uint32_t sQ = base;
   const uint32_t sK = sQ + TILE_BYTES;               // 2 stages
   const uint32_t sV = sK + 2 * TILE_BYTES;           // 2 stages
@@ -153,13 +167,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params 
          PV_DONE = 14, O_EMPTY = 16, N_BARS = 18 };
   auto bar = [&](int id) { return bars + 8u * id; };
   const uint32_t tmem_slot = bars + 8u * N_BARS;
+  const uint32_t s_xchg = bars + 160u;               // float [2 (parity)][2 (warpgroup)][128 rows]: max / sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     for (int i = 0; i < N_BARS; ++i) {
       const bool from_softmax = (i >= P_FULL && i < P_FULL + 2) || (i >= O_EMPTY && i < O_EMPTY + 2);
-      mbar_init(bar(i), from_softmax ? 4 : 1);       // one arrival per softmax warp, else a single producer
+      mbar_init(bar(i), from_softmax ? kSoftmaxWarps : 1);   // one arrival per softmax warp, else one producer
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -256,85 +271,86 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params 
       }
     }
   } else {
-    // ===================== softmax + accumulate (thread = query row) =====================
-    const int q = warp & 3;
+    // ===================== softmax + accumulate (thread = query row x 64 keys) =====================
+    constexpr int HC = DP / 2;                       // output columns owned by this thread
+    const int q = warp & 3;                          // TMEM lane quarter (hardware rule: warp_id % 4)
+    const int wg = (warp - 2) >> 2;                  // warpgroup: which half of the keys / output columns
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t g = 0;
+    auto xchg = [&](uint32_t par, int g_, int r_) { return s_xchg + 4u * (uint32_t)((par * 2 + g_) * 128 + r_); };
+    auto pair_barrier = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    uint32_t g = 0, n_xchg = 0;                      // exchange slots alternate so one barrier per exchange suffices
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       int r, h, qt;
       item_coord(item, r, h, qt);
-      float o[DP];
+      float o[HC];
 #pragma unroll
-      for (int c = 0; c < DP; ++c) o[c] = 0.f;
+      for (int c = 0; c < HC; ++c) o[c] = 0.f;
       float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
 
-      auto accumulate = [&](uint32_t gt, float alpha) {          // O = O*alpha + PV(gt)
+      auto accumulate = [&](uint32_t gt, float alpha) {          // O = O*alpha + PV(gt), own column half
         const uint32_t st = gt & 1u, ph = (gt >> 1) & 1u;
         mbar_wait(bar(PV_DONE + st), ph);
         tc_fence_after();
-        const uint32_t t_pv = t_lane + TMEM_PV0 + st * 128u;
+        const uint32_t t_pv = t_lane + TMEM_PV0 + st * 128u + (uint32_t)(wg * HC);
+        uint32_t pv[HC / 8][8];
 #pragma unroll
-        for (int c0 = 0; c0 < DP; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld_x16(t_pv + c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 16; ++c) o[c0 + c] = o[c0 + c] * alpha + __uint_as_float(v[c]);
-        }
+        for (int c8 = 0; c8 < HC / 8; ++c8) tmem_ld_x8(t_pv + 8 * c8, pv[c8]);   // all loads in flight, one wait
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(O_EMPTY + st));
+        if (lane == 0) mbar_arrive(bar(O_EMPTY + st));             // TMEM tile is free again
+#pragma unroll
+        for (int c = 0; c < HC; ++c) o[c] = o[c] * alpha + __uint_as_float(pv[c >> 3][c & 7]);
       };
 
       for (int j = 0; j < n_kv; ++j) {
         const uint32_t gt = g + j, st = gt & 1u, ph = (gt >> 1) & 1u;
         mbar_wait(bar(S_FULL + st), ph);
         tc_fence_after();
-        const uint32_t t_s = t_lane + TMEM_S0 + st * 128u;
-        const int valid = p.Ntok - j * BKV;          // keys of this tile that exist (>= 1)
-        // pass 1: row maximum
+        const uint32_t t_s = t_lane + TMEM_S0 + st * 128u + (uint32_t)(wg * 64);
+        const int valid = p.Ntok - j * BKV - wg * 64;   // keys of this thread's half that exist (may be <= 0)
+        uint32_t v[2][32];                              // the 64 scores of this thread stay in registers
+        tmem_ld_x32(t_s, v[0]);
+        tmem_ld_x32(t_s + 32, v[1]);
+        tmem_ld_wait();
+        if (valid < 64) {                               // partial tile: mask once, in registers
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            if (c >= valid) v[c >> 5][c & 31] = 0xff800000u;   // -inf
+        }
         float mx = -INFINITY;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BKV; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_x32(t_s + c0, v);
-          tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float s = (c0 + c < valid) ? __uint_as_float(v[c]) : -INFINITY;
-            mx = fmaxf(mx, s);
-          }
-        }
-        const float m_new = fmaxf(m_run, mx);
+        for (int c = 0; c < 64; ++c) mx = fmaxf(mx, __uint_as_float(v[c >> 5][c & 31]));
+        // one exchange with the partner thread (same row, other key half)
+        const uint32_t par = n_xchg++ & 1u;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(xchg(par, wg, row)), "f"(mx) : "memory");
+        pair_barrier();
+        float mx_other;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mx_other) : "r"(xchg(par, wg ^ 1, row)));
+        const float m_new = fmaxf(m_run, fmaxf(mx, mx_other));
         const float alpha = ex2(m_run - m_new);      // 0 on the first tile (m_run = -inf)
-        // pass 2: p = exp2(s - m), row sum, bf16 P in the 128B-swizzled K-major layout
-        float sum = 0.f;
-        const uint32_t p_row = sP + st * P_BYTES + (uint32_t)row * 128u;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BKV; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_x32(t_s + c0, v);
-          tmem_ld_wait();
-          uint32_t pk[16];
+        // p = exp2(s - m), partial row sum, bf16 P into plane `wg` of the 128B-swizzled K-major tile
+        float sum0 = 0.f, sum1 = 0.f;
+        const uint32_t p_row = sP + st * P_BYTES + (uint32_t)wg * kAtomBytes + (uint32_t)row * 128u;
 #pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            const float p0 = (c0 + c < valid) ? ex2(__uint_as_float(v[c]) - m_new) : 0.f;
-            const float p1 = (c0 + c + 1 < valid) ? ex2(__uint_as_float(v[c + 1]) - m_new) : 0.f;
-            sum += p0 + p1;
-            pk[c >> 1] = pack_bf16x2(p0, p1);
-          }
-          // keys c0..c0+31 = four 16-byte units; unit u of this row sits at unit (u ^ (row & 7)) of its plane
+        for (int u = 0; u < 8; ++u) {                // 16-byte unit = 8 keys
+          uint32_t pk[4];
 #pragma unroll
-          for (int u4 = 0; u4 < 4; ++u4) {
-            const int u = (c0 >> 3) + u4;            // 16-byte unit index along the 128 keys (0..15)
-            const uint32_t addr = p_row + (uint32_t)(u >> 3) * kAtomBytes + (uint32_t)(((u & 7) ^ (row & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * u4]), "r"(pk[4 * u4 + 1]),
-                         "r"(pk[4 * u4 + 2]), "r"(pk[4 * u4 + 3])
-                         : "memory");
+          for (int e = 0; e < 4; ++e) {
+            const int c = 8 * u + 2 * e;
+            const float p0 = ex2(__uint_as_float(v[c >> 5][c & 31]) - m_new);
+            const float p1 = ex2(__uint_as_float(v[(c + 1) >> 5][(c + 1) & 31]) - m_new);
+            sum0 += p0;
+            sum1 += p1;
+            pk[e] = pack_bf16x2(p0, p1);
           }
+          const uint32_t addr = p_row + (uint32_t)((u ^ (row & 7)) << 4);   // swizzle: unit ^= row % 8
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                       "r"(pk[3])
+                       : "memory");
         }
-        l_run = l_run * alpha + sum;
+        l_run = l_run * alpha + (sum0 + sum1);
         m_run = m_new;
         // make the generic-proxy writes of P visible to the tensor core (async proxy), then signal
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -345,20 +361,28 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params 
         alpha_prev = alpha;
       }
       accumulate(g + n_kv - 1, alpha_prev);
+      // total row sum = own half + partner's half (both are relative to the same running maximum)
+      const uint32_t par = n_xchg++ & 1u;
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(xchg(par, wg, row)), "f"(l_run) : "memory");
+      pair_barrier();
+      float l_other;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l_other) : "r"(xchg(par, wg ^ 1, row)));
       g += n_kv;
 
       const int qrow = qt * BQ + row;
       if (qrow < p.Ntok) {
-        const float inv = 1.f / l_run;
-        __nv_bfloat16* dst = p.out + ((int64_t)r * p.Ntok + qrow) * ((int64_t)p.heads * DH) + (int64_t)h * DH;
+        const float inv = 1.f / (l_run + l_other);
+        __nv_bfloat16* dst = p.out + ((int64_t)r * p.Ntok + qrow) * ((int64_t)p.heads * DH) + (int64_t)h * DH + wg * HC;
 #pragma unroll
-        for (int c = 0; c < DH; c += 8) {
-          uint4 w;
-          w.x = pack_bf16x2(o[c] * inv, o[c + 1] * inv);
-          w.y = pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv);
-          w.z = pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv);
-          w.w = pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv);
-          *reinterpret_cast<uint4*>(dst + c) = w;
+        for (int c = 0; c < HC; c += 8) {
+          if (wg * HC + c < DH) {
+            uint4 w;
+            w.x = pack_bf16x2(o[c] * inv, o[c + 1] * inv);
+            w.y = pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv);
+            w.z = pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv);
+            w.w = pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv);
+            *reinterpret_cast<uint4*>(dst + c) = w;
+          }
         }
       }
     }
@@ -393,7 +417,8 @@ static EncodeTiledFn get_encode_fn() {
 template <int DH, int DP>
 static int launch(const void* qkv, void* out, int64_t R, int64_t Ntok, int64_t heads, cudaStream_t s) {
   constexpr int ATOMS = (DP + 63) / 64;
-  constexpr int smem_bytes = 5 * ATOMS * kAtomBytes + 2 * 2 * kAtomBytes + 1024 + 256;
+  constexpr int smem_bytes = 5 * ATOMS * kAtomBytes + 2 * 2 * kAtomBytes + 160 /*barriers*/ + 2048 /*exchange*/;
+  static_assert(smem_bytes <= 232448, "attention: shared memory budget exceeded");
   EncodeTiledFn enc = get_encode_fn();
   DFOT_REQUIRE(enc != nullptr, DFOT_ERR_DRIVER, "attention: cuTensorMapEncodeTiled unavailable from the driver");
   // qkv viewed as [tokens][3*heads][DH]: box = 64 (d) x 1 x 128 (tokens); d beyond DH is zero-filled by TMA

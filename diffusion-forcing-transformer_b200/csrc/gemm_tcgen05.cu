@@ -66,10 +66,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t spin = 0;; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(2000u)   // suspend-time hint (ns): sleep in hardware rather than burn issue slots
         : "memory");
     if (done) return;
     if ((spin & 1023u) == 1023u) {
