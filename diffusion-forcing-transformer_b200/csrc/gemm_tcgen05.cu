@@ -69,7 +69,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(2000u)   // suspend-time hint (ns): sleep in hardware rather than burn issue slots
+        : "r"(bar), "r"(parity), "r"(2000u)   // suspend-time hint (ns): sleep in hardware, do not burn issue slots
         : "memory");
     if (done) return;
     if ((spin & 1023u) == 1023u) {
@@ -189,87 +189,97 @@ __device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
 
 // Side inputs of one 32x32 chunk, fetched into registers BEFORE the accumulator is touched so that 32 (or 16)
 // independent coalesced loads per lane are in flight at once (the row-wise pass itself is then load-free).
+// FULL = the chunk lies completely inside the matrix: straight-line code without any predicate.
 template <int EPI> struct ChunkSide {
   float v[32];   // GATE_RESID: residual of (row i, this lane's column);  QKV_ROPE: (cos, sin) of row 2k + (lane>>4)
 };
 
-template <int EPI>
+template <int EPI, bool FULL>
 __device__ __forceinline__ void prefetch_side(const Params& p, ChunkSide<EPI>& sd, int lane, int m0, int n0) {
   if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) {
     const int col = n0 + lane;
-    const bool col_ok = col < p.N;
     const float* res = p.e.resid + (int64_t)m0 * p.e.ld_resid + col;
-    const int rows = p.M - m0;
+    if constexpr (FULL) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) sd.v[i] = (col_ok && i < rows) ? __ldg(res + (int64_t)i * p.e.ld_resid) : 0.f;
+      for (int i = 0; i < 32; ++i) sd.v[i] = __ldg(res + (int64_t)i * p.e.ld_resid);
+    } else {
+      const int rows = p.M - m0;
+      const bool col_ok = col < p.N;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sd.v[i] = (col_ok && i < rows) ? __ldg(res + (int64_t)i * p.e.ld_resid) : 0.f;
+    }
   } else if constexpr (EPI == DFOT_EPI_QKV_ROPE_BF16) {
     const int col = n0 + ((lane & 15) << 1);
     const int dh = (int)p.e.head_dim, tps = (int)p.e.tokens_per_sample;
     const bool rotate = col < 2 * (int)p.e.model_dim && col < p.N;
     const float2* cs = reinterpret_cast<const float2*>(p.e.rope_cs) + ((col % dh) >> 1);
-    const int rows = p.M - m0;
     const int tok0 = (m0 + (lane >> 4)) % tps;
+    const int hd2 = dh >> 1;
+    if (!rotate) {   // v columns: identity rotation
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      int tok = tok0 + 2 * k;
-      if (tok >= tps) tok %= tps;
-      float2 c = make_float2(1.f, 0.f);
-      if (rotate && 2 * k + (lane >> 4) < rows) c = __ldg(cs + (int64_t)tok * (dh >> 1));
-      sd.v[2 * k] = c.x;
-      sd.v[2 * k + 1] = c.y;
+      for (int k = 0; k < 16; ++k) { sd.v[2 * k] = 1.f; sd.v[2 * k + 1] = 0.f; }
+    } else if (FULL && tok0 + 31 < tps) {   // no wrap into the next sample inside this chunk
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float2 c = __ldg(cs + (tok0 + 2 * k) * hd2);
+        sd.v[2 * k] = c.x;
+        sd.v[2 * k + 1] = c.y;
+      }
+    } else {
+      const int rows = p.M - m0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        int tok = tok0 + 2 * k;
+        if (tok >= tps) tok %= tps;
+        float2 c = make_float2(1.f, 0.f);
+        if (2 * k + (lane >> 4) < rows) c = __ldg(cs + tok * hd2);
+        sd.v[2 * k] = c.x;
+        sd.v[2 * k + 1] = c.y;
+      }
     }
   }
 }
 
 // Phase 2 for fp32 outputs: lane = column, loop over the 32 rows of the chunk.
-template <int EPI>
+template <int EPI, bool FULL>
 __device__ __forceinline__ void epilogue_rows_f32(const Params& p, const ChunkSide<EPI>& sd, uint32_t stage, int lane,
                                                   int m0, int n0) {
   const int col = n0 + lane;
-  const bool col_ok = col < p.N;
+  const bool col_ok = FULL || col < p.N;
   const float bias = (p.e.bias != nullptr && col_ok) ? __ldg(p.e.bias + col) : 0.f;
-  const int rows = p.M - m0;
+  const int rows = FULL ? 32 : p.M - m0;
   float* out = reinterpret_cast<float*>(p.C) + (int64_t)m0 * p.ldc + col;
   const uint32_t sbase = stage + (uint32_t)((lane & 3) << 2);
   float gate0 = 0.f, gate1 = 0.f;
-  int split = 32;  // rows [0, split) belong to frame f0, the rest to f0 + 1 (a chunk spans at most 2 frames if P >= 32)
+  int split = 32;  // rows [0, split) belong to frame f0, the rest to f0 + 1 (tokens_per_frame >= 32, host-checked)
   if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) {
-    const int64_t P = p.e.tokens_per_frame;
-    const int64_t f0 = (int64_t)m0 / P;
-    if (P >= 32) {
-      split = (int)min((int64_t)32, (f0 + 1) * P - m0);
-      if (col_ok) {
-        gate0 = __ldg(p.e.gate + f0 * p.e.ld_gate + col);
-        if (split < 32) gate1 = __ldg(p.e.gate + (f0 + 1) * p.e.ld_gate + col);
-      }
+    const int P = (int)p.e.tokens_per_frame;
+    const int f0 = m0 / P;
+    split = min(32, (f0 + 1) * P - m0);
+    if (col_ok) {
+      gate0 = __ldg(p.e.gate + (int64_t)f0 * p.e.ld_gate + col);
+      if (split < 32) gate1 = __ldg(p.e.gate + (int64_t)(f0 + 1) * p.e.ld_gate + col);
     }
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
     const float acc = lds_f32(sbase + (uint32_t)i * 128u + (uint32_t)((((lane >> 2) ^ (i & 7))) << 4));
-    if (col_ok && i < rows) {
-      if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) {
-        float g;
-        if (p.e.tokens_per_frame >= 32) g = i < split ? gate0 : gate1;
-        else g = __ldg(p.e.gate + ((int64_t)(m0 + i) / p.e.tokens_per_frame) * p.e.ld_gate + col);
-        out[(int64_t)i * p.ldc] = sd.v[i] + g * (acc + bias);
-      } else {
-        out[(int64_t)i * p.ldc] = acc + bias;
-      }
-    }
+    float y = acc + bias;
+    if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) y = sd.v[i] + (i < split ? gate0 : gate1) * y;
+    if (FULL || (col_ok && i < rows)) out[(int64_t)i * p.ldc] = y;
   }
 }
 
 // Phase 2 for bf16 outputs: a lane owns two adjacent columns (a RoPE pair); lanes 0-15 take row 2k, 16-31 row 2k+1.
-template <int EPI>
+template <int EPI, bool FULL>
 __device__ __forceinline__ void epilogue_rows_bf16(const Params& p, const ChunkSide<EPI>& sd, uint32_t stage, int lane,
                                                    int m0, int n0) {
   const int cl = (lane & 15) << 1;
   const int col = n0 + cl;
-  const bool col_ok = col < p.N;  // N is even
+  const bool col_ok = FULL || col < p.N;  // N is even
   float2 bias = make_float2(0.f, 0.f);
   if (p.e.bias != nullptr && col_ok) bias = __ldg(reinterpret_cast<const float2*>(p.e.bias + col));
-  const int rows = p.M - m0;
+  const int rows = FULL ? 32 : p.M - m0;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)m0 * p.ldc + col;
   const float qs = (EPI == DFOT_EPI_QKV_ROPE_BF16 && col < (int)p.e.model_dim) ? p.e.q_scale : 1.f;
   const int half = lane >> 4;
@@ -292,8 +302,54 @@ __device__ __forceinline__ void epilogue_rows_bf16(const Params& p, const ChunkS
       v.x = (x0 * c - x1 * sn) * qs;
       v.y = (x1 * c + x0 * sn) * qs;
     }
-    if (col_ok && i < rows) *reinterpret_cast<uint32_t*>(out + (int64_t)i * p.ldc) = pack_bf16x2(v.x, v.y);
+    if (FULL || (col_ok && i < rows)) *reinterpret_cast<uint32_t*>(out + (int64_t)i * p.ldc) = pack_bf16x2(v.x, v.y);
   }
+}
+
+// GATE_RESID with fewer than 32 tokens per frame (small latent grids, e.g. 8x8 latents with patch 2): a chunk spans
+// several frames, so the gate is looked up per row.  Not a performance path (tiny models), kept simple.
+__device__ __noinline__ void epilogue_rows_gate_small_frames(const Params& p, uint32_t stage, int lane, int m0, int n0) {
+  const int col = n0 + lane;
+  if (col >= p.N) return;
+  const float bias = p.e.bias != nullptr ? __ldg(p.e.bias + col) : 0.f;
+  const int rows = min(32, p.M - m0);
+  const int P = (int)p.e.tokens_per_frame;
+  const uint32_t sbase = stage + (uint32_t)((lane & 3) << 2);
+  float* out = reinterpret_cast<float*>(p.C);
+#pragma unroll 1
+  for (int i = 0; i < rows; ++i) {
+    const int m = m0 + i;
+    const float acc = lds_f32(sbase + (uint32_t)i * 128u + (uint32_t)((((lane >> 2) ^ (i & 7))) << 4));
+    const float g = __ldg(p.e.gate + (int64_t)(m / P) * p.e.ld_gate + col);
+    out[(int64_t)m * p.ldc + col] = __ldg(p.e.resid + (int64_t)m * p.e.ld_resid + col) + g * (acc + bias);
+  }
+}
+
+template <int EPI, bool FULL>
+__device__ __forceinline__ void epilogue_chunk(const Params& p, uint32_t t_addr, uint32_t stage_buf, int lane, int m0,
+                                               int n0) {
+  if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) {
+    if (p.e.tokens_per_frame < 32) {   // warp-uniform
+      uint32_t r[32];
+      tmem_ld_x32(t_addr, r);
+      stage_chunk(stage_buf, lane, r);
+      __syncwarp();
+      epilogue_rows_gate_small_frames(p, stage_buf, lane, m0, n0);
+      __syncwarp();
+      return;
+    }
+  }
+  ChunkSide<EPI> side;
+  prefetch_side<EPI, FULL>(p, side, lane, m0, n0);   // loads overlap the TMEM read + transpose below
+  uint32_t r[32];
+  tmem_ld_x32(t_addr, r);
+  stage_chunk(stage_buf, lane, r);
+  __syncwarp();
+  if constexpr (EPI == DFOT_EPI_F32 || EPI == DFOT_EPI_GATE_RESID_F32)
+    epilogue_rows_f32<EPI, FULL>(p, side, stage_buf, lane, m0, n0);
+  else
+    epilogue_rows_bf16<EPI, FULL>(p, side, stage_buf, lane, m0, n0);
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -416,17 +472,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       for (int c = half; c < BN / 32; c += 2) {
         const int n0 = n_blk * BN + c * 32;
         if (n0 >= p.N || m0 >= p.M) break;  // warp-uniform
-        ChunkSide<EPI> side;
-        prefetch_side<EPI>(p, side, lane, m0, n0);   // loads overlap the TMEM read + transpose below
-        uint32_t r[32];
-        tmem_ld_x32(t_row + (uint32_t)(c * 32), r);
-        stage_chunk(stage_buf, lane, r);
-        __syncwarp();
-        if constexpr (EPI == DFOT_EPI_F32 || EPI == DFOT_EPI_GATE_RESID_F32)
-          epilogue_rows_f32<EPI>(p, side, stage_buf, lane, m0, n0);
+        if (m0 + 32 <= p.M && n0 + 32 <= p.N)
+          epilogue_chunk<EPI, true>(p, t_row + (uint32_t)(c * 32), stage_buf, lane, m0, n0);
         else
-          epilogue_rows_bf16<EPI>(p, side, stage_buf, lane, m0, n0);
-        __syncwarp();
+          epilogue_chunk<EPI, false>(p, t_row + (uint32_t)(c * 32), stage_buf, lane, m0, n0);
       }
       tc_fence_before();
       __syncwarp();
@@ -539,9 +588,8 @@ extern "C" int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   DFOT_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0) && ((uintptr_t)Cout % 16 == 0),
                DFOT_ERR_UNSUPPORTED, "gemm: A, W, C must be 16-byte aligned");
   if (epilogue == DFOT_EPI_GATE_RESID_F32)
-    DFOT_REQUIRE(epi->resid && epi->gate && epi->tokens_per_frame > 0 && epi->ld_resid % 4 == 0 &&
-                     epi->ld_gate % 4 == 0,
-                 DFOT_ERR_INVALID_ARG, "gemm: GATE_RESID needs resid, gate, tokens_per_frame and 16-byte rows");
+    DFOT_REQUIRE(epi->resid && epi->gate && epi->tokens_per_frame >= 1 && epi->tokens_per_frame < (1ll << 30),
+                 DFOT_ERR_INVALID_ARG, "gemm: GATE_RESID needs resid, gate and tokens_per_frame");
   if (epilogue == DFOT_EPI_QKV_ROPE_BF16)
     DFOT_REQUIRE(epi->rope_cs && epi->tokens_per_sample > 0 && epi->head_dim > 0 && epi->head_dim % 2 == 0 &&
                      epi->model_dim > 0 && epi->model_dim % epi->head_dim == 0 && N == 3 * epi->model_dim,

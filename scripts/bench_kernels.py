@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Micro-benchmarks of the individual kernels at the K600 DiT-XL shapes (CUDA events on the launch stream).
+Usage: python scripts/bench_kernels.py [attn|gemm|norm|all] [--iters N]"""
+import argparse
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dfot_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+def timeit(fn, iters=20, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3  # us
+
+
+def bench_attn(iters):
+    for (R, heads, dh, N) in [(8, 16, 72, 1280), (8, 16, 64, 1280), (8, 9, 128, 2048), (2, 12, 64, 576), (2, 9, 64, 8192)]:
+        D = heads * dh
+        qkv = (torch.randn((R * N, 3 * D), device=DEV) * 0.5).to(torch.bfloat16)
+        out = torch.empty((R * N, D), device=DEV, dtype=torch.bfloat16)
+        us = timeit(lambda: ops.attention(qkv, out, R, N, heads, dh), iters)
+        fl = 4.0 * R * heads * N * N * dh
+        print(f"attention R={R} heads={heads} d={dh} N={N}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s")
+
+
+def bench_gemm(iters):
+    M = 10240
+    for name, N, K, epi in [("qkv+rope", 3456, 1152, ops.EPI_QKV_ROPE_BF16), ("proj+gate", 1152, 1152, ops.EPI_GATE_RESID_F32),
+                            ("fc1+gelu", 4608, 1152, ops.EPI_GELU_BF16), ("fc2+gate", 1152, 4608, ops.EPI_GATE_RESID_F32),
+                            ("plain bf16 4608x1152", 4608, 1152, ops.EPI_BF16), ("plain f32 1152x1152", 1152, 1152, ops.EPI_F32),
+                            ("plain bf16 1152x1152", 1152, 1152, ops.EPI_BF16), ("plain f32 1152x4608", 1152, 4608, ops.EPI_F32),
+                            ("plain bf16 8192^3", 8192, 8192, ops.EPI_BF16)]:
+        m = 8192 if "8192" in name else M
+        a = torch.randn((m, K), device=DEV).to(torch.bfloat16)
+        w = (torch.randn((N, K), device=DEV) / math.sqrt(K)).to(torch.bfloat16)
+        bias = torch.randn((N,), device=DEV)
+        kw = dict(bias=bias)
+        if epi == ops.EPI_GATE_RESID_F32:
+            out = torch.empty((m, N), device=DEV)
+            mod = torch.randn((m // 256, 3 * N), device=DEV)
+            kw.update(resid=torch.randn((m, N), device=DEV), gate=mod[:, 2 * N:], ld_gate=3 * N, tokens_per_frame=256)
+        elif epi == ops.EPI_QKV_ROPE_BF16:
+            out = torch.empty((m, N), device=DEV, dtype=torch.bfloat16)
+            kw.update(rope_cs=torch.randn((1280, 36, 2), device=DEV), tokens_per_sample=1280, model_dim=1152, head_dim=72,
+                      q_scale=0.17)
+        elif epi == ops.EPI_F32:
+            out = torch.empty((m, N), device=DEV)
+        else:
+            out = torch.empty((m, N), device=DEV, dtype=torch.bfloat16)
+        us = timeit(lambda: ops.gemm_bf16(a, w, out, epi, **kw), iters)
+        print(f"gemm {name:22s} M={m} N={N} K={K}: {us:8.1f} us  {2.0 * m * N * K / us / 1e6:7.1f} TFLOP/s")
+    a = torch.randn((8192, 8192), device=DEV).to(torch.bfloat16)
+    us = timeit(lambda: torch.matmul(a, a.t()), iters)
+    print(f"cuBLAS bf16 8192^3 (reference point): {us:8.1f} us  {2.0 * 8192 ** 3 / us / 1e6:7.1f} TFLOP/s")
+
+
+def bench_norm(iters):
+    M, D, P = 10240, 1152, 256
+    x = torch.randn((M, D), device=DEV)
+    mod = torch.randn((M // P, 6 * D), device=DEV)
+    y32, y16 = torch.empty((M, D), device=DEV), torch.empty((M, D), device=DEV, dtype=torch.bfloat16)
+    us = timeit(lambda: ops.adaln_layernorm(x, mod, 0, D, P, y_f32=y32, y_bf16=y16), iters)
+    print(f"adaln_layernorm M={M} D={D} (f32+bf16 out): {us:7.1f} us  {M * D * 10 / us / 1e3:7.1f} GB/s")
+    us = timeit(lambda: ops.adaln_layernorm(x, mod, 0, D, P, y_bf16=y16), iters)
+    print(f"adaln_layernorm M={M} D={D} (bf16 out):     {us:7.1f} us  {M * D * 6 / us / 1e3:7.1f} GB/s")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("which", nargs="?", default="all")
+    ap.add_argument("--iters", type=int, default=20)
+    a = ap.parse_args()
+    if a.which in ("attn", "all"):
+        bench_attn(a.iters)
+    if a.which in ("gemm", "all"):
+        bench_gemm(a.iters)
+    if a.which in ("norm", "all"):
+        bench_norm(a.iters)
