@@ -61,6 +61,7 @@ class DFoTVideo(BaseVideoAlgo):
         self.trace: Optional[list] = None       # tests: per-step tensors are appended when this is a list
         self.nfe_rows = 0                       # backbone forward-rows executed (NFE counter)
         self.model_in_dtype = torch.bfloat16    # dtype of the branch inputs emitted by K4
+        self.mesh = None                        # dfot_b200.distributed.Mesh for multi-GPU sampling (None = 1 GPU)
 
     def _build_model(self) -> None:
         super()._build_model(ContinuousDiffusion if self.cfg.diffusion.is_continuous else DiscreteDiffusion)
@@ -211,6 +212,39 @@ class DFoTVideo(BaseVideoAlgo):
             cur = xs.shape[1]
         return xs, record
 
+    # ------------------------------------------------------------------ multi-GPU
+    def _backbone_rows(self, model_in, levels, cond, cond_mask, B: int, nfe: int):
+        """Backbone forward over the (b, j) branch rows; with a branch group each member runs its share of the
+        branches and the outputs are all-gathered (the only per-step collective of the path)."""
+        dm = self.diffusion_model
+        bg = self.mesh.branch_group if self.mesh is not None else None
+        if bg is None or nfe == 1:
+            return dm.model(model_in, levels, cond, cond_mask, out_dtype=torch.float32)
+        from dfot_b200 import distributed as D
+        rows = torch.tensor(D.branch_rows(B, nfe, bg), device=model_in.device)
+        sel = lambda t: None if t is None else t.index_select(0, rows)
+        local = dm.model(sel(model_in), sel(levels), sel(cond), sel(cond_mask), out_dtype=torch.float32)
+        return D.gather_branch_outputs(local, B, nfe, bg)
+
+    @torch.no_grad()
+    def sample_sharded(self, xs: Tensor, conditions: Optional[Tensor] = None,
+                       n_context_tokens: Optional[int] = None) -> Tensor:
+        """`_predict_videos` over the dp x br mesh: this rank's sample shard is rolled out (branch rows split inside
+        its branch group) and the finished samples of all shards are all-gathered; every rank returns the full batch.
+        xs / conditions hold the FULL batch on every rank (synthetic or broadcast by the caller)."""
+        from dfot_b200 import distributed as D
+        mesh = self.mesh
+        n_ctx = n_context_tokens if n_context_tokens is not None else self.n_context_tokens
+        if mesh is None:
+            return self._predict_videos(xs, n_ctx, conditions)
+        counts = [len(range(*D.shard_batch(xs.shape[0], mesh.dp, d).indices(xs.shape[0]))) for d in range(mesh.dp)]
+        sl = D.shard_batch(xs.shape[0], mesh.dp, mesh.dp_index)
+        if sl.stop > sl.start:
+            local = self._predict_videos(xs[sl].contiguous(), n_ctx, None if conditions is None else conditions[sl])
+        else:   # more shards than samples: this rank only takes part in the final gather
+            local = xs[sl].clone()
+        return D.gather_samples(local.contiguous(), mesh, counts)
+
     # ------------------------------------------------------------------ window planning (host only)
     def plan_window(self, mask: np.ndarray, horizon: int, padding: int,
                     history_guidance: HistoryGuidance) -> List[sp.StepPlan]:
@@ -317,7 +351,7 @@ class DFoTVideo(BaseVideoAlgo):
                 nh, ne = draw_prepare_noise(p)
                 model_in = torch.empty((B * p.nfe, T, *x_shape), dtype=self.model_in_dtype, device=dev)
                 ops.sampler_step_hg(x, None, model_in, None, prep_dev[0], None, nh, ne, B, p.nfe, T)
-            out = dm.model(model_in, lvl_dev[m], cond_for(p.nfe), cm_dev[m], out_dtype=torch.float32)
+            out = self._backbone_rows(model_in, lvl_dev[m], cond_for(p.nfe), cm_dev[m], B, p.nfe)
             self.nfe_rows += B * p.nfe
             # RNG ③: DDIM noise — drawn even when eta == 0 to keep the stream aligned with the reference
             nd = dm.clipped_noise((B * p.nfe, T, *x_shape), dev)
