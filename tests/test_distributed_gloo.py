@@ -56,15 +56,22 @@ def _worker(rank, world, port, case, br, out_path):
 
 
 def _single(case, shard_starts):
-    algo, cfg, xs, conds, NoiseBank = _build(case)
-    outs = []
-    for a, b in zip(shard_starts[:-1], shard_starts[1:]):
-        if a == b:
-            continue
-        bank = NoiseBank(100 + a)
-        algo.diffusion_model.noise_source = lambda shape, device, bank=bank: bank.randn(shape)
-        outs.append(algo._predict_videos(xs[a:b].contiguous(), cfg["context_frames"], None if conds is None else conds[a:b]))
-    return torch.cat(outs, 0).numpy()
+    sys.path.insert(0, ROOT)
+    from dfot_b200 import ops
+    real_op = ops.sampler_step_hg
+    try:
+        algo, cfg, xs, conds, NoiseBank = _build(case)   # patches ops.sampler_step_hg in this process
+        outs = []
+        for a, b in zip(shard_starts[:-1], shard_starts[1:]):
+            if a == b:
+                continue
+            bank = NoiseBank(100 + a)
+            algo.diffusion_model.noise_source = lambda shape, device, bank=bank: bank.randn(shape)
+            outs.append(algo._predict_videos(xs[a:b].contiguous(), cfg["context_frames"],
+                                             None if conds is None else conds[a:b]))
+        return torch.cat(outs, 0).numpy()
+    finally:
+        ops.sampler_step_hg = real_op
 
 
 @pytest.mark.parametrize("case,br", [("vanilla", 1), ("vanilla", 2), ("continuous_action", 2), ("temporal", 1)])
