@@ -263,10 +263,10 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         run_resident()
-    n0 = _abi.launch_count()
+    n0 = ops.total_launches()
     with ClockSampler(local_rank) as clocks:
         ms = timed(run_resident, args.steps)
-    launches = _abi.launch_count() - n0
+    launches = ops.total_launches() - n0
     run_e2e()
     ms_e2e = timed(run_e2e, args.steps)
 
@@ -285,11 +285,15 @@ def main():
             recs.append((2.0 * M * w.shape[0] * w.shape[1], e0, e1))
 
         ops.gemm_bf16 = timed_gemm
+        backbone = algo.diffusion_model.model
+        graphs_on = backbone.use_cuda_graph
+        backbone.use_cuda_graph = False          # per-launch events need eager launches
         try:
             run_resident()
             torch.cuda.synchronize()
         finally:
             ops.gemm_bf16 = ops_gemm
+            backbone.use_cuda_graph = graphs_on
         big = [(f, a.elapsed_time(b)) for f, a, b in recs if f > 1e9]
         flops, dur = sum(f for f, _ in big), sum(d for _, d in big)
         peaks = {}
@@ -321,6 +325,7 @@ def main():
                     e2e=dict(value=frames / per_e2e_s, unit="generated_frames/s", h2d_bytes_per_step=bytes_in,
                              d2h_bytes_per_step=bytes_in, nfe_per_sec=rows / per_e2e_s),
                     gpu_launches=int(launches), clocks=clocks.summary(), roofline=roof)
+        line["config"]["cuda_graph"] = bool(algo.diffusion_model.model.use_cuda_graph)
         if not args.skip_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(cfg)
         print(json.dumps(line))

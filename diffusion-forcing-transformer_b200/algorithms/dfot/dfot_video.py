@@ -212,6 +212,15 @@ class DFoTVideo(BaseVideoAlgo):
             cur = xs.shape[1]
         return xs, record
 
+    def _model_in_buffer(self, rows: int, T: int, dev) -> Tensor:
+        """Branch-input tensor the fused sampler kernel writes into: the backbone's static (graph-captured) input
+        when it offers one, so no copy sits between K4 and the forward."""
+        model = self.diffusion_model.model
+        bg = self.mesh.branch_group if self.mesh is not None else None
+        if hasattr(model, "input_buffer") and bg is None:
+            return model.input_buffer(rows, T, self.model_in_dtype, dev)
+        return torch.empty((rows, T, *self.x_shape), dtype=self.model_in_dtype, device=dev)
+
     # ------------------------------------------------------------------ multi-GPU (SURVEY.md §8e)
     def _backbone_rows(self, model_in, levels, cond, cond_mask, B: int, nfe: int):
         """Backbone forward over the (b, j) branch rows; with a branch group each member runs its share of the
@@ -349,7 +358,7 @@ class DFoTVideo(BaseVideoAlgo):
                 record.append(x.clone())
             if m == 0:
                 nh, ne = draw_prepare_noise(p)
-                model_in = torch.empty((B * p.nfe, T, *x_shape), dtype=self.model_in_dtype, device=dev)
+                model_in = self._model_in_buffer(B * p.nfe, T, dev)
                 ops.sampler_step_hg(x, None, model_in, None, prep_dev[0], None, nh, ne, B, p.nfe, T)
             out = self._backbone_rows(model_in, lvl_dev[m], cond_for(p.nfe), cm_dev[m], B, p.nfe)
             self.nfe_rows += B * p.nfe
@@ -362,8 +371,7 @@ class DFoTVideo(BaseVideoAlgo):
                 ops.sampler_step_hg(x, out, None, upd_dev[m], None, nd, None, None, B, p.nfe, T)
             else:
                 nh, ne = draw_prepare_noise(nxt)
-                nxt_in = model_in if nxt.nfe == p.nfe else torch.empty((B * nxt.nfe, T, *x_shape),
-                                                                       dtype=self.model_in_dtype, device=dev)
+                nxt_in = model_in if nxt.nfe == p.nfe else self._model_in_buffer(B * nxt.nfe, T, dev)
                 if nxt.nfe == p.nfe:   # one fused launch: update + combine + revert + next-step prepare
                     ops.sampler_step_hg(x, out, nxt_in, upd_dev[m], prep_dev[m + 1], nd, nh, ne, B, p.nfe, T)
                 else:                  # branch count changes between steps: split into update and prepare launches

@@ -15,6 +15,21 @@ from ._abi import (BF16, EPI_BF16, EPI_F32, EPI_GATE_RESID_F32, EPI_GELU_BF16, E
 _DTYPE_TAG = {torch.float32: F32, torch.bfloat16: BF16, torch.int64: I64}
 
 
+_replayed_launches = 0
+
+
+def count_replayed_launches(n: int) -> None:
+    """Kernels of this library that ran through a CUDA-graph replay (they bypass the C-ABI launch counter)."""
+    global _replayed_launches
+    _replayed_launches += n
+
+
+def total_launches() -> int:
+    """Kernels of this library launched so far: direct C-ABI launches + kernels inside replayed graphs
+    (the capture itself is counted once by the C-ABI counter and executes nothing)."""
+    return _abi.launch_count() + _replayed_launches
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
