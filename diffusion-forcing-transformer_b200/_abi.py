@@ -7,12 +7,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdfot_b200.so")
 
 F32, BF16, I64 = 0, 1, 2
-EPI_F32, EPI_BF16, EPI_GELU_BF16, EPI_SILU_BF16, EPI_GATE_RESID_F32, EPI_QKV_ROPE_BF16 = range(6)
+EPI_F32, EPI_BF16, EPI_GELU_BF16, EPI_SILU_BF16, EPI_GATE_RESID_F32, EPI_QKV_ROPE_BF16, EPI_RESID_F32 = range(7)
 
 SYMBOLS = [
     "dfot_abi_version", "dfot_last_error", "dfot_launch_count", "dfot_sampler_step_hg", "dfot_adaln_layernorm",
     "dfot_gemm_bf16", "dfot_attention", "dfot_noise_features", "dfot_silu_sum_bf16", "dfot_patchify_bf16",
-    "dfot_unpatchify", "dfot_cast_bf16",
+    "dfot_unpatchify", "dfot_cast_bf16", "dfot_conv3x3_bf16", "dfot_groupnorm_stats", "dfot_groupnorm_silu_bf16",
+    "dfot_rmsnorm_film_bf16", "dfot_qk_norm_rope", "dfot_avgpool2x2", "dfot_sub_bf16", "dfot_upsample2x_add",
+    "dfot_pose_ray_patches",
 ]
 
 
@@ -63,6 +65,16 @@ def lib() -> ctypes.CDLL:
     L.dfot_patchify_bf16.argtypes = [vp, i, vp, i64, i64, i64, i64, i64, i64, vp]
     L.dfot_unpatchify.argtypes = [vp, i64, vp, i, i64, i64, i64, i64, i64, vp]
     L.dfot_cast_bf16.argtypes = [vp, vp, i64, vp]
+    L.dfot_conv3x3_bf16.argtypes = [vp, vp, vp, i64, i64, i64, i64, i64, i64, i, POINTER(GemmEpilogue), vp]
+    L.dfot_groupnorm_stats.argtypes = [vp, i, vp, i64, i64, i64, i64, vp]
+    L.dfot_groupnorm_silu_bf16.argtypes = [vp, i, vp, vp, vp, c_float, vp, i64, i64, i64, vp, vp, vp, i64, i64, i64,
+                                           i64, vp]
+    L.dfot_rmsnorm_film_bf16.argtypes = [vp, vp, c_float, vp, i64, i64, i64, vp, vp, vp, i64, i64, i64, vp]
+    L.dfot_qk_norm_rope.argtypes = [vp, i64, vp, vp, c_float, vp, i64, i64, i64, i64, c_float, vp]
+    L.dfot_avgpool2x2.argtypes = [vp, i, vp, i, i64, i64, i64, i64, vp]
+    L.dfot_sub_bf16.argtypes = [vp, vp, vp, i64, vp]
+    L.dfot_upsample2x_add.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp]
+    L.dfot_pose_ray_patches.argtypes = [vp, vp, i64, vp, i64, i64, i64, i64, vp]
     for name in SYMBOLS:
         if name not in ("dfot_last_error", "dfot_launch_count"):
             getattr(L, name).restype = c_int

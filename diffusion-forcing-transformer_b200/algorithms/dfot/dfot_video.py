@@ -212,6 +212,10 @@ class DFoTVideo(BaseVideoAlgo):
             cur = xs.shape[1]
         return xs, record
 
+    def _window_conditions(self, conditions: Tensor, nfe: int):
+        """Conditioning of all branch rows `(b h g)` of one window (rows of a sample share its conditions)."""
+        return self._process_conditions(conditions.repeat_interleave(nfe, dim=0).clone(), None)
+
     def _model_in_buffer(self, rows: int, T: int, dev) -> Tensor:
         """Branch-input tensor the fused sampler kernel writes into: the backbone's static (graph-captured) input
         when it offers one, so no copy sits between K4 and the forward."""
@@ -340,8 +344,7 @@ class DFoTVideo(BaseVideoAlgo):
             if conditions is None:
                 return None
             if nfe not in cond_cache:   # constant over the window (the reference recomputes it every step, :732-743)
-                cond_cache[nfe] = self._process_conditions(
-                    conditions.to(dev).repeat_interleave(nfe, dim=0).clone(), None)
+                cond_cache[nfe] = self._window_conditions(conditions.to(dev), nfe)
             return cond_cache[nfe]
 
         def draw_prepare_noise(p: sp.StepPlan):

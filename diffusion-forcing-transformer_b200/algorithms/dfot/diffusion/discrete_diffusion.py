@@ -16,7 +16,7 @@ from torch import nn
 from dfot_b200 import ops
 from dfot_b200.config import to_config
 from .. import sampling_plan as sp
-from ..backbones import DiT3D
+from ..backbones import DiT3D, UViT3DPose
 from .noise_schedule import make_beta_schedule
 
 ModelPrediction = namedtuple("ModelPrediction", ["pred_noise", "pred_x_start", "model_out"])
@@ -55,7 +55,9 @@ class DiscreteDiffusion(nn.Module):
         name = self.backbone_cfg.name
         if name == "dit3d":
             model_cls = DiT3D
-        elif name in ("u_net3d", "u_vit3d", "u_vit3d_pose", "dit3d_pose", "far_dit", "dit1d", "difference_dit3d"):
+        elif name == "u_vit3d_pose":
+            model_cls = UViT3DPose
+        elif name in ("u_net3d", "u_vit3d", "dit3d_pose", "far_dit", "dit1d", "difference_dit3d"):
             raise NotImplementedError(f"backbone `{name}` is not implemented by dfot_b200 yet (see DESIGN.md scope)")
         else:
             raise ValueError(f"unknown model type {name}")

@@ -40,6 +40,11 @@ struct Params {
   void* C;
   int64_t ldc;
   dfot_gemm_epilogue e;
+  // implicit-GEMM 3x3 convolution over NHWC activations (conv_cblks == 0: plain GEMM).  K = 9 taps x Cin; the A tile
+  // of tap (dy, dx) is the pixel tile shifted by (dy, dx), fetched by a 4-D TMA whose out-of-bounds zero fill IS
+  // the convolution's zero padding.
+  int conv_cblks;   // ceil(Cin / 64)
+  int conv_W, conv_H;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -94,6 +99,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
@@ -196,7 +214,7 @@ template <int EPI> struct ChunkSide {
 
 template <int EPI, bool FULL>
 __device__ __forceinline__ void prefetch_side(const Params& p, ChunkSide<EPI>& sd, int lane, int m0, int n0) {
-  if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) {
+  if constexpr (EPI == DFOT_EPI_GATE_RESID_F32 || EPI == DFOT_EPI_RESID_F32) {
     const int col = n0 + lane;
     const float* res = p.e.resid + (int64_t)m0 * p.e.ld_resid + col;
     if constexpr (FULL) {
@@ -266,6 +284,7 @@ __device__ __forceinline__ void epilogue_rows_f32(const Params& p, const ChunkSi
     const float acc = lds_f32(sbase + (uint32_t)i * 128u + (uint32_t)((((lane >> 2) ^ (i & 7))) << 4));
     float y = acc + bias;
     if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) y = sd.v[i] + (i < split ? gate0 : gate1) * y;
+    if constexpr (EPI == DFOT_EPI_RESID_F32) y = sd.v[i] + y;
     if (FULL || (col_ok && i < rows)) out[(int64_t)i * p.ldc] = y;
   }
 }
@@ -345,7 +364,7 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, uint32_t t_addr,
   tmem_ld_x32(t_addr, r);
   stage_chunk(stage_buf, lane, r);
   __syncwarp();
-  if constexpr (EPI == DFOT_EPI_F32 || EPI == DFOT_EPI_GATE_RESID_F32)
+  if constexpr (EPI == DFOT_EPI_F32 || EPI == DFOT_EPI_GATE_RESID_F32 || EPI == DFOT_EPI_RESID_F32)
     epilogue_rows_f32<EPI, FULL>(p, side, stage_buf, lane, m0, n0);
   else
     epilogue_rows_bf16<EPI, FULL>(p, side, stage_buf, lane, m0, n0);
@@ -372,7 +391,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_kb = p.conv_cblks > 0 ? 9 * p.conv_cblks : (p.K + BK - 1) / BK;
   // banded rasterisation: consecutive tiles walk the n-blocks of a band of kRasterBand m-blocks, so the CTAs
   // resident at any time share a small set of A and W tiles in L2
   auto tile_coord = [&](int tile, int& m_blk, int& n_blk) {
@@ -412,13 +431,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m_blk, n_blk;
         tile_coord(tile, m_blk, n_blk);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), C::kStageBytes);
-          const uint32_t sa = smem_base + stage * C::kStageBytes;
-          tma_load_2d(sa, &tma_a, full_bar(stage), kb * BK, m_blk * BM);
-          tma_load_2d(sa + C::kStageBytesA, &tma_b, full_bar(stage), kb * BK, n_blk * BN);
-          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        if (p.conv_cblks == 0) {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), C::kStageBytes);
+            const uint32_t sa = smem_base + stage * C::kStageBytes;
+            tma_load_2d(sa, &tma_a, full_bar(stage), kb * BK, m_blk * BM);
+            tma_load_2d(sa + C::kStageBytesA, &tma_b, full_bar(stage), kb * BK, n_blk * BN);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          }
+        } else {
+          // pixel tile origin (the 128 rows of a tile are bw x bh x bn pixels; host guarantees the divisibility)
+          const int m0 = m_blk * BM;
+          const int x0 = m0 % p.conv_W, y0 = (m0 / p.conv_W) % p.conv_H, img0 = m0 / (p.conv_W * p.conv_H);
+          int tap = 0, cb = 0;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), C::kStageBytes);
+            const uint32_t sa = smem_base + stage * C::kStageBytes;
+            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            tma_load_4d(sa, &tma_a, full_bar(stage), cb * BK, x0 + dx, y0 + dy, img0);
+            tma_load_3d(sa + C::kStageBytesA, &tma_b, full_bar(stage), cb * BK, tap, n_blk * BN);
+            if (++cb == p.conv_cblks) { cb = 0; ++tap; }
+            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          }
         }
       }
     }
@@ -525,6 +561,19 @@ static int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t co
   return DFOT_OK;
 }
 
+// bf16 tensor of `rank` dims (dim 0 contiguous), box[0] = 64 elements = one 128-byte swizzle atom
+static int make_tmap_nd(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* gdim, const cuuint64_t* gstr_bytes,
+                        const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode_fn();
+  DFOT_REQUIRE(enc != nullptr, DFOT_ERR_DRIVER, "conv: cuTensorMapEncodeTiled unavailable from the driver");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstr_bytes,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DFOT_REQUIRE(r == CUDA_SUCCESS, DFOT_ERR_DRIVER, "conv: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return DFOT_OK;
+}
+
 static int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -563,6 +612,7 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
     case DFOT_EPI_SILU_BF16: return launch<BN, DFOT_EPI_SILU_BF16>(ta, tb, p, s);
     case DFOT_EPI_GATE_RESID_F32: return launch<BN, DFOT_EPI_GATE_RESID_F32>(ta, tb, p, s);
     case DFOT_EPI_QKV_ROPE_BF16: return launch<BN, DFOT_EPI_QKV_ROPE_BF16>(ta, tb, p, s);
+    case DFOT_EPI_RESID_F32: return launch<BN, DFOT_EPI_RESID_F32>(ta, tb, p, s);
   }
   set_error("gemm: unknown epilogue %d", epi);
   return DFOT_ERR_INVALID_ARG;
@@ -590,12 +640,15 @@ extern "C" int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   if (epilogue == DFOT_EPI_GATE_RESID_F32)
     DFOT_REQUIRE(epi->resid && epi->gate && epi->tokens_per_frame >= 1 && epi->tokens_per_frame < (1ll << 30),
                  DFOT_ERR_INVALID_ARG, "gemm: GATE_RESID needs resid, gate and tokens_per_frame");
+  if (epilogue == DFOT_EPI_RESID_F32)
+    DFOT_REQUIRE(epi->resid != nullptr && epi->ld_resid >= N, DFOT_ERR_INVALID_ARG, "gemm: RESID needs resid");
   if (epilogue == DFOT_EPI_QKV_ROPE_BF16)
     DFOT_REQUIRE(epi->rope_cs && epi->tokens_per_sample > 0 && epi->head_dim > 0 && epi->head_dim % 2 == 0 &&
                      epi->model_dim > 0 && epi->model_dim % epi->head_dim == 0 && N == 3 * epi->model_dim,
                  DFOT_ERR_INVALID_ARG, "gemm: QKV_ROPE needs rope table, tokens_per_sample, head_dim | model_dim, N=3D");
   Params p;
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.C = Cout; p.ldc = ldc; p.e = *epi;
+  p.conv_cblks = 0; p.conv_W = p.conv_H = 1;
   CUtensorMap ta, tb;
   int rc = make_tmap(&ta, A, M, K, lda, BM);
   if (rc) return rc;
@@ -610,4 +663,69 @@ extern "C" int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   }
   rc = make_tmap(&tb, W, N, K, ldw, 64);
   return rc ? rc : dispatch_epi<64>(epilogue, ta, tb, p, s);
+}
+
+// 3x3 convolution, stride 1, zero padding 1, over NHWC bf16 activations as an implicit GEMM on the same kernel:
+// M = n_img*H*W pixels, N = Cout, K = 9*Cin.  No im2col buffer exists: tap (dy, dx) of a pixel tile is the tile's
+// TMA box moved by (dy, dx); rows/columns that fall outside the image are zero-filled by the TMA unit.
+extern "C" int dfot_conv3x3_bf16(const void* x, const void* w, void* out, int64_t ldc, int64_t n_img, int64_t H,
+                                 int64_t W, int64_t Cin, int64_t Cout, int epilogue, const dfot_gemm_epilogue* epi,
+                                 void* stream) {
+  using namespace dfot;
+  using namespace dfot::gemm;
+  DFOT_REQUIRE(x && w && out && epi, DFOT_ERR_INVALID_ARG, "conv3x3: null pointer");
+  DFOT_REQUIRE(n_img > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && n_img * H * W < (1ll << 31),
+               DFOT_ERR_INVALID_ARG, "conv3x3: bad sizes");
+  DFOT_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0 && ldc % 8 == 0 && ldc >= Cout, DFOT_ERR_UNSUPPORTED,
+               "conv3x3: Cin, Cout, ldc must be multiples of 8; got %lld %lld %lld", (long long)Cin, (long long)Cout,
+               (long long)ldc);
+  DFOT_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)w % 16 == 0) && ((uintptr_t)out % 16 == 0),
+               DFOT_ERR_UNSUPPORTED, "conv3x3: x, w, out must be 16-byte aligned");
+  DFOT_REQUIRE(epilogue == DFOT_EPI_F32 || epilogue == DFOT_EPI_BF16 || epilogue == DFOT_EPI_RESID_F32 ||
+                   epilogue == DFOT_EPI_SILU_BF16,
+               DFOT_ERR_UNSUPPORTED, "conv3x3: epilogue %d unsupported", epilogue);
+  if (epilogue == DFOT_EPI_RESID_F32)
+    DFOT_REQUIRE(epi->resid != nullptr && epi->ld_resid >= Cout, DFOT_ERR_INVALID_ARG, "conv3x3: RESID needs resid");
+  // tile = bw x bh x bn pixels = 128 GEMM rows in (img, y, x) order
+  const bool pow2w = (W & (W - 1)) == 0, pow2h = (H & (H - 1)) == 0;
+  int64_t bw, bh, bn;
+  if (W >= BM) {
+    DFOT_REQUIRE(W % BM == 0, DFOT_ERR_UNSUPPORTED, "conv3x3: W=%lld must be a multiple of 128 or a power of two",
+                 (long long)W);
+    bw = BM; bh = 1; bn = 1;
+  } else {
+    DFOT_REQUIRE(pow2w, DFOT_ERR_UNSUPPORTED, "conv3x3: W=%lld must be a power of two below 128", (long long)W);
+    bw = W;
+    if (H * W >= BM) {
+      DFOT_REQUIRE(H % (BM / W) == 0, DFOT_ERR_UNSUPPORTED, "conv3x3: H=%lld must be a multiple of %lld",
+                   (long long)H, (long long)(BM / W));
+      bh = BM / W; bn = 1;
+    } else {
+      DFOT_REQUIRE(pow2h, DFOT_ERR_UNSUPPORTED, "conv3x3: H=%lld must be a power of two for small images", (long long)H);
+      bh = H; bn = BM / (W * H);
+    }
+  }
+  Params p;
+  p.M = (int)(n_img * H * W); p.N = (int)Cout; p.K = (int)(9 * Cin); p.C = out; p.ldc = ldc; p.e = *epi;
+  p.conv_cblks = (int)ceil_div(Cin, BK); p.conv_W = (int)W; p.conv_H = (int)H;
+  CUtensorMap ta, tb;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
+    cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+    int rc = make_tmap_nd(&ta, x, 4, gdim, gstr, box);
+    if (rc) return rc;
+  }
+  const int bnt = Cout > 128 ? 256 : (Cout > 64 ? 128 : 64);
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)Cin, 9, (cuuint64_t)Cout};
+    cuuint64_t gstr[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)9 * Cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, 1, (cuuint32_t)bnt};
+    int rc = make_tmap_nd(&tb, w, 3, gdim, gstr, box);
+    if (rc) return rc;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (bnt == 256) return dispatch_epi<256>(epilogue, ta, tb, p, s);
+  if (bnt == 128) return dispatch_epi<128>(epilogue, ta, tb, p, s);
+  return dispatch_epi<64>(epilogue, ta, tb, p, s);
 }

@@ -1,0 +1,494 @@
+// HBM-bound kernels of the U-ViT3DPose backbone (channel-last activations everywhere):
+//   GroupNorm statistics / GroupNorm+FiLM+SiLU apply, RMSNorm+FiLM, q/k RMSNorm + RoPE-3D, 2x2 average pooling,
+//   nearest-2x upsample + skip add, subtraction, camera-ray encoding straight into PatchEmbed rows.
+// Every kernel reads each input element once and writes each output element once with 128-bit accesses.
+#include "common.cuh"
+
+namespace dfot {
+namespace uvit {
+
+constexpr int kThreads = 256;
+
+// ---- 8-channel vector load/store helpers (f32: 2 x 16 B, bf16: 1 x 16 B) ----
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const uint4 a = ld_stream_u4(p), b = ld_stream_u4(p + 4);
+  v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
+  v[4] = __uint_as_float(b.x); v[5] = __uint_as_float(b.y); v[6] = __uint_as_float(b.z); v[7] = __uint_as_float(b.w);
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 a = ld_stream_u4(p);
+  float2 t;
+  t = unpack_bf16x2(a.x); v[0] = t.x; v[1] = t.y;
+  t = unpack_bf16x2(a.y); v[2] = t.x; v[3] = t.y;
+  t = unpack_bf16x2(a.z); v[4] = t.x; v[5] = t.y;
+  t = unpack_bf16x2(a.w); v[6] = t.x; v[7] = t.y;
+}
+// cached (re-read) variants for small tables
+__device__ __forceinline__ void ldg8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  st_stream_u4(p, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                             pack_bf16x2(v[6], v[7])));
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  st_stream_u4(p, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
+  st_stream_u4(p + 4, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
+}
+
+// ------------------------------------------------------------------ GroupNorm statistics
+// grid (slabs, n_img); a thread owns one 8-channel vector (fixed) and walks the slab's pixels.
+template <typename TX>
+__global__ void __launch_bounds__(kThreads)
+gn_stats_kernel(const TX* __restrict__ x, double* __restrict__ sums, int64_t HW, int C, int G, int pix_per_block) {
+  __shared__ float s_sum[64], s_sq[64];
+  const int vecs = C >> 3, cpg = C / G;
+  const int img = blockIdx.y;
+  if (threadIdx.x < 64) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+  __syncthreads();
+  const int v = threadIdx.x % vecs, lane_pix = threadIdx.x / vecs, pix_step = kThreads / vecs;
+  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
+  const int64_t p1 = min(HW, p0 + pix_per_block);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  if (lane_pix < pix_step) {
+    for (int64_t pix = p0 + lane_pix; pix < p1; pix += pix_step) {
+      float a[8];
+      load8(x + ((int64_t)img * HW + pix) * C + 8 * v, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += a[j]; q[j] = fmaf(a[j], a[j], q[j]); }
+    }
+  }
+  if (cpg % 8 == 0) {   // the whole vector lies in one group
+    float ts = 0.f, tq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ts += s[j]; tq += q[j]; }
+    atomicAdd(&s_sum[(8 * v) / cpg], ts);
+    atomicAdd(&s_sq[(8 * v) / cpg], tq);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&s_sum[(8 * v + j) / cpg], s[j]);
+      atomicAdd(&s_sq[(8 * v + j) / cpg], q[j]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    atomicAdd(&sums[((int64_t)img * G + threadIdx.x) * 2], (double)s_sum[threadIdx.x]);
+    atomicAdd(&sums[((int64_t)img * G + threadIdx.x) * 2 + 1], (double)s_sq[threadIdx.x]);
+  }
+}
+
+__device__ __forceinline__ void gn_mean_rstd(const double* __restrict__ sums, int64_t idx, double inv_n, float eps,
+                                             float& mean, float& rstd) {
+  const double s = sums[idx * 2], q = sums[idx * 2 + 1];
+  const double m = s * inv_n;
+  const double var = fmax(q * inv_n - m * m, 0.0);
+  mean = (float)m;
+  rstd = rsqrtf((float)var + eps);
+}
+
+// ------------------------------------------------------------------ GroupNorm (+FiLM) + SiLU -> bf16
+template <typename TX>
+__global__ void __launch_bounds__(kThreads)
+gn_silu_kernel(const TX* __restrict__ x, const double* __restrict__ sums, const float* __restrict__ gamma,
+               const float* __restrict__ beta, float eps, const float* __restrict__ mod_img, int64_t ld_img,
+               int64_t scale_col, int64_t shift_col, const __nv_bfloat16* __restrict__ mod_pix,
+               const int32_t* __restrict__ img_map, __nv_bfloat16* __restrict__ y, int64_t n_img, int64_t HW, int C,
+               int G) {
+  const int vecs = C >> 3, cpg = C / G;
+  const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (idx >= n_img * HW * vecs) return;
+  const int v = (int)(idx % vecs);
+  const int64_t m = idx / vecs;
+  const int64_t img = m / HW, pix = m - img * HW;
+  const int c0 = 8 * v;
+  float a[8], ga[8], be[8];
+  load8(x + m * C + c0, a);
+  ldg8(gamma + c0, ga);
+  ldg8(beta + c0, be);
+  const double inv_n = 1.0 / ((double)HW * (double)cpg);
+  if (cpg % 8 == 0) {
+    float mean, rstd;
+    gn_mean_rstd(sums, img * G + c0 / cpg, inv_n, eps, mean, rstd);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = (a[j] - mean) * rstd * ga[j] + be[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float mean, rstd;
+      gn_mean_rstd(sums, img * G + (c0 + j) / cpg, inv_n, eps, mean, rstd);
+      a[j] = (a[j] - mean) * rstd * ga[j] + be[j];
+    }
+  }
+  if (mod_img != nullptr) {
+    float sc[8], sh[8];
+    ldg8(mod_img + img * ld_img + scale_col + c0, sc);
+    ldg8(mod_img + img * ld_img + shift_col + c0, sh);
+    const int32_t src = (mod_pix != nullptr && img_map != nullptr) ? __ldg(img_map + img) : -1;
+    if (src >= 0) {
+      float ps[8], ph[8];
+      const __nv_bfloat16* row = mod_pix + ((int64_t)src * HW + pix) * (2 * C);
+      load8(row + c0, ps);
+      load8(row + C + c0, ph);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sc[j] += ps[j]; sh[j] += ph[j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = fmaf(a[j], 1.f + sc[j], sh[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = silu_f(a[j]);
+  store8(y + m * C + c0, a);
+}
+
+// ------------------------------------------------------------------ RMSNorm + FiLM -> bf16 (warp per token)
+constexpr int kNormWarps = 4;
+template <int NV>
+__global__ void __launch_bounds__(kNormWarps * 32)
+rmsnorm_film_kernel(const float* __restrict__ x, const float* __restrict__ weight, float eps,
+                    const float* __restrict__ mod_img, int64_t ld_img, int64_t scale_col, int64_t shift_col,
+                    const __nv_bfloat16* __restrict__ mod_pix, const int32_t* __restrict__ img_map,
+                    __nv_bfloat16* __restrict__ y, int64_t M, int D, int64_t tokens_per_img) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m = (int64_t)blockIdx.x * kNormWarps + warp;
+  if (m >= M) return;
+  const int nvec = D >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + m * D);
+  float4 v[NV];
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      const uint4 u = ld_stream_u4(xr + c);
+      v[i] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+      sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+  const int64_t img = m / tokens_per_img, pix = m - img * tokens_per_img;
+  const float4* sc = reinterpret_cast<const float4*>(mod_img + img * ld_img + scale_col);
+  const float4* sh = reinterpret_cast<const float4*>(mod_img + img * ld_img + shift_col);
+  const float4* wr = reinterpret_cast<const float4*>(weight);
+  const int32_t src = (mod_pix != nullptr && img_map != nullptr) ? __ldg(img_map + img) : -1;
+  const __nv_bfloat16* prow = src >= 0 ? mod_pix + ((int64_t)src * tokens_per_img + pix) * (2 * D) : nullptr;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      float4 g = __ldg(sc + c), s = __ldg(sh + c);
+      const float4 w = __ldg(wr + c);
+      if (prow != nullptr) {
+        const uint2 ps = ld_stream_u2(prow + 4 * c), ph = ld_stream_u2(prow + D + 4 * c);
+        const float2 a = unpack_bf16x2(ps.x), b = unpack_bf16x2(ps.y), e = unpack_bf16x2(ph.x), f = unpack_bf16x2(ph.y);
+        g.x += a.x; g.y += a.y; g.z += b.x; g.w += b.y;
+        s.x += e.x; s.y += e.y; s.z += f.x; s.w += f.y;
+      }
+      float4 o;
+      o.x = fmaf(v[i].x * rstd * w.x, 1.f + g.x, s.x);
+      o.y = fmaf(v[i].y * rstd * w.y, 1.f + g.y, s.y);
+      o.z = fmaf(v[i].z * rstd * w.z, 1.f + g.z, s.z);
+      o.w = fmaf(v[i].w * rstd * w.w, 1.f + g.w, s.w);
+      st_stream_u2(y + m * D + 4 * c, make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w)));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ q/k RMSNorm(head_dim) + RoPE-3D, in place
+// one warp per (token, head, q|k); a lane owns EPL = DH/32 adjacent elements = EPL/2 rotation pairs
+template <int DH>
+__global__ void __launch_bounds__(kThreads)
+qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, const float* __restrict__ qw,
+                    const float* __restrict__ kw, float eps, const float* __restrict__ rope_cs,
+                    int64_t tokens_per_sample, int64_t M, int heads, float q_scale) {
+  constexpr int EPL = DH / 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (wid >= M * heads * 2) return;
+  const int which = (int)(wid % 2);           // 0 = q, 1 = k
+  const int head = (int)((wid / 2) % heads);
+  const int64_t m = wid / (2 * heads);
+  __nv_bfloat16* p = qkv + m * ld + (int64_t)which * heads * DH + head * DH + lane * EPL;
+  float e[EPL];
+  if constexpr (EPL == 2) {
+    const float2 t = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p));
+    e[0] = t.x; e[1] = t.y;
+  } else {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    e[0] = a.x; e[1] = a.y; e[2] = b.x; e[3] = b.y;
+  }
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) sq = fmaf(e[j], e[j], sq);
+  const float rstd = rsqrtf(warp_sum(sq) / (float)DH + eps);
+  const float* w = (which == 0 ? qw : kw) + lane * EPL;
+  const float mul = which == 0 ? q_scale : 1.f;
+  const int64_t tok = m % tokens_per_sample;
+  const float2* cs = reinterpret_cast<const float2*>(rope_cs) + tok * (DH / 2) + lane * (EPL / 2);
+#pragma unroll
+  for (int j = 0; j < EPL; j += 2) {
+    const float x0 = e[j] * rstd * __ldg(w + j), x1 = e[j + 1] * rstd * __ldg(w + j + 1);
+    const float2 c = __ldg(cs + j / 2);
+    e[j] = (x0 * c.x - x1 * c.y) * mul;
+    e[j + 1] = (x1 * c.x + x0 * c.y) * mul;
+  }
+  if constexpr (EPL == 2) {
+    *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(e[0], e[1]);
+  } else {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]));
+  }
+}
+
+// ------------------------------------------------------------------ pooling / upsampling / subtraction
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(kThreads)
+avgpool2x2_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t n_img, int H, int W, int C) {
+  const int vecs = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (idx >= n_img * Ho * Wo * vecs) return;
+  const int v = (int)(idx % vecs);
+  int64_t t = idx / vecs;
+  const int xo = (int)(t % Wo); t /= Wo;
+  const int yo = (int)(t % Ho);
+  const int64_t img = t / Ho;
+  const TI* base = in + (((img * H + 2 * yo) * W + 2 * xo) * (int64_t)C) + 8 * v;
+  float a[8], b[8], c[8], d[8], o[8];
+  load8(base, a);
+  load8(base + C, b);
+  load8(base + (int64_t)W * C, c);
+  load8(base + (int64_t)W * C + C, d);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = (((a[j] + b[j]) + c[j]) + d[j]) * 0.25f;
+  store8(out + (((img * Ho + yo) * Wo + xo) * (int64_t)C) + 8 * v, o);
+}
+
+__global__ void __launch_bounds__(kThreads)
+sub_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b, __nv_bfloat16* __restrict__ out, int64_t n8) {
+  const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (idx >= n8) return;
+  float x[8], y[8];
+  load8(a + idx * 8, x);
+  load8(b + idx * 8, y);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x[j] -= y[j];
+  store8(out + idx * 8, x);
+}
+
+// out (H x W) = nearest-2x(low (H/2 x W/2)) + skip (H x W)
+__global__ void __launch_bounds__(kThreads)
+upsample2x_add_kernel(const float* __restrict__ low, const float* __restrict__ skip, float* __restrict__ out,
+                      int64_t n_img, int H, int W, int C) {
+  const int vecs = C >> 3;
+  const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (idx >= n_img * H * W * vecs) return;
+  const int v = (int)(idx % vecs);
+  int64_t t = idx / vecs;
+  const int x = (int)(t % W); t /= W;
+  const int y = (int)(t % H);
+  const int64_t img = t / H;
+  float a[8], s[8];
+  ldg8(low + (((img * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) * (int64_t)C) + 8 * v, a);   // re-read 4x: keep cached
+  load8(skip + idx * 8, s);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] += s[j];
+  store8(out + idx * 8, a);
+}
+
+// ------------------------------------------------------------------ camera rays -> ray encoding -> patch rows
+// thread per pixel: 6 ray components x n_freq frequencies x {sin(e), sin(e + pi/2)} = 12*n_freq contiguous bf16.
+// fp32 operation order follows the reference (geometry_utils.py:50-81): e = v * (2^s * pi); e2 = e + pi/2.
+__global__ void __launch_bounds__(kThreads)
+pose_ray_patches_kernel(const float* __restrict__ cams, const float* __restrict__ freq_scale, int n_freq,
+                        __nv_bfloat16* __restrict__ out, int64_t ld, int64_t frames, int res, int p) {
+  const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (idx >= frames * res * res) return;
+  const int X = (int)(idx % res), Y = (int)((idx / res) % res);
+  const int64_t fr = idx / ((int64_t)res * res);
+  const float* c = cams + fr * 16;
+  const float fx = __ldg(c), fy = __ldg(c + 1), px = __ldg(c + 2), py = __ldg(c + 3);
+  const float dx = (((float)X + 0.5f) - px) / fx, dy = (((float)Y + 0.5f) - py) / fy;
+  float v[6];
+  v[0] = __ldg(c + 13); v[1] = __ldg(c + 14); v[2] = __ldg(c + 15);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    v[3 + i] = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(c + 4 + 3 * i), dx), __fmul_rn(__ldg(c + 5 + 3 * i), dy)),
+                         __ldg(c + 6 + 3 * i));
+  const int g = res / p;
+  const int64_t tok = (fr * g + Y / p) * g + X / p;
+  const int per_part = 6 * n_freq;   // 3 components x n_freq x 2
+  __nv_bfloat16* o = out + tok * ld + (int64_t)((Y % p) * p + (X % p)) * (2 * per_part);
+  const float half_pi = 1.5707963267948966f;
+  for (int part = 0; part < 2; ++part)
+    for (int i = 0; i < 3; ++i)
+      for (int s = 0; s < n_freq; ++s) {
+        const float e = __fmul_rn(v[3 * part + i], __ldg(freq_scale + s));
+        const int ch = part * per_part + i * n_freq + s;
+        o[ch] = __float2bfloat16_rn(sinf(e));
+        o[ch + 3 * n_freq] = __float2bfloat16_rn(sinf(__fadd_rn(e, half_pi)));
+      }
+}
+
+static inline unsigned blocks_for(int64_t n) { return (unsigned)ceil_div(n, kThreads); }
+
+}  // namespace uvit
+}  // namespace dfot
+
+using namespace dfot;
+using namespace dfot::uvit;
+
+extern "C" int dfot_groupnorm_stats(const void* x, int x_dtype, double* sums, int64_t n_img, int64_t HW, int64_t C,
+                                    int64_t groups, void* stream) {
+  DFOT_REQUIRE(x && sums && n_img > 0 && HW > 0 && C > 0 && groups > 0, DFOT_ERR_INVALID_ARG, "groupnorm_stats: bad arguments");
+  DFOT_REQUIRE(C % groups == 0 && C % 8 == 0 && groups <= 64 && n_img < 65536, DFOT_ERR_UNSUPPORTED,
+               "groupnorm_stats: need C %% groups == 0, C %% 8 == 0, groups <= 64");
+  const int vecs = (int)(C / 8);
+  DFOT_REQUIRE(vecs <= kThreads && kThreads % vecs == 0, DFOT_ERR_UNSUPPORTED,
+               "groupnorm_stats: C/8 = %d must divide %d", vecs, kThreads);
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * n_img * groups, s);
+  DFOT_REQUIRE(e == cudaSuccess, DFOT_ERR_CUDA, "groupnorm_stats: memset failed: %s", cudaGetErrorString(e));
+  // ~8 resident blocks per SM over the whole batch, at least 8 pixels per thread-row
+  const int pix_rows = kThreads / vecs;
+  int64_t slabs = ceil_div(148 * 8, n_img);
+  int64_t ppb = ceil_div(HW, slabs);
+  if (ppb < 8 * pix_rows) ppb = 8 * pix_rows;
+  slabs = ceil_div(HW, ppb);
+  dim3 grid((unsigned)slabs, (unsigned)n_img);
+  if (x_dtype == DFOT_F32)
+    gn_stats_kernel<float><<<grid, kThreads, 0, s>>>((const float*)x, sums, HW, (int)C, (int)groups, (int)ppb);
+  else if (x_dtype == DFOT_BF16)
+    gn_stats_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>((const __nv_bfloat16*)x, sums, HW, (int)C, (int)groups, (int)ppb);
+  else
+    DFOT_REQUIRE(false, DFOT_ERR_INVALID_ARG, "groupnorm_stats: x dtype must be f32 or bf16");
+  DFOT_CHECK_LAUNCH("groupnorm_stats");
+  return DFOT_OK;
+}
+
+extern "C" int dfot_groupnorm_silu_bf16(const void* x, int x_dtype, const double* sums, const float* gamma,
+                                        const float* beta, float eps, const float* mod_img, int64_t ld_img,
+                                        int64_t scale_col, int64_t shift_col, const void* mod_pix,
+                                        const int32_t* img_map, void* y_bf16, int64_t n_img, int64_t HW, int64_t C,
+                                        int64_t groups, void* stream) {
+  DFOT_REQUIRE(x && sums && gamma && beta && y_bf16 && n_img > 0 && HW > 0 && C > 0 && groups > 0, DFOT_ERR_INVALID_ARG,
+               "groupnorm_silu: bad arguments");
+  DFOT_REQUIRE(C % groups == 0 && C % 8 == 0, DFOT_ERR_UNSUPPORTED, "groupnorm_silu: need C %% groups == 0 and C %% 8 == 0");
+  DFOT_REQUIRE(mod_img == nullptr || (ld_img % 4 == 0 && scale_col % 4 == 0 && shift_col % 4 == 0), DFOT_ERR_UNSUPPORTED,
+               "groupnorm_silu: modulation offsets must be multiples of 4");
+  DFOT_REQUIRE((mod_pix == nullptr) == (img_map == nullptr) && (mod_pix == nullptr || mod_img != nullptr),
+               DFOT_ERR_INVALID_ARG, "groupnorm_silu: mod_pix needs img_map and mod_img");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t total = n_img * HW * (C / 8);
+  if (x_dtype == DFOT_F32)
+    gn_silu_kernel<float><<<blocks_for(total), kThreads, 0, s>>>(
+        (const float*)x, sums, gamma, beta, eps, mod_img, ld_img, scale_col, shift_col, (const __nv_bfloat16*)mod_pix,
+        img_map, (__nv_bfloat16*)y_bf16, n_img, HW, (int)C, (int)groups);
+  else if (x_dtype == DFOT_BF16)
+    gn_silu_kernel<__nv_bfloat16><<<blocks_for(total), kThreads, 0, s>>>(
+        (const __nv_bfloat16*)x, sums, gamma, beta, eps, mod_img, ld_img, scale_col, shift_col,
+        (const __nv_bfloat16*)mod_pix, img_map, (__nv_bfloat16*)y_bf16, n_img, HW, (int)C, (int)groups);
+  else
+    DFOT_REQUIRE(false, DFOT_ERR_INVALID_ARG, "groupnorm_silu: x dtype must be f32 or bf16");
+  DFOT_CHECK_LAUNCH("groupnorm_silu");
+  return DFOT_OK;
+}
+
+extern "C" int dfot_rmsnorm_film_bf16(const float* x, const float* weight, float eps, const float* mod_img,
+                                      int64_t ld_img, int64_t scale_col, int64_t shift_col, const void* mod_pix,
+                                      const int32_t* img_map, void* y_bf16, int64_t M, int64_t D,
+                                      int64_t tokens_per_img, void* stream) {
+  DFOT_REQUIRE(x && weight && mod_img && y_bf16 && M > 0 && D > 0 && tokens_per_img > 0, DFOT_ERR_INVALID_ARG,
+               "rmsnorm_film: bad arguments");
+  DFOT_REQUIRE(D % 4 == 0 && D <= 4096 && ld_img % 4 == 0 && scale_col % 4 == 0 && shift_col % 4 == 0,
+               DFOT_ERR_UNSUPPORTED, "rmsnorm_film: D (<= 4096) and modulation offsets must be multiples of 4");
+  DFOT_REQUIRE((mod_pix == nullptr) == (img_map == nullptr), DFOT_ERR_INVALID_ARG, "rmsnorm_film: mod_pix needs img_map");
+  const unsigned grid = (unsigned)ceil_div(M, kNormWarps);
+  cudaStream_t s = (cudaStream_t)stream;
+#define LAUNCH(NV)                                                                                                   \
+  rmsnorm_film_kernel<NV><<<grid, kNormWarps * 32, 0, s>>>(x, weight, eps, mod_img, ld_img, scale_col, shift_col,    \
+                                                           (const __nv_bfloat16*)mod_pix, img_map,                   \
+                                                           (__nv_bfloat16*)y_bf16, M, (int)D, tokens_per_img)
+  if (D <= 128) LAUNCH(1);
+  else if (D <= 256) LAUNCH(2);
+  else if (D <= 640) LAUNCH(5);
+  else if (D <= 1152) LAUNCH(9);
+  else if (D <= 2048) LAUNCH(16);
+  else LAUNCH(32);
+#undef LAUNCH
+  DFOT_CHECK_LAUNCH("rmsnorm_film");
+  return DFOT_OK;
+}
+
+extern "C" int dfot_qk_norm_rope(void* qkv, int64_t ld, const float* q_weight, const float* k_weight, float eps,
+                                 const float* rope_cs, int64_t tokens_per_sample, int64_t M, int64_t heads,
+                                 int64_t head_dim, float q_scale, void* stream) {
+  DFOT_REQUIRE(qkv && q_weight && k_weight && rope_cs && M > 0 && heads > 0 && tokens_per_sample > 0,
+               DFOT_ERR_INVALID_ARG, "qk_norm_rope: bad arguments");
+  DFOT_REQUIRE(head_dim == 64 || head_dim == 128, DFOT_ERR_UNSUPPORTED, "qk_norm_rope: head_dim must be 64 or 128");
+  DFOT_REQUIRE(ld % 4 == 0 && ld >= 3 * heads * head_dim && (uintptr_t)qkv % 8 == 0, DFOT_ERR_UNSUPPORTED,
+               "qk_norm_rope: ld must be a multiple of 4 and >= 3*heads*head_dim");
+  const int64_t warps = M * heads * 2;
+  const unsigned grid = (unsigned)ceil_div(warps, kThreads / 32);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (head_dim == 64)
+    qk_norm_rope_kernel<64><<<grid, kThreads, 0, s>>>((__nv_bfloat16*)qkv, ld, q_weight, k_weight, eps, rope_cs,
+                                                      tokens_per_sample, M, (int)heads, q_scale);
+  else
+    qk_norm_rope_kernel<128><<<grid, kThreads, 0, s>>>((__nv_bfloat16*)qkv, ld, q_weight, k_weight, eps, rope_cs,
+                                                       tokens_per_sample, M, (int)heads, q_scale);
+  DFOT_CHECK_LAUNCH("qk_norm_rope");
+  return DFOT_OK;
+}
+
+extern "C" int dfot_avgpool2x2(const void* in, int in_dtype, void* out, int out_dtype, int64_t n_img, int64_t H,
+                               int64_t W, int64_t C, void* stream) {
+  DFOT_REQUIRE(in && out && n_img > 0 && H > 0 && W > 0 && C > 0, DFOT_ERR_INVALID_ARG, "avgpool2x2: bad arguments");
+  DFOT_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, DFOT_ERR_UNSUPPORTED, "avgpool2x2: H, W even and C %% 8 == 0");
+  const int64_t total = n_img * (H / 2) * (W / 2) * (C / 8);
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned grid = blocks_for(total);
+  if (in_dtype == DFOT_F32 && out_dtype == DFOT_F32)
+    avgpool2x2_kernel<float, float><<<grid, kThreads, 0, s>>>((const float*)in, (float*)out, n_img, (int)H, (int)W, (int)C);
+  else if (in_dtype == DFOT_F32 && out_dtype == DFOT_BF16)
+    avgpool2x2_kernel<float, __nv_bfloat16><<<grid, kThreads, 0, s>>>((const float*)in, (__nv_bfloat16*)out, n_img, (int)H, (int)W, (int)C);
+  else if (in_dtype == DFOT_BF16 && out_dtype == DFOT_BF16)
+    avgpool2x2_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kThreads, 0, s>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, n_img, (int)H, (int)W, (int)C);
+  else
+    DFOT_REQUIRE(false, DFOT_ERR_INVALID_ARG, "avgpool2x2: unsupported dtype combination");
+  DFOT_CHECK_LAUNCH("avgpool2x2");
+  return DFOT_OK;
+}
+
+extern "C" int dfot_sub_bf16(const float* a, const float* b, void* out_bf16, int64_t n, void* stream) {
+  DFOT_REQUIRE(a && b && out_bf16 && n > 0, DFOT_ERR_INVALID_ARG, "sub_bf16: bad arguments");
+  DFOT_REQUIRE(n % 8 == 0, DFOT_ERR_UNSUPPORTED, "sub_bf16: n must be a multiple of 8");
+  sub_bf16_kernel<<<blocks_for(n / 8), kThreads, 0, (cudaStream_t)stream>>>(a, b, (__nv_bfloat16*)out_bf16, n / 8);
+  DFOT_CHECK_LAUNCH("sub_bf16");
+  return DFOT_OK;
+}
+
+extern "C" int dfot_upsample2x_add(const float* low, const float* skip, float* out, int64_t n_img, int64_t H, int64_t W,
+                                   int64_t C, void* stream) {
+  DFOT_REQUIRE(low && skip && out && n_img > 0 && H > 0 && W > 0 && C > 0, DFOT_ERR_INVALID_ARG, "upsample2x_add: bad arguments");
+  DFOT_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, DFOT_ERR_UNSUPPORTED, "upsample2x_add: H, W even and C %% 8 == 0");
+  upsample2x_add_kernel<<<blocks_for(n_img * H * W * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+      low, skip, out, n_img, (int)H, (int)W, (int)C);
+  DFOT_CHECK_LAUNCH("upsample2x_add");
+  return DFOT_OK;
+}
+
+extern "C" int dfot_pose_ray_patches(const float* cams, const float* freq_scale, int64_t n_freq, void* out_bf16,
+                                     int64_t ld, int64_t frames, int64_t res, int64_t p, void* stream) {
+  DFOT_REQUIRE(cams && freq_scale && out_bf16 && n_freq > 0 && frames > 0 && res > 0 && p > 0, DFOT_ERR_INVALID_ARG,
+               "pose_ray_patches: bad arguments");
+  DFOT_REQUIRE(res % p == 0 && ld >= p * p * 12 * n_freq, DFOT_ERR_INVALID_ARG, "pose_ray_patches: res %% p, ld");
+  pose_ray_patches_kernel<<<blocks_for(frames * res * res), kThreads, 0, (cudaStream_t)stream>>>(
+      cams, freq_scale, (int)n_freq, (__nv_bfloat16*)out_bf16, ld, frames, (int)res, (int)p);
+  DFOT_CHECK_LAUNCH("pose_ray_patches");
+  return DFOT_OK;
+}

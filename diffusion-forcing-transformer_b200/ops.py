@@ -10,7 +10,7 @@ import torch
 
 from . import _abi
 from ._abi import (BF16, EPI_BF16, EPI_F32, EPI_GATE_RESID_F32, EPI_GELU_BF16, EPI_QKV_ROPE_BF16,  # noqa: F401
-                   EPI_SILU_BF16, F32, I64)
+                   EPI_RESID_F32, EPI_SILU_BF16, F32, I64)
 
 _DTYPE_TAG = {torch.float32: F32, torch.bfloat16: BF16, torch.int64: I64}
 
@@ -94,7 +94,7 @@ def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, gate=None, ld_gate=0, 
         raise RuntimeError("dfot_b200: `a` must be a CUDA bf16 matrix with unit inner stride")
     if not out.is_cuda or out.stride(-1) != 1:
         raise RuntimeError("dfot_b200: `out` must be a CUDA matrix with unit inner stride")
-    want = torch.float32 if epilogue in (EPI_F32, EPI_GATE_RESID_F32) else torch.bfloat16
+    want = torch.float32 if epilogue in (EPI_F32, EPI_GATE_RESID_F32, EPI_RESID_F32) else torch.bfloat16
     if out.dtype != want:
         raise RuntimeError(f"dfot_b200: epilogue {epilogue} writes {want}, got {out.dtype}")
     M = a.shape[0] if M is None else M
@@ -178,3 +178,123 @@ def cast_bf16(src, out=None):
     rc = _abi.lib().dfot_cast_bf16(src.data_ptr(), out.data_ptr(), src.numel(), _stream())
     _abi.check(rc, "cast_bf16")
     return out
+
+
+# ------------------------------------------------------------------ U-ViT3DPose kernels
+def conv3x3_bf16(x, w, out, epilogue, bias=None, resid=None):
+    """3x3 conv, stride 1, padding 1, implicit GEMM.  x [n,H,W,Cin] bf16 channel-last, w [Cout,3,3,Cin] bf16,
+    out [n*H*W, Cout] f32|bf16 per epilogue (EPI_F32, EPI_BF16, EPI_SILU_BF16, EPI_RESID_F32)."""
+    _need(x, torch.bfloat16, "x")
+    _need(w, torch.bfloat16, "w")
+    _need(out, None, "out")
+    n, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    if tuple(w.shape) != (Cout, 3, 3, Cin) or out.numel() != n * H * W * Cout:
+        raise RuntimeError(f"dfot_b200: conv3x3 shape mismatch x{tuple(x.shape)} w{tuple(w.shape)} out{tuple(out.shape)}")
+    want = torch.float32 if epilogue in (EPI_F32, EPI_RESID_F32) else torch.bfloat16
+    if out.dtype != want:
+        raise RuntimeError(f"dfot_b200: epilogue {epilogue} writes {want}, got {out.dtype}")
+    e = _abi.GemmEpilogue()
+    if bias is not None:
+        _need(bias, torch.float32, "bias")
+        e.bias = bias.data_ptr()
+    if resid is not None:
+        _need(resid, torch.float32, "resid")
+        e.resid, e.ld_resid = resid.data_ptr(), Cout
+    e.tokens_per_frame = 1
+    rc = _abi.lib().dfot_conv3x3_bf16(x.data_ptr(), w.data_ptr(), out.data_ptr(), Cout, n, H, W, Cin, Cout, epilogue,
+                                      ctypes.byref(e), _stream())
+    _abi.check(rc, "conv3x3_bf16")
+
+
+def groupnorm_stats(x, sums, n_img, HW, C, groups=32):
+    """x [n_img*HW, C] f32|bf16 channel-last → sums [n_img, groups, 2] f64 (sum, sum of squares)."""
+    _need(x, None, "x")
+    _need(sums, torch.float64, "sums")
+    if sums.numel() != n_img * groups * 2 or x.numel() != n_img * HW * C:
+        raise RuntimeError("dfot_b200: groupnorm_stats size mismatch")
+    rc = _abi.lib().dfot_groupnorm_stats(x.data_ptr(), _DTYPE_TAG[x.dtype], sums.data_ptr(), n_img, HW, C, groups,
+                                         _stream())
+    _abi.check(rc, "groupnorm_stats")
+
+
+def groupnorm_silu_bf16(x, sums, gamma, beta, out, n_img, HW, C, groups=32, eps=1e-6, mod_img=None, scale_col=0,
+                        shift_col=0, mod_pix=None, img_map=None):
+    _need(x, None, "x")
+    _need(sums, torch.float64, "sums")
+    _need(gamma, torch.float32, "gamma")
+    _need(beta, torch.float32, "beta")
+    _need(out, torch.bfloat16, "out")
+    if mod_img is not None:
+        _need(mod_img, torch.float32, "mod_img")
+    if mod_pix is not None:
+        _need(mod_pix, torch.bfloat16, "mod_pix")
+        _need(img_map, torch.int32, "img_map")
+    rc = _abi.lib().dfot_groupnorm_silu_bf16(
+        x.data_ptr(), _DTYPE_TAG[x.dtype], sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, _ptr(mod_img),
+        0 if mod_img is None else mod_img.shape[-1], scale_col, shift_col, _ptr(mod_pix), _ptr(img_map),
+        out.data_ptr(), n_img, HW, C, groups, _stream())
+    _abi.check(rc, "groupnorm_silu_bf16")
+
+
+def rmsnorm_film_bf16(x, weight, mod_img, scale_col, shift_col, tokens_per_img, out, mod_pix=None, img_map=None,
+                      eps=1e-6):
+    _need(x, torch.float32, "x")
+    _need(weight, torch.float32, "weight")
+    _need(mod_img, torch.float32, "mod_img")
+    _need(out, torch.bfloat16, "out")
+    if mod_pix is not None:
+        _need(mod_pix, torch.bfloat16, "mod_pix")
+        _need(img_map, torch.int32, "img_map")
+    M, D = x.shape
+    rc = _abi.lib().dfot_rmsnorm_film_bf16(x.data_ptr(), weight.data_ptr(), eps, mod_img.data_ptr(), mod_img.shape[-1],
+                                           scale_col, shift_col, _ptr(mod_pix), _ptr(img_map), out.data_ptr(), M, D,
+                                           tokens_per_img, _stream())
+    _abi.check(rc, "rmsnorm_film_bf16")
+
+
+def qk_norm_rope(qkv, q_weight, k_weight, rope_cs, tokens_per_sample, heads, head_dim, q_scale, eps=1e-6):
+    """In place on qkv [M, ld] bf16 (columns [q | k | v ...]); row stride may exceed 3*heads*head_dim."""
+    if not qkv.is_cuda or qkv.dtype != torch.bfloat16 or qkv.stride(-1) != 1:
+        raise RuntimeError("dfot_b200: `qkv` must be a CUDA bf16 matrix with unit inner stride")
+    _need(q_weight, torch.float32, "q_weight")
+    _need(k_weight, torch.float32, "k_weight")
+    _need(rope_cs, torch.float32, "rope_cs")
+    rc = _abi.lib().dfot_qk_norm_rope(qkv.data_ptr(), qkv.stride(0), q_weight.data_ptr(), k_weight.data_ptr(), eps,
+                                      rope_cs.data_ptr(), tokens_per_sample, qkv.shape[0], heads, head_dim, q_scale,
+                                      _stream())
+    _abi.check(rc, "qk_norm_rope")
+
+
+def avgpool2x2(x, out, n_img, H, W, C):
+    _need(x, None, "x")
+    _need(out, None, "out")
+    rc = _abi.lib().dfot_avgpool2x2(x.data_ptr(), _DTYPE_TAG[x.dtype], out.data_ptr(), _DTYPE_TAG[out.dtype], n_img, H,
+                                    W, C, _stream())
+    _abi.check(rc, "avgpool2x2")
+
+
+def sub_bf16(a, b, out):
+    _need(a, torch.float32, "a")
+    _need(b, torch.float32, "b")
+    _need(out, torch.bfloat16, "out")
+    rc = _abi.lib().dfot_sub_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream())
+    _abi.check(rc, "sub_bf16")
+
+
+def upsample2x_add(low, skip, out, n_img, H, W, C):
+    """out [n,H,W,C] = nearest2x(low [n,H/2,W/2,C]) + skip [n,H,W,C] (all f32, channel-last)."""
+    _need(low, torch.float32, "low")
+    _need(skip, torch.float32, "skip")
+    _need(out, torch.float32, "out")
+    rc = _abi.lib().dfot_upsample2x_add(low.data_ptr(), skip.data_ptr(), out.data_ptr(), n_img, H, W, C, _stream())
+    _abi.check(rc, "upsample2x_add")
+
+
+def pose_ray_patches(cams, freq_scale, out, frames, res, p):
+    _need(cams, torch.float32, "cams")
+    _need(freq_scale, torch.float32, "freq_scale")
+    _need(out, torch.bfloat16, "out")
+    rc = _abi.lib().dfot_pose_ray_patches(cams.data_ptr(), freq_scale.data_ptr(), freq_scale.numel(), out.data_ptr(),
+                                          out.stride(0), frames, res, p, _stream())
+    _abi.check(rc, "pose_ray_patches")

@@ -116,6 +116,7 @@ DFOT_API int dfot_adaln_layernorm(const float* x, const float* mod, int64_t mod_
 #define DFOT_EPI_SILU_BF16 3      /* out bf16 = silu(acc + bias)           (TimestepEmbedding) */
 #define DFOT_EPI_GATE_RESID_F32 4 /* out f32  = resid + gate[f(m), n] * (acc + bias)          */
 #define DFOT_EPI_QKV_ROPE_BF16 5  /* out bf16 = rope3d(acc + bias) on q,k columns; q pre-scaled */
+#define DFOT_EPI_RESID_F32 6      /* out f32  = resid + acc + bias         (U-ViT residual adds) */
 
 typedef struct {
   const float* bias;          /* [N] or NULL */
@@ -135,6 +136,18 @@ typedef struct {
 
 DFOT_API int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int64_t M,
                    int64_t N, int64_t K, int epilogue, const dfot_gemm_epilogue* epi, void* stream);
+
+/* 3x3 convolution (stride 1, zero padding 1) as an implicit GEMM on the same tcgen05 kernel — no im2col buffer:
+ * the A tile of tap (dy, dx) is the pixel tile's 4-D TMA box shifted by (dy, dx), out-of-image rows/columns are
+ * zero-filled by the TMA unit.  Replaces the nn.Conv2d(k=3, padding=1) of the U-ViT ResBlock / Downsample /
+ * Upsample (algorithms/dfot/backbones/u_vit/u_vit_blocks.py:63-75, 277-314).
+ *   x   [n_img, H, W, Cin]  bf16 channel-last;   w [Cout, 3, 3, Cin] bf16 (torch weight permuted (0, 2, 3, 1));
+ *   out [n_img*H*W, ldc]    f32 or bf16 per epilogue (F32, BF16, SILU_BF16, RESID_F32), channel-last.
+ * W must be a power of two below 128 or a multiple of 128; H a multiple of 128/W (or a power of two when H*W < 128).
+ */
+DFOT_API int dfot_conv3x3_bf16(const void* x, const void* w, void* out, int64_t ldc, int64_t n_img, int64_t H,
+                      int64_t W, int64_t Cin, int64_t Cout, int epilogue, const dfot_gemm_epilogue* epi,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3 — attention over space-time latent tokens (non-causal, no mask: context frames are
@@ -165,6 +178,52 @@ DFOT_API int dfot_unpatchify(const float* tok, int64_t ld, void* x, int x_dtype,
                     int64_t W, int64_t p, void* stream);
 /* elementwise f32 → bf16 (weights repack / activations), n % 8 == 0 not required */
 DFOT_API int dfot_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * U-ViT3DPose glue kernels (algorithms/dfot/backbones/u_vit/{u_vit3d_pose,u_vit3d,u_vit_blocks}.py).
+ * Activations are channel-last everywhere: [n_img, H, W, C] == [tokens, C], so ResBlock levels and
+ * transformer levels share one layout and the reference's rearranges (u_vit3d.py:199-235) vanish.
+ *
+ * FiLM inputs: scale/shift = per-image f32 part  mod_img[img*ld_img + {scale,shift}_col + c]   (noise-level
+ * embedding through the block's emb_layer, one GEMM per forward for all blocks) plus an optional per-pixel
+ * bf16 part  mod_pix[(img_map[img]*HW + pix) * 2C + {0, C} + c]  (camera-pose embedding through the same
+ * emb_layer — linear, hence constant over all sampling steps and cached per window; img_map[img] < 0 means
+ * the row's pose embedding is masked out, embeddings.py:336-361).
+ */
+/* GroupNorm statistics (u_vit_blocks.py:52-53: 32 groups): sums[img, g] = (sum, sum of squares) over H*W x C/G,
+   accumulated in f64.  The buffer is zeroed by the call (cudaMemsetAsync on the stream). x f32 or bf16. */
+DFOT_API int dfot_groupnorm_stats(const void* x, int x_dtype, double* sums, int64_t n_img, int64_t HW, int64_t C,
+                         int64_t groups, void* stream);
+/* y = silu( GN(x) * gamma + beta [ * (1 + scale) + shift ] ) -> bf16 (the conv operand).  mod_img/mod_pix NULL: no FiLM */
+DFOT_API int dfot_groupnorm_silu_bf16(const void* x, int x_dtype, const double* sums, const float* gamma,
+                             const float* beta, float eps, const float* mod_img, int64_t ld_img, int64_t scale_col,
+                             int64_t shift_col, const void* mod_pix, const int32_t* img_map, void* y_bf16,
+                             int64_t n_img, int64_t HW, int64_t C, int64_t groups, void* stream);
+/* NormalizeWithCond (u_vit_blocks.py:98-121): y = RMSNorm(x) * weight * (1 + scale) + shift -> bf16; x [M, D] f32,
+   image = m / tokens_per_img */
+DFOT_API int dfot_rmsnorm_film_bf16(const float* x, const float* weight, float eps, const float* mod_img, int64_t ld_img,
+                           int64_t scale_col, int64_t shift_col, const void* mod_pix, const int32_t* img_map,
+                           void* y_bf16, int64_t M, int64_t D, int64_t tokens_per_img, void* stream);
+/* q/k RMSNorm over head_dim (* weight) then RoPE-3D, q additionally * q_scale; in place on qkv [M, ld] bf16 with
+   columns [q | k | v] of `heads*head_dim` each (u_vit_blocks.py:253-259).  head_dim in {64, 128} */
+DFOT_API int dfot_qk_norm_rope(void* qkv, int64_t ld, const float* q_weight, const float* k_weight, float eps,
+                      const float* rope_cs, int64_t tokens_per_sample, int64_t M, int64_t heads, int64_t head_dim,
+                      float q_scale, void* stream);
+/* 2x2 average pooling, channel-last: in [n_img, H, W, C] -> out [n_img, H/2, W/2, C]; dtypes f32|bf16 each */
+DFOT_API int dfot_avgpool2x2(const void* in, int in_dtype, void* out, int out_dtype, int64_t n_img, int64_t H, int64_t W,
+                    int64_t C, void* stream);
+/* out_bf16 = a - b (f32 inputs): the operand of the Upsample conv (u_vit3d_pose.py:125) */
+DFOT_API int dfot_sub_bf16(const float* a, const float* b, void* out_bf16, int64_t n, void* stream);
+/* out[n, Y, X, c] = low[n, Y/2, X/2, c] + skip[n, Y, X, c]  (nearest 2x upsampling + skip, u_vit_blocks.py:299-314) */
+DFOT_API int dfot_upsample2x_add(const float* low, const float* skip, float* out, int64_t n_img, int64_t H, int64_t W,
+                        int64_t C, void* stream);
+/* Camera rays -> sinusoidal ray encoding -> patch rows for the pose PatchEmbed GEMM, never materialising the
+   [frames, 180, H, W] tensor (utils/geometry_utils.py:50-81, 244-295; dfot_video_pose.py:64-110).
+   cams [frames, 16] f32 = (fx, fy, px, py) already multiplied by the resolution, R^-1 row-major (9), origin (3);
+   out [frames*(res/p)^2, ld] bf16 with columns ((py*p + px)*6*2*n_freq + channel), channel order as the reference:
+   [origin: sin(v*2^s*pi) (i s) | sin(. + pi/2) | direction: ... ].  freq_scale [n_freq] f32. */
+DFOT_API int dfot_pose_ray_patches(const float* cams, const float* freq_scale, int64_t n_freq, void* out_bf16, int64_t ld,
+                          int64_t frames, int64_t res, int64_t p, void* stream);
 
 #ifdef __cplusplus
 }

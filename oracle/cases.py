@@ -17,6 +17,8 @@ def _set(d: dict, path: str, value: Any) -> None:
 
 
 def algorithm_cfg(**overrides) -> Dict[str, Any]:
+    overrides = dict(overrides)
+    backbone_override = overrides.pop("backbone", None)
     cfg = dict(
         debug=False, lr=1e-4,
         external_cond_type=None, external_cond_num_classes=None, external_cond_dim=0,
@@ -51,6 +53,8 @@ def algorithm_cfg(**overrides) -> Dict[str, Any]:
                      n_metrics_frames=None, metrics=[], metrics_batch_size=16, sanity_generation=False,
                      raw_dir=None),
     )
+    if backbone_override is not None:
+        cfg["backbone"] = copy.deepcopy(backbone_override)
     for k, v in overrides.items():
         _set(cfg, k.replace("__", "."), copy.deepcopy(v))
     return cfg
@@ -114,4 +118,43 @@ def golden_cases() -> Dict[str, Dict[str, Any]]:
             "tasks.interpolation.history_guidance": dict(name="vanilla", guidance_scale=1.5, visualize=False),
             "tasks.interpolation.max_batch_size": 2}), batch=1, weights="action"),
     }
+    pose = {
+        **continuous_overrides(), "external_cond_type": "action", "external_cond_dim": 16,
+        "camera_pose_conditioning": dict(normalize_by="first", bound=None, type="ray_encoding"),
+        "backbone": dict(name="u_vit3d_pose", channels=[32, 32, 64, 128], emb_channels=64, patch_size=2,
+                         block_types=["ResBlock", "ResBlock", "TransformerBlock", "TransformerBlock"],
+                         block_dropouts=[0.0, 0.0, 0.0, 0.0], num_updown_blocks=[1, 1, 2], num_mid_blocks=2,
+                         num_heads=1, pos_emb_type="rope", use_checkpointing=[False] * 4,
+                         conditioning=dict(dim=None), external_cond_dropout=0.1, use_fourier_noise_embedding=True),
+        "x_shape": [3, 32, 32], "max_frames": 4, "n_frames": 4, "context_frames": 1,
+        "data_mean": [[[0.5]]] * 3, "data_std": [[[0.5]]] * 3, "diffusion.sampling_timesteps": 3,
+    }
+    cases["uvit_pose_vanilla"] = dict(cfg=algorithm_cfg(**{**pose, "tasks.prediction.history_guidance":
+                                                          dict(name="vanilla", guidance_scale=2.0, visualize=False)}),
+                                      batch=1, weights="uvit_pose", algo="dfot_video_pose")
+    cases["uvit_pose_stabilized_interp"] = dict(cfg=algorithm_cfg(**{
+        **pose, "n_frames": 9, "tasks.prediction.keyframe_density": 0.5, "tasks.prediction.sliding_context_len": 1,
+        "tasks.prediction.history_guidance": dict(name="stabilized_vanilla", guidance_scale=2.0,
+                                                  stabilization_level=0.02, visualize=False),
+        "tasks.interpolation.history_guidance": dict(name="vanilla", guidance_scale=1.5, visualize=False),
+        "tasks.interpolation.max_batch_size": 2}), batch=1, weights="uvit_pose", algo="dfot_video_pose")
     return cases
+
+
+def synthetic_poses(batch: int, n_frames: int):
+    """(B, T, 16): intrinsics (fx, fy, px, py) = (0.5, 0.9, 0.5, 0.5) + row-major [R | t] of a smooth yaw/pitch/
+    translation trajectory (valid rotations), as in SURVEY.md §8c."""
+    import math
+
+    import torch
+    out = []
+    for b in range(batch):
+        rows = []
+        for t in range(n_frames):
+            yaw, pitch = 0.05 * t + 0.1 * b, 0.02 * t
+            cy, sy, cp, sp = math.cos(yaw), math.sin(yaw), math.cos(pitch), math.sin(pitch)
+            R = torch.tensor([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @ torch.tensor([[1, 0, 0], [0, cp, -sp], [0, sp, cp]])
+            tv = torch.tensor([0.1 * t, 0.02 * t * (b + 1), 0.05 * t + 0.3])
+            rows.append(torch.cat([torch.tensor([0.5, 0.9, 0.5, 0.5]), torch.cat([R, tv[:, None]], 1).flatten()]))
+        out.append(torch.stack(rows))
+    return torch.stack(out).float()

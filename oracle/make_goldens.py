@@ -30,8 +30,10 @@ WEIGHT_SEED, REDRAW_SEED, DATA_SEED, SAMPLING_SEED = 0, 1, 123, 321
 
 def build_reference_algo(cfg: dict):
     from algorithms.dfot.dfot_video import DFoTVideo
+    from algorithms.dfot.dfot_video_pose import DFoTVideoPose
     torch.manual_seed(WEIGHT_SEED)
-    algo = DFoTVideo(ref_shim.to_dc(cfg)).eval()
+    cls = DFoTVideoPose if cfg["backbone"]["name"] == "u_vit3d_pose" else DFoTVideo
+    algo = cls(ref_shim.to_dc(cfg)).eval()
     ref_shim.rerandomize_zero_params(algo, REDRAW_SEED)
     return algo
 
@@ -40,7 +42,10 @@ def synthetic_inputs(cfg: dict, batch: int):
     g = torch.Generator().manual_seed(DATA_SEED)
     xs = torch.randn((batch, cfg["n_frames"], *cfg["x_shape"]), generator=g)
     conds = None
-    if cfg["external_cond_dim"]:
+    if "camera_pose_conditioning" in cfg:
+        from oracle.cases import synthetic_poses
+        conds = synthetic_poses(batch, cfg["n_frames"])
+    elif cfg["external_cond_dim"]:
         conds = torch.randn((batch, cfg["n_frames"], cfg["external_cond_dim"]), generator=g)
     return xs, conds
 

@@ -25,9 +25,19 @@ def build_oracle(cfg, weights, randn=torch.randn, randn_like=torch.randn_like):
     from oracle.dit3d import DiT3DOracle
     from oracle.sampler import SamplerOracle
     probe = SamplerOracle(cfg, None)
-    model = DiT3DOracle(cfg["backbone"], probe.x_shape, probe.max_tokens, weights,
-                        external_cond_dim=probe.external_cond_dim)
+    if cfg["backbone"]["name"] == "u_vit3d_pose":
+        from oracle.uvit3d_pose import UViT3DPoseOracle
+        model = UViT3DPoseOracle(cfg["backbone"], probe.x_shape, probe.max_tokens, weights)
+    else:
+        model = DiT3DOracle(cfg["backbone"], probe.x_shape, probe.max_tokens, weights,
+                            external_cond_dim=probe.external_cond_dim)
     return SamplerOracle(cfg, model, randn, randn_like), model
+
+
+def build_product(cfg):
+    """The product algorithm class for a golden case's config."""
+    from dfot_b200.algorithms.dfot import DFoTVideo, DFoTVideoPose
+    return (DFoTVideoPose if cfg["backbone"]["name"] == "u_vit3d_pose" else DFoTVideo)(cfg)
 
 
 class NoiseBank:

@@ -1,0 +1,196 @@
+"""-m gpu: the U-ViT3DPose kernels (implicit-GEMM 3x3 conv, GroupNorm/RMSNorm + FiLM, q/k norm + RoPE, pooling,
+upsampling, ray encoding), called through the C ABI, against plain PyTorch fp32 references of the same ops."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from dfot_b200 import ops  # noqa: E402
+from dfot_b200.algorithms.dfot.backbones.dit.dit3d import rope_cos_sin_table  # noqa: E402
+
+DEV = "cuda"
+
+
+def rel_err(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp(min=1e-12)).item()
+
+
+# (n_img, H, W, Cin, Cout): RE10K levels (shrunk batch), the tiny golden config, odd channel counts
+CONV_SHAPES = [(2, 128, 128, 128, 128), (3, 64, 64, 256, 256), (2, 64, 64, 128, 256), (4, 32, 32, 256, 576),
+               (8, 16, 16, 576, 1152), (8, 16, 16, 1152, 576), (4, 16, 16, 32, 32), (4, 8, 8, 32, 32),
+               (4, 4, 4, 32, 64), (8, 2, 2, 64, 128), (5, 2, 2, 128, 64), (3, 8, 8, 64, 32), (1, 256, 256, 8, 16)]
+
+
+@pytest.mark.parametrize("n,H,W,Cin,Cout", CONV_SHAPES)
+def test_conv3x3_implicit_gemm(n, H, W, Cin, Cout):
+    g = torch.Generator().manual_seed(n * 1000 + H + Cin + Cout)
+    x = torch.randn((n, Cin, H, W), generator=g).to(DEV).to(torch.bfloat16)
+    w = (torch.randn((Cout, Cin, 3, 3), generator=g) / math.sqrt(9 * Cin)).to(DEV).to(torch.bfloat16)
+    bias = torch.randn((Cout,), generator=g).to(DEV)
+    ref = F.conv2d(x.float(), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(n * H * W, Cout)
+    x_cl = x.permute(0, 2, 3, 1).contiguous()
+    w_cl = w.permute(0, 2, 3, 1).contiguous()
+    out = torch.full((n * H * W, Cout), float("nan"), device=DEV)
+    ops.conv3x3_bf16(x_cl, w_cl, out, ops.EPI_F32, bias=bias)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() <= 3e-3 * max(1.0, ref.abs().max().item()), (out - ref).abs().max()
+    resid = torch.randn((n * H * W, Cout), generator=g).to(DEV)
+    out2 = torch.empty_like(out)
+    ops.conv3x3_bf16(x_cl, w_cl, out2, ops.EPI_RESID_F32, bias=bias, resid=resid)
+    assert (out2 - (ref + resid)).abs().max().item() <= 3e-3 * max(1.0, ref.abs().max().item())
+    out16 = torch.empty((n * H * W, Cout), device=DEV, dtype=torch.bfloat16)
+    ops.conv3x3_bf16(x_cl, w_cl, out16, ops.EPI_BF16, bias=bias)
+    assert rel_err(out16, ref) < 5e-3
+
+
+def test_gemm_resid_epilogue():
+    M, N, K = 640, 576, 2880
+    g = torch.Generator().manual_seed(11)
+    a = torch.randn((M, K), generator=g).to(DEV).to(torch.bfloat16)
+    w = (torch.randn((N, K), generator=g) / math.sqrt(K)).to(DEV).to(torch.bfloat16)
+    bias = torch.randn((N,), generator=g).to(DEV)
+    resid = torch.randn((M, N), generator=g).to(DEV)
+    out = torch.empty((M, N), device=DEV)
+    ops.gemm_bf16(a, w, out, ops.EPI_RESID_F32, bias=bias, resid=resid)
+    ref = resid + a.float() @ w.float().t() + bias
+    assert (out - ref).abs().max().item() < 5e-3
+    # in place on the residual stream (how the transformer block uses it)
+    x = resid.clone()
+    ops.gemm_bf16(a, w, x, ops.EPI_RESID_F32, bias=bias, resid=x)
+    assert (x - ref).abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize("n,HW,C,dt", [(4, 16384, 128, torch.float32), (3, 4096, 256, torch.bfloat16),
+                                       (8, 256, 32, torch.float32), (8, 64, 32, torch.bfloat16), (2, 100, 64, torch.float32)])
+def test_groupnorm_stats_and_apply(n, HW, C, dt):
+    g = torch.Generator().manual_seed(C + HW)
+    x = (torch.randn((n, HW, C), generator=g) * 2 + 0.7).to(DEV).to(dt)
+    gamma, beta = torch.randn((C,), generator=g).to(DEV), torch.randn((C,), generator=g).to(DEV)
+    sums = torch.empty((n, 32, 2), dtype=torch.float64, device=DEV)
+    ops.groupnorm_stats(x, sums, n, HW, C)
+    xg = x.double().reshape(n, HW, 32, C // 32)
+    assert torch.allclose(sums[..., 0], xg.sum((1, 3)), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(sums[..., 1], (xg * xg).sum((1, 3)), rtol=1e-5, atol=1e-2)
+    x_nchw = x.float().permute(0, 2, 1).reshape(n, C, HW, 1)
+    gn = F.group_norm(x_nchw, 32, gamma, beta, eps=1e-6)
+    out = torch.empty((n * HW, C), dtype=torch.bfloat16, device=DEV)
+    ops.groupnorm_silu_bf16(x, sums, gamma, beta, out, n, HW, C)
+    ref = F.silu(gn).reshape(n, C, HW).permute(0, 2, 1).reshape(n * HW, C)
+    assert (out.float() - ref).abs().max().item() < 3e-2 and rel_err(out, ref) < 6e-3
+    # FiLM: per-image f32 part + per-pixel bf16 part through an image map (-1 = masked)
+    mod_img = torch.randn((n, 4 * C + 8), generator=g).to(DEV) * 0.3
+    n_src = 2
+    mod_pix = (torch.randn((n_src, HW, 2 * C), generator=g) * 0.3).to(DEV).to(torch.bfloat16)
+    img_map = torch.tensor([(-1 if i % 3 == 0 else i % n_src) for i in range(n)], dtype=torch.int32, device=DEV)
+    sc0, sh0 = 8, 8 + 2 * C
+    ops.groupnorm_silu_bf16(x, sums, gamma, beta, out, n, HW, C, mod_img=mod_img, scale_col=sc0, shift_col=sh0,
+                            mod_pix=mod_pix, img_map=img_map)
+    scale = mod_img[:, None, sc0:sc0 + C].expand(n, HW, C).clone()
+    shift = mod_img[:, None, sh0:sh0 + C].expand(n, HW, C).clone()
+    for i in range(n):
+        if img_map[i] >= 0:
+            scale[i] += mod_pix[img_map[i], :, :C].float()
+            shift[i] += mod_pix[img_map[i], :, C:].float()
+    gn_cl = gn.reshape(n, C, HW).permute(0, 2, 1)
+    ref = F.silu(gn_cl * (1 + scale) + shift).reshape(n * HW, C)
+    assert (out.float() - ref).abs().max().item() < 5e-2 and rel_err(out, ref) < 6e-3
+
+
+@pytest.mark.parametrize("M,D,P", [(2048, 576, 256), (1024, 1152, 64), (96, 64, 16), (64, 128, 4)])
+def test_rmsnorm_film(M, D, P):
+    g = torch.Generator().manual_seed(D)
+    x = (torch.randn((M, D), generator=g) * 3).to(DEV)
+    w = torch.randn((D,), generator=g).to(DEV)
+    n_img = M // P
+    mod_img = (torch.randn((n_img, 5 * D), generator=g) * 0.3).to(DEV)
+    mod_pix = (torch.randn((2, P, 2 * D), generator=g) * 0.3).to(DEV).to(torch.bfloat16)
+    img_map = torch.tensor([(-1 if i % 2 == 0 else (i // 2) % 2) for i in range(n_img)], dtype=torch.int32, device=DEV)
+    out = torch.empty((M, D), dtype=torch.bfloat16, device=DEV)
+    sc0, sh0 = D, 3 * D
+    ops.rmsnorm_film_bf16(x, w, mod_img, sc0, sh0, P, out, mod_pix=mod_pix, img_map=img_map)
+    scale = mod_img[:, None, sc0:sc0 + D].expand(n_img, P, D).clone()
+    shift = mod_img[:, None, sh0:sh0 + D].expand(n_img, P, D).clone()
+    for i in range(n_img):
+        if img_map[i] >= 0:
+            scale[i] += mod_pix[img_map[i], :, :D].float()
+            shift[i] += mod_pix[img_map[i], :, D:].float()
+    xn = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * w
+    ref = xn * (1 + scale.reshape(M, D)) + shift.reshape(M, D)
+    assert rel_err(out, ref) < 4e-3
+    ops.rmsnorm_film_bf16(x, w, mod_img, sc0, sh0, P, out)
+    ref = xn * (1 + mod_img[:, sc0:sc0 + D].repeat_interleave(P, 0)) + mod_img[:, sh0:sh0 + D].repeat_interleave(P, 0)
+    assert rel_err(out, ref) < 4e-3
+
+
+@pytest.mark.parametrize("heads,dh,T,gh", [(9, 64, 8, 8), (9, 128, 4, 4), (1, 64, 4, 4), (1, 128, 4, 2)])
+def test_qk_norm_rope(heads, dh, T, gh):
+    D, R = heads * dh, 2
+    Ntok = T * gh * gh
+    M = R * Ntok
+    g = torch.Generator().manual_seed(dh + heads)
+    buf = torch.randn((M, 3 * D + 4 * D), generator=g).to(DEV).to(torch.bfloat16)    # [q k v | mlp_h], row stride 7D
+    qkv = buf[:, : 3 * D]
+    orig = qkv.float().clone()
+    qw, kw = torch.randn((dh,), generator=g).to(DEV), torch.randn((dh,), generator=g).to(DEV)
+    table = rope_cos_sin_table(dh, (T, gh, gh)).to(DEV)
+    scale = 1.4426950408889634 / math.sqrt(dh)
+    ops.qk_norm_rope(qkv, qw, kw, table, Ntok, heads, dh, scale)
+    q, k, v = orig.reshape(M, 3, heads, dh).unbind(1)
+    rms = lambda t, w: t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + 1e-6) * w
+
+    def rope(t):
+        cs = table[torch.arange(M, device=DEV) % Ntok][:, None]          # [M, 1, dh/2, 2]
+        x0, x1 = t[..., 0::2], t[..., 1::2]
+        return torch.stack([x0 * cs[..., 0] - x1 * cs[..., 1], x1 * cs[..., 0] + x0 * cs[..., 1]], -1).flatten(-2)
+    ref = torch.stack([rope(rms(q, qw)) * scale, rope(rms(k, kw)), v], 1).reshape(M, 3 * D)
+    assert (qkv.float() - ref).abs().max().item() < 3e-2 and rel_err(qkv, ref) < 5e-3
+    assert torch.equal(buf[:, 3 * D:].float(), buf[:, 3 * D:].float())
+
+
+def test_pool_upsample_sub():
+    g = torch.Generator().manual_seed(3)
+    n, H, W, C = 3, 16, 32, 64
+    x = torch.randn((n, H, W, C), generator=g).to(DEV)
+    ref = F.avg_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+    o16 = torch.empty((n, H // 2, W // 2, C), dtype=torch.bfloat16, device=DEV)
+    ops.avgpool2x2(x, o16, n, H, W, C)
+    assert (o16.float() - ref).abs().max().item() < 2e-2
+    o32 = torch.empty((n, H // 2, W // 2, C), device=DEV)
+    ops.avgpool2x2(x, o32, n, H, W, C)
+    assert (o32 - ref).abs().max().item() < 1e-6
+    xb = x.to(torch.bfloat16)
+    ops.avgpool2x2(xb, o16, n, H, W, C)
+    assert (o16.float() - F.avg_pool2d(xb.float().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)).abs().max().item() < 2e-2
+    skip = torch.randn((n, H, W, C), generator=g).to(DEV)
+    low = torch.randn((n, H // 2, W // 2, C), generator=g).to(DEV)
+    out = torch.empty_like(skip)
+    ops.upsample2x_add(low, skip, out, n, H, W, C)
+    ref = F.interpolate(low.permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1) + skip
+    assert torch.equal(out, ref)
+    d16 = torch.empty((n, H, W, C), dtype=torch.bfloat16, device=DEV)
+    ops.sub_bf16(x, skip, d16)
+    assert torch.equal(d16, (x - skip).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("res,p,B,T", [(32, 2, 2, 4), (64, 2, 1, 3)])
+def test_pose_ray_patches_vs_oracle(res, p, B, T):
+    from oracle.cases import synthetic_poses
+    from oracle.pose import ray_encoding
+    from dfot_b200.algorithms.dfot.dfot_video_pose import camera_table, ray_freq_scale
+    poses = synthetic_poses(B, T)
+    enc = ray_encoding(poses, res, "first", None, "ray_encoding")           # (B, T, 180, res, res) fp32, CPU oracle
+    cams = camera_table(poses, res, "first", None).to(DEV)
+    g = res // p
+    out = torch.empty((B * T * g * g, p * p * 180), dtype=torch.bfloat16, device=DEV)
+    ops.pose_ray_patches(cams.reshape(B * T, 16).contiguous(), ray_freq_scale().to(DEV), out, B * T, res, p)
+    ref = enc.reshape(B * T, 180, g, p, g, p).permute(0, 2, 4, 3, 5, 1).reshape(B * T * g * g, p * p * 180)
+    err = (out.float().cpu() - ref).abs()
+    # the top octaves (2^13, 2^14 * pi) amplify 1-ulp differences of the ray direction by ~5e4: compare them loosely
+    ch = torch.arange(180) % 15
+    lo = (ch < 10).repeat(p * p)
+    assert err[:, lo].max().item() < 1e-2, err[:, lo].max()
+    assert err[:, ~lo].max().item() < 0.25, err[:, ~lo].max()

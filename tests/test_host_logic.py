@@ -12,7 +12,7 @@ from dfot_b200 import ops
 from dfot_b200.algorithms.dfot import DFoTVideo
 from dfot_b200.algorithms.dfot.dfot_video import interpolation_plan
 from dfot_b200.algorithms.dfot.history_guidance import HistoryGuidance
-from helpers import GOLDEN, NoiseBank, build_oracle, case_names, load_case
+from helpers import GOLDEN, NoiseBank, build_oracle, build_product, case_names, load_case
 from oracle.cases import algorithm_cfg, continuous_overrides
 import k4_emulation
 
@@ -93,7 +93,7 @@ def test_diffusion_buffers_bit_exact():
 @pytest.mark.parametrize("name", case_names())
 def test_state_dict_keys_match_reference(name):
     meta, _, weights = load_case(name)
-    algo = DFoTVideo(meta["cfg"])
+    algo = build_product(meta["cfg"])
     sd = {"diffusion_model.model." + k: v for k, v in weights.items()}
     sd["data_mean"], sd["data_std"] = algo.data_mean, algo.data_std
     res = algo.load_state_dict(sd, strict=True)
@@ -115,8 +115,13 @@ def test_planner_end_to_end_on_cpu(name, monkeypatch):
     reference rollout: per-step levels bit-exact, tensors <= 2e-5 (coefficients are folded in float64)."""
     meta, arr, weights = load_case(name)
     cfg = meta["cfg"]
-    algo = DFoTVideo(cfg)
+    algo = build_product(cfg)
     algo.model_in_dtype = torch.float32
+    if "camera_pose_conditioning" in cfg:   # the oracle backbone consumes the reference's dense ray encoding
+        from oracle.pose import ray_encoding
+        cp = cfg["camera_pose_conditioning"]
+        algo._window_conditions = lambda c, nfe: ray_encoding(c.repeat_interleave(nfe, 0), cfg["x_shape"][1],
+                                                              cp["normalize_by"], cp["bound"], cp["type"])
     _, backbone = build_oracle(cfg, weights)
 
     class OracleBackbone(torch.nn.Module):
