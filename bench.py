@@ -4,10 +4,14 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...   # CPU baseline arm (reference algorithm on host cores)
 
-Workload (configs[1]): K600-shaped DFoT DiT3D-XL latent sampling — latents [16,16,16], 17 frames = 5 tokens
-(2 context tokens), 50 DDIM steps, conditional history guidance (nfe=1), batch 8 per GPU.  A bench "step" is one
-full sampling pass over one batch (50 denoising steps).  Synthetic latents, random-init weights (zero-initialised
-output layers re-drawn N(0,0.02) so the network is not identically 0).
+Workloads (BASELINE.json `configs`):
+  re10k (default; the configuration the metric "RE10K-shaped DFoT + HG" is quoted on, configs[2]): dfot_video_pose,
+        UViT3DPose (channels 128/256/576/1152, blocks 3/3/6 + 20 mid, 9 heads, emb 1024), 8 frames 256x256 pixels,
+        1 context frame, vanilla history guidance scale 4.0 (2 branches), 50 DDIM steps, batch 4 per GPU.
+  k600  (configs[1]): K600-shaped DiT3D-XL latent sampling — latents [16,16,16], 17 frames = 5 tokens (2 context),
+        50 DDIM steps, conditional history guidance (nfe=1), batch 8 per GPU.
+A bench "step" is one full sampling pass over one batch (50 denoising steps).  Synthetic inputs, random-init weights
+(zero-initialised output layers re-drawn N(0,0.02) so the network is not identically 0).
 """
 import argparse
 import json
@@ -60,26 +64,113 @@ def k600_cfg(sampling_timesteps=50, spatial_mlp_ratio=4.0, depth=28, hidden=1152
                      metrics=[], metrics_batch_size=16, sanity_generation=False, raw_dir=None))
 
 
-N_FRAMES, CTX_FRAMES, N_TOKENS, CTX_TOKENS, BATCH = 17, 5, 5, 2, 8
-GEN_FRAMES = N_FRAMES - CTX_FRAMES
+def re10k_cfg(sampling_timesteps=50, guidance_scale=4.0):
+    """`dataset=realestate10k_mini algorithm=dfot_video_pose @diffusion/continuous dataset.context_length=1
+    dataset.n_frames=8 ...history_guidance.name=vanilla +guidance_scale=4.0` (README.md:74) resolved by hand from
+    dfot_video_pose.yaml, backbone/u_vit3d_pose.yaml, dataset_experiment/realestate10k_video_generation.yaml,
+    dataset/realestate10k.yaml, shortcut/diffusion/continuous.yaml."""
+    cfg = k600_cfg(sampling_timesteps)
+    cfg.update(
+        external_cond_type="action", external_cond_dim=16,
+        camera_pose_conditioning=dict(normalize_by="first", bound=None, type="ray_encoding"),
+        backbone=dict(name="u_vit3d_pose", channels=[128, 256, 576, 1152], emb_channels=1024, patch_size=2,
+                      block_types=["ResBlock", "ResBlock", "TransformerBlock", "TransformerBlock"],
+                      block_dropouts=[0.0, 0.0, 0.1, 0.1], num_updown_blocks=[3, 3, 6], num_mid_blocks=20, num_heads=9,
+                      pos_emb_type="rope", use_checkpointing=[False, False, False, True], conditioning=dict(dim=None),
+                      external_cond_dropout=0.1, use_fourier_noise_embedding=True),
+        x_shape=[3, 256, 256], max_frames=8, n_frames=8, frame_skip=20, context_frames=1,
+        latent=dict(enabled=False, type="pre_sample", suffix=None, downsampling_factor=[1, 1], shape=None,
+                    num_channels=3),
+        data_mean=[[[0.577]], [[0.517]], [[0.461]]], data_std=[[[0.249]], [[0.249]], [[0.268]]])
+    cfg["diffusion"].update(is_continuous=True, precond_scale=0.125, beta_schedule="cosine_simple_diffusion",
+                            schedule_fn_kwargs=dict(shifted=0.125, interpolated=False),
+                            training_schedule=dict(name="cosine", shift=0.125),
+                            loss_weighting=dict(strategy="sigmoid", sigmoid_bias=-1.0))
+    cfg["tasks"]["prediction"]["history_guidance"] = dict(name="vanilla", guidance_scale=guidance_scale, visualize=False)
+    return cfg
 
 
-def forward_row_gflop(cfg):
-    """Algorithmic GFLOP per backbone forward-row: per block per token 8D² + 4·N·D (+ 4·r·D²)."""
-    b = cfg["backbone"]
-    D, depth = b["hidden_size"], b["depth"]
-    r = b.get("spatial_mlp_ratio") or 0
-    P = (16 // b["patch_size"]) ** 2
-    N = N_TOKENS * P
-    per_tok = 8 * D * D + 4 * N * D + 4 * r * D * D
-    return depth * N * per_tok / 1e9
+class Workload:
+    """Shapes and counters of one BASELINE.json configuration."""
+
+    def __init__(self, name, args):
+        self.name = name
+        if name == "k600":
+            self.cfg = k600_cfg(args.sampling_steps, None if args.no_mlp else 4.0)
+            self.batch = args.batch or 8
+            self.n_tokens, self.ctx_tokens, self.gen_frames, self.nfe = 5, 2, 17 - 5, 1
+            self.x_shape = [16, 16, 16]
+            self.text = (f"K600-shaped DFoT DiT3D-XL (28x1152, 16 heads d=72, patch 1, "
+                         f"{'no MLP (fork default)' if args.no_mlp else 'MLP x4'}) latent sampling: latents 16x16x16, "
+                         f"17 frames = 5 tokens (2 context), {args.sampling_steps} DDIM steps, conditional HG (nfe=1), "
+                         f"batch {self.batch}/GPU")
+            self.l2 = "per-step activations (~0.5 GB) and weights (1.3 GB bf16) exceed the 126 MB L2; no flush needed"
+        else:
+            self.cfg = re10k_cfg(args.sampling_steps)
+            self.batch = args.batch or 4
+            self.n_tokens, self.ctx_tokens, self.gen_frames, self.nfe = 8, 1, 8 - 1, 2
+            self.x_shape = [3, 256, 256]
+            self.text = (f"RE10K-shaped dfot_video_pose single-image-to-short: UViT3DPose (128/256/576/1152 ch, blocks "
+                         f"3/3/6 + 20 mid, 9 heads, emb 1024), 8 frames 256x256 (1 context), vanilla history guidance "
+                         f"4.0 (2 branches), {args.sampling_steps} DDIM steps, batch {self.batch}/GPU")
+            self.l2 = ("per-forward activations (>1 GB per row), pose modulation cache (~1 GB per sample) and weights "
+                       "(1.1 GB bf16) exceed the 126 MB L2; no flush needed")
+
+    def inputs(self, rank):
+        import torch
+        g = torch.Generator().manual_seed(123 + rank)
+        if self.name == "k600":
+            return torch.randn((self.batch, self.n_tokens, *self.x_shape), generator=g), None
+        xs = torch.rand((self.batch, self.n_tokens, *self.x_shape), generator=g)
+        return xs, synthetic_poses(self.batch, self.n_tokens)
+
+    def forward_row_gflop(self):
+        """Algorithmic GFLOP (2*MAC of GEMM / conv / attention) the sampler must execute per backbone forward-row.
+        DiT: per block per token 8D^2 + 4ND (+ 4rD^2), adaLN per frame.  U-ViT: ResBlock 36*C^2 per
+        pixel, TransformerBlock 24*C^2 + 4*N*C per token, resampling convs 18*Cin*Cout per output pixel; the
+        camera-pose PatchEmbed and pose part of every emb_layer are constant per window and NOT counted (the
+        reference executes them every step: 6626 GFLOP/row there)."""
+        b = self.cfg["backbone"]
+        if self.name == "k600":
+            D, depth, r = b["hidden_size"], b["depth"], b.get("spatial_mlp_ratio") or 0
+            N = self.n_tokens * (16 // b["patch_size"]) ** 2
+            return depth * N * (8 * D * D + 4 * N * D + 4 * r * D * D) / 1e9
+        T, ch, L = self.n_tokens, b["channels"], len(b["channels"])
+        res = [self.x_shape[1] // b["patch_size"] // 2 ** i for i in range(L)]
+        nblk = [2 * n for n in b["num_updown_blocks"]] + [b["num_mid_blocks"]]
+        total = 0.0
+        for i in range(L):
+            px = T * res[i] ** 2
+            if b["block_types"][i] == "ResBlock":
+                total += nblk[i] * px * 36 * ch[i] ** 2
+            else:
+                total += nblk[i] * px * (24 * ch[i] ** 2 + 4 * px * ch[i])
+            if i + 1 < L:
+                total += 2 * (T * res[i + 1] ** 2) * 18 * ch[i] * ch[i + 1]
+        total += 2 * T * res[0] ** 2 * 2 * ch[0] * 12
+        return total / 1e9
+
+
+def synthetic_poses(batch, n_frames):
+    """(B, T, 16) = intrinsics (fx, fy, px, py) = (0.5, 0.9, 0.5, 0.5) + row-major [R | t] of a smooth
+    yaw / pitch / translation trajectory (valid rotations) — SURVEY.md §8c synthetic inputs."""
+    import torch
+    out = torch.zeros((batch, n_frames, 16))
+    for b in range(batch):
+        for t in range(n_frames):
+            yaw, pitch = 0.05 * t + 0.1 * b, 0.02 * t
+            cy, sy, cp, sp = math.cos(yaw), math.sin(yaw), math.cos(pitch), math.sin(pitch)
+            R = torch.tensor([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @ torch.tensor([[1, 0, 0], [0, cp, -sp], [0, sp, cp]])
+            tv = torch.tensor([0.1 * t, 0.02 * t * (b + 1), 0.05 * t + 0.3])
+            out[b, t] = torch.cat([torch.tensor([0.5, 0.9, 0.5, 0.5]), torch.cat([R, tv[:, None]], 1).flatten()])
+    return out
 
 
 def make_weights(cfg, seed=0):
     import torch
-    from dfot_b200.algorithms.dfot import DFoTVideo
+    from dfot_b200.algorithms.dfot import DFoTVideo, DFoTVideoPose
     torch.manual_seed(seed)
-    algo = DFoTVideo(cfg)
+    algo = (DFoTVideoPose if cfg["backbone"]["name"] == "u_vit3d_pose" else DFoTVideo)(cfg)
     g = torch.Generator().manual_seed(seed + 1)
     with torch.no_grad():
         for _, p in algo.named_parameters():
@@ -139,42 +230,48 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------- CPU baseline (oracle port)
-def cpu_baseline(cfg_full, seconds_budget=25.0):
+def cpu_baseline(wl, sampling_steps, seconds_budget=25.0):
     """The reference algorithm restated on the CPU (oracle/, torch fp32, all host threads) on a bounded sample of
-    the same workload: batch 1, 2 sampling steps → 2 forward-rows of the full-size DiT-XL.  NFE/s is step-count
-    independent; frames/s = NFE/s * generated frames / (50 steps * nfe)."""
+    the same workload: batch 1 and 1-2 sampling steps of the full-size backbone.  NFE/s is step-count independent;
+    frames/s = NFE/s * generated frames / (sampling steps * nfe)."""
     import torch
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from oracle.dit3d import DiT3DOracle
     from oracle.sampler import SamplerOracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = json.loads(json.dumps(cfg_full))
-    cfg["diffusion"]["sampling_timesteps"] = 2
+    cfg = json.loads(json.dumps(wl.cfg))
+    n_steps = 2 if wl.name == "k600" else 1
+    cfg["diffusion"]["sampling_timesteps"] = n_steps
     algo = make_weights(cfg, 0)
     weights = {k[len("diffusion_model.model."):]: v.detach() for k, v in algo.state_dict().items()
                if k.startswith("diffusion_model.model.")}
     probe = SamplerOracle(cfg, None)
-    model = DiT3DOracle(cfg["backbone"], probe.x_shape, probe.max_tokens, weights)
+    if wl.name == "k600":
+        from oracle.dit3d import DiT3DOracle
+        model = DiT3DOracle(cfg["backbone"], probe.x_shape, probe.max_tokens, weights)
+    else:
+        from oracle.uvit3d_pose import UViT3DPoseOracle
+        model = UViT3DPoseOracle(cfg["backbone"], probe.x_shape, probe.max_tokens, weights)
+    del algo
     oracle = SamplerOracle(cfg, model)
-    g = torch.Generator().manual_seed(123)
-    xs = torch.randn((1, N_TOKENS, 16, 16, 16), generator=g)
+    xs, conds = wl.inputs(0)
+    xs, conds = xs[:1], None if conds is None else conds[:1]
     torch.manual_seed(123)
     t0 = time.perf_counter()
     rows = 0
     with torch.no_grad():
         while True:
-            oracle.predict_videos(xs.clone(), CTX_TOKENS, None)
-            rows += 2
+            oracle.predict_videos(xs.clone(), wl.ctx_tokens, conds)
+            rows += n_steps * wl.nfe
             if time.perf_counter() - t0 > seconds_budget * 0.5 or rows >= 8:
                 break
     dt = time.perf_counter() - t0
     nfe_s = rows / dt
-    return dict(value=nfe_s * GEN_FRAMES / 50.0, unit="generated_frames/s", cores=cores, kind="port",
-                nfe_per_sec=nfe_s,
-                sample=f"oracle (reference algorithm, torch fp32 CPU, {cores} threads): batch 1 x 2 DDIM steps x "
-                       f"{rows // 2} passes = {rows} forward-rows of the full DiT-XL in {dt:.1f}s; "
-                       "frames/s derived as NFE/s*12/50")
+    return dict(value=nfe_s * wl.gen_frames / (sampling_steps * wl.nfe), unit="generated_frames/s", cores=cores,
+                kind="port", nfe_per_sec=nfe_s,
+                sample=f"oracle (reference algorithm, torch fp32 CPU, {cores} threads): batch 1 x {n_steps} DDIM step(s) "
+                       f"x {wl.nfe} branch(es) x {rows // (n_steps * wl.nfe)} pass(es) = {rows} forward-rows of the "
+                       f"full-size backbone in {dt:.1f}s; frames/s derived as NFE/s*{wl.gen_frames}/"
+                       f"({sampling_steps}*{wl.nfe})")
 
 
 # --------------------------------------------------------------------------------------- main
@@ -185,7 +282,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dfot_b200", choices=["dfot_b200", "reference"])
     ap.add_argument("--no-mlp", action="store_true", help="fork default: spatial_mlp_ratio unset (no MLP blocks)")
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--workload", default="re10k", choices=["re10k", "k600"])
+    ap.add_argument("--batch", type=int, default=0, help="samples per GPU (default: 4 for re10k, 8 for k600)")
     ap.add_argument("--sampling-steps", type=int, default=50)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -193,17 +291,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    cfg = k600_cfg(args.sampling_steps, None if args.no_mlp else 4.0)
-    workload = (f"K600-shaped DFoT DiT3D-XL (28x1152, 16 heads d=72, patch 1, "
-                f"{'no MLP (fork default)' if args.no_mlp else 'MLP x4'}) latent sampling: latents 16x16x16, 17 frames = "
-                f"5 tokens (2 context), {args.sampling_steps} DDIM steps, conditional HG (nfe=1), batch {args.batch}/GPU")
-    config = dict(workload=workload, global_batch=args.batch * world, parallelism=f"samples sharded x{world}",
-                  l2="per-step activations (~0.5 GB) and weights (1.3 GB bf16) exceed the 126 MB L2; no flush needed")
+    wl = Workload(args.workload, args)
+    cfg = wl.cfg
+    config = dict(workload=wl.text, global_batch=wl.batch * world, parallelism=f"samples sharded x{world}", l2=wl.l2)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        cb = cpu_baseline(cfg)
+        cb = cpu_baseline(wl, args.sampling_steps)
         line = dict(metric="generated_frames_per_sec", value=cb["value"], unit="generated_frames/s", n_gpus=args.gpus,
                     steps=args.steps, warmup=args.warmup, ms_per_step=None, higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="f32", data="synthetic", impl="reference", config=config,
@@ -222,10 +317,14 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     algo = make_weights(cfg, 0).to(dev).eval()
-    B = args.batch
-    g = torch.Generator().manual_seed(123 + rank)
-    xs_host = torch.randn((B, N_TOKENS, 16, 16, 16), generator=g).pin_memory()
+    B = wl.batch
+    xs_host, conds_host = wl.inputs(rank)
+    if wl.name == "re10k":
+        xs_host = algo._normalize_x(xs_host.to(dev)).cpu()      # dataset-normalised pixels, as on_after_batch_transfer
+    xs_host = xs_host.pin_memory()
+    conds_host = None if conds_host is None else conds_host.pin_memory()
     xs_dev = xs_host.to(dev)
+    conds_dev = None if conds_host is None else conds_host.to(dev)
     torch.manual_seed(123 + rank)
 
     def barrier():
@@ -234,13 +333,14 @@ def main():
         torch.cuda.synchronize()
 
     def run_resident():
-        return algo._predict_videos(xs_dev, CTX_TOKENS, None)
+        return algo._predict_videos(xs_dev, wl.ctx_tokens, conds_dev)
 
-    gathered = [torch.empty((B, N_TOKENS, 16, 16, 16), device=dev) for _ in range(world)] if world > 1 else None
+    gathered = [torch.empty_like(xs_dev) for _ in range(world)] if world > 1 else None
 
     def run_e2e():
         # public API with HOST buffers: H2D of the latents, sampling, (N>1: final sample gather), D2H of the result
-        batch = {"xs": xs_host.to(dev, non_blocking=True), "conditions": None, "gt_videos": None}
+        batch = {"xs": xs_host.to(dev, non_blocking=True), "gt_videos": None,
+                 "conditions": None if conds_host is None else conds_host.to(dev, non_blocking=True)}
         vids = algo._sample_all_videos(batch, 0)["prediction"]
         if world > 1:
             dist.all_gather(gathered, vids.contiguous())
@@ -270,11 +370,12 @@ def main():
     run_e2e()
     ms_e2e = timed(run_e2e, args.steps)
 
-    # roofline of the dominant kernel (tcgen05 GEMM): instrumented second pass over the same timed region
-    roof = None
+    # roofline of the dominant kernel (the tcgen05 GEMM kernel, which also runs the implicit-GEMM convolutions) and
+    # of the attention kernel: instrumented extra pass over the same region with CUDA events around every launch
+    roof = roof_attn = None
     if rank == 0:
-        ops_gemm = ops.gemm_bf16
-        recs = []
+        ops_gemm, ops_conv, ops_attn = ops.gemm_bf16, ops.conv3x3_bf16, ops.attention
+        recs, recs_attn = [], []
 
         def timed_gemm(a, w, out, epilogue, **kw):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -284,7 +385,21 @@ def main():
             e1.record()
             recs.append((2.0 * M * w.shape[0] * w.shape[1], e0, e1))
 
-        ops.gemm_bf16 = timed_gemm
+        def timed_conv(x, w, out, epilogue, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops_conv(x, w, out, epilogue, **kw)
+            e1.record()
+            recs.append((2.0 * x.shape[0] * x.shape[1] * x.shape[2] * w.shape[0] * 9 * w.shape[3], e0, e1))
+
+        def timed_attn(qkv, out, R, Ntok, heads, head_dim):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops_attn(qkv, out, R, Ntok, heads, head_dim)
+            e1.record()
+            recs_attn.append((4.0 * R * heads * Ntok * Ntok * head_dim, e0, e1))
+
+        ops.gemm_bf16, ops.conv3x3_bf16, ops.attention = timed_gemm, timed_conv, timed_attn
         backbone = algo.diffusion_model.model
         graphs_on = backbone.use_cuda_graph
         backbone.use_cuda_graph = False          # per-launch events need eager launches
@@ -292,10 +407,11 @@ def main():
             run_resident()
             torch.cuda.synchronize()
         finally:
-            ops.gemm_bf16 = ops_gemm
+            ops.gemm_bf16, ops.conv3x3_bf16, ops.attention = ops_gemm, ops_conv, ops_attn
             backbone.use_cuda_graph = graphs_on
         big = [(f, a.elapsed_time(b)) for f, a, b in recs if f > 1e9]
         flops, dur = sum(f for f, _ in big), sum(d for _, d in big)
+        att = [(f, a.elapsed_time(b)) for f, a, b in recs_attn]
         peaks = {}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -308,26 +424,34 @@ def main():
                     frac=ach / peak, traffic=None, launches=len(big), avg_launch_us=1e3 * dur / max(len(big), 1),
                     peak_source="MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
                     gemm_share_of_step=dur / (ms / args.steps))
+        if att:
+            af, ad = sum(f for f, _ in att), sum(d for _, d in att)
+            roof_attn = dict(bound="tensor", kernel="attention_tcgen05_kernel", achieved=af / (ad * 1e-3) / 1e12, peak=peak,
+                             unit="TFLOP/s", frac=af / (ad * 1e-3) / 1e12 / peak, traffic=None, launches=len(att),
+                             avg_launch_us=1e3 * ad / len(att), share_of_step=ad / (ms / args.steps))
     if world > 1:
         dist.barrier()
 
     if rank == 0:
         per_step_s = ms / args.steps / 1e3
-        frames = B * world * GEN_FRAMES
-        rows = B * world * args.sampling_steps
+        frames = B * world * wl.gen_frames
+        rows = B * world * args.sampling_steps * wl.nfe
         per_e2e_s = ms_e2e / args.steps / 1e3
-        bytes_in = xs_host.numel() * 4
+        bytes_out = xs_host.numel() * 4
+        bytes_in = bytes_out + (0 if conds_host is None else conds_host.numel() * 4)
         line = dict(metric="generated_frames_per_sec", value=frames / per_step_s, unit="generated_frames/s",
                     n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps,
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                     config=config, nfe_per_sec=rows / per_step_s,
-                    model_tflops=rows * forward_row_gflop(cfg) / per_step_s / 1e3,
+                    model_tflops=rows * wl.forward_row_gflop() / per_step_s / 1e3,
                     e2e=dict(value=frames / per_e2e_s, unit="generated_frames/s", h2d_bytes_per_step=bytes_in,
-                             d2h_bytes_per_step=bytes_in, nfe_per_sec=rows / per_e2e_s),
+                             d2h_bytes_per_step=bytes_out, nfe_per_sec=rows / per_e2e_s),
                     gpu_launches=int(launches), clocks=clocks.summary(), roofline=roof)
+        if roof_attn is not None:
+            line["roofline_attention"] = roof_attn
         line["config"]["cuda_graph"] = bool(algo.diffusion_model.model.use_cuda_graph)
         if not args.skip_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(cfg)
+            line["cpu_baseline"] = cpu_baseline(wl, args.sampling_steps)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -210,8 +210,7 @@ class UViT3DPose(nn.Module):
         if self._packed is not None and key == self._packed_key:
             return self._packed
         dev = self.embed_input.proj.weight.device
-        if dev.type != "cuda":
-            raise RuntimeError("dfot_b200: UViT3DPose runs on CUDA only (no CPU fallback); move the module to a B200")
+        ops.require_cuda(dev, "UViT3DPose")
         bf = lambda w: ops.cast_bf16(w.detach().float().contiguous())
         f32 = lambda b: b.detach().float().contiguous()
         conv_w = lambda c: bf(c.weight.detach().float().permute(0, 2, 3, 1))      # [Cout, 3, 3, Cin]
@@ -337,8 +336,7 @@ class UViT3DPose(nn.Module):
     def prepare_pose(self, cond: PoseCondition):
         """Make the HBM-resident modulation cache hold `cond` (no-op when it already does)."""
         dev = cond.cams.device
-        if dev.type != "cuda":
-            raise RuntimeError("dfot_b200: UViT3DPose needs CUDA tensors (no CPU fallback)")
+        ops.require_cuda(dev, "UViT3DPose.prepare_pose")
         self.packed()
         n_cond, T = cond.cams.shape[:2]
         if T != self.temporal_length:
@@ -383,8 +381,7 @@ class UViT3DPose(nn.Module):
                 external_cond_mask: Optional[torch.Tensor] = None, out_dtype=torch.float32) -> torch.Tensor:
         """x [R,T,C,H,W] f32|bf16; noise_levels [R,T] int64 | f32; external_cond: PoseCondition (fast path) or the
         reference's dense (R,T,180,H,W) ray-encoding tensor; external_cond_mask [R] bool (True = drop the pose)."""
-        if not x.is_cuda:
-            raise RuntimeError("dfot_b200: UViT3DPose.forward needs CUDA tensors (no CPU fallback)")
+        ops.require_cuda(x.device, "UViT3DPose.forward")
         assert x.shape[1] == self.temporal_length, \
             f"Temporal length of U-ViT is set to {self.temporal_length}, but input has temporal length {x.shape[1]}."
         assert external_cond is not None, "External condition (camera pose) is required for U-ViT3DPose model."
@@ -400,8 +397,8 @@ class UViT3DPose(nn.Module):
             raise ValueError(f"conditioning covers {len(row_map)} rows, x has {R}")
         base = (row_map[:, None] * T + torch.arange(T, dtype=torch.int32)[None, :]).to(dev, non_blocking=True)
         levels = noise_levels if noise_levels.dtype in (torch.int64, torch.float32) else noise_levels.float()
-        graph_ok = self.use_cuda_graph and not torch.cuda.is_current_stream_capturing() and \
-            isinstance(external_cond, PoseCondition)
+        graph_ok = self.use_cuda_graph and x.is_cuda and isinstance(external_cond, PoseCondition) and \
+            not torch.cuda.is_current_stream_capturing()
         if not graph_ok:
             ws = self._workspace(R, dev, out_dtype)
             self._set_img_map(ws["img_map"], base, external_cond_mask)

@@ -30,6 +30,12 @@ def total_launches() -> int:
     return _abi.launch_count() + _replayed_launches
 
 
+def require_cuda(device, what: str) -> None:
+    """There is no CPU implementation of anything in this package: callers guard their entry points with this."""
+    if torch.device(device).type != "cuda":
+        raise RuntimeError(f"dfot_b200: {what} runs on CUDA only (no CPU fallback); move it to a B200")
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 

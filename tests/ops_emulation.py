@@ -1,0 +1,175 @@
+"""Test infrastructure: CPU (torch fp32) restatements of the *contracts* of the C-ABI kernels in include/dfot_b200.h,
+used to drive the product's host-side orchestration (weight packing, buffer flow, column offsets, layouts) on a machine
+without a GPU.  Never imported by the product; the `-m gpu` tests check the real kernels against the same contracts."""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from dfot_b200 import ops
+
+BF = torch.bfloat16
+
+
+def cast_bf16(src, out=None):
+    if out is None:
+        return src.to(BF)
+    out.copy_(src.to(BF))
+    return out
+
+
+def patchify_bf16(x, out, frames, C, H, W, p):
+    x = x.float().reshape(frames, C, H // p, p, W // p, p).permute(0, 2, 4, 1, 3, 5).reshape(-1, C * p * p)
+    out[:, : C * p * p] = x.to(BF)
+
+
+def unpatchify(tok, x, frames, C, H, W, p):
+    t = tok[:, : p * p * C].reshape(frames, H // p, W // p, p, p, C).permute(0, 5, 1, 3, 2, 4).reshape(frames, C, H, W)
+    x.copy_(t.reshape(x.shape).to(x.dtype))
+
+
+def _epilogue(acc, out, epilogue, bias, resid):
+    if bias is not None:
+        acc = acc + bias
+    if epilogue == ops.EPI_SILU_BF16:
+        acc = F.silu(acc)
+    elif epilogue == ops.EPI_GELU_BF16:
+        acc = F.gelu(acc, approximate="tanh")
+    elif epilogue == ops.EPI_RESID_F32:
+        acc = acc + resid.reshape(acc.shape)
+    elif epilogue not in (ops.EPI_F32, ops.EPI_BF16):
+        raise NotImplementedError(epilogue)
+    out.copy_(acc.reshape(out.shape).to(out.dtype))
+
+
+def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, M=None, **kw):
+    assert a.dtype == BF and w.dtype == BF
+    M = a.shape[0] if M is None else M
+    _epilogue(a[:M].float() @ w.float().t(), out[:M], epilogue, bias, None if resid is None else resid[:M])
+
+
+def conv3x3_bf16(x, w, out, epilogue, bias=None, resid=None):
+    assert x.dtype == BF and w.dtype == BF
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), None, padding=1).permute(0, 2, 3, 1)
+    _epilogue(y.reshape(-1, w.shape[0]), out, epilogue, bias, resid)
+
+
+def groupnorm_stats(x, sums, n_img, HW, C, groups=32):
+    xg = x.double().reshape(n_img, HW, groups, C // groups)
+    sums[..., 0] = xg.sum((1, 3))
+    sums[..., 1] = (xg * xg).sum((1, 3))
+
+
+def _film(n_img, HW, C, mod_img, scale_col, shift_col, mod_pix, img_map):
+    scale = mod_img[:, None, scale_col:scale_col + C].expand(n_img, HW, C).clone()
+    shift = mod_img[:, None, shift_col:shift_col + C].expand(n_img, HW, C).clone()
+    if mod_pix is not None:
+        pix = mod_pix.float().reshape(-1, HW, 2 * C)
+        for i, src in enumerate(img_map.tolist()):
+            if src >= 0:
+                scale[i] += pix[src, :, :C]
+                shift[i] += pix[src, :, C:]
+    return scale, shift
+
+
+def groupnorm_silu_bf16(x, sums, gamma, beta, out, n_img, HW, C, groups=32, eps=1e-6, mod_img=None, scale_col=0,
+                        shift_col=0, mod_pix=None, img_map=None):
+    cnt = HW * (C // groups)
+    mean = (sums[..., 0] / cnt)
+    var = (sums[..., 1] / cnt - mean * mean).clamp(min=0)
+    xg = x.float().reshape(n_img, HW, groups, C // groups)
+    y = (xg - mean[:, None, :, None].float()) * torch.rsqrt(var.float() + eps)[:, None, :, None]
+    y = y.reshape(n_img, HW, C) * gamma + beta
+    if mod_img is not None:
+        scale, shift = _film(n_img, HW, C, mod_img, scale_col, shift_col, mod_pix, img_map)
+        y = y * (1 + scale) + shift
+    out.copy_(F.silu(y).reshape(out.shape).to(BF))
+
+
+def rmsnorm_film_bf16(x, weight, mod_img, scale_col, shift_col, tokens_per_img, out, mod_pix=None, img_map=None,
+                      eps=1e-6):
+    M, D = x.shape
+    n_img = M // tokens_per_img
+    scale, shift = _film(n_img, tokens_per_img, D, mod_img, scale_col, shift_col, mod_pix, img_map)
+    xn = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * weight
+    out.copy_((xn * (1 + scale.reshape(M, D)) + shift.reshape(M, D)).to(BF))
+
+
+def qk_norm_rope(qkv, q_weight, k_weight, rope_cs, tokens_per_sample, heads, head_dim, q_scale, eps=1e-6):
+    M = qkv.shape[0]
+    D = heads * head_dim
+    q, k = (qkv[:, i * D:(i + 1) * D].float().reshape(M, heads, head_dim) for i in range(2))
+    cs = rope_cs[torch.arange(M) % tokens_per_sample][:, None]
+
+    def f(t, w, mul):
+        t = t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + eps) * w
+        x0, x1 = t[..., 0::2], t[..., 1::2]
+        return (torch.stack([x0 * cs[..., 0] - x1 * cs[..., 1], x1 * cs[..., 0] + x0 * cs[..., 1]], -1).flatten(-2)
+                * mul).reshape(M, D)
+    qkv[:, :D] = f(q, q_weight, q_scale).to(BF)
+    qkv[:, D:2 * D] = f(k, k_weight, 1.0).to(BF)
+
+
+def attention(qkv, out, R, Ntok, heads, head_dim):
+    D = heads * head_dim
+    q, k, v = qkv.float().reshape(R, Ntok, 3, heads, head_dim).permute(2, 0, 3, 1, 4).unbind(0)
+    w = torch.softmax(q @ k.transpose(-1, -2) * math.log(2.0), dim=-1)       # q carries scale * log2(e)
+    out.copy_((w @ v).transpose(1, 2).reshape(R * Ntok, D).to(BF))
+
+
+def avgpool2x2(x, out, n_img, H, W, C):
+    y = F.avg_pool2d(x.float().reshape(n_img, H, W, C).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+    out.copy_(y.reshape(out.shape).to(out.dtype))
+
+
+def sub_bf16(a, b, out):
+    out.copy_((a - b).to(BF))
+
+
+def upsample2x_add(low, skip, out, n_img, H, W, C):
+    up = F.interpolate(low.reshape(n_img, H // 2, W // 2, C).permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    out.copy_((up.permute(0, 2, 3, 1).reshape(skip.shape) + skip))
+
+
+def pose_ray_patches(cams, freq_scale, out, frames, res, p):
+    lin = torch.arange(res, dtype=torch.float32) + 0.5
+    fx, fy, px, py = (cams[:, i][:, None, None] for i in range(4))
+    dx = ((lin[None, None, :] - px) / fx).expand(frames, res, res)
+    dy = ((lin[None, :, None] - py) / fy).expand(frames, res, res)
+    Rinv = cams[:, 4:13].reshape(frames, 3, 3)
+    d = torch.stack([Rinv[:, i, 0][:, None, None] * dx + Rinv[:, i, 1][:, None, None] * dy + Rinv[:, i, 2][:, None, None]
+                     for i in range(3)], -1)
+    o = cams[:, None, None, 13:16].expand(frames, res, res, 3)
+
+    def enc(v):
+        e = (v[..., None] * freq_scale).flatten(-2)
+        return torch.sin(torch.cat([e, e + 0.5 * math.pi], -1))
+    full = torch.cat([enc(o), enc(d)], -1)                                      # frames, res, res, 12*n_freq
+    g, ch = res // p, full.shape[-1]
+    rows = full.reshape(frames, g, p, g, p, ch).permute(0, 1, 3, 2, 4, 5).reshape(frames * g * g, p * p * ch)
+    out[:, : p * p * ch] = rows.to(BF)
+
+
+def noise_features(levels, out, fourier_freqs=None, fourier_phases=None):
+    k = levels.float().reshape(-1, 1)
+    dim = out.shape[-1]
+    if fourier_freqs is not None:
+        v = torch.cos(k * fourier_freqs + fourier_phases) * math.sqrt(2.0)
+    else:
+        half = dim // 2
+        f = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+        v = torch.cat([torch.cos(k * f), torch.sin(k * f)], -1)
+    out.copy_(v.reshape(out.shape).to(BF))
+
+
+ALL = ["cast_bf16", "patchify_bf16", "unpatchify", "gemm_bf16", "conv3x3_bf16", "groupnorm_stats", "groupnorm_silu_bf16",
+       "rmsnorm_film_bf16", "qk_norm_rope", "attention", "avgpool2x2", "sub_bf16", "upsample2x_add", "pose_ray_patches",
+       "noise_features"]
+
+
+def install(monkeypatch):
+    """Route the product's op calls to the CPU contract emulations and lift its CUDA-only guards (tests only)."""
+    g = globals()
+    for name in ALL:
+        monkeypatch.setattr(ops, name, g[name])
+    monkeypatch.setattr(ops, "require_cuda", lambda *a, **k: None)

@@ -12,7 +12,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from dfot_b200.algorithms.dfot import DFoTVideo  # noqa: E402
-from helpers import NoiseBank, build_oracle, case_names, load_case  # noqa: E402
+from helpers import NoiseBank, build_oracle, build_product, case_names, load_case  # noqa: E402
 from oracle.cases import algorithm_cfg, continuous_overrides  # noqa: E402
 
 DEV = "cuda"
@@ -28,7 +28,7 @@ def psnr(pred, ref, n_ctx):
 
 
 def load_product(cfg, weights):
-    algo = DFoTVideo(cfg)
+    algo = build_product(cfg)
     sd = {"diffusion_model.model." + k: v for k, v in weights.items()}
     sd["data_mean"], sd["data_std"] = algo.data_mean, algo.data_std
     algo.load_state_dict(sd, strict=True)
@@ -159,3 +159,93 @@ def test_api_level_calls():
         assert (px.cpu() - xr).abs().max() < 1e-5
         comp = mgr.compose(px)
         assert (comp.cpu() - ohg.full_compose(tab, excl, xr)).abs().max() < 1e-4
+
+
+# ------------------------------------------------------------------ U-ViT3DPose (RE10K backbone)
+def uvit_cfg(channels, heads, res, frames, updown=(1, 1, 2), mid=2, emb=64, **over):
+    base = {**continuous_overrides(), "external_cond_type": "action", "external_cond_dim": 16,
+            "camera_pose_conditioning": dict(normalize_by="first", bound=None, type="ray_encoding"),
+            "backbone": dict(name="u_vit3d_pose", channels=list(channels), emb_channels=emb, patch_size=2,
+                             block_types=["ResBlock", "ResBlock", "TransformerBlock", "TransformerBlock"],
+                             block_dropouts=[0.0] * 4, num_updown_blocks=list(updown), num_mid_blocks=mid,
+                             num_heads=heads, pos_emb_type="rope", use_checkpointing=[False] * 4,
+                             conditioning=dict(dim=None), external_cond_dropout=0.1, use_fourier_noise_embedding=True),
+            "x_shape": [3, res, res], "max_frames": frames, "n_frames": frames, "context_frames": 1,
+            "data_mean": [[[0.5]]] * 3, "data_std": [[[0.5]]] * 3, "diffusion.sampling_timesteps": 3,
+            "tasks.prediction.history_guidance": dict(name="vanilla", guidance_scale=2.0, visualize=False)}
+    base.update(over)
+    return algorithm_cfg(**base)
+
+
+def random_pose_algo(cfg, seed):
+    from dfot_b200.algorithms.dfot import DFoTVideoPose
+    torch.manual_seed(seed)
+    algo = DFoTVideoPose(cfg)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for _, p in algo.named_parameters():
+            if bool((p == 0).all()):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    return algo
+
+
+@pytest.mark.parametrize("channels,heads,res,frames", [((32, 32, 64, 128), 1, 32, 4), ((64, 128, 128, 256), 2, 64, 3)])
+def test_uvit3d_pose_forward_vs_oracle(channels, heads, res, frames):
+    """One backbone forward (both the dense reference-style conditioning and the cached fast path, with one row's pose
+    masked) against the fp32 oracle on identical weights."""
+    from oracle.cases import synthetic_poses
+    from oracle.pose import ray_encoding
+    from oracle.uvit3d_pose import UViT3DPoseOracle
+    cfg = uvit_cfg(channels, heads, res, frames)
+    algo = random_pose_algo(cfg, 5)
+    model = algo.diffusion_model.model
+    weights = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    oracle = UViT3DPoseOracle(cfg["backbone"], cfg["x_shape"], frames, weights)
+    g = torch.Generator().manual_seed(77)
+    B, nfe = 2, 2
+    R = B * nfe
+    x = torch.randn((R, frames, 3, res, res), generator=g)
+    levels = torch.randn((R, frames), generator=g)
+    poses = synthetic_poses(B, frames)
+    enc = ray_encoding(poses.repeat_interleave(nfe, 0), res, "first", None, "ray_encoding")
+    mask = torch.tensor([True, False] * B)
+    ref = oracle(x, levels, enc, mask)
+    algo = algo.to(DEV).eval()
+    model = algo.diffusion_model.model
+    cond = algo._window_conditions(poses.to(DEV), nfe)
+    for attempt in range(3):   # eager, graph capture, graph replay
+        out = model(x.to(DEV), levels.to(DEV), cond, mask.to(DEV)).cpu()
+        err = (out - ref).abs().max().item()
+        assert err <= STEP_TOL, f"fast path (call {attempt}): max-abs error {err} (ref max {ref.abs().max().item()})"
+    out = model(x.to(DEV), levels.to(DEV), enc.to(DEV), mask.to(DEV)).cpu()
+    err = (out - ref).abs().max().item()
+    assert err <= STEP_TOL, f"dense path: max-abs error {err}"
+
+
+def test_uvit3d_pose_rollout_vs_oracle():
+    """Medium U-ViT3DPose (head dims 64/128, 64x64 frames) vanilla-HG rollout vs the oracle with a shared noise stream."""
+    from oracle.cases import synthetic_poses
+    cfg = uvit_cfg((64, 128, 128, 256), 2, 64, 4)
+    algo = random_pose_algo(cfg, 2)
+    weights = {k[len("diffusion_model.model."):]: v.detach().clone() for k, v in algo.state_dict().items()
+               if k.startswith("diffusion_model.model.")}
+    g = torch.Generator().manual_seed(123)
+    xs = torch.randn((2, 4, 3, 64, 64), generator=g)
+    conds = synthetic_poses(2, 4)
+    bank = NoiseBank(17)
+    oracle, _ = build_oracle(cfg, weights, randn=bank.randn, randn_like=bank.randn_like)
+    oracle.trace = []
+    ref = oracle.predict_videos(xs.clone(), 1, conds)
+    bank2 = NoiseBank(17)
+    algo = algo.to(DEV).eval()
+    algo.diffusion_model.noise_source = lambda shape, device: bank2.randn(shape).to(device)
+    algo.trace = []
+    out = algo._predict_videos(xs.to(DEV), 1, conds.to(DEV)).cpu()
+    assert len(algo.trace) == len(oracle.trace)
+    worst = 0.0
+    for t, o in zip(algo.trace, oracle.trace):
+        assert np.array_equal(t["levels_from"], o["levels_from"].numpy())
+        assert np.array_equal(t["levels_to"], o["levels_to"].numpy())
+        worst = max(worst, (t["model_out"].cpu() - o["model_out"]).abs().max().item())
+    assert worst <= STEP_TOL, f"per-step denoiser output max-abs error {worst}"
+    assert psnr(out, ref, 1) >= PSNR_MIN

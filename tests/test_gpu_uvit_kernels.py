@@ -14,6 +14,11 @@ from dfot_b200.algorithms.dfot.backbones.dit.dit3d import rope_cos_sin_table  # 
 DEV = "cuda"
 
 
+def bf16_close(out, ref, atol=2e-3):
+    """bf16 output vs fp32 reference: one bf16 ulp (2^-8 relative) plus a small absolute slack."""
+    return bool(((out.float() - ref).abs() <= ref.abs() * 2.0 ** -7 + atol).all())
+
+
 def rel_err(a, b):
     return ((a.float() - b.float()).norm() / b.float().norm().clamp(min=1e-12)).item()
 
@@ -80,7 +85,7 @@ def test_groupnorm_stats_and_apply(n, HW, C, dt):
     out = torch.empty((n * HW, C), dtype=torch.bfloat16, device=DEV)
     ops.groupnorm_silu_bf16(x, sums, gamma, beta, out, n, HW, C)
     ref = F.silu(gn).reshape(n, C, HW).permute(0, 2, 1).reshape(n * HW, C)
-    assert (out.float() - ref).abs().max().item() < 3e-2 and rel_err(out, ref) < 6e-3
+    assert bf16_close(out, ref, 1e-2) and rel_err(out, ref) < 6e-3
     # FiLM: per-image f32 part + per-pixel bf16 part through an image map (-1 = masked)
     mod_img = torch.randn((n, 4 * C + 8), generator=g).to(DEV) * 0.3
     n_src = 2
@@ -97,7 +102,7 @@ def test_groupnorm_stats_and_apply(n, HW, C, dt):
             shift[i] += mod_pix[img_map[i], :, C:].float()
     gn_cl = gn.reshape(n, C, HW).permute(0, 2, 1)
     ref = F.silu(gn_cl * (1 + scale) + shift).reshape(n * HW, C)
-    assert (out.float() - ref).abs().max().item() < 5e-2 and rel_err(out, ref) < 6e-3
+    assert bf16_close(out, ref, 1e-2) and rel_err(out, ref) < 6e-3
 
 
 @pytest.mark.parametrize("M,D,P", [(2048, 576, 256), (1024, 1152, 64), (96, 64, 16), (64, 128, 4)])
@@ -147,7 +152,7 @@ def test_qk_norm_rope(heads, dh, T, gh):
         x0, x1 = t[..., 0::2], t[..., 1::2]
         return torch.stack([x0 * cs[..., 0] - x1 * cs[..., 1], x1 * cs[..., 0] + x0 * cs[..., 1]], -1).flatten(-2)
     ref = torch.stack([rope(rms(q, qw)) * scale, rope(rms(k, kw)), v], 1).reshape(M, 3 * D)
-    assert (qkv.float() - ref).abs().max().item() < 3e-2 and rel_err(qkv, ref) < 5e-3
+    assert bf16_close(qkv, ref, 1e-2) and rel_err(qkv, ref) < 5e-3
     assert torch.equal(buf[:, 3 * D:].float(), buf[:, 3 * D:].float())
 
 

@@ -107,6 +107,43 @@ def test_ops_fail_loudly_without_cuda():
     algo = DFoTVideo(_tiny())
     with pytest.raises(RuntimeError, match="CUDA"):
         algo.diffusion_model.model(torch.zeros(1, 8, 4, 8, 8), torch.zeros(1, 8, dtype=torch.long))
+    meta, arr, _ = load_case("uvit_pose_vanilla")
+    pose = build_product(meta["cfg"])
+    cond = pose._window_conditions(torch.from_numpy(arr["conds"]), 1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pose.diffusion_model.model(torch.zeros(1, 4, 3, 32, 32), torch.zeros(1, 4), cond)
+
+
+@pytest.mark.parametrize("name", ["uvit_pose_vanilla", "uvit_pose_stabilized_interp"])
+def test_uvit_host_orchestration_with_emulated_kernels(name, monkeypatch):
+    """The product's U-ViT3DPose host side (weight packing, channel-last buffer flow, FiLM column offsets, per-window
+    pose cache, row maps, K4 tables) driven by CPU restatements of the kernel contracts must reproduce the
+    reference rollout.  bf16 operand rounding is emulated too, hence the 2e-2 / 40 dB gates of BASELINE.json."""
+    import ops_emulation
+    meta, arr, weights = load_case(name)
+    cfg = meta["cfg"]
+    algo = build_product(cfg)
+    sd = {"diffusion_model.model." + k: v for k, v in weights.items()}
+    sd["data_mean"], sd["data_std"] = algo.data_mean, algo.data_std
+    algo.load_state_dict(sd, strict=True)
+    ops_emulation.install(monkeypatch)
+    monkeypatch.setattr(ops, "sampler_step_hg", k4_emulation.emulate)
+    algo.model_in_dtype = torch.float32
+    torch.manual_seed(meta["sampling_seed"])
+    algo.diffusion_model.noise_source = lambda shape, device: torch.randn(shape)
+    algo.trace = []
+    out = algo._predict_videos(torch.from_numpy(arr["xs"]).clone(), cfg["context_frames"], torch.from_numpy(arr["conds"]))
+    assert len(algo.trace) == int(arr["n_steps"])
+    worst = 0.0
+    for i, t in enumerate(algo.trace):
+        p = f"step{i:03d}."
+        assert np.array_equal(t["levels_from"], arr[p + "levels_from"])
+        assert np.array_equal(t["cond_mask"], arr[p + "cond_mask"])
+        worst = max(worst, np.abs(t["model_out"].numpy() - arr[p + "model_out"]).max())
+    assert worst <= 2e-2, worst
+    ref = arr["prediction"][:, cfg["context_frames"]:]
+    mse = float(((out.numpy()[:, cfg["context_frames"]:] - ref) ** 2).mean())
+    assert 10 * np.log10((ref.max() - ref.min()) ** 2 / max(mse, 1e-30)) >= 40.0
 
 
 @pytest.mark.parametrize("name", case_names())
