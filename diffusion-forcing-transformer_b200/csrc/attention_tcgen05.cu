@@ -63,6 +63,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// Latency-critical hand-offs (softmax <-> MMA issuer): plain try_wait polling, no suspend-time hint.
+__device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spin > (1u << 28)) {   // bounded: a protocol bug must trap, never hang the GPU
+      printf("dfot_attention: mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
@@ -112,6 +131,37 @@ __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (P, bf16 pairs packed in 32-bit columns, lane = row) is read
+// straight from tensor memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -396,6 +446,373 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params 
   }
 }
 
+// =====================================================================================================================
+// Kernel 2 — two query tiles per CTA, FA4-style role split (used whenever a sample has more than one query tile):
+//   warp 0    : TMA producer — both 128-row Q tiles once per work item, K / V tiles through 2-stage rings
+//   warp 1    : MMA issuer  — S_t = Q_t·K_jᵀ into TMEM; O_t += P_t·V_j with the A operand P_t read FROM TENSOR MEMORY
+//               (P aliases the first 64 columns of its S tile as packed bf16 pairs) and O_t accumulated in TMEM.
+//               Issue order  S0(0) S1(0) | PV0(j) S0(j+1) PV1(j) S1(j+1) ...  — tensor-core ops execute in issue order,
+//               which is what makes the S/P aliasing safe without extra barriers.
+//   warps 2-3 : idle (they pad warpgroup 0 so that the register reallocation below is warpgroup-aligned)
+//   warps 4-7 : softmax warpgroup of Q tile 0;  warps 8-11 : softmax warpgroup of Q tile 1.  A thread owns a whole
+//               query row (128 scores in registers): row max / row sum need no cross-thread exchange at all, and the
+//               two warpgroups run half a tile out of phase, so the MUFU-bound exp2 phase of one overlaps the
+//               TMEM-load / max / store phases of the other and both overlap the MMAs.
+//   Lazy rescaling: the running maximum used for exp2 is only raised when a tile's maximum exceeds it by more than 8
+//               (log2 units; p <= 256 is harmless in fp32/bf16), so the O_t tile in TMEM is rescaled
+//               (tcgen05.ld → mul → tcgen05.st, by the row's own thread) a handful of times per row instead of once
+//               per KV tile; l and O always share the same reference maximum, so the result is exact.
+//   head_dim <= 64 (SEP_P): tensor memory has room for P_t outside S_t (S 2x128 | P 2x64 | O 2x64 columns), so
+//               S_t(j+1) no longer has to wait for PV_t(j): it is issued as soon as the softmax warpgroup has pulled
+//               S_t(j) into registers (S_FREE) and runs under the exp2 phase — the softmax never waits for the MMAs.
+//   Registers: setmaxnreg moves the register budget from the TMA/MMA warpgroup (96) to the softmax warpgroups (200),
+//               so the 128 scores + packing temporaries of a row never spill.
+// With head_dim 64 the kernel is bound by the 16/clk/SM MUFU (exp2) rate, not the tensor pipe: 128x128 exps = 1024
+// cycles vs 512 cycles of MMA per tile — the roofline is ~50 % of the bf16 tensor peak.
+constexpr int kThreads2 = 384;
+template <int DH, int DP>
+__global__ void __launch_bounds__(kThreads2, 1)
+attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+  constexpr int ATOMS = (DP + 63) / 64;
+  constexpr int TILE_BYTES = ATOMS * kAtomBytes;
+  constexpr int KS_QK = DP / 16, KS_PV = BKV / 16;
+  constexpr uint32_t IDESC_S = make_idesc(BKV, false);
+  constexpr uint32_t IDESC_PV = make_idesc(DP, true);
+  constexpr bool SEP_P = DP <= 64;                   // P_t has its own TMEM columns
+  // aliased: S_t at 128*t (P_t = its first 64 columns), O_t at 256 + 128*t;  separate: S 128*t, P 256 + 64*t, O 384 + 64*t
+  constexpr uint32_t TMEM_S = 0, TMEM_P = SEP_P ? 256 : 0, P_STRIDE = SEP_P ? 64 : 128;
+  constexpr uint32_t TMEM_O = SEP_P ? 384 : 256, O_STRIDE = SEP_P ? 64 : 128;
+  constexpr float kRescaleThreshold = 8.0f;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  if ((base & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("dfot_attention: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  const uint32_t sQ = base;                          // 2 tiles
+  const uint32_t sK = sQ + 2 * TILE_BYTES;           // 2 stages
+  const uint32_t sV = sK + 2 * TILE_BYTES;           // 2 stages
+  const uint32_t bars = sV + 2 * TILE_BYTES;
+  enum { Q_FULL = 0, Q_EMPTY = 1, K_FULL = 2, K_EMPTY = 4, V_FULL = 6, V_EMPTY = 8, S_FULL = 10, P_FULL = 12,
+         O_DONE = 14, O_FREE = 16, S_FREE = 18, PV_DONE = 20, N_BARS = 22 };
+  auto bar = [&](int id) { return bars + 8u * id; };
+  const uint32_t tmem_slot = bars + 8u * N_BARS;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    for (int i = 0; i < N_BARS; ++i) {
+      const bool from_softmax = (i >= P_FULL && i < P_FULL + 2) || (i >= O_FREE && i < O_FREE + 2) ||
+                                (i >= S_FREE && i < S_FREE + 2);
+      mbar_init(bar(i), from_softmax ? 4 : 1);       // one arrival per warp of the tile's softmax warpgroup
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int n_kv = p.kv_tiles;
+  const int q_pairs = (p.q_tiles + 1) >> 1;
+  auto item_coord = [&](int item, int& r, int& h, int& qp) {
+    qp = item % q_pairs;                             // consecutive items share (r, h): K/V stay hot in L2
+    const int rh = item / q_pairs;
+    h = rh % p.heads;
+    r = rh / p.heads;
+  };
+
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t g = 0, it = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        int r, h, qp;
+        item_coord(item, r, h, qp);
+        const int row0 = r * p.Ntok;
+        mbar_wait(bar(Q_EMPTY), (it & 1u) ^ 1u);
+        mbar_expect_tx(bar(Q_FULL), 2 * TILE_BYTES);
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int a = 0; a < ATOMS; ++a)
+            tma_load_3d(sQ + t * TILE_BYTES + a * kAtomBytes, &tmap, bar(Q_FULL), a * 64, h, row0 + (2 * qp + t) * BQ);
+        for (int j = 0; j < n_kv; ++j, ++g) {
+          const uint32_t st = g & 1u, ph = (g >> 1) & 1u;
+          mbar_wait(bar(K_EMPTY + st), ph ^ 1u);
+          mbar_expect_tx(bar(K_FULL + st), TILE_BYTES);
+#pragma unroll
+          for (int a = 0; a < ATOMS; ++a)
+            tma_load_3d(sK + st * TILE_BYTES + a * kAtomBytes, &tmap, bar(K_FULL + st), a * 64, p.heads + h,
+                        row0 + j * BKV);
+          mbar_wait(bar(V_EMPTY + st), ph ^ 1u);
+          mbar_expect_tx(bar(V_FULL + st), TILE_BYTES);
+#pragma unroll
+          for (int a = 0; a < ATOMS; ++a)
+            tma_load_3d(sV + st * TILE_BYTES + a * kAtomBytes, &tmap, bar(V_FULL + st), a * 64, 2 * p.heads + h,
+                        row0 + j * BKV);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t g = 0, it = 0;
+      uint32_t n_p[2] = {0, 0};                      // P_FULL phases consumed per tile
+      uint32_t n_f[2] = {0, 0};                      // S_FREE phases consumed per tile (SEP_P)
+      uint32_t n_o[2] = {0, 0};                      // items in which tile t was active (O_FREE phases)
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        int r, h, qp;
+        item_coord(item, r, h, qp);
+        const bool has1 = (2 * qp + 1) * BQ < p.Ntok;     // second query tile holds rows of this sample
+        auto issue_s = [&](int t, uint32_t st) {          // S_t = Q_t · K^T (K stage st)
+          const uint32_t d = tmem_base + TMEM_S + (uint32_t)t * 128u;
+#pragma unroll
+          for (int s = 0; s < KS_QK; ++s) {
+            const uint32_t off = (uint32_t)(s >> 2) * kAtomBytes + (uint32_t)(s & 3) * 32u;
+            umma_bf16(d, desc_kmajor(sQ + t * TILE_BYTES + off), desc_kmajor(sK + st * TILE_BYTES + off), IDESC_S,
+                      s > 0 ? 1u : 0u);
+          }
+          umma_commit(bar(S_FULL + t));
+        };
+        auto issue_pv = [&](int t, uint32_t st, bool first) {   // O_t (+)= P_t · V (V stage st), A from TMEM
+          const uint32_t d = tmem_base + TMEM_O + (uint32_t)t * O_STRIDE;
+          const uint32_t a = tmem_base + TMEM_P + (uint32_t)t * P_STRIDE;
+#pragma unroll
+          for (int s = 0; s < KS_PV; ++s)
+            umma_bf16_ts(d, a + (uint32_t)(8 * s), desc_mnmajor(sV + st * TILE_BYTES + (uint32_t)s * 2048u, kAtomBytes),
+                         IDESC_PV, (first && s == 0) ? 0u : 1u);
+        };
+        mbar_wait(bar(Q_FULL), it & 1u);
+        {   // prologue: S_t(0)
+          const uint32_t st = g & 1u, ph = (g >> 1) & 1u;
+          mbar_wait(bar(K_FULL + st), ph);
+          tc_fence_after();
+          issue_s(0, st);
+          if (has1) issue_s(1, st);
+          umma_commit(bar(K_EMPTY + st));
+        }
+        // the epilogue of the previous item must have drained O_t before the first (overwriting) PV
+        if (n_o[0] > 0) mbar_wait(bar(O_FREE + 0), (n_o[0] - 1) & 1u);
+        if (has1 && n_o[1] > 0) mbar_wait(bar(O_FREE + 1), (n_o[1] - 1) & 1u);
+        for (int j = 0; j < n_kv; ++j) {
+          const uint32_t gt = g + j, st = gt & 1u, ph = (gt >> 1) & 1u;
+          const uint32_t gn = gt + 1, stn = gn & 1u, phn = (gn >> 1) & 1u;
+          const bool more = j + 1 < n_kv;
+          if constexpr (SEP_P) {
+            // S_t(j+1) only needs the S_t buffer back (softmax holds S_t(j) in registers): it runs under the exp2 phase
+            if (more) {
+              mbar_wait(bar(K_FULL + stn), phn);
+              mbar_wait_fast(bar(S_FREE + 0), n_f[0]++ & 1u);
+              tc_fence_after();
+              issue_s(0, stn);
+            }
+            mbar_wait(bar(V_FULL + st), ph);
+            mbar_wait_fast(bar(P_FULL + 0), n_p[0]++ & 1u);
+            tc_fence_after();
+            issue_pv(0, st, j == 0);
+            umma_commit(bar((more ? PV_DONE : O_DONE) + 0));
+            if (has1) {
+              if (more) {
+                mbar_wait_fast(bar(S_FREE + 1), n_f[1]++ & 1u);
+                tc_fence_after();
+                issue_s(1, stn);
+              }
+              mbar_wait_fast(bar(P_FULL + 1), n_p[1]++ & 1u);
+              tc_fence_after();
+              issue_pv(1, st, j == 0);
+              umma_commit(bar((more ? PV_DONE : O_DONE) + 1));
+            }
+          } else {
+            mbar_wait(bar(V_FULL + st), ph);
+            mbar_wait_fast(bar(P_FULL + 0), n_p[0]++ & 1u);  // P_0(j) is in TMEM (O_0 rescaled if it had to be)
+            tc_fence_after();
+            issue_pv(0, st, j == 0);
+            if (more) {
+              mbar_wait(bar(K_FULL + stn), phn);
+              tc_fence_after();
+              issue_s(0, stn);
+            } else {
+              umma_commit(bar(O_DONE + 0));
+            }
+            if (has1) {
+              mbar_wait_fast(bar(P_FULL + 1), n_p[1]++ & 1u);
+              tc_fence_after();
+              issue_pv(1, st, j == 0);
+              if (more) issue_s(1, stn); else umma_commit(bar(O_DONE + 1));
+            }
+          }
+          umma_commit(bar(V_EMPTY + st));
+          if (more) umma_commit(bar(K_EMPTY + stn));
+        }
+        umma_commit(bar(Q_EMPTY));
+        ++n_o[0];
+        if (has1) ++n_o[1];
+        g += n_kv;
+      }
+    }
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    // ===================== softmax warpgroups (thread = one query row of tile t) =====================
+    const int t = (warp - 4) >> 2;                   // which query tile of the pair
+    const int q = warp & 3;                          // TMEM lane quarter (hardware rule: warp_id % 4)
+    const int row = q * 32 + lane;
+    const uint32_t t_s = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_S + (uint32_t)t * 128u;
+    const uint32_t t_p = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_P + (uint32_t)t * P_STRIDE;
+    const uint32_t t_o = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_O + (uint32_t)t * O_STRIDE;
+    uint32_t n_s = 0, n_items = 0, n_pv = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int r, h, qp;
+      item_coord(item, r, h, qp);
+      const int qt = 2 * qp + t;
+      if (qt * BQ >= p.Ntok) continue;               // (only t == 1 of the last pair) tile lies outside the sample
+      float m_used = 0.f, l_run = 0.f;
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait_fast(bar(S_FULL + t), n_s++ & 1u);
+        tc_fence_after();
+        uint32_t v[4][32];                           // the 128 scores of this row stay in registers
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_x32(t_s + 32 * c, v[c]);
+        tmem_ld_wait();
+        if constexpr (SEP_P) {                       // hand the S_t buffer back: S_t(j+1) may be computed now
+          if (j + 1 < n_kv) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(S_FREE + t));
+          }
+        }
+        const int valid = p.Ntok - j * BKV;          // keys of this tile that exist
+        if (valid < BKV) {
+#pragma unroll
+          for (int c = 0; c < BKV; ++c)
+            if (c >= valid) v[c >> 5][c & 31] = 0xff800000u;   // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          mx0 = fmaxf(mx0, __uint_as_float(v[0][c]));
+          mx1 = fmaxf(mx1, __uint_as_float(v[1][c]));
+          mx2 = fmaxf(mx2, __uint_as_float(v[2][c]));
+          mx3 = fmaxf(mx3, __uint_as_float(v[3][c]));
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        if (j == 0) {
+          m_used = mx;                               // the first PV overwrites O: nothing to rescale
+        } else {
+          if constexpr (SEP_P) {                     // PV_t(j-1) must have retired before O_t may be touched
+            mbar_wait_fast(bar(PV_DONE + t), n_pv++ & 1u);
+            tc_fence_after();
+          }
+          const bool raise = mx > m_used + kRescaleThreshold;
+          if (__any_sync(0xffffffffu, raise)) {      // warp-uniform: tcgen05.ld/st are warp-collective
+            const float m_new = raise ? mx : m_used;
+            const float alpha = ex2(m_used - m_new); // 1 for rows that keep their maximum
+            l_run *= alpha;
+            m_used = m_new;
+            // aliased layout: S_FULL(j) was committed after PV(j-1); separate layout: PV_DONE(j-1) was awaited above.
+            // Either way O_t is complete and idle until this warpgroup arrives on P_FULL
+#pragma unroll
+            for (int c0 = 0; c0 < DP; c0 += 32) {
+              if constexpr (DP % 32 != 0) {
+                if (c0 + 32 > DP) {
+                  uint32_t o[16];
+                  tmem_ld_x16(t_o + c0, o);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int c = 0; c < 16; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+                  tmem_st_x16(t_o + c0, o);
+                  continue;
+                }
+              }
+              uint32_t o[32];
+              tmem_ld_x32(t_o + c0, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+              tmem_st_x32(t_o + c0, o);
+            }
+          }
+        }
+        // p = exp2(s - m) → packed bf16 pairs into the first 64 columns of S_t (the PV MMA's A operand)
+        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            const float p0 = ex2(__uint_as_float(v[c][2 * e]) - m_used);
+            const float p1 = ex2(__uint_as_float(v[c][2 * e + 1]) - m_used);
+            const float p2 = ex2(__uint_as_float(v[c][2 * e + 2]) - m_used);
+            const float p3 = ex2(__uint_as_float(v[c][2 * e + 3]) - m_used);
+            sum0 += p0; sum1 += p1; sum2 += p2; sum3 += p3;
+            pk[e] = pack_bf16x2(p0, p1);
+            pk[e + 1] = pack_bf16x2(p2, p3);
+          }
+          tmem_st_x16(t_p + 16 * c, pk);
+        }
+        l_run += (sum0 + sum1) + (sum2 + sum3);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(P_FULL + t));
+      }
+      // ---- epilogue: O_t / l → bf16 rows
+      mbar_wait_fast(bar(O_DONE + t), n_items++ & 1u);
+      tc_fence_after();
+      const int qrow = qt * BQ + row;
+      const float inv = 1.f / l_run;
+      __nv_bfloat16* dst = p.out + ((int64_t)r * p.Ntok + qrow) * ((int64_t)p.heads * DH) + (int64_t)h * DH;
+#pragma unroll
+      for (int c0 = 0; c0 < DP; c0 += 32) {
+        uint32_t o[32];
+        if (DP % 32 != 0 && c0 + 32 > DP) {
+          uint32_t o16[16];
+          tmem_ld_x16(t_o + c0, o16);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) o[c] = o16[c];
+        } else {
+          tmem_ld_x32(t_o + c0, o);
+          tmem_ld_wait();
+        }
+        if (qrow < p.Ntok) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            if (c0 + c < DH) {   // DH % 8 == 0
+              uint4 w;
+              w.x = pack_bf16x2(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv);
+              w.y = pack_bf16x2(__uint_as_float(o[c + 2]) * inv, __uint_as_float(o[c + 3]) * inv);
+              w.z = pack_bf16x2(__uint_as_float(o[c + 4]) * inv, __uint_as_float(o[c + 5]) * inv);
+              w.w = pack_bf16x2(__uint_as_float(o[c + 6]) * inv, __uint_as_float(o[c + 7]) * inv);
+              *reinterpret_cast<uint4*>(dst + c0 + c) = w;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(O_FREE + t));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -414,11 +831,24 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+static int attention_impl_override() {   // DFOT_ATTENTION_IMPL=1|2 pins the kernel (benchmarking); default: by shape
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DFOT_ATTENTION_IMPL");
+    v = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+  }
+  return v;
+}
+
 template <int DH, int DP>
 static int launch(const void* qkv, void* out, int64_t R, int64_t Ntok, int64_t heads, cudaStream_t s) {
   constexpr int ATOMS = (DP + 63) / 64;
-  constexpr int smem_bytes = 5 * ATOMS * kAtomBytes + 2 * 2 * kAtomBytes + 160 /*barriers*/ + 2048 /*exchange*/;
-  static_assert(smem_bytes <= 232448, "attention: shared memory budget exceeded");
+  constexpr int smem1 = 5 * ATOMS * kAtomBytes + 2 * 2 * kAtomBytes + 160 /*barriers*/ + 2048 /*exchange*/;
+  constexpr int smem2 = 6 * ATOMS * kAtomBytes + 512 /*barriers*/;
+  static_assert(smem1 <= 232448 && smem2 <= 232448, "attention: shared memory budget exceeded");
+  const int ov = attention_impl_override();
+  const bool paired = ov == 2 || (ov == 0 && Ntok > BQ);     // more than one query tile per sample
+  const int smem_bytes = paired ? smem2 : smem1;
   EncodeTiledFn enc = get_encode_fn();
   DFOT_REQUIRE(enc != nullptr, DFOT_ERR_DRIVER, "attention: cuTensorMapEncodeTiled unavailable from the driver");
   // qkv viewed as [tokens][3*heads][DH]: box = 64 (d) x 1 x 128 (tokens); d beyond DH is zero-filled by TMA
@@ -431,25 +861,25 @@ static int launch(const void* qkv, void* out, int64_t R, int64_t Ntok, int64_t h
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DFOT_REQUIRE(cr == CUDA_SUCCESS, DFOT_ERR_DRIVER, "attention: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
-  auto kern = attention_tcgen05_kernel<DH, DP>;
-  static bool configured = false;
-  if (!configured) {
+  auto kern = paired ? attention2_tcgen05_kernel<DH, DP> : attention_tcgen05_kernel<DH, DP>;
+  static bool configured[2] = {false, false};
+  if (!configured[paired]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     DFOT_REQUIRE(e == cudaSuccess, DFOT_ERR_CUDA, "attention: cannot reserve %d B shared memory: %s", smem_bytes,
                  cudaGetErrorString(e));
-    configured = true;
+    configured[paired] = true;
   }
   Params p;
   p.out = (__nv_bfloat16*)out;
   p.R = (int)R; p.Ntok = (int)Ntok; p.heads = (int)heads;
   p.q_tiles = (int)ceil_div(Ntok, BQ);
   p.kv_tiles = (int)ceil_div(Ntok, BKV);
-  p.num_items = (int)(R * heads * p.q_tiles);
+  p.num_items = (int)(R * heads * (paired ? (p.q_tiles + 1) / 2 : p.q_tiles));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.num_items < sms ? p.num_items : sms;
-  kern<<<grid, kThreads, smem_bytes, s>>>(tmap, p);
+  kern<<<grid, paired ? kThreads2 : kThreads, smem_bytes, s>>>(tmap, p);
   DFOT_CHECK_LAUNCH("attention_tcgen05");
   return DFOT_OK;
 }

@@ -28,7 +28,7 @@ def timeit(fn, iters=20, warmup=3):
 
 
 def bench_attn(iters):
-    for (R, heads, dh, N) in [(8, 16, 72, 1280), (8, 16, 64, 1280), (8, 9, 128, 2048), (2, 12, 64, 576), (2, 9, 64, 8192)]:
+    for (R, heads, dh, N) in [(8, 16, 72, 1280), (8, 16, 64, 1280), (8, 9, 128, 2048), (2, 12, 64, 576), (2, 9, 64, 8192), (8, 9, 64, 8192), (2, 9, 128, 2048)]:
         D = heads * dh
         qkv = (torch.randn((R * N, 3 * D), device=DEV) * 0.5).to(torch.bfloat16)
         out = torch.empty((R * N, D), device=DEV, dtype=torch.bfloat16)
