@@ -82,6 +82,17 @@ __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
     }
   }
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {   // non-blocking
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
@@ -479,6 +490,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
   constexpr uint32_t IDESC_S = make_idesc(BKV, false);
   constexpr uint32_t IDESC_PV = make_idesc(DP, true);
   constexpr bool SEP_P = DP <= 64;                   // P_t has its own TMEM columns
+  constexpr bool DUAL = SEP_P;                       // one MMA issuer warp per query tile (measured: helps only SEP_P)
   // aliased: S_t at 128*t (P_t = its first 64 columns), O_t at 256 + 128*t;  separate: S 128*t, P 256 + 64*t, O 384 + 64*t
   constexpr uint32_t TMEM_S = 0, TMEM_P = SEP_P ? 256 : 0, P_STRIDE = SEP_P ? 64 : 128;
   constexpr uint32_t TMEM_O = SEP_P ? 384 : 256, O_STRIDE = SEP_P ? 64 : 128;
@@ -505,7 +517,9 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
     for (int i = 0; i < N_BARS; ++i) {
       const bool from_softmax = (i >= P_FULL && i < P_FULL + 2) || (i >= O_FREE && i < O_FREE + 2) ||
                                 (i >= S_FREE && i < S_FREE + 2);
-      mbar_init(bar(i), from_softmax ? 4 : 1);       // one arrival per warp of the tile's softmax warpgroup
+      const bool from_both_issuers = i == Q_EMPTY || (i >= K_EMPTY && i < K_EMPTY + 2) || (i >= V_EMPTY && i < V_EMPTY + 2);
+      // softmax → one arrival per warp of the tile's warpgroup; ring slots → one per MMA issuer; else one producer
+      mbar_init(bar(i), from_softmax ? 4 : ((DUAL && from_both_issuers) ? 2 : 1));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -563,7 +577,90 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp <= 2) {
+    if constexpr (DUAL) {
+    // ===================== MMA issuers: warp 1 drives query tile 0, warp 2 drives query tile 1 =====================
+    // Two independent in-order streams with hardware-suspended waits (a polling single issuer steals issue slots from
+    // the softmax warps of its scheduler).  Per tile t:  S_t(0) | [S_t(j+1)] PV_t(j) ...   where
+    //   S_t(j+1) needs K(j+1) and the S_t buffer — SEP_P: softmax pulled S_t(j) into registers (S_FREE);
+    //            aliased: it is issued right after PV_t(j) (tensor-core ops of one thread execute in issue order);
+    //   PV_t(j)  needs V(j), P_t(j) (P_FULL) and, for j == 0, the previous item's epilogue to have drained O_t (O_FREE).
+    // K / V / Q ring slots are released by BOTH issuers (barrier count 2).
+    if (lane == 0) {
+      const int t = warp - 1;
+      uint32_t g = 0, it = 0, n_p = 0, n_f = 0, n_o = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        int r, h, qp;
+        item_coord(item, r, h, qp);
+        const bool active = (2 * qp + t) * BQ < p.Ntok;   // (tile 1 of the last pair may lie outside the sample)
+        mbar_wait(bar(Q_FULL), it & 1u);
+        if (!active) {                                 // keep the shared rings moving
+          for (int j = 0; j < n_kv; ++j) {
+            const uint32_t gt = g + j, st = gt & 1u, ph = (gt >> 1) & 1u;
+            mbar_wait(bar(K_FULL + st), ph);
+            mbar_arrive(bar(K_EMPTY + st));
+            mbar_wait(bar(V_FULL + st), ph);
+            mbar_arrive(bar(V_EMPTY + st));
+          }
+          mbar_arrive(bar(Q_EMPTY));
+          g += n_kv;
+          continue;
+        }
+        auto issue_s = [&](uint32_t st) {              // S_t = Q_t · K^T (K stage st)
+          const uint32_t d = tmem_base + TMEM_S + (uint32_t)t * 128u;
+#pragma unroll
+          for (int s = 0; s < KS_QK; ++s) {
+            const uint32_t off = (uint32_t)(s >> 2) * kAtomBytes + (uint32_t)(s & 3) * 32u;
+            umma_bf16(d, desc_kmajor(sQ + t * TILE_BYTES + off), desc_kmajor(sK + st * TILE_BYTES + off), IDESC_S,
+                      s > 0 ? 1u : 0u);
+          }
+          umma_commit(bar(S_FULL + t));
+          umma_commit(bar(K_EMPTY + st));
+        };
+        auto issue_pv = [&](uint32_t st, bool first) {  // O_t (+)= P_t · V (V stage st), A operand from TMEM
+          const uint32_t d = tmem_base + TMEM_O + (uint32_t)t * O_STRIDE;
+          const uint32_t a = tmem_base + TMEM_P + (uint32_t)t * P_STRIDE;
+#pragma unroll
+          for (int s = 0; s < KS_PV; ++s)
+            umma_bf16_ts(d, a + (uint32_t)(8 * s), desc_mnmajor(sV + st * TILE_BYTES + (uint32_t)s * 2048u, kAtomBytes),
+                         IDESC_PV, (first && s == 0) ? 0u : 1u);
+          umma_commit(bar(V_EMPTY + st));
+        };
+        {
+          const uint32_t st = g & 1u, ph = (g >> 1) & 1u;
+          mbar_wait(bar(K_FULL + st), ph);
+          tc_fence_after();
+          issue_s(st);
+        }
+        if (n_o > 0) mbar_wait(bar(O_FREE + t), (n_o - 1) & 1u);
+        for (int j = 0; j < n_kv; ++j) {
+          const uint32_t gt = g + j, st = gt & 1u, ph = (gt >> 1) & 1u;
+          const uint32_t gn = gt + 1, stn = gn & 1u, phn = (gn >> 1) & 1u;
+          const bool more = j + 1 < n_kv;
+          if (SEP_P && more) {
+            mbar_wait(bar(K_FULL + stn), phn);
+            mbar_wait_fast(bar(S_FREE + t), n_f++ & 1u);
+            tc_fence_after();
+            issue_s(stn);
+          }
+          mbar_wait(bar(V_FULL + st), ph);
+          mbar_wait_fast(bar(P_FULL + t), n_p++ & 1u);
+          tc_fence_after();
+          issue_pv(st, j == 0);
+          if (!more) umma_commit(bar(O_DONE + t));
+          else if constexpr (SEP_P) umma_commit(bar(PV_DONE + t));
+          if (!SEP_P && more) {
+            mbar_wait(bar(K_FULL + stn), phn);
+            tc_fence_after();
+            issue_s(stn);
+          }
+        }
+        umma_commit(bar(Q_EMPTY));
+        ++n_o;
+        g += n_kv;
+      }
+    }
+    } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t g = 0, it = 0;
@@ -659,6 +756,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
         if (has1) ++n_o[1];
         g += n_kv;
       }
+    }
     }
   }
   } else {
