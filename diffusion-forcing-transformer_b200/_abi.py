@@ -4,7 +4,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdfot_b200.so")
+LIB_PATH = os.environ.get("DFOT_B200_LIB") or os.path.join(HERE, "libdfot_b200.so")   # env: A/B builds of the kernels
 
 F32, BF16, I64 = 0, 1, 2
 EPI_F32, EPI_BF16, EPI_GELU_BF16, EPI_SILU_BF16, EPI_GATE_RESID_F32, EPI_QKV_ROPE_BF16, EPI_RESID_F32 = range(7)

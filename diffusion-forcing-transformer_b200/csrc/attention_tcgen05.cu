@@ -179,6 +179,21 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// Packed fp32x2 arithmetic (sm_100: one issue slot for two lanes of work)
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // UMMA shared-memory descriptors (cute::UMMA::SmemDescriptor), 128-byte swizzle, version 1.
 //   K-major  operand: 8-row groups 1024 B apart (SBO); LBO unused.
 //   MN-major operand: K rows are 128-byte lines, 8-row groups 1024 B apart (SBO); 64-element MN atoms LBO apart.
@@ -804,19 +819,58 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
           mx3 = fmaxf(mx3, __uint_as_float(v[3][c]));
         }
         const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        // Lazy rescaling decision now (the exps below already use the new maximum); the O_t tile itself is rescaled
+        // after the exp2 phase, when PV_t(j-1) has long retired.
+        float alpha = 1.f;
+        bool rescale = false;
         if (j == 0) {
           m_used = mx;                               // the first PV overwrites O: nothing to rescale
         } else {
-          if constexpr (SEP_P) {                     // PV_t(j-1) must have retired before O_t may be touched
-            mbar_wait_fast(bar(PV_DONE + t), n_pv++ & 1u);
-            tc_fence_after();
-          }
           const bool raise = mx > m_used + kRescaleThreshold;
-          if (__any_sync(0xffffffffu, raise)) {      // warp-uniform: tcgen05.ld/st are warp-collective
-            const float m_new = raise ? mx : m_used;
-            const float alpha = ex2(m_used - m_new); // 1 for rows that keep their maximum
+          rescale = __any_sync(0xffffffffu, raise);  // warp-uniform: tcgen05.ld/st are warp-collective
+          if (raise) {
+            alpha = ex2(m_used - mx);
             l_run *= alpha;
-            m_used = m_new;
+            m_used = mx;
+          }
+        }
+        // p = exp2(s - m) → packed bf16 pairs into P_t (the PV MMA's A operand); fp32x2 packed sub / row sum
+        const uint64_t neg_m2 = pack_f32x2(-m_used, -m_used);
+        uint64_t sum_a = 0ull, sum_b = 0ull;         // (+0.f, +0.f)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            float x0, x1, x2, x3;
+#ifndef DFOT_ATTN_NO_PACKED
+            unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[c][2 * e]), __uint_as_float(v[c][2 * e + 1])), neg_m2), x0, x1);
+            unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[c][2 * e + 2]), __uint_as_float(v[c][2 * e + 3])), neg_m2), x2, x3);
+#else
+            x0 = __uint_as_float(v[c][2 * e]) - m_used; x1 = __uint_as_float(v[c][2 * e + 1]) - m_used;
+            x2 = __uint_as_float(v[c][2 * e + 2]) - m_used; x3 = __uint_as_float(v[c][2 * e + 3]) - m_used;
+#endif
+            const float p0 = ex2(x0), p1 = ex2(x1), p2 = ex2(x2), p3 = ex2(x3);
+            sum_a = add_f32x2(sum_a, pack_f32x2(p0, p1));
+            sum_b = add_f32x2(sum_b, pack_f32x2(p2, p3));
+            pk[e] = pack_bf16x2(p0, p1);
+            pk[e + 1] = pack_bf16x2(p2, p3);
+          }
+          if constexpr (SEP_P) {
+            // PV_t(j-1) reads P_t(j-1) from these very columns (and writes O_t): it must have retired before the first
+            // store of P_t(j).  Waiting here — after the first 32 exps — instead of before them hides its latency.
+            if (c == 0 && j > 0) {
+              mbar_wait_fast(bar(PV_DONE + t), n_pv++ & 1u);
+              tc_fence_after();
+            }
+          }
+          tmem_st_x16(t_p + 16 * c, pk);
+        }
+        float sum0, sum1, sum2, sum3;
+        unpack_f32x2(sum_a, sum0, sum1);
+        unpack_f32x2(sum_b, sum2, sum3);
+        if (j > 0) {
+          if (rescale) {
             // aliased layout: S_FULL(j) was committed after PV(j-1); separate layout: PV_DONE(j-1) was awaited above.
             // Either way O_t is complete and idle until this warpgroup arrives on P_FULL
 #pragma unroll
@@ -840,23 +894,6 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
               tmem_st_x32(t_o + c0, o);
             }
           }
-        }
-        // p = exp2(s - m) → packed bf16 pairs into the first 64 columns of S_t (the PV MMA's A operand)
-        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            const float p0 = ex2(__uint_as_float(v[c][2 * e]) - m_used);
-            const float p1 = ex2(__uint_as_float(v[c][2 * e + 1]) - m_used);
-            const float p2 = ex2(__uint_as_float(v[c][2 * e + 2]) - m_used);
-            const float p3 = ex2(__uint_as_float(v[c][2 * e + 3]) - m_used);
-            sum0 += p0; sum1 += p1; sum2 += p2; sum3 += p3;
-            pk[e] = pack_bf16x2(p0, p1);
-            pk[e + 1] = pack_bf16x2(p2, p3);
-          }
-          tmem_st_x16(t_p + 16 * c, pk);
         }
         l_run += (sum0 + sum1) + (sum2 + sum3);
         tmem_st_wait();
