@@ -66,9 +66,8 @@ def lib() -> ctypes.CDLL:
     L.dfot_unpatchify.argtypes = [vp, i64, vp, i, i64, i64, i64, i64, i64, vp]
     L.dfot_cast_bf16.argtypes = [vp, vp, i64, vp]
     L.dfot_conv3x3_bf16.argtypes = [vp, vp, vp, i64, i64, i64, i64, i64, i64, i, POINTER(GemmEpilogue), vp]
-    L.dfot_groupnorm_stats.argtypes = [vp, i, vp, i64, i64, i64, i64, vp]
-    L.dfot_groupnorm_silu_bf16.argtypes = [vp, i, vp, vp, vp, c_float, vp, i64, i64, i64, vp, vp, vp, i64, i64, i64,
-                                           i64, vp]
+    L.dfot_groupnorm_stats.argtypes = [vp, i, vp, i64, i64, i64, i64, c_float, vp]
+    L.dfot_groupnorm_silu_bf16.argtypes = [vp, i, vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, i64, i64, i64, i64, vp]
     L.dfot_rmsnorm_film_bf16.argtypes = [vp, vp, c_float, vp, i64, i64, i64, vp, vp, vp, i64, i64, i64, vp]
     L.dfot_qk_norm_rope.argtypes = [vp, i64, vp, vp, c_float, vp, i64, i64, i64, i64, c_float, vp]
     L.dfot_avgpool2x2.argtypes = [vp, i, vp, i, i64, i64, i64, i64, vp]

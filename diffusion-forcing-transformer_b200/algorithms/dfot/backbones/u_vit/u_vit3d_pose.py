@@ -292,7 +292,7 @@ class UViT3DPose(nn.Module):
         n_mod = sum(2 * self.channels[l] for _, l in self._blocks_in_order())
         M0 = n * self.res[0] ** 2
         ws = dict(feat=e((n, 256), bf), e1=e((n, E), bf), emb=e((n, E), bf), mod=e((n, n_mod), f32),
-                  patches=torch.zeros((M0, _pad8(C * p * p)), dtype=bf, device=dev), sums=e((n, 32, 2), torch.float64),
+                  patches=torch.zeros((M0, _pad8(C * p * p)), dtype=bf, device=dev), sums=e((n, 32, 3), torch.float64),
                   x0_16=e((M0, self.channels[0]), bf), tok=e((M0, _pad8(p * p * C)), f32),
                   out=e((R, T, *self.x_shape), out_dtype), img_map=e((n,), torch.int32), lv=[])
         for i, ch in enumerate(self.channels):

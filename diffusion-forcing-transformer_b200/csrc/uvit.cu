@@ -81,67 +81,96 @@ gn_stats_kernel(const TX* __restrict__ x, double* __restrict__ sums, int64_t HW,
   }
 }
 
-__device__ __forceinline__ void gn_mean_rstd(const double* __restrict__ sums, int64_t idx, double inv_n, float eps,
-                                             float& mean, float& rstd) {
-  const double s = sums[idx * 2], q = sums[idx * 2 + 1];
-  const double m = s * inv_n;
-  const double var = fmax(q * inv_n - m * m, 0.0);
-  mean = (float)m;
-  rstd = rsqrtf((float)var + eps);
+// (sum, sum of squares) in f64 → (mean, rstd) in f32, once per (image, group): keeps every f64 operation out of the
+// per-element kernel
+__global__ void gn_finalize_kernel(const double* __restrict__ sums, float2* __restrict__ stats, int64_t n, double inv_n,
+                                   float eps) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double m = sums[2 * i] * inv_n;
+  const double var = fmax(sums[2 * i + 1] * inv_n - m * m, 0.0);
+  stats[i] = make_float2((float)m, rsqrtf((float)var + eps));
 }
 
 // ------------------------------------------------------------------ GroupNorm (+FiLM) + SiLU -> bf16
+// grid (pixel slabs, images); a thread owns ONE 8-channel vector (so gamma / beta / statistics / per-image FiLM are
+// loaded once and folded into a per-channel affine) and walks kGnPix pixels of its slab with all loads issued up
+// front — no 64-bit index arithmetic, 4 independent 16/32-byte loads in flight per thread.
+constexpr int kGnPix = 2;
 template <typename TX>
-__global__ void __launch_bounds__(kThreads)
-gn_silu_kernel(const TX* __restrict__ x, const double* __restrict__ sums, const float* __restrict__ gamma,
-               const float* __restrict__ beta, float eps, const float* __restrict__ mod_img, int64_t ld_img,
+__global__ void __launch_bounds__(kThreads, 3)
+gn_silu_kernel(const TX* __restrict__ x, const float2* __restrict__ stats, const float* __restrict__ gamma,
+               const float* __restrict__ beta, const float* __restrict__ mod_img, int64_t ld_img,
                int64_t scale_col, int64_t shift_col, const __nv_bfloat16* __restrict__ mod_pix,
-               const int32_t* __restrict__ img_map, __nv_bfloat16* __restrict__ y, int64_t n_img, int64_t HW, int C,
-               int G) {
+               const int32_t* __restrict__ img_map, __nv_bfloat16* __restrict__ y, int HW, int C, int G) {
   const int vecs = C >> 3, cpg = C / G;
-  const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (idx >= n_img * HW * vecs) return;
-  const int v = (int)(idx % vecs);
-  const int64_t m = idx / vecs;
-  const int64_t img = m / HW, pix = m - img * HW;
+  const int img = blockIdx.y;
+  const int v = threadIdx.x % vecs, prow = threadIdx.x / vecs, pix_step = kThreads / vecs;
   const int c0 = 8 * v;
-  float a[8], ga[8], be[8];
-  load8(x + m * C + c0, a);
-  ldg8(gamma + c0, ga);
-  ldg8(beta + c0, be);
-  const double inv_n = 1.0 / ((double)HW * (double)cpg);
-  if (cpg % 8 == 0) {
-    float mean, rstd;
-    gn_mean_rstd(sums, img * G + c0 / cpg, inv_n, eps, mean, rstd);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = (a[j] - mean) * rstd * ga[j] + be[j];
-  } else {
+  // per-channel affine of this image: t = x * A + B  (GroupNorm), then y = t * (1 + scale) + shift (FiLM)
+  float A[8], B[8], sc[8], sh[8];
+  {
+    float ga[8], be[8];
+    ldg8(gamma + c0, ga);
+    ldg8(beta + c0, be);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float mean, rstd;
-      gn_mean_rstd(sums, img * G + (c0 + j) / cpg, inv_n, eps, mean, rstd);
-      a[j] = (a[j] - mean) * rstd * ga[j] + be[j];
+      const float2 st = __ldg(stats + (int64_t)img * G + (c0 + j) / cpg);
+      A[j] = st.y * ga[j];
+      B[j] = be[j] - st.x * A[j];
     }
   }
-  if (mod_img != nullptr) {
-    float sc[8], sh[8];
-    ldg8(mod_img + img * ld_img + scale_col + c0, sc);
-    ldg8(mod_img + img * ld_img + shift_col + c0, sh);
-    const int32_t src = (mod_pix != nullptr && img_map != nullptr) ? __ldg(img_map + img) : -1;
-    if (src >= 0) {
-      float ps[8], ph[8];
-      const __nv_bfloat16* row = mod_pix + ((int64_t)src * HW + pix) * (2 * C);
-      load8(row + c0, ps);
-      load8(row + C + c0, ph);
+  const bool film = mod_img != nullptr;
+  if (film) {
+    ldg8(mod_img + (int64_t)img * ld_img + scale_col + c0, sc);
+    ldg8(mod_img + (int64_t)img * ld_img + shift_col + c0, sh);
+  }
+  const int32_t src = (film && mod_pix != nullptr && img_map != nullptr) ? __ldg(img_map + img) : -1;
+  if (film && src < 0) {   // no per-pixel part: fold FiLM into the affine
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { sc[j] += ps[j]; sh[j] += ph[j]; }
+    for (int j = 0; j < 8; ++j) { A[j] *= 1.f + sc[j]; B[j] = fmaf(B[j], 1.f + sc[j], sh[j]); }
+  }
+  const int pix0 = blockIdx.x * (pix_step * kGnPix) + prow;
+  const TX* xb = x + (int64_t)img * HW * C + c0;
+  __nv_bfloat16* yb = y + (int64_t)img * HW * C + c0;
+  float a[kGnPix][8];
+#pragma unroll
+  for (int k = 0; k < kGnPix; ++k) {
+    const int pix = pix0 + k * pix_step;
+    if (pix < HW) load8(xb + (int64_t)pix * C, a[k]);
+  }
+  if (src >= 0) {
+    const __nv_bfloat16* pb = mod_pix + (int64_t)src * HW * (2 * C) + c0;
+    float ps[kGnPix][8], ph[kGnPix][8];
+#pragma unroll
+    for (int k = 0; k < kGnPix; ++k) {
+      const int pix = pix0 + k * pix_step;
+      if (pix < HW) {
+        load8(pb + (int64_t)pix * (2 * C), ps[k]);
+        load8(pb + (int64_t)pix * (2 * C) + C, ph[k]);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = fmaf(a[j], 1.f + sc[j], sh[j]);
-  }
+    for (int k = 0; k < kGnPix; ++k) {
+      const int pix = pix0 + k * pix_step;
+      if (pix < HW) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) a[j] = silu_f(a[j]);
-  store8(y + m * C + c0, a);
+        for (int j = 0; j < 8; ++j)
+          a[k][j] = silu_fast_f(fmaf(fmaf(a[k][j], A[j], B[j]), 1.f + (sc[j] + ps[k][j]), sh[j] + ph[k][j]));
+        store8(yb + (int64_t)pix * C, a[k]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kGnPix; ++k) {
+      const int pix = pix0 + k * pix_step;
+      if (pix < HW) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[k][j] = silu_fast_f(fmaf(a[k][j], A[j], B[j]));
+        store8(yb + (int64_t)pix * C, a[k]);
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------ RMSNorm + FiLM -> bf16 (warp per token)
@@ -200,48 +229,70 @@ rmsnorm_film_kernel(const float* __restrict__ x, const float* __restrict__ weigh
 }
 
 // ------------------------------------------------------------------ q/k RMSNorm(head_dim) + RoPE-3D, in place
-// one warp per (token, head, q|k); a lane owns EPL = DH/32 adjacent elements = EPL/2 rotation pairs
-template <int DH>
+// One warp per token: the q and k segments of all heads (2*heads segments of DH elements) are processed in batches of
+// SEG independent loads so that enough bytes are in flight; a lane owns EPL = DH/32 adjacent elements = EPL/2
+// rotation pairs of every segment, so the RoPE (cos, sin) and norm weights are loaded once per token.
+template <int DH, int SEG>
 __global__ void __launch_bounds__(kThreads)
 qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, const float* __restrict__ qw,
                     const float* __restrict__ kw, float eps, const float* __restrict__ rope_cs,
                     int64_t tokens_per_sample, int64_t M, int heads, float q_scale) {
   constexpr int EPL = DH / 32;
   const int lane = threadIdx.x & 31;
-  const int64_t wid = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-  if (wid >= M * heads * 2) return;
-  const int which = (int)(wid % 2);           // 0 = q, 1 = k
-  const int head = (int)((wid / 2) % heads);
-  const int64_t m = wid / (2 * heads);
-  __nv_bfloat16* p = qkv + m * ld + (int64_t)which * heads * DH + head * DH + lane * EPL;
-  float e[EPL];
-  if constexpr (EPL == 2) {
-    const float2 t = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p));
-    e[0] = t.x; e[1] = t.y;
-  } else {
-    const uint2 u = *reinterpret_cast<const uint2*>(p);
-    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-    e[0] = a.x; e[1] = a.y; e[2] = b.x; e[3] = b.y;
-  }
-  float sq = 0.f;
-#pragma unroll
-  for (int j = 0; j < EPL; ++j) sq = fmaf(e[j], e[j], sq);
-  const float rstd = rsqrtf(warp_sum(sq) / (float)DH + eps);
-  const float* w = (which == 0 ? qw : kw) + lane * EPL;
-  const float mul = which == 0 ? q_scale : 1.f;
+  const int64_t m = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  __nv_bfloat16* row = qkv + m * ld + lane * EPL;
+  float wq[EPL], wk[EPL];
+  float2 cs[EPL / 2];
   const int64_t tok = m % tokens_per_sample;
-  const float2* cs = reinterpret_cast<const float2*>(rope_cs) + tok * (DH / 2) + lane * (EPL / 2);
 #pragma unroll
-  for (int j = 0; j < EPL; j += 2) {
-    const float x0 = e[j] * rstd * __ldg(w + j), x1 = e[j + 1] * rstd * __ldg(w + j + 1);
-    const float2 c = __ldg(cs + j / 2);
-    e[j] = (x0 * c.x - x1 * c.y) * mul;
-    e[j + 1] = (x1 * c.x + x0 * c.y) * mul;
-  }
-  if constexpr (EPL == 2) {
-    *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(e[0], e[1]);
-  } else {
-    *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]));
+  for (int j = 0; j < EPL; ++j) { wq[j] = __ldg(qw + lane * EPL + j) * q_scale; wk[j] = __ldg(kw + lane * EPL + j); }
+#pragma unroll
+  for (int j = 0; j < EPL / 2; ++j) cs[j] = __ldg(reinterpret_cast<const float2*>(rope_cs) + tok * (DH / 2) + lane * (EPL / 2) + j);
+  const int n_seg = 2 * heads;                    // segment s: columns [s*DH, (s+1)*DH); s < heads → q, else k
+  for (int s0 = 0; s0 < n_seg; s0 += SEG) {
+    float e[SEG][EPL];
+    float sq[SEG];
+#pragma unroll
+    for (int i = 0; i < SEG; ++i) {
+      if (s0 + i < n_seg) {
+        if constexpr (EPL == 2) {
+          const float2 t = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row + (s0 + i) * DH));
+          e[i][0] = t.x; e[i][1] = t.y;
+        } else {
+          const uint2 u = *reinterpret_cast<const uint2*>(row + (s0 + i) * DH);
+          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+          e[i][0] = a.x; e[i][1] = a.y; e[i][2] = b.x; e[i][3] = b.y;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) e[i][j] = 0.f;
+      }
+      sq[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) sq[i] = fmaf(e[i][j], e[i][j], sq[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int i = 0; i < SEG; ++i) sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
+#pragma unroll
+    for (int i = 0; i < SEG; ++i) {
+      if (s0 + i >= n_seg) continue;
+      const float rstd = rsqrtf(sq[i] / (float)DH + eps);
+      const bool is_q = s0 + i < heads;
+#pragma unroll
+      for (int j = 0; j < EPL; j += 2) {
+        const float x0 = e[i][j] * rstd * (is_q ? wq[j] : wk[j]), x1 = e[i][j + 1] * rstd * (is_q ? wq[j + 1] : wk[j + 1]);
+        e[i][j] = x0 * cs[j / 2].x - x1 * cs[j / 2].y;
+        e[i][j + 1] = x1 * cs[j / 2].x + x0 * cs[j / 2].y;
+      }
+      if constexpr (EPL == 2) {
+        *reinterpret_cast<uint32_t*>(row + (s0 + i) * DH) = pack_bf16x2(e[i][0], e[i][1]);
+      } else {
+        *reinterpret_cast<uint2*>(row + (s0 + i) * DH) = make_uint2(pack_bf16x2(e[i][0], e[i][1]), pack_bf16x2(e[i][2], e[i][3]));
+      }
+    }
   }
 }
 
@@ -343,7 +394,7 @@ using namespace dfot;
 using namespace dfot::uvit;
 
 extern "C" int dfot_groupnorm_stats(const void* x, int x_dtype, double* sums, int64_t n_img, int64_t HW, int64_t C,
-                                    int64_t groups, void* stream) {
+                                    int64_t groups, float eps, void* stream) {
   DFOT_REQUIRE(x && sums && n_img > 0 && HW > 0 && C > 0 && groups > 0, DFOT_ERR_INVALID_ARG, "groupnorm_stats: bad arguments");
   DFOT_REQUIRE(C % groups == 0 && C % 8 == 0 && groups <= 64 && n_img < 65536, DFOT_ERR_UNSUPPORTED,
                "groupnorm_stats: need C %% groups == 0, C %% 8 == 0, groups <= 64");
@@ -367,11 +418,16 @@ extern "C" int dfot_groupnorm_stats(const void* x, int x_dtype, double* sums, in
   else
     DFOT_REQUIRE(false, DFOT_ERR_INVALID_ARG, "groupnorm_stats: x dtype must be f32 or bf16");
   DFOT_CHECK_LAUNCH("groupnorm_stats");
+  // (mean, rstd) as f32 pairs, stored behind the f64 sums in the same buffer
+  float2* stats = reinterpret_cast<float2*>(sums + 2 * n_img * groups);
+  const int64_t n = n_img * groups;
+  gn_finalize_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, s>>>(sums, stats, n, 1.0 / ((double)HW * (double)(C / groups)), eps);
+  DFOT_CHECK_LAUNCH("groupnorm_finalize");
   return DFOT_OK;
 }
 
 extern "C" int dfot_groupnorm_silu_bf16(const void* x, int x_dtype, const double* sums, const float* gamma,
-                                        const float* beta, float eps, const float* mod_img, int64_t ld_img,
+                                        const float* beta, const float* mod_img, int64_t ld_img,
                                         int64_t scale_col, int64_t shift_col, const void* mod_pix,
                                         const int32_t* img_map, void* y_bf16, int64_t n_img, int64_t HW, int64_t C,
                                         int64_t groups, void* stream) {
@@ -383,15 +439,19 @@ extern "C" int dfot_groupnorm_silu_bf16(const void* x, int x_dtype, const double
   DFOT_REQUIRE((mod_pix == nullptr) == (img_map == nullptr) && (mod_pix == nullptr || mod_img != nullptr),
                DFOT_ERR_INVALID_ARG, "groupnorm_silu: mod_pix needs img_map and mod_img");
   cudaStream_t s = (cudaStream_t)stream;
-  const int64_t total = n_img * HW * (C / 8);
+  const int vecs = (int)(C / 8);
+  DFOT_REQUIRE(vecs <= kThreads && kThreads % vecs == 0 && n_img < 65536 && HW < (1ll << 30), DFOT_ERR_UNSUPPORTED,
+               "groupnorm_silu: C/8 = %d must divide %d", vecs, kThreads);
+  const float2* stats = reinterpret_cast<const float2*>(sums + 2 * n_img * groups);
+  const dim3 grid((unsigned)ceil_div(HW, (kThreads / vecs) * kGnPix), (unsigned)n_img);
   if (x_dtype == DFOT_F32)
-    gn_silu_kernel<float><<<blocks_for(total), kThreads, 0, s>>>(
-        (const float*)x, sums, gamma, beta, eps, mod_img, ld_img, scale_col, shift_col, (const __nv_bfloat16*)mod_pix,
-        img_map, (__nv_bfloat16*)y_bf16, n_img, HW, (int)C, (int)groups);
+    gn_silu_kernel<float><<<grid, kThreads, 0, s>>>(
+        (const float*)x, stats, gamma, beta, mod_img, ld_img, scale_col, shift_col, (const __nv_bfloat16*)mod_pix,
+        img_map, (__nv_bfloat16*)y_bf16, (int)HW, (int)C, (int)groups);
   else if (x_dtype == DFOT_BF16)
-    gn_silu_kernel<__nv_bfloat16><<<blocks_for(total), kThreads, 0, s>>>(
-        (const __nv_bfloat16*)x, sums, gamma, beta, eps, mod_img, ld_img, scale_col, shift_col,
-        (const __nv_bfloat16*)mod_pix, img_map, (__nv_bfloat16*)y_bf16, n_img, HW, (int)C, (int)groups);
+    gn_silu_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(
+        (const __nv_bfloat16*)x, stats, gamma, beta, mod_img, ld_img, scale_col, shift_col,
+        (const __nv_bfloat16*)mod_pix, img_map, (__nv_bfloat16*)y_bf16, (int)HW, (int)C, (int)groups);
   else
     DFOT_REQUIRE(false, DFOT_ERR_INVALID_ARG, "groupnorm_silu: x dtype must be f32 or bf16");
   DFOT_CHECK_LAUNCH("groupnorm_silu");
@@ -432,15 +492,14 @@ extern "C" int dfot_qk_norm_rope(void* qkv, int64_t ld, const float* q_weight, c
   DFOT_REQUIRE(head_dim == 64 || head_dim == 128, DFOT_ERR_UNSUPPORTED, "qk_norm_rope: head_dim must be 64 or 128");
   DFOT_REQUIRE(ld % 4 == 0 && ld >= 3 * heads * head_dim && (uintptr_t)qkv % 8 == 0, DFOT_ERR_UNSUPPORTED,
                "qk_norm_rope: ld must be a multiple of 4 and >= 3*heads*head_dim");
-  const int64_t warps = M * heads * 2;
-  const unsigned grid = (unsigned)ceil_div(warps, kThreads / 32);
+  const unsigned grid = (unsigned)ceil_div(M, kThreads / 32);
   cudaStream_t s = (cudaStream_t)stream;
   if (head_dim == 64)
-    qk_norm_rope_kernel<64><<<grid, kThreads, 0, s>>>((__nv_bfloat16*)qkv, ld, q_weight, k_weight, eps, rope_cs,
-                                                      tokens_per_sample, M, (int)heads, q_scale);
+    qk_norm_rope_kernel<64, 6><<<grid, kThreads, 0, s>>>((__nv_bfloat16*)qkv, ld, q_weight, k_weight, eps, rope_cs,
+                                                         tokens_per_sample, M, (int)heads, q_scale);
   else
-    qk_norm_rope_kernel<128><<<grid, kThreads, 0, s>>>((__nv_bfloat16*)qkv, ld, q_weight, k_weight, eps, rope_cs,
-                                                       tokens_per_sample, M, (int)heads, q_scale);
+    qk_norm_rope_kernel<128, 6><<<grid, kThreads, 0, s>>>((__nv_bfloat16*)qkv, ld, q_weight, k_weight, eps, rope_cs,
+                                                          tokens_per_sample, M, (int)heads, q_scale);
   DFOT_CHECK_LAUNCH("qk_norm_rope");
   return DFOT_OK;
 }

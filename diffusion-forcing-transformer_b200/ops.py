@@ -213,18 +213,19 @@ def conv3x3_bf16(x, w, out, epilogue, bias=None, resid=None):
     _abi.check(rc, "conv3x3_bf16")
 
 
-def groupnorm_stats(x, sums, n_img, HW, C, groups=32):
-    """x [n_img*HW, C] f32|bf16 channel-last → sums [n_img, groups, 2] f64 (sum, sum of squares)."""
+def groupnorm_stats(x, sums, n_img, HW, C, groups=32, eps=1e-6):
+    """x [n_img*HW, C] f32|bf16 channel-last → sums [n_img, groups, 3] f64 workspace: (sum, sum of squares) pairs
+    followed by the finalised f32 (mean, rstd) pairs that groupnorm_silu_bf16 reads."""
     _need(x, None, "x")
     _need(sums, torch.float64, "sums")
-    if sums.numel() != n_img * groups * 2 or x.numel() != n_img * HW * C:
-        raise RuntimeError("dfot_b200: groupnorm_stats size mismatch")
-    rc = _abi.lib().dfot_groupnorm_stats(x.data_ptr(), _DTYPE_TAG[x.dtype], sums.data_ptr(), n_img, HW, C, groups,
+    if sums.numel() != n_img * groups * 3 or x.numel() != n_img * HW * C:
+        raise RuntimeError("dfot_b200: groupnorm_stats size mismatch (workspace = 3 * n_img * groups doubles)")
+    rc = _abi.lib().dfot_groupnorm_stats(x.data_ptr(), _DTYPE_TAG[x.dtype], sums.data_ptr(), n_img, HW, C, groups, eps,
                                          _stream())
     _abi.check(rc, "groupnorm_stats")
 
 
-def groupnorm_silu_bf16(x, sums, gamma, beta, out, n_img, HW, C, groups=32, eps=1e-6, mod_img=None, scale_col=0,
+def groupnorm_silu_bf16(x, sums, gamma, beta, out, n_img, HW, C, groups=32, mod_img=None, scale_col=0,
                         shift_col=0, mod_pix=None, img_map=None):
     _need(x, None, "x")
     _need(sums, torch.float64, "sums")
@@ -237,7 +238,7 @@ def groupnorm_silu_bf16(x, sums, gamma, beta, out, n_img, HW, C, groups=32, eps=
         _need(mod_pix, torch.bfloat16, "mod_pix")
         _need(img_map, torch.int32, "img_map")
     rc = _abi.lib().dfot_groupnorm_silu_bf16(
-        x.data_ptr(), _DTYPE_TAG[x.dtype], sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, _ptr(mod_img),
+        x.data_ptr(), _DTYPE_TAG[x.dtype], sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(mod_img),
         0 if mod_img is None else mod_img.shape[-1], scale_col, shift_col, _ptr(mod_pix), _ptr(img_map),
         out.data_ptr(), n_img, HW, C, groups, _stream())
     _abi.check(rc, "groupnorm_silu_bf16")

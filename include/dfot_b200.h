@@ -191,12 +191,13 @@ DFOT_API int dfot_cast_bf16(const float* in, void* out_bf16, int64_t n, void* st
  * the row's pose embedding is masked out, embeddings.py:336-361).
  */
 /* GroupNorm statistics (u_vit_blocks.py:52-53: 32 groups): sums[img, g] = (sum, sum of squares) over H*W x C/G,
-   accumulated in f64.  The buffer is zeroed by the call (cudaMemsetAsync on the stream). x f32 or bf16. */
+   accumulated in f64, then finalised to f32 (mean, rstd) pairs stored right behind the sums: the workspace `sums` must
+   hold 3*n_img*groups doubles.  The buffer is zeroed by the call (cudaMemsetAsync on the stream). x f32 or bf16. */
 DFOT_API int dfot_groupnorm_stats(const void* x, int x_dtype, double* sums, int64_t n_img, int64_t HW, int64_t C,
-                         int64_t groups, void* stream);
+                         int64_t groups, float eps, void* stream);
 /* y = silu( GN(x) * gamma + beta [ * (1 + scale) + shift ] ) -> bf16 (the conv operand).  mod_img/mod_pix NULL: no FiLM */
 DFOT_API int dfot_groupnorm_silu_bf16(const void* x, int x_dtype, const double* sums, const float* gamma,
-                             const float* beta, float eps, const float* mod_img, int64_t ld_img, int64_t scale_col,
+                             const float* beta, const float* mod_img, int64_t ld_img, int64_t scale_col,
                              int64_t shift_col, const void* mod_pix, const int32_t* img_map, void* y_bf16,
                              int64_t n_img, int64_t HW, int64_t C, int64_t groups, void* stream);
 /* NormalizeWithCond (u_vit_blocks.py:98-121): y = RMSNorm(x) * weight * (1 + scale) + shift -> bf16; x [M, D] f32,

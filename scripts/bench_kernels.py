@@ -79,6 +79,46 @@ def bench_norm(iters):
     print(f"adaln_layernorm M={M} D={D} (bf16 out):     {us:7.1f} us  {M * D * 6 / us / 1e3:7.1f} GB/s")
 
 
+def bench_uvit(iters):
+    """HBM-bound U-ViT3DPose kernels at the RE10K level-0 / level-2 sizes of a batch-4 (8-row) forward."""
+    n, HW, C = 64, 16384, 128
+    x32 = torch.randn((n * HW, C), device=DEV)
+    x16 = x32.to(torch.bfloat16)
+    out = torch.empty((n * HW, C), device=DEV, dtype=torch.bfloat16)
+    gamma, beta = torch.randn((C,), device=DEV), torch.randn((C,), device=DEV)
+    sums = torch.empty((n, 32, 3), dtype=torch.float64, device=DEV)
+    mod_img = torch.randn((n, 4 * C), device=DEV)
+    mod_pix = torch.randn((32 * HW, 2 * C), device=DEV).to(torch.bfloat16)
+    img_map = torch.tensor([(-1 if i % 16 < 8 else (i // 16) * 8 + i % 8) for i in range(n)], dtype=torch.int32, device=DEV)
+    gb = lambda b, us: b / us / 1e3
+    us = timeit(lambda: ops.groupnorm_stats(x32, sums, n, HW, C), iters)
+    print(f"groupnorm_stats f32  [{n}x{HW}x{C}]: {us:7.1f} us  {gb(n * HW * C * 4, us):7.1f} GB/s")
+    us = timeit(lambda: ops.groupnorm_stats(x16, sums, n, HW, C), iters)
+    print(f"groupnorm_stats bf16 [{n}x{HW}x{C}]: {us:7.1f} us  {gb(n * HW * C * 2, us):7.1f} GB/s")
+    us = timeit(lambda: ops.groupnorm_silu_bf16(x32, sums, gamma, beta, out, n, HW, C), iters)
+    print(f"groupnorm_silu f32->bf16:            {us:7.1f} us  {gb(n * HW * C * 6, us):7.1f} GB/s")
+    us = timeit(lambda: ops.groupnorm_silu_bf16(x16, sums, gamma, beta, out, n, HW, C, mod_img=mod_img, scale_col=0,
+                                                shift_col=C, mod_pix=mod_pix, img_map=img_map), iters)
+    print(f"groupnorm_silu bf16+FiLM(half rows): {us:7.1f} us  {gb(n * HW * C * (4 + 2), us):7.1f} GB/s")
+    us = timeit(lambda: ops.cast_bf16(x32, out), iters)
+    print(f"cast_bf16:                           {us:7.1f} us  {gb(n * HW * C * 6, us):7.1f} GB/s")
+    for heads, dh, T, g in [(9, 64, 8, 32), (9, 128, 8, 16)]:
+        D, Ntok = heads * dh, T * g * g
+        M = 8 * Ntok
+        qkv = torch.randn((M, 3 * D), device=DEV).to(torch.bfloat16)
+        qw, kw = torch.randn((dh,), device=DEV), torch.randn((dh,), device=DEV)
+        table = torch.randn((Ntok, dh // 2, 2), device=DEV)
+        us = timeit(lambda: ops.qk_norm_rope(qkv, qw, kw, table, Ntok, heads, dh, 0.18), iters)
+        print(f"qk_norm_rope M={M} heads={heads} d={dh}: {us:7.1f} us  {gb(M * 2 * D * 4, us):7.1f} GB/s")
+        x = torch.randn((M, D), device=DEV)
+        w = torch.randn((D,), device=DEV)
+        mi = torch.randn((64, 4 * D), device=DEV)
+        mp = torch.randn((32 * g * g, 2 * D), device=DEV).to(torch.bfloat16)
+        o = torch.empty((M, D), device=DEV, dtype=torch.bfloat16)
+        us = timeit(lambda: ops.rmsnorm_film_bf16(x, w, mi, 0, D, g * g, o, mod_pix=mp, img_map=img_map), iters)
+        print(f"rmsnorm_film M={M} D={D}:           {us:7.1f} us  {gb(M * D * (4 + 2 + 2), us):7.1f} GB/s")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("which", nargs="?", default="all")
@@ -90,3 +130,5 @@ if __name__ == "__main__":
         bench_gemm(a.iters)
     if a.which in ("norm", "all"):
         bench_norm(a.iters)
+    if a.which in ("uvit", "all"):
+        bench_uvit(a.iters)

@@ -54,10 +54,13 @@ def conv3x3_bf16(x, w, out, epilogue, bias=None, resid=None):
     _epilogue(y.reshape(-1, w.shape[0]), out, epilogue, bias, resid)
 
 
-def groupnorm_stats(x, sums, n_img, HW, C, groups=32):
+def groupnorm_stats(x, sums, n_img, HW, C, groups=32, eps=1e-6):
     xg = x.double().reshape(n_img, HW, groups, C // groups)
-    sums[..., 0] = xg.sum((1, 3))
-    sums[..., 1] = (xg * xg).sum((1, 3))
+    cnt = HW * (C // groups)
+    mean = xg.sum((1, 3)) / cnt
+    var = ((xg * xg).sum((1, 3)) / cnt - mean * mean).clamp(min=0)
+    sums[..., 0] = mean                      # emulation keeps (mean, rstd) in the first two slots of the workspace
+    sums[..., 1] = torch.rsqrt(var.float() + eps).double()
 
 
 def _film(n_img, HW, C, mod_img, scale_col, shift_col, mod_pix, img_map):
@@ -72,13 +75,10 @@ def _film(n_img, HW, C, mod_img, scale_col, shift_col, mod_pix, img_map):
     return scale, shift
 
 
-def groupnorm_silu_bf16(x, sums, gamma, beta, out, n_img, HW, C, groups=32, eps=1e-6, mod_img=None, scale_col=0,
+def groupnorm_silu_bf16(x, sums, gamma, beta, out, n_img, HW, C, groups=32, mod_img=None, scale_col=0,
                         shift_col=0, mod_pix=None, img_map=None):
-    cnt = HW * (C // groups)
-    mean = (sums[..., 0] / cnt)
-    var = (sums[..., 1] / cnt - mean * mean).clamp(min=0)
     xg = x.float().reshape(n_img, HW, groups, C // groups)
-    y = (xg - mean[:, None, :, None].float()) * torch.rsqrt(var.float() + eps)[:, None, :, None]
+    y = (xg - sums[..., 0][:, None, :, None].float()) * sums[..., 1][:, None, :, None].float()
     y = y.reshape(n_img, HW, C) * gamma + beta
     if mod_img is not None:
         scale, shift = _film(n_img, HW, C, mod_img, scale_col, shift_col, mod_pix, img_map)

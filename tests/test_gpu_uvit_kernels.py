@@ -75,11 +75,12 @@ def test_groupnorm_stats_and_apply(n, HW, C, dt):
     g = torch.Generator().manual_seed(C + HW)
     x = (torch.randn((n, HW, C), generator=g) * 2 + 0.7).to(DEV).to(dt)
     gamma, beta = torch.randn((C,), generator=g).to(DEV), torch.randn((C,), generator=g).to(DEV)
-    sums = torch.empty((n, 32, 2), dtype=torch.float64, device=DEV)
+    sums = torch.empty((n, 32, 3), dtype=torch.float64, device=DEV)
     ops.groupnorm_stats(x, sums, n, HW, C)
     xg = x.double().reshape(n, HW, 32, C // 32)
-    assert torch.allclose(sums[..., 0], xg.sum((1, 3)), rtol=1e-5, atol=1e-2)
-    assert torch.allclose(sums[..., 1], (xg * xg).sum((1, 3)), rtol=1e-5, atol=1e-2)
+    acc = sums.reshape(-1)[: n * 32 * 2].reshape(n, 32, 2)
+    assert torch.allclose(acc[..., 0], xg.sum((1, 3)), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(acc[..., 1], (xg * xg).sum((1, 3)), rtol=1e-5, atol=1e-2)
     x_nchw = x.float().permute(0, 2, 1).reshape(n, C, HW, 1)
     gn = F.group_norm(x_nchw, 32, gamma, beta, eps=1e-6)
     out = torch.empty((n * HW, C), dtype=torch.bfloat16, device=DEV)
