@@ -256,10 +256,13 @@ class UViT3DPose(nn.Module):
                 ew = blk.norm.emb_layer.weight.detach().float()
                 eb = blk.norm.emb_layer.bias
                 fw, fb = blk.fused_attn_mlp_proj.weight.detach().float(), blk.fused_attn_mlp_proj.bias.detach().float()
+                # attn_out and mlp_out both add into the residual stream: ONE GEMM over the concatenated operand
+                # [attention | SiLU(mlp_h)] (K = 5C) with concatenated weights and summed biases
+                out_w = torch.cat([blk.attn_out.weight.detach().float(), blk.mlp_out[2].weight.detach().float()], 1)
                 d.update(norm_w=f32(blk.norm.norm.weight), qkv_w=bf(fw[: 3 * ch]), qkv_b=fb[: 3 * ch].contiguous(),
                          mlp_w=bf(fw[3 * ch:]), mlp_b=fb[3 * ch:].contiguous(), qn_w=f32(blk.q_norm.weight),
-                         kn_w=f32(blk.k_norm.weight), ao_w=bf(blk.attn_out.weight), ao_b=f32(blk.attn_out.bias),
-                         mo_w=bf(blk.mlp_out[2].weight), mo_b=f32(blk.mlp_out[2].bias))
+                         kn_w=f32(blk.k_norm.weight), out_w=bf(out_w),
+                         out_b=(blk.attn_out.bias.detach().float() + blk.mlp_out[2].bias.detach().float()).contiguous())
             d["emb_w"] = bf(ew)
             mods_w.append(ew)
             mods_b.append(eb.detach().float())
@@ -299,7 +302,7 @@ class UViT3DPose(nn.Module):
             M = n * self.res[i] ** 2
             d = dict(x=e((M, ch), f32), a16=e((M, ch), bf))
             if self.is_transformers[i]:
-                d.update(qkv=e((M, 3 * ch), bf), att=e((M, ch), bf), mh=e((M, 4 * ch), bf))
+                d.update(qkv=e((M, 3 * ch), bf), cat=e((M, 5 * ch), bf))     # cat = [attention out | SiLU(mlp_h)]
             else:
                 d.update(h16=e((M, ch), bf))
             if i + 1 < self.num_levels:
@@ -481,12 +484,11 @@ class UViT3DPose(nn.Module):
                     Ntok = T * HW
                     ops.rmsnorm_film_bf16(src, bw["norm_w"], mod, sc, sh, HW, w["a16"], mod_pix=cache, img_map=img_map)
                     ops.gemm_bf16(w["a16"], bw["qkv_w"], w["qkv"], ops.EPI_BF16, bias=bw["qkv_b"])
-                    ops.gemm_bf16(w["a16"], bw["mlp_w"], w["mh"], ops.EPI_SILU_BF16, bias=bw["mlp_b"])
+                    ops.gemm_bf16(w["a16"], bw["mlp_w"], w["cat"][:, ch:], ops.EPI_SILU_BF16, bias=bw["mlp_b"])
                     ops.qk_norm_rope(w["qkv"], bw["qn_w"], bw["kn_w"], Pk["rope"][i], Ntok, self.num_heads, dh,
                                      LOG2E / math.sqrt(dh))
-                    ops.attention(w["qkv"], w["att"], R, Ntok, self.num_heads, dh)
-                    ops.gemm_bf16(w["att"], bw["ao_w"], dst, ops.EPI_RESID_F32, bias=bw["ao_b"], resid=src)
-                    ops.gemm_bf16(w["mh"], bw["mo_w"], dst, ops.EPI_RESID_F32, bias=bw["mo_b"], resid=dst)
+                    ops.attention(w["qkv"], w["cat"][:, :ch], R, Ntok, self.num_heads, dh)
+                    ops.gemm_bf16(w["cat"], bw["out_w"], dst, ops.EPI_RESID_F32, bias=bw["out_b"], resid=src)
                 src = dst
             return dst
 

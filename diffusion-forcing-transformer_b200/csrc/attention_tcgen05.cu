@@ -213,6 +213,7 @@ __device__ __forceinline__ constexpr uint32_t make_idesc(int n, bool b_mn) {
 
 struct Params {
   __nv_bfloat16* out;
+  int64_t ld_out;   // row stride of `out` in elements (>= heads*head_dim): lets the output land inside a wider buffer
   int R, Ntok, heads, q_tiles, kv_tiles, num_items;
 };
 
@@ -448,7 +449,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params 
       const int qrow = qt * BQ + row;
       if (qrow < p.Ntok) {
         const float inv = 1.f / (l_run + l_other);
-        __nv_bfloat16* dst = p.out + ((int64_t)r * p.Ntok + qrow) * ((int64_t)p.heads * DH) + (int64_t)h * DH + wg * HC;
+        __nv_bfloat16* dst = p.out + ((int64_t)r * p.Ntok + qrow) * p.ld_out + (int64_t)h * DH + wg * HC;
 #pragma unroll
         for (int c = 0; c < HC; c += 8) {
           if (wg * HC + c < DH) {
@@ -906,7 +907,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
       tc_fence_after();
       const int qrow = qt * BQ + row;
       const float inv = 1.f / l_run;
-      __nv_bfloat16* dst = p.out + ((int64_t)r * p.Ntok + qrow) * ((int64_t)p.heads * DH) + (int64_t)h * DH;
+      __nv_bfloat16* dst = p.out + ((int64_t)r * p.Ntok + qrow) * p.ld_out + (int64_t)h * DH;
 #pragma unroll
       for (int c0 = 0; c0 < DP; c0 += 32) {
         uint32_t o[32];
@@ -976,7 +977,7 @@ static int attention_impl_override() {   // DFOT_ATTENTION_IMPL=1|2 pins the ker
 }
 
 template <int DH, int DP>
-static int launch(const void* qkv, void* out, int64_t R, int64_t Ntok, int64_t heads, cudaStream_t s) {
+static int launch(const void* qkv, void* out, int64_t ld_out, int64_t R, int64_t Ntok, int64_t heads, cudaStream_t s) {
   constexpr int ATOMS = (DP + 63) / 64;
   constexpr int smem1 = 5 * ATOMS * kAtomBytes + 2 * 2 * kAtomBytes + 160 /*barriers*/ + 2048 /*exchange*/;
   constexpr int smem2 = 6 * ATOMS * kAtomBytes + 512 /*barriers*/;
@@ -1006,6 +1007,7 @@ static int launch(const void* qkv, void* out, int64_t R, int64_t Ntok, int64_t h
   }
   Params p;
   p.out = (__nv_bfloat16*)out;
+  p.ld_out = ld_out;
   p.R = (int)R; p.Ntok = (int)Ntok; p.heads = (int)heads;
   p.q_tiles = (int)ceil_div(Ntok, BQ);
   p.kv_tiles = (int)ceil_div(Ntok, BKV);
@@ -1024,17 +1026,24 @@ static int launch(const void* qkv, void* out, int64_t R, int64_t Ntok, int64_t h
 
 extern "C" int dfot_attention(const void* qkv, void* out, int64_t R, int64_t Ntok, int64_t heads, int64_t head_dim,
                               void* stream) {
+  return dfot_attention_strided(qkv, out, heads * head_dim, R, Ntok, heads, head_dim, stream);
+}
+
+extern "C" int dfot_attention_strided(const void* qkv, void* out, int64_t ld_out, int64_t R, int64_t Ntok, int64_t heads,
+                                      int64_t head_dim, void* stream) {
   using namespace dfot;
   DFOT_REQUIRE(qkv && out && R > 0 && Ntok > 0 && heads > 0, DFOT_ERR_INVALID_ARG, "attention: bad arguments");
+  DFOT_REQUIRE(ld_out >= heads * head_dim && ld_out % 8 == 0, DFOT_ERR_INVALID_ARG,
+               "attention: ld_out must be a multiple of 8 and >= heads*head_dim");
   DFOT_REQUIRE(R * Ntok < (1ll << 31) && R * heads * ceil_div(Ntok, 128) < (1ll << 31), DFOT_ERR_UNSUPPORTED,
                "attention: problem too large");
   DFOT_REQUIRE(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 16 == 0), DFOT_ERR_UNSUPPORTED,
                "attention: qkv and out must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   switch (head_dim) {
-    case 64: return fattn::launch<64, 64>(qkv, out, R, Ntok, heads, s);
-    case 72: return fattn::launch<72, 80>(qkv, out, R, Ntok, heads, s);
-    case 128: return fattn::launch<128, 128>(qkv, out, R, Ntok, heads, s);
+    case 64: return fattn::launch<64, 64>(qkv, out, ld_out, R, Ntok, heads, s);
+    case 72: return fattn::launch<72, 80>(qkv, out, ld_out, R, Ntok, heads, s);
+    case 128: return fattn::launch<128, 128>(qkv, out, ld_out, R, Ntok, heads, s);
   }
   set_error("attention: head_dim %lld unsupported (64, 72, 128)", (long long)head_dim);
   return DFOT_ERR_UNSUPPORTED;

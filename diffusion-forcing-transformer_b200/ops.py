@@ -129,10 +129,12 @@ def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, gate=None, ld_gate=0, 
 
 
 def attention(qkv, out, R, Ntok, heads, head_dim):
-    """K3. qkv [R*Ntok, 3*D] bf16 (q rotated+scaled, k rotated), out [R*Ntok, D] bf16."""
+    """K3. qkv [R*Ntok, 3*D] bf16 (q rotated+scaled, k rotated), out [R*Ntok, D] bf16 (row stride may exceed D)."""
     _need(qkv, torch.bfloat16, "qkv")
-    _need(out, torch.bfloat16, "out")
-    rc = _abi.lib().dfot_attention(qkv.data_ptr(), out.data_ptr(), R, Ntok, heads, head_dim, _stream())
+    if not out.is_cuda or out.dtype != torch.bfloat16 or out.stride(-1) != 1 or out.shape[-1] != heads * head_dim:
+        raise RuntimeError("dfot_b200: `out` must be a CUDA bf16 [tokens, heads*head_dim] matrix with unit inner stride")
+    rc = _abi.lib().dfot_attention_strided(qkv.data_ptr(), out.data_ptr(), out.stride(0), R, Ntok, heads, head_dim,
+                                           _stream())
     _abi.check(rc, "attention")
 
 

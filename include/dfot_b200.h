@@ -159,6 +159,10 @@ DFOT_API int dfot_conv3x3_bf16(const void* x, const void* w, void* out, int64_t 
  */
 DFOT_API int dfot_attention(const void* qkv, void* out, int64_t R, int64_t Ntok, int64_t heads, int64_t head_dim,
                    void* stream);
+/* same, with an explicit row stride for `out` (elements): the U-ViT block writes the attention output straight into
+   the [attention | SiLU(mlp_h)] operand of its fused attn_out + mlp_out GEMM (u_vit_blocks.py:262-271) */
+DFOT_API int dfot_attention_strided(const void* qkv, void* out, int64_t ld_out, int64_t R, int64_t Ntok, int64_t heads,
+                           int64_t head_dim, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Small glue kernels of the DiT3D backbone (dit3d.py:153-192, embeddings.py:67-153).

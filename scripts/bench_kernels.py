@@ -79,6 +79,51 @@ def bench_norm(iters):
     print(f"adaln_layernorm M={M} D={D} (bf16 out):     {us:7.1f} us  {M * D * 6 / us / 1e3:7.1f} GB/s")
 
 
+def bench_uvit_gemm(iters):
+    """GEMM / implicit-GEMM conv shapes of one RE10K-size UViT3DPose forward at batch 4 (8 rows, 64 images)."""
+    tot_f, tot_t = 0.0, 0.0
+    print("-- convs (n_img, H, W, Cin, Cout, epilogue, count per forward)")
+    for (n, H, Cin, Cout, epi, cnt) in [(64, 128, 128, 128, ops.EPI_BF16, 6), (64, 128, 128, 128, ops.EPI_RESID_F32, 6),
+                                        (64, 64, 256, 256, ops.EPI_BF16, 6), (64, 64, 256, 256, ops.EPI_RESID_F32, 6),
+                                        (64, 64, 128, 256, ops.EPI_F32, 1), (64, 32, 256, 576, ops.EPI_F32, 1),
+                                        (64, 16, 576, 1152, ops.EPI_F32, 1), (64, 16, 1152, 576, ops.EPI_F32, 1),
+                                        (64, 32, 576, 256, ops.EPI_F32, 1), (64, 64, 256, 128, ops.EPI_F32, 1)]:
+        x = torch.randn((n, H, H, Cin), device=DEV).to(torch.bfloat16)
+        w = (torch.randn((Cout, 3, 3, Cin), device=DEV) / math.sqrt(9 * Cin)).to(torch.bfloat16)
+        bias = torch.randn((Cout,), device=DEV)
+        f32 = epi in (ops.EPI_F32, ops.EPI_RESID_F32)
+        out = torch.empty((n * H * H, Cout), device=DEV, dtype=torch.float32 if f32 else torch.bfloat16)
+        kw = dict(bias=bias)
+        if epi == ops.EPI_RESID_F32:
+            kw["resid"] = out
+        us = timeit(lambda: ops.conv3x3_bf16(x, w, out, epi, **kw), iters)
+        fl = 2.0 * n * H * H * Cout * 9 * Cin
+        tot_f += fl * cnt
+        tot_t += us * cnt
+        print(f"conv {H:3d}x{H:<3d} {Cin:4d}->{Cout:<4d} epi={epi}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  x{cnt}")
+    print("-- linears (M, N, K, epilogue, count per forward)")
+    for (M, N, K, epi, cnt) in [(65536, 1728, 576, ops.EPI_BF16, 12), (65536, 2304, 576, ops.EPI_SILU_BF16, 12),
+                                (65536, 576, 576, ops.EPI_RESID_F32, 12), (65536, 576, 2304, ops.EPI_RESID_F32, 12),
+                                (65536, 576, 2880, ops.EPI_RESID_F32, 0),
+                                (16384, 3456, 1152, ops.EPI_BF16, 20), (16384, 4608, 1152, ops.EPI_SILU_BF16, 20),
+                                (16384, 1152, 1152, ops.EPI_RESID_F32, 20), (16384, 1152, 4608, ops.EPI_RESID_F32, 20),
+                                (16384, 1152, 5760, ops.EPI_RESID_F32, 0)]:
+        a = torch.randn((M, K), device=DEV).to(torch.bfloat16)
+        w = (torch.randn((N, K), device=DEV) / math.sqrt(K)).to(torch.bfloat16)
+        bias = torch.randn((N,), device=DEV)
+        f32 = epi in (ops.EPI_F32, ops.EPI_RESID_F32)
+        out = torch.empty((M, N), device=DEV, dtype=torch.float32 if f32 else torch.bfloat16)
+        kw = dict(bias=bias)
+        if epi == ops.EPI_RESID_F32:
+            kw["resid"] = out
+        us = timeit(lambda: ops.gemm_bf16(a, w, out, epi, **kw), iters)
+        fl = 2.0 * M * N * K
+        tot_f += fl * cnt
+        tot_t += us * cnt
+        print(f"gemm M={M} N={N:4d} K={K:4d} epi={epi}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  x{cnt}")
+    print(f"per forward: {tot_t / 1e3:.2f} ms, {tot_f / tot_t / 1e6:.1f} TFLOP/s average")
+
+
 def bench_uvit(iters):
     """HBM-bound U-ViT3DPose kernels at the RE10K level-0 / level-2 sizes of a batch-4 (8-row) forward."""
     n, HW, C = 64, 16384, 128
@@ -132,3 +177,5 @@ if __name__ == "__main__":
         bench_norm(a.iters)
     if a.which in ("uvit", "all"):
         bench_uvit(a.iters)
+    if a.which in ("uvit_gemm", "all"):
+        bench_uvit_gemm(a.iters)
