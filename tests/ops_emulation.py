@@ -173,3 +173,17 @@ def install(monkeypatch):
     for name in ALL:
         monkeypatch.setattr(ops, name, g[name])
     monkeypatch.setattr(ops, "require_cuda", lambda *a, **k: None)
+
+
+def install_raw():
+    """Same as install() without a pytest fixture (sub-processes); returns a function that undoes it."""
+    g = globals()
+    saved = {name: getattr(ops, name) for name in ALL + ["require_cuda"]}
+    for name in ALL:
+        setattr(ops, name, g[name])
+    ops.require_cuda = lambda *a, **k: None
+
+    def restore():
+        for name, fn in saved.items():
+            setattr(ops, name, fn)
+    return restore

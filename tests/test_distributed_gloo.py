@@ -18,19 +18,26 @@ def _build(case):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import k4_emulation
     from dfot_b200 import ops
-    from dfot_b200.algorithms.dfot import DFoTVideo
-    from helpers import NoiseBank, build_oracle, load_case
+    from helpers import NoiseBank, build_oracle, build_product, load_case
     meta, arr, weights = load_case(case)
     cfg = meta["cfg"]
-    algo = DFoTVideo(cfg)
+    algo = build_product(cfg)
     algo.model_in_dtype = torch.float32
-    _, backbone = build_oracle(cfg, weights)
+    if cfg["backbone"]["name"] == "u_vit3d_pose":
+        # the product's own U-ViT3DPose host code (pose cache, row maps under branch sharding) on emulated kernels
+        import ops_emulation
+        sd = {"diffusion_model.model." + k: v for k, v in weights.items()}
+        sd["data_mean"], sd["data_std"] = algo.data_mean, algo.data_std
+        algo.load_state_dict(sd, strict=True)
+        ops_emulation.install_raw()
+    else:
+        _, backbone = build_oracle(cfg, weights)
 
-    class OracleBackbone(torch.nn.Module):
-        def forward(self, x, k, c=None, cm=None, out_dtype=None):
-            return backbone(x, k, c, cm)
+        class OracleBackbone(torch.nn.Module):
+            def forward(self, x, k, c=None, cm=None, out_dtype=None):
+                return backbone(x, k, c, cm)
 
-    algo.diffusion_model.model = OracleBackbone()
+        algo.diffusion_model.model = OracleBackbone()
     ops.sampler_step_hg = k4_emulation.emulate
     xs = torch.from_numpy(arr["xs"])
     conds = torch.from_numpy(arr["conds"]) if "conds" in arr else None
@@ -58,7 +65,7 @@ def _worker(rank, world, port, case, br, out_path):
 def _single(case, shard_starts):
     sys.path.insert(0, ROOT)
     from dfot_b200 import ops
-    real_op = ops.sampler_step_hg
+    real_ops = dict(vars(ops))
     try:
         algo, cfg, xs, conds, NoiseBank = _build(case)   # patches ops.sampler_step_hg in this process
         outs = []
@@ -71,10 +78,12 @@ def _single(case, shard_starts):
                                              None if conds is None else conds[a:b]))
         return torch.cat(outs, 0).numpy()
     finally:
-        ops.sampler_step_hg = real_op
+        for k, v in real_ops.items():
+            setattr(ops, k, v)
 
 
-@pytest.mark.parametrize("case,br", [("vanilla", 1), ("vanilla", 2), ("continuous_action", 2), ("temporal", 1)])
+@pytest.mark.parametrize("case,br", [("vanilla", 1), ("vanilla", 2), ("continuous_action", 2), ("temporal", 1),
+                                     ("uvit_pose_vanilla", 2)])
 def test_world2_matches_single_process(case, br, tmp_path):
     world = 2
     port = 29500 + (os.getpid() + hash((case, br))) % 2000
@@ -93,4 +102,4 @@ def test_world2_matches_single_process(case, br, tmp_path):
     if br == 1:
         assert np.array_equal(got, want)          # sample sharding: bit-exact
     else:                                         # branch sharding changes the CPU BLAS batch shape of the checker
-        assert np.abs(got - want).max() <= 1e-5
+        assert np.abs(got - want).max() <= (2e-2 if "uvit" in case else 1e-5)   # (bf16-emulated kernels for U-ViT)
