@@ -96,7 +96,7 @@ __global__ void gn_finalize_kernel(const double* __restrict__ sums, float2* __re
 // grid (pixel slabs, images); a thread owns ONE 8-channel vector (so gamma / beta / statistics / per-image FiLM are
 // loaded once and folded into a per-channel affine) and walks kGnPix pixels of its slab with all loads issued up
 // front — no 64-bit index arithmetic, 4 independent 16/32-byte loads in flight per thread.
-constexpr int kGnPix = 2;
+constexpr int kGnPix = 2, kGnIter = 4;
 template <typename TX>
 __global__ void __launch_bounds__(kThreads, 3)
 gn_silu_kernel(const TX* __restrict__ x, const float2* __restrict__ stats, const float* __restrict__ gamma,
@@ -130,44 +130,49 @@ gn_silu_kernel(const TX* __restrict__ x, const float2* __restrict__ stats, const
 #pragma unroll
     for (int j = 0; j < 8; ++j) { A[j] *= 1.f + sc[j]; B[j] = fmaf(B[j], 1.f + sc[j], sh[j]); }
   }
-  const int pix0 = blockIdx.x * (pix_step * kGnPix) + prow;
   const TX* xb = x + (int64_t)img * HW * C + c0;
   __nv_bfloat16* yb = y + (int64_t)img * HW * C + c0;
-  float a[kGnPix][8];
-#pragma unroll
-  for (int k = 0; k < kGnPix; ++k) {
-    const int pix = pix0 + k * pix_step;
-    if (pix < HW) load8(xb + (int64_t)pix * C, a[k]);
-  }
-  if (src >= 0) {
-    const __nv_bfloat16* pb = mod_pix + (int64_t)src * HW * (2 * C) + c0;
-    float ps[kGnPix][8], ph[kGnPix][8];
+  const __nv_bfloat16* pb = src >= 0 ? mod_pix + (int64_t)src * HW * (2 * C) + c0 : nullptr;
+  // kGnIter groups of kGnPix pixels: the prologue above (≈20 cached loads) is amortised over kGnIter*kGnPix pixels
+#pragma unroll 1
+  for (int it = 0; it < kGnIter; ++it) {
+    const int pix0 = (blockIdx.x * kGnIter + it) * (pix_step * kGnPix) + prow;
+    if (pix0 >= HW) break;
+    float a[kGnPix][8];
 #pragma unroll
     for (int k = 0; k < kGnPix; ++k) {
       const int pix = pix0 + k * pix_step;
-      if (pix < HW) {
-        load8(pb + (int64_t)pix * (2 * C), ps[k]);
-        load8(pb + (int64_t)pix * (2 * C) + C, ph[k]);
-      }
+      if (pix < HW) load8(xb + (int64_t)pix * C, a[k]);
     }
+    if (pb != nullptr) {
+      float ps[kGnPix][8], ph[kGnPix][8];
 #pragma unroll
-    for (int k = 0; k < kGnPix; ++k) {
-      const int pix = pix0 + k * pix_step;
-      if (pix < HW) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          a[k][j] = silu_fast_f(fmaf(fmaf(a[k][j], A[j], B[j]), 1.f + (sc[j] + ps[k][j]), sh[j] + ph[k][j]));
-        store8(yb + (int64_t)pix * C, a[k]);
+      for (int k = 0; k < kGnPix; ++k) {
+        const int pix = pix0 + k * pix_step;
+        if (pix < HW) {
+          load8(pb + (int64_t)pix * (2 * C), ps[k]);
+          load8(pb + (int64_t)pix * (2 * C) + C, ph[k]);
+        }
       }
-    }
-  } else {
 #pragma unroll
-    for (int k = 0; k < kGnPix; ++k) {
-      const int pix = pix0 + k * pix_step;
-      if (pix < HW) {
+      for (int k = 0; k < kGnPix; ++k) {
+        const int pix = pix0 + k * pix_step;
+        if (pix < HW) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[k][j] = silu_fast_f(fmaf(a[k][j], A[j], B[j]));
-        store8(yb + (int64_t)pix * C, a[k]);
+          for (int j = 0; j < 8; ++j)
+            a[k][j] = silu_fast_f(fmaf(fmaf(a[k][j], A[j], B[j]), 1.f + (sc[j] + ps[k][j]), sh[j] + ph[k][j]));
+          store8(yb + (int64_t)pix * C, a[k]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kGnPix; ++k) {
+        const int pix = pix0 + k * pix_step;
+        if (pix < HW) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[k][j] = silu_fast_f(fmaf(a[k][j], A[j], B[j]));
+          store8(yb + (int64_t)pix * C, a[k]);
+        }
       }
     }
   }
@@ -443,7 +448,7 @@ extern "C" int dfot_groupnorm_silu_bf16(const void* x, int x_dtype, const double
   DFOT_REQUIRE(vecs <= kThreads && kThreads % vecs == 0 && n_img < 65536 && HW < (1ll << 30), DFOT_ERR_UNSUPPORTED,
                "groupnorm_silu: C/8 = %d must divide %d", vecs, kThreads);
   const float2* stats = reinterpret_cast<const float2*>(sums + 2 * n_img * groups);
-  const dim3 grid((unsigned)ceil_div(HW, (kThreads / vecs) * kGnPix), (unsigned)n_img);
+  const dim3 grid((unsigned)ceil_div(HW, (kThreads / vecs) * kGnPix * kGnIter), (unsigned)n_img);
   if (x_dtype == DFOT_F32)
     gn_silu_kernel<float><<<grid, kThreads, 0, s>>>(
         (const float*)x, stats, gamma, beta, mod_img, ld_img, scale_col, shift_col, (const __nv_bfloat16*)mod_pix,
