@@ -31,7 +31,8 @@ class GemmEpilogue(Structure):
     _fields_ = [("bias", c_void_p), ("resid", c_void_p), ("ld_resid", c_int64), ("gate", c_void_p),
                 ("ld_gate", c_int64), ("tokens_per_frame", c_int64), ("rope_cs", c_void_p),
                 ("tokens_per_sample", c_int64), ("model_dim", c_int64), ("head_dim", c_int64),
-                ("q_scale", c_float)]
+                ("q_scale", c_float), ("gn_sums", c_void_p), ("gn_rows_per_img", c_int64), ("gn_groups", c_int64),
+                ("gn_eps", c_float)]
 
 
 _lib = None

@@ -295,7 +295,7 @@ class UViT3DPose(nn.Module):
         n_mod = sum(2 * self.channels[l] for _, l in self._blocks_in_order())
         M0 = n * self.res[0] ** 2
         ws = dict(feat=e((n, 256), bf), e1=e((n, E), bf), emb=e((n, E), bf), mod=e((n, n_mod), f32),
-                  patches=torch.zeros((M0, _pad8(C * p * p)), dtype=bf, device=dev), sums=e((n, 32, 3), torch.float64),
+                  patches=torch.zeros((M0, _pad8(C * p * p)), dtype=bf, device=dev), sums=e((n, 32, 3), torch.float64), sums_h=e((n, 32, 3), torch.float64),
                   x0_16=e((M0, self.channels[0]), bf), tok=e((M0, _pad8(p * p * C)), f32),
                   out=e((R, T, *self.x_shape), out_dtype), img_map=e((n,), torch.int32), lv=[])
         for i, ch in enumerate(self.channels):
@@ -445,7 +445,7 @@ class UViT3DPose(nn.Module):
         C, H, W = self.x_shape
         p, L, n = self.patch_size, self.num_levels, R * T
         Pk = self.packed()
-        lv, mod, img_map, sums = ws["lv"], ws["mod"], ws["img_map"], ws["sums"]
+        lv, mod, img_map, sums, sums_h = ws["lv"], ws["mod"], ws["img_map"], ws["sums"], ws["sums_h"]
         x = x.contiguous()
         levels = levels.contiguous()
 
@@ -466,19 +466,27 @@ class UViT3DPose(nn.Module):
             g = self.res[i]
             HW = g * g
             dst = w["x"]
-            for _ in range(count):
+            # GroupNorm statistics ride on the conv epilogues (of the values as stored); only a level's first ResBlock
+            # needs a stand-alone statistics pass over its input.  (HW % 32 == 0 is what the epilogue path needs.)
+            fused_stats = HW % 32 == 0 and ch // 32 in (1, 2, 4, 8, 16, 32)
+            have_stats = False
+            for b in range(count):
                 bw, cache = next(blocks)
                 assert bw["level"] == i
                 sc, sh = bw["col"], bw["col"] + ch
                 if bw["kind"] == "res":
-                    ops.groupnorm_stats(src, sums, n, HW, ch)
+                    if not have_stats:
+                        ops.groupnorm_stats(src, sums, n, HW, ch)
                     ops.groupnorm_silu_bf16(src, sums, bw["gn1_w"], bw["gn1_b"], w["a16"], n, HW, ch)
-                    ops.conv3x3_bf16(w["a16"].view(n, g, g, ch), bw["conv1_w"], w["h16"], ops.EPI_BF16, bias=bw["conv1_b"])
-                    ops.groupnorm_stats(w["h16"], sums, n, HW, ch)
-                    ops.groupnorm_silu_bf16(w["h16"], sums, bw["gn2_w"], bw["gn2_b"], w["a16"], n, HW, ch, mod_img=mod,
+                    ops.conv3x3_bf16(w["a16"].view(n, g, g, ch), bw["conv1_w"], w["h16"], ops.EPI_BF16, bias=bw["conv1_b"],
+                                     gn_sums=sums_h if fused_stats else None)
+                    if not fused_stats:
+                        ops.groupnorm_stats(w["h16"], sums_h, n, HW, ch)
+                    ops.groupnorm_silu_bf16(w["h16"], sums_h, bw["gn2_w"], bw["gn2_b"], w["a16"], n, HW, ch, mod_img=mod,
                                             scale_col=sc, shift_col=sh, mod_pix=cache, img_map=img_map)
+                    have_stats = fused_stats and b + 1 < count      # statistics of the block's output for the next block
                     ops.conv3x3_bf16(w["a16"].view(n, g, g, ch), bw["conv2_w"], dst, ops.EPI_RESID_F32,
-                                     bias=bw["conv2_b"], resid=src)
+                                     bias=bw["conv2_b"], resid=src, gn_sums=sums if have_stats else None)
                 else:
                     dh = ch // self.num_heads
                     Ntok = T * HW

@@ -37,6 +37,11 @@ void count_launch(int n = 1);
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// GroupNorm statistics workspace helpers shared by uvit.cu (stand-alone pass) and gemm_tcgen05.cu (epilogue side output):
+// sums = [n_img*groups][2] f64 (sum, sum of squares) followed by [n_img*groups] float2 (mean, rstd)
+int gn_zero_sums(double* sums, int64_t n_img, int64_t groups, cudaStream_t s);
+int gn_finalize(double* sums, int64_t n_img, int64_t groups, int64_t count_per_group, float eps, cudaStream_t s);
+
 // ---- device helpers ----
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

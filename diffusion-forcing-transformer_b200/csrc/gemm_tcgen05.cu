@@ -258,6 +258,34 @@ __device__ __forceinline__ void prefetch_side(const Params& p, ChunkSide<EPI>& s
   }
 }
 
+// GroupNorm side output: a lane holds (sum, sum of squares) of `ncol` adjacent columns starting at `col` over the rows
+// of this chunk (all of one image: rows_per_img % 32 == 0).  Lanes of one group are combined by xor-shuffles
+// (channels per group is a power of two), then one f64 atomic pair per group and chunk goes to the workspace.
+// lane_cols = columns covered by consecutive lanes (1 for the f32 pass, 2 for the bf16 pass, where lanes 16-31 mirror
+// lanes 0-15 on the odd rows).
+__device__ __forceinline__ void gn_flush(const Params& p, int lane, int m0, int col, int lane_cols, float s, float q,
+                                         bool col_ok) {
+  const int cpg = p.N / (int)p.e.gn_groups;
+  if (!col_ok) { s = 0.f; q = 0.f; }
+  if (lane_cols == 2) {   // fold the two row-halves of the warp
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+    q += __shfl_xor_sync(0xffffffffu, q, 16);
+  }
+  const int lanes_per_group = cpg / lane_cols;   // >= 1 (cpg == 1 is handled by the caller with lane_cols == 1)
+  for (int o = 1; o < lanes_per_group && o < 32; o <<= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const int l = lane_cols == 2 ? (lane & 15) : lane;
+  const bool leader = (l % (lanes_per_group > 32 ? 32 : lanes_per_group)) == 0 && (lane_cols == 1 || lane < 16);
+  if (leader && col_ok) {
+    const int64_t img = m0 / p.e.gn_rows_per_img;
+    double* dst = p.e.gn_sums + (img * p.e.gn_groups + col / cpg) * 2;
+    atomicAdd(dst, (double)s);
+    atomicAdd(dst + 1, (double)q);
+  }
+}
+
 // Phase 2 for fp32 outputs: lane = column, loop over the 32 rows of the chunk.
 template <int EPI, bool FULL>
 __device__ __forceinline__ void epilogue_rows_f32(const Params& p, const ChunkSide<EPI>& sd, uint32_t stage, int lane,
@@ -279,14 +307,20 @@ __device__ __forceinline__ void epilogue_rows_f32(const Params& p, const ChunkSi
       if (split < 32) gate1 = __ldg(p.e.gate + (int64_t)(f0 + 1) * p.e.ld_gate + col);
     }
   }
+  const bool gn = p.e.gn_sums != nullptr;   // warp-uniform
+  float gs = 0.f, gq = 0.f;
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
     const float acc = lds_f32(sbase + (uint32_t)i * 128u + (uint32_t)((((lane >> 2) ^ (i & 7))) << 4));
     float y = acc + bias;
     if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) y = sd.v[i] + (i < split ? gate0 : gate1) * y;
     if constexpr (EPI == DFOT_EPI_RESID_F32) y = sd.v[i] + y;
-    if (FULL || (col_ok && i < rows)) out[(int64_t)i * p.ldc] = y;
+    if (FULL || (col_ok && i < rows)) {
+      out[(int64_t)i * p.ldc] = y;
+      if (gn) { gs += y; gq = fmaf(y, y, gq); }
+    }
   }
+  if (gn) gn_flush(p, lane, m0, col, 1, gs, gq, col_ok);
 }
 
 // Phase 2 for bf16 outputs: a lane owns two adjacent columns (a RoPE pair); lanes 0-15 take row 2k, 16-31 row 2k+1.
@@ -302,6 +336,8 @@ __device__ __forceinline__ void epilogue_rows_bf16(const Params& p, const ChunkS
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)m0 * p.ldc + col;
   const float qs = (EPI == DFOT_EPI_QKV_ROPE_BF16 && col < (int)p.e.model_dim) ? p.e.q_scale : 1.f;
   const int half = lane >> 4;
+  const bool gn = p.e.gn_sums != nullptr;   // warp-uniform
+  float gs0 = 0.f, gq0 = 0.f, gs1 = 0.f, gq1 = 0.f;
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     const int i = 2 * k + half;
@@ -321,7 +357,29 @@ __device__ __forceinline__ void epilogue_rows_bf16(const Params& p, const ChunkS
       v.x = (x0 * c - x1 * sn) * qs;
       v.y = (x1 * c + x0 * sn) * qs;
     }
-    if (FULL || (col_ok && i < rows)) *reinterpret_cast<uint32_t*>(out + (int64_t)i * p.ldc) = pack_bf16x2(v.x, v.y);
+    if (FULL || (col_ok && i < rows)) {
+      const uint32_t packed = pack_bf16x2(v.x, v.y);
+      *reinterpret_cast<uint32_t*>(out + (int64_t)i * p.ldc) = packed;
+      if (gn) {   // statistics of the values as stored (bf16-rounded), like a separate pass over the output would see
+        const float2 r = unpack_bf16x2(packed);
+        gs0 += r.x; gq0 = fmaf(r.x, r.x, gq0);
+        gs1 += r.y; gq1 = fmaf(r.y, r.y, gq1);
+      }
+    }
+  }
+  if (gn) {
+    if (p.N / (int)p.e.gn_groups == 1) {   // one channel per group: the two columns of a lane are separate groups
+      gs0 += __shfl_xor_sync(0xffffffffu, gs0, 16); gq0 += __shfl_xor_sync(0xffffffffu, gq0, 16);
+      gs1 += __shfl_xor_sync(0xffffffffu, gs1, 16); gq1 += __shfl_xor_sync(0xffffffffu, gq1, 16);
+      if (lane < 16 && col_ok) {
+        const int64_t img = m0 / p.e.gn_rows_per_img;
+        double* dst = p.e.gn_sums + (img * p.e.gn_groups + col) * 2;
+        atomicAdd(dst, (double)gs0); atomicAdd(dst + 1, (double)gq0);
+        atomicAdd(dst + 2, (double)gs1); atomicAdd(dst + 3, (double)gq1);
+      }
+    } else {
+      gn_flush(p, lane, m0, col, 2, gs0 + gs1, gq0 + gq1, col_ok);
+    }
   }
 }
 
@@ -603,6 +661,25 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   return DFOT_OK;
 }
 
+// GroupNorm side output: validate, zero the workspace before the launch (gn_begin) and finalise after it (gn_end)
+static int gn_begin(const Params& p, int epilogue, cudaStream_t s) {
+  if (p.e.gn_sums == nullptr) return DFOT_OK;
+  DFOT_REQUIRE(epilogue == DFOT_EPI_F32 || epilogue == DFOT_EPI_RESID_F32 || epilogue == DFOT_EPI_BF16,
+               DFOT_ERR_UNSUPPORTED, "gemm: GroupNorm side output needs the F32, RESID_F32 or BF16 epilogue");
+  const int64_t G = p.e.gn_groups, rpi = p.e.gn_rows_per_img;
+  DFOT_REQUIRE(G > 0 && p.N % G == 0 && rpi > 0 && rpi % 32 == 0 && p.M % rpi == 0, DFOT_ERR_UNSUPPORTED,
+               "gemm: GroupNorm side output needs N %% groups == 0, rows_per_img %% 32 == 0 and M %% rows_per_img == 0");
+  const int64_t cpg = p.N / G;
+  DFOT_REQUIRE((cpg & (cpg - 1)) == 0, DFOT_ERR_UNSUPPORTED, "gemm: channels per group (%lld) must be a power of two",
+               (long long)cpg);
+  return gn_zero_sums(p.e.gn_sums, p.M / rpi, G, s);
+}
+static int gn_end(const Params& p, cudaStream_t s) {
+  if (p.e.gn_sums == nullptr) return DFOT_OK;
+  const int64_t G = p.e.gn_groups, rpi = p.e.gn_rows_per_img;
+  return gn_finalize(p.e.gn_sums, p.M / rpi, G, rpi * (p.N / G), p.e.gn_eps, s);
+}
+
 template <int BN>
 static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t s) {
   switch (epi) {
@@ -653,16 +730,19 @@ extern "C" int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   int rc = make_tmap(&ta, A, M, K, lda, BM);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = gn_begin(p, epilogue, s))) return rc;
   // widest tile whose last column block is not mostly padding
   if (N > 128) {
     rc = make_tmap(&tb, W, N, K, ldw, 256);
-    return rc ? rc : dispatch_epi<256>(epilogue, ta, tb, p, s);
+    if (!rc) rc = dispatch_epi<256>(epilogue, ta, tb, p, s);
   } else if (N > 64) {
     rc = make_tmap(&tb, W, N, K, ldw, 128);
-    return rc ? rc : dispatch_epi<128>(epilogue, ta, tb, p, s);
+    if (!rc) rc = dispatch_epi<128>(epilogue, ta, tb, p, s);
+  } else {
+    rc = make_tmap(&tb, W, N, K, ldw, 64);
+    if (!rc) rc = dispatch_epi<64>(epilogue, ta, tb, p, s);
   }
-  rc = make_tmap(&tb, W, N, K, ldw, 64);
-  return rc ? rc : dispatch_epi<64>(epilogue, ta, tb, p, s);
+  return rc ? rc : gn_end(p, s);
 }
 
 // 3x3 convolution, stride 1, zero padding 1, over NHWC bf16 activations as an implicit GEMM on the same kernel:
@@ -725,7 +805,10 @@ extern "C" int dfot_conv3x3_bf16(const void* x, const void* w, void* out, int64_
     if (rc) return rc;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (bnt == 256) return dispatch_epi<256>(epilogue, ta, tb, p, s);
-  if (bnt == 128) return dispatch_epi<128>(epilogue, ta, tb, p, s);
-  return dispatch_epi<64>(epilogue, ta, tb, p, s);
+  int rc = gn_begin(p, epilogue, s);
+  if (rc) return rc;
+  if (bnt == 256) rc = dispatch_epi<256>(epilogue, ta, tb, p, s);
+  else if (bnt == 128) rc = dispatch_epi<128>(epilogue, ta, tb, p, s);
+  else rc = dispatch_epi<64>(epilogue, ta, tb, p, s);
+  return rc ? rc : gn_end(p, s);
 }

@@ -393,6 +393,19 @@ pose_ray_patches_kernel(const float* __restrict__ cams, const float* __restrict_
 static inline unsigned blocks_for(int64_t n) { return (unsigned)ceil_div(n, kThreads); }
 
 }  // namespace uvit
+
+int gn_zero_sums(double* sums, int64_t n_img, int64_t groups, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * n_img * groups, s);
+  DFOT_REQUIRE(e == cudaSuccess, DFOT_ERR_CUDA, "groupnorm: memset failed: %s", cudaGetErrorString(e));
+  return DFOT_OK;
+}
+int gn_finalize(double* sums, int64_t n_img, int64_t groups, int64_t count_per_group, float eps, cudaStream_t s) {
+  float2* stats = reinterpret_cast<float2*>(sums + 2 * n_img * groups);
+  const int64_t n = n_img * groups;
+  uvit::gn_finalize_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, s>>>(sums, stats, n, 1.0 / (double)count_per_group, eps);
+  DFOT_CHECK_LAUNCH("groupnorm_finalize");
+  return DFOT_OK;
+}
 }  // namespace dfot
 
 using namespace dfot;
@@ -407,8 +420,7 @@ extern "C" int dfot_groupnorm_stats(const void* x, int x_dtype, double* sums, in
   DFOT_REQUIRE(vecs <= kThreads && kThreads % vecs == 0, DFOT_ERR_UNSUPPORTED,
                "groupnorm_stats: C/8 = %d must divide %d", vecs, kThreads);
   cudaStream_t s = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * n_img * groups, s);
-  DFOT_REQUIRE(e == cudaSuccess, DFOT_ERR_CUDA, "groupnorm_stats: memset failed: %s", cudaGetErrorString(e));
+  if (int rc = gn_zero_sums(sums, n_img, groups, s)) return rc;
   // ~8 resident blocks per SM over the whole batch, at least 8 pixels per thread-row
   const int pix_rows = kThreads / vecs;
   int64_t slabs = ceil_div(148 * 8, n_img);
@@ -424,11 +436,7 @@ extern "C" int dfot_groupnorm_stats(const void* x, int x_dtype, double* sums, in
     DFOT_REQUIRE(false, DFOT_ERR_INVALID_ARG, "groupnorm_stats: x dtype must be f32 or bf16");
   DFOT_CHECK_LAUNCH("groupnorm_stats");
   // (mean, rstd) as f32 pairs, stored behind the f64 sums in the same buffer
-  float2* stats = reinterpret_cast<float2*>(sums + 2 * n_img * groups);
-  const int64_t n = n_img * groups;
-  gn_finalize_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, s>>>(sums, stats, n, 1.0 / ((double)HW * (double)(C / groups)), eps);
-  DFOT_CHECK_LAUNCH("groupnorm_finalize");
-  return DFOT_OK;
+  return gn_finalize(sums, n_img, groups, HW * (C / groups), eps, s);
 }
 
 extern "C" int dfot_groupnorm_silu_bf16(const void* x, int x_dtype, const double* sums, const float* gamma,

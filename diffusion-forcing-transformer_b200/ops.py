@@ -92,8 +92,19 @@ def adaln_layernorm(x, mod, shift_col, scale_col, tokens_per_frame, y_f32=None, 
     _abi.check(rc, "adaln_layernorm")
 
 
+def _gn_side_output(e, gn_sums, gn_rows_per_img, gn_groups, gn_eps, M, N):
+    """GroupNorm statistics of the output as a side product of the epilogue (see include/dfot_b200.h)."""
+    if gn_sums is None:
+        return
+    _need(gn_sums, torch.float64, "gn_sums")
+    if gn_rows_per_img <= 0 or M % gn_rows_per_img or gn_sums.numel() != 3 * (M // gn_rows_per_img) * gn_groups:
+        raise RuntimeError("dfot_b200: gn_sums must hold 3 * n_img * groups doubles (n_img = M / gn_rows_per_img)")
+    e.gn_sums, e.gn_rows_per_img, e.gn_groups, e.gn_eps = gn_sums.data_ptr(), gn_rows_per_img, gn_groups, gn_eps
+
+
 def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, gate=None, ld_gate=0, tokens_per_frame=1, rope_cs=None,
-              tokens_per_sample=1, model_dim=0, head_dim=0, q_scale=1.0, M=None):
+              tokens_per_sample=1, model_dim=0, head_dim=0, q_scale=1.0, M=None, gn_sums=None, gn_rows_per_img=0,
+              gn_groups=32, gn_eps=1e-6):
     """K2. a [M,K] bf16 (row stride may exceed K), w [N,K] bf16, out [M,N] f32|bf16 per epilogue."""
     _need(w, torch.bfloat16, "w")
     if not a.is_cuda or a.dtype != torch.bfloat16 or a.stride(-1) != 1:
@@ -123,6 +134,7 @@ def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, gate=None, ld_gate=0, 
         _need(rope_cs, torch.float32, "rope_cs")
         e.rope_cs = rope_cs.data_ptr()
     e.tokens_per_sample, e.model_dim, e.head_dim, e.q_scale = tokens_per_sample, model_dim, head_dim, q_scale
+    _gn_side_output(e, gn_sums, gn_rows_per_img, gn_groups, gn_eps, M, N)
     rc = _abi.lib().dfot_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
                                    out.stride(0), M, N, K, epilogue, ctypes.byref(e), _stream())
     _abi.check(rc, "gemm_bf16")
@@ -189,7 +201,7 @@ def cast_bf16(src, out=None):
 
 
 # ------------------------------------------------------------------ U-ViT3DPose kernels
-def conv3x3_bf16(x, w, out, epilogue, bias=None, resid=None):
+def conv3x3_bf16(x, w, out, epilogue, bias=None, resid=None, gn_sums=None, gn_groups=32, gn_eps=1e-6):
     """3x3 conv, stride 1, padding 1, implicit GEMM.  x [n,H,W,Cin] bf16 channel-last, w [Cout,3,3,Cin] bf16,
     out [n*H*W, Cout] f32|bf16 per epilogue (EPI_F32, EPI_BF16, EPI_SILU_BF16, EPI_RESID_F32)."""
     _need(x, torch.bfloat16, "x")
@@ -210,6 +222,7 @@ def conv3x3_bf16(x, w, out, epilogue, bias=None, resid=None):
         _need(resid, torch.float32, "resid")
         e.resid, e.ld_resid = resid.data_ptr(), Cout
     e.tokens_per_frame = 1
+    _gn_side_output(e, gn_sums, H * W, gn_groups, gn_eps, n * H * W, Cout)
     rc = _abi.lib().dfot_conv3x3_bf16(x.data_ptr(), w.data_ptr(), out.data_ptr(), Cout, n, H, W, Cin, Cout, epilogue,
                                       ctypes.byref(e), _stream())
     _abi.check(rc, "conv3x3_bf16")

@@ -132,6 +132,14 @@ typedef struct {
   int64_t model_dim;          /* D */
   int64_t head_dim;
   float q_scale;              /* multiplies q after rotation (softmax scale * log2 e) */
+  /* optional side output of the F32 / RESID_F32 / BF16 epilogues: GroupNorm statistics of the OUTPUT (as stored),
+     so the next GroupNorm needs no extra pass over HBM.  gn_sums: the 3*n_img*groups-double workspace of
+     dfot_groupnorm_stats (zeroed, accumulated and finalised to (mean, rstd) by the call); image = m / gn_rows_per_img
+     (gn_rows_per_img % 32 == 0), group = n / (N / gn_groups) (power-of-two channels per group). NULL = off */
+  double* gn_sums;
+  int64_t gn_rows_per_img;
+  int64_t gn_groups;
+  float gn_eps;
 } dfot_gemm_epilogue;
 
 DFOT_API int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int64_t M,

@@ -48,10 +48,13 @@ def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, M=None, **kw):
     _epilogue(a[:M].float() @ w.float().t(), out[:M], epilogue, bias, None if resid is None else resid[:M])
 
 
-def conv3x3_bf16(x, w, out, epilogue, bias=None, resid=None):
+def conv3x3_bf16(x, w, out, epilogue, bias=None, resid=None, gn_sums=None, gn_groups=32, gn_eps=1e-6):
     assert x.dtype == BF and w.dtype == BF
     y = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), None, padding=1).permute(0, 2, 3, 1)
     _epilogue(y.reshape(-1, w.shape[0]), out, epilogue, bias, resid)
+    if gn_sums is not None:      # side output: statistics of the stored output
+        n, H, W_, _ = x.shape
+        groupnorm_stats(out, gn_sums, n, H * W_, w.shape[0], gn_groups, gn_eps)
 
 
 def groupnorm_stats(x, sums, n_img, HW, C, groups=32, eps=1e-6):

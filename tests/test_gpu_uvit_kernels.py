@@ -52,6 +52,33 @@ def test_conv3x3_implicit_gemm(n, H, W, Cin, Cout):
     assert rel_err(out16, ref) < 5e-3
 
 
+@pytest.mark.parametrize("n,H,C,epi", [(4, 64, 128, "bf16"), (4, 64, 128, "resid"), (3, 32, 256, "bf16"), (3, 32, 256, "f32"),
+                                       (4, 16, 32, "bf16"), (4, 16, 32, "resid"), (6, 8, 64, "bf16"), (2, 16, 1024, "f32")])
+def test_conv_groupnorm_side_output(n, H, C, epi):
+    """GroupNorm statistics produced by the conv epilogue == a stand-alone statistics pass over the stored output."""
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn((n, H, H, C), generator=g).to(DEV).to(torch.bfloat16)
+    w = (torch.randn((C, 3, 3, C), generator=g) / math.sqrt(9 * C)).to(DEV).to(torch.bfloat16)
+    bias = torch.randn((C,), generator=g).to(DEV)
+    side = torch.full((n, 32, 3), float("nan"), dtype=torch.float64, device=DEV)
+    alone = torch.empty_like(side)
+    if epi == "bf16":
+        out = torch.empty((n * H * H, C), dtype=torch.bfloat16, device=DEV)
+        ops.conv3x3_bf16(x, w, out, ops.EPI_BF16, bias=bias, gn_sums=side)
+    else:
+        out = torch.empty((n * H * H, C), device=DEV)
+        resid = torch.randn((n * H * H, C), generator=g).to(DEV) if epi == "resid" else None
+        ops.conv3x3_bf16(x, w, out, ops.EPI_RESID_F32 if epi == "resid" else ops.EPI_F32, bias=bias, resid=resid,
+                         gn_sums=side)
+    ops.groupnorm_stats(out, alone, n, H * H, C)
+    k = n * 32 * 2
+    a, b = side.reshape(-1)[:k], alone.reshape(-1)[:k]
+    assert torch.allclose(a, b, rtol=1e-4, atol=1e-2), (a - b).abs().max()
+    fa = side.reshape(-1)[k:].view(torch.float32).reshape(n, 32, 2)
+    fb = alone.reshape(-1)[k:].view(torch.float32).reshape(n, 32, 2)
+    assert torch.allclose(fa, fb, rtol=1e-3, atol=1e-4)
+
+
 def test_gemm_resid_epilogue():
     M, N, K = 640, 576, 2880
     g = torch.Generator().manual_seed(11)
