@@ -249,3 +249,63 @@ def test_uvit3d_pose_rollout_vs_oracle():
         worst = max(worst, (t["model_out"].cpu() - o["model_out"]).abs().max().item())
     assert worst <= STEP_TOL, f"per-step denoiser output max-abs error {worst}"
     assert psnr(out, ref, 1) >= PSNR_MIN
+
+
+def _rollout_vs_oracle(cfg, algo, xs, conds, n_ctx, seed=29):
+    weights = {k[len("diffusion_model.model."):]: v.detach().clone() for k, v in algo.state_dict().items()
+               if k.startswith("diffusion_model.model.")}
+    bank = NoiseBank(seed)
+    oracle, _ = build_oracle(cfg, weights, randn=bank.randn, randn_like=bank.randn_like)
+    oracle.trace = []
+    ref = oracle.predict_videos(xs.clone(), n_ctx, conds)
+    bank2 = NoiseBank(seed)
+    algo = algo.to(DEV).eval()
+    algo.diffusion_model.noise_source = lambda shape, device: bank2.randn(shape).to(device)
+    algo.trace = []
+    out = algo._predict_videos(xs.to(DEV), n_ctx, None if conds is None else conds.to(DEV)).cpu()
+    assert len(algo.trace) == len(oracle.trace)
+    worst = 0.0
+    for t, o in zip(algo.trace, oracle.trace):
+        assert np.array_equal(t["levels_from"], o["levels_from"].numpy())
+        assert np.array_equal(t["levels_to"], o["levels_to"].numpy())
+        worst = max(worst, (t["model_out"].cpu() - o["model_out"]).abs().max().item())
+    assert worst <= STEP_TOL, f"per-step denoiser output max-abs error {worst}"
+    assert psnr(out, ref, n_ctx) >= PSNR_MIN
+    return len(algo.trace)
+
+
+def test_cfg5_shaped_long_context_dit_vs_oracle():
+    """BASELINE configs[4] shape family (DMLab): DiT-B width (768, 12 heads of 64), latents [32,8,8] with patch 2
+    (16 tokens per frame), 36-frame context window, continuous diffusion, action conditioning with mask_first,
+    vanilla history guidance — depth cut to 2 so that the CPU oracle finishes in seconds."""
+    over = {**continuous_overrides(), "backbone.hidden_size": 768, "backbone.depth": 2, "backbone.num_heads": 12,
+            "backbone.spatial_mlp_ratio": 4.0, "x_shape": [32, 8, 8], "max_frames": 36, "n_frames": 36, "context_frames": 4,
+            "external_cond_type": "action", "external_cond_dim": 3, "external_cond_processing": "mask_first",
+            "backbone.external_cond_dropout": 0.1, "diffusion.sampling_timesteps": 4,
+            "tasks.prediction.history_guidance": dict(name="vanilla", guidance_scale=2.0, visualize=False)}
+    cfg = algorithm_cfg(**over)
+    algo = random_weights(cfg, 4)
+    g = torch.Generator().manual_seed(5)
+    xs = torch.randn((2, 36, 32, 8, 8), generator=g)
+    conds = torch.randn((2, 36, 3), generator=g)
+    assert _rollout_vs_oracle(cfg, algo, xs, conds, 4) == 4
+
+
+def test_cfg4_shaped_long_rollout_uvit_vs_oracle():
+    """BASELINE configs[3] structure at reduced size: single image -> 25 frames with a 4-frame U-ViT3DPose window:
+    7 keyframes by two sliding windows under stabilized_vanilla guidance, then rounds of vanilla-guided interpolation
+    in batches of 4 chunks (ragged last batch: 6 = 4 + 2), every window with its own camera-pose cache."""
+    from oracle.cases import synthetic_poses
+    cfg = uvit_cfg((32, 32, 64, 128), 1, 32, 4, **{
+        "n_frames": 25, "tasks.prediction.keyframe_density": 0.28, "tasks.prediction.sliding_context_len": 1,
+        "diffusion.sampling_timesteps": 2,
+        "tasks.prediction.history_guidance": dict(name="stabilized_vanilla", guidance_scale=2.0,
+                                                  stabilization_level=0.02, visualize=False),
+        "tasks.interpolation.history_guidance": dict(name="vanilla", guidance_scale=1.5, visualize=False),
+        "tasks.interpolation.max_batch_size": 4})
+    algo = random_pose_algo(cfg, 6)
+    g = torch.Generator().manual_seed(8)
+    xs = torch.randn((1, 25, 3, 32, 32), generator=g)
+    conds = synthetic_poses(1, 25)
+    steps = _rollout_vs_oracle(cfg, algo, xs, conds, 1)
+    assert steps > 10      # several windows x 2 steps
