@@ -194,6 +194,30 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
   return r;
 }
 
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// 2^x for a pair of fp32 values WITHOUT the MUFU: round-to-nearest split x = j + f (|f| <= 0.5) by the 1.5*2^23 trick,
+// degree-3 minimax polynomial for 2^f (max relative error 7.5e-5, far below the bf16 rounding of P), and the exponent
+// added with integer arithmetic.  All fp32 work is packed f32x2 (FMA pipe); used for a fraction of the scores so that
+// the 16/clk/SM MUFU and the FMA pipe work side by side (the exp2 rate is what bounds head_dim-64 attention).
+__device__ __forceinline__ void ex2_poly_x2(float xa, float xb, float& pa, float& pb) {
+  const uint64_t magic = pack_f32x2(12582912.f, 12582912.f), neg_magic = pack_f32x2(-12582912.f, -12582912.f);
+  const uint64_t x = pack_f32x2(fmaxf(xa, -125.f), fmaxf(xb, -125.f));
+  const uint64_t t = add_f32x2(x, magic);                         // integer part in the low mantissa bits
+  const uint64_t f = fma_f32x2(add_f32x2(t, neg_magic), pack_f32x2(-1.f, -1.f), x);
+  uint64_t p = fma_f32x2(f, pack_f32x2(0.05517168f, 0.05517168f), pack_f32x2(0.24261113f, 0.24261113f));
+  p = fma_f32x2(p, f, pack_f32x2(0.69326097f, 0.69326097f));
+  p = fma_f32x2(p, f, pack_f32x2(0.99992806f, 0.99992806f));
+  float ta, tb, qa, qb;
+  unpack_f32x2(t, ta, tb);
+  unpack_f32x2(p, qa, qb);
+  pa = __int_as_float(__float_as_int(qa) + (__float_as_int(ta) << 23));
+  pb = __int_as_float(__float_as_int(qb) + (__float_as_int(tb) << 23));
+}
+
 // UMMA shared-memory descriptors (cute::UMMA::SmemDescriptor), 128-byte swizzle, version 1.
 //   K-major  operand: 8-row groups 1024 B apart (SBO); LBO unused.
 //   MN-major operand: K rows are 128-byte lines, 8-row groups 1024 B apart (SBO); 64-element MN atoms LBO apart.
@@ -511,6 +535,14 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
   constexpr uint32_t TMEM_S = 0, TMEM_P = SEP_P ? 256 : 0, P_STRIDE = SEP_P ? 64 : 128;
   constexpr uint32_t TMEM_O = SEP_P ? 384 : 256, O_STRIDE = SEP_P ? 64 : 128;
   constexpr float kRescaleThreshold = 8.0f;
+  // which of the 16 score pairs of every 32-score group go through the polynomial exp2 (bit i: iteration i of 8).
+  // Measured on B200 (d = 64, N = 8192): 0 % poly 786 TFLOP/s, 25 % 753, 31 % 774, 37.5 % 746, 50 % 693 — the kernel is
+  // issue/latency-bound before it is MUFU-bound (XU pipe 70 % busy), so extra FMA-pipe instructions do not pay: off.
+#ifndef DFOT_ATTN_POLY_FIRST
+#define DFOT_ATTN_POLY_FIRST 0x00
+#define DFOT_ATTN_POLY_SECOND 0x00
+#endif
+  constexpr uint32_t kPolyFirst = SEP_P ? DFOT_ATTN_POLY_FIRST : 0u, kPolySecond = SEP_P ? DFOT_ATTN_POLY_SECOND : 0u;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
@@ -851,7 +883,10 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
             x0 = __uint_as_float(v[c][2 * e]) - m_used; x1 = __uint_as_float(v[c][2 * e + 1]) - m_used;
             x2 = __uint_as_float(v[c][2 * e + 2]) - m_used; x3 = __uint_as_float(v[c][2 * e + 3]) - m_used;
 #endif
-            const float p0 = ex2(x0), p1 = ex2(x1), p2 = ex2(x2), p3 = ex2(x3);
+            // pairs selected by kPolyFirst / kPolySecond take the FMA-pipe exp2, the others the MUFU
+            float p0, p1, p2, p3;
+            if ((kPolyFirst >> (e >> 1)) & 1) ex2_poly_x2(x0, x1, p0, p1); else { p0 = ex2(x0); p1 = ex2(x1); }
+            if ((kPolySecond >> (e >> 1)) & 1) ex2_poly_x2(x2, x3, p2, p3); else { p2 = ex2(x2); p3 = ex2(x3); }
             sum_a = add_f32x2(sum_a, pack_f32x2(p0, p1));
             sum_b = add_f32x2(sum_b, pack_f32x2(p2, p3));
             pk[e] = pack_bf16x2(p0, p1);

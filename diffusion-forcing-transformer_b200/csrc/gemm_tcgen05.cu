@@ -205,26 +205,93 @@ __device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
   return v;
 }
 
-// Side inputs of one 32x32 chunk, fetched into registers BEFORE the accumulator is touched so that 32 (or 16)
-// independent coalesced loads per lane are in flight at once (the row-wise pass itself is then load-free).
-// FULL = the chunk lies completely inside the matrix: straight-line code without any predicate.
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// silu(x) = h + h*tanh(h), h = x/2: one MUFU + 2 FP32 ops
+__device__ __forceinline__ float silu_fast2(float x) {
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(h), h);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Phase 2 of the epilogue walks the staged 32x32 fp32 chunk ROW-WISE WITH 128-BIT ACCESSES: a lane owns one 16-byte
+// unit of the staged row per step (4 fp32 outputs = 16 B, or 8 bf16 outputs = 16 B), so a chunk costs 8 (f32) or
+// 4 x 2 (bf16) shared loads and 8 / 4 global stores per lane instead of 32 / 16 scalar ones, and row addresses advance
+// by one 64-bit add per step.  The XOR swizzle (unit j of row r at j ^ (r & 7)) keeps every access at the 4-wavefront
+// minimum.  (At K = 576 the scalar version made the kernel epilogue-bound: 483 instructions per chunk and warp.)
+// Side inputs (residual rows) are fetched BEFORE the accumulator is touched so that 8 independent 16-byte loads per
+// lane are in flight during the TMEM read + transpose.  FULL = chunk completely inside the matrix: no predicates.
+
+// GroupNorm side output (F32 / RESID_F32 / BF16 epilogues).  A lane holds per-column (sum, sum of squares) of its NC
+// adjacent columns over the rows it visited; LPR lanes share a row, lanes with equal (lane % LPR) share columns.  All
+// 32 rows of a chunk belong to one image (rows_per_img % 32 == 0); channels per group is a power of two.
+template <int NC, int LPR>
+__device__ __forceinline__ void gn_flush(const Params& p, int lane, int m0, int col0, const float (&s)[NC],
+                                         const float (&q)[NC], bool col_ok) {
+  const int cpg = p.N / (int)p.e.gn_groups;
+  const int64_t img = m0 / p.e.gn_rows_per_img;
+  double* base = p.e.gn_sums + img * p.e.gn_groups * 2;
+  if (cpg >= NC) {   // all NC columns of the lane lie in one group; cpg / NC lanes share it
+    float ts = 0.f, tq = 0.f;
+    if (col_ok) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) { ts += s[j]; tq += q[j]; }
+    }
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {             // fold the rows
+      ts += __shfl_xor_sync(0xffffffffu, ts, o);
+      tq += __shfl_xor_sync(0xffffffffu, tq, o);
+    }
+    const int lpg = cpg / NC;                         // lanes per group inside the row (power of two, may exceed LPR)
+    for (int o = 1; o < lpg && o < LPR; o <<= 1) {
+      ts += __shfl_xor_sync(0xffffffffu, ts, o);
+      tq += __shfl_xor_sync(0xffffffffu, tq, o);
+    }
+    if (lane < LPR && (lane % (lpg < LPR ? lpg : LPR)) == 0 && col_ok) {
+      atomicAdd(base + (col0 / cpg) * 2, (double)ts);
+      atomicAdd(base + (col0 / cpg) * 2 + 1, (double)tq);
+    }
+  } else {           // several groups inside the lane's columns (tiny channel counts only)
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      float ts = col_ok ? s[j] : 0.f, tq = col_ok ? q[j] : 0.f;
+#pragma unroll
+      for (int o = LPR; o < 32; o <<= 1) {
+        ts += __shfl_xor_sync(0xffffffffu, ts, o);
+        tq += __shfl_xor_sync(0xffffffffu, tq, o);
+      }
+      if (lane < LPR && col_ok) {
+        atomicAdd(base + ((col0 + j) / cpg) * 2, (double)ts);
+        atomicAdd(base + ((col0 + j) / cpg) * 2 + 1, (double)tq);
+      }
+    }
+  }
+}
+
 template <int EPI> struct ChunkSide {
-  float v[32];   // GATE_RESID: residual of (row i, this lane's column);  QKV_ROPE: (cos, sin) of row 2k + (lane>>4)
+  float4 r[8];   // *_RESID_F32: residual of (row 4*it + lane/8, columns 4*(lane%8)..+3), it = 0..7
+  float v[32];   // QKV_ROPE: (cos, sin) of row 2k + (lane>>4) for the lane's rotation pair
 };
 
 template <int EPI, bool FULL>
 __device__ __forceinline__ void prefetch_side(const Params& p, ChunkSide<EPI>& sd, int lane, int m0, int n0) {
   if constexpr (EPI == DFOT_EPI_GATE_RESID_F32 || EPI == DFOT_EPI_RESID_F32) {
-    const int col = n0 + lane;
-    const float* res = p.e.resid + (int64_t)m0 * p.e.ld_resid + col;
+    const int col = n0 + ((lane & 7) << 2), rsub = lane >> 3;
+    const float* res = p.e.resid + (int64_t)(m0 + rsub) * p.e.ld_resid + col;
+    const int64_t step = 4 * p.e.ld_resid;
     if constexpr (FULL) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) sd.v[i] = __ldg(res + (int64_t)i * p.e.ld_resid);
+      for (int it = 0; it < 8; ++it, res += step) sd.r[it] = __ldg(reinterpret_cast<const float4*>(res));
     } else {
       const int rows = p.M - m0;
-      const bool col_ok = col < p.N;
+      const bool col_ok = col < p.N;   // N % 4 == 0: a 16-byte unit is entirely inside or outside
 #pragma unroll
-      for (int i = 0; i < 32; ++i) sd.v[i] = (col_ok && i < rows) ? __ldg(res + (int64_t)i * p.e.ld_resid) : 0.f;
+      for (int it = 0; it < 8; ++it, res += step)
+        sd.r[it] = (col_ok && 4 * it + rsub < rows) ? __ldg(reinterpret_cast<const float4*>(res))
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   } else if constexpr (EPI == DFOT_EPI_QKV_ROPE_BF16) {
     const int col = n0 + ((lane & 15) << 1);
@@ -258,75 +325,111 @@ __device__ __forceinline__ void prefetch_side(const Params& p, ChunkSide<EPI>& s
   }
 }
 
-// GroupNorm side output: a lane holds (sum, sum of squares) of `ncol` adjacent columns starting at `col` over the rows
-// of this chunk (all of one image: rows_per_img % 32 == 0).  Lanes of one group are combined by xor-shuffles
-// (channels per group is a power of two), then one f64 atomic pair per group and chunk goes to the workspace.
-// lane_cols = columns covered by consecutive lanes (1 for the f32 pass, 2 for the bf16 pass, where lanes 16-31 mirror
-// lanes 0-15 on the odd rows).
-__device__ __forceinline__ void gn_flush(const Params& p, int lane, int m0, int col, int lane_cols, float s, float q,
-                                         bool col_ok) {
-  const int cpg = p.N / (int)p.e.gn_groups;
-  if (!col_ok) { s = 0.f; q = 0.f; }
-  if (lane_cols == 2) {   // fold the two row-halves of the warp
-    s += __shfl_xor_sync(0xffffffffu, s, 16);
-    q += __shfl_xor_sync(0xffffffffu, q, 16);
-  }
-  const int lanes_per_group = cpg / lane_cols;   // >= 1 (cpg == 1 is handled by the caller with lane_cols == 1)
-  for (int o = 1; o < lanes_per_group && o < 32; o <<= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    q += __shfl_xor_sync(0xffffffffu, q, o);
-  }
-  const int l = lane_cols == 2 ? (lane & 15) : lane;
-  const bool leader = (l % (lanes_per_group > 32 ? 32 : lanes_per_group)) == 0 && (lane_cols == 1 || lane < 16);
-  if (leader && col_ok) {
-    const int64_t img = m0 / p.e.gn_rows_per_img;
-    double* dst = p.e.gn_sums + (img * p.e.gn_groups + col / cpg) * 2;
-    atomicAdd(dst, (double)s);
-    atomicAdd(dst + 1, (double)q);
-  }
-}
-
-// Phase 2 for fp32 outputs: lane = column, loop over the 32 rows of the chunk.
+// fp32 outputs (F32, RESID_F32, GATE_RESID_F32): lane = (row 4*it + lane/8, columns 4*(lane%8)..+3), 8 steps.
 template <int EPI, bool FULL>
 __device__ __forceinline__ void epilogue_rows_f32(const Params& p, const ChunkSide<EPI>& sd, uint32_t stage, int lane,
                                                   int m0, int n0) {
-  const int col = n0 + lane;
+  const int cq = lane & 7, rsub = lane >> 3;
+  const int col = n0 + (cq << 2);
   const bool col_ok = FULL || col < p.N;
-  const float bias = (p.e.bias != nullptr && col_ok) ? __ldg(p.e.bias + col) : 0.f;
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.e.bias != nullptr && col_ok) bias = __ldg(reinterpret_cast<const float4*>(p.e.bias + col));
   const int rows = FULL ? 32 : p.M - m0;
-  float* out = reinterpret_cast<float*>(p.C) + (int64_t)m0 * p.ldc + col;
-  const uint32_t sbase = stage + (uint32_t)((lane & 3) << 2);
-  float gate0 = 0.f, gate1 = 0.f;
+  float* out = reinterpret_cast<float*>(p.C) + (int64_t)(m0 + rsub) * p.ldc + col;
+  const int64_t step = 4 * p.ldc;
+  float4 gate0 = make_float4(0.f, 0.f, 0.f, 0.f), gate1 = gate0;
   int split = 32;  // rows [0, split) belong to frame f0, the rest to f0 + 1 (tokens_per_frame >= 32, host-checked)
   if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) {
     const int P = (int)p.e.tokens_per_frame;
     const int f0 = m0 / P;
     split = min(32, (f0 + 1) * P - m0);
     if (col_ok) {
-      gate0 = __ldg(p.e.gate + (int64_t)f0 * p.e.ld_gate + col);
-      if (split < 32) gate1 = __ldg(p.e.gate + (int64_t)(f0 + 1) * p.e.ld_gate + col);
+      gate0 = __ldg(reinterpret_cast<const float4*>(p.e.gate + (int64_t)f0 * p.e.ld_gate + col));
+      if (split < 32) gate1 = __ldg(reinterpret_cast<const float4*>(p.e.gate + (int64_t)(f0 + 1) * p.e.ld_gate + col));
     }
   }
   const bool gn = p.e.gn_sums != nullptr;   // warp-uniform
-  float gs = 0.f, gq = 0.f;
+  float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const float acc = lds_f32(sbase + (uint32_t)i * 128u + (uint32_t)((((lane >> 2) ^ (i & 7))) << 4));
-    float y = acc + bias;
-    if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) y = sd.v[i] + (i < split ? gate0 : gate1) * y;
-    if constexpr (EPI == DFOT_EPI_RESID_F32) y = sd.v[i] + y;
+  for (int it = 0; it < 8; ++it, out += step) {
+    const int i = 4 * it + rsub;
+    float4 y = lds_f32x4(stage + (uint32_t)i * 128u + (uint32_t)((cq ^ (i & 7)) << 4));
+    y.x += bias.x; y.y += bias.y; y.z += bias.z; y.w += bias.w;
+    if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) {
+      const float4 g = i < split ? gate0 : gate1;
+      y.x = fmaf(g.x, y.x, sd.r[it].x); y.y = fmaf(g.y, y.y, sd.r[it].y);
+      y.z = fmaf(g.z, y.z, sd.r[it].z); y.w = fmaf(g.w, y.w, sd.r[it].w);
+    }
+    if constexpr (EPI == DFOT_EPI_RESID_F32) {
+      y.x += sd.r[it].x; y.y += sd.r[it].y; y.z += sd.r[it].z; y.w += sd.r[it].w;
+    }
     if (FULL || (col_ok && i < rows)) {
-      out[(int64_t)i * p.ldc] = y;
-      if (gn) { gs += y; gq = fmaf(y, y, gq); }
+      *reinterpret_cast<float4*>(out) = y;
+      if (gn) {
+        gs[0] += y.x; gq[0] = fmaf(y.x, y.x, gq[0]); gs[1] += y.y; gq[1] = fmaf(y.y, y.y, gq[1]);
+        gs[2] += y.z; gq[2] = fmaf(y.z, y.z, gq[2]); gs[3] += y.w; gq[3] = fmaf(y.w, y.w, gq[3]);
+      }
     }
   }
-  if (gn) gn_flush(p, lane, m0, col, 1, gs, gq, col_ok);
+  if (gn) gn_flush<4, 8>(p, lane, m0, col, gs, gq, col_ok);
 }
 
-// Phase 2 for bf16 outputs: a lane owns two adjacent columns (a RoPE pair); lanes 0-15 take row 2k, 16-31 row 2k+1.
+// bf16 outputs without rotation (BF16, GELU_BF16, SILU_BF16): lane = (row 8*it + lane/4, columns 8*(lane%4)..+7), 4 steps.
 template <int EPI, bool FULL>
-__device__ __forceinline__ void epilogue_rows_bf16(const Params& p, const ChunkSide<EPI>& sd, uint32_t stage, int lane,
-                                                   int m0, int n0) {
+__device__ __forceinline__ void epilogue_rows_bf16(const Params& p, uint32_t stage, int lane, int m0, int n0) {
+  const int cq = lane & 3, rsub = lane >> 2;
+  const int col = n0 + (cq << 3);
+  const bool col_ok = FULL || col < p.N;    // N % 8 == 0
+  float b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (p.e.bias != nullptr && col_ok) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.e.bias + col));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.e.bias + col + 4));
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+  }
+  const int rows = FULL ? 32 : p.M - m0;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)(m0 + rsub) * p.ldc + col;
+  const int64_t step = 8 * p.ldc;
+  const bool gn = p.e.gn_sums != nullptr;   // warp-uniform
+  float gs[8], gq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { gs[j] = 0.f; gq[j] = 0.f; }
+#pragma unroll
+  for (int it = 0; it < 4; ++it, out += step) {
+    const int i = 8 * it + rsub;
+    const uint32_t row = stage + (uint32_t)i * 128u;
+    const float4 lo = lds_f32x4(row + (uint32_t)(((2 * cq) ^ (i & 7)) << 4));
+    const float4 hi = lds_f32x4(row + (uint32_t)(((2 * cq + 1) ^ (i & 7)) << 4));
+    float v[8] = {lo.x + b[0], lo.y + b[1], lo.z + b[2], lo.w + b[3], hi.x + b[4], hi.y + b[5], hi.z + b[6], hi.w + b[7]};
+    if constexpr (EPI == DFOT_EPI_GELU_BF16) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = gelu_tanh_fast(v[j]);
+    } else if constexpr (EPI == DFOT_EPI_SILU_BF16) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = silu_fast2(v[j]);
+    }
+    if (FULL || (col_ok && i < rows)) {
+      const uint4 w = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                 pack_bf16x2(v[6], v[7]));
+      *reinterpret_cast<uint4*>(out) = w;
+      if (gn) {   // statistics of the values as stored (bf16-rounded), like a separate pass over the output would see
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 r = unpack_bf16x2(ww[j]);
+          gs[2 * j] += r.x; gq[2 * j] = fmaf(r.x, r.x, gq[2 * j]);
+          gs[2 * j + 1] += r.y; gq[2 * j + 1] = fmaf(r.y, r.y, gq[2 * j + 1]);
+        }
+      }
+    }
+  }
+  if (gn) gn_flush<8, 4>(p, lane, m0, col, gs, gq, col_ok);
+}
+
+// bf16 outputs with RoPE-3D (QKV_ROPE): a lane owns two adjacent columns (a rotation pair); lanes 0-15 take row 2k,
+// lanes 16-31 row 2k+1.
+template <bool FULL>
+__device__ __forceinline__ void epilogue_rows_rope(const Params& p, const ChunkSide<DFOT_EPI_QKV_ROPE_BF16>& sd,
+                                                   uint32_t stage, int lane, int m0, int n0) {
   const int cl = (lane & 15) << 1;
   const int col = n0 + cl;
   const bool col_ok = FULL || col < p.N;  // N is even
@@ -334,10 +437,8 @@ __device__ __forceinline__ void epilogue_rows_bf16(const Params& p, const ChunkS
   if (p.e.bias != nullptr && col_ok) bias = __ldg(reinterpret_cast<const float2*>(p.e.bias + col));
   const int rows = FULL ? 32 : p.M - m0;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)m0 * p.ldc + col;
-  const float qs = (EPI == DFOT_EPI_QKV_ROPE_BF16 && col < (int)p.e.model_dim) ? p.e.q_scale : 1.f;
+  const float qs = col < (int)p.e.model_dim ? p.e.q_scale : 1.f;
   const int half = lane >> 4;
-  const bool gn = p.e.gn_sums != nullptr;   // warp-uniform
-  float gs0 = 0.f, gq0 = 0.f, gs1 = 0.f, gq1 = 0.f;
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     const int i = 2 * k + half;
@@ -345,41 +446,11 @@ __device__ __forceinline__ void epilogue_rows_bf16(const Params& p, const ChunkS
                          (uint32_t)((cl & 3) << 2));
     v.x += bias.x;
     v.y += bias.y;
-    if constexpr (EPI == DFOT_EPI_GELU_BF16) {
-      v.x = gelu_tanh_fast(v.x);
-      v.y = gelu_tanh_fast(v.y);
-    } else if constexpr (EPI == DFOT_EPI_SILU_BF16) {
-      v.x = silu_fast(v.x);
-      v.y = silu_fast(v.y);
-    } else if constexpr (EPI == DFOT_EPI_QKV_ROPE_BF16) {
-      const float c = sd.v[2 * k], sn = sd.v[2 * k + 1];   // (1, 0) on v columns
-      const float x0 = v.x, x1 = v.y;
-      v.x = (x0 * c - x1 * sn) * qs;
-      v.y = (x1 * c + x0 * sn) * qs;
-    }
-    if (FULL || (col_ok && i < rows)) {
-      const uint32_t packed = pack_bf16x2(v.x, v.y);
-      *reinterpret_cast<uint32_t*>(out + (int64_t)i * p.ldc) = packed;
-      if (gn) {   // statistics of the values as stored (bf16-rounded), like a separate pass over the output would see
-        const float2 r = unpack_bf16x2(packed);
-        gs0 += r.x; gq0 = fmaf(r.x, r.x, gq0);
-        gs1 += r.y; gq1 = fmaf(r.y, r.y, gq1);
-      }
-    }
-  }
-  if (gn) {
-    if (p.N / (int)p.e.gn_groups == 1) {   // one channel per group: the two columns of a lane are separate groups
-      gs0 += __shfl_xor_sync(0xffffffffu, gs0, 16); gq0 += __shfl_xor_sync(0xffffffffu, gq0, 16);
-      gs1 += __shfl_xor_sync(0xffffffffu, gs1, 16); gq1 += __shfl_xor_sync(0xffffffffu, gq1, 16);
-      if (lane < 16 && col_ok) {
-        const int64_t img = m0 / p.e.gn_rows_per_img;
-        double* dst = p.e.gn_sums + (img * p.e.gn_groups + col) * 2;
-        atomicAdd(dst, (double)gs0); atomicAdd(dst + 1, (double)gq0);
-        atomicAdd(dst + 2, (double)gs1); atomicAdd(dst + 3, (double)gq1);
-      }
-    } else {
-      gn_flush(p, lane, m0, col, 2, gs0 + gs1, gq0 + gq1, col_ok);
-    }
+    const float c = sd.v[2 * k], sn = sd.v[2 * k + 1];   // (1, 0) on v columns
+    const float x0 = v.x, x1 = v.y;
+    v.x = (x0 * c - x1 * sn) * qs;
+    v.y = (x1 * c + x0 * sn) * qs;
+    if (FULL || (col_ok && i < rows)) *reinterpret_cast<uint32_t*>(out + (int64_t)i * p.ldc) = pack_bf16x2(v.x, v.y);
   }
 }
 
@@ -424,8 +495,10 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, uint32_t t_addr,
   __syncwarp();
   if constexpr (EPI == DFOT_EPI_F32 || EPI == DFOT_EPI_GATE_RESID_F32 || EPI == DFOT_EPI_RESID_F32)
     epilogue_rows_f32<EPI, FULL>(p, side, stage_buf, lane, m0, n0);
+  else if constexpr (EPI == DFOT_EPI_QKV_ROPE_BF16)
+    epilogue_rows_rope<FULL>(p, side, stage_buf, lane, m0, n0);
   else
-    epilogue_rows_bf16<EPI, FULL>(p, side, stage_buf, lane, m0, n0);
+    epilogue_rows_bf16<EPI, FULL>(p, stage_buf, lane, m0, n0);
   __syncwarp();
 }
 
@@ -714,9 +787,18 @@ extern "C" int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
                "gemm: N and ldc must be multiples of 8; got N=%lld ldc=%lld", (long long)N, (long long)ldc);
   DFOT_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0) && ((uintptr_t)Cout % 16 == 0),
                DFOT_ERR_UNSUPPORTED, "gemm: A, W, C must be 16-byte aligned");
+  // the epilogue reads bias / residual / gate and writes the output with 16-byte accesses
+  DFOT_REQUIRE(epi->bias == nullptr || (uintptr_t)epi->bias % 16 == 0, DFOT_ERR_UNSUPPORTED,
+               "gemm: bias must be 16-byte aligned");
   if (epilogue == DFOT_EPI_GATE_RESID_F32)
     DFOT_REQUIRE(epi->resid && epi->gate && epi->tokens_per_frame >= 1 && epi->tokens_per_frame < (1ll << 30),
                  DFOT_ERR_INVALID_ARG, "gemm: GATE_RESID needs resid, gate and tokens_per_frame");
+  if (epilogue == DFOT_EPI_GATE_RESID_F32 && epi->tokens_per_frame >= 32)
+    DFOT_REQUIRE((uintptr_t)epi->gate % 16 == 0 && epi->ld_gate % 4 == 0, DFOT_ERR_UNSUPPORTED,
+                 "gemm: gate must be 16-byte aligned with ld_gate %% 4 == 0");
+  if (epilogue == DFOT_EPI_GATE_RESID_F32 || epilogue == DFOT_EPI_RESID_F32)
+    DFOT_REQUIRE(epi->resid != nullptr && (uintptr_t)epi->resid % 16 == 0 && epi->ld_resid % 4 == 0, DFOT_ERR_UNSUPPORTED,
+                 "gemm: resid must be 16-byte aligned with ld_resid %% 4 == 0");
   if (epilogue == DFOT_EPI_RESID_F32)
     DFOT_REQUIRE(epi->resid != nullptr && epi->ld_resid >= N, DFOT_ERR_INVALID_ARG, "gemm: RESID needs resid");
   if (epilogue == DFOT_EPI_QKV_ROPE_BF16)
@@ -765,7 +847,11 @@ extern "C" int dfot_conv3x3_bf16(const void* x, const void* w, void* out, int64_
                    epilogue == DFOT_EPI_SILU_BF16,
                DFOT_ERR_UNSUPPORTED, "conv3x3: epilogue %d unsupported", epilogue);
   if (epilogue == DFOT_EPI_RESID_F32)
-    DFOT_REQUIRE(epi->resid != nullptr && epi->ld_resid >= Cout, DFOT_ERR_INVALID_ARG, "conv3x3: RESID needs resid");
+    DFOT_REQUIRE(epi->resid != nullptr && epi->ld_resid >= Cout && (uintptr_t)epi->resid % 16 == 0 &&
+                     epi->ld_resid % 4 == 0,
+                 DFOT_ERR_INVALID_ARG, "conv3x3: RESID needs a 16-byte aligned resid with ld_resid %% 4 == 0");
+  DFOT_REQUIRE(epi->bias == nullptr || (uintptr_t)epi->bias % 16 == 0, DFOT_ERR_UNSUPPORTED,
+               "conv3x3: bias must be 16-byte aligned");
   // tile = bw x bh x bn pixels = 128 GEMM rows in (img, y, x) order
   const bool pow2w = (W & (W - 1)) == 0, pow2h = (H & (H - 1)) == 0;
   int64_t bw, bh, bn;

@@ -27,6 +27,13 @@ elif which == "gemm":    # level-3 fused qkv projection: M = 16384 tokens, 1152 
     bias = torch.randn((N,), device=DEV)
     out = torch.empty((M, N), device=DEV, dtype=torch.bfloat16)
     fn = lambda: ops.gemm_bf16(a, w, out, ops.EPI_BF16, bias=bias)
+elif which == "gemm_l2":  # level-2 mlp half of the fused projection: M = 65536 tokens, 576 -> 2304, SiLU, bf16 out
+    M, N, K = 65536, 2304, 576
+    a = torch.randn((M, K), device=DEV).to(torch.bfloat16)
+    w = (torch.randn((N, K), device=DEV) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn((N,), device=DEV)
+    out = torch.empty((M, N), device=DEV, dtype=torch.bfloat16)
+    fn = lambda: ops.gemm_bf16(a, w, out, ops.EPI_SILU_BF16, bias=bias)
 elif which == "gn_silu":  # level-0 GroupNorm + FiLM (per-pixel pose part on half of the rows) + SiLU
     n, HW, C = 64, 16384, 128
     x = torch.randn((n * HW, C), device=DEV).to(torch.bfloat16)

@@ -2,6 +2,10 @@
 set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-run() { local name=$1 to=$2; shift 2; echo "=== $name"; timeout "$to" "$@" > "gpurun_out/$name.log" 2>&1; echo "rc=$?"; tail -n ${TAILN:-3} "gpurun_out/$name.log"; }
-run t_attn_a 300 python -m pytest tests/test_gpu_kernels.py -q -k "attention" --timeout 120
-DFOT_B200_LIB=$PWD/diffusion-forcing-transformer_b200/build/lib_nopack.so run t_attn_b 300 python -m pytest tests/test_gpu_kernels.py -q -k "attention" --timeout 120
+echo "== default (0xB5)"; python -m pytest tests/test_gpu_kernels.py -q -k "attention" --timeout 120 2>&1 | tail -1
+python scripts/bench_kernels.py attn 2>&1 | grep "d=64 N=8192\|d=64 N=1280"
+for v in a c d e; do
+  echo "== variant $v"
+  DFOT_B200_LIB=$PWD/diffusion-forcing-transformer_b200/build/lib_poly_$v.so python -m pytest tests/test_gpu_kernels.py -q -k "attention" --timeout 120 2>&1 | tail -1
+  DFOT_B200_LIB=$PWD/diffusion-forcing-transformer_b200/build/lib_poly_$v.so python scripts/bench_kernels.py attn 2>&1 | grep "d=64 N=8192\|d=64 N=1280"
+done
