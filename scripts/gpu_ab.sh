@@ -2,10 +2,8 @@
 set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-echo "== default (0xB5)"; python -m pytest tests/test_gpu_kernels.py -q -k "attention" --timeout 120 2>&1 | tail -1
-python scripts/bench_kernels.py attn 2>&1 | grep "d=64 N=8192\|d=64 N=1280"
-for v in a c d e; do
-  echo "== variant $v"
-  DFOT_B200_LIB=$PWD/diffusion-forcing-transformer_b200/build/lib_poly_$v.so python -m pytest tests/test_gpu_kernels.py -q -k "attention" --timeout 120 2>&1 | tail -1
-  DFOT_B200_LIB=$PWD/diffusion-forcing-transformer_b200/build/lib_poly_$v.so python scripts/bench_kernels.py attn 2>&1 | grep "d=64 N=8192\|d=64 N=1280"
+for lib in "" "$PWD/diffusion-forcing-transformer_b200/build/lib_direct.so"; do
+  echo "== lib=${lib:-default}"
+  DFOT_B200_LIB=$lib python -m pytest tests/test_gpu_kernels.py -q -k "gemm" --timeout 120 2>&1 | tail -1
+  DFOT_B200_LIB=$lib python scripts/bench_kernels.py uvit_gemm 2>&1 | grep "epi=1\|epi=3\|per forward"
 done
