@@ -173,6 +173,62 @@ class BaseVideoAlgo(nn.Module):
         m = np.arange(height, dtype=np.int64)[:, None]
         return np.clip(sampling_timesteps + lag[None, :] - m, 0, sampling_timesteps)
 
+    # ------------------------------------------------------------------ checkpoint ingestion (:1096-1201)
+    # Same rules as the reference's Lightning hooks, so a reference `.ckpt` (full training state or the lightweight
+    # EMA-only release files such as DFoT_RE10K.ckpt) or a `.safetensors` dump drops in: torch.compile prefixes are
+    # stripped, EMA weights replace the raw ones for inference, only `diffusion_model.model.*` is taken from the file,
+    # and missing keys raise unless `checkpoint.strict` is off.
+    def _should_include_in_checkpoint(self, key: str) -> bool:
+        return key.startswith("diffusion_model.model") or key.startswith("diffusion_model._orig_mod.model")
+
+    def _load_ema_weights_to_state_dict(self, checkpoint: Dict) -> None:
+        if checkpoint.get("pretrained_ema", False) and len(checkpoint.get("optimizer_states", [])) == 0:
+            return   # EMA-only release checkpoint: the state_dict already holds the EMA weights
+        ema_weights = checkpoint["optimizer_states"][0]["ema"]
+        keys = ["diffusion_model." + k for k, _ in self.diffusion_model.named_parameters()]
+        assert len(keys) == len(ema_weights), "Number of original weights and EMA weights do not match."
+        for key, weight in zip(keys, ema_weights):
+            checkpoint["state_dict"][key] = weight
+
+    def on_save_checkpoint(self, checkpoint: Dict) -> None:
+        state_dict = checkpoint["state_dict"]
+        for key in list(state_dict.keys()):
+            if not self._should_include_in_checkpoint(key):
+                del state_dict[key]
+
+    def on_load_checkpoint(self, checkpoint: Dict) -> None:
+        sd = checkpoint["state_dict"]
+        # a checkpoint written by a torch.compile'd reference model carries `_orig_mod.` in its keys (:1099-1113)
+        checkpoint["state_dict"] = sd = {k.replace("diffusion_model._orig_mod.", "diffusion_model."): v for k, v in sd.items()}
+        if "optimizer_states" in checkpoint and (len(checkpoint["optimizer_states"]) > 0 or
+                                                 not checkpoint.get("pretrained_ema", False)):
+            if len(checkpoint["optimizer_states"]) > 0 and "ema" in checkpoint["optimizer_states"][0]:
+                self._load_ema_weights_to_state_dict(checkpoint)
+        new_sd = {}
+        own = self.state_dict()
+        for key, value in own.items():
+            new_sd[key] = sd[key] if self._should_include_in_checkpoint(key) and key in sd else value
+        self.ckpt_ignored_keys = [k for k in sd if not self._should_include_in_checkpoint(k)]
+        self.ckpt_missing_keys = [k for k in own if self._should_include_in_checkpoint(k) and k not in sd]
+        if self.ckpt_missing_keys and self.cfg.checkpoint.strict:
+            raise ValueError(f"The following keys are not found in the checkpoint: {self.ckpt_missing_keys}. Thus, the "
+                             "checkpoint cannot be loaded. To ignore this error, turn off strict checkpoint loading by "
+                             "setting `algorithm.checkpoint.strict=False`.")
+        checkpoint["state_dict"] = new_sd
+
+    def load_checkpoint(self, path: str) -> None:
+        """Load model weights from a reference checkpoint file (`.ckpt` Lightning / Accelerate dict or `.safetensors`,
+        experiments/simple_video_generation.py:602-629) through the hooks above."""
+        if path.endswith(".safetensors"):
+            from safetensors.torch import load_file
+            checkpoint = {"state_dict": load_file(path), "pretrained_ema": True, "optimizer_states": []}
+        else:
+            checkpoint = torch.load(path, map_location="cpu", weights_only=False)
+            if "state_dict" not in checkpoint:
+                checkpoint = {"state_dict": checkpoint, "pretrained_ema": True, "optimizer_states": []}
+        self.on_load_checkpoint(checkpoint)
+        self.load_state_dict(checkpoint["state_dict"], strict=True)
+
     # ------------------------------------------------------------------ frames vs tokens (:986-1033)
     def _n_frames_to_n_tokens(self, n_frames: int) -> int:
         return (n_frames - 1) // self.temporal_downsampling_factor + 1
