@@ -7,7 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DFOT_B200_LIB") or os.path.join(HERE, "libdfot_b200.so")   # env: A/B builds of the kernels
 
 F32, BF16, I64 = 0, 1, 2
-EPI_F32, EPI_BF16, EPI_GELU_BF16, EPI_SILU_BF16, EPI_GATE_RESID_F32, EPI_QKV_ROPE_BF16, EPI_RESID_F32 = range(7)
+EPI_F32, EPI_BF16, EPI_GELU_BF16, EPI_SILU_BF16, EPI_GATE_RESID_F32, EPI_QKV_ROPE_BF16, EPI_RESID_F32, \
+    EPI_QKNORM_ROPE_BF16 = range(8)
 
 SYMBOLS = [
     "dfot_abi_version", "dfot_last_error", "dfot_launch_count", "dfot_sampler_step_hg", "dfot_adaln_layernorm",
@@ -31,7 +32,8 @@ class GemmEpilogue(Structure):
     _fields_ = [("bias", c_void_p), ("resid", c_void_p), ("ld_resid", c_int64), ("gate", c_void_p),
                 ("ld_gate", c_int64), ("tokens_per_frame", c_int64), ("rope_cs", c_void_p),
                 ("tokens_per_sample", c_int64), ("model_dim", c_int64), ("head_dim", c_int64),
-                ("q_scale", c_float), ("gn_sums", c_void_p), ("gn_rows_per_img", c_int64), ("gn_groups", c_int64),
+                ("q_scale", c_float), ("qn_w", c_void_p), ("kn_w", c_void_p), ("qk_eps", c_float),
+                ("gn_sums", c_void_p), ("gn_rows_per_img", c_int64), ("gn_groups", c_int64),
                 ("gn_eps", c_float)]
 
 

@@ -491,10 +491,11 @@ class UViT3DPose(nn.Module):
                     dh = ch // self.num_heads
                     Ntok = T * HW
                     ops.rmsnorm_film_bf16(src, bw["norm_w"], mod, sc, sh, HW, w["a16"], mod_pix=cache, img_map=img_map)
-                    ops.gemm_bf16(w["a16"], bw["qkv_w"], w["qkv"], ops.EPI_BF16, bias=bw["qkv_b"])
+                    # q/k RMSNorm(head_dim) + RoPE-3D + softmax scale ride on the QKV GEMM's epilogue (fp32 accumulators)
+                    ops.gemm_bf16(w["a16"], bw["qkv_w"], w["qkv"], ops.EPI_QKNORM_ROPE_BF16, bias=bw["qkv_b"],
+                                  rope_cs=Pk["rope"][i], tokens_per_sample=Ntok, model_dim=ch, head_dim=dh,
+                                  q_scale=LOG2E / math.sqrt(dh), qn_w=bw["qn_w"], kn_w=bw["kn_w"])
                     ops.gemm_bf16(w["a16"], bw["mlp_w"], w["cat"][:, ch:], ops.EPI_SILU_BF16, bias=bw["mlp_b"])
-                    ops.qk_norm_rope(w["qkv"], bw["qn_w"], bw["kn_w"], Pk["rope"][i], Ntok, self.num_heads, dh,
-                                     LOG2E / math.sqrt(dh))
                     ops.attention(w["qkv"], w["cat"][:, :ch], R, Ntok, self.num_heads, dh)
                     ops.gemm_bf16(w["cat"], bw["out_w"], dst, ops.EPI_RESID_F32, bias=bw["out_b"], resid=src)
                 src = dst

@@ -155,6 +155,20 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_x32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_all() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // K-major operand tile in shared memory, 128-byte swizzle: rows are 128 B apart, 8-row groups 1024 B apart.
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64))
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
@@ -454,6 +468,89 @@ __device__ __forceinline__ void epilogue_rows_rope(const Params& p, const ChunkS
   }
 }
 
+// QKNORM_ROPE: one HEAD (DH = 64 or 128 columns) of the lane-quarter's 32 rows.  Thread = row while the accumulators are in
+// registers, so bias, the head's sum of squares and 1/rms are thread-local (no shuffles, fp32 accumulators); the
+// normalised values then go through the usual swizzled transpose, and the row-wise pass applies the per-column norm
+// weight and the RoPE-3D rotation (a lane's 8 columns = 4 rotation pairs) before the 16-byte bf16 stores.
+template <int DH, bool FULL>
+__device__ __forceinline__ void epilogue_head_qknorm(const Params& p, uint32_t t_addr, uint32_t stage, int lane, int m0,
+                                                     int n0) {
+  constexpr int NCH = DH / 32;
+  const int which = n0 / (int)p.e.model_dim;            // 0 = q, 1 = k, 2 = v (heads never straddle: model_dim % DH == 0)
+  // pass 1: the head's sum of squares (accumulators + bias), 32 columns at a time — TMEM reads are cheap, registers
+  // are not (a 128-wide head would need 128 live accumulators)
+  float ss = 0.f;
+  if (which < 2) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      uint32_t r[32];
+      tmem_ld_x32(t_addr + 32 * c, r);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.e.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.e.bias + n0 + 32 * c + j));   // warp-uniform
+        const float v0 = __uint_as_float(r[j]) + b.x, v1 = __uint_as_float(r[j + 1]) + b.y;
+        const float v2 = __uint_as_float(r[j + 2]) + b.z, v3 = __uint_as_float(r[j + 3]) + b.w;
+        ss = fmaf(v0, v0, ss); ss = fmaf(v1, v1, ss); ss = fmaf(v2, v2, ss); ss = fmaf(v3, v3, ss);
+      }
+    }
+  }
+  const float rstd = which < 2 ? rsqrtf(ss / (float)DH + p.e.qk_eps) * (which == 0 ? p.e.q_scale : 1.f) : 1.f;
+  const float* wn = which == 0 ? p.e.qn_w : p.e.kn_w;
+  const int cq = lane & 3, rsub = lane >> 2;
+  const int tps = (int)p.e.tokens_per_sample;
+  const int rows = FULL ? 32 : p.M - m0;
+  // pass 2: (accumulator + bias) * rstd → transpose → weight, RoPE, bf16
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t r[32];
+    tmem_ld_x32(t_addr + 32 * c, r);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.e.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.e.bias + n0 + 32 * c + j));
+      r[j] = __float_as_uint((__uint_as_float(r[j]) + b.x) * rstd);
+      r[j + 1] = __float_as_uint((__uint_as_float(r[j + 1]) + b.y) * rstd);
+      r[j + 2] = __float_as_uint((__uint_as_float(r[j + 2]) + b.z) * rstd);
+      r[j + 3] = __float_as_uint((__uint_as_float(r[j + 3]) + b.w) * rstd);
+    }
+    stage_chunk(stage, lane, r);
+    __syncwarp();
+    const int hc = 32 * c + 8 * cq;                     // first of the lane's 8 columns inside the head
+    float w[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+    if (which < 2) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wn + hc)), w1 = __ldg(reinterpret_cast<const float4*>(wn + hc + 4));
+      w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
+    }
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)(m0 + rsub) * p.ldc + n0 + hc;
+    const int64_t step = 8 * p.ldc;
+#pragma unroll
+    for (int it = 0; it < 4; ++it, out += step) {
+      const int i = 8 * it + rsub;
+      const uint32_t row = stage + (uint32_t)i * 128u;
+      const float4 lo = lds_f32x4(row + (uint32_t)(((2 * cq) ^ (i & 7)) << 4));
+      const float4 hi = lds_f32x4(row + (uint32_t)(((2 * cq + 1) ^ (i & 7)) << 4));
+      float v[8] = {lo.x * w[0], lo.y * w[1], lo.z * w[2], lo.w * w[3], hi.x * w[4], hi.y * w[5], hi.z * w[6], hi.w * w[7]};
+      if (which < 2 && (FULL || i < rows)) {
+        const int tok = (m0 + i) % tps;
+        const float4* cs = reinterpret_cast<const float4*>(p.e.rope_cs + ((int64_t)tok * (DH / 2) + (hc >> 1)) * 2);
+        const float4 c0 = __ldg(cs), c1 = __ldg(cs + 1);   // (cos, sin) of the lane's 4 pairs
+        const float cs8[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float x0 = v[2 * e], x1 = v[2 * e + 1];
+          v[2 * e] = x0 * cs8[2 * e] - x1 * cs8[2 * e + 1];
+          v[2 * e + 1] = x1 * cs8[2 * e] + x0 * cs8[2 * e + 1];
+        }
+      }
+      if (FULL || i < rows)
+        *reinterpret_cast<uint4*>(out) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                    pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+    __syncwarp();
+  }
+}
+
 // GATE_RESID with fewer than 32 tokens per frame (small latent grids, e.g. 8x8 latents with patch 2): a chunk spans
 // several frames, so the gate is looked up per row.  Not a performance path (tiny models), kept simple.
 __device__ __noinline__ void epilogue_rows_gate_small_frames(const Params& p, uint32_t stage, int lane, int m0, int n0) {
@@ -635,14 +732,32 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       tc_fence_after();
       const int m0 = m_blk * BM + q * 32;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      if constexpr (EPI == DFOT_EPI_QKNORM_ROPE_BF16) {
+        // head-wise: the two warps of a lane quarter alternate over the heads of the 256-column tile
+        const int dh = (int)p.e.head_dim;               // 64 or 128 (host-checked), N % dh == 0
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
-        const int n0 = n_blk * BN + c * 32;
-        if (n0 >= p.N || m0 >= p.M) break;  // warp-uniform
-        if (m0 + 32 <= p.M && n0 + 32 <= p.N)
-          epilogue_chunk<EPI, true>(p, t_row + (uint32_t)(c * 32), stage_buf, lane, m0, n0);
-        else
-          epilogue_chunk<EPI, false>(p, t_row + (uint32_t)(c * 32), stage_buf, lane, m0, n0);
+        for (int hh = half; hh * dh < BN; hh += 2) {
+          const int n0 = n_blk * BN + hh * dh;
+          if (n0 >= p.N || m0 >= p.M) break;  // warp-uniform
+          const uint32_t ta = t_row + (uint32_t)(hh * dh);
+          if (dh == 64) {
+            if (m0 + 32 <= p.M) epilogue_head_qknorm<64, true>(p, ta, stage_buf, lane, m0, n0);
+            else epilogue_head_qknorm<64, false>(p, ta, stage_buf, lane, m0, n0);
+          } else {
+            if (m0 + 32 <= p.M) epilogue_head_qknorm<128, true>(p, ta, stage_buf, lane, m0, n0);
+            else epilogue_head_qknorm<128, false>(p, ta, stage_buf, lane, m0, n0);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += 2) {
+          const int n0 = n_blk * BN + c * 32;
+          if (n0 >= p.N || m0 >= p.M) break;  // warp-uniform
+          if (m0 + 32 <= p.M && n0 + 32 <= p.N)
+            epilogue_chunk<EPI, true>(p, t_row + (uint32_t)(c * 32), stage_buf, lane, m0, n0);
+          else
+            epilogue_chunk<EPI, false>(p, t_row + (uint32_t)(c * 32), stage_buf, lane, m0, n0);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -763,6 +878,9 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
     case DFOT_EPI_GATE_RESID_F32: return launch<BN, DFOT_EPI_GATE_RESID_F32>(ta, tb, p, s);
     case DFOT_EPI_QKV_ROPE_BF16: return launch<BN, DFOT_EPI_QKV_ROPE_BF16>(ta, tb, p, s);
     case DFOT_EPI_RESID_F32: return launch<BN, DFOT_EPI_RESID_F32>(ta, tb, p, s);
+    case DFOT_EPI_QKNORM_ROPE_BF16:
+      if constexpr (BN == 256) return launch<256, DFOT_EPI_QKNORM_ROPE_BF16>(ta, tb, p, s);
+      break;
   }
   set_error("gemm: unknown epilogue %d", epi);
   return DFOT_ERR_INVALID_ARG;
@@ -801,6 +919,13 @@ extern "C" int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
                  "gemm: resid must be 16-byte aligned with ld_resid %% 4 == 0");
   if (epilogue == DFOT_EPI_RESID_F32)
     DFOT_REQUIRE(epi->resid != nullptr && epi->ld_resid >= N, DFOT_ERR_INVALID_ARG, "gemm: RESID needs resid");
+  if (epilogue == DFOT_EPI_QKNORM_ROPE_BF16)
+    DFOT_REQUIRE(epi->rope_cs && epi->qn_w && epi->kn_w && epi->tokens_per_sample > 0 &&
+                     (epi->head_dim == 64 || epi->head_dim == 128) && epi->model_dim % epi->head_dim == 0 &&
+                     N == 3 * epi->model_dim && N > 128 && (uintptr_t)epi->rope_cs % 16 == 0 &&
+                     (uintptr_t)epi->qn_w % 16 == 0 && (uintptr_t)epi->kn_w % 16 == 0,
+                 DFOT_ERR_INVALID_ARG,
+                 "gemm: QKNORM_ROPE needs rope table, q/k norm weights (16-byte aligned), head_dim 64|128, N = 3D > 128");
   if (epilogue == DFOT_EPI_QKV_ROPE_BF16)
     DFOT_REQUIRE(epi->rope_cs && epi->tokens_per_sample > 0 && epi->head_dim > 0 && epi->head_dim % 2 == 0 &&
                      epi->model_dim > 0 && epi->model_dim % epi->head_dim == 0 && N == 3 * epi->model_dim,

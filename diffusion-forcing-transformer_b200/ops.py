@@ -10,7 +10,7 @@ import torch
 
 from . import _abi
 from ._abi import (BF16, EPI_BF16, EPI_F32, EPI_GATE_RESID_F32, EPI_GELU_BF16, EPI_QKV_ROPE_BF16,  # noqa: F401
-                   EPI_RESID_F32, EPI_SILU_BF16, F32, I64)
+                   EPI_QKNORM_ROPE_BF16, EPI_RESID_F32, EPI_SILU_BF16, F32, I64)
 
 _DTYPE_TAG = {torch.float32: F32, torch.bfloat16: BF16, torch.int64: I64}
 
@@ -104,7 +104,7 @@ def _gn_side_output(e, gn_sums, gn_rows_per_img, gn_groups, gn_eps, M, N):
 
 def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, gate=None, ld_gate=0, tokens_per_frame=1, rope_cs=None,
               tokens_per_sample=1, model_dim=0, head_dim=0, q_scale=1.0, M=None, gn_sums=None, gn_rows_per_img=0,
-              gn_groups=32, gn_eps=1e-6):
+              gn_groups=32, gn_eps=1e-6, qn_w=None, kn_w=None, qk_eps=1e-6):
     """K2. a [M,K] bf16 (row stride may exceed K), w [N,K] bf16, out [M,N] f32|bf16 per epilogue."""
     _need(w, torch.bfloat16, "w")
     if not a.is_cuda or a.dtype != torch.bfloat16 or a.stride(-1) != 1:
@@ -134,6 +134,10 @@ def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, gate=None, ld_gate=0, 
         _need(rope_cs, torch.float32, "rope_cs")
         e.rope_cs = rope_cs.data_ptr()
     e.tokens_per_sample, e.model_dim, e.head_dim, e.q_scale = tokens_per_sample, model_dim, head_dim, q_scale
+    if qn_w is not None:
+        _need(qn_w, torch.float32, "qn_w")
+        _need(kn_w, torch.float32, "kn_w")
+        e.qn_w, e.kn_w, e.qk_eps = qn_w.data_ptr(), kn_w.data_ptr(), qk_eps
     _gn_side_output(e, gn_sums, gn_rows_per_img, gn_groups, gn_eps, M, N)
     rc = _abi.lib().dfot_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
                                    out.stride(0), M, N, K, epilogue, ctypes.byref(e), _stream())

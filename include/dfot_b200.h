@@ -117,6 +117,9 @@ DFOT_API int dfot_adaln_layernorm(const float* x, const float* mod, int64_t mod_
 #define DFOT_EPI_GATE_RESID_F32 4 /* out f32  = resid + gate[f(m), n] * (acc + bias)          */
 #define DFOT_EPI_QKV_ROPE_BF16 5  /* out bf16 = rope3d(acc + bias) on q,k columns; q pre-scaled */
 #define DFOT_EPI_RESID_F32 6      /* out f32  = resid + acc + bias         (U-ViT residual adds) */
+#define DFOT_EPI_QKNORM_ROPE_BF16 7 /* out bf16 = [rope3d(rmsnorm_d(acc + bias) * w_q) * q_scale | rope3d(rmsnorm_d(.) * w_k) | v]:
+                                     q/k RMSNorm over head_dim from the fp32 accumulators, then RoPE-3D
+                                     (u_vit_blocks.py:253-259); N = 3*model_dim, head_dim in {64, 128} */
 
 typedef struct {
   const float* bias;          /* [N] or NULL */
@@ -132,6 +135,10 @@ typedef struct {
   int64_t model_dim;          /* D */
   int64_t head_dim;
   float q_scale;              /* multiplies q after rotation (softmax scale * log2 e) */
+  /* QKNORM_ROPE: RMSNorm weights of q and k over head_dim, eps */
+  const float* qn_w;
+  const float* kn_w;
+  float qk_eps;
   /* optional side output of the F32 / RESID_F32 / BF16 epilogues: GroupNorm statistics of the OUTPUT (as stored),
      so the next GroupNorm needs no extra pass over HBM.  gn_sums: the 3*n_img*groups-double workspace of
      dfot_groupnorm_stats (zeroed, accumulated and finalised to (mean, rstd) by the call); image = m / gn_rows_per_img

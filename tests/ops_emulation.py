@@ -45,7 +45,23 @@ def _epilogue(acc, out, epilogue, bias, resid):
 def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, M=None, **kw):
     assert a.dtype == BF and w.dtype == BF
     M = a.shape[0] if M is None else M
-    _epilogue(a[:M].float() @ w.float().t(), out[:M], epilogue, bias, None if resid is None else resid[:M])
+    acc = a[:M].float() @ w.float().t()
+    if epilogue == ops.EPI_QKNORM_ROPE_BF16:      # q/k RMSNorm(head_dim) * weight, RoPE-3D, q * q_scale; v untouched
+        acc = acc + bias
+        D, dh, tps = kw["model_dim"], kw["head_dim"], kw["tokens_per_sample"]
+        heads = D // dh
+        q, k, v = (acc[:, i * D:(i + 1) * D].reshape(M, heads, dh) for i in range(3))
+        cs = kw["rope_cs"][torch.arange(M) % tps][:, None]
+
+        def f(t, wn, mul):
+            t = t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + kw.get("qk_eps", 1e-6)) * wn
+            x0, x1 = t[..., 0::2], t[..., 1::2]
+            return torch.stack([x0 * cs[..., 0] - x1 * cs[..., 1], x1 * cs[..., 0] + x0 * cs[..., 1]], -1).flatten(-2) * mul
+        res = torch.cat([f(q, kw["qn_w"], kw["q_scale"]).reshape(M, D), f(k, kw["kn_w"], 1.0).reshape(M, D),
+                         v.reshape(M, D)], 1)
+        out[:M].copy_(res.to(out.dtype))
+        return
+    _epilogue(acc, out[:M], epilogue, bias, None if resid is None else resid[:M])
 
 
 def conv3x3_bf16(x, w, out, epilogue, bias=None, resid=None, gn_sums=None, gn_groups=32, gn_eps=1e-6):

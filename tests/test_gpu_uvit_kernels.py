@@ -184,6 +184,36 @@ def test_qk_norm_rope(heads, dh, T, gh):
     assert torch.equal(buf[:, 3 * D:].float(), buf[:, 3 * D:].float())
 
 
+@pytest.mark.parametrize("heads,dh,T,gh,R", [(9, 64, 8, 8, 2), (9, 128, 4, 4, 2), (1, 64, 4, 4, 3), (2, 128, 4, 2, 1),
+                                             (3, 64, 5, 3, 1)])
+def test_gemm_qknorm_rope_epilogue(heads, dh, T, gh, R):
+    """QKV GEMM with fused q/k RMSNorm(head_dim) + RoPE-3D + q scale (incl. a token count that is not a multiple of 32)."""
+    D = heads * dh
+    Ntok = T * gh * gh
+    M = R * Ntok
+    g = torch.Generator().manual_seed(dh + heads + T)
+    a = torch.randn((M, D), generator=g).to(DEV).to(torch.bfloat16)
+    w = (torch.randn((3 * D, D), generator=g) / math.sqrt(D)).to(DEV).to(torch.bfloat16)
+    bias = torch.randn((3 * D,), generator=g).to(DEV)
+    qw, kw = torch.randn((dh,), generator=g).to(DEV), torch.randn((dh,), generator=g).to(DEV)
+    table = rope_cos_sin_table(dh, (T, gh, gh)).to(DEV)
+    scale = 1.4426950408889634 / math.sqrt(dh)
+    buf = torch.full((M, 3 * D), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.gemm_bf16(a, w, buf, ops.EPI_QKNORM_ROPE_BF16, bias=bias, rope_cs=table, tokens_per_sample=Ntok, model_dim=D,
+                  head_dim=dh, q_scale=scale, qn_w=qw, kn_w=kw)
+    acc = a.float() @ w.float().t() + bias
+    q, k, v = acc.reshape(M, 3, heads, dh).unbind(1)
+    rms = lambda t, wn: t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + 1e-6) * wn
+
+    def rope(t):
+        cs = table[torch.arange(M, device=DEV) % Ntok][:, None]
+        x0, x1 = t[..., 0::2], t[..., 1::2]
+        return torch.stack([x0 * cs[..., 0] - x1 * cs[..., 1], x1 * cs[..., 0] + x0 * cs[..., 1]], -1).flatten(-2)
+    ref = torch.stack([rope(rms(q, qw)) * scale, rope(rms(k, kw)), v], 1).reshape(M, 3 * D)
+    assert torch.isfinite(buf.float()).all()
+    assert bf16_close(buf, ref, 1e-2) and rel_err(buf, ref) < 5e-3
+
+
 def test_pool_upsample_sub():
     g = torch.Generator().manual_seed(3)
     n, H, W, C = 3, 16, 32, 64
