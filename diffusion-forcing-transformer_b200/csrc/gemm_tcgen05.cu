@@ -242,47 +242,49 @@ __device__ __forceinline__ float silu_fast2(float x) {
 // GroupNorm side output (F32 / RESID_F32 / BF16 epilogues).  A lane holds per-column (sum, sum of squares) of its NC
 // adjacent columns over the rows it visited; LPR lanes share a row, lanes with equal (lane % LPR) share columns.  All
 // 32 rows of a chunk belong to one image (rows_per_img % 32 == 0); channels per group is a power of two.
-template <int NC, int LPR>
-__device__ __forceinline__ void gn_flush(const Params& p, int lane, int m0, int col0, const float (&s)[NC],
-                                         const float (&q)[NC], bool col_ok) {
-  const int cpg = p.N / (int)p.e.gn_groups;
+// GPL = groups inside a lane's NC columns (1 when a group is at least NC wide).
+template <int NC, int LPR, int GPL>
+__device__ __forceinline__ void gn_flush_impl(const Params& p, int lane, int m0, int col0, int cpg, const float (&s)[NC],
+                                              const float (&q)[NC], bool col_ok) {
+  constexpr int CPL = NC / GPL;                        // columns of one group inside the lane
   const int64_t img = m0 / p.e.gn_rows_per_img;
   double* base = p.e.gn_sums + img * p.e.gn_groups * 2;
-  if (cpg >= NC) {   // all NC columns of the lane lie in one group; cpg / NC lanes share it
+#pragma unroll
+  for (int g = 0; g < GPL; ++g) {
     float ts = 0.f, tq = 0.f;
     if (col_ok) {
 #pragma unroll
-      for (int j = 0; j < NC; ++j) { ts += s[j]; tq += q[j]; }
+      for (int j = 0; j < CPL; ++j) { ts += s[g * CPL + j]; tq += q[g * CPL + j]; }
     }
 #pragma unroll
-    for (int o = LPR; o < 32; o <<= 1) {             // fold the rows
+    for (int o = LPR; o < 32; o <<= 1) {               // fold the rows (lanes with equal lane % LPR share columns)
       ts += __shfl_xor_sync(0xffffffffu, ts, o);
       tq += __shfl_xor_sync(0xffffffffu, tq, o);
     }
-    const int lpg = cpg / NC;                         // lanes per group inside the row (power of two, may exceed LPR)
-    for (int o = 1; o < lpg && o < LPR; o <<= 1) {
-      ts += __shfl_xor_sync(0xffffffffu, ts, o);
-      tq += __shfl_xor_sync(0xffffffffu, tq, o);
-    }
-    if (lane < LPR && (lane % (lpg < LPR ? lpg : LPR)) == 0 && col_ok) {
-      atomicAdd(base + (col0 / cpg) * 2, (double)ts);
-      atomicAdd(base + (col0 / cpg) * 2 + 1, (double)tq);
-    }
-  } else {           // several groups inside the lane's columns (tiny channel counts only)
-#pragma unroll
-    for (int j = 0; j < NC; ++j) {
-      float ts = col_ok ? s[j] : 0.f, tq = col_ok ? q[j] : 0.f;
-#pragma unroll
-      for (int o = LPR; o < 32; o <<= 1) {
+    int lpg = 1;                                       // lanes of the row that share the group (GPL == 1 only)
+    if (GPL == 1) {
+      lpg = cpg / NC;
+      if (lpg > LPR) lpg = LPR;
+      for (int o = 1; o < lpg; o <<= 1) {
         ts += __shfl_xor_sync(0xffffffffu, ts, o);
         tq += __shfl_xor_sync(0xffffffffu, tq, o);
       }
-      if (lane < LPR && col_ok) {
-        atomicAdd(base + ((col0 + j) / cpg) * 2, (double)ts);
-        atomicAdd(base + ((col0 + j) / cpg) * 2 + 1, (double)tq);
-      }
+    }
+    if (lane < LPR && (lane % lpg) == 0 && col_ok) {
+      double* dst = base + ((col0 + g * CPL) / cpg) * 2;
+      atomicAdd(dst, (double)ts);
+      atomicAdd(dst + 1, (double)tq);
     }
   }
+}
+template <int NC, int LPR>
+__device__ __forceinline__ void gn_flush(const Params& p, int lane, int m0, int col0, const float (&s)[NC],
+                                         const float (&q)[NC], bool col_ok) {
+  const int cpg = p.N / (int)p.e.gn_groups;            // power of two (host-checked), warp-uniform
+  if (cpg >= NC) gn_flush_impl<NC, LPR, 1>(p, lane, m0, col0, cpg, s, q, col_ok);
+  else if (2 * cpg == NC) gn_flush_impl<NC, LPR, 2>(p, lane, m0, col0, cpg, s, q, col_ok);
+  else if (4 * cpg == NC) gn_flush_impl<NC, LPR, 4>(p, lane, m0, col0, cpg, s, q, col_ok);
+  else gn_flush_impl<NC, LPR, NC>(p, lane, m0, col0, cpg, s, q, col_ok);       // one channel per group
 }
 
 template <int EPI> struct ChunkSide {
