@@ -392,10 +392,10 @@ def main():
             e1.record()
             recs.append((2.0 * x.shape[0] * x.shape[1] * x.shape[2] * w.shape[0] * 9 * w.shape[3], e0, e1))
 
-        def timed_attn(qkv, out, R, Ntok, heads, head_dim):
+        def timed_attn(qkv, out, R, Ntok, heads, head_dim, **kw):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            ops_attn(qkv, out, R, Ntok, heads, head_dim)
+            ops_attn(qkv, out, R, Ntok, heads, head_dim, **kw)
             e1.record()
             recs_attn.append((4.0 * R * heads * Ntok * Ntok * head_dim, e0, e1))
 

@@ -262,6 +262,10 @@ class UViT3DPose(nn.Module):
                 d.update(norm_w=f32(blk.norm.norm.weight), qkv_w=bf(fw[: 3 * ch]), qkv_b=fb[: 3 * ch].contiguous(),
                          mlp_w=bf(fw[3 * ch:]), mlp_b=fb[3 * ch:].contiguous(), qn_w=f32(blk.q_norm.weight),
                          kn_w=f32(blk.k_norm.weight), out_w=bf(out_w),
+                         # QK-normalised attention has bounded logits: |q.k| * scale * log2e <= sqrt(d) max|w_q| max|w_k| log2e
+                         # (Cauchy-Schwarz on RMS-normalised, RoPE-rotated vectors; 5 % slack for bf16 rounding)
+                         score_bound=1.05 * LOG2E * math.sqrt(ch // self.num_heads) *
+                         float(blk.q_norm.weight.detach().abs().max()) * float(blk.k_norm.weight.detach().abs().max()),
                          out_b=(blk.attn_out.bias.detach().float() + blk.mlp_out[2].bias.detach().float()).contiguous())
             d["emb_w"] = bf(ew)
             mods_w.append(ew)
@@ -504,7 +508,7 @@ class UViT3DPose(nn.Module):
                         ops.qk_norm_rope(w["qkv"], bw["qn_w"], bw["kn_w"], Pk["rope"][i], Ntok, self.num_heads, dh,
                                          LOG2E / math.sqrt(dh))
                     ops.gemm_bf16(w["a16"], bw["mlp_w"], w["cat"][:, ch:], ops.EPI_SILU_BF16, bias=bw["mlp_b"])
-                    ops.attention(w["qkv"], w["cat"][:, :ch], R, Ntok, self.num_heads, dh)
+                    ops.attention(w["qkv"], w["cat"][:, :ch], R, Ntok, self.num_heads, dh, score_bound=bw["score_bound"])
                     ops.gemm_bf16(w["cat"], bw["out_w"], dst, ops.EPI_RESID_F32, bias=bw["out_b"], resid=src)
                 src = dst
             return dst

@@ -144,13 +144,15 @@ def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, gate=None, ld_gate=0, 
     _abi.check(rc, "gemm_bf16")
 
 
-def attention(qkv, out, R, Ntok, heads, head_dim):
-    """K3. qkv [R*Ntok, 3*D] bf16 (q rotated+scaled, k rotated), out [R*Ntok, D] bf16 (row stride may exceed D)."""
+def attention(qkv, out, R, Ntok, heads, head_dim, score_bound=0.0):
+    """K3. qkv [R*Ntok, 3*D] bf16 (q rotated+scaled, k rotated), out [R*Ntok, D] bf16 (row stride may exceed D).
+    score_bound > 0: an upper bound of |q.k| (pre-scaled, log2 units), e.g. from QK-normalisation — lets the kernel drop
+    the running maximum (see include/dfot_b200.h)."""
     _need(qkv, torch.bfloat16, "qkv")
     if not out.is_cuda or out.dtype != torch.bfloat16 or out.stride(-1) != 1 or out.shape[-1] != heads * head_dim:
         raise RuntimeError("dfot_b200: `out` must be a CUDA bf16 [tokens, heads*head_dim] matrix with unit inner stride")
-    rc = _abi.lib().dfot_attention_strided(qkv.data_ptr(), out.data_ptr(), out.stride(0), R, Ntok, heads, head_dim,
-                                           _stream())
+    rc = _abi.lib().dfot_attention_bounded(qkv.data_ptr(), out.data_ptr(), out.stride(0), R, Ntok, heads, head_dim,
+                                           float(score_bound), _stream())
     _abi.check(rc, "attention")
 
 

@@ -178,6 +178,13 @@ DFOT_API int dfot_attention(const void* qkv, void* out, int64_t R, int64_t Ntok,
    the [attention | SiLU(mlp_h)] operand of its fused attn_out + mlp_out GEMM (u_vit_blocks.py:262-271) */
 DFOT_API int dfot_attention_strided(const void* qkv, void* out, int64_t ld_out, int64_t R, int64_t Ntok, int64_t heads,
                            int64_t head_dim, void* stream);
+/* same, for BOUNDED scores: `score_bound` >= |q.k| of the pre-scaled operands (log2 units).  With QK-normalisation
+   (u_vit_blocks.py:253-254) |q.k|*scale*log2e <= sqrt(head_dim)*max|w_q|*max|w_k|*log2e, typically ~12: the softmax
+   then needs no running maximum at all — p = 2^s, out = (sum p v) / (sum p) is the identical function — which removes
+   the max pass, the subtraction and every O rescale from the MUFU-bound inner loop.  0 < score_bound <= 96 selects the
+   bounded path (N > 128); 0 = unknown (online softmax with a running maximum). */
+DFOT_API int dfot_attention_bounded(const void* qkv, void* out, int64_t ld_out, int64_t R, int64_t Ntok, int64_t heads,
+                           int64_t head_dim, float score_bound, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Small glue kernels of the DiT3D backbone (dit3d.py:153-192, embeddings.py:67-153).

@@ -35,6 +35,8 @@ def bench_attn(iters):
         us = timeit(lambda: ops.attention(qkv, out, R, N, heads, dh), iters)
         fl = 4.0 * R * heads * N * N * dh
         print(f"attention R={R} heads={heads} d={dh} N={N}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s")
+        us = timeit(lambda: ops.attention(qkv, out, R, N, heads, dh, score_bound=40.0), iters)
+        print(f"  bounded scores (no running max):        {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s")
 
 
 def bench_gemm(iters):

@@ -129,7 +129,7 @@ def qk_norm_rope(qkv, q_weight, k_weight, rope_cs, tokens_per_sample, heads, hea
     qkv[:, D:2 * D] = f(k, k_weight, 1.0).to(BF)
 
 
-def attention(qkv, out, R, Ntok, heads, head_dim):
+def attention(qkv, out, R, Ntok, heads, head_dim, score_bound=0.0):
     D = heads * head_dim
     q, k, v = qkv.float().reshape(R, Ntok, 3, heads, head_dim).permute(2, 0, 3, 1, 4).unbind(0)
     w = torch.softmax(q @ k.transpose(-1, -2) * math.log(2.0), dim=-1)       # q carries scale * log2(e)

@@ -116,6 +116,31 @@ def test_attention_matches_sdpa(R, heads, dh, N):
     assert rel_err(out, ref) < 1e-2
 
 
+@pytest.mark.parametrize("R,heads,dh,N", [(2, 9, 64, 1024), (1, 9, 128, 512), (2, 3, 64, 200), (1, 2, 128, 129),
+                                          (1, 2, 64, 100), (3, 4, 72, 384)])
+def test_attention_bounded_scores_matches_sdpa(R, heads, dh, N):
+    """QK-normalised operands with a declared score bound: the kernel may drop the running maximum (p = 2^s); the
+    result must still be the softmax attention.  Scores reach the declared bound on the diagonal (q == k direction)."""
+    D = heads * dh
+    g = torch.Generator().manual_seed(N + dh + 1)
+    t = torch.randn((R, N, 3, heads, dh), generator=g)
+    wq, wk = 1.7, 1.3                                               # norm weights
+    scale = math.log2(math.e) / math.sqrt(dh)
+    t[:, :, 1] = t[:, :, 1] / t[:, :, 1].pow(2).mean(-1, keepdim=True).sqrt() * wk
+    t[:, :, 0] = t[:, :, 1] / wk * wq * scale                       # q parallel to its own key: score = the bound
+    t[:, : N // 2, 0] = torch.randn((R, N // 2, heads, dh), generator=g) * scale   # ... for half of the queries
+    bound = 1.05 * math.sqrt(dh) * wq * wk * math.log2(math.e)
+    qkv = t.reshape(R * N, 3 * D).to(DEV).to(torch.bfloat16)
+    q, k, v = qkv.float().reshape(R, N, 3, heads, dh).permute(2, 0, 3, 1, 4).unbind(0)
+    s = q @ k.transpose(-1, -2)
+    assert s.abs().max().item() <= bound
+    ref = (torch.softmax(s * math.log(2.0), dim=-1) @ v).transpose(1, 2).reshape(R * N, D)
+    out = torch.full((R * N, D), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.attention(qkv, out, R, N, heads, dh, score_bound=bound)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() < 3e-2 and rel_err(out, ref) < 1e-2
+
+
 @pytest.mark.parametrize("heads,dh,N", [(3, 64, 2048), (2, 128, 1024), (2, 72, 640)])
 def test_attention_rescale_stress_is_deterministic(heads, dh, N):
     """Large, growing logits force the lazy-rescale path (O tile rescaled in tensor memory) on most KV tiles; repeated
