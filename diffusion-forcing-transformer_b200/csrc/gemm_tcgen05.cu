@@ -28,8 +28,8 @@ template <int BN> struct Cfg {
   static constexpr int kStageBytesA = BM * BK * 2;
   static constexpr int kStageBytesB = BN * BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two >= 32)
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int kTmemCols = BN == 192 ? 512 : 2 * BN;  // two accumulator stages at columns 0 and BN (power of two >= 32)
   static constexpr int kEpiStageBytes = 32 * 32 * 4;  // per epilogue warp: 32 rows x 32 fp32, swizzled
   static constexpr int kSmemBytes =
       kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -870,6 +870,17 @@ static int gn_end(const Params& p, cudaStream_t s) {
   return gn_finalize(p.e.gn_sums, p.M / rpi, G, rpi * (p.N / G), p.e.gn_eps, s);
 }
 
+// Tile width: the widest tile unless 192 columns (3 x 64, a valid UMMA N) leave at least 15 % fewer padded columns —
+// e.g. N = 576 = 3 x 192 instead of 3 x 256 (measured: 225 -> 205 us at K = 2880).  A 10 % saving (N = 1152) does not
+// pay for the narrower tile's worse operand-bandwidth ratio at large K (measured: 103 -> 113 us at K = 4608).
+static int pick_bn(int64_t N, int epilogue) {
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  if (epilogue == DFOT_EPI_QKNORM_ROPE_BF16) return 256;
+  const int64_t pad256 = ceil_div(N, 256) * 256, pad192 = ceil_div(N, 192) * 192;
+  return (pad192 * 100 <= pad256 * 85) ? 192 : 256;
+}
+
 template <int BN>
 static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t s) {
   switch (epi) {
@@ -940,11 +951,14 @@ extern "C" int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   if ((rc = gn_begin(p, epilogue, s))) return rc;
-  // widest tile whose last column block is not mostly padding
-  if (N > 128) {
+  const int bn = pick_bn(N, epilogue);
+  if (bn == 256) {
     rc = make_tmap(&tb, W, N, K, ldw, 256);
     if (!rc) rc = dispatch_epi<256>(epilogue, ta, tb, p, s);
-  } else if (N > 64) {
+  } else if (bn == 192) {
+    rc = make_tmap(&tb, W, N, K, ldw, 192);
+    if (!rc) rc = dispatch_epi<192>(epilogue, ta, tb, p, s);
+  } else if (bn == 128) {
     rc = make_tmap(&tb, W, N, K, ldw, 128);
     if (!rc) rc = dispatch_epi<128>(epilogue, ta, tb, p, s);
   } else {
@@ -1009,7 +1023,7 @@ extern "C" int dfot_conv3x3_bf16(const void* x, const void* w, void* out, int64_
     int rc = make_tmap_nd(&ta, x, 4, gdim, gstr, box);
     if (rc) return rc;
   }
-  const int bnt = Cout > 128 ? 256 : (Cout > 64 ? 128 : 64);
+  const int bnt = pick_bn(Cout, epilogue);
   {
     cuuint64_t gdim[3] = {(cuuint64_t)Cin, 9, (cuuint64_t)Cout};
     cuuint64_t gstr[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)9 * Cin * 2};
@@ -1021,6 +1035,7 @@ extern "C" int dfot_conv3x3_bf16(const void* x, const void* w, void* out, int64_
   int rc = gn_begin(p, epilogue, s);
   if (rc) return rc;
   if (bnt == 256) rc = dispatch_epi<256>(epilogue, ta, tb, p, s);
+  else if (bnt == 192) rc = dispatch_epi<192>(epilogue, ta, tb, p, s);
   else if (bnt == 128) rc = dispatch_epi<128>(epilogue, ta, tb, p, s);
   else rc = dispatch_epi<64>(epilogue, ta, tb, p, s);
   return rc ? rc : gn_end(p, s);
