@@ -114,6 +114,62 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: the TMA of either CTA signals the LEADER CTA's mbarrier (peer bit cleared) ----
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the same-offset mbarrier of BOTH CTAs of the pair once all previously issued MMAs have completed
+__device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {   // arrive on the leader CTA's copy of `bar`
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tmem2_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem2_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -775,6 +831,175 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   }
 }
 
+// ------------------------------------------------------------------ the CTA-pair kernel (cta_group::2)
+// Two CTAs of a cluster (the two SMs of a TPC) compute one 256 x 256 tile: CTA r holds rows [128r, 128r+128) of A and of
+// the accumulator, and HALF of the B tile (rows [128r, 128r+128) of the 256 output columns); the MMA — issued by the
+// leader CTA only, UMMA M = 256 — reads the other half from the peer's shared memory.  Per k-block every SM now moves
+// 32 KB (16 A + 16 B) through L2 / TMA / its shared-memory port instead of 48 KB for the same 128 x 256 x 64 of MMA work:
+// the operand traffic that caps the single-CTA kernel near 2/3 of the tensor rate drops by a third, and the ring gets
+// six stages.  Barriers: every TMA (both CTAs) completes on the LEADER's full barrier; the MMA's commits are multicast
+// to both CTAs' empty / tmem_full barriers; both CTAs' epilogue warps arrive on the LEADER's tmem_empty barrier.
+struct Cfg2 {
+  static constexpr int BN = 256;
+  static constexpr int kStageBytesA = BM * BK * 2;          // this CTA's 128 rows of A
+  static constexpr int kStageBytesB = (BN / 2) * BK * 2;    // this CTA's half of the B tile
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kStages = 6;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kEpiStageBytes = 32 * 32 * 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024 + 256;
+};
+__device__ __forceinline__ constexpr uint32_t make_idesc_pair() {   // M = 256 (pair), N = 256
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                          const Params p) {
+  using C = Cfg2;
+  constexpr int BN = C::BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + C::kStages * C::kStageBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C::kStages + s); };
+  auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * C::kStages + a); };
+  auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * C::kStages + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * C::kStages + 4);
+  const uint32_t epi_stage0 = bars + 256u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();              // 0 = leader
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_m = (p.M + 2 * BM - 1) / (2 * BM), num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = p.conv_cblks > 0 ? 9 * p.conv_cblks : (p.K + BK - 1) / BK;
+  auto tile_coord = [&](int tile, int& m_blk, int& n_blk) {   // banded rasterisation (bands of 8 pair-rows = 2048 rows)
+    constexpr int kBand = kRasterBand / 2;
+    const int band_tiles = kBand * num_n;
+    const int band = tile / band_tiles, in_band = tile - band * band_tiles;
+    const int band_m0 = band * kBand;
+    const int band_h = min(kBand, num_m - band_m0);
+    m_blk = band_m0 + in_band % band_h;
+    n_blk = in_band / band_h;
+  };
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tma_a);
+    prefetch_tmap(&tma_b);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(full_bar(s), 1);                // leader's copy: one expect_tx arrival, bytes of both CTAs
+      mbar_init(empty_bar(s), 1);               // multicast commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);           // multicast commit
+      mbar_init(tmem_empty_bar(a), 2 * kEpiWarps);   // leader's copy: epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem2_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();                            // barriers of both CTAs are initialised before anyone signals them
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs: own A rows, own half of B) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        int m_blk, n_blk;
+        tile_coord(tile, m_blk, n_blk);
+        const int m0 = m_blk * 2 * BM + rank * BM;
+        const int nb0 = n_blk * BN + rank * (BN / 2);
+        const int x0 = m0 % p.conv_W, y0 = (m0 / p.conv_W) % p.conv_H, img0 = m0 / (p.conv_W * p.conv_H);
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::kStageBytes);
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
+          if (p.conv_cblks == 0) {
+            tma2_load_2d(sa, &tma_a, full_bar(stage), kb * BK, m0);
+            tma2_load_2d(sa + C::kStageBytesA, &tma_b, full_bar(stage), kb * BK, nb0);
+          } else {
+            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            tma2_load_4d(sa, &tma_a, full_bar(stage), cb * BK, x0 + dx, y0 + dy, img0);
+            tma2_load_3d(sa + C::kStageBytesA, &tma_b, full_bar(stage), cb * BK, tap, nb0);
+            if (++cb == p.conv_cblks) { cb = 0; ++tap; }
+          }
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_pair();
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);    // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);                 // both CTAs' TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
+          const uint64_t a_desc = make_smem_desc_sw128(sa);
+          const uint64_t b_desc = make_smem_desc_sw128(sa + C::kStageBytesA);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma2_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma2_commit_both(empty_bar(stage));               // ring slot reusable in BOTH CTAs
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma2_commit_both(tmem_full_bar(acc));               // accumulator complete → both epilogues
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs: their own 128 accumulator rows) =====================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const uint32_t stage_buf = epi_stage0 + (uint32_t)(warp - 2) * C::kEpiStageBytes;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      int m_blk, n_blk;
+      tile_coord(tile, m_blk, n_blk);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tc_fence_after();
+      const int m0 = m_blk * 2 * BM + rank * BM + q * 32;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = half; c < BN / 32; c += 2) {
+        const int n0 = n_blk * BN + c * 32;
+        if (n0 >= p.N || m0 >= p.M) break;  // warp-uniform
+        if (m0 + 32 <= p.M && n0 + 32 <= p.N)
+          epilogue_chunk<EPI, true>(p, t_row + (uint32_t)(c * 32), stage_buf, lane, m0, n0);
+        else
+          epilogue_chunk<EPI, false>(p, t_row + (uint32_t)(c * 32), stage_buf, lane, m0, n0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tmem_empty_bar(acc));
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();                            // the peer may still be reading this CTA's shared memory / signalling it
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem2_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -849,6 +1074,51 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   kern<<<grid, kThreads, C::kSmemBytes, s>>>(ta, tb, p);
   DFOT_CHECK_LAUNCH("gemm_bf16_tcgen05");
   return DFOT_OK;
+}
+
+template <int EPI>
+static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t s) {
+  auto kern = gemm2_bf16_tcgen05_kernel<EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::kSmemBytes);
+    DFOT_REQUIRE(e == cudaSuccess, DFOT_ERR_CUDA, "gemm: cannot reserve %d B of shared memory: %s", Cfg2::kSmemBytes,
+                 cudaGetErrorString(e));
+    configured = true;
+  }
+  const int tiles = (int)(ceil_div(p.M, 2 * BM) * ceil_div(p.N, 256));
+  int pairs = num_sms() / 2;
+  if (tiles < pairs) pairs = tiles;
+  kern<<<2 * pairs, kThreads, Cfg2::kSmemBytes, s>>>(ta, tb, p);   // static __cluster_dims__(2, 1, 1)
+  DFOT_CHECK_LAUNCH("gemm2_bf16_tcgen05");
+  return DFOT_OK;
+}
+static int dispatch_pair(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t s) {
+  switch (epi) {
+    case DFOT_EPI_F32: return launch_pair<DFOT_EPI_F32>(ta, tb, p, s);
+    case DFOT_EPI_BF16: return launch_pair<DFOT_EPI_BF16>(ta, tb, p, s);
+    case DFOT_EPI_GELU_BF16: return launch_pair<DFOT_EPI_GELU_BF16>(ta, tb, p, s);
+    case DFOT_EPI_SILU_BF16: return launch_pair<DFOT_EPI_SILU_BF16>(ta, tb, p, s);
+    case DFOT_EPI_GATE_RESID_F32: return launch_pair<DFOT_EPI_GATE_RESID_F32>(ta, tb, p, s);
+    case DFOT_EPI_QKV_ROPE_BF16: return launch_pair<DFOT_EPI_QKV_ROPE_BF16>(ta, tb, p, s);
+    case DFOT_EPI_RESID_F32: return launch_pair<DFOT_EPI_RESID_F32>(ta, tb, p, s);
+  }
+  set_error("gemm: epilogue %d has no CTA-pair kernel", epi);
+  return DFOT_ERR_INVALID_ARG;
+}
+// CTA-pair kernel when there is enough work for every pair and the 256-wide tile wastes little; DFOT_GEMM_PAIR=0|1 pins
+// the choice (benchmarking)
+static bool use_pair(int64_t M, int64_t N, int epilogue) {
+  static int ov = -2;
+  if (ov == -2) {
+    const char* e = getenv("DFOT_GEMM_PAIR");
+    ov = e == nullptr ? -1 : (e[0] == '1' ? 1 : 0);
+  }
+  if (epilogue == DFOT_EPI_QKNORM_ROPE_BF16 || N <= 128) return false;
+  if (ov >= 0) return ov == 1;
+  const int64_t tiles = ceil_div(M, 2 * BM) * ceil_div(N, 256);
+  const int64_t pad256 = ceil_div(N, 256) * 256;
+  return tiles >= num_sms() / 2 && pad256 * 100 <= N * 115;
 }
 
 // GroupNorm side output: validate, zero the workspace before the launch (gn_begin) and finalise after it (gn_end)
@@ -951,6 +1221,11 @@ extern "C" int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   if ((rc = gn_begin(p, epilogue, s))) return rc;
+  if (use_pair(M, N, epilogue)) {
+    rc = make_tmap(&tb, W, N, K, ldw, 128);              // each CTA loads half of the 256-column B tile
+    if (!rc) rc = dispatch_pair(epilogue, ta, tb, p, s);
+    return rc ? rc : gn_end(p, s);
+  }
   const int bn = pick_bn(N, epilogue);
   if (bn == 256) {
     rc = make_tmap(&tb, W, N, K, ldw, 256);
@@ -1023,7 +1298,8 @@ extern "C" int dfot_conv3x3_bf16(const void* x, const void* w, void* out, int64_
     int rc = make_tmap_nd(&ta, x, 4, gdim, gstr, box);
     if (rc) return rc;
   }
-  const int bnt = pick_bn(Cout, epilogue);
+  const bool pair = use_pair(n_img * H * W, Cout, epilogue);
+  const int bnt = pair ? 128 : pick_bn(Cout, epilogue);
   {
     cuuint64_t gdim[3] = {(cuuint64_t)Cin, 9, (cuuint64_t)Cout};
     cuuint64_t gstr[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)9 * Cin * 2};
@@ -1034,7 +1310,8 @@ extern "C" int dfot_conv3x3_bf16(const void* x, const void* w, void* out, int64_
   cudaStream_t s = (cudaStream_t)stream;
   int rc = gn_begin(p, epilogue, s);
   if (rc) return rc;
-  if (bnt == 256) rc = dispatch_epi<256>(epilogue, ta, tb, p, s);
+  if (pair) rc = dispatch_pair(epilogue, ta, tb, p, s);
+  else if (bnt == 256) rc = dispatch_epi<256>(epilogue, ta, tb, p, s);
   else if (bnt == 192) rc = dispatch_epi<192>(epilogue, ta, tb, p, s);
   else if (bnt == 128) rc = dispatch_epi<128>(epilogue, ta, tb, p, s);
   else rc = dispatch_epi<64>(epilogue, ta, tb, p, s);
