@@ -839,26 +839,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
 // the operand traffic that caps the single-CTA kernel near 2/3 of the tensor rate drops by a third, and the ring gets
 // six stages.  Barriers: every TMA (both CTAs) completes on the LEADER's full barrier; the MMA's commits are multicast
 // to both CTAs' empty / tmem_full barriers; both CTAs' epilogue warps arrive on the LEADER's tmem_empty barrier.
-struct Cfg2 {
-  static constexpr int BN = 256;
+template <int BN_> struct Cfg2 {                            // BN_ in {128, 192, 256}: columns of the pair's tile
+  static constexpr int BN = BN_;
   static constexpr int kStageBytesA = BM * BK * 2;          // this CTA's 128 rows of A
   static constexpr int kStageBytesB = (BN / 2) * BK * 2;    // this CTA's half of the B tile
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = 6;
-  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kStages = BN == 256 ? 6 : (BN == 192 ? 6 : 8);
+  static constexpr int kTmemCols = BN == 128 ? 256 : 512;   // two accumulator stages at columns 0 and BN
   static constexpr int kEpiStageBytes = 32 * 32 * 4;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024 + 256;
 };
-__device__ __forceinline__ constexpr uint32_t make_idesc_pair() {   // M = 256 (pair), N = 256
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc_pair() {   // M = 256 (pair), N = BN
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
-template <int EPI>
+template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                           const Params p) {
-  using C = Cfg2;
-  constexpr int BN = C::BN;
+  using C = Cfg2<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + C::kStages * C::kStageBytes;
@@ -937,7 +936,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc_pair();
+      constexpr uint32_t idesc = make_idesc_pair<BN>();
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -977,14 +976,31 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
       tc_fence_after();
       const int m0 = m_blk * 2 * BM + rank * BM + q * 32;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      if constexpr (EPI == DFOT_EPI_QKNORM_ROPE_BF16) {
+        const int dh = (int)p.e.head_dim;               // 64 or 128 (host-checked), N % dh == 0, BN % dh == 0
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
-        const int n0 = n_blk * BN + c * 32;
-        if (n0 >= p.N || m0 >= p.M) break;  // warp-uniform
-        if (m0 + 32 <= p.M && n0 + 32 <= p.N)
-          epilogue_chunk<EPI, true>(p, t_row + (uint32_t)(c * 32), stage_buf, lane, m0, n0);
-        else
-          epilogue_chunk<EPI, false>(p, t_row + (uint32_t)(c * 32), stage_buf, lane, m0, n0);
+        for (int hh = half; hh * dh < BN; hh += 2) {
+          const int n0 = n_blk * BN + hh * dh;
+          if (n0 >= p.N || m0 >= p.M) break;  // warp-uniform
+          const uint32_t ta = t_row + (uint32_t)(hh * dh);
+          if (dh == 64) {
+            if (m0 + 32 <= p.M) epilogue_head_qknorm<64, true>(p, ta, stage_buf, lane, m0, n0);
+            else epilogue_head_qknorm<64, false>(p, ta, stage_buf, lane, m0, n0);
+          } else {
+            if (m0 + 32 <= p.M) epilogue_head_qknorm<128, true>(p, ta, stage_buf, lane, m0, n0);
+            else epilogue_head_qknorm<128, false>(p, ta, stage_buf, lane, m0, n0);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += 2) {
+          const int n0 = n_blk * BN + c * 32;
+          if (n0 >= p.N || m0 >= p.M) break;  // warp-uniform
+          if (m0 + 32 <= p.M && n0 + 32 <= p.N)
+            epilogue_chunk<EPI, true>(p, t_row + (uint32_t)(c * 32), stage_buf, lane, m0, n0);
+          else
+            epilogue_chunk<EPI, false>(p, t_row + (uint32_t)(c * 32), stage_buf, lane, m0, n0);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -1076,49 +1092,64 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   return DFOT_OK;
 }
 
-template <int EPI>
+template <int BN, int EPI>
 static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t s) {
-  auto kern = gemm2_bf16_tcgen05_kernel<EPI>;
+  using C = Cfg2<BN>;
+  auto kern = gemm2_bf16_tcgen05_kernel<BN, EPI>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::kSmemBytes);
-    DFOT_REQUIRE(e == cudaSuccess, DFOT_ERR_CUDA, "gemm: cannot reserve %d B of shared memory: %s", Cfg2::kSmemBytes,
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    DFOT_REQUIRE(e == cudaSuccess, DFOT_ERR_CUDA, "gemm: cannot reserve %d B of shared memory: %s", C::kSmemBytes,
                  cudaGetErrorString(e));
     configured = true;
   }
-  const int tiles = (int)(ceil_div(p.M, 2 * BM) * ceil_div(p.N, 256));
+  const int tiles = (int)(ceil_div(p.M, 2 * BM) * ceil_div(p.N, BN));
   int pairs = num_sms() / 2;
   if (tiles < pairs) pairs = tiles;
-  kern<<<2 * pairs, kThreads, Cfg2::kSmemBytes, s>>>(ta, tb, p);   // static __cluster_dims__(2, 1, 1)
+  kern<<<2 * pairs, kThreads, C::kSmemBytes, s>>>(ta, tb, p);   // static __cluster_dims__(2, 1, 1)
   DFOT_CHECK_LAUNCH("gemm2_bf16_tcgen05");
   return DFOT_OK;
 }
+template <int BN>
 static int dispatch_pair(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t s) {
   switch (epi) {
-    case DFOT_EPI_F32: return launch_pair<DFOT_EPI_F32>(ta, tb, p, s);
-    case DFOT_EPI_BF16: return launch_pair<DFOT_EPI_BF16>(ta, tb, p, s);
-    case DFOT_EPI_GELU_BF16: return launch_pair<DFOT_EPI_GELU_BF16>(ta, tb, p, s);
-    case DFOT_EPI_SILU_BF16: return launch_pair<DFOT_EPI_SILU_BF16>(ta, tb, p, s);
-    case DFOT_EPI_GATE_RESID_F32: return launch_pair<DFOT_EPI_GATE_RESID_F32>(ta, tb, p, s);
-    case DFOT_EPI_QKV_ROPE_BF16: return launch_pair<DFOT_EPI_QKV_ROPE_BF16>(ta, tb, p, s);
-    case DFOT_EPI_RESID_F32: return launch_pair<DFOT_EPI_RESID_F32>(ta, tb, p, s);
+    case DFOT_EPI_F32: return launch_pair<BN, DFOT_EPI_F32>(ta, tb, p, s);
+    case DFOT_EPI_BF16: return launch_pair<BN, DFOT_EPI_BF16>(ta, tb, p, s);
+    case DFOT_EPI_GELU_BF16: return launch_pair<BN, DFOT_EPI_GELU_BF16>(ta, tb, p, s);
+    case DFOT_EPI_SILU_BF16: return launch_pair<BN, DFOT_EPI_SILU_BF16>(ta, tb, p, s);
+    case DFOT_EPI_GATE_RESID_F32: return launch_pair<BN, DFOT_EPI_GATE_RESID_F32>(ta, tb, p, s);
+    case DFOT_EPI_QKV_ROPE_BF16: return launch_pair<BN, DFOT_EPI_QKV_ROPE_BF16>(ta, tb, p, s);
+    case DFOT_EPI_RESID_F32: return launch_pair<BN, DFOT_EPI_RESID_F32>(ta, tb, p, s);
+    case DFOT_EPI_QKNORM_ROPE_BF16:
+      if constexpr (BN == 256) return launch_pair<256, DFOT_EPI_QKNORM_ROPE_BF16>(ta, tb, p, s);
+      break;
   }
-  set_error("gemm: epilogue %d has no CTA-pair kernel", epi);
+  set_error("gemm: epilogue %d has no CTA-pair kernel at this tile width", epi);
   return DFOT_ERR_INVALID_ARG;
 }
-// CTA-pair kernel when there is enough work for every pair and the 256-wide tile wastes little; DFOT_GEMM_PAIR=0|1 pins
-// the choice (benchmarking)
-static bool use_pair(int64_t M, int64_t N, int epilogue) {
+static int dispatch_pair_bn(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t s) {
+  if (bn == 256) return dispatch_pair<256>(epi, ta, tb, p, s);
+  if (bn == 192) return dispatch_pair<192>(epi, ta, tb, p, s);
+  return dispatch_pair<128>(epi, ta, tb, p, s);
+}
+// Tile width of the CTA-pair kernel (0 = use the single-CTA kernel): the width with the fewest padded columns (wider on
+// ties), provided every SM pair gets at least one 256-row tile.  DFOT_GEMM_PAIR=0|1 pins the choice (benchmarking).
+static int pick_pair_bn(int64_t M, int64_t N, int epilogue) {
   static int ov = -2;
   if (ov == -2) {
     const char* e = getenv("DFOT_GEMM_PAIR");
     ov = e == nullptr ? -1 : (e[0] == '1' ? 1 : 0);
   }
-  if (epilogue == DFOT_EPI_QKNORM_ROPE_BF16 || N <= 128) return false;
-  if (ov >= 0) return ov == 1;
-  const int64_t tiles = ceil_div(M, 2 * BM) * ceil_div(N, 256);
-  const int64_t pad256 = ceil_div(N, 256) * 256;
-  return tiles >= num_sms() / 2 && pad256 * 100 <= N * 115;
+  if (ov == 0 || N < 128) return 0;
+  int bn = 256;
+  if (epilogue != DFOT_EPI_QKNORM_ROPE_BF16) {
+    const int64_t pad256 = ceil_div(N, 256) * 256, pad192 = ceil_div(N, 192) * 192, pad128 = ceil_div(N, 128) * 128;
+    if (pad192 * 100 <= pad256 * 85) bn = 192;
+    if (pad128 * 100 <= (bn == 256 ? pad256 : pad192) * 85) bn = 128;
+  }
+  const int64_t tiles = ceil_div(M, 2 * BM) * ceil_div(N, bn);
+  if (ov != 1 && tiles < num_sms() / 2) return 0;
+  return bn;
 }
 
 // GroupNorm side output: validate, zero the workspace before the launch (gn_begin) and finalise after it (gn_end)
@@ -1221,9 +1252,9 @@ extern "C" int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   if ((rc = gn_begin(p, epilogue, s))) return rc;
-  if (use_pair(M, N, epilogue)) {
-    rc = make_tmap(&tb, W, N, K, ldw, 128);              // each CTA loads half of the 256-column B tile
-    if (!rc) rc = dispatch_pair(epilogue, ta, tb, p, s);
+  if (const int pbn = pick_pair_bn(M, N, epilogue)) {
+    rc = make_tmap(&tb, W, N, K, ldw, pbn / 2);          // each CTA loads half of the pair's B tile
+    if (!rc) rc = dispatch_pair_bn(pbn, epilogue, ta, tb, p, s);
     return rc ? rc : gn_end(p, s);
   }
   const int bn = pick_bn(N, epilogue);
@@ -1298,8 +1329,9 @@ extern "C" int dfot_conv3x3_bf16(const void* x, const void* w, void* out, int64_
     int rc = make_tmap_nd(&ta, x, 4, gdim, gstr, box);
     if (rc) return rc;
   }
-  const bool pair = use_pair(n_img * H * W, Cout, epilogue);
-  const int bnt = pair ? 128 : pick_bn(Cout, epilogue);
+  const int pbn = pick_pair_bn(n_img * H * W, Cout, epilogue);
+  const bool pair = pbn != 0;
+  const int bnt = pair ? pbn / 2 : pick_bn(Cout, epilogue);
   {
     cuuint64_t gdim[3] = {(cuuint64_t)Cin, 9, (cuuint64_t)Cout};
     cuuint64_t gstr[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)9 * Cin * 2};
@@ -1310,7 +1342,7 @@ extern "C" int dfot_conv3x3_bf16(const void* x, const void* w, void* out, int64_
   cudaStream_t s = (cudaStream_t)stream;
   int rc = gn_begin(p, epilogue, s);
   if (rc) return rc;
-  if (pair) rc = dispatch_pair(epilogue, ta, tb, p, s);
+  if (pair) rc = dispatch_pair_bn(pbn, epilogue, ta, tb, p, s);
   else if (bnt == 256) rc = dispatch_epi<256>(epilogue, ta, tb, p, s);
   else if (bnt == 192) rc = dispatch_epi<192>(epilogue, ta, tb, p, s);
   else if (bnt == 128) rc = dispatch_epi<128>(epilogue, ta, tb, p, s);
