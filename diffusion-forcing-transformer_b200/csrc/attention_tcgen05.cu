@@ -17,6 +17,8 @@
 // The N x N score matrix never leaves the SM (the reference materialises it in HBM: dit_blocks.py:21-44).
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace dfot {
@@ -207,6 +209,22 @@ __device__ __forceinline__ void ex2_poly_x2(float xa, float xb, float& pa, float
   const uint64_t magic = pack_f32x2(12582912.f, 12582912.f), neg_magic = pack_f32x2(-12582912.f, -12582912.f);
   const uint64_t x = pack_f32x2(fmaxf(xa, -125.f), fmaxf(xb, -125.f));
   const uint64_t t = add_f32x2(x, magic);                         // integer part in the low mantissa bits
+  const uint64_t f = fma_f32x2(add_f32x2(t, neg_magic), pack_f32x2(-1.f, -1.f), x);
+  uint64_t p = fma_f32x2(f, pack_f32x2(0.05517168f, 0.05517168f), pack_f32x2(0.24261113f, 0.24261113f));
+  p = fma_f32x2(p, f, pack_f32x2(0.69326097f, 0.69326097f));
+  p = fma_f32x2(p, f, pack_f32x2(0.99992806f, 0.99992806f));
+  float ta, tb, qa, qb;
+  unpack_f32x2(t, ta, tb);
+  unpack_f32x2(p, qa, qb);
+  pa = __int_as_float(__float_as_int(qa) + (__float_as_int(ta) << 23));
+  pb = __int_as_float(__float_as_int(qb) + (__float_as_int(tb) << 23));
+}
+
+// same for bounded arguments (|x| <= ~100: no clamp needed)
+__device__ __forceinline__ void ex2_poly_x2_bounded(float xa, float xb, float& pa, float& pb) {
+  const uint64_t magic = pack_f32x2(12582912.f, 12582912.f), neg_magic = pack_f32x2(-12582912.f, -12582912.f);
+  const uint64_t x = pack_f32x2(xa, xb);
+  const uint64_t t = add_f32x2(x, magic);
   const uint64_t f = fma_f32x2(add_f32x2(t, neg_magic), pack_f32x2(-1.f, -1.f), x);
   uint64_t p = fma_f32x2(f, pack_f32x2(0.05517168f, 0.05517168f), pack_f32x2(0.24261113f, 0.24261113f));
   p = fma_f32x2(p, f, pack_f32x2(0.69326097f, 0.69326097f));
@@ -545,6 +563,12 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
 #define DFOT_ATTN_POLY_SECOND 0x00
 #endif
   constexpr uint32_t kPolyFirst = SEP_P ? DFOT_ATTN_POLY_FIRST : 0u, kPolySecond = SEP_P ? DFOT_ATTN_POLY_SECOND : 0u;
+  // bounded-score path (2 instead of 3 base instructions per score): polynomial share, see the measurements below
+#ifndef DFOT_ATTN_POLYB_FIRST
+#define DFOT_ATTN_POLYB_FIRST 0x00
+#define DFOT_ATTN_POLYB_SECOND 0xFF
+#endif
+  constexpr uint32_t kPolyFirstB = SEP_P ? DFOT_ATTN_POLYB_FIRST : 0u, kPolySecondB = SEP_P ? DFOT_ATTN_POLYB_SECOND : 0u;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
@@ -882,40 +906,38 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
           // Bounded scores: p = 2^s directly (reference maximum 0 for every row and tile) — no row maximum, no
           // subtraction, no O rescaling; everything else (P in TMEM, PV, row sums) is unchanged.
           uint64_t sum_a = 0ull, sum_b = 0ull;
+          // half of the score pairs take the FMA-pipe polynomial exp2, the other half the MUFU (measured: 832 -> 930
+          // TFLOP/s at d = 64, N = 8192).  A partial last tile carries -inf masks the polynomial cannot take: MUFU only.
+          auto exp_tile = [&](auto poly_tag) {
+            constexpr bool POLY = decltype(poly_tag)::value;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t pk[16];
+            for (int c = 0; c < 4; ++c) {
+              uint32_t pk[16];
 #pragma unroll
-            for (int e = 0; e < 16; e += 2) {
-              const float p0 = ex2(__uint_as_float(v[c][2 * e])), p1 = ex2(__uint_as_float(v[c][2 * e + 1]));
-              const float p2 = ex2(__uint_as_float(v[c][2 * e + 2])), p3 = ex2(__uint_as_float(v[c][2 * e + 3]));
-              sum_a = add_f32x2(sum_a, pack_f32x2(p0, p1));
-              sum_b = add_f32x2(sum_b, pack_f32x2(p2, p3));
-              pk[e] = pack_bf16x2(p0, p1);
-              pk[e + 1] = pack_bf16x2(p2, p3);
-            }
-            if constexpr (SEP_P) {
-              if (c == 0 && j > 0) {                 // PV_t(j-1) still reads P_t(j-1) from these columns
-                mbar_wait_fast(bar(PV_DONE + t), n_pv++ & 1u);
-                tc_fence_after();
+              for (int e = 0; e < 16; e += 2) {
+                float p0, p1, p2, p3;
+                if (POLY && ((kPolyFirstB >> (e >> 1)) & 1))
+                  ex2_poly_x2_bounded(__uint_as_float(v[c][2 * e]), __uint_as_float(v[c][2 * e + 1]), p0, p1);
+                else { p0 = ex2(__uint_as_float(v[c][2 * e])); p1 = ex2(__uint_as_float(v[c][2 * e + 1])); }
+                if (POLY && ((kPolySecondB >> (e >> 1)) & 1))
+                  ex2_poly_x2_bounded(__uint_as_float(v[c][2 * e + 2]), __uint_as_float(v[c][2 * e + 3]), p2, p3);
+                else { p2 = ex2(__uint_as_float(v[c][2 * e + 2])); p3 = ex2(__uint_as_float(v[c][2 * e + 3])); }
+                sum_a = add_f32x2(sum_a, pack_f32x2(p0, p1));
+                sum_b = add_f32x2(sum_b, pack_f32x2(p2, p3));
+                pk[e] = pack_bf16x2(p0, p1);
+                pk[e + 1] = pack_bf16x2(p2, p3);
               }
-            }
-            tmem_st_x16(t_p + 16 * c, pk);
-            if constexpr (PREFETCH) {
-              if (more) {
-                if (c == 2) {
-                  load_begin();
-                  tmem_ld_x32(t_s, v[0]);
-                  tmem_ld_x32(t_s + 32, v[1]);
-                  tmem_ld_x32(t_s + 64, v[2]);
+              if constexpr (SEP_P) {
+                if (c == 0 && j > 0) {               // PV_t(j-1) still reads P_t(j-1) from these columns
+                  mbar_wait_fast(bar(PV_DONE + t), n_pv++ & 1u);
+                  tc_fence_after();
                 }
-                if (c == 3) tmem_ld_x32(t_s + 96, v[3]);
               }
+              tmem_st_x16(t_p + 16 * c, pk);
             }
-          }
-          if constexpr (PREFETCH) {
-            if (more) mx = load_end(j + 1);
-          }
+          };
+          if (p.Ntok - j * BKV >= BKV) exp_tile(std::true_type{});
+          else exp_tile(std::false_type{});
           float s0, s1, s2, s3;
           unpack_f32x2(sum_a, s0, s1);
           unpack_f32x2(sum_b, s2, s3);
