@@ -563,10 +563,15 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
 #define DFOT_ATTN_POLY_SECOND 0x00
 #endif
   constexpr uint32_t kPolyFirst = SEP_P ? DFOT_ATTN_POLY_FIRST : 0u, kPolySecond = SEP_P ? DFOT_ATTN_POLY_SECOND : 0u;
-  // bounded-score path (2 instead of 3 base instructions per score): polynomial share, see the measurements below
+  // bounded-score path (2 instead of 3 base instructions per score): polynomial share of the score pairs.  Measured
+  // on B200 (d = 64, N = 8192, R = 8; run-to-run spread of one box ~3 %): 0 % 824, 12.5 % 853, 19 % 874, 25 % 884-918,
+  // 31 % 857, 37.5 % 886, 44 % 874, 50 % 864-877, 62.5 % 867, 75 % 813 TFLOP/s — flat between 25 % and 50 %, so the
+  // smaller share is used (fewer FMA-pipe instructions = less power under the cap).  Also measured and dropped: two
+  // softmax warpgroups per query tile, each owning 64 of the 128 score columns (4 warps per scheduler; needs
+  // setmaxnreg 64/104 because a CTA can only re-use registers its own warps released): 845 vs 870 TFLOP/s.
 #ifndef DFOT_ATTN_POLYB_FIRST
 #define DFOT_ATTN_POLYB_FIRST 0x00
-#define DFOT_ATTN_POLYB_SECOND 0xFF
+#define DFOT_ATTN_POLYB_SECOND 0x55
 #endif
   constexpr uint32_t kPolyFirstB = SEP_P ? DFOT_ATTN_POLYB_FIRST : 0u, kPolySecondB = SEP_P ? DFOT_ATTN_POLYB_SECOND : 0u;
 
@@ -906,7 +911,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
           // Bounded scores: p = 2^s directly (reference maximum 0 for every row and tile) — no row maximum, no
           // subtraction, no O rescaling; everything else (P in TMEM, PV, row sums) is unchanged.
           uint64_t sum_a = 0ull, sum_b = 0ull;
-          // half of the score pairs take the FMA-pipe polynomial exp2, the other half the MUFU (measured: 832 -> 930
+          // a quarter of the score pairs take the FMA-pipe polynomial exp2, the rest the MUFU (measured: 824 -> ~900
           // TFLOP/s at d = 64, N = 8192).  A partial last tile carries -inf masks the polynomial cannot take: MUFU only.
           auto exp_tile = [&](auto poly_tag) {
             constexpr bool POLY = decltype(poly_tag)::value;

@@ -133,23 +133,21 @@ gn_silu_kernel(const TX* __restrict__ x, const float2* __restrict__ stats, const
   const TX* xb = x + (int64_t)img * HW * C + c0;
   __nv_bfloat16* yb = y + (int64_t)img * HW * C + c0;
   const __nv_bfloat16* pb = src >= 0 ? mod_pix + (int64_t)src * HW * (2 * C) + c0 : nullptr;
-  // kGnIter groups of kGnPix pixels: the prologue above (≈20 cached loads) is amortised over kGnIter*kGnPix pixels
+  // kGnIter groups of kGnPix pixels: the prologue above (≈20 cached loads) is amortised over kGnIter*kGnPix pixels.
+  // Images without a per-pixel part have a third of the loads per pixel, so they walk the same pixels in half as many
+  // groups of 2*kGnPix to keep as many bytes in flight.
+  const int first = blockIdx.x * (kGnIter * kGnPix) * pix_step + prow;
+  if (pb != nullptr) {
 #pragma unroll 1
-  for (int it = 0; it < kGnIter; ++it) {
-    const int pix0 = (blockIdx.x * kGnIter + it) * (pix_step * kGnPix) + prow;
-    if (pix0 >= HW) break;
-    float a[kGnPix][8];
-#pragma unroll
-    for (int k = 0; k < kGnPix; ++k) {
-      const int pix = pix0 + k * pix_step;
-      if (pix < HW) load8(xb + (int64_t)pix * C, a[k]);
-    }
-    if (pb != nullptr) {
-      float ps[kGnPix][8], ph[kGnPix][8];
+    for (int it = 0; it < kGnIter; ++it) {
+      const int pix0 = first + it * (kGnPix * pix_step);
+      if (pix0 >= HW) break;
+      float a[kGnPix][8], ps[kGnPix][8], ph[kGnPix][8];
 #pragma unroll
       for (int k = 0; k < kGnPix; ++k) {
         const int pix = pix0 + k * pix_step;
         if (pix < HW) {
+          load8(xb + (int64_t)pix * C, a[k]);
           load8(pb + (int64_t)pix * (2 * C), ps[k]);
           load8(pb + (int64_t)pix * (2 * C) + C, ph[k]);
         }
@@ -164,9 +162,21 @@ gn_silu_kernel(const TX* __restrict__ x, const float2* __restrict__ stats, const
           store8(yb + (int64_t)pix * C, a[k]);
         }
       }
-    } else {
+    }
+  } else {
+    constexpr int kPix = 2 * kGnPix;
+#pragma unroll 1
+    for (int it = 0; it < kGnIter / 2; ++it) {
+      const int pix0 = first + it * (kPix * pix_step);
+      if (pix0 >= HW) break;
+      float a[kPix][8];
 #pragma unroll
-      for (int k = 0; k < kGnPix; ++k) {
+      for (int k = 0; k < kPix; ++k) {
+        const int pix = pix0 + k * pix_step;
+        if (pix < HW) load8(xb + (int64_t)pix * C, a[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < kPix; ++k) {
         const int pix = pix0 + k * pix_step;
         if (pix < HW) {
 #pragma unroll
@@ -204,13 +214,23 @@ rmsnorm_film_kernel(const float* __restrict__ x, const float* __restrict__ weigh
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+  // the per-pixel FiLM part is a second DRAM stream: issue its loads before the reduction so that both streams of the
+  // token are in flight together (one round trip per token instead of two)
   const int64_t img = m / tokens_per_img, pix = m - img * tokens_per_img;
+  const int32_t src = (mod_pix != nullptr && img_map != nullptr) ? __ldg(img_map + img) : -1;
+  const __nv_bfloat16* prow = src >= 0 ? mod_pix + ((int64_t)src * tokens_per_img + pix) * (2 * D) : nullptr;
+  uint2 ps[NV], ph[NV];
+  if (prow != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) { ps[i] = ld_stream_u2(prow + 4 * c); ph[i] = ld_stream_u2(prow + D + 4 * c); }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
   const float4* sc = reinterpret_cast<const float4*>(mod_img + img * ld_img + scale_col);
   const float4* sh = reinterpret_cast<const float4*>(mod_img + img * ld_img + shift_col);
   const float4* wr = reinterpret_cast<const float4*>(weight);
-  const int32_t src = (mod_pix != nullptr && img_map != nullptr) ? __ldg(img_map + img) : -1;
-  const __nv_bfloat16* prow = src >= 0 ? mod_pix + ((int64_t)src * tokens_per_img + pix) * (2 * D) : nullptr;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = lane + i * 32;
@@ -218,8 +238,7 @@ rmsnorm_film_kernel(const float* __restrict__ x, const float* __restrict__ weigh
       float4 g = __ldg(sc + c), s = __ldg(sh + c);
       const float4 w = __ldg(wr + c);
       if (prow != nullptr) {
-        const uint2 ps = ld_stream_u2(prow + 4 * c), ph = ld_stream_u2(prow + D + 4 * c);
-        const float2 a = unpack_bf16x2(ps.x), b = unpack_bf16x2(ps.y), e = unpack_bf16x2(ph.x), f = unpack_bf16x2(ph.y);
+        const float2 a = unpack_bf16x2(ps[i].x), b = unpack_bf16x2(ps[i].y), e = unpack_bf16x2(ph[i].x), f = unpack_bf16x2(ph[i].y);
         g.x += a.x; g.y += a.y; g.z += b.x; g.w += b.y;
         s.x += e.x; s.y += e.y; s.z += f.x; s.w += f.y;
       }
@@ -234,70 +253,72 @@ rmsnorm_film_kernel(const float* __restrict__ x, const float* __restrict__ weigh
 }
 
 // ------------------------------------------------------------------ q/k RMSNorm(head_dim) + RoPE-3D, in place
-// One warp per token: the q and k segments of all heads (2*heads segments of DH elements) are processed in batches of
-// SEG independent loads so that enough bytes are in flight; a lane owns EPL = DH/32 adjacent elements = EPL/2
-// rotation pairs of every segment, so the RoPE (cos, sin) and norm weights are loaded once per token.
-template <int DH, int SEG>
+// One warp per token.  The q and k columns of a token are one contiguous run of 2*heads*DH bf16, streamed as 16-byte
+// pieces: a lane owns 8 adjacent elements (4 rotation pairs) of one head, LPH = DH/8 lanes share a head and one load
+// instruction covers 32/LPH heads (512 contiguous bytes).  ALL pieces of the token are loaded before the first reduction
+// (NI loads in flight per lane, one DRAM round trip per token); head sums are xor-shuffles inside the LPH-lane group.
+template <int DH, int NI>
 __global__ void __launch_bounds__(kThreads)
 qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, const float* __restrict__ qw,
                     const float* __restrict__ kw, float eps, const float* __restrict__ rope_cs,
                     int64_t tokens_per_sample, int64_t M, int heads, float q_scale) {
-  constexpr int EPL = DH / 32;
+  constexpr int LPH = DH / 8, HPI = 32 / LPH;       // lanes per head, heads per load instruction
   const int lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   if (m >= M) return;
-  __nv_bfloat16* row = qkv + m * ld + lane * EPL;
-  float wq[EPL], wk[EPL];
-  float2 cs[EPL / 2];
+  const int sub = lane % LPH, hsel = lane / LPH;    // position inside the head, head inside the instruction
+  uint4* row = reinterpret_cast<uint4*>(qkv + m * ld) + lane;
+  const int n_seg = 2 * heads;                      // segment s: columns [s*DH, (s+1)*DH); s < heads → q, else k
+  uint4 raw[NI];
+#pragma unroll
+  for (int i = 0; i < NI; ++i)
+    if (i * HPI + hsel < n_seg) raw[i] = *(row + i * 32);
+  float wq[8], wk[8];
+  float2 cs[4];
   const int64_t tok = m % tokens_per_sample;
+  ldg8(qw + sub * 8, wq);
+  ldg8(kw + sub * 8, wk);
 #pragma unroll
-  for (int j = 0; j < EPL; ++j) { wq[j] = __ldg(qw + lane * EPL + j) * q_scale; wk[j] = __ldg(kw + lane * EPL + j); }
+  for (int j = 0; j < 8; ++j) wq[j] *= q_scale;
+  {
+    const float4* c4 = reinterpret_cast<const float4*>(rope_cs + (tok * (DH / 2) + sub * 4) * 2);
+    const float4 a = __ldg(c4), b = __ldg(c4 + 1);
+    cs[0] = make_float2(a.x, a.y); cs[1] = make_float2(a.z, a.w);
+    cs[2] = make_float2(b.x, b.y); cs[3] = make_float2(b.z, b.w);
+  }
+  float sq[NI];             // the raw bf16 pieces stay in registers; they are unpacked twice rather than kept as f32
 #pragma unroll
-  for (int j = 0; j < EPL / 2; ++j) cs[j] = __ldg(reinterpret_cast<const float2*>(rope_cs) + tok * (DH / 2) + lane * (EPL / 2) + j);
-  const int n_seg = 2 * heads;                    // segment s: columns [s*DH, (s+1)*DH); s < heads → q, else k
-  for (int s0 = 0; s0 < n_seg; s0 += SEG) {
-    float e[SEG][EPL];
-    float sq[SEG];
+  for (int i = 0; i < NI; ++i) {
+    sq[i] = 0.f;
+    if (i * HPI + hsel < n_seg) {
+      const uint32_t u[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
 #pragma unroll
-    for (int i = 0; i < SEG; ++i) {
-      if (s0 + i < n_seg) {
-        if constexpr (EPL == 2) {
-          const float2 t = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row + (s0 + i) * DH));
-          e[i][0] = t.x; e[i][1] = t.y;
-        } else {
-          const uint2 u = *reinterpret_cast<const uint2*>(row + (s0 + i) * DH);
-          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-          e[i][0] = a.x; e[i][1] = a.y; e[i][2] = b.x; e[i][3] = b.y;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < EPL; ++j) e[i][j] = 0.f;
-      }
-      sq[i] = 0.f;
-#pragma unroll
-      for (int j = 0; j < EPL; ++j) sq[i] = fmaf(e[i][j], e[i][j], sq[i]);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-      for (int i = 0; i < SEG; ++i) sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
-#pragma unroll
-    for (int i = 0; i < SEG; ++i) {
-      if (s0 + i >= n_seg) continue;
-      const float rstd = rsqrtf(sq[i] / (float)DH + eps);
-      const bool is_q = s0 + i < heads;
-#pragma unroll
-      for (int j = 0; j < EPL; j += 2) {
-        const float x0 = e[i][j] * rstd * (is_q ? wq[j] : wk[j]), x1 = e[i][j + 1] * rstd * (is_q ? wq[j + 1] : wk[j + 1]);
-        e[i][j] = x0 * cs[j / 2].x - x1 * cs[j / 2].y;
-        e[i][j + 1] = x1 * cs[j / 2].x + x0 * cs[j / 2].y;
-      }
-      if constexpr (EPL == 2) {
-        *reinterpret_cast<uint32_t*>(row + (s0 + i) * DH) = pack_bf16x2(e[i][0], e[i][1]);
-      } else {
-        *reinterpret_cast<uint2*>(row + (s0 + i) * DH) = make_uint2(pack_bf16x2(e[i][0], e[i][1]), pack_bf16x2(e[i][2], e[i][3]));
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = unpack_bf16x2(u[j]);
+        sq[i] = fmaf(t.x, t.x, fmaf(t.y, t.y, sq[i]));
       }
     }
+  }
+#pragma unroll
+  for (int o = LPH / 2; o > 0; o >>= 1)
+#pragma unroll
+    for (int i = 0; i < NI; ++i) sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int seg = i * HPI + hsel;
+    if (seg >= n_seg) continue;
+    const float rstd = rsqrtf(sq[i] / (float)DH + eps);
+    const bool is_q = seg < heads;
+    const uint32_t u[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = unpack_bf16x2(u[j]);
+      const float x0 = t.x * rstd * (is_q ? wq[2 * j] : wk[2 * j]);
+      const float x1 = t.y * rstd * (is_q ? wq[2 * j + 1] : wk[2 * j + 1]);
+      o[j] = pack_bf16x2(x0 * cs[j].x - x1 * cs[j].y, x1 * cs[j].x + x0 * cs[j].y);
+    }
+    *(row + i * 32) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -503,16 +524,30 @@ extern "C" int dfot_qk_norm_rope(void* qkv, int64_t ld, const float* q_weight, c
   DFOT_REQUIRE(qkv && q_weight && k_weight && rope_cs && M > 0 && heads > 0 && tokens_per_sample > 0,
                DFOT_ERR_INVALID_ARG, "qk_norm_rope: bad arguments");
   DFOT_REQUIRE(head_dim == 64 || head_dim == 128, DFOT_ERR_UNSUPPORTED, "qk_norm_rope: head_dim must be 64 or 128");
-  DFOT_REQUIRE(ld % 4 == 0 && ld >= 3 * heads * head_dim && (uintptr_t)qkv % 8 == 0, DFOT_ERR_UNSUPPORTED,
-               "qk_norm_rope: ld must be a multiple of 4 and >= 3*heads*head_dim");
+  DFOT_REQUIRE(ld % 8 == 0 && ld >= 3 * heads * head_dim && (uintptr_t)qkv % 16 == 0, DFOT_ERR_UNSUPPORTED,
+               "qk_norm_rope: ld must be a multiple of 8 and >= 3*heads*head_dim, qkv 16-byte aligned");
+  DFOT_REQUIRE(2 * heads * (head_dim / 8) <= 16 * 32, DFOT_ERR_UNSUPPORTED,
+               "qk_norm_rope: 2*heads*head_dim = %lld > 4096 unsupported", (long long)(2 * heads * head_dim));
+  DFOT_REQUIRE((uintptr_t)rope_cs % 16 == 0 && (uintptr_t)q_weight % 16 == 0 && (uintptr_t)k_weight % 16 == 0,
+               DFOT_ERR_UNSUPPORTED, "qk_norm_rope: weights and rope table must be 16-byte aligned");
   const unsigned grid = (unsigned)ceil_div(M, kThreads / 32);
   cudaStream_t s = (cudaStream_t)stream;
-  if (head_dim == 64)
-    qk_norm_rope_kernel<64, 6><<<grid, kThreads, 0, s>>>((__nv_bfloat16*)qkv, ld, q_weight, k_weight, eps, rope_cs,
-                                                         tokens_per_sample, M, (int)heads, q_scale);
-  else
-    qk_norm_rope_kernel<128, 6><<<grid, kThreads, 0, s>>>((__nv_bfloat16*)qkv, ld, q_weight, k_weight, eps, rope_cs,
-                                                          tokens_per_sample, M, (int)heads, q_scale);
+  // NI = load instructions per token: 2*heads segments, 32/(head_dim/8) of them per instruction
+  const int64_t ni = ceil_div(2 * heads * (head_dim / 8), 32);
+#define LAUNCH(DH, NI)                                                                                                 \
+  qk_norm_rope_kernel<DH, NI><<<grid, kThreads, 0, s>>>((__nv_bfloat16*)qkv, ld, q_weight, k_weight, eps, rope_cs,     \
+                                                        tokens_per_sample, M, (int)heads, q_scale)
+  if (head_dim == 64) {
+    if (ni <= 3) LAUNCH(64, 3);
+    else if (ni <= 5) LAUNCH(64, 5);
+    else if (ni <= 8) LAUNCH(64, 8);
+    else LAUNCH(64, 16);
+  } else {
+    if (ni <= 5) LAUNCH(128, 5);
+    else if (ni <= 9) LAUNCH(128, 9);
+    else LAUNCH(128, 16);
+  }
+#undef LAUNCH
   DFOT_CHECK_LAUNCH("qk_norm_rope");
   return DFOT_OK;
 }

@@ -71,14 +71,38 @@ def bench_gemm(iters):
 
 
 def bench_norm(iters):
-    M, D, P = 10240, 1152, 256
-    x = torch.randn((M, D), device=DEV)
-    mod = torch.randn((M // P, 6 * D), device=DEV)
-    y32, y16 = torch.empty((M, D), device=DEV), torch.empty((M, D), device=DEV, dtype=torch.bfloat16)
-    us = timeit(lambda: ops.adaln_layernorm(x, mod, 0, D, P, y_f32=y32, y_bf16=y16), iters)
-    print(f"adaln_layernorm M={M} D={D} (f32+bf16 out): {us:7.1f} us  {M * D * 10 / us / 1e3:7.1f} GB/s")
-    us = timeit(lambda: ops.adaln_layernorm(x, mod, 0, D, P, y_bf16=y16), iters)
-    print(f"adaln_layernorm M={M} D={D} (bf16 out):     {us:7.1f} us  {M * D * 6 / us / 1e3:7.1f} GB/s")
+    for M, D, P in [(10240, 1152, 256), (81920, 1152, 256)]:      # K600 step (8 rows x 1280 tokens) and 8x that (asymptote)
+        x = torch.randn((M, D), device=DEV)
+        mod = torch.randn((M // P, 6 * D), device=DEV)
+        y32, y16 = torch.empty((M, D), device=DEV), torch.empty((M, D), device=DEV, dtype=torch.bfloat16)
+        us = timeit(lambda: ops.adaln_layernorm(x, mod, 0, D, P, y_f32=y32, y_bf16=y16), iters)
+        print(f"adaln_layernorm M={M} D={D} (f32+bf16 out): {us:7.1f} us  {M * D * 10 / us / 1e3:7.1f} GB/s")
+        us = timeit(lambda: ops.adaln_layernorm(x, mod, 0, D, P, y_bf16=y16), iters)
+        print(f"adaln_layernorm M={M} D={D} (bf16 out):     {us:7.1f} us  {M * D * 6 / us / 1e3:7.1f} GB/s")
+
+
+def bench_sampler(iters):
+    """K4 (fused DDIM update + history-guidance combine + next-step inputs): algorithmic bytes per element =
+    nfe*4 (model out f32) + 4 (x_t) + 4 (x_t+1) + nfe*2 (bf16 inputs) + 4 (history noise)."""
+    import numpy as np
+    from dfot_b200.algorithms.dfot import sampling_plan as sp
+    for B, nfe, T, F in [(4, 2, 8, 3 * 256 * 256), (32, 2, 8, 3 * 256 * 256), (8, 1, 5, 16 * 16 * 16)]:
+        x = torch.randn((B, T, F), device=DEV)
+        mo = torch.randn((B * nfe, T, F), device=DEV)
+        mi = torch.empty((B * nfe, T, F), device=DEV, dtype=torch.bfloat16)
+        nh = torch.randn((B, T, F), device=DEV)
+        upd = np.zeros((B * nfe, T), dtype=sp.UPDATE_DTYPE)
+        upd["a"], upd["b"], upd["w"], upd["generate"] = 0.9, 0.1, 1.0, 1
+        upd["generate"][:, 0] = 0
+        prep = np.zeros((B * nfe, T), dtype=sp.PREPARE_DTYPE)
+        prep["mode"][0::nfe, 0] = 1
+        prep["qa"], prep["qb"] = 0.3, 0.9
+        prep["noise_row"] = np.arange(B * nfe)[:, None] // nfe
+        ud, pd = sp.to_device_bytes(upd, DEV), sp.to_device_bytes(prep, DEV)
+        us = timeit(lambda: ops.sampler_step_hg(x, mo, mi, ud, pd, None, nh, None, B, nfe, T), iters)
+        n = B * T * F
+        by = n * (nfe * 4 + 4 + 4 + nfe * 2) + B * F * 4        # history-noise read only for the context frame
+        print(f"sampler_step_hg B={B} nfe={nfe} T={T} F={F}: {us:7.1f} us  {by / us / 1e3:7.1f} GB/s  ({by / 1e6:.0f} MB)")
 
 
 def bench_uvit_gemm(iters):
@@ -177,6 +201,8 @@ if __name__ == "__main__":
         bench_gemm(a.iters)
     if a.which in ("norm", "all"):
         bench_norm(a.iters)
+    if a.which in ("sampler", "all"):
+        bench_sampler(a.iters)
     if a.which in ("uvit", "all"):
         bench_uvit(a.iters)
     if a.which in ("uvit_gemm", "all"):

@@ -159,7 +159,8 @@ def test_rmsnorm_film(M, D, P):
     assert rel_err(out, ref) < 4e-3
 
 
-@pytest.mark.parametrize("heads,dh,T,gh", [(9, 64, 8, 8), (9, 128, 4, 4), (1, 64, 4, 4), (1, 128, 4, 2)])
+@pytest.mark.parametrize("heads,dh,T,gh", [(9, 64, 8, 8), (9, 128, 4, 4), (1, 64, 4, 4), (1, 128, 4, 2), (12, 64, 4, 4),
+                                           (20, 64, 2, 2), (5, 128, 3, 2), (16, 128, 2, 2)])
 def test_qk_norm_rope(heads, dh, T, gh):
     D, R = heads * dh, 2
     Ntok = T * gh * gh
