@@ -35,12 +35,16 @@ __device__ __forceinline__ float4 clamp4(float4 v, float c) {
 }
 
 // grid = (chunks, T, B); each thread owns 4 consecutive elements per iteration.
-template <typename TOut, typename TIn>
+// NFE > 0: the branch count is a compile-time constant, so every stream of an element (x_t, the NFE model outputs, the
+// DDIM / history / excluded-token noise) is loaded before the first use — one DRAM round trip per element with
+// (2 + 2*NFE) x 16 bytes in flight per thread instead of one dependent load after another.  NFE == 0: generic loop.
+template <typename TOut, typename TIn, int NFE>
 __global__ void __launch_bounds__(kSamplerThreads)
 sampler_step_hg_kernel(float* __restrict__ x, const TOut* __restrict__ model_out, TIn* __restrict__ model_in_next,
                        const dfot_frame_update* __restrict__ upd, const dfot_frame_prepare* __restrict__ prep,
                        const float* __restrict__ noise_ddim, const float* __restrict__ noise_hist,
-                       const float* __restrict__ noise_excl, int nfe, int T, int64_t F) {
+                       const float* __restrict__ noise_excl, int nfe_rt, int T, int64_t F) {
+  const int nfe = NFE > 0 ? NFE : nfe_rt;
   const int t = blockIdx.y, b = blockIdx.z;
   __shared__ dfot_frame_update s_upd[kMaxNfe];
   __shared__ dfot_frame_prepare s_prep[kMaxNfe];
@@ -52,42 +56,95 @@ sampler_step_hg_kernel(float* __restrict__ x, const TOut* __restrict__ model_out
   __syncthreads();
   const bool do_update = (model_out != nullptr) && (upd != nullptr) && s_upd[0].generate != 0;
   const int64_t frame_x = ((int64_t)b * T + t) * F;
+  const int64_t row_stride = (int64_t)T * F;                    // between the branches of a sample
+  const int64_t frame_r = ((int64_t)b * nfe * T + t) * F;       // branch 0 of this (sample, frame)
   for (int64_t e = ((int64_t)blockIdx.x * kSamplerThreads + threadIdx.x) * 4; e < F;
        e += (int64_t)gridDim.x * kSamplerThreads * 4) {
     // x is updated in place: plain (coherent) load, not the .nc streaming path
     float4 xv = *reinterpret_cast<const float4*>(x + frame_x + e);
-    if (do_update) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int j = 0; j < nfe; ++j) {
-        const dfot_frame_update u = s_upd[j];
-        if (u.w == 0.f) continue;
-        const int64_t off = (((int64_t)b * nfe + j) * T + t) * F + e;
-        float4 o = Vec4<TOut>::load(model_out + off);
-        if (u.clip > 0.f) o = clamp4(o, u.clip);
-        float4 v = make_float4(u.a * xv.x + u.b * o.x, u.a * xv.y + u.b * o.y, u.a * xv.z + u.b * o.z,
-                               u.a * xv.w + u.b * o.w);
-        if (u.sigma != 0.f && noise_ddim != nullptr) {
-          float4 n = Vec4<float>::load(noise_ddim + off);
-          v.x += u.sigma * n.x; v.y += u.sigma * n.y; v.z += u.sigma * n.z; v.w += u.sigma * n.w;
+    if constexpr (NFE > 0) {
+      float4 o[NFE], nd[NFE], np[NFE];
+      if (do_update) {
+#pragma unroll
+        for (int j = 0; j < NFE; ++j) {
+          if (s_upd[j].w == 0.f) continue;
+          o[j] = Vec4<TOut>::load(model_out + frame_r + j * row_stride + e);
+          if (s_upd[j].sigma != 0.f && noise_ddim != nullptr) nd[j] = Vec4<float>::load(noise_ddim + frame_r + j * row_stride + e);
         }
-        acc.x += u.w * v.x; acc.y += u.w * v.y; acc.z += u.w * v.z; acc.w += u.w * v.w;
       }
-      xv = acc;
-      Vec4<float>::store(x + frame_x + e, xv);
-    }
-    if (model_in_next != nullptr) {
-      for (int j = 0; j < nfe; ++j) {
-        const dfot_frame_prepare p = s_prep[j];
-        const int64_t off = (((int64_t)b * nfe + j) * T + t) * F + e;
-        float4 v = xv;
-        if (p.mode == 1) {
-          float4 n = Vec4<float>::load(noise_hist + ((int64_t)p.noise_row * T + t) * F + e);
-          v = make_float4(p.qa * xv.x + p.qb * n.x, p.qa * xv.y + p.qb * n.y, p.qa * xv.z + p.qb * n.z,
-                          p.qa * xv.w + p.qb * n.w);
-        } else if (p.mode == 2) {
-          v = Vec4<float>::load(noise_excl + off);
+      if (model_in_next != nullptr) {
+#pragma unroll
+        for (int j = 0; j < NFE; ++j) {
+          const int mode = s_prep[j].mode;
+          if (mode == 1) np[j] = Vec4<float>::load(noise_hist + ((int64_t)s_prep[j].noise_row * T + t) * F + e);
+          else if (mode == 2) np[j] = Vec4<float>::load(noise_excl + frame_r + j * row_stride + e);
         }
-        Vec4<TIn>::store(model_in_next + off, v);
+      }
+      if (do_update) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < NFE; ++j) {
+          const dfot_frame_update u = s_upd[j];
+          if (u.w == 0.f) continue;
+          float4 ov = o[j];
+          if (u.clip > 0.f) ov = clamp4(ov, u.clip);
+          float4 v = make_float4(u.a * xv.x + u.b * ov.x, u.a * xv.y + u.b * ov.y, u.a * xv.z + u.b * ov.z,
+                                 u.a * xv.w + u.b * ov.w);
+          if (u.sigma != 0.f && noise_ddim != nullptr) {
+            v.x += u.sigma * nd[j].x; v.y += u.sigma * nd[j].y; v.z += u.sigma * nd[j].z; v.w += u.sigma * nd[j].w;
+          }
+          acc.x += u.w * v.x; acc.y += u.w * v.y; acc.z += u.w * v.z; acc.w += u.w * v.w;
+        }
+        xv = acc;
+        Vec4<float>::store(x + frame_x + e, xv);
+      }
+      if (model_in_next != nullptr) {
+#pragma unroll
+        for (int j = 0; j < NFE; ++j) {
+          const dfot_frame_prepare p = s_prep[j];
+          float4 v = xv;
+          if (p.mode == 1)
+            v = make_float4(p.qa * xv.x + p.qb * np[j].x, p.qa * xv.y + p.qb * np[j].y, p.qa * xv.z + p.qb * np[j].z,
+                            p.qa * xv.w + p.qb * np[j].w);
+          else if (p.mode == 2)
+            v = np[j];
+          Vec4<TIn>::store(model_in_next + frame_r + j * row_stride + e, v);
+        }
+      }
+    } else {
+      if (do_update) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < nfe; ++j) {
+          const dfot_frame_update u = s_upd[j];
+          if (u.w == 0.f) continue;
+          const int64_t off = frame_r + j * row_stride + e;
+          float4 o = Vec4<TOut>::load(model_out + off);
+          if (u.clip > 0.f) o = clamp4(o, u.clip);
+          float4 v = make_float4(u.a * xv.x + u.b * o.x, u.a * xv.y + u.b * o.y, u.a * xv.z + u.b * o.z,
+                                 u.a * xv.w + u.b * o.w);
+          if (u.sigma != 0.f && noise_ddim != nullptr) {
+            float4 n = Vec4<float>::load(noise_ddim + off);
+            v.x += u.sigma * n.x; v.y += u.sigma * n.y; v.z += u.sigma * n.z; v.w += u.sigma * n.w;
+          }
+          acc.x += u.w * v.x; acc.y += u.w * v.y; acc.z += u.w * v.z; acc.w += u.w * v.w;
+        }
+        xv = acc;
+        Vec4<float>::store(x + frame_x + e, xv);
+      }
+      if (model_in_next != nullptr) {
+        for (int j = 0; j < nfe; ++j) {
+          const dfot_frame_prepare p = s_prep[j];
+          const int64_t off = frame_r + j * row_stride + e;
+          float4 v = xv;
+          if (p.mode == 1) {
+            float4 n = Vec4<float>::load(noise_hist + ((int64_t)p.noise_row * T + t) * F + e);
+            v = make_float4(p.qa * xv.x + p.qb * n.x, p.qa * xv.y + p.qb * n.y, p.qa * xv.z + p.qb * n.z,
+                            p.qa * xv.w + p.qb * n.w);
+          } else if (p.mode == 2) {
+            v = Vec4<float>::load(noise_excl + off);
+          }
+          Vec4<TIn>::store(model_in_next + off, v);
+        }
       }
     }
   }
@@ -117,9 +174,19 @@ extern "C" int dfot_sampler_step_hg(float* x, const void* model_out, int model_o
   if (chunks > cap) chunks = cap < 1 ? 1 : cap;
   dim3 grid((unsigned)chunks, (unsigned)T, (unsigned)B), block(kSamplerThreads);
   cudaStream_t s = (cudaStream_t)stream;
-#define LAUNCH(TO, TI)                                                                                       \
-  sampler_step_hg_kernel<TO, TI><<<grid, block, 0, s>>>(x, (const TO*)model_out, (TI*)model_in_next, upd, prep, \
-                                                        noise_ddim, noise_hist, noise_excl, (int)nfe, (int)T, F)
+#define LAUNCH_N(TO, TI, N)                                                                                       \
+  sampler_step_hg_kernel<TO, TI, N><<<grid, block, 0, s>>>(x, (const TO*)model_out, (TI*)model_in_next, upd, prep,  \
+                                                           noise_ddim, noise_hist, noise_excl, (int)nfe, (int)T, F)
+#define LAUNCH(TO, TI)                                                                                            \
+  do {                                                                                                            \
+    switch (nfe) {                                                                                                \
+      case 1: LAUNCH_N(TO, TI, 1); break;                                                                         \
+      case 2: LAUNCH_N(TO, TI, 2); break;                                                                         \
+      case 3: LAUNCH_N(TO, TI, 3); break;                                                                         \
+      case 4: LAUNCH_N(TO, TI, 4); break;                                                                         \
+      default: LAUNCH_N(TO, TI, 0);                                                                               \
+    }                                                                                                             \
+  } while (0)
   const bool ob = model_out_dtype == DFOT_BF16, ib = model_in_dtype == DFOT_BF16;
   DFOT_REQUIRE((model_out_dtype == DFOT_F32 || ob) && (model_in_dtype == DFOT_F32 || ib), DFOT_ERR_INVALID_ARG,
                "sampler_step_hg: dtype tags must be DFOT_F32 or DFOT_BF16");
@@ -127,6 +194,7 @@ extern "C" int dfot_sampler_step_hg(float* x, const void* model_out, int model_o
   else if (ob) LAUNCH(__nv_bfloat16, float);
   else if (ib) LAUNCH(float, __nv_bfloat16);
   else LAUNCH(float, float);
+#undef LAUNCH_N
 #undef LAUNCH
   DFOT_CHECK_LAUNCH("sampler_step_hg");
   return DFOT_OK;

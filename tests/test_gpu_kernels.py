@@ -185,7 +185,7 @@ def test_adaln_layernorm(M, D, P):
 @pytest.mark.parametrize("out_dt,in_dt", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
                                           (torch.bfloat16, torch.bfloat16)])
 @pytest.mark.parametrize("B,nfe,T,shape", [(2, 2, 8, (4, 16, 16)), (8, 1, 5, (16, 16, 16)), (1, 6, 4, (4, 8, 8)),
-                                           (1, 2, 8, (3, 64, 64))])
+                                           (1, 2, 8, (3, 64, 64)), (2, 3, 4, (4, 8, 8)), (1, 4, 3, (4, 16, 16))])
 def test_sampler_step_hg_matches_contract(out_dt, in_dt, B, nfe, T, shape):
     g = torch.Generator().manual_seed(B * 100 + nfe * 10 + T)
     rng = np.random.default_rng(B + nfe + T)
