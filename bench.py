@@ -105,6 +105,25 @@ class Workload:
                          f"17 frames = 5 tokens (2 context), {args.sampling_steps} DDIM steps, conditional HG (nfe=1), "
                          f"batch {self.batch}/GPU")
             self.l2 = "per-step activations (~0.5 GB) and weights (1.3 GB bf16) exceed the 126 MB L2; no flush needed"
+        elif name == "re10k_long":
+            # README.md:69 "Single Image to Long Video (200 Frames)" = BASELINE config[3]
+            self.cfg = re10k_cfg(args.sampling_steps)
+            self.cfg.update(n_frames=200)
+            self.cfg["tasks"]["prediction"].update(
+                history_guidance=dict(name="stabilized_vanilla", guidance_scale=4.0, stabilization_level=0.02,
+                                      visualize=False), keyframe_density=0.0625)
+            self.cfg["tasks"]["interpolation"].update(
+                history_guidance=dict(name="vanilla", guidance_scale=1.5, visualize=False), max_batch_size=4)
+            self.batch = args.batch or 1
+            self.n_tokens, self.ctx_tokens, self.gen_frames, self.nfe = 200, 1, 200 - 1, 2
+            self.x_shape = [3, 256, 256]
+            self.text = (f"RE10K single-image-to-200-frame rollout (dfot_video_pose, UViT3DPose as in the short workload): "
+                         f"12 keyframes by two sliding windows under stabilized_vanilla(4.0, 0.02), then two rounds of "
+                         f"vanilla(1.5) keyframe interpolation (11 + 35 chunks in batches of 4), {args.sampling_steps} "
+                         f"DDIM steps, {self.batch} sample(s) in total (strong scaling: chunk batches dealt over the "
+                         f"sample axis of the mesh, branches split inside pairs)")
+            self.l2 = ("per-forward activations (>1 GB per row), pose modulation cache and weights (1.1 GB bf16) exceed "
+                       "the 126 MB L2; no flush needed")
         else:
             self.cfg = re10k_cfg(args.sampling_steps)
             self.batch = args.batch or 4
@@ -118,6 +137,8 @@ class Workload:
 
     def inputs(self, rank):
         import torch
+        if self.name == "re10k_long":
+            rank = 0                                   # strong scaling: every rank holds the same sample(s)
         g = torch.Generator().manual_seed(123 + rank)
         if self.name == "k600":
             return torch.randn((self.batch, self.n_tokens, *self.x_shape), generator=g), None
@@ -135,7 +156,7 @@ class Workload:
             D, depth, r = b["hidden_size"], b["depth"], b.get("spatial_mlp_ratio") or 0
             N = self.n_tokens * (16 // b["patch_size"]) ** 2
             return depth * N * (8 * D * D + 4 * N * D + 4 * r * D * D) / 1e9
-        T, ch, L = self.n_tokens, b["channels"], len(b["channels"])
+        T, ch, L = self.cfg["max_frames"], b["channels"], len(b["channels"])
         res = [self.x_shape[1] // b["patch_size"] // 2 ** i for i in range(L)]
         nblk = [2 * n for n in b["num_updown_blocks"]] + [b["num_mid_blocks"]]
         total = 0.0
@@ -236,6 +257,14 @@ def cpu_baseline(wl, sampling_steps, seconds_budget=25.0):
     frames/s = NFE/s * generated frames / (sampling steps * nfe)."""
     import torch
     from oracle.sampler import SamplerOracle
+    if wl.name == "re10k_long":
+        # same backbone and per-row cost as the 8-frame workload: time that bounded sample and convert with the long
+        # rollout's row count (96 forward-rows per DDIM step per sample: 2 + 2 keyframe-window rows, 22 + 70 chunk rows)
+        short = Workload("re10k", type("A", (), dict(sampling_steps=sampling_steps, no_mlp=False, batch=1))())
+        cb = cpu_baseline(short, sampling_steps, seconds_budget)
+        cb["value"] = cb["nfe_per_sec"] * wl.gen_frames / (sampling_steps * 96)
+        cb["sample"] += f"; long rollout: frames/s = NFE/s*{wl.gen_frames}/({sampling_steps}*96 rows per step)"
+        return cb
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     cfg = json.loads(json.dumps(wl.cfg))
@@ -282,7 +311,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dfot_b200", choices=["dfot_b200", "reference"])
     ap.add_argument("--no-mlp", action="store_true", help="fork default: spatial_mlp_ratio unset (no MLP blocks)")
-    ap.add_argument("--workload", default="re10k", choices=["re10k", "k600"])
+    ap.add_argument("--workload", default="re10k", choices=["re10k", "k600", "re10k_long"])
     ap.add_argument("--batch", type=int, default=0, help="samples per GPU (default: 4 for re10k, 8 for k600)")
     ap.add_argument("--sampling-steps", type=int, default=50)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -293,7 +322,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = Workload(args.workload, args)
     cfg = wl.cfg
-    config = dict(workload=wl.text, global_batch=wl.batch * world, parallelism=f"samples sharded x{world}", l2=wl.l2)
+    strong = wl.name == "re10k_long"          # fixed total work: one rollout spread over the mesh
+    br = 2 if (strong and world % 2 == 0) else 1
+    config = dict(workload=wl.text, global_batch=wl.batch * (1 if strong else world),
+                  parallelism=(f"chunk batches x{world // br} x branches x{br}" if strong
+                               else f"samples sharded x{world}"), l2=wl.l2)
 
     if args.impl == "reference":
         if rank != 0:
@@ -319,13 +352,16 @@ def main():
     algo = make_weights(cfg, 0).to(dev).eval()
     B = wl.batch
     xs_host, conds_host = wl.inputs(rank)
-    if wl.name == "re10k":
+    if strong and world > 1:
+        from dfot_b200 import distributed as D
+        algo.mesh = D.build_mesh(br=br)
+    if wl.name != "k600":
         xs_host = algo._normalize_x(xs_host.to(dev)).cpu()      # dataset-normalised pixels, as on_after_batch_transfer
     xs_host = xs_host.pin_memory()
     conds_host = None if conds_host is None else conds_host.pin_memory()
     xs_dev = xs_host.to(dev)
     conds_dev = None if conds_host is None else conds_host.to(dev)
-    torch.manual_seed(123 + rank)
+    torch.manual_seed(123 + (0 if strong else rank))     # a shared rollout needs one noise stream on every rank
 
     def barrier():
         if world > 1:
@@ -333,14 +369,19 @@ def main():
         torch.cuda.synchronize()
 
     def run_resident():
+        if strong:
+            return algo.sample_sharded(xs_dev, conds_dev, wl.ctx_tokens)
         return algo._predict_videos(xs_dev, wl.ctx_tokens, conds_dev)
 
-    gathered = [torch.empty_like(xs_dev) for _ in range(world)] if world > 1 else None
+    gathered = [torch.empty_like(xs_dev) for _ in range(world)] if (world > 1 and not strong) else None
 
     def run_e2e():
         # public API with HOST buffers: H2D of the latents, sampling, (N>1: final sample gather), D2H of the result
         batch = {"xs": xs_host.to(dev, non_blocking=True), "gt_videos": None,
                  "conditions": None if conds_host is None else conds_host.to(dev, non_blocking=True)}
+        if strong:      # the sharded entry point (every rank ends with the whole video; rank 0's copy goes to the host)
+            vids = algo._unnormalize_x(algo.sample_sharded(batch["xs"], batch["conditions"], wl.ctx_tokens))
+            return vids.to("cpu")
         vids = algo._sample_all_videos(batch, 0)["prediction"]
         if world > 1:
             dist.all_gather(gathered, vids.contiguous())
@@ -361,19 +402,23 @@ def main():
             ms = t.item()
         return ms
 
-    for _ in range(max(args.warmup, 3)):
+    # W >= 3 warm-up steps; a step of the long rollout is 700 sequential backbone calls, one warm-up pass suffices there
+    n_warm = max(args.warmup, 1 if strong else 3)
+    for _ in range(n_warm):
         run_resident()
     n0 = ops.total_launches()
+    p0 = algo.nfe_rows_planned
     with ClockSampler(local_rank) as clocks:
         ms = timed(run_resident, args.steps)
     launches = ops.total_launches() - n0
+    rows_planned, passes_counted = algo.nfe_rows_planned - p0, args.steps
     run_e2e()
     ms_e2e = timed(run_e2e, args.steps)
 
     # roofline of the dominant kernel (the tcgen05 GEMM kernel, which also runs the implicit-GEMM convolutions) and
     # of the attention kernel: instrumented extra pass over the same region with CUDA events around every launch
     roof = roof_attn = None
-    if rank == 0:
+    if rank == 0 or strong:            # (a shared rollout has collectives: every rank takes part in the extra pass)
         ops_gemm, ops_conv, ops_attn = ops.gemm_bf16, ops.conv3x3_bf16, ops.attention
         recs, recs_attn = [], []
 
@@ -425,8 +470,8 @@ def main():
                 traffic = json.load(f)["launches"]
         except Exception:
             pass
-        t_gemm = traffic.get("gemm_level3_qkv_16384x3456x1152_bf16" if wl.name == "re10k" else "", {}).get("dram_bytes")
-        t_attn = traffic.get("attention_level2_d64_N8192_R8" if wl.name == "re10k" else "", {}).get("dram_bytes")
+        t_gemm = traffic.get("gemm_level3_qkv_16384x3456x1152_bf16" if wl.name != "k600" else "", {}).get("dram_bytes")
+        t_attn = traffic.get("attention_level2_d64_N8192_R8" if wl.name != "k600" else "", {}).get("dram_bytes")
         ach = flops / (dur * 1e-3) / 1e12
         roof = dict(bound="tensor", kernel="gemm2_bf16_tcgen05_kernel (CTA pair) + gemm_bf16_tcgen05_kernel", achieved=ach, peak=peak, unit="TFLOP/s",
                     frac=ach / peak, traffic=t_gemm, launches=len(big), avg_launch_us=1e3 * dur / max(len(big), 1),
@@ -444,15 +489,17 @@ def main():
 
     if rank == 0:
         per_step_s = ms / args.steps / 1e3
-        frames = B * world * wl.gen_frames
+        frames = B * (1 if strong else world) * wl.gen_frames
         rows = B * world * args.sampling_steps * wl.nfe
+        if strong:      # useful forward-rows of one rollout = what a single GPU executes (replicated keyframe rows and
+            rows = rows_planned // passes_counted          # noise-only replays are not counted twice)
         per_e2e_s = ms_e2e / args.steps / 1e3
         bytes_out = xs_host.numel() * 4
         bytes_in = bytes_out + (0 if conds_host is None else conds_host.numel() * 4)
         line = dict(metric="generated_frames_per_sec", value=frames / per_step_s, unit="generated_frames/s",
-                    n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps,
-                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-                    config=config, nfe_per_sec=rows / per_step_s,
+                    n_gpus=world, steps=args.steps, warmup=n_warm, ms_per_step=ms / args.steps,
+                    higher_is_better=True, scaling="strong" if strong else "weak", vs_baseline=None, dtype="bf16",
+                    data="synthetic", config=config, nfe_per_sec=rows / per_step_s,
                     model_tflops=rows * wl.forward_row_gflop() / per_step_s / 1e3,
                     e2e=dict(value=frames / per_e2e_s, unit="generated_frames/s", h2d_bytes_per_step=bytes_in,
                              d2h_bytes_per_step=bytes_out, nfe_per_sec=rows / per_e2e_s),

@@ -60,8 +60,10 @@ class DFoTVideo(BaseVideoAlgo):
         super().__init__(cfg)
         self.trace: Optional[list] = None       # tests: per-step tensors are appended when this is a list
         self.nfe_rows = 0                       # backbone forward-rows executed (NFE counter)
+        self.nfe_rows_planned = 0               # ... including rows another shard executes (dry_run replays)
         self.model_in_dtype = torch.bfloat16    # dtype of the branch inputs emitted by K4
         self.mesh = None                        # dfot_b200.distributed.Mesh for multi-GPU sampling (None = 1 GPU)
+        self.shard_chunks = False               # interpolation chunk batches spread over the dp axis (sample_sharded)
 
     def _build_model(self) -> None:
         super()._build_model(ContinuousDiffusion if self.cfg.diffusion.is_continuous else DiscreteDiffusion)
@@ -143,13 +145,23 @@ class DFoTVideo(BaseVideoAlgo):
                                      "Supported types are 'label' and 'action'.")
             rows = ctx.shape[0]
             mb = task.get("max_batch_size") or rows
-            outs = []
-            for s in range(0, rows, mb):   # every chunk is processed (the reference's conditions=None path drops
-                e = min(rows, s + mb)      # the last partial batch — quirk Q10, not replicated)
+            # Chunk batches of one round are independent (SURVEY.md §8e axis 3).  With `shard_chunks` (set by
+            # sample_sharded when the samples themselves cannot fill the dp axis) batch i is sampled by dp shard
+            # i mod dp; the other shards replay its noise draws only, so the result equals the single-GPU rollout.
+            mesh = self.mesh if self.shard_chunks else None
+            outs, owners = [], []
+            for bi, s in enumerate(range(0, rows, mb)):   # every chunk is processed (the reference's conditions=None
+                e = min(rows, s + mb)                     # path drops the last partial batch — quirk Q10, not replicated)
+                owner = bi % mesh.dp if mesh is not None else 0
                 o, _ = self._sample_sequence(batch_size=e - s, context=ctx[s:e],
                                              context_mask=torch.from_numpy(msk[s:e].astype(np.int64)),
-                                             conditions=None if cnd is None else cnd[s:e], history_guidance=guidance)
+                                             conditions=None if cnd is None else cnd[s:e], history_guidance=guidance,
+                                             dry_run=mesh is not None and owner != mesh.dp_index)
                 outs.append(o)
+                owners.append(owner)
+            if mesh is not None:
+                from dfot_b200 import distributed as D
+                outs = [D.broadcast_from_shard(o.contiguous(), owner, mesh) for o, owner in zip(outs, owners)]
             outs = torch.cat(outs, 0)
             for c, i, pred in zip(chunks, idx, outs.chunk(len(chunks), 0)):
                 xs[:, i] = pred[:, : len(c)]
@@ -250,12 +262,18 @@ class DFoTVideo(BaseVideoAlgo):
         n_ctx = n_context_tokens if n_context_tokens is not None else self.n_context_tokens
         if mesh is None:
             return self._predict_videos(xs, n_ctx, conditions)
+        if xs.shape[0] < mesh.dp:
+            # fewer samples than dp shards (the 200-frame single-sample rollout of BASELINE config[3]): every shard rolls
+            # the whole batch — keyframe windows replicated (branches still split inside the branch group), interpolation
+            # chunk batches spread over the dp axis.  All ranks must share the noise seed.
+            self.shard_chunks = True
+            try:
+                return self._predict_videos(xs, n_ctx, conditions)
+            finally:
+                self.shard_chunks = False
         counts = [len(range(*D.shard_batch(xs.shape[0], mesh.dp, d).indices(xs.shape[0]))) for d in range(mesh.dp)]
         sl = D.shard_batch(xs.shape[0], mesh.dp, mesh.dp_index)
-        if sl.stop > sl.start:
-            local = self._predict_videos(xs[sl].contiguous(), n_ctx, None if conditions is None else conditions[sl])
-        else:   # more shards than samples: this rank only takes part in the final gather
-            local = xs[sl].clone()
+        local = self._predict_videos(xs[sl].contiguous(), n_ctx, None if conditions is None else conditions[sl])
         return D.gather_samples(local.contiguous(), mesh, counts)
 
     # ------------------------------------------------------------------ window planning (host only)
@@ -286,7 +304,10 @@ class DFoTVideo(BaseVideoAlgo):
                          context_mask: Optional[Tensor] = None, conditions: Optional[Tensor] = None,
                          guidance_fn: Optional[Callable] = None, reconstruction_guidance: float = 0.0,
                          history_guidance: Optional[HistoryGuidance] = None, return_all: bool = False,
-                         pbar=None) -> Tuple[Tensor, Optional[Tensor]]:
+                         pbar=None, dry_run: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
+        """The window sampler (reference `_sample_sequence`, dfot_video.py:530-763).  `dry_run` (multi-GPU chunk
+        sharding) draws exactly the noise a real call would — so every rank's generator stays where the single-GPU run
+        would have it — but launches no kernel; the returned tensor is a placeholder for the owner's broadcast."""
         x_shape = self.x_shape
         if guidance_fn is not None or reconstruction_guidance > 0:
             raise NotImplementedError("guidance_fn / reconstruction guidance needs autograd through the backbone "
@@ -341,7 +362,7 @@ class DFoTVideo(BaseVideoAlgo):
         cond_cache: Dict[int, Tensor] = {}
 
         def cond_for(nfe: int):
-            if conditions is None:
+            if conditions is None or dry_run:
                 return None
             if nfe not in cond_cache:   # constant over the window (the reference recomputes it every step, :732-743)
                 cond_cache[nfe] = self._window_conditions(conditions.to(dev), nfe)
@@ -356,32 +377,39 @@ class DFoTVideo(BaseVideoAlgo):
         record = [] if return_all else None
         T = horizon
         model_in = None
+        def k4(*args):
+            if not dry_run:
+                ops.sampler_step_hg(*args)
+
         for m, p in enumerate(plans):
             if return_all:
                 record.append(x.clone())
             if m == 0:
                 nh, ne = draw_prepare_noise(p)
                 model_in = self._model_in_buffer(B * p.nfe, T, dev)
-                ops.sampler_step_hg(x, None, model_in, None, prep_dev[0], None, nh, ne, B, p.nfe, T)
-            out = self._backbone_rows(model_in, lvl_dev[m], cond_for(p.nfe), cm_dev[m], B, p.nfe)
-            self.nfe_rows += B * p.nfe
+                k4(x, None, model_in, None, prep_dev[0], None, nh, ne, B, p.nfe, T)
+            out = None
+            self.nfe_rows_planned += B * p.nfe
+            if not dry_run:
+                out = self._backbone_rows(model_in, lvl_dev[m], cond_for(p.nfe), cm_dev[m], B, p.nfe)
+                self.nfe_rows += B * p.nfe
             # RNG ③: DDIM noise — drawn even when eta == 0 to keep the stream aligned with the reference
             nd = dm.clipped_noise((B * p.nfe, T, *x_shape), dev)
             nd = nd if tb.eta != 0 else None
             trace_in = model_in.float().clone() if self.trace is not None else None
             nxt = plans[m + 1] if m + 1 < n_steps else None
             if nxt is None:
-                ops.sampler_step_hg(x, out, None, upd_dev[m], None, nd, None, None, B, p.nfe, T)
+                k4(x, out, None, upd_dev[m], None, nd, None, None, B, p.nfe, T)
             else:
                 nh, ne = draw_prepare_noise(nxt)
                 nxt_in = model_in if nxt.nfe == p.nfe else self._model_in_buffer(B * nxt.nfe, T, dev)
                 if nxt.nfe == p.nfe:   # one fused launch: update + combine + revert + next-step prepare
-                    ops.sampler_step_hg(x, out, nxt_in, upd_dev[m], prep_dev[m + 1], nd, nh, ne, B, p.nfe, T)
+                    k4(x, out, nxt_in, upd_dev[m], prep_dev[m + 1], nd, nh, ne, B, p.nfe, T)
                 else:                  # branch count changes between steps: split into update and prepare launches
-                    ops.sampler_step_hg(x, out, None, upd_dev[m], None, nd, None, None, B, p.nfe, T)
-                    ops.sampler_step_hg(x, None, nxt_in, None, prep_dev[m + 1], None, nh, ne, B, nxt.nfe, T)
+                    k4(x, out, None, upd_dev[m], None, nd, None, None, B, p.nfe, T)
+                    k4(x, None, nxt_in, None, prep_dev[m + 1], None, nh, ne, B, nxt.nfe, T)
                 model_in = nxt_in
-            if self.trace is not None:
+            if self.trace is not None and not dry_run:
                 self.trace.append(dict(model_in=trace_in, levels_from=p.levels_from, levels_to=p.levels_to,
                                        cond_mask=p.cond_mask, model_out=out.float().clone(), x_after=x.clone(),
                                        context_mask=p.context_mask))

@@ -1142,7 +1142,15 @@ static int pick_pair_bn(int64_t M, int64_t N, int epilogue) {
   }
   if (ov == 0 || N < 128) return 0;
   int bn = 256;
-  if (epilogue != DFOT_EPI_QKNORM_ROPE_BF16) {
+  static int force_bn = -1;                          // DFOT_GEMM_BN=128|192|256 pins the pair tile width (benchmarking)
+  if (force_bn < 0) {
+    const char* e = getenv("DFOT_GEMM_BN");
+    force_bn = e == nullptr ? 0 : atoi(e);
+    if (force_bn != 128 && force_bn != 192 && force_bn != 256) force_bn = 0;
+  }
+  if (force_bn != 0 && epilogue != DFOT_EPI_QKNORM_ROPE_BF16) {
+    bn = force_bn;
+  } else if (epilogue != DFOT_EPI_QKNORM_ROPE_BF16) {
     const int64_t pad256 = ceil_div(N, 256) * 256, pad192 = ceil_div(N, 192) * 192, pad128 = ceil_div(N, 128) * 128;
     if (pad192 * 100 <= pad256 * 85) bn = 192;
     if (pad128 * 100 <= (bn == 256 ? pad256 : pad192) * 85) bn = 128;

@@ -4,6 +4,10 @@ sequence:
 
   * samples  — every rank samples its own slice of the batch with no communication inside the loop; one
                all_gather of the finished samples at the end (`gather_samples`);
+  * interpolation chunk batches — when there are fewer samples than dp shards, the chunk batches of an interpolation
+               round (independent `_sample_sequence` calls) are dealt round-robin over the dp axis; every other shard
+               replays the batch's noise draws only, and the owner broadcasts the finished batch
+               (`broadcast_from_shard`), so the result equals the single-GPU rollout;
   * history-guidance branches — within a branch group of `br` ranks (br divides nfe) each rank runs the backbone
                on its share of the branch rows of every sample; one all_gather of the backbone output per step,
                after which every member runs the identical fused K4 step (same noise seed), so x_t stays replicated.
@@ -92,3 +96,12 @@ def gather_samples(local: torch.Tensor, mesh: Mesh, counts: List[int]) -> torch.
     parts = [torch.empty_like(pad) for _ in range(mesh.dp)]
     dist.all_gather(parts, pad, group=mesh.dp_group if mesh.br > 1 else None)
     return torch.cat([p[:c] for p, c in zip(parts, counts)], 0)
+
+
+def broadcast_from_shard(t: torch.Tensor, owner_dp_index: int, mesh: Mesh) -> torch.Tensor:
+    """Broadcast a finished chunk batch from dp shard `owner_dp_index` to the same branch member of every other shard
+    (in place; x_t is replicated inside a branch group, so each member serves its own column of the mesh)."""
+    if mesh.dp == 1:
+        return t
+    dist.broadcast(t, src=owner_dp_index * mesh.br + mesh.br_index, group=mesh.dp_group if mesh.br > 1 else None)
+    return t

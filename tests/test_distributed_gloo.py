@@ -51,11 +51,13 @@ def _worker(rank, world, port, case, br, out_path):
         algo, cfg, xs, conds, NoiseBank = _build(case)
         from dfot_b200 import distributed as D
         algo.mesh = D.build_mesh(br=br)
-        # per-sample noise streams so that a sample's result does not depend on which shard it lands in
+        # per-sample noise streams so that a sample's result does not depend on which shard it lands in; with fewer
+        # samples than shards (interpolation chunk sharding) every rank replays the same stream
         sl = D.shard_batch(xs.shape[0], algo.mesh.dp, algo.mesh.dp_index)
-        bank = NoiseBank(100 + sl.start)
+        bank = NoiseBank(100 + (sl.start if xs.shape[0] >= algo.mesh.dp else 0))
         algo.diffusion_model.noise_source = lambda shape, device: bank.randn(shape)
         out = algo.sample_sharded(xs, conds, cfg["context_frames"])
+        np.save(out_path + f".rows{rank}.npy", np.array([algo.nfe_rows]))
         if rank == 0:
             np.save(out_path, out.numpy())
     finally:
@@ -76,6 +78,7 @@ def _single(case, shard_starts):
             algo.diffusion_model.noise_source = lambda shape, device, bank=bank: bank.randn(shape)
             outs.append(algo._predict_videos(xs[a:b].contiguous(), cfg["context_frames"],
                                              None if conds is None else conds[a:b]))
+        _single.nfe_rows = algo.nfe_rows
         return torch.cat(outs, 0).numpy()
     finally:
         for k, v in real_ops.items():
@@ -103,3 +106,19 @@ def test_world2_matches_single_process(case, br, tmp_path):
         assert np.array_equal(got, want)          # sample sharding: bit-exact
     else:                                         # branch sharding changes the CPU BLAS batch shape of the checker
         assert np.abs(got - want).max() <= (2e-2 if "uvit" in case else 1e-5)   # (bf16-emulated kernels for U-ViT)
+
+
+@pytest.mark.parametrize("case", ["keyframes_interp", "uvit_pose_stabilized_interp"])
+def test_world2_interpolation_chunks_are_sharded(case, tmp_path):
+    """One sample, two dp shards: the chunk batches of every interpolation round are dealt over the shards (the other
+    shard only replays the noise draws) and the rollout must equal the single-process one bit for bit."""
+    world = 2
+    port = 29500 + (os.getpid() + hash((case, "chunks"))) % 2000
+    out_path = str(tmp_path / "out.npy")
+    mp.spawn(_worker, args=(world, port, case, 1, out_path), nprocs=world, join=True)
+    got = np.load(out_path)
+    want = _single(case, [0, 1])
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+    rows = [int(np.load(out_path + f".rows{r}.npy")[0]) for r in range(world)]
+    assert max(rows) < _single.nfe_rows and sum(rows) > _single.nfe_rows    # interpolation split, keyframes replicated
