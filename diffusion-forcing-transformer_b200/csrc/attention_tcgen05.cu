@@ -265,6 +265,7 @@ struct Params {
 template <int DH, int DP>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh (pdl_wait() follows the prologue)
   constexpr int ATOMS = (DP + 63) / 64;              // 64-wide swizzle planes per Q/K/V tile
   constexpr int TILE_BYTES = ATOMS * kAtomBytes;     // Q, K or V tile
   constexpr int P_BYTES = 2 * kAtomBytes;            // 128 rows x 128 keys bf16
@@ -309,6 +310,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params 
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();   // barriers and tensor memory are set up; global memory is only touched from here on
 
   const int n_kv = p.kv_tiles;
   auto item_coord = [&](int item, int& r, int& h, int& qt) {
@@ -544,6 +546,7 @@ constexpr int kThreads2 = 384;
 template <int DH, int DP, bool NOMAX>   // NOMAX: bounded scores, p = 2^s without a running maximum (Params::no_max)
 __global__ void __launch_bounds__(kThreads2, 1)
 attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh (pdl_wait() follows the prologue)
   constexpr int ATOMS = (DP + 63) / 64;
   constexpr int TILE_BYTES = ATOMS * kAtomBytes;
   constexpr int KS_QK = DP / 16, KS_PV = BKV / 16;
@@ -612,6 +615,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();   // barriers and tensor memory are set up; global memory is only touched from here on
 
   const int n_kv = p.kv_tiles;
   const int q_pairs = (p.q_tiles + 1) >> 1;
@@ -1119,6 +1123,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
 constexpr int kThreads3 = 640;   // warp 0 TMA, warps 1-2 MMA issuers (tile 0 / 1), warp 3 idle, warps 4-19 softmax
 __global__ void __launch_bounds__(kThreads3, 1)
 attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh (pdl_wait() follows the prologue)
   constexpr int DH = 64;
   constexpr int TILE_BYTES = kAtomBytes;             // 128 rows x 64 bf16
   constexpr uint32_t IDESC_S = make_idesc(BKV, false);
@@ -1162,6 +1167,7 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();   // barriers and tensor memory are set up; global memory is only touched from here on
 
   const int n_kv = p.kv_tiles;
   const int q_pairs = (p.q_tiles + 1) >> 1;
@@ -1477,7 +1483,7 @@ static int launch(const void* qkv, void* out, int64_t ld_out, int64_t R, int64_t
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.num_items < sms ? p.num_items : sms;
-  kern<<<grid, split ? kThreads3 : (paired ? kThreads2 : kThreads), smem_bytes, s>>>(tmap, p);
+  launch_pdl(kern, dim3(grid), dim3(split ? kThreads3 : (paired ? kThreads2 : kThreads)), smem_bytes, s, tmap, p);
   DFOT_CHECK_LAUNCH("attention_tcgen05");
   return DFOT_OK;
 }

@@ -8,6 +8,8 @@ namespace dfot {
 __global__ void noise_features_kernel(const void* __restrict__ levels, int levels_dtype,
                                       const float* __restrict__ freqs, const float* __restrict__ phases,
                                       __nv_bfloat16* __restrict__ out, int64_t n, int dim) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * dim) return;
   const int64_t r = idx / dim;
@@ -29,6 +31,8 @@ __global__ void noise_features_kernel(const void* __restrict__ levels, int level
 __global__ void silu_sum_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                      const uint8_t* __restrict__ row_mask, int64_t rows_per_mask,
                                      __nv_bfloat16* __restrict__ out, int64_t n_rows, int64_t D) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_rows * D) return;
   float v = a[idx];
@@ -44,6 +48,8 @@ __global__ void silu_sum_bf16_kernel(const float* __restrict__ a, const float* _
 template <typename TX>
 __global__ void patchify_kernel(const TX* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t ld,
                                 int64_t frames, int C, int H, int W, int p) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int gw = W / p, gh = H / p, kk = C * p * p;
   const int64_t total = frames * gh * gw * kk;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -61,6 +67,8 @@ __global__ void patchify_kernel(const TX* __restrict__ x, __nv_bfloat16* __restr
 template <typename TX>
 __global__ void unpatchify_kernel(const float* __restrict__ tok, int64_t ld, TX* __restrict__ x, int64_t frames,
                                   int C, int H, int W, int p) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int64_t total = frames * C * H * W;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -73,11 +81,15 @@ __global__ void unpatchify_kernel(const float* __restrict__ tok, int64_t ld, TX*
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = __float2bfloat16_rn(in[i]);
 }
 // 8 elements per thread: 2 x 16-byte streaming loads, one 16-byte store (pointers 16-byte aligned, n % 8 == 0)
 __global__ void cast_bf16_vec8_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n8) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   const uint4 a = ld_stream_u4(in + 8 * i), b = ld_stream_u4(in + 8 * i + 4);
@@ -102,7 +114,7 @@ extern "C" int dfot_noise_features(const void* levels, int levels_dtype, const f
                "noise_features: levels must be int64 or f32");
   DFOT_REQUIRE((fourier_freqs == nullptr) == (fourier_phases == nullptr), DFOT_ERR_INVALID_ARG,
                "noise_features: freqs and phases go together");
-  noise_features_kernel<<<blocks_for(n * dim, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(noise_features_kernel, dim3(blocks_for(n * dim, 256)), dim3(256), 0, (cudaStream_t)stream, 
       levels, levels_dtype, fourier_freqs, fourier_phases, (__nv_bfloat16*)out_bf16, n, (int)dim);
   DFOT_CHECK_LAUNCH("noise_features");
   return DFOT_OK;
@@ -112,7 +124,7 @@ extern "C" int dfot_silu_sum_bf16(const float* a, const float* b, const uint8_t*
                                   void* out_bf16, int64_t n_rows, int64_t D, void* stream) {
   DFOT_REQUIRE(a && out_bf16 && n_rows > 0 && D > 0, DFOT_ERR_INVALID_ARG, "silu_sum_bf16: bad arguments");
   DFOT_REQUIRE(row_mask == nullptr || rows_per_mask > 0, DFOT_ERR_INVALID_ARG, "silu_sum_bf16: rows_per_mask");
-  silu_sum_bf16_kernel<<<blocks_for(n_rows * D, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(silu_sum_bf16_kernel, dim3(blocks_for(n_rows * D, 256)), dim3(256), 0, (cudaStream_t)stream, 
       a, b, row_mask, rows_per_mask, (__nv_bfloat16*)out_bf16, n_rows, D);
   DFOT_CHECK_LAUNCH("silu_sum_bf16");
   return DFOT_OK;
@@ -124,10 +136,10 @@ extern "C" int dfot_patchify_bf16(const void* x, int x_dtype, void* out_bf16, in
                DFOT_ERR_INVALID_ARG, "patchify: bad arguments");
   const int64_t total = frames * C * H * W;
   if (x_dtype == DFOT_F32)
-    patchify_kernel<float><<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(patchify_kernel<float>, dim3(blocks_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
         (const float*)x, (__nv_bfloat16*)out_bf16, ld, frames, (int)C, (int)H, (int)W, (int)p);
   else if (x_dtype == DFOT_BF16)
-    patchify_kernel<__nv_bfloat16><<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(patchify_kernel<__nv_bfloat16>, dim3(blocks_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
         (const __nv_bfloat16*)x, (__nv_bfloat16*)out_bf16, ld, frames, (int)C, (int)H, (int)W, (int)p);
   else
     DFOT_REQUIRE(false, DFOT_ERR_INVALID_ARG, "patchify: x dtype must be f32 or bf16");
@@ -141,10 +153,10 @@ extern "C" int dfot_unpatchify(const float* tok, int64_t ld, void* x, int x_dtyp
                DFOT_ERR_INVALID_ARG, "unpatchify: bad arguments");
   const int64_t total = frames * C * H * W;
   if (x_dtype == DFOT_F32)
-    unpatchify_kernel<float><<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(unpatchify_kernel<float>, dim3(blocks_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
         tok, ld, (float*)x, frames, (int)C, (int)H, (int)W, (int)p);
   else if (x_dtype == DFOT_BF16)
-    unpatchify_kernel<__nv_bfloat16><<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(unpatchify_kernel<__nv_bfloat16>, dim3(blocks_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
         tok, ld, (__nv_bfloat16*)x, frames, (int)C, (int)H, (int)W, (int)p);
   else
     DFOT_REQUIRE(false, DFOT_ERR_INVALID_ARG, "unpatchify: x dtype must be f32 or bf16");
@@ -155,9 +167,9 @@ extern "C" int dfot_unpatchify(const float* tok, int64_t ld, void* x, int x_dtyp
 extern "C" int dfot_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream) {
   DFOT_REQUIRE(in && out_bf16 && n > 0, DFOT_ERR_INVALID_ARG, "cast_bf16: bad arguments");
   if (n % 8 == 0 && (uintptr_t)in % 16 == 0 && (uintptr_t)out_bf16 % 16 == 0)
-    cast_bf16_vec8_kernel<<<blocks_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out_bf16, n / 8);
+    launch_pdl(cast_bf16_vec8_kernel, dim3(blocks_for(n / 8, 256)), dim3(256), 0, (cudaStream_t)stream, in, (__nv_bfloat16*)out_bf16, n / 8);
   else
-    cast_bf16_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out_bf16, n);
+    launch_pdl(cast_bf16_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, in, (__nv_bfloat16*)out_bf16, n);
   DFOT_CHECK_LAUNCH("cast_bf16");
   return DFOT_OK;
 }

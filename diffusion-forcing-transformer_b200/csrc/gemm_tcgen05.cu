@@ -662,6 +662,7 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                          const Params p) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh (pdl_wait() follows the prologue)
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms must start on 1024-byte boundaries
@@ -708,6 +709,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();   // barriers, tensor memory and tensor maps are set up; global memory is only touched from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -857,6 +859,7 @@ template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                           const Params p) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh (pdl_wait() follows the prologue)
   using C = Cfg2<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -903,6 +906,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();   // barriers, tensor memory and tensor maps are set up; global memory is only touched from here on
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs: own A rows, own half of B) =====================
@@ -1087,7 +1091,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   }
   const int tiles = (int)(ceil_div(p.M, BM) * ceil_div(p.N, BN));
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kThreads, C::kSmemBytes, s>>>(ta, tb, p);
+  launch_pdl(kern, dim3(grid), dim3(kThreads), C::kSmemBytes, s, ta, tb, p);
   DFOT_CHECK_LAUNCH("gemm_bf16_tcgen05");
   return DFOT_OK;
 }
@@ -1106,7 +1110,7 @@ static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const Param
   const int tiles = (int)(ceil_div(p.M, 2 * BM) * ceil_div(p.N, BN));
   int pairs = num_sms() / 2;
   if (tiles < pairs) pairs = tiles;
-  kern<<<2 * pairs, kThreads, C::kSmemBytes, s>>>(ta, tb, p);   // static __cluster_dims__(2, 1, 1)
+  launch_pdl(kern, dim3(2 * pairs), dim3(kThreads), C::kSmemBytes, s, ta, tb, p);   // static __cluster_dims__(2, 1, 1)
   DFOT_CHECK_LAUNCH("gemm2_bf16_tcgen05");
   return DFOT_OK;
 }

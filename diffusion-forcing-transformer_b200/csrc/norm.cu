@@ -12,6 +12,8 @@ __global__ void __launch_bounds__(kNormWarps * 32)
 adaln_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ mod, int64_t mod_ld,
                        int64_t shift_col, int64_t scale_col, float* __restrict__ y_f32,
                        __nv_bfloat16* __restrict__ y_bf16, int64_t M, int D, int64_t tokens_per_frame, float eps) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * kNormWarps + warp;
   if (m >= M) return;
@@ -76,7 +78,7 @@ extern "C" int dfot_adaln_layernorm(const float* x, const float* mod, int64_t mo
   const unsigned grid = (unsigned)ceil_div(M, kNormWarps);
   cudaStream_t s = (cudaStream_t)stream;
 #define LAUNCH(NV)                                                                                             \
-  adaln_layernorm_kernel<NV><<<grid, kNormWarps * 32, 0, s>>>(x, mod, mod_ld, shift_col, scale_col, y_f32,     \
+  launch_pdl(adaln_layernorm_kernel<NV>, dim3(grid), dim3(kNormWarps * 32), 0, s, x, mod, mod_ld, shift_col, scale_col, y_f32,     \
                                                               (__nv_bfloat16*)y_bf16, M, (int)D,               \
                                                               tokens_per_frame, eps)
   if (D <= 256) LAUNCH(2);

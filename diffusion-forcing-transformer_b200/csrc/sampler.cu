@@ -44,6 +44,8 @@ sampler_step_hg_kernel(float* __restrict__ x, const TOut* __restrict__ model_out
                        const dfot_frame_update* __restrict__ upd, const dfot_frame_prepare* __restrict__ prep,
                        const float* __restrict__ noise_ddim, const float* __restrict__ noise_hist,
                        const float* __restrict__ noise_excl, int nfe_rt, int T, int64_t F) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int nfe = NFE > 0 ? NFE : nfe_rt;
   const int t = blockIdx.y, b = blockIdx.z;
   __shared__ dfot_frame_update s_upd[kMaxNfe];
@@ -175,7 +177,7 @@ extern "C" int dfot_sampler_step_hg(float* x, const void* model_out, int model_o
   dim3 grid((unsigned)chunks, (unsigned)T, (unsigned)B), block(kSamplerThreads);
   cudaStream_t s = (cudaStream_t)stream;
 #define LAUNCH_N(TO, TI, N)                                                                                       \
-  sampler_step_hg_kernel<TO, TI, N><<<grid, block, 0, s>>>(x, (const TO*)model_out, (TI*)model_in_next, upd, prep,  \
+  launch_pdl(sampler_step_hg_kernel<TO, TI, N>, dim3(grid), dim3(block), 0, s, x, (const TO*)model_out, (TI*)model_in_next, upd, prep,  \
                                                            noise_ddim, noise_hist, noise_excl, (int)nfe, (int)T, F)
 #define LAUNCH(TO, TI)                                                                                            \
   do {                                                                                                            \

@@ -42,6 +42,8 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
 template <typename TX>
 __global__ void __launch_bounds__(kThreads)
 gn_stats_kernel(const TX* __restrict__ x, double* __restrict__ sums, int64_t HW, int C, int G, int pix_per_block) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   __shared__ float s_sum[64], s_sq[64];
   const int vecs = C >> 3, cpg = C / G;
   const int img = blockIdx.y;
@@ -85,6 +87,8 @@ gn_stats_kernel(const TX* __restrict__ x, double* __restrict__ sums, int64_t HW,
 // per-element kernel
 __global__ void gn_finalize_kernel(const double* __restrict__ sums, float2* __restrict__ stats, int64_t n, double inv_n,
                                    float eps) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double m = sums[2 * i] * inv_n;
@@ -103,6 +107,8 @@ gn_silu_kernel(const TX* __restrict__ x, const float2* __restrict__ stats, const
                const float* __restrict__ beta, const float* __restrict__ mod_img, int64_t ld_img,
                int64_t scale_col, int64_t shift_col, const __nv_bfloat16* __restrict__ mod_pix,
                const int32_t* __restrict__ img_map, __nv_bfloat16* __restrict__ y, int HW, int C, int G) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int vecs = C >> 3, cpg = C / G;
   const int img = blockIdx.y;
   const int v = threadIdx.x % vecs, prow = threadIdx.x / vecs, pix_step = kThreads / vecs;
@@ -196,6 +202,8 @@ rmsnorm_film_kernel(const float* __restrict__ x, const float* __restrict__ weigh
                     const float* __restrict__ mod_img, int64_t ld_img, int64_t scale_col, int64_t shift_col,
                     const __nv_bfloat16* __restrict__ mod_pix, const int32_t* __restrict__ img_map,
                     __nv_bfloat16* __restrict__ y, int64_t M, int D, int64_t tokens_per_img) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * kNormWarps + warp;
   if (m >= M) return;
@@ -262,6 +270,8 @@ __global__ void __launch_bounds__(kThreads)
 qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, const float* __restrict__ qw,
                     const float* __restrict__ kw, float eps, const float* __restrict__ rope_cs,
                     int64_t tokens_per_sample, int64_t M, int heads, float q_scale) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   constexpr int LPH = DH / 8, HPI = 32 / LPH;       // lanes per head, heads per load instruction
   const int lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -326,6 +336,8 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, const float* __
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(kThreads)
 avgpool2x2_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t n_img, int H, int W, int C) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int vecs = C >> 3, Ho = H >> 1, Wo = W >> 1;
   const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (idx >= n_img * Ho * Wo * vecs) return;
@@ -347,6 +359,8 @@ avgpool2x2_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t n_img
 
 __global__ void __launch_bounds__(kThreads)
 sub_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b, __nv_bfloat16* __restrict__ out, int64_t n8) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (idx >= n8) return;
   float x[8], y[8];
@@ -361,6 +375,8 @@ sub_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b, __nv_b
 __global__ void __launch_bounds__(kThreads)
 upsample2x_add_kernel(const float* __restrict__ low, const float* __restrict__ skip, float* __restrict__ out,
                       int64_t n_img, int H, int W, int C) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int vecs = C >> 3;
   const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (idx >= n_img * H * W * vecs) return;
@@ -383,6 +399,8 @@ upsample2x_add_kernel(const float* __restrict__ low, const float* __restrict__ s
 __global__ void __launch_bounds__(kThreads)
 pose_ray_patches_kernel(const float* __restrict__ cams, const float* __restrict__ freq_scale, int n_freq,
                         __nv_bfloat16* __restrict__ out, int64_t ld, int64_t frames, int res, int p) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (idx >= frames * res * res) return;
   const int X = (int)(idx % res), Y = (int)((idx / res) % res);
@@ -423,7 +441,7 @@ int gn_zero_sums(double* sums, int64_t n_img, int64_t groups, cudaStream_t s) {
 int gn_finalize(double* sums, int64_t n_img, int64_t groups, int64_t count_per_group, float eps, cudaStream_t s) {
   float2* stats = reinterpret_cast<float2*>(sums + 2 * n_img * groups);
   const int64_t n = n_img * groups;
-  uvit::gn_finalize_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, s>>>(sums, stats, n, 1.0 / (double)count_per_group, eps);
+  launch_pdl(uvit::gn_finalize_kernel, dim3((unsigned)ceil_div(n, 128)), dim3(128), 0, s, sums, stats, n, 1.0 / (double)count_per_group, eps);
   DFOT_CHECK_LAUNCH("groupnorm_finalize");
   return DFOT_OK;
 }
@@ -450,9 +468,9 @@ extern "C" int dfot_groupnorm_stats(const void* x, int x_dtype, double* sums, in
   slabs = ceil_div(HW, ppb);
   dim3 grid((unsigned)slabs, (unsigned)n_img);
   if (x_dtype == DFOT_F32)
-    gn_stats_kernel<float><<<grid, kThreads, 0, s>>>((const float*)x, sums, HW, (int)C, (int)groups, (int)ppb);
+    launch_pdl(gn_stats_kernel<float>, dim3(grid), dim3(kThreads), 0, s, (const float*)x, sums, HW, (int)C, (int)groups, (int)ppb);
   else if (x_dtype == DFOT_BF16)
-    gn_stats_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>((const __nv_bfloat16*)x, sums, HW, (int)C, (int)groups, (int)ppb);
+    launch_pdl(gn_stats_kernel<__nv_bfloat16>, dim3(grid), dim3(kThreads), 0, s, (const __nv_bfloat16*)x, sums, HW, (int)C, (int)groups, (int)ppb);
   else
     DFOT_REQUIRE(false, DFOT_ERR_INVALID_ARG, "groupnorm_stats: x dtype must be f32 or bf16");
   DFOT_CHECK_LAUNCH("groupnorm_stats");
@@ -479,11 +497,11 @@ extern "C" int dfot_groupnorm_silu_bf16(const void* x, int x_dtype, const double
   const float2* stats = reinterpret_cast<const float2*>(sums + 2 * n_img * groups);
   const dim3 grid((unsigned)ceil_div(HW, (kThreads / vecs) * kGnPix * kGnIter), (unsigned)n_img);
   if (x_dtype == DFOT_F32)
-    gn_silu_kernel<float><<<grid, kThreads, 0, s>>>(
+    launch_pdl(gn_silu_kernel<float>, dim3(grid), dim3(kThreads), 0, s, 
         (const float*)x, stats, gamma, beta, mod_img, ld_img, scale_col, shift_col, (const __nv_bfloat16*)mod_pix,
         img_map, (__nv_bfloat16*)y_bf16, (int)HW, (int)C, (int)groups);
   else if (x_dtype == DFOT_BF16)
-    gn_silu_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(
+    launch_pdl(gn_silu_kernel<__nv_bfloat16>, dim3(grid), dim3(kThreads), 0, s, 
         (const __nv_bfloat16*)x, stats, gamma, beta, mod_img, ld_img, scale_col, shift_col,
         (const __nv_bfloat16*)mod_pix, img_map, (__nv_bfloat16*)y_bf16, (int)HW, (int)C, (int)groups);
   else
@@ -504,7 +522,7 @@ extern "C" int dfot_rmsnorm_film_bf16(const float* x, const float* weight, float
   const unsigned grid = (unsigned)ceil_div(M, kNormWarps);
   cudaStream_t s = (cudaStream_t)stream;
 #define LAUNCH(NV)                                                                                                   \
-  rmsnorm_film_kernel<NV><<<grid, kNormWarps * 32, 0, s>>>(x, weight, eps, mod_img, ld_img, scale_col, shift_col,    \
+  launch_pdl(rmsnorm_film_kernel<NV>, dim3(grid), dim3(kNormWarps * 32), 0, s, x, weight, eps, mod_img, ld_img, scale_col, shift_col,    \
                                                            (const __nv_bfloat16*)mod_pix, img_map,                   \
                                                            (__nv_bfloat16*)y_bf16, M, (int)D, tokens_per_img)
   if (D <= 128) LAUNCH(1);
@@ -535,7 +553,7 @@ extern "C" int dfot_qk_norm_rope(void* qkv, int64_t ld, const float* q_weight, c
   // NI = load instructions per token: 2*heads segments, 32/(head_dim/8) of them per instruction
   const int64_t ni = ceil_div(2 * heads * (head_dim / 8), 32);
 #define LAUNCH(DH, NI)                                                                                                 \
-  qk_norm_rope_kernel<DH, NI><<<grid, kThreads, 0, s>>>((__nv_bfloat16*)qkv, ld, q_weight, k_weight, eps, rope_cs,     \
+  launch_pdl(qk_norm_rope_kernel<DH, NI>, dim3(grid), dim3(kThreads), 0, s, (__nv_bfloat16*)qkv, ld, q_weight, k_weight, eps, rope_cs,     \
                                                         tokens_per_sample, M, (int)heads, q_scale)
   if (head_dim == 64) {
     if (ni <= 3) LAUNCH(64, 3);
@@ -560,11 +578,11 @@ extern "C" int dfot_avgpool2x2(const void* in, int in_dtype, void* out, int out_
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned grid = blocks_for(total);
   if (in_dtype == DFOT_F32 && out_dtype == DFOT_F32)
-    avgpool2x2_kernel<float, float><<<grid, kThreads, 0, s>>>((const float*)in, (float*)out, n_img, (int)H, (int)W, (int)C);
+    launch_pdl(avgpool2x2_kernel<float, float>, dim3(grid), dim3(kThreads), 0, s, (const float*)in, (float*)out, n_img, (int)H, (int)W, (int)C);
   else if (in_dtype == DFOT_F32 && out_dtype == DFOT_BF16)
-    avgpool2x2_kernel<float, __nv_bfloat16><<<grid, kThreads, 0, s>>>((const float*)in, (__nv_bfloat16*)out, n_img, (int)H, (int)W, (int)C);
+    launch_pdl(avgpool2x2_kernel<float, __nv_bfloat16>, dim3(grid), dim3(kThreads), 0, s, (const float*)in, (__nv_bfloat16*)out, n_img, (int)H, (int)W, (int)C);
   else if (in_dtype == DFOT_BF16 && out_dtype == DFOT_BF16)
-    avgpool2x2_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kThreads, 0, s>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, n_img, (int)H, (int)W, (int)C);
+    launch_pdl(avgpool2x2_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(grid), dim3(kThreads), 0, s, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, n_img, (int)H, (int)W, (int)C);
   else
     DFOT_REQUIRE(false, DFOT_ERR_INVALID_ARG, "avgpool2x2: unsupported dtype combination");
   DFOT_CHECK_LAUNCH("avgpool2x2");
@@ -574,7 +592,7 @@ extern "C" int dfot_avgpool2x2(const void* in, int in_dtype, void* out, int out_
 extern "C" int dfot_sub_bf16(const float* a, const float* b, void* out_bf16, int64_t n, void* stream) {
   DFOT_REQUIRE(a && b && out_bf16 && n > 0, DFOT_ERR_INVALID_ARG, "sub_bf16: bad arguments");
   DFOT_REQUIRE(n % 8 == 0, DFOT_ERR_UNSUPPORTED, "sub_bf16: n must be a multiple of 8");
-  sub_bf16_kernel<<<blocks_for(n / 8), kThreads, 0, (cudaStream_t)stream>>>(a, b, (__nv_bfloat16*)out_bf16, n / 8);
+  launch_pdl(sub_bf16_kernel, dim3(blocks_for(n / 8)), dim3(kThreads), 0, (cudaStream_t)stream, a, b, (__nv_bfloat16*)out_bf16, n / 8);
   DFOT_CHECK_LAUNCH("sub_bf16");
   return DFOT_OK;
 }
@@ -583,7 +601,7 @@ extern "C" int dfot_upsample2x_add(const float* low, const float* skip, float* o
                                    int64_t C, void* stream) {
   DFOT_REQUIRE(low && skip && out && n_img > 0 && H > 0 && W > 0 && C > 0, DFOT_ERR_INVALID_ARG, "upsample2x_add: bad arguments");
   DFOT_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, DFOT_ERR_UNSUPPORTED, "upsample2x_add: H, W even and C %% 8 == 0");
-  upsample2x_add_kernel<<<blocks_for(n_img * H * W * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+  launch_pdl(upsample2x_add_kernel, dim3(blocks_for(n_img * H * W * (C / 8))), dim3(kThreads), 0, (cudaStream_t)stream, 
       low, skip, out, n_img, (int)H, (int)W, (int)C);
   DFOT_CHECK_LAUNCH("upsample2x_add");
   return DFOT_OK;
@@ -594,7 +612,7 @@ extern "C" int dfot_pose_ray_patches(const float* cams, const float* freq_scale,
   DFOT_REQUIRE(cams && freq_scale && out_bf16 && n_freq > 0 && frames > 0 && res > 0 && p > 0, DFOT_ERR_INVALID_ARG,
                "pose_ray_patches: bad arguments");
   DFOT_REQUIRE(res % p == 0 && ld >= p * p * 12 * n_freq, DFOT_ERR_INVALID_ARG, "pose_ray_patches: res %% p, ld");
-  pose_ray_patches_kernel<<<blocks_for(frames * res * res), kThreads, 0, (cudaStream_t)stream>>>(
+  launch_pdl(pose_ray_patches_kernel, dim3(blocks_for(frames * res * res)), dim3(kThreads), 0, (cudaStream_t)stream, 
       cams, freq_scale, (int)n_freq, (__nv_bfloat16*)out_bf16, ld, frames, (int)res, (int)p);
   DFOT_CHECK_LAUNCH("pose_ray_patches");
   return DFOT_OK;
