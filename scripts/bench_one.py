@@ -65,6 +65,24 @@ elif which == "sampler":  # K4 at the RE10K shape: B=4, nfe=2, T=8, 3x256x256
     prep["noise_row"] = np.arange(B * nfe)[:, None] // nfe
     ud, pd = sp.to_device_bytes(upd, DEV), sp.to_device_bytes(prep, DEV)
     fn = lambda: ops.sampler_step_hg(x, mo, mi, ud, pd, None, nh, None, B, nfe, T)
+elif which == "rmsnorm":  # level-2 RMSNorm + FiLM with the per-pixel pose part on half of the images: M = 65536, D = 576
+    g, D = 32, 576
+    M = 64 * g * g
+    x = torch.randn((M, D), device=DEV)
+    w = torch.randn((D,), device=DEV)
+    mi = torch.randn((64, 4 * D), device=DEV)
+    mp = torch.randn((32 * g * g, 2 * D), device=DEV).to(torch.bfloat16)
+    o = torch.empty((M, D), device=DEV, dtype=torch.bfloat16)
+    img_map = torch.tensor([(-1 if i % 16 < 8 else (i // 16) * 8 + i % 8) for i in range(64)], dtype=torch.int32, device=DEV)
+    fn = lambda: ops.rmsnorm_film_bf16(x, w, mi, 0, D, g * g, o, mod_pix=mp, img_map=img_map)
+elif which == "qknorm":   # level-2 q/k RMSNorm(head_dim 64) + RoPE-3D in place: M = 65536 tokens, 9 heads
+    heads, dh, T, g = 9, 64, 8, 32
+    D, Ntok = heads * dh, T * g * g
+    M = 8 * Ntok
+    qkv = torch.randn((M, 3 * D), device=DEV).to(torch.bfloat16)
+    qw, kw = torch.randn((dh,), device=DEV), torch.randn((dh,), device=DEV)
+    table = torch.randn((Ntok, dh // 2, 2), device=DEV)
+    fn = lambda: ops.qk_norm_rope(qkv, qw, kw, table, Ntok, heads, dh, 0.18)
 else:
     raise SystemExit(f"unknown kernel {which}")
 for _ in range(2):

@@ -19,6 +19,8 @@ prof gemm "gemm2?_bf16" python scripts/bench_one.py gemm 3
 prof gemm_l2 "gemm2?_bf16" python scripts/bench_one.py gemm_l2 3
 prof gn_silu gn_silu python scripts/bench_one.py gn_silu 3
 prof sampler sampler python scripts/bench_one.py sampler 3
+prof rmsnorm rmsnorm_film python scripts/bench_one.py rmsnorm 3
+prof qknorm qk_norm_rope python scripts/bench_one.py qknorm 3
 [ -n "${ONLY:-}" ] && exit 0
 python scripts/profile_forward.py 4 2 > gpurun_out/fwd_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_re10k.csv python scripts/profile_forward.py 4 2 > gpurun_out/ncu_launch.log 2>&1
