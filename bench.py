@@ -64,6 +64,28 @@ def k600_cfg(sampling_timesteps=50, spatial_mlp_ratio=4.0, depth=28, hidden=1152
                      metrics=[], metrics_batch_size=16, sanity_generation=False, raw_dir=None))
 
 
+def dmlab_cfg(sampling_timesteps=50, frames=36, guidance_scale=None):
+    """`dataset=dmlab algorithm=dfot_video @diffusion/continuous @DiT/B dataset.max_frames=T` (BASELINE config[4]) resolved
+    by hand: dmlab.yaml (latents 32 ch, 64 px / 8 -> [32, 8, 8]; action dim 3 stacked over frame_skip 1, mask_first),
+    dmlab_video_generation.yaml (patch 2, external_cond_dropout 0.1, sigmoid weighting, shifted cosine 0.125),
+    shortcut/DiT/B.yaml (768 x 12, 12 heads), shortcut/diffusion/continuous.yaml; context_length 4 (base_video.yaml)."""
+    cfg = k600_cfg(sampling_timesteps, 4.0, depth=12, hidden=768, heads=12)
+    cfg.update(external_cond_type="action", external_cond_dim=3, external_cond_stack=True,
+               external_cond_processing="mask_first", x_shape=[3, 64, 64], max_frames=frames, n_frames=frames,
+               context_frames=4, data_mean=[[[0.0]]] * 32, data_std=[[[3.46140533056]]] * 32,
+               latent=dict(enabled=True, type="pre_sample", suffix=None, downsampling_factor=[1, 8], shape=None,
+                           num_channels=32))
+    cfg["backbone"].update(patch_size=2, external_cond_dropout=0.1)
+    cfg["diffusion"].update(is_continuous=True, precond_scale=0.125, beta_schedule="cosine_simple_diffusion",
+                            schedule_fn_kwargs=dict(shifted=0.125, interpolated=False),
+                            training_schedule=dict(name="cosine", shift=0.125),
+                            loss_weighting=dict(strategy="sigmoid", sigmoid_bias=-1.0))
+    if guidance_scale:
+        cfg["tasks"]["prediction"]["history_guidance"] = dict(name="vanilla", guidance_scale=guidance_scale,
+                                                              visualize=False)
+    return cfg
+
+
 def re10k_cfg(sampling_timesteps=50, guidance_scale=4.0):
     """`dataset=realestate10k_mini algorithm=dfot_video_pose @diffusion/continuous dataset.context_length=1
     dataset.n_frames=8 ...history_guidance.name=vanilla +guidance_scale=4.0` (README.md:74) resolved by hand from
@@ -105,6 +127,19 @@ class Workload:
                          f"17 frames = 5 tokens (2 context), {args.sampling_steps} DDIM steps, conditional HG (nfe=1), "
                          f"batch {self.batch}/GPU")
             self.l2 = "per-step activations (~0.5 GB) and weights (1.3 GB bf16) exceed the 126 MB L2; no flush needed"
+        elif name == "dmlab":
+            T = args.frames or 36
+            hg = args.guidance or 0.0
+            self.cfg = dmlab_cfg(args.sampling_steps, T, hg if hg > 1.0 else None)
+            self.batch = args.batch or 16
+            self.n_tokens, self.ctx_tokens, self.gen_frames, self.nfe = T, 4, T - 4, 2 if hg > 1.0 else 1
+            self.x_shape = [32, 8, 8]
+            self.text = (f"DMLab-shaped long-context DFoT DiT3D-B (12x768, 12 heads d=64, patch 2, MLP x4), continuous "
+                         f"diffusion, latents 32x8x8, {T} frames = {T * 16} tokens (4 context), action conditioning "
+                         f"(mask_first), {args.sampling_steps} DDIM steps, "
+                         f"{'vanilla HG %.1f (nfe=2)' % hg if hg > 1.0 else 'conditional HG (nfe=1)'}, batch {self.batch}/GPU")
+            self.l2 = ("small model (170 MB of bf16 weights): activations of a step fit the 126 MB L2 at small batch; "
+                       "256 MiB of HBM are overwritten between timed passes to flush it")
         elif name == "re10k_long":
             # README.md:69 "Single Image to Long Video (200 Frames)" = BASELINE config[3]
             self.cfg = re10k_cfg(args.sampling_steps)
@@ -142,6 +177,9 @@ class Workload:
         g = torch.Generator().manual_seed(123 + rank)
         if self.name == "k600":
             return torch.randn((self.batch, self.n_tokens, *self.x_shape), generator=g), None
+        if self.name == "dmlab":
+            return (torch.randn((self.batch, self.n_tokens, *self.x_shape), generator=g),
+                    torch.randn((self.batch, self.n_tokens, 3), generator=g))
         xs = torch.rand((self.batch, self.n_tokens, *self.x_shape), generator=g)
         return xs, synthetic_poses(self.batch, self.n_tokens)
 
@@ -152,9 +190,9 @@ class Workload:
         camera-pose PatchEmbed and pose part of every emb_layer are constant per window and NOT counted (the
         reference executes them every step: 6626 GFLOP/row there)."""
         b = self.cfg["backbone"]
-        if self.name == "k600":
+        if self.name in ("k600", "dmlab"):
             D, depth, r = b["hidden_size"], b["depth"], b.get("spatial_mlp_ratio") or 0
-            N = self.n_tokens * (16 // b["patch_size"]) ** 2
+            N = self.n_tokens * (self.x_shape[1] // b["patch_size"]) ** 2
             return depth * N * (8 * D * D + 4 * N * D + 4 * r * D * D) / 1e9
         T, ch, L = self.cfg["max_frames"], b["channels"], len(b["channels"])
         res = [self.x_shape[1] // b["patch_size"] // 2 ** i for i in range(L)]
@@ -268,15 +306,16 @@ def cpu_baseline(wl, sampling_steps, seconds_budget=25.0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     cfg = json.loads(json.dumps(wl.cfg))
-    n_steps = 2 if wl.name == "k600" else 1
+    n_steps = 2 if wl.name in ("k600", "dmlab") else 1
     cfg["diffusion"]["sampling_timesteps"] = n_steps
     algo = make_weights(cfg, 0)
     weights = {k[len("diffusion_model.model."):]: v.detach() for k, v in algo.state_dict().items()
                if k.startswith("diffusion_model.model.")}
     probe = SamplerOracle(cfg, None)
-    if wl.name == "k600":
+    if wl.name in ("k600", "dmlab"):
         from oracle.dit3d import DiT3DOracle
-        model = DiT3DOracle(cfg["backbone"], probe.x_shape, probe.max_tokens, weights)
+        model = DiT3DOracle(cfg["backbone"], probe.x_shape, probe.max_tokens, weights,
+                            external_cond_dim=probe.external_cond_dim)
     else:
         from oracle.uvit3d_pose import UViT3DPoseOracle
         model = UViT3DPoseOracle(cfg["backbone"], probe.x_shape, probe.max_tokens, weights)
@@ -311,7 +350,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dfot_b200", choices=["dfot_b200", "reference"])
     ap.add_argument("--no-mlp", action="store_true", help="fork default: spatial_mlp_ratio unset (no MLP blocks)")
-    ap.add_argument("--workload", default="re10k", choices=["re10k", "k600", "re10k_long"])
+    ap.add_argument("--workload", default="re10k", choices=["re10k", "k600", "re10k_long", "dmlab"])
+    ap.add_argument("--frames", type=int, default=None, help="dmlab: context window length T (16 / 36 / 72 / 144)")
+    ap.add_argument("--guidance", type=float, default=None, help="dmlab: vanilla history-guidance scale (> 1: nfe = 2)")
     ap.add_argument("--batch", type=int, default=0, help="samples per GPU (default: 4 for re10k, 8 for k600)")
     ap.add_argument("--sampling-steps", type=int, default=50)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -355,7 +396,7 @@ def main():
     if strong and world > 1:
         from dfot_b200 import distributed as D
         algo.mesh = D.build_mesh(br=br)
-    if wl.name != "k600":
+    if wl.name.startswith("re10k"):
         xs_host = algo._normalize_x(xs_host.to(dev)).cpu()      # dataset-normalised pixels, as on_after_batch_transfer
     xs_host = xs_host.pin_memory()
     conds_host = None if conds_host is None else conds_host.pin_memory()
@@ -387,11 +428,16 @@ def main():
             dist.all_gather(gathered, vids.contiguous())
         return vids.to("cpu")
 
+    # small-model workload: its per-step working set can sit in the 126 MB L2, so 256 MiB are overwritten between passes
+    flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev) if wl.name == "dmlab" else None
+
     def timed(fn, steps):
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for _ in range(steps):
+            if flush is not None:
+                flush.zero_()
             fn()
         ev1.record()
         barrier()
@@ -470,8 +516,8 @@ def main():
                 traffic = json.load(f)["launches"]
         except Exception:
             pass
-        t_gemm = traffic.get("gemm_level3_qkv_16384x3456x1152_bf16" if wl.name != "k600" else "", {}).get("dram_bytes")
-        t_attn = traffic.get("attention_level2_d64_N8192_R8" if wl.name != "k600" else "", {}).get("dram_bytes")
+        t_gemm = traffic.get("gemm_level3_qkv_16384x3456x1152_bf16" if wl.name.startswith("re10k") else "", {}).get("dram_bytes")
+        t_attn = traffic.get("attention_level2_d64_N8192_R8" if wl.name.startswith("re10k") else "", {}).get("dram_bytes")
         ach = flops / (dur * 1e-3) / 1e12
         roof = dict(bound="tensor", kernel="gemm2_bf16_tcgen05_kernel (CTA pair) + gemm_bf16_tcgen05_kernel", achieved=ach, peak=peak, unit="TFLOP/s",
                     frac=ach / peak, traffic=t_gemm, launches=len(big), avg_launch_us=1e3 * dur / max(len(big), 1),
