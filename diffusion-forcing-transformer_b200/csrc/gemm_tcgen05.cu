@@ -410,12 +410,18 @@ __device__ __forceinline__ void epilogue_rows_f32(const Params& p, const ChunkSi
   float* out = reinterpret_cast<float*>(p.C) + (int64_t)(m0 + rsub) * p.ldc + col;
   const int64_t step = 4 * p.ldc;
   float4 gate0 = make_float4(0.f, 0.f, 0.f, 0.f), gate1 = gate0;
-  int split = 32;  // rows [0, split) belong to frame f0, the rest to f0 + 1 (tokens_per_frame >= 32, host-checked)
+  // tokens_per_frame >= 32: rows [0, split) of the chunk belong to frame f0, the rest to f0 + 1 — two gate vectors per
+  // lane.  Smaller frames (8x8 latents with patch 2: 16 tokens, the DMLab / Minecraft DiT configurations): a chunk spans
+  // several frames and every row looks its (L1-resident) gate vector up.
+  int split = 32, P = 1, f0 = 0, rem0 = 0;
+  bool small_frames = false;     // warp-uniform
   if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) {
-    const int P = (int)p.e.tokens_per_frame;
-    const int f0 = m0 / P;
+    P = (int)p.e.tokens_per_frame;
+    f0 = m0 / P;
+    rem0 = m0 - f0 * P;
+    small_frames = P < 32;
     split = min(32, (f0 + 1) * P - m0);
-    if (col_ok) {
+    if (col_ok && !small_frames) {
       gate0 = __ldg(reinterpret_cast<const float4*>(p.e.gate + (int64_t)f0 * p.e.ld_gate + col));
       if (split < 32) gate1 = __ldg(reinterpret_cast<const float4*>(p.e.gate + (int64_t)(f0 + 1) * p.e.ld_gate + col));
     }
@@ -428,7 +434,9 @@ __device__ __forceinline__ void epilogue_rows_f32(const Params& p, const ChunkSi
     float4 y = lds_f32x4(stage + (uint32_t)i * 128u + (uint32_t)((cq ^ (i & 7)) << 4));
     y.x += bias.x; y.y += bias.y; y.z += bias.z; y.w += bias.w;
     if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) {
-      const float4 g = i < split ? gate0 : gate1;
+      float4 g = i < split ? gate0 : gate1;
+      if (small_frames && col_ok && (FULL || i < rows))
+        g = __ldg(reinterpret_cast<const float4*>(p.e.gate + (int64_t)(f0 + (rem0 + i) / P) * p.e.ld_gate + col));
       y.x = fmaf(g.x, y.x, sd.r[it].x); y.y = fmaf(g.y, y.y, sd.r[it].y);
       y.z = fmaf(g.z, y.z, sd.r[it].z); y.w = fmaf(g.w, y.w, sd.r[it].w);
     }
@@ -609,39 +617,9 @@ __device__ __forceinline__ void epilogue_head_qknorm(const Params& p, uint32_t t
   }
 }
 
-// GATE_RESID with fewer than 32 tokens per frame (small latent grids, e.g. 8x8 latents with patch 2): a chunk spans
-// several frames, so the gate is looked up per row.  Not a performance path (tiny models), kept simple.
-__device__ __noinline__ void epilogue_rows_gate_small_frames(const Params& p, uint32_t stage, int lane, int m0, int n0) {
-  const int col = n0 + lane;
-  if (col >= p.N) return;
-  const float bias = p.e.bias != nullptr ? __ldg(p.e.bias + col) : 0.f;
-  const int rows = min(32, p.M - m0);
-  const int P = (int)p.e.tokens_per_frame;
-  const uint32_t sbase = stage + (uint32_t)((lane & 3) << 2);
-  float* out = reinterpret_cast<float*>(p.C);
-#pragma unroll 1
-  for (int i = 0; i < rows; ++i) {
-    const int m = m0 + i;
-    const float acc = lds_f32(sbase + (uint32_t)i * 128u + (uint32_t)((((lane >> 2) ^ (i & 7))) << 4));
-    const float g = __ldg(p.e.gate + (int64_t)(m / P) * p.e.ld_gate + col);
-    out[(int64_t)m * p.ldc + col] = __ldg(p.e.resid + (int64_t)m * p.e.ld_resid + col) + g * (acc + bias);
-  }
-}
-
 template <int EPI, bool FULL>
 __device__ __forceinline__ void epilogue_chunk(const Params& p, uint32_t t_addr, uint32_t stage_buf, int lane, int m0,
                                                int n0) {
-  if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) {
-    if (p.e.tokens_per_frame < 32) {   // warp-uniform
-      uint32_t r[32];
-      tmem_ld_x32(t_addr, r);
-      stage_chunk(stage_buf, lane, r);
-      __syncwarp();
-      epilogue_rows_gate_small_frames(p, stage_buf, lane, m0, n0);
-      __syncwarp();
-      return;
-    }
-  }
   ChunkSide<EPI> side;
   prefetch_side<EPI, FULL>(p, side, lane, m0, n0);   // loads overlap the TMEM read + transpose below
   uint32_t r[32];
@@ -1237,7 +1215,7 @@ extern "C" int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   if (epilogue == DFOT_EPI_GATE_RESID_F32)
     DFOT_REQUIRE(epi->resid && epi->gate && epi->tokens_per_frame >= 1 && epi->tokens_per_frame < (1ll << 30),
                  DFOT_ERR_INVALID_ARG, "gemm: GATE_RESID needs resid, gate and tokens_per_frame");
-  if (epilogue == DFOT_EPI_GATE_RESID_F32 && epi->tokens_per_frame >= 32)
+  if (epilogue == DFOT_EPI_GATE_RESID_F32)
     DFOT_REQUIRE((uintptr_t)epi->gate % 16 == 0 && epi->ld_gate % 4 == 0, DFOT_ERR_UNSUPPORTED,
                  "gemm: gate must be 16-byte aligned with ld_gate %% 4 == 0");
   if (epilogue == DFOT_EPI_GATE_RESID_F32 || epilogue == DFOT_EPI_RESID_F32)

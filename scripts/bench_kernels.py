@@ -81,6 +81,33 @@ def bench_norm(iters):
         print(f"adaln_layernorm M={M} D={D} (bf16 out):     {us:7.1f} us  {M * D * 6 / us / 1e3:7.1f} GB/s")
 
 
+def bench_gemm_ditb(iters):
+    """DiT-B (DMLab) block GEMMs: D = 768, 12 heads of 64, 16 tokens per frame, M = rows x frames x 16 tokens."""
+    D, P = 768, 16
+    for M in (36864, 147456):
+        for name, N, K, epi in [("qkv+rope", 3 * D, D, ops.EPI_QKV_ROPE_BF16), ("qkv plain", 3 * D, D, ops.EPI_BF16),
+                                ("proj+gate", D, D, ops.EPI_GATE_RESID_F32), ("proj plain f32", D, D, ops.EPI_F32),
+                                ("fc1+gelu", 4 * D, D, ops.EPI_GELU_BF16), ("fc1 plain", 4 * D, D, ops.EPI_BF16),
+                                ("fc2+gate", D, 4 * D, ops.EPI_GATE_RESID_F32), ("fc2 plain f32", D, 4 * D, ops.EPI_F32)]:
+            a = torch.randn((M, K), device=DEV).to(torch.bfloat16)
+            w = (torch.randn((N, K), device=DEV) / math.sqrt(K)).to(torch.bfloat16)
+            kw = dict(bias=torch.randn((N,), device=DEV))
+            if epi == ops.EPI_GATE_RESID_F32:
+                out = torch.empty((M, N), device=DEV)
+                mod = torch.randn((M // P, 3 * N), device=DEV)
+                kw.update(resid=torch.randn((M, N), device=DEV), gate=mod[:, 2 * N:], ld_gate=3 * N, tokens_per_frame=P)
+            elif epi == ops.EPI_QKV_ROPE_BF16:
+                out = torch.empty((M, N), device=DEV, dtype=torch.bfloat16)
+                kw.update(rope_cs=torch.randn((2304, 32, 2), device=DEV), tokens_per_sample=2304, model_dim=D, head_dim=64,
+                          q_scale=0.18)
+            elif epi == ops.EPI_F32:
+                out = torch.empty((M, N), device=DEV)
+            else:
+                out = torch.empty((M, N), device=DEV, dtype=torch.bfloat16)
+            us = timeit(lambda: ops.gemm_bf16(a, w, out, epi, **kw), iters)
+            print(f"gemm {name:16s} M={M} N={N} K={K}: {us:8.1f} us  {2.0 * M * N * K / us / 1e6:7.1f} TFLOP/s")
+
+
 def bench_sampler(iters):
     """K4 (fused DDIM update + history-guidance combine + next-step inputs): algorithmic bytes per element =
     nfe*4 (model out f32) + 4 (x_t) + 4 (x_t+1) + nfe*2 (bf16 inputs) + 4 (history noise)."""
@@ -201,6 +228,8 @@ if __name__ == "__main__":
         bench_gemm(a.iters)
     if a.which in ("norm", "all"):
         bench_norm(a.iters)
+    if a.which in ("gemm_ditb",):
+        bench_gemm_ditb(a.iters)
     if a.which in ("sampler", "all"):
         bench_sampler(a.iters)
     if a.which in ("uvit", "all"):

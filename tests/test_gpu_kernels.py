@@ -46,9 +46,11 @@ def test_gemm_bias_f32_and_bf16(M, N, K):
     assert rel_err(out16, ref) < 5e-3
 
 
-@pytest.mark.parametrize("P", [64, 16, 40])
-def test_gemm_activations_and_gate_residual(P):
-    M, N, K = 640, 1152, 256
+@pytest.mark.parametrize("P,M", [(64, 640), (16, 640), (40, 640), (4, 640), (20, 640), (8, 600), (16, 20480), (48, 18432)])
+def test_gemm_activations_and_gate_residual(P, M):
+    """(incl. frames smaller than a 32-row epilogue chunk — 16 tokens per frame are the DMLab / Minecraft DiT shapes —
+    ragged M, and sizes that take the CTA-pair kernel)"""
+    N, K = 1152, 256
     g = torch.Generator().manual_seed(5)
     a = torch.randn((M, K), generator=g).to(DEV).to(torch.bfloat16)
     w = (torch.randn((N, K), generator=g) / math.sqrt(K)).to(DEV).to(torch.bfloat16)
