@@ -1164,12 +1164,27 @@ static int gn_end(const Params& p, cudaStream_t s) {
 // Tile width: the widest tile unless 192 columns (3 x 64, a valid UMMA N) leave at least 15 % fewer padded columns —
 // e.g. N = 576 = 3 x 192 instead of 3 x 256 (measured: 225 -> 205 us at K = 2880).  A 10 % saving (N = 1152) does not
 // pay for the narrower tile's worse operand-bandwidth ratio at large K (measured: 103 -> 113 us at K = 4608).
-static int pick_bn(int64_t N, int epilogue) {
+static int pick_bn(int64_t M, int64_t N, int epilogue) {
   if (N <= 64) return 64;
-  if (N <= 128) return 128;
   if (epilogue == DFOT_EPI_QKNORM_ROPE_BF16) return 256;
-  const int64_t pad256 = ceil_div(N, 256) * 256, pad192 = ceil_div(N, 192) * 192;
-  return (pad192 * 100 <= pad256 * 85) ? 192 : 256;
+  int bn = 128;
+  if (N > 128) {
+    const int64_t pad256 = ceil_div(N, 256) * 256, pad192 = ceil_div(N, 192) * 192;
+    bn = (pad192 * 100 <= pad256 * 85) ? 192 : 256;
+  }
+  // latency regime (small batches: fewer tiles than SMs): narrower tiles spread the problem over more SMs and shorten
+  // every CTA's serial k-loop.  Time model per wave: MMA time proportional to the tile width plus a fixed per-tile cost
+  // (pipeline fill, epilogue tail) worth about 64 columns; the width with the fewest wave-units wins.
+  const int64_t m_tiles = ceil_div(M, BM), sms = num_sms();
+  if (m_tiles * ceil_div(N, bn) < sms) {
+    int64_t best = ceil_div(m_tiles * ceil_div(N, bn), sms) * (bn + 64);
+    for (int cand : {192, 128, 64}) {
+      if (cand >= bn) continue;
+      const int64_t t = ceil_div(m_tiles * ceil_div(N, cand), sms) * (cand + 64);
+      if (t < best) { best = t; bn = cand; }
+    }
+  }
+  return bn;
 }
 
 template <int BN>
@@ -1247,7 +1262,7 @@ extern "C" int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
     if (!rc) rc = dispatch_pair_bn(pbn, epilogue, ta, tb, p, s);
     return rc ? rc : gn_end(p, s);
   }
-  const int bn = pick_bn(N, epilogue);
+  const int bn = pick_bn(M, N, epilogue);
   if (bn == 256) {
     rc = make_tmap(&tb, W, N, K, ldw, 256);
     if (!rc) rc = dispatch_epi<256>(epilogue, ta, tb, p, s);
@@ -1321,7 +1336,7 @@ extern "C" int dfot_conv3x3_bf16(const void* x, const void* w, void* out, int64_
   }
   const int pbn = pick_pair_bn(n_img * H * W, Cout, epilogue);
   const bool pair = pbn != 0;
-  const int bnt = pair ? pbn / 2 : pick_bn(Cout, epilogue);
+  const int bnt = pair ? pbn / 2 : pick_bn(n_img * H * W, Cout, epilogue);
   {
     cuuint64_t gdim[3] = {(cuuint64_t)Cin, 9, (cuuint64_t)Cout};
     cuuint64_t gstr[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)9 * Cin * 2};
