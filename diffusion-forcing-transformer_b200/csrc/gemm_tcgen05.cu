@@ -45,6 +45,7 @@ struct Params {
   // the convolution's zero padding.
   int conv_cblks;   // ceil(Cin / 64)
   int conv_W, conv_H;
+  int conv_taps;    // 9 (3x3) or 9*kt (causal kt x 3 x 3 over a frame axis: tap / 9 = frame offset of the TMA box)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -656,7 +657,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
-  const int num_kb = p.conv_cblks > 0 ? 9 * p.conv_cblks : (p.K + BK - 1) / BK;
+  const int num_kb = p.conv_cblks > 0 ? p.conv_taps * p.conv_cblks : (p.K + BK - 1) / BK;
   // banded rasterisation: consecutive tiles walk the n-blocks of a band of kRasterBand m-blocks, so the CTAs
   // resident at any time share a small set of A and W tiles in L2
   auto tile_coord = [&](int tile, int& m_blk, int& n_blk) {
@@ -715,8 +716,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
             mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_expect_tx(full_bar(stage), C::kStageBytes);
             const uint32_t sa = smem_base + stage * C::kStageBytes;
-            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-            tma_load_4d(sa, &tma_a, full_bar(stage), cb * BK, x0 + dx, y0 + dy, img0);
+            const int dt = tap / 9, sp = tap - dt * 9;
+            const int dy = sp / 3 - 1, dx = sp - (sp / 3) * 3 - 1;
+            tma_load_4d(sa, &tma_a, full_bar(stage), cb * BK, x0 + dx, y0 + dy, img0 + dt);
             tma_load_3d(sa + C::kStageBytesA, &tma_b, full_bar(stage), cb * BK, tap, n_blk * BN);
             if (++cb == p.conv_cblks) { cb = 0; ++tap; }
             if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
@@ -854,7 +856,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int num_m = (p.M + 2 * BM - 1) / (2 * BM), num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
-  const int num_kb = p.conv_cblks > 0 ? 9 * p.conv_cblks : (p.K + BK - 1) / BK;
+  const int num_kb = p.conv_cblks > 0 ? p.conv_taps * p.conv_cblks : (p.K + BK - 1) / BK;
   auto tile_coord = [&](int tile, int& m_blk, int& n_blk) {   // banded rasterisation (bands of 8 pair-rows = 2048 rows)
     constexpr int kBand = kRasterBand / 2;
     const int band_tiles = kBand * num_n;
@@ -906,8 +908,9 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
             tma2_load_2d(sa, &tma_a, full_bar(stage), kb * BK, m0);
             tma2_load_2d(sa + C::kStageBytesA, &tma_b, full_bar(stage), kb * BK, nb0);
           } else {
-            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-            tma2_load_4d(sa, &tma_a, full_bar(stage), cb * BK, x0 + dx, y0 + dy, img0);
+            const int dt = tap / 9, sp = tap - dt * 9;
+            const int dy = sp / 3 - 1, dx = sp - (sp / 3) * 3 - 1;
+            tma2_load_4d(sa, &tma_a, full_bar(stage), cb * BK, x0 + dx, y0 + dy, img0 + dt);
             tma2_load_3d(sa + C::kStageBytesA, &tma_b, full_bar(stage), cb * BK, tap, nb0);
             if (++cb == p.conv_cblks) { cb = 0; ++tap; }
           }
@@ -1251,7 +1254,7 @@ extern "C" int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
                  DFOT_ERR_INVALID_ARG, "gemm: QKV_ROPE needs rope table, tokens_per_sample, head_dim | model_dim, N=3D");
   Params p;
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.C = Cout; p.ldc = ldc; p.e = *epi;
-  p.conv_cblks = 0; p.conv_W = p.conv_H = 1;
+  p.conv_cblks = 0; p.conv_W = p.conv_H = 1; p.conv_taps = 9;
   CUtensorMap ta, tb;
   int rc = make_tmap(&ta, A, M, K, lda, BM);
   if (rc) return rc;
@@ -1282,12 +1285,15 @@ extern "C" int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
 // 3x3 convolution, stride 1, zero padding 1, over NHWC bf16 activations as an implicit GEMM on the same kernel:
 // M = n_img*H*W pixels, N = Cout, K = 9*Cin.  No im2col buffer exists: tap (dy, dx) of a pixel tile is the tile's
 // TMA box moved by (dy, dx); rows/columns that fall outside the image are zero-filled by the TMA unit.
-extern "C" int dfot_conv3x3_bf16(const void* x, const void* w, void* out, int64_t ldc, int64_t n_img, int64_t H,
-                                 int64_t W, int64_t Cin, int64_t Cout, int epilogue, const dfot_gemm_epilogue* epi,
-                                 void* stream) {
+// kt = 1: 3x3 convolution of n_img images.  kt > 1: "causal" kt x 3 x 3 convolution along a frame axis — x holds
+// n_img + kt - 1 frames and output frame j = sum over dt < kt of conv3x3(x[j + dt], w[:, dt]); the caller lays the frames
+// out so that x[j .. j + kt - 1] are frame j's causal window (first frame repeated in front, see dfot_b200.h).
+static int conv_impl(const void* x, const void* w, void* out, int64_t ldc, int64_t n_img, int64_t H, int64_t W,
+                     int64_t Cin, int64_t Cout, int64_t kt, int epilogue, const dfot_gemm_epilogue* epi, void* stream) {
   using namespace dfot;
   using namespace dfot::gemm;
   DFOT_REQUIRE(x && w && out && epi, DFOT_ERR_INVALID_ARG, "conv3x3: null pointer");
+  DFOT_REQUIRE(kt >= 1 && kt <= 7, DFOT_ERR_INVALID_ARG, "conv3d: temporal kernel size %lld not in [1, 7]", (long long)kt);
   DFOT_REQUIRE(n_img > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && n_img * H * W < (1ll << 31),
                DFOT_ERR_INVALID_ARG, "conv3x3: bad sizes");
   DFOT_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0 && ldc % 8 == 0 && ldc >= Cout, DFOT_ERR_UNSUPPORTED,
@@ -1324,11 +1330,11 @@ extern "C" int dfot_conv3x3_bf16(const void* x, const void* w, void* out, int64_
     }
   }
   Params p;
-  p.M = (int)(n_img * H * W); p.N = (int)Cout; p.K = (int)(9 * Cin); p.C = out; p.ldc = ldc; p.e = *epi;
-  p.conv_cblks = (int)ceil_div(Cin, BK); p.conv_W = (int)W; p.conv_H = (int)H;
+  p.M = (int)(n_img * H * W); p.N = (int)Cout; p.K = (int)(9 * kt * Cin); p.C = out; p.ldc = ldc; p.e = *epi;
+  p.conv_cblks = (int)ceil_div(Cin, BK); p.conv_W = (int)W; p.conv_H = (int)H; p.conv_taps = (int)(9 * kt);
   CUtensorMap ta, tb;
   {
-    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
+    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(n_img + kt - 1)};
     cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
     cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
     int rc = make_tmap_nd(&ta, x, 4, gdim, gstr, box);
@@ -1338,8 +1344,8 @@ extern "C" int dfot_conv3x3_bf16(const void* x, const void* w, void* out, int64_
   const bool pair = pbn != 0;
   const int bnt = pair ? pbn / 2 : pick_bn(n_img * H * W, Cout, epilogue);
   {
-    cuuint64_t gdim[3] = {(cuuint64_t)Cin, 9, (cuuint64_t)Cout};
-    cuuint64_t gstr[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)9 * Cin * 2};
+    cuuint64_t gdim[3] = {(cuuint64_t)Cin, (cuuint64_t)(9 * kt), (cuuint64_t)Cout};
+    cuuint64_t gstr[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)(9 * kt) * Cin * 2};
     cuuint32_t box[3] = {(cuuint32_t)BK, 1, (cuuint32_t)bnt};
     int rc = make_tmap_nd(&tb, w, 3, gdim, gstr, box);
     if (rc) return rc;
@@ -1353,4 +1359,16 @@ extern "C" int dfot_conv3x3_bf16(const void* x, const void* w, void* out, int64_
   else if (bnt == 128) rc = dispatch_epi<128>(epilogue, ta, tb, p, s);
   else rc = dispatch_epi<64>(epilogue, ta, tb, p, s);
   return rc ? rc : gn_end(p, s);
+}
+
+extern "C" int dfot_conv3x3_bf16(const void* x, const void* w, void* out, int64_t ldc, int64_t n_img, int64_t H,
+                                 int64_t W, int64_t Cin, int64_t Cout, int epilogue, const dfot_gemm_epilogue* epi,
+                                 void* stream) {
+  return conv_impl(x, w, out, ldc, n_img, H, W, Cin, Cout, 1, epilogue, epi, stream);
+}
+
+extern "C" int dfot_conv3d_causal_bf16(const void* x, const void* w, void* out, int64_t ldc, int64_t n_frames_out,
+                                       int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t kt, int epilogue,
+                                       const dfot_gemm_epilogue* epi, void* stream) {
+  return conv_impl(x, w, out, ldc, n_frames_out, H, W, Cin, Cout, kt, epilogue, epi, stream);
 }

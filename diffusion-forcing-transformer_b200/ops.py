@@ -234,6 +234,34 @@ def conv3x3_bf16(x, w, out, epilogue, bias=None, resid=None, gn_sums=None, gn_gr
     _abi.check(rc, "conv3x3_bf16")
 
 
+def conv3d_causal_bf16(x, w, out, epilogue, bias=None, resid=None):
+    """Causal kt x 3 x 3 conv along a frame axis (the reference VideoVAE's PaddedConv3D).  x [n_out + kt - 1, H, W, Cin]
+    bf16 channel-last with frames j .. j+kt-1 = output frame j's causal window, w [Cout, kt, 3, 3, Cin] bf16,
+    out [n_out*H*W, Cout] f32|bf16 per epilogue (EPI_F32, EPI_BF16, EPI_SILU_BF16, EPI_RESID_F32)."""
+    _need(x, torch.bfloat16, "x")
+    _need(w, torch.bfloat16, "w")
+    _need(out, None, "out")
+    n_in, H, W, Cin = x.shape
+    Cout, kt = w.shape[0], w.shape[1]
+    n_out = n_in - kt + 1
+    if tuple(w.shape) != (Cout, kt, 3, 3, Cin) or n_out < 1 or out.numel() != n_out * H * W * Cout:
+        raise RuntimeError(f"dfot_b200: conv3d shape mismatch x{tuple(x.shape)} w{tuple(w.shape)} out{tuple(out.shape)}")
+    want = torch.float32 if epilogue in (EPI_F32, EPI_RESID_F32) else torch.bfloat16
+    if out.dtype != want:
+        raise RuntimeError(f"dfot_b200: epilogue {epilogue} writes {want}, got {out.dtype}")
+    e = _abi.GemmEpilogue()
+    if bias is not None:
+        _need(bias, torch.float32, "bias")
+        e.bias = bias.data_ptr()
+    if resid is not None:
+        _need(resid, torch.float32, "resid")
+        e.resid, e.ld_resid = resid.data_ptr(), Cout
+    e.tokens_per_frame = 1
+    rc = _abi.lib().dfot_conv3d_causal_bf16(x.data_ptr(), w.data_ptr(), out.data_ptr(), Cout, n_out, H, W, Cin, Cout, kt,
+                                            epilogue, ctypes.byref(e), _stream())
+    _abi.check(rc, "conv3d_causal_bf16")
+
+
 def groupnorm_stats(x, sums, n_img, HW, C, groups=32, eps=1e-6):
     """x [n_img*HW, C] f32|bf16 channel-last → sums [n_img, groups, 3] f64 workspace: (sum, sum of squares) pairs
     followed by the finalised f32 (mean, rstd) pairs that groupnorm_silu_bf16 reads."""

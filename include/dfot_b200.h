@@ -164,6 +164,20 @@ DFOT_API int dfot_conv3x3_bf16(const void* x, const void* w, void* out, int64_t 
                       int64_t W, int64_t Cin, int64_t Cout, int epilogue, const dfot_gemm_epilogue* epi,
                       void* stream);
 
+/* Causal kt x 3 x 3 convolution along a frame axis on the same kernel (K = kt*9 taps x Cin; the temporal tap is a
+ * frame offset of the 4-D TMA box) — the PaddedConv3D of the reference's causal VideoVAE
+ * (algorithms/vae/common/modules/conv.py:39-108: the first frame repeated kt-1 times in front, no other temporal
+ * padding; spatial zero padding 1).  First building block of the VAE-decode row.
+ *   x   [n_frames_out + kt - 1, H, W, Cin] bf16 channel-last, laid out by the caller so that frames j .. j+kt-1 are
+ *       output frame j's causal window (per clip: kt-1 copies of its first frame, then its frames);
+ *   w   [Cout, kt, 3, 3, Cin] bf16 (torch Conv3d weight permuted (0, 2, 3, 4, 1));
+ *   out [n_frames_out*H*W, ldc], output frame j = sum_dt conv3x3(x[j + dt], w[:, dt]).  Same epilogues and size
+ *       rules as dfot_conv3x3_bf16; kt = 1 is that function.
+ */
+DFOT_API int dfot_conv3d_causal_bf16(const void* x, const void* w, void* out, int64_t ldc, int64_t n_frames_out,
+                            int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t kt, int epilogue,
+                            const dfot_gemm_epilogue* epi, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K3 — attention over space-time latent tokens (non-causal, no mask: context frames are
  * expressed through per-frame noise levels, never an attention mask — SURVEY.md §8a Q9).

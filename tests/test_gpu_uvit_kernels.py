@@ -52,6 +52,39 @@ def test_conv3x3_implicit_gemm(n, H, W, Cin, Cout):
     assert rel_err(out16, ref) < 5e-3
 
 
+@pytest.mark.parametrize("B,T,H,W,Cin,Cout,kt", [(2, 5, 16, 16, 64, 128, 3), (1, 9, 32, 32, 128, 64, 3), (2, 3, 8, 8, 64, 64, 3),
+                                                 (1, 3, 4, 4, 128, 128, 3), (1, 17, 64, 64, 64, 8, 3), (2, 4, 32, 32, 64, 64, 1),
+                                                 (3, 5, 128, 128, 32, 32, 3)])
+def test_conv3d_causal_implicit_gemm(B, T, H, W, Cin, Cout, kt):
+    """Causal kt x 3 x 3 convolution (the reference VideoVAE's PaddedConv3D, conv.py:98-108) on the implicit-GEMM
+    kernel: clips laid out with kt-1 leading copies of their first frame; the kt-1 output slots that straddle two clips
+    are junk by construction and skipped."""
+    g = torch.Generator().manual_seed(B * 100 + T * 10 + Cin + Cout)
+    x = torch.randn((B, Cin, T, H, W), generator=g).to(DEV).to(torch.bfloat16)
+    w = (torch.randn((Cout, Cin, kt, 3, 3), generator=g) / math.sqrt(9 * kt * Cin)).to(DEV).to(torch.bfloat16)
+    bias = torch.randn((Cout,), generator=g).to(DEV)
+    xp = torch.cat([x[:, :, :1].repeat(1, 1, kt - 1, 1, 1), x], 2).float()                  # conv.py:100-104
+    ref = F.conv3d(xp, w.float(), bias, padding=(0, 1, 1)).permute(0, 2, 3, 4, 1)             # [B, T, H, W, Cout]
+    P = kt - 1
+    frames = torch.cat([x[:, :, :1].repeat(1, 1, P, 1, 1), x], 2).permute(0, 2, 3, 4, 1)      # [B, T+P, H, W, Cin]
+    x_cl = frames.reshape(B * (T + P), H, W, Cin).contiguous()
+    w_cl = w.permute(0, 2, 3, 4, 1).contiguous()
+    n_out = B * (T + P) - P
+    out = torch.full((n_out * H * W, Cout), float("nan"), device=DEV)
+    ops.conv3d_causal_bf16(x_cl, w_cl, out, ops.EPI_F32, bias=bias)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    tol = 3e-3 * max(1.0, ref.abs().max().item())
+    got = out.reshape(n_out, H, W, Cout)
+    for b in range(B):
+        sl = got[b * (T + P): b * (T + P) + T]
+        assert (sl - ref[b]).abs().max().item() <= tol, (b, (sl - ref[b]).abs().max())
+    resid = torch.randn((n_out * H * W, Cout), generator=g).to(DEV)
+    out2 = torch.empty_like(out)
+    ops.conv3d_causal_bf16(x_cl, w_cl, out2, ops.EPI_RESID_F32, bias=bias, resid=resid)
+    assert (out2 - out - resid).abs().max().item() <= 1e-5 * max(1.0, out.abs().max().item())
+
+
 @pytest.mark.parametrize("n,H,C,epi", [(4, 64, 128, "bf16"), (4, 64, 128, "resid"), (3, 32, 256, "bf16"), (3, 32, 256, "f32"),
                                        (4, 16, 32, "bf16"), (4, 16, 32, "resid"), (6, 8, 64, "bf16"), (2, 16, 1024, "f32")])
 def test_conv_groupnorm_side_output(n, H, C, epi):
