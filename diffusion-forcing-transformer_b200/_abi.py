@@ -15,7 +15,8 @@ SYMBOLS = [
     "dfot_gemm_bf16", "dfot_attention", "dfot_attention_strided", "dfot_attention_bounded", "dfot_noise_features", "dfot_silu_sum_bf16", "dfot_patchify_bf16",
     "dfot_unpatchify", "dfot_cast_bf16", "dfot_conv3x3_bf16", "dfot_conv3d_causal_bf16", "dfot_groupnorm_stats", "dfot_groupnorm_silu_bf16",
     "dfot_rmsnorm_film_bf16", "dfot_qk_norm_rope", "dfot_avgpool2x2", "dfot_sub_bf16", "dfot_upsample2x_add",
-    "dfot_pose_ray_patches",
+    "dfot_pose_ray_patches", "dfot_groupnorm_stats_strided", "dfot_groupnorm_apply_bf16", "dfot_vae_upsample2x_bf16",
+    "dfot_vae_fill_pad_frames", "dfot_softmax_rows_bf16",
 ]
 
 
@@ -73,6 +74,11 @@ def lib() -> ctypes.CDLL:
     L.dfot_conv3x3_bf16.argtypes = [vp, vp, vp, i64, i64, i64, i64, i64, i64, i, POINTER(GemmEpilogue), vp]
     L.dfot_conv3d_causal_bf16.argtypes = [vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i, POINTER(GemmEpilogue), vp]
     L.dfot_groupnorm_stats.argtypes = [vp, i, vp, i64, i64, i64, i64, c_float, vp]
+    L.dfot_groupnorm_stats_strided.argtypes = [vp, i, vp, i64, i64, i64, i64, i64, c_float, vp]
+    L.dfot_groupnorm_apply_bf16.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i, vp]
+    L.dfot_vae_upsample2x_bf16.argtypes = [vp, vp, i64, i64, i64, i64, i64, i, vp]
+    L.dfot_vae_fill_pad_frames.argtypes = [vp, i64, i64, i64, vp]
+    L.dfot_softmax_rows_bf16.argtypes = [vp, i64, vp, i64, i64, i64, c_float, vp]
     L.dfot_groupnorm_silu_bf16.argtypes = [vp, i, vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, i64, i64, i64, i64, vp]
     L.dfot_rmsnorm_film_bf16.argtypes = [vp, vp, c_float, vp, i64, i64, i64, vp, vp, vp, i64, i64, i64, vp]
     L.dfot_qk_norm_rope.argtypes = [vp, i64, vp, vp, c_float, vp, i64, i64, i64, i64, c_float, vp]

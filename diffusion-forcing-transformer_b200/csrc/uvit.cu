@@ -41,7 +41,8 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
 // grid (slabs, n_img); a thread owns one 8-channel vector (fixed) and walks the slab's pixels.
 template <typename TX>
 __global__ void __launch_bounds__(kThreads)
-gn_stats_kernel(const TX* __restrict__ x, double* __restrict__ sums, int64_t HW, int C, int G, int pix_per_block) {
+gn_stats_kernel(const TX* __restrict__ x, double* __restrict__ sums, int64_t HW, int64_t img_stride, int C, int G,
+                int pix_per_block) {
   pdl_trigger();   // programmatic dependent launch: see common.cuh
   pdl_wait();
   __shared__ float s_sum[64], s_sq[64];
@@ -58,7 +59,7 @@ gn_stats_kernel(const TX* __restrict__ x, double* __restrict__ sums, int64_t HW,
   if (lane_pix < pix_step) {
     for (int64_t pix = p0 + lane_pix; pix < p1; pix += pix_step) {
       float a[8];
-      load8(x + ((int64_t)img * HW + pix) * C + 8 * v, a);
+      load8(x + (int64_t)img * img_stride + pix * C + 8 * v, a);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s[j] += a[j]; q[j] = fmaf(a[j], a[j], q[j]); }
     }
@@ -101,12 +102,13 @@ __global__ void gn_finalize_kernel(const double* __restrict__ sums, float2* __re
 // loaded once and folded into a per-channel affine) and walks kGnPix pixels of its slab with all loads issued up
 // front — no 64-bit index arithmetic, 4 independent 16/32-byte loads in flight per thread.
 constexpr int kGnPix = 2, kGnIter = 4;
-template <typename TX>
+template <typename TX, bool SILU = true>
 __global__ void __launch_bounds__(kThreads, 3)
 gn_silu_kernel(const TX* __restrict__ x, const float2* __restrict__ stats, const float* __restrict__ gamma,
                const float* __restrict__ beta, const float* __restrict__ mod_img, int64_t ld_img,
                int64_t scale_col, int64_t shift_col, const __nv_bfloat16* __restrict__ mod_pix,
-               const int32_t* __restrict__ img_map, __nv_bfloat16* __restrict__ y, int HW, int C, int G) {
+               const int32_t* __restrict__ img_map, __nv_bfloat16* __restrict__ y, int HW, int C, int G,
+               int64_t img_stride) {
   pdl_trigger();   // programmatic dependent launch: see common.cuh
   pdl_wait();
   const int vecs = C >> 3, cpg = C / G;
@@ -136,8 +138,8 @@ gn_silu_kernel(const TX* __restrict__ x, const float2* __restrict__ stats, const
 #pragma unroll
     for (int j = 0; j < 8; ++j) { A[j] *= 1.f + sc[j]; B[j] = fmaf(B[j], 1.f + sc[j], sh[j]); }
   }
-  const TX* xb = x + (int64_t)img * HW * C + c0;
-  __nv_bfloat16* yb = y + (int64_t)img * HW * C + c0;
+  const TX* xb = x + (int64_t)img * img_stride + c0;
+  __nv_bfloat16* yb = y + (int64_t)img * img_stride + c0;
   const __nv_bfloat16* pb = src >= 0 ? mod_pix + (int64_t)src * HW * (2 * C) + c0 : nullptr;
   // kGnIter groups of kGnPix pixels: the prologue above (≈20 cached loads) is amortised over kGnIter*kGnPix pixels.
   // Images without a per-pixel part have a third of the loads per pixel, so they walk the same pixels in half as many
@@ -186,7 +188,10 @@ gn_silu_kernel(const TX* __restrict__ x, const float2* __restrict__ stats, const
         const int pix = pix0 + k * pix_step;
         if (pix < HW) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) a[k][j] = silu_fast_f(fmaf(a[k][j], A[j], B[j]));
+          for (int j = 0; j < 8; ++j) {
+            const float t = fmaf(a[k][j], A[j], B[j]);
+            a[k][j] = SILU ? silu_fast_f(t) : t;
+          }
           store8(yb + (int64_t)pix * C, a[k]);
         }
       }
@@ -452,7 +457,14 @@ using namespace dfot::uvit;
 
 extern "C" int dfot_groupnorm_stats(const void* x, int x_dtype, double* sums, int64_t n_img, int64_t HW, int64_t C,
                                     int64_t groups, float eps, void* stream) {
+  return dfot_groupnorm_stats_strided(x, x_dtype, sums, n_img, HW, HW * C, C, groups, eps, stream);
+}
+
+extern "C" int dfot_groupnorm_stats_strided(const void* x, int x_dtype, double* sums, int64_t n_img, int64_t HW,
+                                            int64_t img_stride, int64_t C, int64_t groups, float eps, void* stream) {
   DFOT_REQUIRE(x && sums && n_img > 0 && HW > 0 && C > 0 && groups > 0, DFOT_ERR_INVALID_ARG, "groupnorm_stats: bad arguments");
+  DFOT_REQUIRE(img_stride >= HW * C && img_stride % 8 == 0, DFOT_ERR_INVALID_ARG,
+               "groupnorm_stats: img_stride must be a multiple of 8 and >= HW*C");
   DFOT_REQUIRE(C % groups == 0 && C % 8 == 0 && groups <= 64 && n_img < 65536, DFOT_ERR_UNSUPPORTED,
                "groupnorm_stats: need C %% groups == 0, C %% 8 == 0, groups <= 64");
   const int vecs = (int)(C / 8);
@@ -468,9 +480,9 @@ extern "C" int dfot_groupnorm_stats(const void* x, int x_dtype, double* sums, in
   slabs = ceil_div(HW, ppb);
   dim3 grid((unsigned)slabs, (unsigned)n_img);
   if (x_dtype == DFOT_F32)
-    launch_pdl(gn_stats_kernel<float>, dim3(grid), dim3(kThreads), 0, s, (const float*)x, sums, HW, (int)C, (int)groups, (int)ppb);
+    launch_pdl(gn_stats_kernel<float>, dim3(grid), dim3(kThreads), 0, s, (const float*)x, sums, HW, img_stride, (int)C, (int)groups, (int)ppb);
   else if (x_dtype == DFOT_BF16)
-    launch_pdl(gn_stats_kernel<__nv_bfloat16>, dim3(grid), dim3(kThreads), 0, s, (const __nv_bfloat16*)x, sums, HW, (int)C, (int)groups, (int)ppb);
+    launch_pdl(gn_stats_kernel<__nv_bfloat16>, dim3(grid), dim3(kThreads), 0, s, (const __nv_bfloat16*)x, sums, HW, img_stride, (int)C, (int)groups, (int)ppb);
   else
     DFOT_REQUIRE(false, DFOT_ERR_INVALID_ARG, "groupnorm_stats: x dtype must be f32 or bf16");
   DFOT_CHECK_LAUNCH("groupnorm_stats");
@@ -499,14 +511,40 @@ extern "C" int dfot_groupnorm_silu_bf16(const void* x, int x_dtype, const double
   if (x_dtype == DFOT_F32)
     launch_pdl(gn_silu_kernel<float>, dim3(grid), dim3(kThreads), 0, s, 
         (const float*)x, stats, gamma, beta, mod_img, ld_img, scale_col, shift_col, (const __nv_bfloat16*)mod_pix,
-        img_map, (__nv_bfloat16*)y_bf16, (int)HW, (int)C, (int)groups);
+        img_map, (__nv_bfloat16*)y_bf16, (int)HW, (int)C, (int)groups, HW * C);
   else if (x_dtype == DFOT_BF16)
     launch_pdl(gn_silu_kernel<__nv_bfloat16>, dim3(grid), dim3(kThreads), 0, s, 
         (const __nv_bfloat16*)x, stats, gamma, beta, mod_img, ld_img, scale_col, shift_col,
-        (const __nv_bfloat16*)mod_pix, img_map, (__nv_bfloat16*)y_bf16, (int)HW, (int)C, (int)groups);
+        (const __nv_bfloat16*)mod_pix, img_map, (__nv_bfloat16*)y_bf16, (int)HW, (int)C, (int)groups, HW * C);
   else
     DFOT_REQUIRE(false, DFOT_ERR_INVALID_ARG, "groupnorm_silu: x dtype must be f32 or bf16");
   DFOT_CHECK_LAUNCH("groupnorm_silu");
+  return DFOT_OK;
+}
+
+// GroupNorm (+ optional SiLU) -> bf16 over strided "images" (a clip's valid frames inside a padded frame axis), no FiLM
+extern "C" int dfot_groupnorm_apply_bf16(const float* x, const double* sums, const float* gamma, const float* beta,
+                                         void* y_bf16, int64_t n_img, int64_t HW, int64_t img_stride, int64_t C,
+                                         int64_t groups, int silu, void* stream) {
+  DFOT_REQUIRE(x && sums && gamma && beta && y_bf16 && n_img > 0 && HW > 0 && C > 0 && groups > 0, DFOT_ERR_INVALID_ARG,
+               "groupnorm_apply: bad arguments");
+  DFOT_REQUIRE(C % groups == 0 && C % 8 == 0 && img_stride >= HW * C && img_stride % 8 == 0, DFOT_ERR_UNSUPPORTED,
+               "groupnorm_apply: need C %% groups == 0, C %% 8 == 0, img_stride %% 8 == 0 and >= HW*C");
+  const int vecs = (int)(C / 8);
+  DFOT_REQUIRE(vecs <= kThreads && kThreads % vecs == 0 && n_img < 65536 && HW < (1ll << 30), DFOT_ERR_UNSUPPORTED,
+               "groupnorm_apply: C/8 = %d must divide %d", vecs, kThreads);
+  const float2* stats = reinterpret_cast<const float2*>(sums + 2 * n_img * groups);
+  const dim3 grid((unsigned)ceil_div(HW, (kThreads / vecs) * kGnPix * kGnIter), (unsigned)n_img);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (silu)
+    launch_pdl(gn_silu_kernel<float, true>, grid, dim3(kThreads), 0, s, x, stats, gamma, beta, (const float*)nullptr,
+               (int64_t)0, (int64_t)0, (int64_t)0, (const __nv_bfloat16*)nullptr, (const int32_t*)nullptr,
+               (__nv_bfloat16*)y_bf16, (int)HW, (int)C, (int)groups, img_stride);
+  else
+    launch_pdl(gn_silu_kernel<float, false>, grid, dim3(kThreads), 0, s, x, stats, gamma, beta, (const float*)nullptr,
+               (int64_t)0, (int64_t)0, (int64_t)0, (const __nv_bfloat16*)nullptr, (const int32_t*)nullptr,
+               (__nv_bfloat16*)y_bf16, (int)HW, (int)C, (int)groups, img_stride);
+  DFOT_CHECK_LAUNCH("groupnorm_apply");
   return DFOT_OK;
 }
 

@@ -262,6 +262,59 @@ def conv3d_causal_bf16(x, w, out, epilogue, bias=None, resid=None):
     _abi.check(rc, "conv3d_causal_bf16")
 
 
+# ---------------------------------------------------------------- VAE-decode building blocks (clips [B, 2 + T, H, W, C])
+def groupnorm_stats_strided(x, sums, n_img, HW, img_stride, C, groups=32, eps=1e-6):
+    """GroupNorm statistics over strided images: image i = HW rows of C channels starting at x.flatten()[i*img_stride]."""
+    _need(x, None, "x")
+    _need(sums, torch.float64, "sums")
+    if sums.numel() != n_img * groups * 3:
+        raise RuntimeError("dfot_b200: groupnorm_stats_strided workspace must hold n_img*groups*3 doubles")
+    rc = _abi.lib().dfot_groupnorm_stats_strided(x.data_ptr(), _DTYPE_TAG[x.dtype], sums.data_ptr(), n_img, HW, img_stride,
+                                                 C, groups, eps, _stream())
+    _abi.check(rc, "groupnorm_stats_strided")
+
+
+def groupnorm_apply_bf16(x, sums, gamma, beta, out, n_img, HW, img_stride, C, groups=32, silu=True):
+    """y = GroupNorm(x) * gamma + beta (then x*sigmoid(x) if silu) -> bf16 at the same strided offsets of `out`."""
+    _need(x, torch.float32, "x")
+    _need(out, torch.bfloat16, "out")
+    _need(gamma, torch.float32, "gamma")
+    _need(beta, torch.float32, "beta")
+    rc = _abi.lib().dfot_groupnorm_apply_bf16(x.data_ptr(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                              out.data_ptr(), n_img, HW, img_stride, C, groups, 1 if silu else 0, _stream())
+    _abi.check(rc, "groupnorm_apply_bf16")
+
+
+def vae_upsample2x_bf16(x, out, B, T_in, H, W, C, temporal):
+    """fp32 clip [B, 2+T_in, H, W, C] -> bf16 clip [B, 2+T_out, 2H, 2W, C]; temporal: T_out = 2*T_in - 1 (first frame
+    bilinear, the others trilinear), else nearest with T_out = T_in; pad slots of `out` are filled."""
+    _need(x, torch.float32, "x")
+    _need(out, torch.bfloat16, "out")
+    T_out = 2 * T_in - 1 if temporal else T_in
+    if x.numel() != B * (2 + T_in) * H * W * C or out.numel() != B * (2 + T_out) * 4 * H * W * C:
+        raise RuntimeError("dfot_b200: vae_upsample2x shape mismatch")
+    rc = _abi.lib().dfot_vae_upsample2x_bf16(x.data_ptr(), out.data_ptr(), B, T_in, H, W, C, 1 if temporal else 0, _stream())
+    _abi.check(rc, "vae_upsample2x_bf16")
+
+
+def vae_fill_pad_frames(x, B, T, frame_elems):
+    """pad slots (2 per clip) of a bf16 clip [B, 2+T, ...] <- the clip's first frame."""
+    _need(x, torch.bfloat16, "x")
+    if x.numel() != B * (2 + T) * frame_elems:
+        raise RuntimeError("dfot_b200: vae_fill_pad_frames shape mismatch")
+    rc = _abi.lib().dfot_vae_fill_pad_frames(x.data_ptr(), B, T, frame_elems, _stream())
+    _abi.check(rc, "vae_fill_pad_frames")
+
+
+def softmax_rows_bf16(s, p, scale=1.0):
+    """p = softmax(scale * s, dim=-1): s [rows, n] f32 (row stride s.stride(0)) -> p [rows, n] bf16."""
+    if s.dtype != torch.float32 or p.dtype != torch.bfloat16 or not s.is_cuda or s.shape != p.shape or s.stride(1) != 1 or p.stride(1) != 1:
+        raise RuntimeError("dfot_b200: softmax_rows_bf16 needs CUDA f32 logits and a bf16 output of the same shape")
+    rc = _abi.lib().dfot_softmax_rows_bf16(s.data_ptr(), s.stride(0), p.data_ptr(), p.stride(0), s.shape[0], s.shape[1],
+                                           float(scale), _stream())
+    _abi.check(rc, "softmax_rows_bf16")
+
+
 def groupnorm_stats(x, sums, n_img, HW, C, groups=32, eps=1e-6):
     """x [n_img*HW, C] f32|bf16 channel-last → sums [n_img, groups, 3] f64 workspace: (sum, sum of squares) pairs
     followed by the finalised f32 (mean, rstd) pairs that groupnorm_silu_bf16 reads."""

@@ -240,6 +240,32 @@ DFOT_API int dfot_groupnorm_silu_bf16(const void* x, int x_dtype, const double* 
                              const float* beta, const float* mod_img, int64_t ld_img, int64_t scale_col,
                              int64_t shift_col, const void* mod_pix, const int32_t* img_map, void* y_bf16,
                              int64_t n_img, int64_t HW, int64_t C, int64_t groups, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * VAE-decode row: building blocks of the reference's causal VideoVAE decoder
+ * (algorithms/vae/video_vae/model.py:153-270).  Clips are channel-last with a padded frame axis
+ * [B, 2 + T, H, W, C]: the two leading slots of a clip hold copies of its first frame in bf16 conv inputs (the causal
+ * window of dfot_conv3d_causal_bf16) and are unused in the fp32 stream.
+ *   dfot_groupnorm_stats_strided / dfot_groupnorm_apply_bf16 — Normalize = GroupNorm(32, eps 1e-6) over a clip's valid
+ *     frames (normalize.py:4-7): "image" i starts at x + i*img_stride and has HW rows of C channels; apply writes
+ *     bf16 at the same offsets of y, with or without the x*sigmoid(x) nonlinearity (ops.py:21-22).
+ *   dfot_vae_upsample2x_bf16 — temporal = 0: nearest x2 in (H, W) (SpatialUpsample2x, updownsample.py:73-80);
+ *     temporal = 1: first frame bilinear x2, the others trilinear x(2,2,2), align_corners = False
+ *     (Spatial2xTime2x3DUpsample, updownsample.py:131-147).  fp32 clip in -> bf16 clip out (pads filled).
+ *   dfot_vae_fill_pad_frames — pad slots of a bf16 clip <- its first frame (PaddedConv3D.forward, conv.py:98-104).
+ *   dfot_softmax_rows_bf16 — softmax(scale * s) per row, fp32 -> bf16 (AttnBlock3D, attention.py:138-140).
+ */
+DFOT_API int dfot_groupnorm_stats_strided(const void* x, int x_dtype, double* sums, int64_t n_img, int64_t HW,
+                                 int64_t img_stride, int64_t C, int64_t groups, float eps, void* stream);
+DFOT_API int dfot_groupnorm_apply_bf16(const float* x, const double* sums, const float* gamma, const float* beta,
+                              void* y_bf16, int64_t n_img, int64_t HW, int64_t img_stride, int64_t C,
+                              int64_t groups, int silu, void* stream);
+DFOT_API int dfot_vae_upsample2x_bf16(const float* in, void* out_bf16, int64_t B, int64_t T_in, int64_t H, int64_t W,
+                             int64_t C, int temporal, void* stream);
+DFOT_API int dfot_vae_fill_pad_frames(void* x_bf16, int64_t B, int64_t T, int64_t frame_elems, void* stream);
+DFOT_API int dfot_softmax_rows_bf16(const float* s, int64_t ld_s, void* p_bf16, int64_t ld_p, int64_t rows, int64_t n,
+                           float scale, void* stream);
+
 /* NormalizeWithCond (u_vit_blocks.py:98-121): y = RMSNorm(x) * weight * (1 + scale) + shift -> bf16; x [M, D] f32,
    image = m / tokens_per_img */
 DFOT_API int dfot_rmsnorm_film_bf16(const float* x, const float* weight, float eps, const float* mod_img, int64_t ld_img,
