@@ -1,8 +1,9 @@
 """BaseVideoAlgo — the slice of the reference's algorithms/common/base_pytorch_video_algo.py that the
 denoising sampling path uses: shape / latent / token bookkeeping (:37-88, :986-1033), model construction
 (:142-174), normalisation (:489-502), condition processing (:635-700), scheduling matrices (:877-947) and
-the validation entry point (:234-264).  Training, VAE encode/decode, metrics and logging are out of scope
-(SURVEY.md §2): the hooks exist where callers need them and raise or no-op explicitly.
+the validation entry point (:234-264), plus the VideoVAE decode of sampled latents (:507-629).
+Training, VAE encoding, image VAEs, metrics and logging are out of scope: the hooks exist where callers
+need them and raise or no-op explicitly.
 
 It is a plain ``nn.Module`` (Lightning is not a dependency of the sampling path); ``state_dict()`` keys are
 identical to the reference's (``data_mean``, ``data_std``, ``diffusion_model.model.*``).
@@ -93,6 +94,40 @@ class BaseVideoAlgo(nn.Module):
 
     def _unnormalize_x(self, xs: Tensor) -> Tensor:
         return xs * self._stat(self.data_std, xs) + self._stat(self.data_mean, xs)
+
+    # ------------------------------------------------------------------ latent decode (:507-629)
+    def _load_vae(self) -> None:
+        """(:507-551) — the causal VideoVAE decoder on the B200 kernels; image VAEs (DC-AE, KL, TiTok: diffusers /
+        external model code) are not built."""
+        name = self.cfg.vae.get("name")
+        if name is not None or not self.is_latent_video_vae:
+            raise NotImplementedError("only the reference's VideoVAE (temporal downsampling > 1) is decoded by dfot_b200; "
+                                      f"vae.name={name!r} / image VAEs are out of scope")
+        from ..vae import VideoVAE
+        self.vae = VideoVAE.from_pretrained(path=self.cfg.vae.pretrained_path,
+                                            **dict(self.cfg.vae.get("pretrained_kwargs") or {})).to(self.device)
+        for p in self.vae.parameters():
+            p.requires_grad_(False)
+
+    @torch.no_grad()
+    def _run_vae(self, x: Tensor, shape: str, vae_fn: Callable[[Tensor], Tensor]) -> Tensor:
+        """(:555-585) — `shape` is a permutation of "b t c h w"; the batch is cut into cfg.vae.batch_size chunks."""
+        axes = shape.split()
+        x = x.permute(*[axes.index(a) for a in "bcthw"])
+        n, step = x.shape[0], self.cfg.vae.batch_size
+        outs = [vae_fn(c.contiguous()) for c in torch.chunk(x, (n + step - 1) // step, 0)]
+        y = torch.cat(outs, 0)
+        return y.permute(*["bcthw".index(a) for a in axes])
+
+    def _encode(self, x: Tensor, shape: str = "b t c h w") -> Tensor:
+        raise NotImplementedError("VAE encoding is outside the scope of dfot_b200 (pass offline `latents`)")
+
+    def _decode(self, latents: Tensor, shape: str = "b t c h w") -> Tensor:
+        """(:599-629) — latent tokens -> frames in [0, 1]."""
+        if self.vae is None:
+            self._load_vae()
+        n_frames = self._n_tokens_to_n_frames(latents.shape[shape.split().index("t")])
+        return self._run_vae(latents, shape, lambda y: self.vae.decode(y, n_frames) * 0.5 + 0.5)
 
     @torch.no_grad()
     def new_validation_step(self, batch, batch_idx, accelerator=None, namespace="validation", validate_sample=True):

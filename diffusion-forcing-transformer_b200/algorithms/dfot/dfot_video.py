@@ -81,9 +81,11 @@ class DFoTVideo(BaseVideoAlgo):
             fn = self._predict_videos if task == "prediction" else self._interpolate_videos
             videos[task] = fn(xs, conditions=conditions, n_context_tokens=n_ctx)
         videos = {k: self._unnormalize_x(v).detach() for k, v in videos.items() if v is not None}
-        if self.is_latent_diffusion:
-            # decoding sampled latents is the VAE's job — rank 1 of SURVEY.md §8(f), not part of this path
-            videos = {k: v for k, v in videos.items()}
+        if self.is_latent_diffusion and (self.vae is not None or (self.cfg.get("vae") or {}).get("pretrained_path")):
+            # (:104-111) decode latents to frames; with no decoder configured (vae.pretrained_path null and no `vae`
+            # attached) the latents themselves are returned
+            gt = batch.get("gt_videos")
+            videos = {k: (gt if k == "gt" and gt is not None else self._decode(v)) for k, v in videos.items()}
         return videos
 
     @torch.no_grad()

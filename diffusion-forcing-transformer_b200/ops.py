@@ -105,8 +105,9 @@ def _gn_side_output(e, gn_sums, gn_rows_per_img, gn_groups, gn_eps, M, N):
 def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, gate=None, ld_gate=0, tokens_per_frame=1, rope_cs=None,
               tokens_per_sample=1, model_dim=0, head_dim=0, q_scale=1.0, M=None, gn_sums=None, gn_rows_per_img=0,
               gn_groups=32, gn_eps=1e-6, qn_w=None, kn_w=None, qk_eps=1e-6):
-    """K2. a [M,K] bf16 (row stride may exceed K), w [N,K] bf16, out [M,N] f32|bf16 per epilogue."""
-    _need(w, torch.bfloat16, "w")
+    """K2. a [M,K] bf16, w [N,K] bf16 (row strides may exceed K), out [M,N] f32|bf16 per epilogue."""
+    if not w.is_cuda or w.dtype != torch.bfloat16 or w.stride(-1) != 1:
+        raise RuntimeError("dfot_b200: `w` must be a CUDA bf16 matrix with unit inner stride")
     if not a.is_cuda or a.dtype != torch.bfloat16 or a.stride(-1) != 1:
         raise RuntimeError("dfot_b200: `a` must be a CUDA bf16 matrix with unit inner stride")
     if not out.is_cuda or out.stride(-1) != 1:
