@@ -54,7 +54,7 @@ def k600_cfg(sampling_timesteps=50, spatial_mlp_ratio=4.0, depth=28, hidden=1152
                        use_causal_mask=False, clip_noise=20.0, objective="pred_v",
                        loss_weighting=dict(strategy="fused_min_snr", snr_clip=5.0, cum_snr_decay=0.96),
                        sampling_timesteps=sampling_timesteps, ddim_sampling_eta=0.0, reconstruction_guidance=0.0),
-        vae=dict(pretrained_path=None, pretrained_kwargs={}, use_fp16=False, batch_size=2),
+        vae=dict(pretrained_path=None, pretrained_kwargs={}, use_fp16=False, batch_size=16),
         checkpoint=dict(reset_optimizer=False, strict=True),
         tasks=dict(prediction=dict(enabled=True, history_guidance=dict(name="conditional", visualize=False),
                                    keyframe_density=None, sliding_context_len=None),
@@ -356,6 +356,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="samples per GPU (default: 4 for re10k, 8 for k600)")
     ap.add_argument("--sampling-steps", type=int, default=50)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--decode", action="store_true",
+                    help="k600: VideoVAE-decode the sampled latents to 128x128 frames inside the e2e region (random-init "
+                         "decoder, hidden 128, z 16) and report the decode on its own; `value` stays sampling-only (SURVEY 8d)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -392,6 +395,11 @@ def main():
 
     algo = make_weights(cfg, 0).to(dev).eval()
     B = wl.batch
+    if args.decode:
+        assert wl.name == "k600", "--decode applies to the latent-video workload (k600)"
+        from dfot_b200.algorithms.vae import VideoVAE
+        torch.manual_seed(1)
+        algo.vae = VideoVAE(hidden_size=128, z_channels=16, embed_dim=16, hidden_size_mult=(1, 2, 4, 4)).to(dev)
     xs_host, conds_host = wl.inputs(rank)
     if strong and world > 1:
         from dfot_b200 import distributed as D
@@ -414,7 +422,7 @@ def main():
             return algo.sample_sharded(xs_dev, conds_dev, wl.ctx_tokens)
         return algo._predict_videos(xs_dev, wl.ctx_tokens, conds_dev)
 
-    gathered = [torch.empty_like(xs_dev) for _ in range(world)] if (world > 1 and not strong) else None
+    gathered = []
 
     def run_e2e():
         # public API with HOST buffers: H2D of the latents, sampling, (N>1: final sample gather), D2H of the result
@@ -425,6 +433,8 @@ def main():
             return vids.to("cpu")
         vids = algo._sample_all_videos(batch, 0)["prediction"]
         if world > 1:
+            if not gathered:
+                gathered.extend(torch.empty_like(vids) for _ in range(world))
             dist.all_gather(gathered, vids.contiguous())
         return vids.to("cpu")
 
@@ -458,8 +468,13 @@ def main():
         ms = timed(run_resident, args.steps)
     launches = ops.total_launches() - n0
     rows_planned, passes_counted = algo.nfe_rows_planned - p0, args.steps
-    run_e2e()
+    vids_host = run_e2e()
     ms_e2e = timed(run_e2e, args.steps)
+    ms_decode = None
+    if args.decode:       # the decode on its own: latents resident in HBM -> frames in HBM
+        lat = algo._unnormalize_x(xs_dev)
+        algo._decode(lat)
+        ms_decode = timed(lambda: algo._decode(lat), args.steps) / args.steps
 
     # roofline of the dominant kernel (the tcgen05 GEMM kernel, which also runs the implicit-GEMM convolutions) and
     # of the attention kernel: instrumented extra pass over the same region with CUDA events around every launch
@@ -540,8 +555,8 @@ def main():
         if strong:      # useful forward-rows of one rollout = what a single GPU executes (replicated keyframe rows and
             rows = rows_planned // passes_counted          # noise-only replays are not counted twice)
         per_e2e_s = ms_e2e / args.steps / 1e3
-        bytes_out = xs_host.numel() * 4
-        bytes_in = bytes_out + (0 if conds_host is None else conds_host.numel() * 4)
+        bytes_out = vids_host.numel() * 4
+        bytes_in = xs_host.numel() * 4 + (0 if conds_host is None else conds_host.numel() * 4)
         line = dict(metric="generated_frames_per_sec", value=frames / per_step_s, unit="generated_frames/s",
                     n_gpus=world, steps=args.steps, warmup=n_warm, ms_per_step=ms / args.steps,
                     higher_is_better=True, scaling="strong" if strong else "weak", vs_baseline=None, dtype="bf16",
@@ -552,6 +567,12 @@ def main():
                     gpu_launches=int(launches), clocks=clocks.summary(), roofline=roof)
         if roof_attn is not None:
             line["roofline_attention"] = roof_attn
+        if ms_decode is not None:
+            n_fr = B * world * vids_host.shape[1]
+            line["vae_decode"] = dict(ms_per_batch=ms_decode, decoded_frames_per_sec=n_fr / ms_decode * 1e3,
+                                      video_shape=list(vids_host.shape), vae_batch_size=cfg["vae"]["batch_size"],
+                                      note="VideoVAE decoder (hidden 128, mult 1-2-4-4, z 16, random init); e2e includes "
+                                           "it, `value` does not (SURVEY 8d excludes the decode)")
         line["config"]["cuda_graph"] = bool(algo.diffusion_model.model.use_cuda_graph)
         if not args.skip_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(wl, args.sampling_steps)
