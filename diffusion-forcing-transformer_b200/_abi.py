@@ -16,7 +16,7 @@ SYMBOLS = [
     "dfot_unpatchify", "dfot_cast_bf16", "dfot_conv3x3_bf16", "dfot_conv3d_causal_bf16", "dfot_groupnorm_stats", "dfot_groupnorm_silu_bf16",
     "dfot_rmsnorm_film_bf16", "dfot_qk_norm_rope", "dfot_avgpool2x2", "dfot_sub_bf16", "dfot_upsample2x_add",
     "dfot_pose_ray_patches", "dfot_groupnorm_stats_strided", "dfot_groupnorm_apply_bf16", "dfot_vae_upsample2x_bf16",
-    "dfot_vae_fill_pad_frames", "dfot_softmax_rows_bf16",
+    "dfot_vae_fill_pad_frames", "dfot_softmax_rows_bf16", "dfot_upsample2x_nearest_bf16",
 ]
 
 
@@ -78,6 +78,7 @@ def lib() -> ctypes.CDLL:
     L.dfot_groupnorm_apply_bf16.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i, vp]
     L.dfot_vae_upsample2x_bf16.argtypes = [vp, vp, i64, i64, i64, i64, i64, i, vp]
     L.dfot_vae_fill_pad_frames.argtypes = [vp, i64, i64, i64, vp]
+    L.dfot_upsample2x_nearest_bf16.argtypes = [vp, vp, i64, i64, i64, i64, vp]
     L.dfot_softmax_rows_bf16.argtypes = [vp, i64, vp, i64, i64, i64, c_float, vp]
     L.dfot_groupnorm_silu_bf16.argtypes = [vp, i, vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, i64, i64, i64, i64, vp]
     L.dfot_rmsnorm_film_bf16.argtypes = [vp, vp, c_float, vp, i64, i64, i64, vp, vp, vp, i64, i64, i64, vp]

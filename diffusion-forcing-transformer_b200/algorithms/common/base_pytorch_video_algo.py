@@ -97,25 +97,34 @@ class BaseVideoAlgo(nn.Module):
 
     # ------------------------------------------------------------------ latent decode (:507-629)
     def _load_vae(self) -> None:
-        """(:507-551) — the causal VideoVAE decoder on the B200 kernels; image VAEs (DC-AE, KL, TiTok: diffusers /
-        external model code) are not built."""
+        """(:507-551) — the reference's own VAEs on the B200 kernels: the causal VideoVAE when latents are temporally
+        compressed, else the ImageVAE; the external image VAEs (DC-AE, diffusers KL, TiTok) are not built."""
         name = self.cfg.vae.get("name")
-        if name is not None or not self.is_latent_video_vae:
-            raise NotImplementedError("only the reference's VideoVAE (temporal downsampling > 1) is decoded by dfot_b200; "
-                                      f"vae.name={name!r} / image VAEs are out of scope")
-        from ..vae import VideoVAE
-        self.vae = VideoVAE.from_pretrained(path=self.cfg.vae.pretrained_path,
-                                            **dict(self.cfg.vae.get("pretrained_kwargs") or {})).to(self.device)
+        if name is not None:
+            raise NotImplementedError(f"vae.name={name!r} (DC-AE / KL / TiTok: external model code) is not decoded by "
+                                      "dfot_b200; only the reference's VideoVAE and ImageVAE are")
+        from ..vae import ImageVAE, VideoVAE
+        vae_cls = VideoVAE if self.is_latent_video_vae else ImageVAE
+        self.vae = vae_cls.from_pretrained(path=self.cfg.vae.pretrained_path,
+                                           **dict(self.cfg.vae.get("pretrained_kwargs") or {})).to(self.device)
         for p in self.vae.parameters():
             p.requires_grad_(False)
 
     @torch.no_grad()
     def _run_vae(self, x: Tensor, shape: str, vae_fn: Callable[[Tensor], Tensor]) -> Tensor:
-        """(:555-585) — `shape` is a permutation of "b t c h w"; the batch is cut into cfg.vae.batch_size chunks."""
+        """(:555-585) — `shape` is a permutation of "b t c h w"; the batch is cut into cfg.vae.batch_size chunks; an
+        image VAE sees the frames of a chunk as a batch of images."""
         axes = shape.split()
         x = x.permute(*[axes.index(a) for a in "bcthw"])
         n, step = x.shape[0], self.cfg.vae.batch_size
-        outs = [vae_fn(c.contiguous()) for c in torch.chunk(x, (n + step - 1) // step, 0)]
+        outs = []
+        for c in torch.chunk(x, (n + step - 1) // step, 0):
+            if self.is_latent_video_vae:
+                outs.append(vae_fn(c.contiguous()))
+            else:
+                b, ch, t, h, w = c.shape
+                y = vae_fn(c.permute(0, 2, 1, 3, 4).reshape(b * t, ch, h, w))
+                outs.append(y.reshape(b, t, *y.shape[1:]).permute(0, 2, 1, 3, 4))
         y = torch.cat(outs, 0)
         return y.permute(*["bcthw".index(a) for a in axes])
 
@@ -126,6 +135,8 @@ class BaseVideoAlgo(nn.Module):
         """(:599-629) — latent tokens -> frames in [0, 1]."""
         if self.vae is None:
             self._load_vae()
+        if not self.is_latent_video_vae:
+            return self._run_vae(latents, shape, lambda y: self.vae.decode(y) * 0.5 + 0.5)
         n_frames = self._n_tokens_to_n_frames(latents.shape[shape.split().index("t")])
         return self._run_vae(latents, shape, lambda y: self.vae.decode(y, n_frames) * 0.5 + 0.5)
 

@@ -26,25 +26,27 @@ __device__ __forceinline__ void load8f(const float* p, float (&v)[8]) {
 // x2 spatial (and, with TIME, x2 temporal on all frames but the first) upsampling, fp32 clip -> bf16 clip with pads.
 //   TIME = false: nearest x2 in (H, W)                               (SpatialUpsample2x, updownsample.py:73-80)
 //   TIME = true : frame 0 bilinear x2; frames 1.. trilinear x(2,2,2) (Spatial2xTime2x3DUpsample, updownsample.py:131-147)
-// One thread = 8 channels of one output pixel; output slots 0..kPad-1 of a clip replicate its first frame.
+// One thread = 8 channels of one output pixel; output slots 0..pad-1 of a clip replicate its first frame (pad = kPad for
+// video clips, 0 for plain image batches).
 template <bool TIME>
 __global__ void __launch_bounds__(kThreads)
-upsample2x_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int Tin, int H, int W, int C) {
+upsample2x_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int Tin, int H, int W, int C,
+                  int pad) {
   pdl_trigger();
   pdl_wait();
   const int vecs = C >> 3, Ho = 2 * H, Wo = 2 * W;
   const int Tout = TIME ? 2 * Tin - 1 : Tin;
-  const int64_t total = (int64_t)B * (kPad + Tout) * Ho * Wo * vecs;
+  const int64_t total = (int64_t)B * (pad + Tout) * Ho * Wo * vecs;
   const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (idx >= total) return;
   const int v = (int)(idx % vecs);
   int64_t r = idx / vecs;
   const int xo = (int)(r % Wo); r /= Wo;
   const int yo = (int)(r % Ho); r /= Ho;
-  const int slot = (int)(r % (kPad + Tout));
-  const int b = (int)(r / (kPad + Tout));
-  const int to = slot < kPad ? 0 : slot - kPad;                      // pads replicate output frame 0
-  const float* clip = in + ((int64_t)b * (kPad + Tin) + kPad) * H * W * C + 8 * v;
+  const int slot = (int)(r % (pad + Tout));
+  const int b = (int)(r / (pad + Tout));
+  const int to = slot < pad ? 0 : slot - pad;                      // pads replicate output frame 0
+  const float* clip = in + ((int64_t)b * (pad + Tin) + pad) * H * W * C + 8 * v;
   auto px = [&](int t, int y, int x) { return clip + (((int64_t)t * H + y) * W + x) * C; };
   float acc[8];
   if constexpr (!TIME) {
@@ -74,7 +76,7 @@ upsample2x_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
       }
     }
   }
-  __nv_bfloat16* dst = out + ((((int64_t)b * (kPad + Tout) + slot) * Ho + yo) * Wo + xo) * C + 8 * v;
+  __nv_bfloat16* dst = out + ((((int64_t)b * (pad + Tout) + slot) * Ho + yo) * Wo + xo) * C + 8 * v;
   *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
                                               pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
 }
@@ -154,11 +156,25 @@ extern "C" int dfot_vae_upsample2x_bf16(const float* in, void* out_bf16, int64_t
   const dim3 grid((unsigned)ceil_div(total, vae::kThreads));
   if (temporal)
     launch_pdl(vae::upsample2x_kernel<true>, grid, dim3(vae::kThreads), 0, (cudaStream_t)stream, in,
-               (__nv_bfloat16*)out_bf16, (int)B, (int)T_in, (int)H, (int)W, (int)C);
+               (__nv_bfloat16*)out_bf16, (int)B, (int)T_in, (int)H, (int)W, (int)C, vae::kPad);
   else
     launch_pdl(vae::upsample2x_kernel<false>, grid, dim3(vae::kThreads), 0, (cudaStream_t)stream, in,
-               (__nv_bfloat16*)out_bf16, (int)B, (int)T_in, (int)H, (int)W, (int)C);
+               (__nv_bfloat16*)out_bf16, (int)B, (int)T_in, (int)H, (int)W, (int)C, vae::kPad);
   DFOT_CHECK_LAUNCH("vae_upsample2x");
+  return DFOT_OK;
+}
+
+extern "C" int dfot_upsample2x_nearest_bf16(const float* in, void* out_bf16, int64_t n_img, int64_t H, int64_t W, int64_t C,
+                                            void* stream) {
+  DFOT_REQUIRE(in && out_bf16 && n_img > 0 && H > 0 && W > 0 && C > 0, DFOT_ERR_INVALID_ARG,
+               "upsample2x_nearest: bad arguments");
+  DFOT_REQUIRE(C % 8 == 0 && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out_bf16 % 16 == 0), DFOT_ERR_UNSUPPORTED,
+               "upsample2x_nearest: C %% 8 == 0 and 16-byte aligned pointers required");
+  const int64_t total = n_img * 4 * H * W * (C / 8);
+  DFOT_REQUIRE(total < (1ll << 40) && n_img < (1ll << 31), DFOT_ERR_UNSUPPORTED, "upsample2x_nearest: problem too large");
+  launch_pdl(vae::upsample2x_kernel<false>, dim3((unsigned)ceil_div(total, vae::kThreads)), dim3(vae::kThreads), 0,
+             (cudaStream_t)stream, in, (__nv_bfloat16*)out_bf16, (int)n_img, 1, (int)H, (int)W, (int)C, 0);
+  DFOT_CHECK_LAUNCH("upsample2x_nearest");
   return DFOT_OK;
 }
 

@@ -298,6 +298,16 @@ def vae_upsample2x_bf16(x, out, B, T_in, H, W, C, temporal):
     _abi.check(rc, "vae_upsample2x_bf16")
 
 
+def upsample2x_nearest_bf16(x, out, n_img, H, W, C):
+    """fp32 images [n_img, H, W, C] -> bf16 [n_img, 2H, 2W, C], nearest x2 (the ImageVAE decoder's Upsample)."""
+    _need(x, torch.float32, "x")
+    _need(out, torch.bfloat16, "out")
+    if x.numel() != n_img * H * W * C or out.numel() != 4 * x.numel():
+        raise RuntimeError("dfot_b200: upsample2x_nearest shape mismatch")
+    rc = _abi.lib().dfot_upsample2x_nearest_bf16(x.data_ptr(), out.data_ptr(), n_img, H, W, C, _stream())
+    _abi.check(rc, "upsample2x_nearest_bf16")
+
+
 def vae_fill_pad_frames(x, B, T, frame_elems):
     """pad slots (2 per clip) of a bf16 clip [B, 2+T, ...] <- the clip's first frame."""
     _need(x, torch.bfloat16, "x")

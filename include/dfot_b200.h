@@ -262,6 +262,10 @@ DFOT_API int dfot_groupnorm_apply_bf16(const float* x, const double* sums, const
                               int64_t groups, int silu, void* stream);
 DFOT_API int dfot_vae_upsample2x_bf16(const float* in, void* out_bf16, int64_t B, int64_t T_in, int64_t H, int64_t W,
                              int64_t C, int temporal, void* stream);
+/* nearest x2 of a plain image batch, fp32 [n_img, H, W, C] -> bf16 [n_img, 2H, 2W, C]: the interpolation of `Upsample`
+   in the reference's ImageVAE decoder (algorithms/vae/common/modules/updownsample.py:10-24) */
+DFOT_API int dfot_upsample2x_nearest_bf16(const float* in, void* out_bf16, int64_t n_img, int64_t H, int64_t W, int64_t C,
+                                 void* stream);
 DFOT_API int dfot_vae_fill_pad_frames(void* x_bf16, int64_t B, int64_t T, int64_t frame_elems, void* stream);
 DFOT_API int dfot_softmax_rows_bf16(const float* s, int64_t ld_s, void* p_bf16, int64_t ld_p, int64_t rows, int64_t n,
                            float scale, void* stream);

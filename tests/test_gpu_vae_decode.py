@@ -137,3 +137,67 @@ def test_sample_all_videos_decodes_latents():
     algo.vae = vae
     batch = algo.on_after_batch_transfer({"latents": latents, "videos": gt})
     assert torch.equal(algo._sample_all_videos(batch)["gt"], gt)
+
+
+# ---------------------------------------------------------------------------------------------- ImageVAE (2-D decoder)
+def _image_model(dd, embed, seed):
+    from dfot_b200.algorithms.vae import ImageVAE
+    from oracle.image_vae import image_decoder_param_shapes, seeded_image_weights
+    shapes = image_decoder_param_shapes(dd["ch"], dd["z_channels"], embed, tuple(dd["ch_mult"]), dd["num_res_blocks"])
+    sd = seeded_image_weights(shapes, seed)
+    m = ImageVAE(dict(ddconfig=dd, embed_dim=embed))
+    m.load_state_dict(sd)
+    return m.to(DEV), sd
+
+
+def test_image_decode_matches_reference_fixture():
+    with open(os.path.join(GOLDEN, "vae_image_decode.json")) as f:
+        c = json.load(f)["case"]
+    arr = dict(np.load(os.path.join(GOLDEN, "vae_image_decode.npz")))
+    m, _ = _image_model(c["ddconfig"], c["embed_dim"], c["weight_seed"])
+    images = m.decode(torch.from_numpy(arr["z"]).to(DEV))
+    assert list(images.shape) == list(arr["images"].shape)
+    rel, psnr = _errors(images, torch.from_numpy(arr["images"]))
+    print(f"image fixture: rel {rel:.3e} psnr {psnr:.1f} dB")
+    assert rel <= REL_TOL and psnr >= PSNR_MIN
+
+
+@pytest.mark.parametrize("ch,mult,n,hw", [(128, (1, 2, 4, 4), 5, 8), (64, (1, 2), 3, 16), (32, (1, 2, 4, 4), 20, 4)])
+def test_image_decode_matches_oracle(ch, mult, n, hw):
+    """configurations/algorithm/image_vae.yaml's ddconfig (ch 128, mult 1-2-4-4, z 4) and two other topologies, with the
+    oracle's torch fp32 ops executed on the GPU (TF32 off) for the wide one."""
+    from oracle.image_vae import ImageVAEDecoderOracle
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dd = dict(double_z=True, z_channels=4, resolution=hw * 2 ** (len(mult) - 1), in_channels=3, out_ch=3, ch=ch,
+              ch_mult=list(mult), num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    m, sd = _image_model(dd, 4, seed=ch + n)
+    z = torch.randn((n, 4, hw, hw), generator=torch.Generator().manual_seed(n)).to(DEV)
+    ref = ImageVAEDecoderOracle({k: v.to(DEV) for k, v in sd.items()}, mult).decode(z)
+    got = m.decode(z)
+    assert got.shape == ref.shape == (n, 3, hw * 2 ** (len(mult) - 1), hw * 2 ** (len(mult) - 1))
+    rel, psnr = _errors(got, ref)
+    print(f"image oracle case: rel {rel:.3e} psnr {psnr:.1f} dB")
+    assert rel <= REL_TOL and psnr >= PSNR_MIN
+
+
+def test_decode_of_image_latents_through_the_algorithm():
+    """`_decode` of a [b, t, c, h, w] latent video with an image VAE (temporal downsampling 1): frames go through the
+    decoder as a batch of images in chunks of vae.batch_size clips (base_pytorch_video_algo.py:555-629)."""
+    from dfot_b200.algorithms.dfot.dfot_video import DFoTVideo
+    from oracle.cases import algorithm_cfg
+    from oracle.image_vae import ImageVAEDecoderOracle
+    cfg = algorithm_cfg(**{"backbone.hidden_size": 64, "backbone.depth": 1, "backbone.num_heads": 1, "x_shape": [3, 64, 64],
+                           "latent.enabled": True, "latent.downsampling_factor": [1, 8], "latent.num_channels": 4,
+                           "max_frames": 4, "n_frames": 4, "vae.batch_size": 2})
+    algo = DFoTVideo(cfg).to(DEV).eval()
+    assert algo.x_shape == [4, 8, 8] and not algo.is_latent_video_vae
+    dd = dict(double_z=True, z_channels=4, resolution=64, in_channels=3, out_ch=3, ch=32, ch_mult=[1, 2, 2, 4],
+              num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    algo.vae, sd = _image_model(dd, 4, seed=2)
+    lat = torch.randn((3, 4, 4, 8, 8), generator=torch.Generator().manual_seed(4)).to(DEV)
+    frames = algo._decode(lat)
+    assert frames.shape == (3, 4, 3, 64, 64)
+    ref = ImageVAEDecoderOracle(sd, (1, 2, 2, 4)).decode(lat.cpu().reshape(12, 4, 8, 8)).reshape(3, 4, 3, 64, 64) * 0.5 + 0.5
+    rel, psnr = _errors(frames, ref)
+    assert rel <= REL_TOL and psnr >= PSNR_MIN

@@ -70,6 +70,7 @@ def test_run_vae_layout_and_chunking():
             torch.nn.Module.__init__(self)
             self.cfg = to_config({"vae": {"batch_size": 2}})
             self.temporal_downsampling_factor = 4
+            self.is_latent_video_vae = True
             self.vae = None
             self.calls = []
 
@@ -87,3 +88,84 @@ def test_run_vae_layout_and_chunking():
     assert torch.equal(out[:, 0, :, ::2, ::2], x[:, 0, :3])
     with pytest.raises(NotImplementedError):
         algo._encode(x)
+
+
+def test_run_vae_feeds_image_vaes_frame_by_frame():
+    from dfot_b200.algorithms.common.base_pytorch_video_algo import BaseVideoAlgo
+    from dfot_b200.config import to_config
+
+    class Stub(BaseVideoAlgo):
+        def __init__(self):
+            torch.nn.Module.__init__(self)
+            self.cfg = to_config({"vae": {"batch_size": 2}})
+            self.temporal_downsampling_factor = 1
+            self.is_latent_video_vae = False
+            self.vae = None
+            self.calls = []
+
+    algo = Stub()
+
+    def fake_decode(y):                     # (b t) c h w -> (b t) 3 2h 2w
+        algo.calls.append(tuple(y.shape))
+        return y[:, :3].repeat_interleave(2, 2).repeat_interleave(2, 3)
+
+    x = torch.arange(3 * 4 * 5 * 2 * 2, dtype=torch.float32).reshape(3, 4, 5, 2, 2)         # b t c h w
+    out = algo._run_vae(x, "b t c h w", fake_decode)
+    assert out.shape == (3, 4, 3, 4, 4)
+    assert algo.calls == [(8, 5, 2, 2), (4, 5, 2, 2)]
+    assert torch.equal(out[:, :, :, ::2, ::2], x[:, :, :3])
+
+
+def test_image_vae_keys_checkpoint_and_refusals(tmp_path):
+    from dfot_b200.algorithms.vae import ImageVAE
+    from oracle.image_vae import image_decoder_param_shapes, seeded_image_weights
+    with open(os.path.join(GOLDEN, "vae_image_decode.json")) as f:
+        meta = json.load(f)
+    c = meta["case"]
+    dd = c["ddconfig"]
+    m = ImageVAE(dict(ddconfig=dd, embed_dim=c["embed_dim"]))
+    assert list(m.state_dict().keys()) == meta["keys"]
+    shapes = image_decoder_param_shapes(dd["ch"], dd["z_channels"], c["embed_dim"], tuple(dd["ch_mult"]), dd["num_res_blocks"])
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == dict(shapes)
+    sd = seeded_image_weights(shapes, 3)
+    full = {"encoder.conv_in.weight": torch.zeros(32, 3, 3, 3), "loss.logvar": torch.zeros(())}
+    full.update(sd)
+    path = str(tmp_path / "image_vae.ckpt")
+    torch.save({"cfg": dict(ddconfig=dd, embed_dim=c["embed_dim"]), "state_dict": full}, path)
+    got = ImageVAE.from_pretrained(path).state_dict()
+    assert all(torch.equal(got[k], sd[k]) for k in sd) and len(got) == len(sd)
+    with pytest.raises(NotImplementedError):
+        ImageVAE.from_pretrained("diffuser:madebyollin/sdxl-vae-fp16-fix")
+    with pytest.raises(NotImplementedError):
+        ImageVAE(dict(ddconfig={**dd, "attn_resolutions": [16]}, embed_dim=4))
+    with pytest.raises(NotImplementedError):
+        m.encode(torch.zeros(1))
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m.decode(torch.zeros(1, 4, 8, 8))
+
+
+def test_weights_pack_into_kernel_layout():
+    """[Cout, kt, 3, 3, Cin] bf16 conv weights (Cin of conv_in / post_quant padded to one K tile, Cout of conv_out to 8),
+    [Cout, Cin] for 1x1 convolutions, fp32 biases and norm affine pairs — for both decoders."""
+    from dfot_b200.algorithms.vae import ImageVAE
+    v = VideoVAE(hidden_size=32, z_channels=4, embed_dim=4, hidden_size_mult=(1, 2, 2, 2))
+    P = v._pack(torch.device("cpu"))
+    assert tuple(P["decoder.conv_in"][0].shape) == (64, 3, 3, 3, 64) and P["decoder.conv_in"][0].dtype == torch.bfloat16
+    assert tuple(P["post_quant_conv"][0].shape) == (64, 64) and tuple(P["decoder.conv_out"][0].shape) == (8, 3, 3, 3, 32)
+    assert tuple(P["decoder.up.1.upsample.conv"][0].shape) == (64, 1, 3, 3, 64)
+    assert tuple(P["decoder.up.2.upsample.conv"][0].shape) == (64, 3, 3, 3, 64)
+    assert tuple(P["decoder.mid.attn_1.q"][0].shape) == (64, 64) and tuple(P["decoder.norm_out"][0].shape) == (32,)
+    w = v.state_dict()["decoder.mid.block_1.conv1.conv.weight"]
+    assert torch.equal(P["decoder.mid.block_1.conv1"][0], w.permute(0, 2, 3, 4, 1).to(torch.bfloat16))
+    dd = dict(double_z=True, z_channels=4, resolution=32, in_channels=3, out_ch=3, ch=32, ch_mult=[1, 2, 2],
+              num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    m = ImageVAE(dict(ddconfig=dd, embed_dim=4))
+    P = m._pack(torch.device("cpu"))
+    assert tuple(P["decoder.conv_in"][0].shape) == (64, 1, 3, 3, 64) and tuple(P["decoder.conv_out"][0].shape) == (8, 1, 3, 3, 32)
+    assert tuple(P["decoder.up.1.upsample.conv"][0].shape) == (64, 1, 3, 3, 64) and tuple(P["post_quant_conv"][0].shape) == (64, 64)
+    assert tuple(P["decoder.up.0.block.0.nin_shortcut"][0].shape) == (32, 64) and "decoder.up.1.block.0.nin_shortcut" not in P
+    w = m.state_dict()["decoder.mid.block_2.conv2.weight"]
+    assert torch.equal(P["decoder.mid.block_2.conv2"][0][:, 0], w.permute(0, 2, 3, 1).to(torch.bfloat16))
+    n_convs = sum(1 for k, t in m.state_dict().items() if t.ndim == 4)
+    n_norms = sum(1 for k, t in m.state_dict().items() if t.ndim == 1 and k.endswith(".weight"))
+    assert len(P) - 1 == n_convs + n_norms
