@@ -17,9 +17,12 @@ run() { # name, timeout, command...
 run t_kernels 600 python -m pytest tests/test_gpu_kernels.py -q --timeout 120
 run t_uvit_kernels 600 python -m pytest tests/test_gpu_uvit_kernels.py -q --timeout 120
 run t_parity 900 python -m pytest tests/test_gpu_parity.py -q --timeout 600
+run t_vae_kernels 600 python -m pytest tests/test_gpu_vae_kernels.py -q --timeout 120
+run t_vae_decode 600 python -m pytest tests/test_gpu_vae_decode.py -q --timeout 300
 run smoke 600 python __graft_entry__.py smoke
 if [ "${1:-}" != "nobench" ]; then
   run bench_re10k 900 python bench.py --steps 3 --warmup 3
   run bench_k600 900 python bench.py --workload k600 --steps 3 --warmup 3
   run bench_ref 600 python bench.py --impl reference --steps 1 --warmup 0
+  run bench_vae 300 python scripts/bench_vae_decode.py --batch 8
 fi

@@ -181,9 +181,64 @@ def noise_features(levels, out, fourier_freqs=None, fourier_phases=None):
     out.copy_(v.reshape(out.shape).to(BF))
 
 
+# ------------------------------------------------------------------ VAE-decode row (clips [B, 2 + T, H, W, C])
+def conv3d_causal_bf16(x, w, out, epilogue, bias=None, resid=None):
+    assert x.dtype == BF and w.dtype == BF
+    kt = w.shape[1]
+    xs = x.float().permute(3, 0, 1, 2)[None]                                    # [1, Cin, n_in, H, W]
+    y = F.conv3d(xs, w.float().permute(0, 4, 1, 2, 3), None, padding=(0, 1, 1))[0].permute(1, 2, 3, 0)
+    assert y.shape[0] == x.shape[0] - kt + 1
+    _epilogue(y.reshape(-1, w.shape[0]), out, epilogue, bias, resid)
+
+
+def _strided_images(x, n_img, HW, img_stride, C):
+    return torch.as_strided(x, (n_img, HW, C), (img_stride, C, 1))
+
+
+def groupnorm_stats_strided(x, sums, n_img, HW, img_stride, C, groups=32, eps=1e-6):
+    groupnorm_stats(_strided_images(x, n_img, HW, img_stride, C), sums, n_img, HW, C, groups, eps)
+
+
+def groupnorm_apply_bf16(x, sums, gamma, beta, out, n_img, HW, img_stride, C, groups=32, silu=True):
+    xg = _strided_images(x, n_img, HW, img_stride, C).float().reshape(n_img, HW, groups, C // groups)
+    y = ((xg - sums[..., 0].float()[:, None, :, None]) * sums[..., 1].float()[:, None, :, None]).reshape(n_img, HW, C)
+    y = y * gamma + beta
+    if silu:
+        y = F.silu(y)
+    _strided_images(out, n_img, HW, img_stride, C).copy_(y.to(BF))
+
+
+def vae_fill_pad_frames(x, B, T, frame_elems):
+    v = x.view(B, 2 + T, frame_elems)
+    v[:, :2] = v[:, 2:3]
+
+
+def vae_upsample2x_bf16(x, out, B, T_in, H, W, C, temporal):
+    v = x.view(B, 2 + T_in, H, W, C)[:, 2:].float().permute(0, 4, 1, 2, 3)         # b c t h w
+    if not temporal:
+        y = F.interpolate(v.reshape(B, C * T_in, H, W), scale_factor=(2, 2), mode="nearest").reshape(B, C, T_in, 2 * H, 2 * W)
+    else:
+        y = F.interpolate(v[:, :, :1], scale_factor=(1, 2, 2), mode="trilinear")
+        if T_in > 1:
+            y = torch.cat([y, F.interpolate(v[:, :, 1:], scale_factor=(2, 2, 2), mode="trilinear")], 2)
+    o = out.view(B, 2 + y.shape[2], 2 * H, 2 * W, C)
+    o[:, 2:] = y.permute(0, 2, 3, 4, 1).to(BF)
+    o[:, :2] = o[:, 2:3]
+
+
+def upsample2x_nearest_bf16(x, out, n_img, H, W, C):
+    y = F.interpolate(x.view(n_img, H, W, C).float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    out.view(n_img, 2 * H, 2 * W, C).copy_(y.permute(0, 2, 3, 1).to(BF))
+
+
+def softmax_rows_bf16(s, p, scale=1.0):
+    p.copy_(torch.softmax(s.float() * scale, -1).to(BF))
+
+
 ALL = ["cast_bf16", "patchify_bf16", "unpatchify", "gemm_bf16", "conv3x3_bf16", "groupnorm_stats", "groupnorm_silu_bf16",
        "rmsnorm_film_bf16", "qk_norm_rope", "attention", "avgpool2x2", "sub_bf16", "upsample2x_add", "pose_ray_patches",
-       "noise_features"]
+       "noise_features", "conv3d_causal_bf16", "groupnorm_stats_strided", "groupnorm_apply_bf16",
+       "vae_upsample2x_bf16", "upsample2x_nearest_bf16", "vae_fill_pad_frames", "softmax_rows_bf16"]
 
 
 def install(monkeypatch):

@@ -169,3 +169,38 @@ def test_weights_pack_into_kernel_layout():
     n_convs = sum(1 for k, t in m.state_dict().items() if t.ndim == 4)
     n_norms = sum(1 for k, t in m.state_dict().items() if t.ndim == 1 and k.endswith(".weight"))
     assert len(P) - 1 == n_convs + n_norms
+
+
+def test_decoder_host_orchestration_with_emulated_kernels(monkeypatch):
+    """Both decoders' host side (weight packing, padded-clip buffer flow, pointer offsets of the causal convolutions,
+    strided GroupNorm, per-frame attention GEMMs, upsampling schedule) driven on the CPU by contract emulations of the
+    kernels (tests/ops_emulation.py, bf16 operand rounding included) against the fixtures of the executed reference."""
+    import numpy as np
+    import ops_emulation
+    from dfot_b200.algorithms.vae import ImageVAE
+    from oracle.image_vae import image_decoder_param_shapes, seeded_image_weights
+    ops_emulation.install(monkeypatch)
+
+    def close(got, ref):
+        got, ref = got.float(), torch.from_numpy(ref)
+        assert list(got.shape) == list(ref.shape)
+        assert ((got - ref).norm() / ref.norm()).item() <= 2e-2
+
+    c = _meta()["case"]
+    arr = dict(np.load(os.path.join(GOLDEN, "vae_video_decode.npz")))
+    v = VideoVAE(hidden_size=c["hidden_size"], z_channels=c["z_channels"], embed_dim=c["embed_dim"],
+                 hidden_size_mult=tuple(c["hidden_size_mult"]))
+    v.load_state_dict(seeded_weights(decoder_param_shapes(c["hidden_size"], c["z_channels"], c["embed_dim"],
+                                                          tuple(c["hidden_size_mult"])), c["weight_seed"]))
+    z = torch.from_numpy(arr["z"])
+    close(v.decode(z, c["temporal_length"]), arr["video"])
+    close(v.decode(z[:, :, :2].contiguous(), 5), arr["short"])
+
+    with open(os.path.join(GOLDEN, "vae_image_decode.json")) as f:
+        ci = json.load(f)["case"]
+    dd = ci["ddconfig"]
+    arr = dict(np.load(os.path.join(GOLDEN, "vae_image_decode.npz")))
+    m = ImageVAE(dict(ddconfig=dd, embed_dim=ci["embed_dim"]))
+    m.load_state_dict(seeded_image_weights(image_decoder_param_shapes(dd["ch"], dd["z_channels"], ci["embed_dim"],
+                                                                      tuple(dd["ch_mult"]), dd["num_res_blocks"]), ci["weight_seed"]))
+    close(m.decode(torch.from_numpy(arr["z"])), arr["images"])
