@@ -258,6 +258,9 @@ class _DecoderOnKernels(nn.Module):
         decoded ones, T')."""
         dev, pad = z_cl.device, self.pad
         P = self._pack(dev)
+        sig = (B, T, H, W, str(dev))
+        if self._ws.get("sig") != sig:                          # one workspace set per input shape: a new shape frees the old
+            self._ws = {"sig": sig}
         # latent -> channel-last (padded) bf16 clip (layout change of a tiny tensor; channels zero-padded to one K tile)
         z16 = self._buf("z16", (B, pad + T, H, W, _CMIN), torch.bfloat16, dev)
         z16[:, pad:, :, :, :Cz] = z_cl
