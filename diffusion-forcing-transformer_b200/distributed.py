@@ -8,6 +8,8 @@ sequence:
                round (independent `_sample_sequence` calls) are dealt round-robin over the dp axis; every other shard
                replays the batch's noise draws only, and the owner broadcasts the finished batch
                (`broadcast_from_shard`), so the result equals the single-GPU rollout;
+  * VAE decode — after the final gather every rank holds every sampled latent; the decode (per-sample independent) is
+               dealt over ALL ranks and gathered once (`decode_sharded`);
   * history-guidance branches — within a branch group of `br` ranks (br divides nfe) each rank runs the backbone
                on its share of the branch rows of every sample; one all_gather of the backbone output per step,
                after which every member runs the identical fused K4 step (same noise seed), so x_t stays replicated.
@@ -105,3 +107,18 @@ def broadcast_from_shard(t: torch.Tensor, owner_dp_index: int, mesh: Mesh) -> to
         return t
     dist.broadcast(t, src=owner_dp_index * mesh.br + mesh.br_index, group=mesh.dp_group if mesh.br > 1 else None)
     return t
+
+
+def decode_sharded(decode_fn, latents: torch.Tensor) -> torch.Tensor:
+    """VAE decode of a batch every rank holds (the state after `gather_samples`): samples are independent, so rank r
+    decodes samples [r * per, (r + 1) * per) (indices past the batch repeat the last sample so shapes agree) and one
+    all_gather over the whole world returns the decoded batch to every rank.  No process group: plain `decode_fn`."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return decode_fn(latents)
+    world, rank, n = dist.get_world_size(), dist.get_rank(), latents.shape[0]
+    per = (n + world - 1) // world
+    idx = torch.arange(rank * per, (rank + 1) * per, device=latents.device).clamp(max=n - 1)
+    mine = decode_fn(latents.index_select(0, idx)).contiguous()
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    return torch.cat(parts, 0)[:n]

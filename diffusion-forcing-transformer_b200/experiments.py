@@ -67,6 +67,7 @@ class SamplingExperiment:
                 else:
                     pred = algo._interpolate_videos(batch["xs"], conditions=batch["conditions"])
                 videos[task] = algo._unnormalize_x(pred).detach()
+            videos = self._decode_latents(videos, batch)
             if dev.type == "cuda":
                 torch.cuda.synchronize(dev)
             self.stats["seconds"] += time.perf_counter() - t0
@@ -75,6 +76,17 @@ class SamplingExperiment:
             self.stats["videos"] += batch["xs"].shape[0]
             out.append(videos)
         return out
+
+    def _decode_latents(self, videos: Dict[str, torch.Tensor], batch: Dict) -> Dict[str, torch.Tensor]:
+        """The latent -> pixel step of `_sample_all_videos` (dfot_video.py:104-111) for latent configurations with a VAE
+        configured (`vae.pretrained_path`, or an `algo.vae` attached): every entry is decoded, sharded over all ranks;
+        `gt` comes from the dataset's videos when the batch carries them."""
+        algo = self.algo
+        if not (algo.is_latent_diffusion and (algo.vae is not None or (algo.cfg.get("vae") or {}).get("pretrained_path"))):
+            return videos
+        from dfot_b200 import distributed as D
+        gt = batch.get("gt_videos")
+        return {k: (gt if k == "gt" and gt is not None else D.decode_sharded(algo._decode, v)) for k, v in videos.items()}
 
 
 def _load_tree(path: str):

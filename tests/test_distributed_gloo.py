@@ -122,3 +122,61 @@ def test_world2_interpolation_chunks_are_sharded(case, tmp_path):
     assert np.array_equal(got, want)
     rows = [int(np.load(out_path + f".rows{r}.npy")[0]) for r in range(world)]
     assert max(rows) < _single.nfe_rows and sum(rows) > _single.nfe_rows    # interpolation split, keyframes replicated
+
+
+# ------------------------------------------------------------------------------------------------ sharded VAE decode
+def _vae_for_gloo():
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ops_emulation
+    from dfot_b200.algorithms.vae import VideoVAE
+    from oracle.video_vae import decoder_param_shapes, seeded_weights
+    vae = VideoVAE(hidden_size=32, z_channels=4, embed_dim=4, hidden_size_mult=(1, 2, 2, 2))
+    vae.load_state_dict(seeded_weights(decoder_param_shapes(32, 4, 4, (1, 2, 2, 2)), 11))
+    restore = ops_emulation.install_raw()
+    z = torch.randn((5, 4, 2, 4, 4), generator=torch.Generator().manual_seed(3))      # 5 clips: uneven over 2 and 3 ranks
+    return vae, z, restore
+
+
+def _decode_worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        vae, z, _ = _vae_for_gloo()
+        from dfot_b200 import distributed as D
+        calls = []
+
+        def decode(lat):
+            calls.append(lat.shape[0])
+            return vae.decode(lat, 5)
+        out = D.decode_sharded(decode, z)
+        np.save(out_path + f".{rank}.npy", out.numpy())
+        np.save(out_path + f".calls{rank}.npy", np.array(calls))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_vae_decode_sharded_over_ranks_equals_single_process(world, tmp_path):
+    """`decode_sharded` (the decode after the final sample gather): every rank decodes ceil(5 / world) clips, one
+    all_gather, and every rank ends with the single-process result bit for bit (kernels: CPU contract emulations; the
+    single process decodes the same chunks, since the CPU convolution's blocking — hence its rounding — depends on the
+    batch size)."""
+    from dfot_b200 import ops
+    real_ops = dict(vars(ops))
+    per = -(-5 // world)
+    try:
+        vae, z, _ = _vae_for_gloo()
+        chunks = [torch.arange(r * per, (r + 1) * per).clamp(max=4) for r in range(world)]
+        ref = torch.cat([vae.decode(z[i], 5) for i in chunks], 0)[:5].numpy()
+    finally:
+        for k, v in real_ops.items():
+            setattr(ops, k, v)
+    out_path = str(tmp_path / "dec")
+    port = 29640 + world
+    mp.spawn(_decode_worker, args=(world, port, out_path), nprocs=world, join=True)
+    for r in range(world):
+        got = np.load(out_path + f".{r}.npy")
+        assert got.shape == ref.shape == (5, 3, 5, 32, 32)
+        assert np.array_equal(got, ref)
+        assert list(np.load(out_path + f".calls{r}.npy")) == [per]

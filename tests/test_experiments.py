@@ -32,3 +32,33 @@ def test_driver_matches_reference_rollout(monkeypatch, tmp_path):
     rng = float(ref.max() - ref.min())
     assert 10 * np.log10(rng * rng / max(mse, 1e-30)) >= 40.0
     assert torch.allclose(out["gt"], videos, atol=1e-6)
+
+
+def test_driver_decodes_latents_with_the_configured_vae(monkeypatch, tmp_path):
+    """Latent-video configuration (temporal downsampling 4): the driver loads the VideoVAE named by `vae.pretrained_path`
+    with the reference's checkpoint rules and returns decoded frames (dfot_video.py:104-111), `gt` from the dataset's
+    videos when present.  The sampler is stubbed to the identity — the decode plumbing is what is under test."""
+    from oracle.cases import algorithm_cfg
+    from oracle.video_vae import VideoVAEDecoderOracle, decoder_param_shapes, seeded_weights
+    mult = (1, 2, 2, 2)
+    sd = seeded_weights(decoder_param_shapes(32, 4, 4, mult), 11)
+    vae_ckpt = str(tmp_path / "vae.ckpt")
+    torch.save({"model_cfg": dict(hidden_size=32, z_channels=4, embed_dim=4, hidden_size_mult=list(mult), resolution=32,
+                                  temporal_length=9),
+                "optimizer_states": [], "state_dict": {f"vae.{k}": v for k, v in sd.items()}}, vae_ckpt)
+    cfg = algorithm_cfg(**{"backbone.hidden_size": 64, "backbone.depth": 1, "backbone.num_heads": 1, "x_shape": [3, 32, 32],
+                           "latent.enabled": True, "latent.downsampling_factor": [4, 8], "latent.num_channels": 4,
+                           "max_frames": 9, "n_frames": 9, "context_frames": 5, "vae.pretrained_path": vae_ckpt,
+                           "vae.batch_size": 2, "data_mean": [[[0.2]]] * 4, "data_std": [[[2.0]]] * 4})
+    ops_emulation.install(monkeypatch)
+    exp = SamplingExperiment(cfg, None)
+    monkeypatch.setattr(exp.algo, "sample_sharded", lambda xs, conds, n_ctx: xs)
+    latents = torch.randn((3, 3, 4, 4, 4), generator=torch.Generator().manual_seed(0))
+    out = exp.run_validation([{"latents": latents}])[0]
+    assert out["prediction"].shape == out["gt"].shape == (3, 9, 3, 32, 32)
+    ref = VideoVAEDecoderOracle(sd, mult).decode(latents.permute(0, 2, 1, 3, 4), 9).permute(0, 2, 1, 3, 4) * 0.5 + 0.5
+    for k in ("gt", "prediction"):
+        assert ((out[k] - ref).norm() / ref.norm()).item() <= 2e-2
+    gt = torch.rand((3, 9, 3, 32, 32))
+    out = exp.run_validation([{"latents": latents, "videos": gt}])[0]
+    assert torch.equal(out["gt"], gt)
