@@ -346,7 +346,11 @@ class VideoVAE(_DecoderOnKernels):
             # EMA weights are stored as a list in the FULL model's named_parameters() order; names are needed to pick the
             # decode side, so the checkpoint's own state_dict supplies them
             names = [k.replace("vae.", "", 1) for k in ckpt["state_dict"] if k.startswith("vae.")]
-            full = dict(zip(names, ckpt["optimizer_states"][0]["ema"]))
+            ema = ckpt["optimizer_states"][0]["ema"]
+            if len(names) != len(ema):
+                raise RuntimeError(f"VideoVAE.from_pretrained: {len(ema)} EMA tensors for {len(names)} `vae.*` entries of "
+                                   "the state_dict — cannot name the EMA weights")
+            full = dict(zip(names, ema))
         else:
             full = {k.replace("vae.", "", 1): v for k, v in ckpt["state_dict"].items() if k.startswith("vae.")}
         missing = [n for n in own if n not in full]
