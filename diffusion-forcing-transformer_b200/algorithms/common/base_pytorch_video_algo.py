@@ -196,6 +196,24 @@ class BaseVideoAlgo(nn.Module):
                     levels[i * horizon + j, j + 1:] = prev_last[j + 1:]
         return torch.nn.functional.pad(levels, (0, padding, 0, 0), value=self.timesteps - 1)
 
+    def _generate_refine_scheduling_matrix(self, horizon: int, goback_length: int, n_goback: int,
+                                           padding: int = 0) -> Tensor:
+        """(:949-976, fork-only refinement sampling) the DDIM index walk S .. 0 which, after every index t in
+        range(1, S - goback_length, goback_length), climbs back to t + goback_length and descends to t again, n_goback
+        times; indices -> noise levels; pad columns are pure noise."""
+        assert self.cfg.scheduling_matrix == "full_sequence", "Refining only support full_sequence scheduling matrix"
+        S = self.sampling_timesteps
+        goback = set(range(1, S - goback_length, goback_length))
+        walk = []
+        for t in range(S, -1, -1):
+            walk.append(t)
+            if t in goback:
+                for _ in range(n_goback):
+                    walk.extend(range(t + 1, t + goback_length + 1))
+                    walk.extend(range(t + goback_length - 1, t - 1, -1))
+        levels = self.diffusion_model.ddim_idx_to_noise_level(torch.tensor(walk).long())[:, None].repeat(1, horizon)
+        return torch.nn.functional.pad(levels, (0, padding, 0, 0), value=self.timesteps - 1)
+
     def _generate_interleaved_scheduling_matrix(self, horizon: int, interleaved_size: int = 2,
                                                 sampling_timesteps: int = 50) -> np.ndarray:
         S, k = sampling_timesteps, interleaved_size

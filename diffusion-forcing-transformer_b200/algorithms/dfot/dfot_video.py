@@ -155,7 +155,7 @@ class DFoTVideo(BaseVideoAlgo):
             for bi, s in enumerate(range(0, rows, mb)):   # every chunk is processed (the reference's conditions=None
                 e = min(rows, s + mb)                     # path drops the last partial batch — quirk Q10, not replicated)
                 owner = bi % mesh.dp if mesh is not None else 0
-                o, _ = self._sample_sequence(batch_size=e - s, context=ctx[s:e],
+                o, _ = self._window_sampler()(batch_size=e - s, context=ctx[s:e],
                                              context_mask=torch.from_numpy(msk[s:e].astype(np.int64)),
                                              conditions=None if cnd is None else cnd[s:e], history_guidance=guidance,
                                              dry_run=mesh is not None and owner != mesh.dp_index)
@@ -218,10 +218,10 @@ class DFoTVideo(BaseVideoAlgo):
                 else:
                     raise ValueError(f"Unknown external condition type: {self.external_cond_type}. "
                                      "Supported types are 'label' and 'action'.")
-            new, record = self._sample_sequence(B, length=c + h, context=window, context_mask=torch.from_numpy(mask),
-                                                conditions=cond, guidance_fn=guidance_fn,
-                                                reconstruction_guidance=reconstruction_guidance,
-                                                history_guidance=history_guidance, return_all=return_all)
+            new, record = self._window_sampler()(B, length=c + h, context=window, context_mask=torch.from_numpy(mask),
+                                                 conditions=cond, guidance_fn=guidance_fn,
+                                                 reconstruction_guidance=reconstruction_guidance,
+                                                 history_guidance=history_guidance, return_all=return_all)
             xs = torch.cat([xs, new[:, -h:]], 1)
             cur = xs.shape[1]
         return xs, record
@@ -299,6 +299,115 @@ class DFoTVideo(BaseVideoAlgo):
             plans.append(history_guidance.plan_step(dm.host_tables, mask, frm, to, self.is_full_sequence,
                                                     dm.is_continuous, dm.precond_scale))
         return plans
+
+    # ------------------------------------------------------------------ refinement sampling (fork-only, :765-1008)
+    def _window_sampler(self) -> Callable:
+        rs = self.cfg.get("refinement_sampling")
+        return self._sample_sequence_refine if rs is not None and rs.get("enabled") else self._sample_sequence
+
+    @torch.no_grad()
+    def _sample_sequence_refine(self, batch_size: int, goback_length: Optional[int] = None, n_goback: Optional[int] = None,
+                                length: Optional[int] = None, context: Optional[Tensor] = None,
+                                context_mask: Optional[Tensor] = None, conditions: Optional[Tensor] = None,
+                                guidance_fn: Optional[Callable] = None, reconstruction_guidance: float = 0.0,
+                                history_guidance: Optional[HistoryGuidance] = None, return_all: bool = False,
+                                pbar=None, dry_run: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
+        """The window sampler over the refinement walk (`_generate_refine_scheduling_matrix`): a row whose LAST column's
+        level decreases is a denoising step (backbone + fused DDIM update), any other row re-noises every token from its
+        level up to the next one (`q_sample_from_x_k`, one K4 launch).  As in the reference, the loop only works with a
+        single history-guidance branch (its `q_sample(context, to_noise_levels)` at :983 mixes (B, T) data with
+        (B·nfe, T) levels) — that draw is kept for the RNG stream, its result is discarded there as well (:986-989).
+        With the discrete cosine schedule ᾱ[-1] == 0, so the re-noising scale of context tokens (level -1) is 0/0 and
+        the reference's rollout is NaN (quirk Q11); the arithmetic here is the same."""
+        rs = self.cfg.refinement_sampling
+        goback_length = rs.goback_length if goback_length is None else goback_length
+        n_goback = rs.n_goback if n_goback is None else n_goback
+        x_shape = self.x_shape
+        if guidance_fn is not None or reconstruction_guidance > 0:
+            raise NotImplementedError("guidance_fn / reconstruction guidance needs autograd through the backbone "
+                                      "and is outside the dfot_b200 scope (SURVEY.md §3.4)")
+        if dry_run:
+            raise NotImplementedError("refinement sampling is not sharded over interpolation chunk batches")
+        if context is None:
+            raise ValueError("context must be provided")
+        if length is None:
+            length = context.shape[1]
+        if length > self.max_tokens:
+            raise ValueError(f"length is expected to <={self.max_tokens}, got {length}.")
+        if context_mask is None:
+            raise ValueError("context_mask must be provided if context is given.")
+        if context.shape[0] != batch_size:
+            raise ValueError(f"context batch size is expected to be {batch_size} but got {context.shape[0]}.")
+        if context.shape[1] != length:
+            raise ValueError(f"context length is expected to be {length} but got {context.shape[1]}.")
+        if tuple(context.shape[2:]) != tuple(x_shape):
+            raise ValueError(f"context shape not compatible with x_stacked_shape {x_shape}.")
+        if tuple(context.shape[:2]) != tuple(context_mask.shape):
+            raise ValueError("context and context_mask must have the same shape.")
+        dev, dm, B = context.device, self.diffusion_model, batch_size
+        horizon = length if self.use_causal_mask else self.max_tokens
+        padding = horizon - length
+        if dm.noise_source is None and self.generator is not None:
+            x = torch.randn((B, horizon, *x_shape), device=dev, generator=self.generator)
+        else:
+            x = dm.randn((B, horizon, *x_shape), dev)
+        x = torch.clamp(x, -self.clip_noise, self.clip_noise)
+        mask = context_mask.detach().cpu().numpy().astype(np.int64)
+        if padding > 0:
+            context = torch.cat([context, torch.zeros((B, padding, *x_shape), dtype=context.dtype, device=dev)], 1)
+            mask = np.concatenate([mask, -np.ones((B, padding), dtype=np.int64)], 1)
+        if history_guidance is None:
+            history_guidance = HistoryGuidance.conditional(timesteps=self.timesteps)
+        x = torch.where(self._extend_x_dim(torch.from_numpy(mask).to(dev)) >= 1, context.float(), x).contiguous()
+        S = self._generate_refine_scheduling_matrix(horizon - padding, goback_length, n_goback, padding).numpy()
+        S = np.repeat(S[:, None, :], B, axis=1)
+        S = np.where(mask[None] >= 1, -1, S)                                # (:889-891)
+        T = horizon
+        cond = None if conditions is None else self._window_conditions(conditions.to(dev), 1)
+        record = [] if return_all else None
+        spare = torch.empty_like(x)
+        for m in range(S.shape[0] - 1):
+            frm, to = S[m], S[m + 1]
+            if frm[0, -1] > to[0, -1]:
+                mask = np.where((mask == 0) & (frm == -1), 2, mask)
+                if return_all:
+                    record.append(x.clone())
+                p = history_guidance.plan_step(dm.host_tables, mask, frm, to, self.is_full_sequence, dm.is_continuous,
+                                               dm.precond_scale)
+                if p.nfe != 1:
+                    raise NotImplementedError("refinement sampling runs with one history-guidance branch only (the "
+                                              "reference's loop fails for nfe > 1, dfot_video.py:983)")
+                # RNG: q_sample noise of the history tokens, then (full manager) the excluded-token noise — always drawn
+                nh = dm.clipped_noise((p.n_hist_rows, T, *x_shape), dev) if p.n_hist_rows else None
+                ne = dm.randn((B, T, *x_shape), dev) if p.draws_excluded_noise else None
+                model_in = self._model_in_buffer(B, T, dev)
+                ops.sampler_step_hg(x, None, model_in, None, sp.to_device_bytes(p.prepare, dev), None, nh, ne, B, 1, T)
+                self.nfe_rows_planned += B
+                lv = torch.from_numpy(p.levels).to(dev, non_blocking=True)
+                cm = None if p.cond_mask is None else torch.from_numpy(p.cond_mask).to(dev, non_blocking=True)
+                out = self._backbone_rows(model_in, lv, cond, cm, B, 1)
+                self.nfe_rows += B
+                nd = dm.clipped_noise((B, T, *x_shape), dev)                 # RNG: DDIM noise, drawn even when eta == 0
+                trace_in = model_in.float().clone() if self.trace is not None else None
+                ops.sampler_step_hg(x, out, None, sp.to_device_bytes(p.update, dev), None,
+                                    nd if dm.host_tables.eta != 0 else None, None, None, B, 1, T)
+                dm.clipped_noise((B, T, *x_shape), dev)                      # RNG: q_sample(context, to) of :983, unused
+                if self.trace is not None:
+                    self.trace.append(dict(model_in=trace_in, levels_from=p.levels_from, levels_to=p.levels_to,
+                                           cond_mask=p.cond_mask, model_out=out.float().clone(), x_after=x.clone(),
+                                           context_mask=p.context_mask))
+            else:
+                noise = dm.clipped_noise((B, T, *x_shape), dev)
+                prep = dm.renoise_table(frm, to)
+                ops.sampler_step_hg(x, None, spare, None, sp.to_device_bytes(prep, dev), None, noise, None, B, 1, T)
+                x, spare = spare, x
+        if return_all:
+            record.append(x.clone())
+            record = torch.stack(record)
+        if padding > 0:
+            x = x[:, :-padding]
+            record = record[:, :, :-padding] if return_all else None
+        return x, record
 
     # ------------------------------------------------------------------ the hot loop
     @torch.no_grad()

@@ -136,6 +136,34 @@ class DiscreteDiffusion(nn.Module):
                             sp.to_device_bytes(prep, x_start.device), None, noise.contiguous().float(), None, R, 1, T)
         return out
 
+    def renoise_table(self, cur: np.ndarray, nxt: np.ndarray) -> np.ndarray:
+        """Per-frame records of `q_sample_from_x_k` (host): qa = sqrt(s), qb = sqrt(1 - s), s = ᾱ[next] / ᾱ[cur] in fp32
+        (index -1 = last entry, as in the reference), s = 1 where next == 999."""
+        ac = self.host_tables.alphas_cumprod.astype(np.float32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            scale = (ac[nxt] / ac[cur]).astype(np.float32)
+            scale = np.where(nxt == 999, np.float32(1.0), scale)
+            prep = np.zeros(cur.shape, dtype=sp.PREPARE_DTYPE)
+            prep["mode"] = sp.MODE_QSAMPLE
+            prep["noise_row"] = np.arange(cur.shape[0], dtype=np.int32)[:, None]
+            prep["qa"] = np.sqrt(scale)
+            prep["qb"] = np.sqrt(np.float32(1.0) - scale)
+        return prep
+
+    def q_sample_from_x_k(self, x_k: torch.Tensor, cur_noise_levels: torch.Tensor, next_noise_levels: torch.Tensor,
+                          noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(:252-260, refinement sampling) forward diffusion from level `cur` up to level `next`:
+        sqrt(s)·x_k + sqrt(1-s)·noise — one K4 launch in prepare-only mode."""
+        R, T = cur_noise_levels.shape
+        if noise is None:
+            noise = self.clipped_noise(x_k.shape, x_k.device)
+        prep = self.renoise_table(cur_noise_levels.detach().cpu().numpy().astype(np.int64),
+                                  next_noise_levels.detach().cpu().numpy().astype(np.int64))
+        out = torch.empty(x_k.shape, dtype=torch.float32, device=x_k.device)
+        ops.sampler_step_hg(x_k.contiguous().float().clone(), None, out, None, sp.to_device_bytes(prep, x_k.device), None,
+                            noise.contiguous().float(), None, R, 1, T)
+        return out
+
     def model_input_levels(self, k: torch.Tensor) -> torch.Tensor:
         return k
 

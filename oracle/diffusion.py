@@ -48,6 +48,16 @@ class Diffusion:
         s = _per_frame(self.buf["sqrt_one_minus_alphas_cumprod"][k], x0)
         return a * x0 + s * noise
 
+    def q_sample_from_x_k(self, x_k: torch.Tensor, cur: torch.Tensor, nxt: torch.Tensor,
+                          noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        # discrete_diffusion.py:252-260 — forward diffusion from level `cur` up to level `nxt` (refinement sampling)
+        if noise is None:
+            noise = self.clipped_noise(x_k)
+        ac = self.buf["alphas_cumprod"]
+        scale = _per_frame(ac[nxt], x_k) / _per_frame(ac[cur], x_k)
+        scale = torch.where(_per_frame(nxt, x_k) == 999, torch.ones_like(scale), scale)
+        return torch.sqrt(scale) * x_k + torch.sqrt(1 - scale) * noise
+
     def model_input_level(self, k: torch.Tensor) -> torch.Tensor:
         # discrete: int64 k; continuous: fp32 precond_scale * logsnr[k]  (continuous_diffusion.py:118-121)
         return self.precond_scale * self.buf["logsnr"][k] if self.is_continuous else k

@@ -14,7 +14,7 @@ import torch
 
 from . import history_guidance as hg
 from .diffusion import Diffusion
-from .schedule import scheduling_matrix
+from .schedule import refine_scheduling_matrix, scheduling_matrix
 
 
 def interpolation_plan(known: torch.Tensor, max_tokens: int) -> List[List[torch.Tensor]]:
@@ -144,6 +144,58 @@ class SamplerOracle:
                                        context_mask=context_mask.clone()))
         return x[:, :length] if padding > 0 else x
 
+    # dfot_video.py:765-1008 (fork-only): the same window sampler over the refinement walk — a row whose LAST column's
+    # level decreases is a denoising step, any other row re-noises every token from its level up to the next one
+    def sample_sequence_refine(self, batch_size: int, length: Optional[int], context: torch.Tensor,
+                               context_mask: torch.Tensor, conditions=None, scheme: Optional[hg.Scheme] = None):
+        rs = self.cfg["refinement_sampling"]
+        if length is None:
+            length = context.shape[1]
+        if length > self.max_tokens:
+            raise ValueError("length > max_tokens")
+        horizon = length if self.use_causal_mask else self.max_tokens
+        padding = horizon - length
+        x = torch.clamp(self.randn((batch_size, horizon, *self.x_shape)), -self.clip_noise, self.clip_noise)
+        context_mask = context_mask.long()
+        if padding > 0:
+            context = torch.cat([context, torch.zeros((batch_size, padding, *self.x_shape))], 1)
+            context_mask = torch.cat([context_mask, -torch.ones((batch_size, padding), dtype=torch.long)], 1)
+        if scheme is None:
+            scheme = hg.scheme_from_config({"name": "conditional"}, self.timesteps)
+        x = torch.where(self._bcast(context_mask) >= 1, context, x)
+        assert self.cfg["scheduling_matrix"] == "full_sequence", "Refining only support full_sequence scheduling matrix"
+        S = refine_scheduling_matrix(horizon - padding, rs["goback_length"], rs["n_goback"], padding, self.timesteps,
+                                     self.sampling_timesteps)
+        S = S[:, None, :].repeat(1, batch_size, 1)
+        S = torch.where(context_mask[None] >= 1, -1, S)                     # (:889-891) unconditionally here
+        for m in range(S.shape[0] - 1):
+            frm, to = S[m], S[m + 1]
+            if frm[0, -1].item() > to[0, -1].item():
+                context_mask = torch.where((context_mask == 0) & (frm == -1), 2, context_mask)
+                x_prev = x.clone()
+                assert scheme.is_simple and scheme.hist_weights[0] == 1, \
+                    "the reference's refinement loop only runs with one branch (q_sample(context, to) at :983)"
+                xr, f, t, cond_mask = hg.simple_prepare(scheme, context_mask, x, frm, to, self.diffusion.q_sample)
+                cond = None
+                if conditions is not None:
+                    cond = self.process_conditions(conditions.clone(), f)
+                x_new, model_out = self.diffusion.sample_step(xr, f, t, cond, cond_mask, return_model_out=True)
+                composed = hg.simple_compose(scheme, x_new)
+                xc_t = self.diffusion.q_sample(context, t)                   # (:983) draws noise; overwritten below
+                composed = torch.where(self._bcast(context_mask) == 0, composed, xc_t)
+                x = torch.where(self._bcast(context_mask) == 0, composed, x_prev)
+                if self.trace is not None:
+                    self.trace.append(dict(model_in=xr, levels_from=f, levels_to=t, cond_mask=cond_mask,
+                                           model_out=model_out, step_out=x_new, x_after=x.clone(),
+                                           context_mask=context_mask.clone()))
+            else:
+                x = self.diffusion.q_sample_from_x_k(x, frm, to)
+        return x[:, :length] if padding > 0 else x
+
+    def _window(self, *a):
+        fn = self.sample_sequence_refine if self.cfg.get("refinement_sampling", {}).get("enabled") else self.sample_sequence
+        return fn(*a)
+
     # dfot_video.py:362-514
     def predict_sequence(self, context, length=None, conditions=None, scheme=None, sliding_context_len=None):
         if length is None:
@@ -174,7 +226,7 @@ class SamplerOracle:
             if conditions is not None:
                 cond = conditions if self.cfg["external_cond_type"] == "label" else \
                     conditions[:, cur - c: cur - c + cond_len]
-            new = self.sample_sequence(B, c + h, ctx, mask, cond, scheme)
+            new = self._window(B, c + h, ctx, mask, cond, scheme)
             xs = torch.cat([xs, new[:, -h:]], 1)
             cur = xs.shape[1]
         return xs
@@ -222,7 +274,7 @@ class SamplerOracle:
             mb = task.get("max_batch_size") or ctx.shape[0]
             outs = []
             for s in range(0, ctx.shape[0], mb):
-                outs.append(self.sample_sequence(min(mb, ctx.shape[0] - s), None, ctx[s:s + mb],
+                outs.append(self._window(min(mb, ctx.shape[0] - s), None, ctx[s:s + mb],
                                                  msk[s:s + mb].long(), None if cnd is None else cnd[s:s + mb], scheme))
             outs = torch.cat(outs, 0)
             for frames, pred in zip(round_, outs.chunk(len(round_), 0)):

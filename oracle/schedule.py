@@ -171,3 +171,20 @@ def scheduling_matrix(kind: str, horizon: int, padding: int, timesteps: int, sam
             for j in range(horizon):
                 lv[i * horizon + j, j + 1:] = lv[(i - 1) * horizon + horizon - 1, j + 1:]
     return torch.nn.functional.pad(lv, (0, padding, 0, 0), value=timesteps - 1)
+
+
+def refine_scheduling_matrix(horizon: int, goback_length: int, n_goback: int, padding: int, timesteps: int,
+                             sampling_timesteps: int) -> torch.Tensor:
+    """base_pytorch_video_algo.py:949-976 (fork-only refinement sampling, full_sequence only): the DDIM index walk
+    S, S-1, ..., 0 where, after every index t in range(1, S - goback_length, goback_length), the walk goes back up to
+    t + goback_length and down to t again, n_goback times; indices -> levels; pad columns = timesteps - 1."""
+    S = sampling_timesteps
+    goback = set(range(1, S - goback_length, goback_length))
+    walk = []
+    for t in range(S, -1, -1):
+        walk.append(t)
+        if t in goback:
+            for _ in range(n_goback):
+                walk += list(range(t + 1, t + goback_length + 1)) + list(range(t + goback_length - 1, t - 1, -1))
+    lv = ddim_idx_to_noise_level(torch.tensor(walk).long(), timesteps, S)[:, None].repeat(1, horizon)
+    return torch.nn.functional.pad(lv, (0, padding, 0, 0), value=timesteps - 1)

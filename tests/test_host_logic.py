@@ -186,3 +186,45 @@ def test_planner_end_to_end_on_cpu(name, monkeypatch):
             assert err <= 2e-5, (name, i, k, err)
     err = np.abs(out.numpy() - arr["prediction"]).max()
     assert err <= 2e-5, (name, err)
+
+
+# ------------------------------------------------------------------------------------- refinement sampling (fork-only)
+def test_refine_scheduling_matrices_bit_exact():
+    """`_generate_refine_scheduling_matrix` of the product and of the oracle against the executed reference
+    (tests/golden/refine_matrices.json, oracle/make_goldens_refine.py)."""
+    from oracle.schedule import refine_scheduling_matrix
+    with open(os.path.join(GOLDEN, "refine_matrices.json")) as f:
+        recs = json.load(f)
+    assert len(recs) >= 5
+    for r in recs:
+        algo = DFoTVideo(_tiny(**{"diffusion.sampling_timesteps": r["steps"], "max_frames": r["horizon"] + r["padding"]}))
+        m = algo._generate_refine_scheduling_matrix(r["horizon"], r["goback_length"], r["n_goback"], r["padding"])
+        assert m.dtype == torch.int64 and m.tolist() == r["matrix"]
+        o = refine_scheduling_matrix(r["horizon"], r["goback_length"], r["n_goback"], r["padding"], 1000, r["steps"])
+        assert o.tolist() == r["matrix"]
+
+
+def test_q_sample_from_x_k_matches_oracle(monkeypatch):
+    """API parity of `q_sample_from_x_k` (discrete_diffusion.py:252-260): the K4 records built on the host (contract
+    emulation) against the oracle's restatement, context (-1), pad (999) and ordinary levels mixed; continuous schedule
+    (with the discrete cosine schedule ᾱ[-1] = 0 and the context scale is 0/0 in the reference too — quirk Q11)."""
+    from oracle.cases import continuous_overrides
+    from oracle.diffusion import Diffusion
+    monkeypatch.setattr(ops, "sampler_step_hg", k4_emulation.emulate)
+    monkeypatch.setattr(ops, "require_cuda", lambda *a, **k: None)
+    cfg = _tiny(**continuous_overrides())
+    algo = DFoTVideo(cfg)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((2, 4, 4, 8, 8), generator=g)
+    noise = torch.randn((2, 4, 4, 8, 8), generator=g)
+    cur = torch.tensor([[-1, 499, 499, 999], [-1, 19, 665, 999]])
+    nxt = torch.tensor([[-1, 665, 832, 999], [-1, 39, 999, 999]])
+    got = algo.diffusion_model.q_sample_from_x_k(x, cur, nxt, noise)
+    ref = Diffusion(cfg["diffusion"], None).q_sample_from_x_k(x, cur, nxt, noise)
+    assert torch.isfinite(ref).all() and (got - ref).abs().max().item() <= 1e-6
+    assert torch.equal(got[:, 0], x[:, 0]) and torch.equal(got[:, 3], x[:, 3])      # context and pad tokens untouched
+    # the discrete cosine schedule: NaN on the context token in the reference's arithmetic, here as well
+    algo = DFoTVideo(_tiny())
+    bad = algo.diffusion_model.q_sample_from_x_k(x, cur, nxt, noise)
+    ref = Diffusion(_tiny()["diffusion"], None).q_sample_from_x_k(x, cur, nxt, noise)
+    assert torch.isnan(bad[:, 0]).all() and torch.isnan(ref[:, 0]).all() and torch.isfinite(bad[:, 1]).all()
