@@ -36,6 +36,13 @@ class _TimestepMLP(nn.Module):          # diffusers TimestepEmbedding: linear_1 
         self.linear_2 = nn.Linear(dim, dim)
 
 
+class _LabelEmbedding(nn.Module):       # diffusers LabelEmbedding (base_backbone.py:47-51): eval = a table lookup; the
+    def __init__(self, num_classes: int, dim: int, dropout_prob: float):    # extra row is the training-time "dropped" class
+        super().__init__()
+        self.embedding_table = nn.Embedding(num_classes + int(dropout_prob > 0), dim)
+        self.num_classes, self.dropout_prob = num_classes, dropout_prob
+
+
 class _Fourier(nn.Module):              # embeddings.py:94-109 (persistent random buffers)
     def __init__(self, dim: int):
         super().__init__()
@@ -154,8 +161,6 @@ class DiT3D(nn.Module):
         if cfg.get("variant", "full") != "full" or cfg.get("pos_emb_type", "rope_3d") != "rope_3d":
             raise NotImplementedError("dfot_b200 DiT3D supports variant=full with pos_emb_type=rope_3d "
                                       "(the default dit3d.yaml); other variants are fork-only ablations")
-        if external_cond_type == "label" and external_cond_dim:
-            raise NotImplementedError("label conditioning is outside the B200 hot-path scope (SURVEY.md §8)")
         self.cfg = cfg
         self.x_shape = list(x_shape)
         self.max_tokens = max_tokens
@@ -177,7 +182,13 @@ class DiT3D(nn.Module):
 
         self.noise_level_pos_embedding = _NoiseLevelEmbedding(256, D, bool(cfg.get("use_fourier_noise_embedding",
                                                                                   False)))
-        if self.external_cond_dim:
+        self.label_cond = bool(self.external_cond_dim) and external_cond_type == "label"
+        if self.label_cond:
+            self.external_cond_embedding = _LabelEmbedding(external_cond_num_classes, D, self.external_cond_dropout)
+        elif self.external_cond_dim:
+            if external_cond_type != "action":
+                raise ValueError(f"Unknown external condition type: {external_cond_type}. "
+                                 "Supported types are 'label' and 'action'.")
             self.external_cond_embedding = (_TimestepMLP(self.external_cond_dim, D) if self.external_cond_dropout == 0
                                             else _CondEmbeddingDropout(self.external_cond_dim, D))
         else:
@@ -234,7 +245,9 @@ class DiT3D(nn.Module):
         if hasattr(self.noise_level_pos_embedding, "timesteps"):
             P["four_f"] = f32(self.noise_level_pos_embedding.timesteps.freqs)
             P["four_p"] = f32(self.noise_level_pos_embedding.timesteps.phases)
-        if self.external_cond_embedding is not None:
+        if self.label_cond:
+            P["label_table"] = f32(self.external_cond_embedding.embedding_table.weight)
+        elif self.external_cond_embedding is not None:
             ce = self.external_cond_embedding if self.external_cond_dropout == 0 else self.external_cond_embedding.embedding
             kc = _pad8(self.external_cond_dim)
             w1 = torch.zeros((D, kc), device=dev)
@@ -377,13 +390,19 @@ class DiT3D(nn.Module):
         if external_cond is not None:
             if self.external_cond_embedding is None:
                 raise ValueError("external_cond given but the backbone was built with external_cond_dim=0")
-            ws["cin"][:, : self.external_cond_dim] = external_cond.reshape(RT, -1).to(torch.bfloat16)
-            ops.gemm_bf16(ws["cin"], Pk["c1_w"], ws["c1"], ops.EPI_SILU_BF16, bias=Pk["c1_b"])
-            ops.gemm_bf16(ws["c1"], Pk["c2_w"], ws["cemb"], ops.EPI_F32, bias=Pk["c2_b"])
             cemb = ws["cemb"]
-            # embeddings.py:364-387: with dropout_prob == 0 the embedding is a plain MLP and ignores the mask
-            if external_cond_mask is not None and self.external_cond_dropout != 0:
-                row_mask = external_cond_mask.to(torch.uint8).contiguous()
+            if self.label_cond:
+                # dit3d.py:171-173: emb + table[labels]; labels [R, 1] (one per clip, ucf_101.py:304-309) or [R, T]; the
+                # mask is not passed to the label embedding.  The row gather is data movement (torch indexing).
+                lab = external_cond.reshape(R, -1).long()
+                cemb.view(R, T, -1).copy_(Pk["label_table"][lab].expand(R, T, -1))
+            else:
+                ws["cin"][:, : self.external_cond_dim] = external_cond.reshape(RT, -1).to(torch.bfloat16)
+                ops.gemm_bf16(ws["cin"], Pk["c1_w"], ws["c1"], ops.EPI_SILU_BF16, bias=Pk["c1_b"])
+                ops.gemm_bf16(ws["c1"], Pk["c2_w"], ws["cemb"], ops.EPI_F32, bias=Pk["c2_b"])
+                # embeddings.py:364-387: with dropout_prob == 0 the embedding is a plain MLP and ignores the mask
+                if external_cond_mask is not None and self.external_cond_dropout != 0:
+                    row_mask = external_cond_mask.to(torch.uint8).contiguous()
         ops.silu_sum_bf16(ws["emb"], cemb, row_mask, T, ws["cact"])
         ops.gemm_bf16(ws["cact"], Pk["mod_w"], ws["mod"], ops.EPI_F32, bias=Pk["mod_b"])
         mod, ldm = ws["mod"], ws["mod"].shape[1]

@@ -137,7 +137,10 @@ class DiT3DOracle:
         tok = tok.flatten(2).transpose(1, 2).reshape(B, T * self.P, self.D)
         emb = self.noise_embedding(noise_levels)
         if external_cond is not None:
-            emb = emb + self.cond_embedding(external_cond.float(), external_cond_mask)
+            if "external_cond_embedding.embedding_table.weight" in sd:   # label conditioning (dit3d.py:171-173): a table
+                emb = emb + sd["external_cond_embedding.embedding_table.weight"][external_cond.long().reshape(B, -1)]
+            else:
+                emb = emb + self.cond_embedding(external_cond.float(), external_cond_mask)
         c_act = F.silu(emb.repeat_interleave(self.P, dim=1))      # per-token copy of a per-frame vector
         h = tok
         for i in range(self.depth):
