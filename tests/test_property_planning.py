@@ -93,3 +93,22 @@ def test_interpolation_plan_equals_oracle(n_frames, max_tokens, data):
             assert len(c) <= max_tokens and filled[c[0]] and filled[c[-1]]      # every chunk is anchored at both ends
             filled[np.asarray(c)] = True
     assert filled.all()                                                            # the plan reaches every frame
+
+
+@settings(**SETTINGS)
+@given(horizon=st.integers(1, 8), padding=st.integers(0, 3), steps=st.sampled_from([2, 3, 5, 8, 10, 25, 50]),
+       goback_length=st.integers(1, 20), n_goback=st.integers(0, 4))
+def test_refine_scheduling_matrix_equals_oracle(horizon, padding, steps, goback_length, n_goback):
+    """The refinement walk (base_pytorch_video_algo.py:949-976): product == oracle, every row transition moves the walk
+    by exactly one DDIM index, it ends at level -1, and it has steps + 1 + 2 * goback_length * n_goback * (#go-back
+    indices) rows."""
+    algo = _algo("full_sequence", steps, horizon + padding)
+    got = algo._generate_refine_scheduling_matrix(horizon, goback_length, n_goback, padding)
+    want = schedule.refine_scheduling_matrix(horizon, goback_length, n_goback, padding, 1000, steps)
+    assert got.dtype == torch.int64 and got.tolist() == want.tolist()
+    n_idx = len(range(1, steps - goback_length, goback_length))
+    assert got.shape == (steps + 1 + 2 * goback_length * n_goback * n_idx, horizon + padding)
+    assert (got[-1, :horizon] == -1).all() and (got[:, horizon:] == 999).all()
+    table = schedule.ddim_idx_to_noise_level(torch.arange(steps + 1), 1000, steps).tolist()
+    idx = [table.index(v) for v in got[:, 0].tolist()]
+    assert all(abs(a - b) == 1 for a, b in zip(idx[:-1], idx[1:])) and max(idx) <= steps
