@@ -233,8 +233,7 @@ class DiT3D(nn.Module):
         if self._packed is not None and key == self._packed_key:
             return self._packed
         dev = self.patch_embedder.proj.weight.device
-        if dev.type != "cuda":
-            raise RuntimeError("dfot_b200: DiT3D runs on CUDA only (no CPU fallback); move the module to a B200")
+        ops.require_cuda(dev, "DiT3D")                          # no CPU implementation exists
         D, C, p = self.hidden_size, self.x_shape[0], self.patch_size
         bf = lambda w: ops.cast_bf16(w.detach().float().contiguous())
         f32 = lambda b: b.detach().float().contiguous()
@@ -326,8 +325,7 @@ class DiT3D(nn.Module):
                 external_cond_mask: Optional[torch.Tensor] = None, out_dtype=torch.float32) -> torch.Tensor:
         """x [R,T,C,H,W] f32|bf16; noise_levels [R,T] int64 (discrete) or f32 (continuous: precond*logsnr).
         Returns a tensor shaped like x (a workspace buffer that the next call overwrites)."""
-        if not x.is_cuda:
-            raise RuntimeError("dfot_b200: DiT3D.forward needs CUDA tensors (no CPU fallback)")
+        ops.require_cuda(x.device, "DiT3D.forward")
         if not self.use_cuda_graph or torch.cuda.is_current_stream_capturing():
             return self._forward_impl(x, noise_levels, external_cond, external_cond_mask, out_dtype)
         R, T = x.shape[:2]

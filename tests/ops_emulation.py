@@ -61,7 +61,43 @@ def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, M=None, **kw):
                          v.reshape(M, D)], 1)
         out[:M].copy_(res.to(out.dtype))
         return
+    if epilogue == ops.EPI_QKV_ROPE_BF16:         # RoPE-3D on the q and k columns (pairs (2i, 2i+1) per head), q * q_scale
+        acc = acc + bias
+        D, dh, tps = kw["model_dim"], kw["head_dim"], kw["tokens_per_sample"]
+        heads = D // dh
+        q, k, v = (acc[:, i * D:(i + 1) * D].reshape(M, heads, dh) for i in range(3))
+        cs = kw["rope_cs"][torch.arange(M) % tps][:, None]
+
+        def rot(t, mul):
+            x0, x1 = t[..., 0::2], t[..., 1::2]
+            return torch.stack([x0 * cs[..., 0] - x1 * cs[..., 1], x1 * cs[..., 0] + x0 * cs[..., 1]], -1).flatten(-2) * mul
+        out[:M].copy_(torch.cat([rot(q, kw["q_scale"]).reshape(M, D), rot(k, 1.0).reshape(M, D), v.reshape(M, D)], 1).to(out.dtype))
+        return
+    if epilogue == ops.EPI_GATE_RESID_F32:        # out = resid + gate[frame(m), n] * (acc + bias)
+        frame = torch.arange(M) // kw["tokens_per_frame"]
+        out[:M].copy_(resid[:M] + kw["gate"][frame][:, : acc.shape[1]] * (acc + bias))
+        return
     _epilogue(acc, out[:M], epilogue, bias, None if resid is None else resid[:M])
+
+
+def adaln_layernorm(x, mod, shift_col, scale_col, tokens_per_frame, y_f32=None, y_bf16=None, eps=1e-6):
+    M, D = x.shape
+    frame = torch.arange(M) // tokens_per_frame
+    y = F.layer_norm(x.float(), (D,), eps=eps) * (1 + mod[frame, scale_col:scale_col + D]) + mod[frame, shift_col:shift_col + D]
+    if y_f32 is not None:
+        y_f32.copy_(y)
+    if y_bf16 is not None:
+        y_bf16.copy_(y.to(BF))
+
+
+def silu_sum_bf16(a, b, row_mask, rows_per_mask, out):
+    s = a.float()
+    if b is not None:
+        keep = 1.0
+        if row_mask is not None:
+            keep = (row_mask.reshape(-1) == 0).float().repeat_interleave(rows_per_mask)[:, None]
+        s = s + b.float() * keep
+    out.copy_(F.silu(s).to(BF))
 
 
 def conv3x3_bf16(x, w, out, epilogue, bias=None, resid=None, gn_sums=None, gn_groups=32, gn_eps=1e-6):
@@ -238,7 +274,8 @@ def softmax_rows_bf16(s, p, scale=1.0):
 ALL = ["cast_bf16", "patchify_bf16", "unpatchify", "gemm_bf16", "conv3x3_bf16", "groupnorm_stats", "groupnorm_silu_bf16",
        "rmsnorm_film_bf16", "qk_norm_rope", "attention", "avgpool2x2", "sub_bf16", "upsample2x_add", "pose_ray_patches",
        "noise_features", "conv3d_causal_bf16", "groupnorm_stats_strided", "groupnorm_apply_bf16",
-       "vae_upsample2x_bf16", "upsample2x_nearest_bf16", "vae_fill_pad_frames", "softmax_rows_bf16"]
+       "vae_upsample2x_bf16", "upsample2x_nearest_bf16", "vae_fill_pad_frames", "softmax_rows_bf16", "adaln_layernorm",
+       "silu_sum_bf16"]
 
 
 def install(monkeypatch):

@@ -228,3 +228,38 @@ def test_q_sample_from_x_k_matches_oracle(monkeypatch):
     bad = algo.diffusion_model.q_sample_from_x_k(x, cur, nxt, noise)
     ref = Diffusion(_tiny()["diffusion"], None).q_sample_from_x_k(x, cur, nxt, noise)
     assert torch.isnan(bad[:, 0]).all() and torch.isnan(ref[:, 0]).all() and torch.isfinite(bad[:, 1]).all()
+
+
+@pytest.mark.parametrize("name", [n for n in case_names() if not n.startswith("uvit")])
+def test_dit3d_host_orchestration_with_emulated_kernels(name, monkeypatch):
+    """The product's DiT3D host side (weight packing, per-frame modulation columns, RoPE table, QKV / gate epilogue
+    arguments, action / label conditioning, K4 tables, refinement walk) driven by CPU restatements of the kernel
+    contracts must reproduce every reference rollout.  bf16 operand rounding is emulated, hence the 2e-2 / 40 dB gates."""
+    import ops_emulation
+    meta, arr, weights = load_case(name)
+    cfg = meta["cfg"]
+    algo = build_product(cfg)
+    sd = {"diffusion_model.model." + k: v for k, v in weights.items()}
+    sd["data_mean"], sd["data_std"] = algo.data_mean, algo.data_std
+    algo.load_state_dict(sd, strict=True)
+    ops_emulation.install(monkeypatch)
+    monkeypatch.setattr(ops, "sampler_step_hg", k4_emulation.emulate)
+    algo.model_in_dtype = torch.float32
+    algo.diffusion_model.model.use_cuda_graph = False
+    torch.manual_seed(meta["sampling_seed"])
+    algo.diffusion_model.noise_source = lambda shape, device: torch.randn(shape)
+    algo.trace = []
+    conds = torch.from_numpy(arr["conds"]) if "conds" in arr else None
+    out = algo._predict_videos(torch.from_numpy(arr["xs"]).clone(), cfg["context_frames"], conds)
+    assert len(algo.trace) == int(arr["n_steps"])
+    worst = 0.0
+    for i, t in enumerate(algo.trace):
+        p = f"step{i:03d}."
+        assert np.array_equal(t["levels_from"], arr[p + "levels_from"])
+        assert np.array_equal(t["levels_to"], arr[p + "levels_to"])
+        worst = max(worst, np.abs(t["model_out"].numpy() - arr[p + "model_out"]).max())
+    assert worst <= 2e-2, worst
+    n_ctx = cfg["context_frames"]
+    ref = arr["prediction"][:, n_ctx:]
+    mse = float(((out.numpy()[:, n_ctx:] - ref) ** 2).mean())
+    assert 10 * np.log10((ref.max() - ref.min()) ** 2 / max(mse, 1e-30)) >= 40.0
