@@ -86,7 +86,8 @@ def _single(case, shard_starts):
 
 
 @pytest.mark.parametrize("case,br", [("vanilla", 1), ("vanilla", 2), ("continuous_action", 2), ("temporal", 1),
-                                     ("uvit_pose_vanilla", 2)])
+                                     ("uvit_pose_vanilla", 2), ("label_vanilla", 1), ("label_vanilla", 2),
+                                     ("refine_conditional", 1)])
 def test_world2_matches_single_process(case, br, tmp_path):
     world = 2
     port = 29500 + (os.getpid() + hash((case, br))) % 2000
