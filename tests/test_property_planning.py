@@ -112,3 +112,29 @@ def test_refine_scheduling_matrix_equals_oracle(horizon, padding, steps, goback_
     table = schedule.ddim_idx_to_noise_level(torch.arange(steps + 1), 1000, steps).tolist()
     idx = [table.index(v) for v in got[:, 0].tolist()]
     assert all(abs(a - b) == 1 for a, b in zip(idx[:-1], idx[1:])) and max(idx) <= steps
+
+
+@settings(**SETTINGS)
+@given(data=st.data(), rows=st.integers(1, 3), frames=st.integers(1, 6))
+def test_renoise_records_equal_oracle_arithmetic(data, rows, frames):
+    """`renoise_table` (the K4 records of q_sample_from_x_k, discrete_diffusion.py:252-260) for random level pairs —
+    context (-1), pad (999) and ordinary levels, also downward pairs — against the oracle's fp32 arithmetic."""
+    from oracle.cases import continuous_overrides
+    from oracle.diffusion import Diffusion
+    key = ("renoise", 0, 0)
+    if key not in _ALGOS:
+        cfg = algorithm_cfg(**{"backbone.hidden_size": 64, "backbone.depth": 1, "backbone.num_heads": 1, "x_shape": [4, 8, 8],
+                               **continuous_overrides()})
+        _ALGOS[key] = (DFoTVideo(cfg), Diffusion(cfg["diffusion"], None))
+    algo, orc = _ALGOS[key]
+    lv = st.sampled_from([-1, 0, 19, 165, 332, 499, 665, 832, 998, 999])
+    cur = np.array(data.draw(st.lists(st.lists(lv, min_size=frames, max_size=frames), min_size=rows, max_size=rows)))
+    nxt = np.array(data.draw(st.lists(st.lists(lv, min_size=frames, max_size=frames), min_size=rows, max_size=rows)))
+    prep = algo.diffusion_model.renoise_table(cur, nxt)
+    x, n = torch.ones((rows, frames, 1, 1, 1)), torch.full((rows, frames, 1, 1, 1), 2.0)
+    ref = orc.q_sample_from_x_k(x, torch.from_numpy(cur), torch.from_numpy(nxt), n).reshape(rows, frames).numpy()
+    got = prep["qa"] * 1.0 + prep["qb"] * 2.0
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert np.abs(got[ok] - ref[ok]).max(initial=0.0) <= 1e-6
+    assert (prep["noise_row"] == np.arange(rows)[:, None]).all()
