@@ -42,19 +42,22 @@ _lib = None
 
 
 def lib() -> ctypes.CDLL:
-    """Load the library; build it first if the sources are newer / it is missing and nvcc exists.
-    Fails loudly — there is no fallback implementation."""
+    """Load the library.  It is (re)built first whenever it is missing or was built from other sources than the ones in
+    the tree (content hash of csrc/ + include/, see build.source_hash) — a stale .so would mis-marshal the ctypes structs
+    silently.  Fails loudly when that is needed and impossible: there is no fallback implementation."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from .build import build
-        try:
-            build()
-        except Exception as e:  # noqa: BLE001
-            raise RuntimeError(
-                f"dfot_b200: CUDA extension {LIB_PATH} is missing and could not be built ({e}). "
-                "Run `python __graft_entry__.py build` on a machine with nvcc; there is no CPU fallback.") from e
+    if not os.environ.get("DFOT_B200_LIB"):          # (an explicitly pinned A/B build is loaded as it is)
+        from . import build as B
+        if not B.is_current():
+            try:
+                B.build()
+            except Exception as e:  # noqa: BLE001
+                what = "is missing" if not os.path.exists(LIB_PATH) else "is stale (built from different sources)"
+                raise RuntimeError(
+                    f"dfot_b200: CUDA extension {LIB_PATH} {what} and could not be built ({e}). "
+                    "Run `python __graft_entry__.py build` on a machine with nvcc; there is no CPU fallback.") from e
     L = ctypes.CDLL(LIB_PATH)
     L.dfot_abi_version.restype = c_int
     L.dfot_last_error.restype = c_char_p

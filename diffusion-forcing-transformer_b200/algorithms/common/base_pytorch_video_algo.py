@@ -14,6 +14,7 @@ import numpy as np
 import torch
 from torch import Tensor, nn
 
+from dfot_b200.checkpoint_io import load_checkpoint_file
 from dfot_b200.config import to_config
 
 
@@ -287,7 +288,7 @@ class BaseVideoAlgo(nn.Module):
             from safetensors.torch import load_file
             checkpoint = {"state_dict": load_file(path), "pretrained_ema": True, "optimizer_states": []}
         else:
-            checkpoint = torch.load(path, map_location="cpu", weights_only=False)
+            checkpoint = load_checkpoint_file(path)
             if "state_dict" not in checkpoint:
                 checkpoint = {"state_dict": checkpoint, "pretrained_ema": True, "optimizer_states": []}
         self.on_load_checkpoint(checkpoint)

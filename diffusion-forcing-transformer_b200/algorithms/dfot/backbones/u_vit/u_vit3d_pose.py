@@ -167,12 +167,14 @@ class UViT3DPose(nn.Module):
             ch = self.channels[level]
             return _TransformerBlock(ch, self.num_heads, E) if self.is_transformers[level] else _ResBlock(ch, E)
 
+        # registration order = the reference's (u_vit3d.py:113-152: down_blocks, up_blocks, then mid_blocks): the EMA list
+        # of a Lightning checkpoint is zipped with named_parameters(), so the ORDER is part of the drop-in contract
         self.down_blocks = nn.ModuleList()
+        self.up_blocks = nn.ModuleList()
         for i in range(L - 1):
             self.down_blocks.append(nn.ModuleList([block(i) for _ in range(self.num_updown_blocks[i])]
                                                   + [_Resample(self.channels[i], self.channels[i + 1])]))
         self.mid_blocks = nn.ModuleList([block(L - 1) for _ in range(self.num_mid_blocks)])
-        self.up_blocks = nn.ModuleList()
         for u in range(L - 1):
             i = L - 2 - u
             self.up_blocks.append(nn.ModuleList([_Resample(self.channels[i + 1], self.channels[i])]

@@ -275,8 +275,28 @@ class DFoTVideo(BaseVideoAlgo):
                 self.shard_chunks = False
         counts = [len(range(*D.shard_batch(xs.shape[0], mesh.dp, d).indices(xs.shape[0]))) for d in range(mesh.dp)]
         sl = D.shard_batch(xs.shape[0], mesh.dp, mesh.dp_index)
-        local = self._predict_videos(xs[sl].contiguous(), n_ctx, None if conditions is None else conditions[sl])
+        # Every rank is seeded identically (the replicated paths above and inside a branch group need ONE noise stream);
+        # the shards of a sample-sharded batch must not share their noise, so each dp shard draws from its own generator,
+        # derived from the common seed (members of a branch group share dp_index, hence the stream).
+        dm = self.diffusion_model
+        prev = dm.generator
+        if mesh.dp > 1 and dm.noise_source is None and prev is None:
+            dm.generator = self._shard_generator(xs.device, mesh.dp_index)
+        try:
+            local = self._predict_videos(xs[sl].contiguous(), n_ctx, None if conditions is None else conditions[sl])
+        finally:
+            dm.generator = prev
         return D.gather_samples(local.contiguous(), mesh, counts)
+
+    def _shard_generator(self, device, dp_index: int) -> torch.Generator:
+        """Noise stream of dp shard `dp_index`: seeded once from the process-wide seed (`torch.manual_seed`, identical on
+        all ranks) and then advanced batch after batch; re-seeding the process starts a new stream."""
+        key = (str(device), torch.initial_seed(), dp_index)
+        if getattr(self, "_shard_gen_key", None) != key:
+            g = torch.Generator(device=device)
+            g.manual_seed((torch.initial_seed() + 0x9E3779B1 * (dp_index + 1)) % (1 << 63))
+            self._shard_gen, self._shard_gen_key = g, key
+        return self._shard_gen
 
     # ------------------------------------------------------------------ window planning (host only)
     def plan_window(self, mask: np.ndarray, horizon: int, padding: int,
@@ -488,9 +508,9 @@ class DFoTVideo(BaseVideoAlgo):
         record = [] if return_all else None
         T = horizon
         model_in = None
-        def k4(*args):
+        def k4(*args, hist_rows: int = 0):
             if not dry_run:
-                ops.sampler_step_hg(*args)
+                ops.sampler_step_hg(*args, max_noise_row=hist_rows - 1 if hist_rows else None)
 
         for m, p in enumerate(plans):
             if return_all:
@@ -498,7 +518,7 @@ class DFoTVideo(BaseVideoAlgo):
             if m == 0:
                 nh, ne = draw_prepare_noise(p)
                 model_in = self._model_in_buffer(B * p.nfe, T, dev)
-                k4(x, None, model_in, None, prep_dev[0], None, nh, ne, B, p.nfe, T)
+                k4(x, None, model_in, None, prep_dev[0], None, nh, ne, B, p.nfe, T, hist_rows=p.n_hist_rows)
             out = None
             self.nfe_rows_planned += B * p.nfe
             if not dry_run:
@@ -515,10 +535,10 @@ class DFoTVideo(BaseVideoAlgo):
                 nh, ne = draw_prepare_noise(nxt)
                 nxt_in = model_in if nxt.nfe == p.nfe else self._model_in_buffer(B * nxt.nfe, T, dev)
                 if nxt.nfe == p.nfe:   # one fused launch: update + combine + revert + next-step prepare
-                    k4(x, out, nxt_in, upd_dev[m], prep_dev[m + 1], nd, nh, ne, B, p.nfe, T)
+                    k4(x, out, nxt_in, upd_dev[m], prep_dev[m + 1], nd, nh, ne, B, p.nfe, T, hist_rows=nxt.n_hist_rows)
                 else:                  # branch count changes between steps: split into update and prepare launches
                     k4(x, out, None, upd_dev[m], None, nd, None, None, B, p.nfe, T)
-                    k4(x, None, nxt_in, None, prep_dev[m + 1], None, nh, ne, B, nxt.nfe, T)
+                    k4(x, None, nxt_in, None, prep_dev[m + 1], None, nh, ne, B, nxt.nfe, T, hist_rows=nxt.n_hist_rows)
                 model_in = nxt_in
             if self.trace is not None and not dry_run:
                 self.trace.append(dict(model_in=trace_in, levels_from=p.levels_from, levels_to=p.levels_to,

@@ -47,6 +47,7 @@ class DiscreteDiffusion(nn.Module):
         self.backbone_cfg = backbone_cfg
         self.use_causal_mask = cfg.use_causal_mask
         self.noise_source: Optional[Callable] = None   # test hook: callable(shape, device) -> standard normal tensor
+        self.generator: Optional[torch.Generator] = None   # per-shard noise stream (DFoTVideo.sample_sharded); None = global
         self._build_model()
         self._build_buffer()
 
@@ -109,7 +110,7 @@ class DiscreteDiffusion(nn.Module):
         for ``device`` unless a test injected ``noise_source``."""
         if self.noise_source is not None:
             return self.noise_source(tuple(shape), device)
-        return torch.randn(tuple(shape), device=device)
+        return torch.randn(tuple(shape), device=device, generator=self.generator)
 
     def clipped_noise(self, shape, device) -> torch.Tensor:
         return torch.clamp(self.randn(shape, device), -self.clip_noise, self.clip_noise)
@@ -125,6 +126,9 @@ class DiscreteDiffusion(nn.Module):
         R, T = k.shape
         if noise is None:
             noise = self.clipped_noise(x_start.shape, x_start.device)
+        if tuple(noise.shape) != tuple(x_start.shape) or tuple(x_start.shape[:2]) != (R, T):
+            raise ValueError(f"q_sample: x_start {tuple(x_start.shape)}, k {tuple(k.shape)} and noise "
+                             f"{tuple(noise.shape)} do not describe the same (rows, frames, ...) batch")
         kh = k.detach().cpu().numpy().astype(np.int64)
         prep = np.zeros((R, T), dtype=sp.PREPARE_DTYPE)
         prep["mode"] = sp.MODE_QSAMPLE
@@ -133,7 +137,8 @@ class DiscreteDiffusion(nn.Module):
         prep["qb"] = self.host_tables.sqrt_one_minus_alphas_cumprod[kh]
         out = torch.empty(x_start.shape, dtype=torch.float32, device=x_start.device)
         ops.sampler_step_hg(x_start.contiguous().float().clone(), None, out, None,
-                            sp.to_device_bytes(prep, x_start.device), None, noise.contiguous().float(), None, R, 1, T)
+                            sp.to_device_bytes(prep, x_start.device), None, noise.contiguous().float(), None, R, 1, T,
+                            max_noise_row=R - 1)
         return out
 
     def renoise_table(self, cur: np.ndarray, nxt: np.ndarray) -> np.ndarray:
@@ -157,11 +162,14 @@ class DiscreteDiffusion(nn.Module):
         R, T = cur_noise_levels.shape
         if noise is None:
             noise = self.clipped_noise(x_k.shape, x_k.device)
+        if tuple(noise.shape) != tuple(x_k.shape) or tuple(x_k.shape[:2]) != (R, T):
+            raise ValueError(f"q_sample_from_x_k: x_k {tuple(x_k.shape)}, levels {(R, T)} and noise {tuple(noise.shape)} "
+                             "do not describe the same (rows, frames, ...) batch")
         prep = self.renoise_table(cur_noise_levels.detach().cpu().numpy().astype(np.int64),
                                   next_noise_levels.detach().cpu().numpy().astype(np.int64))
         out = torch.empty(x_k.shape, dtype=torch.float32, device=x_k.device)
         ops.sampler_step_hg(x_k.contiguous().float().clone(), None, out, None, sp.to_device_bytes(prep, x_k.device), None,
-                            noise.contiguous().float(), None, R, 1, T)
+                            noise.contiguous().float(), None, R, 1, T, max_noise_row=R - 1)
         return out
 
     def model_input_levels(self, k: torch.Tensor) -> torch.Tensor:

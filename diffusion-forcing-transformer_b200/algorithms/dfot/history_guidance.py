@@ -304,7 +304,7 @@ class _ManagerBase:
             noise_excl = diffusion.randn((B * nfe, *x.shape[1:]), x.device)
         out = torch.empty((B * nfe, *x.shape[1:]), dtype=torch.float32, device=x.device)
         ops.sampler_step_hg(x.clone(), None, out, None, sp.to_device_bytes(plan.prepare, x.device), None, noise_hist,
-                            noise_excl, B, nfe, T)
+                            noise_excl, B, nfe, T, max_noise_row=plan.n_hist_rows - 1 if plan.n_hist_rows else None)
         dev = x.device
         cond_mask = None if plan.cond_mask is None else torch.from_numpy(plan.cond_mask).to(dev)
         return (out, torch.from_numpy(plan.levels_from).to(dev), torch.from_numpy(plan.levels_to).to(dev), cond_mask)

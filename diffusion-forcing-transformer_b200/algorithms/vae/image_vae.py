@@ -17,6 +17,7 @@ import torch
 from torch import Tensor, nn
 
 from ... import ops
+from ...checkpoint_io import load_checkpoint_file
 from ...config import to_config
 from .video_vae import _DecoderOnKernels, _register
 
@@ -106,7 +107,7 @@ class ImageVAE(_DecoderOnKernels):
     def from_pretrained(cls, path: str, **kwargs) -> "ImageVAE":
         if path.startswith("diffuser:"):
             raise NotImplementedError("ImageVAE: diffusers AutoencoderKL checkpoints are outside the scope of dfot_b200")
-        ckpt: Dict = torch.load(path, map_location="cpu", weights_only=False)
+        ckpt: Dict = load_checkpoint_file(path)
         model = cls(ckpt.get("cfg", _DEFAULT_CFG))
         sd = {k: v for k, v in ckpt["state_dict"].items() if not k.startswith("loss")}
         own = [n for n, _ in model.named_parameters()]

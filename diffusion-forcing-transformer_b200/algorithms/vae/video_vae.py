@@ -25,6 +25,7 @@ import torch
 from torch import Tensor, nn
 
 from ... import ops
+from ...checkpoint_io import load_checkpoint_file
 
 PAD = 2          # leading pad slots per clip (the causal window of a kt = 3 convolution)
 _CMIN = 64       # channel padding of the z / post-quant operands (one K tile of the implicit GEMM)
@@ -338,7 +339,7 @@ class VideoVAE(_DecoderOnKernels):
     # ------------------------------------------------------------------ checkpoint (model.py:505-530)
     @classmethod
     def from_pretrained(cls, path: str, **kwargs) -> "VideoVAE":
-        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        ckpt = load_checkpoint_file(path)
         cfg = {k: tuple(v) if isinstance(v, list) else v for k, v in ckpt["model_cfg"].items()}
         model = cls(**cfg)
         own = [n for n, _ in model.named_parameters()]

@@ -27,6 +27,36 @@ def _nvcc() -> str:
     return nvcc
 
 
+HASH_FILE = os.path.join(OBJ, "sources.sha256")     # travels with the .so (build/ is git-ignored, not gpurun-ignored)
+
+
+def _dep_files():
+    headers = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "dfot_b200.h"))
+    return [os.path.join(CSRC, s) for s in SOURCES], headers
+
+
+def source_hash() -> str:
+    """Content hash of everything the library is built from (sources, headers, flags): mtimes do not survive a snapshot
+    copy to another machine, contents do."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    srcs, headers = _dep_files()
+    for f in srcs + headers:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def is_current() -> bool:
+    """True when libdfot_b200.so exists and was built from exactly the sources now in the tree."""
+    if not (os.path.exists(LIB) and os.path.exists(HASH_FILE)):
+        return False
+    with open(HASH_FILE) as fh:
+        return fh.read().strip() == source_hash()
+
+
 def _stale(target: str, deps) -> bool:
     if not os.path.exists(target):
         return True
@@ -35,10 +65,8 @@ def _stale(target: str, deps) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    headers.append(os.path.join(os.path.dirname(HERE), "include", "dfot_b200.h"))
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    if not force and not _stale(LIB, srcs + headers + [os.path.abspath(__file__)]):
+    srcs, headers = _dep_files()
+    if not force and is_current():
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
@@ -60,6 +88,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(HASH_FILE, "w") as fh:
+        fh.write(source_hash() + "\n")
     return LIB
 
 

@@ -70,7 +70,7 @@ sampler_step_hg_kernel(float* __restrict__ x, const TOut* __restrict__ model_out
 #pragma unroll
         for (int j = 0; j < NFE; ++j) {
           if (s_upd[j].w == 0.f) continue;
-          o[j] = Vec4<TOut>::load(model_out + frame_r + j * row_stride + e);
+          if (s_upd[j].b != 0.f) o[j] = Vec4<TOut>::load(model_out + frame_r + j * row_stride + e);
           if (s_upd[j].sigma != 0.f && noise_ddim != nullptr) nd[j] = Vec4<float>::load(noise_ddim + frame_r + j * row_stride + e);
         }
       }
@@ -90,8 +90,11 @@ sampler_step_hg_kernel(float* __restrict__ x, const TOut* __restrict__ model_out
           if (u.w == 0.f) continue;
           float4 ov = o[j];
           if (u.clip > 0.f) ov = clamp4(ov, u.clip);
-          float4 v = make_float4(u.a * xv.x + u.b * ov.x, u.a * xv.y + u.b * ov.y, u.a * xv.z + u.b * ov.z,
-                                 u.a * xv.w + u.b * ov.w);
+          // b == 0 marks a frame whose level does not change (a = 1): the reference keeps x through torch.where, so a
+          // NaN / Inf in the model output of such a frame must not reach x (0 * NaN = NaN)
+          float4 v = u.b == 0.f ? make_float4(u.a * xv.x, u.a * xv.y, u.a * xv.z, u.a * xv.w)
+                                : make_float4(u.a * xv.x + u.b * ov.x, u.a * xv.y + u.b * ov.y, u.a * xv.z + u.b * ov.z,
+                                              u.a * xv.w + u.b * ov.w);
           if (u.sigma != 0.f && noise_ddim != nullptr) {
             v.x += u.sigma * nd[j].x; v.y += u.sigma * nd[j].y; v.z += u.sigma * nd[j].z; v.w += u.sigma * nd[j].w;
           }
@@ -120,10 +123,12 @@ sampler_step_hg_kernel(float* __restrict__ x, const TOut* __restrict__ model_out
           const dfot_frame_update u = s_upd[j];
           if (u.w == 0.f) continue;
           const int64_t off = frame_r + j * row_stride + e;
-          float4 o = Vec4<TOut>::load(model_out + off);
-          if (u.clip > 0.f) o = clamp4(o, u.clip);
-          float4 v = make_float4(u.a * xv.x + u.b * o.x, u.a * xv.y + u.b * o.y, u.a * xv.z + u.b * o.z,
-                                 u.a * xv.w + u.b * o.w);
+          float4 v = make_float4(u.a * xv.x, u.a * xv.y, u.a * xv.z, u.a * xv.w);
+          if (u.b != 0.f) {   // (b == 0: kept frame, the model output is not read — see above)
+            float4 o = Vec4<TOut>::load(model_out + off);
+            if (u.clip > 0.f) o = clamp4(o, u.clip);
+            v.x += u.b * o.x; v.y += u.b * o.y; v.z += u.b * o.z; v.w += u.b * o.w;
+          }
           if (u.sigma != 0.f && noise_ddim != nullptr) {
             float4 n = Vec4<float>::load(noise_ddim + off);
             v.x += u.sigma * n.x; v.y += u.sigma * n.y; v.z += u.sigma * n.z; v.w += u.sigma * n.w;

@@ -43,8 +43,12 @@ class SamplingExperiment:
             from dfot_b200 import distributed as D
             self.algo.mesh = D.build_mesh(br=branch_group_size)
         self.rank = dist.get_rank() if self.distributed else 0
-        if manual_seed is not None:   # set_seed(manual_seed, device_specific=True) of the reference (:341-342)
-            torch.manual_seed(manual_seed + (self.algo.mesh.dp_index if self.distributed else 0))
+        if manual_seed is not None:
+            # the reference calls set_seed(manual_seed, device_specific=True) (:341-342) because every rank samples its own
+            # batch; here a batch may be REPLICATED over ranks (branch groups; keyframe windows when batch < dp shards), and
+            # those ranks must draw the same noise: all ranks share the seed, `sample_sharded` derives a per-shard stream
+            # from it only where the samples themselves are sharded.
+            torch.manual_seed(manual_seed)
         self.stats = {"batches": 0, "videos": 0, "forward_rows": 0, "seconds": 0.0}
 
     @torch.no_grad()

@@ -53,9 +53,11 @@ def _need(t: torch.Tensor, dtype, name: str) -> None:
         raise RuntimeError(f"dfot_b200: `{name}` must be contiguous")
 
 
-def sampler_step_hg(x, model_out, model_in_next, upd, prep, noise_ddim, noise_hist, noise_excl, B, nfe, T):
+def sampler_step_hg(x, model_out, model_in_next, upd, prep, noise_ddim, noise_hist, noise_excl, B, nfe, T,
+                    max_noise_row=None):
     """K4. x [B,T,...] f32 in place; model_out / model_in_next [B*nfe,T,...] f32|bf16 or None;
-    upd / prep: uint8 CUDA tensors holding packed dfot_frame_update / dfot_frame_prepare records."""
+    upd / prep: uint8 CUDA tensors holding packed dfot_frame_update / dfot_frame_prepare records; `max_noise_row`: the
+    largest `noise_row` of the prepare table (known to the host planner), checked against the rows of `noise_hist`."""
     _need(x, torch.float32, "x")
     F = x[0, 0].numel()
     for t, n in ((model_out, "model_out"), (model_in_next, "model_in_next")):
@@ -63,9 +65,20 @@ def sampler_step_hg(x, model_out, model_in_next, upd, prep, noise_ddim, noise_hi
             _need(t, None, n)
             if t.dtype not in (torch.float32, torch.bfloat16) or t.numel() != B * nfe * T * F:
                 raise RuntimeError(f"dfot_b200: `{n}` has wrong dtype/size")
-    for t, n in ((noise_ddim, "noise_ddim"), (noise_hist, "noise_hist"), (noise_excl, "noise_excl")):
+    if x.dim() < 3 or tuple(x.shape[:2]) != (B, T):
+        raise RuntimeError(f"dfot_b200: `x` must be [B={B}, T={T}, ...], got {tuple(x.shape)}")
+    for t, n in ((noise_ddim, "noise_ddim"), (noise_excl, "noise_excl")):
         if t is not None:
             _need(t, torch.float32, n)
+            if t.numel() != B * nfe * T * F:
+                raise RuntimeError(f"dfot_b200: `{n}` has {t.numel()} elements, expected B*nfe*T*F = {B * nfe * T * F}")
+    if noise_hist is not None:
+        _need(noise_hist, torch.float32, "noise_hist")
+        if noise_hist.numel() % (T * F):
+            raise RuntimeError(f"dfot_b200: `noise_hist` must hold whole [T, F] rows, got {noise_hist.numel()} elements")
+        if prep is not None and max_noise_row is not None and noise_hist.numel() < (max_noise_row + 1) * T * F:
+            raise RuntimeError(f"dfot_b200: `noise_hist` holds {noise_hist.numel() // (T * F)} rows, the prepare table "
+                               f"addresses row {max_noise_row}")
     for t, n, sz in ((upd, "upd", 24), (prep, "prep", 16)):
         if t is not None:
             _need(t, torch.uint8, n)

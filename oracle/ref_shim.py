@@ -1,9 +1,10 @@
 """TEST INFRASTRUCTURE — import shim for the *real* reference (/root/reference).
 
-Only usable in the authoring container (the GPU box has no /root/reference).
-It is used by ``oracle/make_goldens.py`` to (a) generate the committed golden
-vectors under ``tests/golden/`` and (b) pin the CPU restatement in ``oracle/``
-against the executed reference.  Nothing in the product package imports this.
+Used by ``oracle/make_goldens*.py`` (authoring container, /root/reference) to (a) generate
+the committed golden vectors under ``tests/golden/`` and (b) pin the CPU restatement in
+``oracle/`` against the executed reference; and by ``bench.py --impl reference`` on the
+GPU box, where the reference's files come from the git-ignored copy ``oracle/_ref/``
+made by ``oracle/build_ref.py``.  Nothing in the product package imports this.
 
 The reference depends on packages that are absent here (omegaconf, timm,
 diffusers, lightning, accelerate, rotary_embedding_torch, roma, matplotlib,
@@ -23,7 +24,22 @@ import types
 import torch
 from torch import nn
 
-REF = os.environ.get("DFOT_REFERENCE_ROOT", "/root/reference")
+_SHIPPED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference")   # oracle/build_ref.py
+
+
+def _find_reference() -> str:
+    """$DFOT_REFERENCE_ROOT, else /root/reference (authoring container), else the unmodified copy of the sampling
+    path's files that oracle/build_ref.py ships to the GPU box (git-ignored oracle/_ref/)."""
+    env = os.environ.get("DFOT_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _SHIPPED):
+        if os.path.isdir(os.path.join(cand, "algorithms", "dfot")):
+            return cand
+    return "/root/reference"
+
+
+REF = _find_reference()
 
 
 def available() -> bool:

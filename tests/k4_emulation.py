@@ -17,7 +17,7 @@ def _table(t, dtype, rows, T):
     return np.frombuffer(t.tobytes(), dtype=dtype).reshape(rows, T)
 
 
-def emulate(x, model_out, model_in_next, upd, prep, noise_ddim, noise_hist, noise_excl, B, nfe, T):
+def emulate(x, model_out, model_in_next, upd, prep, noise_ddim, noise_hist, noise_excl, B, nfe, T, max_noise_row=None):
     """In-place on x (f32 [B,T,...]) and model_in_next, like the kernel."""
     F = x[0, 0].numel()
     xs = x.reshape(B, T, F)
@@ -29,7 +29,7 @@ def emulate(x, model_out, model_in_next, upd, prep, noise_ddim, noise_hist, nois
         a, b, sg, w, clip = (f32(upd[k]).reshape(B, nfe, T, 1) for k in ("a", "b", "sigma", "w", "clip"))
         gen = torch.from_numpy(upd["generate"].reshape(B, nfe, T)[:, 0].copy()).bool()
         o = torch.where(clip > 0, torch.maximum(torch.minimum(out, clip), -clip), out)
-        v = a * xs[:, None] + b * o
+        v = torch.where(b == 0, a * xs[:, None], a * xs[:, None] + b * o)     # b == 0: kept frame, out is not read
         if noise_ddim is not None:
             v = v + sg * noise_ddim.float().reshape(B, nfe, T, F)
         comp = (w * v).sum(1)

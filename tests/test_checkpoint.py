@@ -61,3 +61,36 @@ def test_missing_keys_follow_strict_flag(tmp_path):
     saved = {"state_dict": dict(lenient.state_dict())}
     lenient.on_save_checkpoint(saved)
     assert all(k.startswith("diffusion_model.model") for k in saved["state_dict"])
+
+
+def test_uvit3d_pose_parameter_order_matches_the_reference():
+    """The EMA list of a Lightning checkpoint is zipped with `named_parameters()` (base_pytorch_video_algo.py:1130-1144 of the
+    reference): the product's order must be the reference's, or same-shaped tensors would be swapped silently.  The golden
+    weight file was written from the executed reference's `state_dict()` (oracle/make_goldens.py), whose key order is its
+    named_parameters() order with the persistent buffers in between."""
+    import numpy as np
+    import os
+    from helpers import GOLDEN
+    for case, wfile in [("uvit_pose_vanilla", "weights_uvit_pose.npz"), ("vanilla", "weights_plain.npz"),
+                        ("continuous_action", "weights_action.npz"), ("label_vanilla", "weights_label.npz")]:
+        algo, _, _ = _algo_and_weights(case)
+        ref_keys = list(np.load(os.path.join(GOLDEN, wfile)).files)
+        model = algo.diffusion_model.model
+        assert list(model.state_dict().keys()) == ref_keys, case
+        own = [k for k, _ in model.named_parameters()]
+        params = set(own)
+        assert own == [k for k in ref_keys if k in params], case
+
+
+def test_pickled_objects_need_an_opt_in(tmp_path, monkeypatch):
+    """A `.ckpt` is loaded with the tensor-only unpickler; arbitrary pickled objects load only after an explicit opt-in."""
+    import argparse
+    algo, sd, _ = _algo_and_weights()
+    path = str(tmp_path / "objects.ckpt")
+    torch.save({"state_dict": sd, "pretrained_ema": True, "optimizer_states": [], "hparams": argparse.Namespace(a=1)}, path)
+    monkeypatch.delenv("DFOT_ALLOW_PICKLE_CKPT", raising=False)
+    with pytest.raises(RuntimeError, match="DFOT_ALLOW_PICKLE_CKPT"):
+        algo.load_checkpoint(path)
+    monkeypatch.setenv("DFOT_ALLOW_PICKLE_CKPT", "1")
+    algo.load_checkpoint(path)
+    assert all(torch.equal(v, sd[k]) for k, v in _model_state(algo).items())

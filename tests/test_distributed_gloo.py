@@ -125,6 +125,61 @@ def test_world2_interpolation_chunks_are_sharded(case, tmp_path):
     assert max(rows) < _single.nfe_rows and sum(rows) > _single.nfe_rows    # interpolation split, keyframes replicated
 
 
+def _seeded_worker(rank, world, port, case, seed, duplicate, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        algo, cfg, xs, conds, _ = _build(case)
+        from dfot_b200 import distributed as D
+        algo.mesh = D.build_mesh(br=1)
+        if duplicate:                      # two copies of sample 0: only the noise can tell the shards apart
+            xs = xs[:1].repeat(2, *[1] * (xs.dim() - 1))
+            conds = None if conds is None else conds[:1].repeat(2, *[1] * (conds.dim() - 1))
+        torch.manual_seed(seed)            # what SamplingExperiment(manual_seed=seed) does: the SAME seed on every rank
+        out = algo.sample_sharded(xs, conds, cfg["context_frames"])
+        np.save(out_path + f".{rank}.npy", out.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_seeded_single_sample_rollout_is_coherent(tmp_path):
+    """with a user seed and fewer samples than dp shards, keyframe windows are replicated and
+    interpolation chunks are dealt over the shards — every rank must draw ONE noise stream, end with the same video, and
+    that video must be the single-process rollout of the same seed."""
+    case, seed = "keyframes_interp", 77
+    out_path = str(tmp_path / "seeded")
+    mp.spawn(_seeded_worker, args=(2, 29500 + (os.getpid() + 11) % 2000, case, seed, False, out_path), nprocs=2, join=True)
+    got = [np.load(out_path + f".{r}.npy") for r in range(2)]
+    assert np.array_equal(got[0], got[1])
+    sys.path.insert(0, ROOT)
+    from dfot_b200 import ops
+    real_ops = dict(vars(ops))
+    try:
+        algo, cfg, xs, conds, _ = _build(case)
+        torch.manual_seed(seed)
+        want = algo._predict_videos(xs, cfg["context_frames"], conds).numpy()
+    finally:
+        for k, v in real_ops.items():
+            setattr(ops, k, v)
+    assert np.array_equal(got[0], want)
+
+
+def test_world2_seeded_sample_shards_draw_different_noise(tmp_path):
+    """Same seed on every rank, samples sharded: each dp shard derives its own stream (two copies of one input must not
+    come out identical), every rank ends with the same gathered batch, and a second run reproduces it."""
+    case, seed = "vanilla", 5
+    runs = []
+    for attempt in range(2):
+        out_path = str(tmp_path / f"dup{attempt}")
+        mp.spawn(_seeded_worker, args=(2, 29500 + (os.getpid() + 23 + attempt) % 2000, case, seed, True, out_path),
+                 nprocs=2, join=True)
+        got = [np.load(out_path + f".{r}.npy") for r in range(2)]
+        assert np.array_equal(got[0], got[1])
+        runs.append(got[0])
+    assert np.array_equal(runs[0], runs[1])
+    assert np.abs(runs[0][0] - runs[0][1]).max() > 1e-3
+
+
 # ------------------------------------------------------------------------------------------------ sharded VAE decode
 def _vae_for_gloo():
     sys.path.insert(0, ROOT)
