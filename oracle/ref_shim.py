@@ -275,8 +275,10 @@ def install():
         setattr(ah, n, lambda *a, **k: None)
     ah.attn_maps = {}
     v = _mod("algorithms.vae")
+    # (latent configurations with `latent.type: online` construct their VAE in __init__; the sampling path on latents never
+    #  calls it, and no VAE checkpoint exists offline: an empty module stands in)
     for n in ["ImageVAE", "VideoVAE", "MyAutoencoderDC", "AutoencoderKL", "TiTok_KL"]:
-        setattr(v, n, type(n, (), {}))
+        setattr(v, n, type(n, (), {"from_pretrained": classmethod(lambda cls, *a, **k: nn.Identity())}))
     ulog = _mod("utils.logging_utils")
     ulog.log_video = lambda *a, **k: None
 

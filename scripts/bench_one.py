@@ -83,6 +83,32 @@ elif which == "qknorm":   # level-2 q/k RMSNorm(head_dim 64) + RoPE-3D in place:
     qw, kw = torch.randn((dh,), device=DEV), torch.randn((dh,), device=DEV)
     table = torch.randn((Ntok, dh // 2, 2), device=DEV)
     fn = lambda: ops.qk_norm_rope(qkv, qw, kw, table, Ntok, heads, dh, 0.18)
+elif which == "rmsnorm1152":  # level-3 RMSNorm + FiLM: M = 16384 tokens, D = 1152 (pose part on half of the images)
+    g, D = 16, 1152
+    M = 64 * g * g
+    x = torch.randn((M, D), device=DEV)
+    w = torch.randn((D,), device=DEV)
+    mi = torch.randn((64, 4 * D), device=DEV)
+    mp = torch.randn((32 * g * g, 2 * D), device=DEV).to(torch.bfloat16)
+    o = torch.empty((M, D), device=DEV, dtype=torch.bfloat16)
+    img_map = torch.tensor([(-1 if i % 16 < 8 else (i // 16) * 8 + i % 8) for i in range(64)], dtype=torch.int32, device=DEV)
+    fn = lambda: ops.rmsnorm_film_bf16(x, w, mi, 0, D, g * g, o, mod_pix=mp, img_map=img_map)
+elif which == "gn_stats":  # stand-alone GroupNorm statistics of a level-0 bf16 feature map: 64 images 128x128x128
+    n, HW, C = 64, 16384, 128
+    x = torch.randn((n * HW, C), device=DEV).to(torch.bfloat16)
+    sums = torch.empty((n, 32, 3), dtype=torch.float64, device=DEV)
+    fn = lambda: ops.groupnorm_stats(x, sums, n, HW, C)
+elif which == "gn_stats_f32":  # ... of the fp32 residual stream (the first ResBlock of a level)
+    n, HW, C = 64, 16384, 128
+    x = torch.randn((n * HW, C), device=DEV)
+    sums = torch.empty((n, 32, 3), dtype=torch.float64, device=DEV)
+    fn = lambda: ops.groupnorm_stats(x, sums, n, HW, C)
+elif which == "adaln":     # K600 adaLN-LayerNorm launch: 8 x 1280 tokens, D = 1152, bf16 output only
+    M, D, tpf = 8 * 1280, 1152, 256
+    x = torch.randn((M, D), device=DEV)
+    mod = torch.randn((M // tpf, 6 * D), device=DEV)
+    y = torch.empty((M, D), device=DEV, dtype=torch.bfloat16)
+    fn = lambda: ops.adaln_layernorm(x, mod, 0, D, tpf, y_bf16=y)
 else:
     raise SystemExit(f"unknown kernel {which}")
 for _ in range(2):
