@@ -19,6 +19,7 @@ Per forward (R rows, T frames, P patches/frame, M = R*T*P tokens, D hidden):
 import math
 from typing import Optional
 
+import numpy as np
 import torch
 from torch import nn
 
@@ -115,9 +116,29 @@ class _FinalLayer(nn.Module):           # dit_blocks.py:513-542
         nn.init.zeros_(self.linear.bias)
 
 
-class _DiTBase(nn.Module):
-    def __init__(self, dim: int, depth: int, spatial_mlp_ratio: Optional[float], out_channels: int):
+def sincos_1d_table(dim: int, n: int) -> torch.Tensor:
+    """dit_base.py:528-580 for a 1-D shape: [n, dim] = [sin(pos * w) | cos(pos * w)], w_i = 10000^(-2i/dim), float64 → f32."""
+    omega = 1.0 / 10000 ** (np.arange(dim // 2, dtype=np.float64) / (dim / 2.0))
+    out = np.einsum("m,d->md", np.arange(n, dtype=np.float32).astype(np.float64), omega)
+    return torch.from_numpy(np.concatenate([np.sin(out), np.cos(out)], axis=1)).float()
+
+
+class _AbsPosEmb(nn.Module):            # dit_base.py:504-525 (SinusoidalPositionalEmbedding, learnable or fixed)
+    def __init__(self, dim: int, n_tokens: int, learnable: bool):
         super().__init__()
+        if learnable:
+            self.pos_emb = nn.Parameter(torch.zeros(1, n_tokens, dim).normal_(std=0.02))
+        else:
+            self.register_buffer("pos_emb", sincos_1d_table(dim, n_tokens).unsqueeze(0), persistent=False)
+
+
+class _DiTBase(nn.Module):
+    def __init__(self, dim: int, depth: int, spatial_mlp_ratio: Optional[float], out_channels: int,
+                 pos_emb_type: str = "rope_3d", n_tokens: int = 0):
+        super().__init__()
+        # dit_base.py:156: the positional embedding is registered BEFORE the blocks (named_parameters() order)
+        if pos_emb_type in ("learned_1d", "sinusoidal_1d"):
+            self.pos_emb = _AbsPosEmb(dim, n_tokens, pos_emb_type == "learned_1d")
         # dit_base.py:185,192 — "full" blocks take spatial_mlp_ratio (None ⇒ no MLP; fork quirk Q2)
         self.blocks = nn.ModuleList([_Block(dim, spatial_mlp_ratio) for _ in range(depth)])
         self.final_layer = _FinalLayer(dim, out_channels)
@@ -158,9 +179,11 @@ class DiT3D(nn.Module):
             raise NotImplementedError("Causal masking is not yet implemented for DiT3D backbone")  # dit3d.py:23-26
         super().__init__()
         cfg = to_config(cfg)
-        if cfg.get("variant", "full") != "full" or cfg.get("pos_emb_type", "rope_3d") != "rope_3d":
-            raise NotImplementedError("dfot_b200 DiT3D supports variant=full with pos_emb_type=rope_3d "
-                                      "(the default dit3d.yaml); other variants are fork-only ablations")
+        self.pos_emb_type = cfg.get("pos_emb_type", "rope_3d")
+        if cfg.get("variant", "full") != "full" or self.pos_emb_type not in ("rope_3d", "learned_1d", "sinusoidal_1d"):
+            raise NotImplementedError("dfot_b200 DiT3D supports variant=full with pos_emb_type rope_3d (the default "
+                                      "dit3d.yaml), learned_1d or sinusoidal_1d; the factorized / matrix-attention variants "
+                                      "and sinusoidal_3d (which asserts in the fork itself) are fork-only ablations")
         self.cfg = cfg
         self.x_shape = list(x_shape)
         self.max_tokens = max_tokens
@@ -194,7 +217,9 @@ class DiT3D(nn.Module):
         else:
             self.external_cond_embedding = None
         self.patch_embedder = _PatchEmbed(C, D, self.patch_size)
-        self.dit_base = _DiTBase(D, self.depth, cfg.get("spatial_mlp_ratio", None), self.patch_size ** 2 * C)
+        self.dit_base = _DiTBase(D, self.depth, cfg.get("spatial_mlp_ratio", None), self.patch_size ** 2 * C,
+                                 self.pos_emb_type, max_tokens * self.num_patches)
+        self.use_rope = self.pos_emb_type == "rope_3d"
         self.use_mlp = self.dit_base.blocks[0].use_mlp
         self._init_embedders()
         self._packed = None
@@ -270,8 +295,17 @@ class DiT3D(nn.Module):
         P["mod_w"] = bf(torch.cat([w.detach().float() for w in mods_w], 0))
         P["mod_b"] = torch.cat([b.detach().float() for b in mods_b], 0).contiguous()
         P["blocks"] = []
+        if not self.use_rope:
+            # absolute position table: the residual operand of the patch-embed GEMM; without RoPE the QKV epilogue is a plain
+            # bf16 store, so the softmax scale (x log2 e: the attention kernel exponentiates in base 2) is folded into W_q, b_q
+            P["pos"] = f32(self.dit_base.pos_emb.pos_emb[0])
+            qs = torch.ones((3 * D, 1), device=dev)
+            qs[:D] = LOG2E / math.sqrt(self.head_dim)
         for blk in self.dit_base.blocks:
-            d = dict(qkv_w=bf(blk.attn.qkv.weight), qkv_b=f32(blk.attn.qkv.bias), proj_w=bf(blk.attn.proj.weight),
+            qw, qb = blk.attn.qkv.weight.detach().float(), blk.attn.qkv.bias.detach().float()
+            if not self.use_rope:
+                qw, qb = qw * qs, qb * qs[:, 0]
+            d = dict(qkv_w=bf(qw), qkv_b=f32(qb), proj_w=bf(blk.attn.proj.weight),
                      proj_b=f32(blk.attn.proj.bias))
             if blk.use_mlp:
                 d.update(fc1_w=bf(blk.mlp.fc1.weight), fc1_b=f32(blk.mlp.fc1.bias), fc2_w=bf(blk.mlp.fc2.weight),
@@ -283,7 +317,8 @@ class DiT3D(nn.Module):
         bfin = torch.zeros((no,), device=dev)
         bfin[: p * p * C] = fl.linear.bias.detach().float()
         P["fin_w"], P["fin_b"] = bf(wf), bfin
-        P["rope"] = rope_cos_sin_table(self.head_dim, (self.max_tokens, self.num_patches_h, self.num_patches_w)).to(dev)
+        if self.use_rope:
+            P["rope"] = rope_cos_sin_table(self.head_dim, (self.max_tokens, self.num_patches_h, self.num_patches_w)).to(dev)
         self._packed, self._packed_key = P, key
         return P
 
@@ -303,11 +338,24 @@ class DiT3D(nn.Module):
                   tok=e((M, _pad8(p * p * C)), f32), out=e((R, T, *self.x_shape), out_dtype))
         if self.use_mlp:
             ws["h"] = e((M, self.dit_base.blocks[0].mlp.fc1.out_features), bf)
+        if not self.use_rope:
+            ws["pos_rows"], ws["pos_key"] = e((M, D), f32), None     # the table repeated per row (filled lazily)
         if self.external_cond_embedding is not None:
             ws.update(cin=torch.zeros((RT, _pad8(self.external_cond_dim)), dtype=bf, device=dev), c1=e((RT, D), bf),
                       cemb=e((RT, D), f32))
         self._ws[key] = ws
         return ws
+
+    def _fill_pos_rows(self, ws, R: int, Ntok: int) -> None:
+        """The absolute position table repeated for every row of the batch (the GEMM epilogue's residual operand has no
+        modulo addressing).  Re-filled when the weights change; never inside a graph capture (forward() calls it first)."""
+        if ws["pos_key"] == self._packed_key:
+            return
+        if ws["pos_rows"].is_cuda and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("DiT3D: the position rows must be filled before a CUDA-graph capture")
+        D = self.hidden_size
+        ws["pos_rows"].view(R, Ntok, D).copy_(self.packed()["pos"][:Ntok].unsqueeze(0).expand(R, Ntok, D))
+        ws["pos_key"] = self._packed_key
 
     # ------------------------------------------------------------------ forward
     def input_buffer(self, R: int, T: int, dtype, device) -> torch.Tensor:
@@ -341,6 +389,9 @@ class DiT3D(nn.Module):
         xin = self.input_buffer(R, T, x.dtype, x.device)
         if x.data_ptr() != xin.data_ptr():
             xin.copy_(x)
+        if not self.use_rope:
+            self.packed()
+            self._fill_pos_rows(self._workspace(R, T, x.device, out_dtype), R, T * self.num_patches)
         if st["graph"] is None:
             self.packed()
             st["levels"] = torch.empty_like(levels)
@@ -379,7 +430,11 @@ class DiT3D(nn.Module):
 
         # --- tokens
         ops.patchify_bf16(x, ws["patches"], RT, C, H, W, p)
-        ops.gemm_bf16(ws["patches"], Pk["pe_w"], ws["x"], ops.EPI_F32, bias=Pk["pe_b"])
+        if self.use_rope:
+            ops.gemm_bf16(ws["patches"], Pk["pe_w"], ws["x"], ops.EPI_F32, bias=Pk["pe_b"])
+        else:       # dit_base.py:352-353: x + pos_emb[:, :seq_len], as the residual operand of the patch-embed GEMM
+            self._fill_pos_rows(ws, R, Ntok)
+            ops.gemm_bf16(ws["patches"], Pk["pe_w"], ws["x"], ops.EPI_RESID_F32, bias=Pk["pe_b"], resid=ws["pos_rows"])
         # --- per-frame conditioning vector c = silu(noise_emb [+ cond_emb])
         ops.noise_features(levels, ws["feat"], Pk.get("four_f"), Pk.get("four_p"))
         ops.gemm_bf16(ws["feat"], Pk["t1_w"], ws["e1"], ops.EPI_SILU_BF16, bias=Pk["t1_b"])
@@ -411,8 +466,12 @@ class DiT3D(nn.Module):
         xa, xb = ws["x"], ws["y"]
         for bw in Pk["blocks"]:
             ops.adaln_layernorm(xa, mod, col, col + D, Pn, y_f32=xb, y_bf16=ws["y16"])
-            ops.gemm_bf16(ws["y16"], bw["qkv_w"], ws["qkv"], ops.EPI_QKV_ROPE_BF16, bias=bw["qkv_b"], rope_cs=Pk["rope"],
-                          tokens_per_sample=Ntok, model_dim=D, head_dim=self.head_dim, q_scale=q_scale)
+            if self.use_rope:
+                ops.gemm_bf16(ws["y16"], bw["qkv_w"], ws["qkv"], ops.EPI_QKV_ROPE_BF16, bias=bw["qkv_b"],
+                              rope_cs=Pk["rope"], tokens_per_sample=Ntok, model_dim=D, head_dim=self.head_dim,
+                              q_scale=q_scale)
+            else:
+                ops.gemm_bf16(ws["y16"], bw["qkv_w"], ws["qkv"], ops.EPI_BF16, bias=bw["qkv_b"])
             ops.attention(ws["qkv"], ws["att"], R, Ntok, self.num_heads, self.head_dim)
             # x1 = y + gate1 * proj(att)   (residual base is the modulated tensor — reference quirk Q1)
             ops.gemm_bf16(ws["att"], bw["proj_w"], xa, ops.EPI_GATE_RESID_F32, bias=bw["proj_b"], resid=xb,

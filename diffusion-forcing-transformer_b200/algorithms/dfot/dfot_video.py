@@ -410,7 +410,7 @@ class DFoTVideo(BaseVideoAlgo):
                 nd = dm.clipped_noise((B, T, *x_shape), dev)                 # RNG: DDIM noise, drawn even when eta == 0
                 trace_in = model_in.float().clone() if self.trace is not None else None
                 ops.sampler_step_hg(x, out, None, sp.to_device_bytes(p.update, dev), None,
-                                    nd if dm.host_tables.eta != 0 else None, None, None, B, 1, T)
+                                    nd if dm.host_tables.uses_step_noise else None, None, None, B, 1, T)
                 dm.clipped_noise((B, T, *x_shape), dev)                      # RNG: q_sample(context, to) of :983, unused
                 if self.trace is not None:
                     self.trace.append(dict(model_in=trace_in, levels_from=p.levels_from, levels_to=p.levels_to,
@@ -524,9 +524,9 @@ class DFoTVideo(BaseVideoAlgo):
             if not dry_run:
                 out = self._backbone_rows(model_in, lvl_dev[m], cond_for(p.nfe), cm_dev[m], B, p.nfe)
                 self.nfe_rows += B * p.nfe
-            # RNG ③: DDIM noise — drawn even when eta == 0 to keep the stream aligned with the reference
+            # RNG ③: the step's noise (DDIM sigma / DDPM) — drawn even when eta == 0, to stay aligned with the reference's stream
             nd = dm.clipped_noise((B * p.nfe, T, *x_shape), dev)
-            nd = nd if tb.eta != 0 else None
+            nd = nd if tb.uses_step_noise else None
             trace_in = model_in.float().clone() if self.trace is not None else None
             nxt = plans[m + 1] if m + 1 < n_steps else None
             if nxt is None:

@@ -102,7 +102,10 @@ class DiscreteDiffusion(nn.Module):
             sqrt_recip_alphas_cumprod=f("sqrt_recip_alphas_cumprod"),
             sqrt_recipm1_alphas_cumprod=f("sqrt_recipm1_alphas_cumprod"),
             logsnr=f("logsnr") if "logsnr" in tables else None, objective=self.objective,
-            eta=float(self.ddim_sampling_eta), clip_noise=float(self.clip_noise), timesteps=self.timesteps)
+            eta=float(self.ddim_sampling_eta), clip_noise=float(self.clip_noise), timesteps=self.timesteps,
+            is_ddim=self.is_ddim_sampling, posterior_mean_coef1=f("posterior_mean_coef1"),
+            posterior_mean_coef2=f("posterior_mean_coef2"),
+            posterior_log_variance_clipped=f("posterior_log_variance_clipped"))
 
     # ------------------------------------------------------------------ noise plumbing
     def randn(self, shape, device) -> torch.Tensor:
@@ -203,21 +206,20 @@ class DiscreteDiffusion(nn.Module):
     def sample_step(self, x: torch.Tensor, curr_noise_level: torch.Tensor, next_noise_level: torch.Tensor,
                     external_cond: Optional[torch.Tensor], external_cond_mask: Optional[torch.Tensor] = None,
                     guidance_fn: Optional[Callable] = None) -> torch.Tensor:
-        """(:386-538) backbone forward + fused per-frame DDIM update.  ``guidance_fn`` (reconstruction guidance,
-        needs autograd through the backbone) and DDPM sampling are out of scope."""
+        """(:386-538) backbone forward + fused per-frame update: DDIM, or the DDPM ancestral step (:423-452) when
+        sampling_timesteps == timesteps — the same kernel with another host coefficient table.  ``guidance_fn``
+        (reconstruction guidance) needs autograd through the backbone and is out of scope."""
         if guidance_fn is not None:
             raise NotImplementedError("guidance_fn / reconstruction guidance is not supported by dfot_b200")
-        if not self.is_ddim_sampling:
-            raise NotImplementedError("DDPM sampling (sampling_timesteps == timesteps) is not supported by dfot_b200")
         R, T = curr_noise_level.shape
         frm = curr_noise_level.detach().cpu().numpy().astype(np.int64)
         to = next_noise_level.detach().cpu().numpy().astype(np.int64)
         tb = self.host_tables
-        upd = sp.ddim_update_table(tb, frm, to, np.ones((R, T), np.float32), np.ones((R, T), np.int32))
+        upd = sp.step_update_table(tb, frm, to, np.ones((R, T), np.float32), np.ones((R, T), np.int32))
         levels = torch.from_numpy(sp.model_levels(tb, frm, self.is_continuous, self.precond_scale)).to(x.device)
         out = self.model(x, levels, external_cond, external_cond_mask)
         noise = self.clipped_noise(x.shape, x.device)          # drawn even when eta == 0 (:525-526)
         y = x.contiguous().float().clone()
         ops.sampler_step_hg(y, out, None, sp.to_device_bytes(upd, x.device), None,
-                            noise if tb.eta != 0 else None, None, None, R, 1, T)
+                            noise if tb.uses_step_noise else None, None, None, R, 1, T)
         return y

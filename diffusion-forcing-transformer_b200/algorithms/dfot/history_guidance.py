@@ -190,7 +190,7 @@ class HistoryGuidance:
             n_hist, draws_excl = B * h, True
         f2, t2 = f.reshape(B * nfe, T), t.reshape(B * nfe, T)
         generate = np.repeat((mask == 0).astype(np.int32)[:, None], nfe, 1).reshape(B * nfe, T)
-        update = sp.ddim_update_table(tb, f2, t2, w.reshape(B * nfe, T), generate)
+        update = sp.step_update_table(tb, f2, t2, w.reshape(B * nfe, T), generate)
         prep = np.zeros((B * nfe, T), dtype=sp.PREPARE_DTYPE)
         prep["mode"] = mode.reshape(B * nfe, T)
         prep["noise_row"] = noise_row.reshape(B * nfe, T)

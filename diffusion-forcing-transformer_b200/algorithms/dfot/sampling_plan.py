@@ -33,6 +33,52 @@ class HostTables:
     eta: float
     clip_noise: float
     timesteps: int
+    is_ddim: bool = True                                   # False: sampling_timesteps == timesteps, DDPM ancestral steps
+    posterior_mean_coef1: Optional[np.ndarray] = None
+    posterior_mean_coef2: Optional[np.ndarray] = None
+    posterior_log_variance_clipped: Optional[np.ndarray] = None
+
+    @property
+    def uses_step_noise(self) -> bool:
+        """Does the update consume the per-step noise draw?  (It is DRAWN either way, to keep the RNG stream aligned.)"""
+        return self.eta != 0 or not self.is_ddim
+
+
+def step_update_table(tb: "HostTables", frm: np.ndarray, to: np.ndarray, weight: np.ndarray,
+                      generate: np.ndarray) -> np.ndarray:
+    """Per (row, frame) coefficients of one sampling step: DDIM, or DDPM when sampling_timesteps == timesteps
+    (discrete_diffusion.py:386-421 dispatch)."""
+    return ddim_update_table(tb, frm, to, weight, generate) if tb.is_ddim else ddpm_update_table(tb, frm, weight, generate)
+
+
+def ddpm_update_table(tb: "HostTables", frm: np.ndarray, weight: np.ndarray, generate: np.ndarray) -> np.ndarray:
+    """DDPM ancestral step (discrete_diffusion.py:423-452, 231-240) in the same  x' = a*x + b*g(out) + sigma*noise  form:
+    x0 = ax*x + ao*g(out) by objective, mean = coef1[k]*x0 + coef2[k]*x, sigma = exp(0.5*log_var[k]) where k > 0 (the
+    reference zeroes the noise at k == 0), and the frame is kept only where the current level is -1."""
+    k = np.clip(frm, 0, None)
+    f8 = np.float64
+    c1, c2 = tb.posterior_mean_coef1.astype(f8)[k], tb.posterior_mean_coef2.astype(f8)[k]
+    sa = tb.sqrt_alphas_cumprod.astype(f8)[k]
+    sb = tb.sqrt_one_minus_alphas_cumprod.astype(f8)[k]
+    if tb.objective == "pred_v":
+        ax, ao, clip = sa, -sb, np.zeros_like(sa)
+    elif tb.objective == "pred_x0":
+        ax, ao, clip = np.zeros_like(sa), np.ones_like(sa), np.zeros_like(sa)
+    elif tb.objective == "pred_noise":
+        ax, ao = tb.sqrt_recip_alphas_cumprod.astype(f8)[k], -tb.sqrt_recipm1_alphas_cumprod.astype(f8)[k]
+        clip = np.full_like(sa, tb.clip_noise)
+    else:
+        raise ValueError(f"unknown objective {tb.objective}")
+    sigma = np.where(k > 0, np.exp(0.5 * tb.posterior_log_variance_clipped.astype(f8)[k]), 0.0)
+    keep = frm == -1
+    out = np.zeros(frm.shape, dtype=UPDATE_DTYPE)
+    out["a"] = np.where(keep, 1.0, c1 * ax + c2)
+    out["b"] = np.where(keep, 0.0, c1 * ao)
+    out["sigma"] = np.where(keep, 0.0, sigma)
+    out["w"] = weight
+    out["clip"] = clip
+    out["generate"] = generate
+    return out
 
 
 def ddim_update_table(tb: HostTables, frm: np.ndarray, to: np.ndarray, weight: np.ndarray,

@@ -2,7 +2,7 @@
 
 Restates algorithms/dfot/diffusion/discrete_diffusion.py
   q_sample :242-250, model_predictions :173-191, predict_* :193-223,
-  ddim_sample_step :454-538
+  ddim_sample_step :454-538, ddpm_sample_step :423-452 (+ q_posterior :231-240)
 and continuous_diffusion.py:118-138 (model is fed precond_scale*logsnr[k]).
 """
 from typing import Callable, Dict, Optional
@@ -35,7 +35,7 @@ class Diffusion:
         self.clip_noise = diff_cfg["clip_noise"]
         self.is_continuous = bool(diff_cfg.get("is_continuous", False))
         self.precond_scale = diff_cfg.get("precond_scale", 1.0)
-        assert self.sampling_timesteps < self.timesteps, "oracle covers DDIM sampling only (D4 out of scope)"
+        self.is_ddim_sampling = self.sampling_timesteps < self.timesteps       # else: DDPM ancestral step (:403-413)
 
     def clipped_noise(self, like: torch.Tensor) -> torch.Tensor:
         return torch.clamp(self.randn_like(like), -self.clip_noise, self.clip_noise)
@@ -92,7 +92,21 @@ class Diffusion:
         c = (1 - alpha_next - sigma ** 2).sqrt()
         return k, alpha_next, sigma, c
 
+    def ddpm_sample_step(self, x, curr, cond=None, cond_mask=None, return_model_out: bool = False):
+        # discrete_diffusion.py:423-452: x0 from the model, posterior mean / variance at level k, fresh noise where k > 0
+        k = torch.clamp(curr, min=0)
+        _, x0, out = self.predictions(x, k, cond, cond_mask)
+        mean = _per_frame(self.buf["posterior_mean_coef1"][k], x) * x0 + _per_frame(self.buf["posterior_mean_coef2"][k], x) * x
+        log_var = _per_frame(self.buf["posterior_log_variance_clipped"][k], x)
+        noise = torch.where(_per_frame(k > 0, x), self.randn_like(x), torch.zeros_like(x))
+        noise = torch.clamp(noise, -self.clip_noise, self.clip_noise)
+        x_new = mean + torch.exp(0.5 * log_var) * noise
+        x_new = torch.where(_per_frame(curr == -1, x), x, x_new)
+        return (x_new, out) if return_model_out else x_new
+
     def sample_step(self, x, curr, nxt, cond=None, cond_mask=None, return_model_out: bool = False):
+        if not self.is_ddim_sampling:
+            return self.ddpm_sample_step(x, curr, cond, cond_mask, return_model_out)
         # discrete_diffusion.py:454-538, guidance_fn=None branch
         k, alpha_next, sigma, c = self.ddim_coefficients(curr, nxt)
         eps, x0, out = self.predictions(x, k, cond, cond_mask)

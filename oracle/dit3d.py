@@ -1,4 +1,4 @@
-"""ORACLE (test infrastructure): DiT3D backbone forward (variant=full, rope_3d),
+"""ORACLE (test infrastructure): DiT3D backbone forward (variant=full; rope_3d, learned_1d or sinusoidal_1d positions),
 functional over a reference-keyed state dict.
 
 Restates
@@ -78,7 +78,8 @@ class DiT3DOracle:
     def __init__(self, backbone_cfg: dict, x_shape, max_tokens: int, state_dict: Dict[str, torch.Tensor],
                  external_cond_dim: int = 0):
         cfg = backbone_cfg
-        assert cfg.get("variant", "full") == "full" and cfg.get("pos_emb_type", "rope_3d") == "rope_3d"
+        self.pos_emb_type = cfg.get("pos_emb_type", "rope_3d")
+        assert cfg.get("variant", "full") == "full" and self.pos_emb_type in ("rope_3d", "learned_1d", "sinusoidal_1d")
         self.sd = {k: v.detach().float() for k, v in state_dict.items()}
         self.p = cfg["patch_size"]
         self.C, self.H, self.W = x_shape
@@ -91,7 +92,16 @@ class DiT3DOracle:
         self.use_fourier = bool(cfg.get("use_fourier_noise_embedding", False))
         self.external_cond_dim = external_cond_dim
         self.cond_dropout = cfg.get("external_cond_dropout", 0.0)
-        self.angles = rope_angles(self.dh, (max_tokens, self.gh, self.gw))
+        # dit_base.py:230-253: rope_3d rotates q / k in every block; learned_1d / sinusoidal_1d add one table to the tokens
+        self.angles = rope_angles(self.dh, (max_tokens, self.gh, self.gw)) if self.pos_emb_type == "rope_3d" else None
+        if self.pos_emb_type == "learned_1d":
+            self.pos_emb = self.sd["dit_base.pos_emb.pos_emb"]
+        elif self.pos_emb_type == "sinusoidal_1d":      # non-persistent buffer (dit_base.py:514-521, 528-580)
+            import numpy as np
+            n = max_tokens * self.P
+            omega = 1.0 / 10000 ** (np.arange(self.D // 2, dtype=np.float64) / (self.D / 2.0))
+            ang = np.einsum("m,d->md", np.arange(n, dtype=np.float32).astype(np.float64), omega)
+            self.pos_emb = torch.from_numpy(np.concatenate([np.sin(ang), np.cos(ang)], axis=1)).float().unsqueeze(0)
         # dit_base.py:185,192: MLP exists only if spatial_mlp_ratio is set (fork quirk Q2)
         self.use_mlp = "dit_base.blocks.0.mlp.fc1.weight" in self.sd
         self.taps = None  # optional dict filled with intermediates for kernel-level parity tests
@@ -122,7 +132,8 @@ class DiT3DOracle:
         B, N, D = y.shape
         qkv = _linear(y, self.sd, f"dit_base.blocks.{i}.attn.qkv")
         q, k, v = qkv.reshape(B, N, 3, self.heads, self.dh).permute(2, 0, 3, 1, 4).unbind(0)
-        q, k = apply_rope(q, self.angles), apply_rope(k, self.angles)
+        if self.angles is not None:
+            q, k = apply_rope(q, self.angles), apply_rope(k, self.angles)
         w = torch.softmax(q @ k.transpose(-2, -1) * (1 / math.sqrt(self.dh)), dim=-1)
         o = (w @ v).transpose(1, 2).reshape(B, N, D)
         if self.taps is not None and i == 0:
@@ -135,6 +146,8 @@ class DiT3DOracle:
         tok = F.conv2d(x.reshape(B * T, self.C, self.H, self.W).float(), sd["patch_embedder.proj.weight"],
                        sd["patch_embedder.proj.bias"], stride=self.p)
         tok = tok.flatten(2).transpose(1, 2).reshape(B, T * self.P, self.D)
+        if self.angles is None:
+            tok = tok + self.pos_emb[:, : tok.shape[1]]             # dit_base.py:352-353, 523-525
         emb = self.noise_embedding(noise_levels)
         if external_cond is not None:
             if "external_cond_embedding.embedding_table.weight" in sd:   # label conditioning (dit3d.py:171-173): a table

@@ -104,8 +104,14 @@ def diffusion_buffers(diff_cfg: dict) -> Dict[str, torch.Tensor]:
     kwargs = dict(diff_cfg.get("schedule_fn_kwargs") or {})
     betas = make_betas(diff_cfg["beta_schedule"], diff_cfg["timesteps"],
                        zero_terminal_snr=diff_cfg["objective"] != "pred_noise", **kwargs)
-    ac = torch.cumprod(1.0 - betas, dim=0)
+    alphas = 1.0 - betas
+    ac = torch.cumprod(alphas, dim=0)
+    ac_prev = torch.cat([torch.ones(1, dtype=ac.dtype), ac[:-1]])
+    post_var = betas * (1.0 - ac_prev) / (1.0 - ac)          # q(x_{t-1} | x_t, x_0), discrete_diffusion.py:135-157
     out = {
+        "posterior_log_variance_clipped": torch.log(post_var.clamp(min=1e-20)),
+        "posterior_mean_coef1": betas * torch.sqrt(ac_prev) / (1.0 - ac),
+        "posterior_mean_coef2": (1.0 - ac_prev) * torch.sqrt(alphas) / (1.0 - ac),
         "betas": betas,
         "alphas_cumprod": ac,
         "sqrt_alphas_cumprod": torch.sqrt(ac),
