@@ -475,7 +475,9 @@ def strong_section(args, wl, algo, dev, world):
         t1, o1 = timed(single, 2)
         t2, o2 = timed(split, 2)
         local = torch.randn((1, wl.n_tokens, *wl.x_shape), device=dev)
-        gather = lambda: D.gather_branch_outputs(local, 1, 2, mesh.branch_group)
+        bg = mesh.branch_group
+        shard = D.RowShard(world=bg.size, rank=bg.rank, group=bg.group)
+        gather = lambda: shard.gather(local, 2, tuple(local.shape[1:]), torch.float32, dev)
         gather()
         tg, _ = timed(gather, 20)
         rows = args.sampling_steps * wl.nfe

@@ -63,7 +63,8 @@ class DFoTVideo(BaseVideoAlgo):
         self.nfe_rows_planned = 0               # ... including rows another shard executes (dry_run replays)
         self.model_in_dtype = torch.bfloat16    # dtype of the branch inputs emitted by K4
         self.mesh = None                        # dfot_b200.distributed.Mesh for multi-GPU sampling (None = 1 GPU)
-        self.shard_chunks = False               # interpolation chunk batches spread over the dp axis (sample_sharded)
+        self.row_shard = None                   # distributed.RowShard: forward rows dealt over the whole world (sample_sharded)
+        self._row_cond_cache: Dict = {}
 
     def _build_model(self) -> None:
         super()._build_model(ContinuousDiffusion if self.cfg.diffusion.is_continuous else DiscreteDiffusion)
@@ -147,23 +148,24 @@ class DFoTVideo(BaseVideoAlgo):
                                      "Supported types are 'label' and 'action'.")
             rows = ctx.shape[0]
             mb = task.get("max_batch_size") or rows
-            # Chunk batches of one round are independent (SURVEY.md §8e axis 3).  With `shard_chunks` (set by
-            # sample_sharded when the samples themselves cannot fill the dp axis) batch i is sampled by dp shard
-            # i mod dp; the other shards replay its noise draws only, so the result equals the single-GPU rollout.
-            mesh = self.mesh if self.shard_chunks else None
-            outs, owners = [], []
-            for bi, s in enumerate(range(0, rows, mb)):   # every chunk is processed (the reference's conditions=None
-                e = min(rows, s + mb)                     # path drops the last partial batch — quirk Q10, not replicated)
-                owner = bi % mesh.dp if mesh is not None else 0
-                o, _ = self._window_sampler()(batch_size=e - s, context=ctx[s:e],
-                                             context_mask=torch.from_numpy(msk[s:e].astype(np.int64)),
-                                             conditions=None if cnd is None else cnd[s:e], history_guidance=guidance,
-                                             dry_run=mesh is not None and owner != mesh.dp_index)
-                outs.append(o)
-                owners.append(owner)
-            if mesh is not None:
-                from dfot_b200 import distributed as D
-                outs = [D.broadcast_from_shard(o.contiguous(), owner, mesh) for o, owner in zip(outs, owners)]
+            # every chunk is processed (the reference's conditions=None path drops the last partial batch — quirk Q10,
+            # not replicated).  The chunk batches of one round are independent (SURVEY.md §8e axis 3): on one GPU they are
+            # sampled one after the other like the reference does; with a row shard they advance in lockstep, so that the
+            # rows of the WHOLE round are what the GPUs share (`_run_lockstep`; same noise per batch either way).
+            spans = [(s, min(rows, s + mb)) for s in range(0, rows, mb)]
+
+            def maker(s, e):
+                return lambda dry: _WindowRun(self, e - s, None, ctx[s:e], torch.from_numpy(msk[s:e].astype(np.int64)),
+                                              None if cnd is None else cnd[s:e], None, 0.0, guidance, False, dry=dry)
+
+            sampler = self._window_sampler()
+            if self.row_shard is not None and sampler == self._sample_sequence and self.diffusion_model.noise_can_fork():
+                outs = [o for o, _ in self._run_lockstep([maker(s, e) for s, e in spans])]
+            else:
+                outs = [sampler(batch_size=e - s, context=ctx[s:e],
+                                context_mask=torch.from_numpy(msk[s:e].astype(np.int64)),
+                                conditions=None if cnd is None else cnd[s:e], history_guidance=guidance)[0]
+                        for s, e in spans]
             outs = torch.cat(outs, 0)
             for c, i, pred in zip(chunks, idx, outs.chunk(len(chunks), 0)):
                 xs[:, i] = pred[:, : len(c)]
@@ -234,25 +236,11 @@ class DFoTVideo(BaseVideoAlgo):
         """Branch-input tensor the fused sampler kernel writes into: the backbone's static (graph-captured) input
         when it offers one, so no copy sits between K4 and the forward."""
         model = self.diffusion_model.model
-        bg = self.mesh.branch_group if self.mesh is not None else None
-        if hasattr(model, "input_buffer") and bg is None:
+        if hasattr(model, "input_buffer") and self._active_row_shard() is None:
             return model.input_buffer(rows, T, self.model_in_dtype, dev)
         return torch.empty((rows, T, *self.x_shape), dtype=self.model_in_dtype, device=dev)
 
     # ------------------------------------------------------------------ multi-GPU (SURVEY.md §8e)
-    def _backbone_rows(self, model_in, levels, cond, cond_mask, B: int, nfe: int):
-        """Backbone forward over the (b, j) branch rows; with a branch group each member runs its share of the
-        branches and the outputs are all-gathered (the only per-step collective of the path)."""
-        dm = self.diffusion_model
-        bg = self.mesh.branch_group if self.mesh is not None else None
-        if bg is None or nfe == 1:
-            return dm.model(model_in, levels, cond, cond_mask, out_dtype=torch.float32)
-        from dfot_b200 import distributed as D
-        rows = torch.tensor(D.branch_rows(B, nfe, bg), device=model_in.device)
-        sel = lambda t: None if t is None else t.index_select(0, rows)
-        local = dm.model(sel(model_in), sel(levels), sel(cond), sel(cond_mask), out_dtype=torch.float32)
-        return D.gather_branch_outputs(local, B, nfe, bg)
-
     @torch.no_grad()
     def sample_sharded(self, xs: Tensor, conditions: Optional[Tensor] = None,
                        n_context_tokens: Optional[int] = None) -> Tensor:
@@ -265,14 +253,15 @@ class DFoTVideo(BaseVideoAlgo):
         if mesh is None:
             return self._predict_videos(xs, n_ctx, conditions)
         if xs.shape[0] < mesh.dp:
-            # fewer samples than dp shards (the 200-frame single-sample rollout of BASELINE config[3]): every shard rolls
-            # the whole batch — keyframe windows replicated (branches still split inside the branch group), interpolation
-            # chunk batches spread over the dp axis.  All ranks must share the noise seed.
-            self.shard_chunks = True
+            # fewer samples than dp shards (the 200-frame single-sample rollout of BASELINE config[3]): the sampler state
+            # is replicated on every rank — all ranks must share the noise seed — and the backbone forward rows (keyframe
+            # windows; whole interpolation rounds in lockstep) are dealt over ALL ranks.  Every rank ends with the video.
+            self.row_shard = D.RowShard()
             try:
                 return self._predict_videos(xs, n_ctx, conditions)
             finally:
-                self.shard_chunks = False
+                self.row_shard = None
+                self._row_cond_cache = {}
         counts = [len(range(*D.shard_batch(xs.shape[0], mesh.dp, d).indices(xs.shape[0]))) for d in range(mesh.dp)]
         sl = D.shard_batch(xs.shape[0], mesh.dp, mesh.dp_index)
         # Every rank is seeded identically (the replicated paths above and inside a branch group need ONE noise stream);
@@ -405,7 +394,7 @@ class DFoTVideo(BaseVideoAlgo):
                 self.nfe_rows_planned += B
                 lv = torch.from_numpy(p.levels).to(dev, non_blocking=True)
                 cm = None if p.cond_mask is None else torch.from_numpy(p.cond_mask).to(dev, non_blocking=True)
-                out = self._backbone_rows(model_in, lv, cond, cm, B, 1)
+                out = dm.model(model_in, lv, cond, cm, out_dtype=torch.float32)
                 self.nfe_rows += B
                 nd = dm.clipped_noise((B, T, *x_shape), dev)                 # RNG: DDIM noise, drawn even when eta == 0
                 trace_in = model_in.float().clone() if self.trace is not None else None
@@ -436,10 +425,136 @@ class DFoTVideo(BaseVideoAlgo):
                          guidance_fn: Optional[Callable] = None, reconstruction_guidance: float = 0.0,
                          history_guidance: Optional[HistoryGuidance] = None, return_all: bool = False,
                          pbar=None, dry_run: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
-        """The window sampler (reference `_sample_sequence`, dfot_video.py:530-763).  `dry_run` (multi-GPU chunk
-        sharding) draws exactly the noise a real call would — so every rank's generator stays where the single-GPU run
-        would have it — but launches no kernel; the returned tensor is a placeholder for the owner's broadcast."""
-        x_shape = self.x_shape
+        """The window sampler (reference `_sample_sequence`, dfot_video.py:530-763): plan the window, then per step one
+        backbone forward over the branch rows and one fused K4 launch.  `dry_run` draws exactly the noise a real call
+        would — so the generator ends where the real call leaves it — but launches no kernel."""
+        run = _WindowRun(self, batch_size, length, context, context_mask, conditions, guidance_fn, reconstruction_guidance,
+                         history_guidance, return_all, dry=dry_run)
+        run.begin()
+        while not run.done:
+            run.advance(None if dry_run else self._forward_runs([run])[0])
+        return run.result()
+
+    # ------------------------------------------------------------------ backbone forward over the rows of >= 1 windows
+    def _active_row_shard(self):
+        """How the forward rows are spread over GPUs: the whole world (`row_shard`, replicated sampler state), the members
+        of this sample shard's branch group (mesh br > 1), or not at all."""
+        if self.row_shard is not None:
+            return self.row_shard
+        bg = self.mesh.branch_group if self.mesh is not None else None
+        if bg is None:
+            return None
+        if getattr(self, "_bg_shard", None) is None or self._bg_shard.group is not bg.group:
+            from dfot_b200 import distributed as D
+            self._bg_shard = D.RowShard(world=bg.size, rank=bg.rank, group=bg.group)
+        return self._bg_shard
+
+    def _forward_runs(self, runs: List["_WindowRun"]) -> List[Tensor]:
+        """ONE backbone forward for the current step of every window in `runs` (their branch rows concatenated) — on a
+        single GPU over all rows; with a row shard over this rank's contiguous block of the rows, followed by the only
+        per-step collective of the path: an all_gather_into_tensor of the outputs."""
+        dm = self.diffusion_model
+        ins = [r.step_inputs() for r in runs]
+        counts = [i["model_in"].shape[0] for i in ins]
+        n = sum(counts)
+        self.nfe_rows_planned += n
+        rs = self._active_row_shard()
+        if rs is None and len(runs) == 1:
+            i = ins[0]
+            self.nfe_rows += n
+            return [dm.model(i["model_in"], i["levels"], i["cond"], i["cond_mask"], out_dtype=torch.float32)]
+        start, stop = (0, n) if rs is None else rs.block(n)[1:]
+        pieces, off = [], 0
+        for k, c in enumerate(counts):          # (window, first row, last row) of the rows in [start, stop)
+            lo, hi = max(start, off), min(stop, off + c)
+            if lo < hi:
+                pieces.append((k, lo - off, hi - off))
+            off += c
+        local = None
+        if pieces:
+            cat = lambda key: torch.cat([ins[k][key][lo:hi] for k, lo, hi in pieces], 0)
+            cond = self._gather_conditions([(runs[k], ins[k]["cond"], lo, hi) for k, lo, hi in pieces])
+            cm = None if ins[pieces[0][0]]["cond_mask"] is None else cat("cond_mask")
+            local = dm.model(cat("model_in"), cat("levels"), cond, cm, out_dtype=torch.float32)
+            self.nfe_rows += stop - start
+        if rs is None:
+            full = local
+        else:
+            ref = ins[0]["model_in"]
+            full = rs.gather(local, n, tuple(ref.shape[1:]), torch.float32, ref.device)
+        return list(full.split(counts, 0))
+
+    def _gather_conditions(self, pieces):
+        """Conditioning of the local rows of a multi-window forward.  Tensors (actions, labels) are concatenated; the
+        camera-pose handles of the U-ViT are merged into ONE handle over the windows this rank actually forwards, cached per
+        set of pieces so that the pose modulation cache is filled once per round, not once per step."""
+        conds = [c for _, c, _, _ in pieces]
+        if conds[0] is None:
+            return None
+        if torch.is_tensor(conds[0]):
+            return torch.cat([c[lo:hi] for _, c, lo, hi in pieces], 0)
+        key = tuple((id(r), lo, hi) for r, _, lo, hi in pieces)
+        hit = self._row_cond_cache.get(key)
+        if hit is None:
+            from .backbones.u_vit.u_vit3d_pose import PoseCondition
+            cams, row_map = [], []
+            for _, c, lo, hi in pieces:
+                used = sorted(set(c.row_map[lo:hi]))
+                base = sum(x.shape[0] for x in cams)
+                cams.append(c.cams[used])
+                row_map += [base + used.index(j) for j in c.row_map[lo:hi]]
+            hit = PoseCondition(torch.cat(cams, 0), row_map)
+            self._row_cond_cache = {key: hit}          # one live entry: the previous round's cache can go
+        return hit
+
+    @torch.no_grad()
+    def _run_lockstep(self, makers: List[Callable]) -> List[Tuple[Tensor, Optional[Tensor]]]:
+        """Independent windows that the reference samples one after the other (the chunk batches of an interpolation round,
+        dfot_video.py:284-358), advanced TOGETHER: one backbone forward per step over the rows of all of them — which is
+        what lets 8 GPUs share a round of 70 rows evenly instead of 4 chunks at a time.  Every window still draws exactly
+        the noise the sequential order gives it: the stream position at the start of each window is found by replaying
+        the preceding windows' draws (no kernels), and each window then draws from its own position.
+        makers[i](dry) -> _WindowRun."""
+        dm = self.diffusion_model
+        dev = self.device
+        states = []
+        for mk in makers:
+            states.append(dm.noise_get_state(dev))
+            r = mk(True)
+            r.begin()
+            while not r.done:
+                r.advance(None)
+        final = dm.noise_get_state(dev)
+        runs = []
+        for mk, st in zip(makers, states):
+            dm.noise_set_state(dev, st)
+            r = mk(False)
+            r.begin()
+            r.noise_state = dm.noise_get_state(dev)
+            runs.append(r)
+        while True:
+            active = [r for r in runs if not r.done]
+            if not active:
+                break
+            for r, out in zip(active, self._forward_runs(active)):
+                dm.noise_set_state(dev, r.noise_state)
+                r.advance(out)
+                r.noise_state = dm.noise_get_state(dev)
+        dm.noise_set_state(dev, final)
+        return [r.result() for r in runs]
+
+
+class _WindowRun:
+    """One denoising window as a resumable state machine: `begin()` builds the first step's branch inputs, `step_inputs()`
+    hands them to a backbone forward, `advance(out)` applies the fused K4 step (DDIM / DDPM update, guidance combine,
+    context revert, next step's branch inputs).  RNG order = the reference's: (1) initial noise; per step (2) history
+    re-noising + excluded-token noise of the step's branch inputs, (3) the step's update noise."""
+
+    def __init__(self, algo: DFoTVideo, batch_size: int, length: Optional[int], context: Optional[Tensor],
+                 context_mask: Optional[Tensor], conditions: Optional[Tensor], guidance_fn: Optional[Callable],
+                 reconstruction_guidance: float, history_guidance: Optional[HistoryGuidance], return_all: bool,
+                 dry: bool = False):
+        x_shape = algo.x_shape
         if guidance_fn is not None or reconstruction_guidance > 0:
             raise NotImplementedError("guidance_fn / reconstruction guidance needs autograd through the backbone "
                                       "and is outside the dfot_b200 scope (SURVEY.md §3.4)")
@@ -448,8 +563,8 @@ class DFoTVideo(BaseVideoAlgo):
             raise ValueError("context must be provided")
         if length is None:
             length = context.shape[1]
-        if length > self.max_tokens:
-            raise ValueError(f"length is expected to <={self.max_tokens}, got {length}.")
+        if length > algo.max_tokens:
+            raise ValueError(f"length is expected to <={algo.max_tokens}, got {length}.")
         if context_mask is None:
             raise ValueError("context_mask must be provided if context is given.")
         if context.shape[0] != batch_size:
@@ -460,94 +575,116 @@ class DFoTVideo(BaseVideoAlgo):
             raise ValueError(f"context shape not compatible with x_stacked_shape {x_shape}.")
         if tuple(context.shape[:2]) != tuple(context_mask.shape):
             raise ValueError("context and context_mask must have the same shape.")
-        dev = context.device
-        dm = self.diffusion_model
-        B = batch_size
-        horizon = length if self.use_causal_mask else self.max_tokens
-        padding = horizon - length
+        self.algo, self.dry, self.return_all = algo, dry, return_all
+        self.dev = dev = context.device
+        self.dm = dm = algo.diffusion_model
+        self.B = B = batch_size
+        horizon = length if algo.use_causal_mask else algo.max_tokens
+        self.T, self.padding = horizon, horizon - length
+        self.conditions = conditions
+        self.noise_state = None
 
-        # ---- RNG ①: initial noise (:607-612)
-        if dm.noise_source is None and self.generator is not None:
-            x = torch.randn((B, horizon, *x_shape), device=dev, generator=self.generator)
+        # ---- RNG (1): initial noise (:607-612)
+        if dm.noise_source is None and algo.generator is not None:
+            x = torch.randn((B, horizon, *x_shape), device=dev, generator=algo.generator)
         else:
             x = dm.randn((B, horizon, *x_shape), dev)
-        x = torch.clamp(x, -self.clip_noise, self.clip_noise)
-
+        x = torch.clamp(x, -algo.clip_noise, algo.clip_noise)
         mask = context_mask.detach().cpu().numpy().astype(np.int64)
-        if padding > 0:   # -1 marks padding frames (:620-630); they carry noise at level T-1 and ARE attended (Q4)
-            context = torch.cat([context, torch.zeros((B, padding, *x_shape), dtype=context.dtype, device=dev)], 1)
-            mask = np.concatenate([mask, -np.ones((B, padding), dtype=np.int64)], 1)
+        if self.padding > 0:   # -1 marks padding frames (:620-630); they carry noise at level T-1 and ARE attended (Q4)
+            context = torch.cat([context, torch.zeros((B, self.padding, *x_shape), dtype=context.dtype, device=dev)], 1)
+            mask = np.concatenate([mask, -np.ones((B, self.padding), dtype=np.int64)], 1)
         if history_guidance is None:
-            history_guidance = HistoryGuidance.conditional(timesteps=self.timesteps)
+            history_guidance = HistoryGuidance.conditional(timesteps=algo.timesteps)
         mask_dev = torch.from_numpy(mask).to(dev)
-        x = torch.where(self._extend_x_dim(mask_dev) >= 1, context.float(), x).contiguous()
+        self.x = torch.where(algo._extend_x_dim(mask_dev) >= 1, context.float(), x).contiguous()
 
-        plans = self.plan_window(mask, horizon, padding, history_guidance)
-        n_steps = len(plans)
-        tb = dm.host_tables
-        upd_dev = [sp.to_device_bytes(p.update, dev) for p in plans]
-        prep_dev = [sp.to_device_bytes(p.prepare, dev) for p in plans]
-        lvl_dev = [torch.from_numpy(p.levels).to(dev, non_blocking=True) for p in plans]
-        cm_dev = [None if p.cond_mask is None else torch.from_numpy(p.cond_mask).to(dev, non_blocking=True)
-                  for p in plans]
-        cond_cache: Dict[int, Tensor] = {}
+        self.plans = algo.plan_window(mask, horizon, self.padding, history_guidance)
+        self.n_steps = len(self.plans)
+        if not dry:
+            self.upd_dev = [sp.to_device_bytes(p.update, dev) for p in self.plans]
+            self.prep_dev = [sp.to_device_bytes(p.prepare, dev) for p in self.plans]
+            self.lvl_dev = [torch.from_numpy(p.levels).to(dev, non_blocking=True) for p in self.plans]
+            self.cm_dev = [None if p.cond_mask is None else torch.from_numpy(p.cond_mask).to(dev, non_blocking=True)
+                           for p in self.plans]
+        self.cond_cache: Dict[int, Tensor] = {}
+        self.record = [] if return_all else None
+        self.model_in = None
+        self.m = 0
 
-        def cond_for(nfe: int):
-            if conditions is None or dry_run:
-                return None
-            if nfe not in cond_cache:   # constant over the window (the reference recomputes it every step, :732-743)
-                cond_cache[nfe] = self._window_conditions(conditions.to(dev), nfe)
-            return cond_cache[nfe]
+    @property
+    def done(self) -> bool:
+        return self.m >= self.n_steps
 
-        def draw_prepare_noise(p: sp.StepPlan):
-            # RNG ②: q_sample noise, then (full manager only) the excluded-token noise — always drawn
-            nh = dm.clipped_noise((p.n_hist_rows, horizon, *x_shape), dev) if p.n_hist_rows else None
-            ne = dm.randn((B * p.nfe, horizon, *x_shape), dev) if p.draws_excluded_noise else None
-            return nh, ne
+    def _cond_for(self, nfe: int):
+        if self.conditions is None or self.dry:
+            return None
+        if nfe not in self.cond_cache:   # constant over the window (the reference recomputes it every step, :732-743)
+            self.cond_cache[nfe] = self.algo._window_conditions(self.conditions.to(self.dev), nfe)
+        return self.cond_cache[nfe]
 
-        record = [] if return_all else None
-        T = horizon
-        model_in = None
-        def k4(*args, hist_rows: int = 0):
-            if not dry_run:
-                ops.sampler_step_hg(*args, max_noise_row=hist_rows - 1 if hist_rows else None)
+    def _draw_prepare_noise(self, p: sp.StepPlan):
+        # RNG (2): q_sample noise, then (full manager only) the excluded-token noise — always drawn
+        shape = (self.T, *self.algo.x_shape)
+        nh = self.dm.clipped_noise((p.n_hist_rows, *shape), self.dev) if p.n_hist_rows else None
+        ne = self.dm.randn((self.B * p.nfe, *shape), self.dev) if p.draws_excluded_noise else None
+        return nh, ne
 
-        for m, p in enumerate(plans):
-            if return_all:
-                record.append(x.clone())
-            if m == 0:
-                nh, ne = draw_prepare_noise(p)
-                model_in = self._model_in_buffer(B * p.nfe, T, dev)
-                k4(x, None, model_in, None, prep_dev[0], None, nh, ne, B, p.nfe, T, hist_rows=p.n_hist_rows)
-            out = None
-            self.nfe_rows_planned += B * p.nfe
-            if not dry_run:
-                out = self._backbone_rows(model_in, lvl_dev[m], cond_for(p.nfe), cm_dev[m], B, p.nfe)
-                self.nfe_rows += B * p.nfe
-            # RNG ③: the step's noise (DDIM sigma / DDPM) — drawn even when eta == 0, to stay aligned with the reference's stream
-            nd = dm.clipped_noise((B * p.nfe, T, *x_shape), dev)
-            nd = nd if tb.uses_step_noise else None
-            trace_in = model_in.float().clone() if self.trace is not None else None
-            nxt = plans[m + 1] if m + 1 < n_steps else None
-            if nxt is None:
-                k4(x, out, None, upd_dev[m], None, nd, None, None, B, p.nfe, T)
-            else:
-                nh, ne = draw_prepare_noise(nxt)
-                nxt_in = model_in if nxt.nfe == p.nfe else self._model_in_buffer(B * nxt.nfe, T, dev)
-                if nxt.nfe == p.nfe:   # one fused launch: update + combine + revert + next-step prepare
-                    k4(x, out, nxt_in, upd_dev[m], prep_dev[m + 1], nd, nh, ne, B, p.nfe, T, hist_rows=nxt.n_hist_rows)
-                else:                  # branch count changes between steps: split into update and prepare launches
-                    k4(x, out, None, upd_dev[m], None, nd, None, None, B, p.nfe, T)
-                    k4(x, None, nxt_in, None, prep_dev[m + 1], None, nh, ne, B, nxt.nfe, T, hist_rows=nxt.n_hist_rows)
-                model_in = nxt_in
-            if self.trace is not None and not dry_run:
-                self.trace.append(dict(model_in=trace_in, levels_from=p.levels_from, levels_to=p.levels_to,
-                                       cond_mask=p.cond_mask, model_out=out.float().clone(), x_after=x.clone(),
-                                       context_mask=p.context_mask))
-        if return_all:
-            record.append(x.clone())
-            record = torch.stack(record)
-        if padding > 0:
-            x = x[:, :-padding]
-            record = record[:, :, :-padding] if return_all else None
+    def _k4(self, *args, hist_rows: int = 0):
+        if not self.dry:
+            ops.sampler_step_hg(*args, max_noise_row=hist_rows - 1 if hist_rows else None)
+
+    def begin(self) -> None:
+        if self.n_steps == 0:
+            return
+        p = self.plans[0]
+        nh, ne = self._draw_prepare_noise(p)
+        if not self.dry:
+            self.model_in = self.algo._model_in_buffer(self.B * p.nfe, self.T, self.dev)
+        self._k4(self.x, None, self.model_in, None, None if self.dry else self.prep_dev[0], None, nh, ne, self.B, p.nfe,
+                 self.T, hist_rows=p.n_hist_rows)
+
+    def step_inputs(self) -> dict:
+        p = self.plans[self.m]
+        return dict(model_in=self.model_in, levels=self.lvl_dev[self.m], cond=self._cond_for(p.nfe),
+                    cond_mask=self.cm_dev[self.m])
+
+    def advance(self, out: Optional[Tensor]) -> None:
+        algo, dm, m, B, T = self.algo, self.dm, self.m, self.B, self.T
+        p = self.plans[m]
+        if self.return_all:
+            self.record.append(self.x.clone())
+        # RNG (3): the step's noise (DDIM sigma / DDPM) — drawn even when eta == 0, to stay aligned with the reference
+        nd = dm.clipped_noise((B * p.nfe, T, *algo.x_shape), self.dev)
+        nd = nd if dm.host_tables.uses_step_noise else None
+        tracing = algo.trace is not None and not self.dry
+        trace_in = self.model_in.float().clone() if tracing else None
+        nxt = self.plans[m + 1] if m + 1 < self.n_steps else None
+        upd = None if self.dry else self.upd_dev[m]
+        if nxt is None:
+            self._k4(self.x, out, None, upd, None, nd, None, None, B, p.nfe, T)
+        else:
+            nh, ne = self._draw_prepare_noise(nxt)
+            prep = None if self.dry else self.prep_dev[m + 1]
+            if nxt.nfe == p.nfe:   # one fused launch: update + combine + revert + next-step prepare
+                self._k4(self.x, out, self.model_in, upd, prep, nd, nh, ne, B, p.nfe, T, hist_rows=nxt.n_hist_rows)
+            else:                  # branch count changes between steps: split into update and prepare launches
+                self._k4(self.x, out, None, upd, None, nd, None, None, B, p.nfe, T)
+                if not self.dry:
+                    self.model_in = algo._model_in_buffer(B * nxt.nfe, T, self.dev)
+                self._k4(self.x, None, self.model_in, None, prep, None, nh, ne, B, nxt.nfe, T, hist_rows=nxt.n_hist_rows)
+        if tracing:
+            algo.trace.append(dict(model_in=trace_in, levels_from=p.levels_from, levels_to=p.levels_to,
+                                   cond_mask=p.cond_mask, model_out=out.float().clone(), x_after=self.x.clone(),
+                                   context_mask=p.context_mask))
+        self.m += 1
+
+    def result(self) -> Tuple[Tensor, Optional[Tensor]]:
+        x, record = self.x, None
+        if self.return_all:
+            self.record.append(x.clone())
+            record = torch.stack(self.record)
+        if self.padding > 0:
+            x = x[:, :-self.padding]
+            record = record[:, :, :-self.padding] if self.return_all else None
         return x, record

@@ -118,6 +118,34 @@ class DiscreteDiffusion(nn.Module):
     def clipped_noise(self, shape, device) -> torch.Tensor:
         return torch.clamp(self.randn(shape, device), -self.clip_noise, self.clip_noise)
 
+    def _torch_generator(self, device) -> torch.Generator:
+        if self.generator is not None:
+            return self.generator
+        device = torch.device(device)
+        if device.type == "cuda":
+            return torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+        return torch.default_generator
+
+    def noise_get_state(self, device):
+        """Position of the noise stream (host-side: seed + offset of torch's generator, or the injected source's own state).
+        Lets independent windows that the reference samples one after the other advance TOGETHER (lockstep rounds,
+        DFoTVideo._run_lockstep) while each still draws exactly the values the sequential order gives it."""
+        if self.noise_source is not None:
+            get = getattr(self.noise_source, "get_state", None)
+            if get is None:
+                raise RuntimeError("the injected noise_source cannot fork its stream (no get_state / set_state)")
+            return get()
+        return self._torch_generator(device).get_state()
+
+    def noise_set_state(self, device, state) -> None:
+        if self.noise_source is not None:
+            self.noise_source.set_state(state)
+        else:
+            self._torch_generator(device).set_state(state)
+
+    def noise_can_fork(self) -> bool:
+        return self.noise_source is None or (hasattr(self.noise_source, "get_state") and hasattr(self.noise_source, "set_state"))
+
     # ------------------------------------------------------------------ reference API
     def ddim_idx_to_noise_level(self, indices: torch.Tensor) -> torch.Tensor:
         # fp32 linspace then truncation (discrete_diffusion.py:379-384) — bit-exact host arithmetic

@@ -4,15 +4,17 @@ sequence:
 
   * samples  — every rank samples its own slice of the batch with no communication inside the loop; one
                all_gather of the finished samples at the end (`gather_samples`);
-  * interpolation chunk batches — when there are fewer samples than dp shards, the chunk batches of an interpolation
-               round (independent `_sample_sequence` calls) are dealt round-robin over the dp axis; every other shard
-               replays the batch's noise draws only, and the owner broadcasts the finished batch
-               (`broadcast_from_shard`), so the result equals the single-GPU rollout;
+  * forward rows — when there are fewer samples than dp shards (the single-sample 200-frame rollout), the sampler
+               state (x_t, plans, noise) is REPLICATED on every rank and only the backbone forward is sharded: the branch
+               rows of a keyframe window, or of ALL chunk batches of an interpolation round advancing in lockstep, are dealt
+               in equal contiguous blocks over the whole world (`RowShard`), one `all_gather_into_tensor` of the backbone
+               outputs per step, then every rank runs the identical fused K4 steps (same noise seed);
   * VAE decode — after the final gather every rank holds every sampled latent; the decode (per-sample independent) is
                dealt over ALL ranks and gathered once (`decode_sharded`);
-  * history-guidance branches — within a branch group of `br` ranks (br divides nfe) each rank runs the backbone
-               on its share of the branch rows of every sample; one all_gather of the backbone output per step,
-               after which every member runs the identical fused K4 step (same noise seed), so x_t stays replicated.
+  * history-guidance branches — within a branch group of `br` ranks each rank runs the backbone on its contiguous
+               block of the group's (sample, branch) rows (`RowShard` over the group: with one sample per group that is one
+               branch per member); one all_gather_into_tensor of the backbone output per step, after which every member
+               runs the identical fused K4 step (same noise seed), so x_t stays replicated inside the group.
 
 Mesh: world = dp x br, rank = dp_index * br + br_index.
 """
@@ -71,23 +73,6 @@ def shard_batch(n: int, parts: int, index: int) -> slice:
     return slice(start, start + base + (1 if index < extra else 0))
 
 
-def branch_rows(batch: int, nfe: int, bg: BranchGroup) -> List[int]:
-    """Rows (b, j) of the (b h g)-ordered branch batch owned by this member: j ≡ rank (mod size)."""
-    if nfe % bg.size:
-        raise ValueError(f"nfe={nfe} is not divisible by the branch-group size {bg.size}")
-    return [b * nfe + j for b in range(batch) for j in range(nfe) if j % bg.size == bg.rank]
-
-
-def gather_branch_outputs(local: torch.Tensor, batch: int, nfe: int, bg: BranchGroup) -> torch.Tensor:
-    """all_gather of the per-step backbone outputs inside the branch group, re-ordered to (b, j)."""
-    per = nfe // bg.size
-    parts = [torch.empty_like(local) for _ in range(bg.size)]
-    dist.all_gather(parts, local.contiguous(), group=bg.group)
-    # member m holds rows (b, j = m + size*k), k < per, ordered (b, k)
-    stacked = torch.stack(parts, 0).reshape(bg.size, batch, per, *local.shape[1:])   # [m, b, k, ...]
-    return stacked.permute(1, 2, 0, *range(3, stacked.ndim)).reshape(batch * nfe, *local.shape[1:]).contiguous()
-
-
 def gather_samples(local: torch.Tensor, mesh: Mesh, counts: List[int]) -> torch.Tensor:
     """Final all_gather of the samples of all dp shards (ragged shards are padded to the largest)."""
     if mesh.dp == 1:
@@ -100,13 +85,36 @@ def gather_samples(local: torch.Tensor, mesh: Mesh, counts: List[int]) -> torch.
     return torch.cat([p[:c] for p, c in zip(parts, counts)], 0)
 
 
-def broadcast_from_shard(t: torch.Tensor, owner_dp_index: int, mesh: Mesh) -> torch.Tensor:
-    """Broadcast a finished chunk batch from dp shard `owner_dp_index` to the same branch member of every other shard
-    (in place; x_t is replicated inside a branch group, so each member serves its own column of the mesh)."""
-    if mesh.dp == 1:
-        return t
-    dist.broadcast(t, src=owner_dp_index * mesh.br + mesh.br_index, group=mesh.dp_group if mesh.br > 1 else None)
-    return t
+class RowShard:
+    """Deal n forward-rows over the whole world in equal contiguous blocks of `per = ceil(n / world)` rows (the last
+    blocks may be short or empty) and bring the per-row outputs back to every rank with ONE all_gather_into_tensor into a
+    [world * per, ...] buffer whose first n rows are the outputs in row order — no list gather, no re-ordering copies."""
+
+    def __init__(self, world: Optional[int] = None, rank: Optional[int] = None, group=None):
+        self.world = dist.get_world_size(group) if world is None else world
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.group = group
+        self._bufs = {}
+
+    def block(self, n: int):
+        """(per, start, stop): this rank forwards rows [start, stop) of the n."""
+        per = -(-n // self.world)
+        start = min(self.rank * per, n)
+        return per, start, min(start + per, n)
+
+    def gather(self, local: Optional[torch.Tensor], n: int, row_shape, dtype, device) -> torch.Tensor:
+        """local: [stop - start, *row_shape] outputs of this rank's rows (None when it has none) -> [n, *row_shape]."""
+        per, start, stop = self.block(n)
+        key = (n, tuple(row_shape), dtype, str(device))
+        buf = self._bufs.get(key)
+        if buf is None:
+            buf = self._bufs[key] = (torch.empty((self.world * per, *row_shape), dtype=dtype, device=device),
+                                     torch.zeros((per, *row_shape), dtype=dtype, device=device))
+        full, mine = buf
+        if stop > start:
+            mine[: stop - start].copy_(local)
+        dist.all_gather_into_tensor(full, mine, group=self.group)
+        return full[:n]
 
 
 def decode_sharded(decode_fn, latents: torch.Tensor) -> torch.Tensor:

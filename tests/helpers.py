@@ -53,3 +53,13 @@ class NoiseBank:
 
     def randn_like(self, x):
         return self.randn(x.shape)
+
+    # usable directly as `diffusion_model.noise_source` — and forkable, which the lockstep rounds of the multi-GPU path need
+    def __call__(self, shape, device):
+        return self.randn(shape).to(device)
+
+    def get_state(self):
+        return self.i
+
+    def set_state(self, i):
+        self.i = i
