@@ -328,9 +328,12 @@ __device__ __forceinline__ void gn_flush_impl(const Params& p, int lane, int m0,
       }
     }
     if (lane < LPR && (lane % lpg) == 0 && col_ok) {
-      double* dst = base + ((col0 + g * CPL) / cpg) * 2;
-      atomicAdd(dst, (double)ts);
-      atomicAdd(dst + 1, (double)tq);
+      // 64-bit fixed point (2^-32 units, the format of uvit.cu's statistics kernel): integer atomics are associative, so
+      // the order in which the chunks of an image arrive cannot change the statistics; `ts` / `tq` themselves are fp32
+      // sums over a fixed pattern (32 rows x the group's columns of one chunk) that no tile shape or batch size alters
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(base) + ((col0 + g * CPL) / cpg) * 2;
+      atomicAdd(dst, (unsigned long long)__float2ll_rn(ts * 4294967296.f));
+      atomicAdd(dst + 1, (unsigned long long)__float2ll_rn(tq * 4294967296.f));
     }
   }
 }

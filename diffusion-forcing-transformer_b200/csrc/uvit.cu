@@ -38,53 +38,74 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
 }
 
 // ------------------------------------------------------------------ GroupNorm statistics
-// grid (slabs, n_img); a thread owns one 8-channel vector (fixed) and walks the slab's pixels.
-template <typename TX>
+// DETERMINISTIC and BATCH-INVARIANT: (sum, sum of squares) are accumulated as 64-bit FIXED-POINT integers (2^-32 units).
+// Integer addition is associative, so neither the order in which warps / blocks reach their atomics nor the way the
+// pixels are split over blocks (which depends on the number of images in the launch) can change a single bit; the only
+// floating-point sums are fp32 "micro-partials" over one thread's 8 channels x kGnMicro pixels of a globally aligned
+// pixel chunk, whose composition depends on (HW, C) alone.  Two forwards of the same image — alone, inside a batch, on
+// another rank — therefore see identical statistics (the r01 version used fp32 shared-memory atomics and agreed to ~1e-6).
+constexpr int kGnMicro = 8;                               // pixels per fp32 micro-partial
+constexpr float kGnFix = 4294967296.f;                    // 2^32: |partial| < 2^31 is ample for activations
+__device__ __forceinline__ unsigned long long gn_fix(float v) { return (unsigned long long)__float2ll_rn(v * kGnFix); }
+
+// grid (slabs, n_img); a thread owns one 8-channel vector (fixed) and walks the slab's pixels; GPV = groups per vector.
+template <typename TX, int GPV>
 __global__ void __launch_bounds__(kThreads)
 gn_stats_kernel(const TX* __restrict__ x, double* __restrict__ sums, int64_t HW, int64_t img_stride, int C, int G,
                 int pix_per_block) {
   pdl_trigger();   // programmatic dependent launch: see common.cuh
   pdl_wait();
-  __shared__ float s_sum[64], s_sq[64];
+  __shared__ unsigned long long s_sum[64], s_sq[64];
   const int vecs = C >> 3, cpg = C / G;
   const int img = blockIdx.y;
-  if (threadIdx.x < 64) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+  if (threadIdx.x < 64) { s_sum[threadIdx.x] = 0ull; s_sq[threadIdx.x] = 0ull; }
   __syncthreads();
   const int v = threadIdx.x % vecs, lane_pix = threadIdx.x / vecs, pix_step = kThreads / vecs;
-  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
+  constexpr int CPV = 8 / GPV;                            // channels of one group inside the vector
+  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;  // multiple of kGnMicro * pix_step (host): chunks are aligned
   const int64_t p1 = min(HW, p0 + pix_per_block);
-  float s[8], q[8];
+  unsigned long long as[GPV], aq[GPV];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  for (int g = 0; g < GPV; ++g) { as[g] = 0ull; aq[g] = 0ull; }
   if (lane_pix < pix_step) {
-    for (int64_t pix = p0 + lane_pix; pix < p1; pix += pix_step) {
-      float a[8];
-      load8(x + (int64_t)img * img_stride + pix * C + 8 * v, a);
+    for (int64_t base = p0 + lane_pix; base < p1; base += (int64_t)kGnMicro * pix_step) {
+      float a[kGnMicro][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s[j] += a[j]; q[j] = fmaf(a[j], a[j], q[j]); }
+      for (int k = 0; k < kGnMicro; ++k) {                // all loads of the micro-partial in flight
+        const int64_t pix = base + (int64_t)k * pix_step;
+        if (pix < p1) load8(x + (int64_t)img * img_stride + pix * C + 8 * v, a[k]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[k][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < GPV; ++g) {
+        float ts = 0.f, tq = 0.f;
+#pragma unroll
+        for (int k = 0; k < kGnMicro; ++k)
+#pragma unroll
+          for (int j = 0; j < CPV; ++j) { const float e = a[k][g * CPV + j]; ts += e; tq = fmaf(e, e, tq); }
+        as[g] += gn_fix(ts);
+        aq[g] += gn_fix(tq);
+      }
     }
   }
-  if (cpg % 8 == 0) {   // the whole vector lies in one group
-    float ts = 0.f, tq = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { ts += s[j]; tq += q[j]; }
-    atomicAdd(&s_sum[(8 * v) / cpg], ts);
-    atomicAdd(&s_sq[(8 * v) / cpg], tq);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&s_sum[(8 * v + j) / cpg], s[j]);
-      atomicAdd(&s_sq[(8 * v + j) / cpg], q[j]);
-    }
+  for (int g = 0; g < GPV; ++g) {
+    const int grp = (8 * v + g * CPV) / cpg;
+    atomicAdd(&s_sum[grp], as[g]);
+    atomicAdd(&s_sq[grp], aq[g]);
   }
   __syncthreads();
   if (threadIdx.x < G) {
-    atomicAdd(&sums[((int64_t)img * G + threadIdx.x) * 2], (double)s_sum[threadIdx.x]);
-    atomicAdd(&sums[((int64_t)img * G + threadIdx.x) * 2 + 1], (double)s_sq[threadIdx.x]);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(sums) + ((int64_t)img * G + threadIdx.x) * 2;
+    atomicAdd(dst, s_sum[threadIdx.x]);
+    atomicAdd(dst + 1, s_sq[threadIdx.x]);
   }
 }
 
-// (sum, sum of squares) in f64 → (mean, rstd) in f32, once per (image, group): keeps every f64 operation out of the
+// fixed-point (sum, sum of squares) → (mean, rstd) in f32, once per (image, group): keeps every f64 operation out of the
 // per-element kernel
 __global__ void gn_finalize_kernel(const double* __restrict__ sums, float2* __restrict__ stats, int64_t n, double inv_n,
                                    float eps) {
@@ -92,8 +113,10 @@ __global__ void gn_finalize_kernel(const double* __restrict__ sums, float2* __re
   pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const double m = sums[2 * i] * inv_n;
-  const double var = fmax(sums[2 * i + 1] * inv_n - m * m, 0.0);
+  const long long* fx = reinterpret_cast<const long long*>(sums);
+  constexpr double kUnit = 1.0 / 4294967296.0;
+  const double m = (double)fx[2 * i] * kUnit * inv_n;
+  const double var = fmax((double)fx[2 * i + 1] * kUnit * inv_n - m * m, 0.0);
   stats[i] = make_float2((float)m, rsqrtf((float)var + eps));
 }
 
@@ -472,19 +495,32 @@ extern "C" int dfot_groupnorm_stats_strided(const void* x, int x_dtype, double* 
                "groupnorm_stats: C/8 = %d must divide %d", vecs, kThreads);
   cudaStream_t s = (cudaStream_t)stream;
   if (int rc = gn_zero_sums(sums, n_img, groups, s)) return rc;
-  // ~8 resident blocks per SM over the whole batch, at least 8 pixels per thread-row
+  // ~8 resident blocks per SM over the whole batch; a block's pixel range is a whole number of aligned micro-partial
+  // chunks (kGnMicro pixels per thread-row), so the fp32 micro-partials do not depend on how many blocks share an image
   const int pix_rows = kThreads / vecs;
+  const int64_t chunk = (int64_t)kGnMicro * pix_rows;
   int64_t slabs = ceil_div(148 * 8, n_img);
-  int64_t ppb = ceil_div(HW, slabs);
-  if (ppb < 8 * pix_rows) ppb = 8 * pix_rows;
+  int64_t ppb = ceil_div(ceil_div(HW, slabs), chunk) * chunk;
   slabs = ceil_div(HW, ppb);
   dim3 grid((unsigned)slabs, (unsigned)n_img);
-  if (x_dtype == DFOT_F32)
-    launch_pdl(gn_stats_kernel<float>, dim3(grid), dim3(kThreads), 0, s, (const float*)x, sums, HW, img_stride, (int)C, (int)groups, (int)ppb);
-  else if (x_dtype == DFOT_BF16)
-    launch_pdl(gn_stats_kernel<__nv_bfloat16>, dim3(grid), dim3(kThreads), 0, s, (const __nv_bfloat16*)x, sums, HW, img_stride, (int)C, (int)groups, (int)ppb);
+  const int64_t cpg = C / groups;
+  const int gpv = cpg >= 8 ? 1 : (int)(8 / cpg);
+  DFOT_REQUIRE(cpg >= 8 ? cpg % 8 == 0 : 8 % cpg == 0, DFOT_ERR_UNSUPPORTED,
+               "groupnorm_stats: channels per group (%lld) must divide 8 or be a multiple of 8", (long long)cpg);
+#define DFOT_GN_STATS(T, GPV)                                                                                     \
+  launch_pdl(gn_stats_kernel<T, GPV>, dim3(grid), dim3(kThreads), 0, s, (const T*)x, sums, HW, img_stride, (int)C, \
+             (int)groups, (int)ppb)
+#define DFOT_GN_STATS_T(T)                                                                                        \
+  do {                                                                                                            \
+    if (gpv == 1) DFOT_GN_STATS(T, 1); else if (gpv == 2) DFOT_GN_STATS(T, 2);                                    \
+    else if (gpv == 4) DFOT_GN_STATS(T, 4); else DFOT_GN_STATS(T, 8);                                             \
+  } while (0)
+  if (x_dtype == DFOT_F32) DFOT_GN_STATS_T(float);
+  else if (x_dtype == DFOT_BF16) DFOT_GN_STATS_T(__nv_bfloat16);
   else
     DFOT_REQUIRE(false, DFOT_ERR_INVALID_ARG, "groupnorm_stats: x dtype must be f32 or bf16");
+#undef DFOT_GN_STATS_T
+#undef DFOT_GN_STATS
   DFOT_CHECK_LAUNCH("groupnorm_stats");
   // (mean, rstd) as f32 pairs, stored behind the f64 sums in the same buffer
   return gn_finalize(sums, n_img, groups, HW * (C / groups), eps, s);

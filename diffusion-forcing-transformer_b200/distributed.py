@@ -104,6 +104,8 @@ class RowShard:
 
     def gather(self, local: Optional[torch.Tensor], n: int, row_shape, dtype, device) -> torch.Tensor:
         """local: [stop - start, *row_shape] outputs of this rank's rows (None when it has none) -> [n, *row_shape]."""
+        if self.world == 1:
+            return local
         per, start, stop = self.block(n)
         key = (n, tuple(row_shape), dtype, str(device))
         buf = self._bufs.get(key)

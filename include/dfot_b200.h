@@ -231,8 +231,10 @@ DFOT_API int dfot_cast_bf16(const float* in, void* out_bf16, int64_t n, void* st
  * the row's pose embedding is masked out, embeddings.py:336-361).
  */
 /* GroupNorm statistics (u_vit_blocks.py:52-53: 32 groups): sums[img, g] = (sum, sum of squares) over H*W x C/G,
-   accumulated in f64, then finalised to f32 (mean, rstd) pairs stored right behind the sums: the workspace `sums` must
-   hold 3*n_img*groups doubles.  The buffer is zeroed by the call (cudaMemsetAsync on the stream). x f32 or bf16. */
+   accumulated as 64-bit FIXED-POINT integers (2^-32 units; integer atomics are associative, so the statistics are
+   deterministic and do not depend on how many images share a launch), then finalised to f32 (mean, rstd) pairs stored
+   right behind the sums: the workspace `sums` must hold 3*n_img*groups 8-byte words (declared double for alignment).
+   The buffer is zeroed by the call (cudaMemsetAsync on the stream). x f32 or bf16; C/groups divides 8 or is a multiple. */
 DFOT_API int dfot_groupnorm_stats(const void* x, int x_dtype, double* sums, int64_t n_img, int64_t HW, int64_t C,
                          int64_t groups, float eps, void* stream);
 /* y = silu( GN(x) * gamma + beta [ * (1 + scale) + shift ] ) -> bf16 (the conv operand).  mod_img/mod_pix NULL: no FiLM */

@@ -309,3 +309,72 @@ def test_cfg4_shaped_long_rollout_uvit_vs_oracle():
     conds = synthetic_poses(1, 25)
     steps = _rollout_vs_oracle(cfg, algo, xs, conds, 1)
     assert steps > 10      # several windows x 2 steps
+
+
+# ------------------------------------------------------------------ batch invariance / lockstep rounds (multi-GPU contract)
+def test_uvit_forward_rows_do_not_depend_on_the_batch():
+    """A forward-row's output is bit-identical whether the row is forwarded alone or inside a batch: GEMM / conv tiles,
+    attention items and the fixed-point GroupNorm statistics never mix rows.  This is what lets the multi-GPU path deal
+    rows over ranks (RowShard) and still reproduce the single-GPU rollout exactly."""
+    from oracle.cases import synthetic_poses
+    cfg = uvit_cfg((64, 128, 128, 256), 2, 64, 3)
+    algo = random_pose_algo(cfg, 5).to(DEV).eval()
+    model = algo.diffusion_model.model
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn((4, 3, 3, 64, 64), generator=g).to(DEV)
+    levels = torch.randn((4, 3), generator=g).to(DEV)
+    cond = algo._window_conditions(synthetic_poses(2, 3).to(DEV), 2)
+    mask = torch.tensor([True, False, True, False], device=DEV)
+    full = model(x, levels, cond, mask).clone()
+    again = model(x, levels, cond, mask).clone()        # second call = CUDA-graph capture / replay of the same signature
+    assert torch.equal(full, again)
+    for i in range(4):
+        rows = torch.tensor([i])
+        one = model(x[i:i + 1].contiguous(), levels[i:i + 1].contiguous(), cond.index_select(0, rows), mask[i:i + 1])
+        assert torch.equal(one[0], full[i]), f"row {i}: max diff {(one[0] - full[i]).abs().max().item()}"
+
+
+def test_dit_forward_rows_do_not_depend_on_the_batch():
+    cfg = tiny_cfg1()
+    algo = random_weights(cfg, 2).to(DEV).eval()
+    model = algo.diffusion_model.model
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn((4, 8, 4, 16, 16), generator=g).to(DEV)
+    k = torch.randint(0, 1000, (4, 8), generator=g).to(DEV)
+    full = model(x, k).clone()
+    for i in range(4):
+        one = model(x[i:i + 1].contiguous(), k[i:i + 1].contiguous())
+        assert torch.equal(one[0], full[i]), f"row {i}: max diff {(one[0] - full[i]).abs().max().item()}"
+
+
+def test_lockstep_rounds_reproduce_the_sequential_rollout_on_gpu():
+    """BASELINE configs[3] structure (keyframe windows + interpolation rounds): with a row shard the chunk batches of a
+    round advance in lockstep, every batch drawing from its own position of torch's CUDA generator stream.  On one GPU
+    (a world of 1) that must give the sequential rollout bit for bit and leave the generator where the sequential run
+    leaves it."""
+    from dfot_b200 import distributed as D
+    from oracle.cases import synthetic_poses
+    cfg = uvit_cfg((32, 32, 64, 128), 1, 32, 4, **{
+        "n_frames": 25, "tasks.prediction.keyframe_density": 0.28, "tasks.prediction.sliding_context_len": 1,
+        "diffusion.sampling_timesteps": 3,
+        "tasks.prediction.history_guidance": dict(name="stabilized_vanilla", guidance_scale=2.0,
+                                                  stabilization_level=0.02, visualize=False),
+        "tasks.interpolation.history_guidance": dict(name="vanilla", guidance_scale=1.5, visualize=False),
+        "tasks.interpolation.max_batch_size": 2})
+    algo = random_pose_algo(cfg, 6).to(DEV).eval()
+    g = torch.Generator().manual_seed(8)
+    xs = torch.randn((1, 25, 3, 32, 32), generator=g).to(DEV)
+    conds = synthetic_poses(1, 25).to(DEV)
+    torch.manual_seed(11)
+    seq = algo._predict_videos(xs, 1, conds).clone()
+    state_seq = torch.cuda.get_rng_state()
+    rows_seq = algo.nfe_rows
+    torch.manual_seed(11)
+    algo.row_shard = D.RowShard(world=1, rank=0)
+    try:
+        lock = algo._predict_videos(xs, 1, conds).clone()
+    finally:
+        algo.row_shard = None
+    assert torch.equal(torch.cuda.get_rng_state(), state_seq)
+    assert algo.nfe_rows == 2 * rows_seq
+    assert torch.equal(lock, seq), f"max diff {(lock - seq).abs().max().item()}"

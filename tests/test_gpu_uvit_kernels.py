@@ -85,6 +85,49 @@ def test_conv3d_causal_implicit_gemm(B, T, H, W, Cin, Cout, kt):
     assert (out2 - out - resid).abs().max().item() <= 1e-5 * max(1.0, out.abs().max().item())
 
 
+def fixed_point_sums(ws, k):
+    """(sum, sum of squares) of a GroupNorm workspace: 64-bit fixed point in 2^-32 units (csrc/uvit.cu)."""
+    return ws.reshape(-1)[:k].view(torch.int64).double() / 2.0 ** 32
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_groupnorm_statistics_are_deterministic_and_batch_invariant(dt):
+    """Fixed-point accumulation: the statistics of an image do not depend on the run, on how many images share the launch
+    (which changes the pixel split over blocks) or on the path that produced them twice (stand-alone pass)."""
+    n, HW, C = 6, 4096, 128
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn((n, HW, C), generator=g) * 3 + 0.3).to(DEV).to(dt)
+    full = torch.empty((n, 32, 3), dtype=torch.float64, device=DEV)
+    ops.groupnorm_stats(x, full, n, HW, C)
+    again = torch.empty_like(full)
+    for _ in range(3):
+        ops.groupnorm_stats(x, again, n, HW, C)
+        assert torch.equal(full.view(torch.int64), again.view(torch.int64))
+    for i in (0, 3, 5):                       # one image alone: other grid, other slab size — same bits
+        one = torch.empty((1, 32, 3), dtype=torch.float64, device=DEV)
+        ops.groupnorm_stats(x[i:i + 1].contiguous(), one, 1, HW, C)
+        assert torch.equal(fixed_point_sums(one, 64), fixed_point_sums(full, n * 64)[i * 64:(i + 1) * 64])
+
+
+def test_conv_groupnorm_side_output_is_batch_invariant():
+    """The statistics riding on the conv epilogue: image i inside a batch of 5 == image i convolved alone, bit for bit,
+    and so is the convolution output itself (what makes a forward independent of the rows it is batched with)."""
+    n, H, C = 5, 32, 128
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn((n, H, H, C), generator=g).to(DEV).to(torch.bfloat16)
+    w = (torch.randn((C, 3, 3, C), generator=g) / math.sqrt(9 * C)).to(DEV).to(torch.bfloat16)
+    bias = torch.randn((C,), generator=g).to(DEV)
+    side = torch.empty((n, 32, 3), dtype=torch.float64, device=DEV)
+    out = torch.empty((n * H * H, C), dtype=torch.bfloat16, device=DEV)
+    ops.conv3x3_bf16(x, w, out, ops.EPI_BF16, bias=bias, gn_sums=side)
+    for i in (0, 2, 4):
+        s1 = torch.empty((1, 32, 3), dtype=torch.float64, device=DEV)
+        o1 = torch.empty((H * H, C), dtype=torch.bfloat16, device=DEV)
+        ops.conv3x3_bf16(x[i:i + 1].contiguous(), w, o1, ops.EPI_BF16, bias=bias, gn_sums=s1)
+        assert torch.equal(o1, out[i * H * H:(i + 1) * H * H])
+        assert torch.equal(fixed_point_sums(s1, 64), fixed_point_sums(side, n * 64)[i * 64:(i + 1) * 64])
+
+
 @pytest.mark.parametrize("n,H,C,epi", [(4, 64, 128, "bf16"), (4, 64, 128, "resid"), (3, 32, 256, "bf16"), (3, 32, 256, "f32"),
                                        (4, 16, 32, "bf16"), (4, 16, 32, "resid"), (6, 8, 64, "bf16"), (2, 16, 1024, "f32")])
 def test_conv_groupnorm_side_output(n, H, C, epi):
@@ -105,7 +148,7 @@ def test_conv_groupnorm_side_output(n, H, C, epi):
                          gn_sums=side)
     ops.groupnorm_stats(out, alone, n, H * H, C)
     k = n * 32 * 2
-    a, b = side.reshape(-1)[:k], alone.reshape(-1)[:k]
+    a, b = fixed_point_sums(side, k), fixed_point_sums(alone, k)
     assert torch.allclose(a, b, rtol=1e-4, atol=1e-2), (a - b).abs().max()
     fa = side.reshape(-1)[k:].view(torch.float32).reshape(n, 32, 2)
     fb = alone.reshape(-1)[k:].view(torch.float32).reshape(n, 32, 2)
@@ -138,7 +181,7 @@ def test_groupnorm_stats_and_apply(n, HW, C, dt):
     sums = torch.empty((n, 32, 3), dtype=torch.float64, device=DEV)
     ops.groupnorm_stats(x, sums, n, HW, C)
     xg = x.double().reshape(n, HW, 32, C // 32)
-    acc = sums.reshape(-1)[: n * 32 * 2].reshape(n, 32, 2)
+    acc = fixed_point_sums(sums, n * 32 * 2).reshape(n, 32, 2)
     assert torch.allclose(acc[..., 0], xg.sum((1, 3)), rtol=1e-5, atol=1e-2)
     assert torch.allclose(acc[..., 1], (xg * xg).sum((1, 3)), rtol=1e-5, atol=1e-2)
     x_nchw = x.float().permute(0, 2, 1).reshape(n, C, HW, 1)
