@@ -75,7 +75,7 @@ def dmlab_cfg(sampling_timesteps=50, frames=36, guidance_scale=None):
                context_frames=4, data_mean=[[[0.0]]] * 32, data_std=[[[3.46140533056]]] * 32,
                latent=dict(enabled=True, type="pre_sample", suffix=None, downsampling_factor=[1, 8], shape=None,
                            num_channels=32))
-    cfg["backbone"].update(patch_size=2, external_cond_dropout=0.1)
+    cfg["backbone"].update(patch_size=2, external_cond_dropout=0.1, use_fourier_noise_embedding=True)
     cfg["diffusion"].update(is_continuous=True, precond_scale=0.125, beta_schedule="cosine_simple_diffusion",
                             schedule_fn_kwargs=dict(shifted=0.125, interpolated=False),
                             training_schedule=dict(name="cosine", shift=0.125),
@@ -143,7 +143,7 @@ class Workload:
         elif name == "re10k_long":
             # README.md:69 "Single Image to Long Video (200 Frames)" = BASELINE config[3]
             self.cfg = re10k_cfg(args.sampling_steps)
-            self.cfg.update(n_frames=200)
+            self.cfg.update(n_frames=200, frame_skip=1)
             self.cfg["tasks"]["prediction"].update(
                 history_guidance=dict(name="stabilized_vanilla", guidance_scale=4.0, stabilization_level=0.02,
                                       visualize=False), keyframe_density=0.0625)

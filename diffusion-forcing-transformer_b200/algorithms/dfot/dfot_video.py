@@ -493,19 +493,21 @@ class DFoTVideo(BaseVideoAlgo):
             return None
         if torch.is_tensor(conds[0]):
             return torch.cat([c[lo:hi] for _, c, lo, hi in pieces], 0)
-        key = tuple((id(r), lo, hi) for r, _, lo, hi in pieces)
-        hit = self._row_cond_cache.get(key)
-        if hit is None:
-            from .backbones.u_vit.u_vit3d_pose import PoseCondition
-            cams, row_map = [], []
-            for _, c, lo, hi in pieces:
-                used = sorted(set(c.row_map[lo:hi]))
-                base = sum(x.shape[0] for x in cams)
-                cams.append(c.cams[used])
-                row_map += [base + used.index(j) for j in c.row_map[lo:hi]]
-            hit = PoseCondition(torch.cat(cams, 0), row_map)
-            self._row_cond_cache = {key: hit}          # one live entry: the previous round's cache can go
-        return hit
+        # the cache entry HOLDS the handles it was built from (identity comparison; ids of dead objects get re-used)
+        held = self._row_cond_cache.get("pieces")
+        if held is not None and len(held) == len(pieces) and all(
+                h[0] is c and h[1:] == (lo, hi) for h, (_, c, lo, hi) in zip(held, pieces)):
+            return self._row_cond_cache["merged"]
+        from .backbones.u_vit.u_vit3d_pose import PoseCondition
+        cams, row_map = [], []
+        for _, c, lo, hi in pieces:
+            used = sorted(set(c.row_map[lo:hi]))
+            base = sum(x.shape[0] for x in cams)
+            cams.append(c.cams[used])
+            row_map += [base + used.index(j) for j in c.row_map[lo:hi]]
+        merged = PoseCondition(torch.cat(cams, 0), row_map)
+        self._row_cond_cache = {"pieces": [(c, lo, hi) for _, c, lo, hi in pieces], "merged": merged}
+        return merged
 
     @torch.no_grad()
     def _run_lockstep(self, makers: List[Callable]) -> List[Tuple[Tensor, Optional[Tensor]]]:

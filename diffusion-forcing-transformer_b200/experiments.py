@@ -6,10 +6,16 @@ by samples over the `dp x br` mesh of `dfot_b200.distributed` (the reference rep
 Accelerate split the loader; here the split is explicit and the only collective is the final gather of each batch).
 Metrics, logging and data modules are outside the scope of this package: batches are plain dicts.
 
-CLI (single GPU, or under torchrun for several):
+CLI (single GPU, or under torchrun for several) — either the reference's own command line, composed against the user's
+checkout of its `configurations/` tree (dfot_b200/hydra_compose.py; `load=<path>` names the checkpoint):
+    python -m dfot_b200.experiments --config-dir /path/to/diffusion-forcing-transformer/configurations \
+        --input batch.npz --output videos.npz -- dataset=realestate10k_mini algorithm=dfot_video_pose \
+        experiment=video_generation @diffusion/continuous load=DFoT_RE10K.ckpt 'experiment.tasks=[validation]' \
+        dataset.context_length=1 dataset.n_frames=8 algorithm.tasks.prediction.history_guidance.name=vanilla \
+        +algorithm.tasks.prediction.history_guidance.guidance_scale=4.0
+or an already resolved `algorithm` tree:
     python -m dfot_b200.experiments --config algo.json --ckpt model.ckpt --input batch.npz --output videos.npz [--br 2]
-where `algo.json|yaml` is the resolved `algorithm` tree (what Hydra hands to `DFoTVideo.__init__`) and `batch.npz`
-holds `videos` (or `latents`) [B, T, C, H, W] in [0, 1] and optionally `conds` [B, T, d].
+`batch.npz` holds `videos` (or `latents`) [B, T, C, H, W] in [0, 1] and optionally `conds` [B, T, d].
 """
 import argparse
 import json
@@ -101,12 +107,34 @@ def _load_tree(path: str):
         return json.load(f)
 
 
+def resolve_cli_config(args):
+    """(algorithm tree, checkpoint path) from either `--config` or `--config-dir -- <reference command line>`."""
+    if (args.config is None) == (args.config_dir is None):
+        raise SystemExit("give exactly one of --config (a resolved algorithm tree) and --config-dir (the reference's tree)")
+    if args.config is not None:
+        return _load_tree(args.config), args.ckpt
+    from dfot_b200.hydra_compose import compose
+    cfg = compose(args.config_dir, list(args.overrides))
+    tasks = cfg.get("experiment", {}).get("tasks", [])
+    if tasks and "validation" not in tasks and "test" not in tasks:
+        raise SystemExit(f"experiment.tasks={tasks}: only the sampling tasks (validation / test) are implemented here")
+    load = args.ckpt or cfg.get("load")
+    if isinstance(load, str) and load.startswith("pretrained:"):
+        raise SystemExit(f"load={load}: the reference downloads this from the Hugging Face hub; there is no network here — "
+                         "download it yourself and pass the file (load=/path/to/file.ckpt or --ckpt)")
+    return cfg["algorithm"], load
+
+
 def main(argv=None):
     import numpy as np
     import torch.distributed as dist
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
-    ap.add_argument("--config", required=True, help="resolved `algorithm` config tree (json / yaml)")
-    ap.add_argument("--ckpt", default=None, help="reference checkpoint (.ckpt / .safetensors)")
+    ap.add_argument("--config", default=None, help="resolved `algorithm` config tree (json / yaml)")
+    ap.add_argument("--config-dir", default=None,
+                    help="the reference's `configurations/` directory: the arguments after `--` are the reference's own "
+                         "command line (group choices, overrides, @shortcuts) and are composed against it")
+    ap.add_argument("overrides", nargs="*", help="with --config-dir: the reference's `python -m main` arguments")
+    ap.add_argument("--ckpt", default=None, help="reference checkpoint (.ckpt / .safetensors); default: `load=` of the command line")
     ap.add_argument("--input", required=True, help=".npz with videos|latents [B,T,C,H,W] and optional conds [B,T,d]")
     ap.add_argument("--output", required=True)
     ap.add_argument("--br", type=int, default=1, help="branch-group size (splits history-guidance branches over GPUs)")
@@ -118,7 +146,7 @@ def main(argv=None):
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    exp = SamplingExperiment(_load_tree(args.config), args.ckpt, dev, args.br, args.seed)
+    exp = SamplingExperiment(*resolve_cli_config(args), dev, args.br, args.seed)
     data = np.load(args.input)
     batch = {k: torch.from_numpy(data[k]) for k in data.files}
     videos = exp.run_validation([batch])[0]

@@ -210,7 +210,9 @@ class _Composer:
                     key = key[len("optional "):].strip() if opt else key
                     rel, _, pkg = key.partition("@")
                     sub_group = self._norm(group, rel)
-                    choice = self._choice(sub_group, choice, overrides)
+                    # Hydra keys a default with an explicit package as `group@package`: a plain `group=choice` on the
+                    # command line (or an `override group:`) does not touch it
+                    choice = self._choice(f"{sub_group}@{pkg}" if pkg else sub_group, choice, overrides)
                     if not pkg:
                         self.choices[sub_group] = choice
                     if choice is None:

@@ -1,6 +1,7 @@
 """Sampling driver: config → algorithm → checkpoint → batches → videos, on CPU with the kernel
 contract emulations (the CUDA path is covered by the -m gpu tests)."""
 import numpy as np
+import pytest
 import torch
 
 import k4_emulation
@@ -62,3 +63,28 @@ def test_driver_decodes_latents_with_the_configured_vae(monkeypatch, tmp_path):
     gt = torch.rand((3, 9, 3, 32, 32))
     out = exp.run_validation([{"latents": latents, "videos": gt}])[0]
     assert torch.equal(out["gt"], gt)
+
+
+def test_cli_resolves_the_reference_command_line(tmp_path):
+    """`--config-dir <configurations> -- <python -m main arguments>`: composed like the reference's Hydra entry point."""
+    import argparse
+    import os
+    from dfot_b200.experiments import resolve_cli_config
+    root = str(tmp_path)
+    os.makedirs(os.path.join(root, "algorithm"))
+    for rel, text in {"config.yaml": "defaults:\n  - experiment: gen\n  - dataset: d\n  - algorithm: a\nload: null\n",
+                      "experiment/gen.yaml": "tasks: [training]\n", "dataset/d.yaml": "n_frames: 8\n",
+                      "algorithm/a.yaml": "n_frames: ${dataset.n_frames}\nname: toy\n"}.items():
+        os.makedirs(os.path.dirname(os.path.join(root, rel)), exist_ok=True)
+        with open(os.path.join(root, rel), "w") as f:
+            f.write(text)
+    ns = argparse.Namespace(config=None, config_dir=root, ckpt=None,
+                            overrides=["experiment.tasks=[validation]", "dataset.n_frames=200", "load=/w/model.ckpt"])
+    tree, ckpt = resolve_cli_config(ns)
+    assert tree == {"n_frames": 200, "name": "toy", "_name": "a"} and ckpt == "/w/model.ckpt"
+    ns.overrides = ["load=pretrained:DFoT_RE10K.ckpt", "experiment.tasks=[validation]"]
+    with pytest.raises(SystemExit, match="no network"):
+        resolve_cli_config(ns)
+    ns.overrides = []
+    with pytest.raises(SystemExit, match="sampling tasks"):
+        resolve_cli_config(ns)
