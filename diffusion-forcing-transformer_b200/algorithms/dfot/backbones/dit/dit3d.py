@@ -398,10 +398,14 @@ class DiT3D(nn.Module):
             st["cond"] = None if external_cond is None else torch.empty_like(external_cond, dtype=torch.float32)
             st["mask"] = torch.empty_like(external_cond_mask) if use_mask else None
         st["levels"].copy_(levels)
-        if st["cond"] is not None:
-            st["cond"].copy_(external_cond)
-        if st["mask"] is not None:
-            st["mask"].copy_(external_cond_mask)
+        # conditions / masks are constant over the steps of a window: refresh the graph's static copies only when the source
+        # tensor (or its contents: _version) changed
+        for name, src in (("cond", external_cond), ("mask", external_cond_mask)):
+            if st[name] is not None:
+                key = (src.data_ptr(), src._version, tuple(src.shape))
+                if st.get(name + "_key") != key:
+                    st[name].copy_(src)
+                    st[name + "_key"] = key
         if st["graph"] is None:
             g = torch.cuda.CUDAGraph()
             n0 = _abi.launch_count()

@@ -185,6 +185,7 @@ class UViT3DPose(nn.Module):
         self._pose_state = {}
         self.use_cuda_graph = True
         self._graphs = {}
+        self._img_base = {}
 
     @property
     def n_tokens_per_frame(self) -> int:
@@ -398,13 +399,19 @@ class UViT3DPose(nn.Module):
         dev = x.device
         if isinstance(external_cond, PoseCondition):
             st = self.prepare_pose(external_cond)
-            row_map = torch.tensor(external_cond.row_map, dtype=torch.int32)
+            row_map = external_cond.row_map
         else:
             st = self._prepare_dense(external_cond)
-            row_map = torch.arange(R, dtype=torch.int32)
+            row_map = list(range(R))
         if len(row_map) != R:
             raise ValueError(f"conditioning covers {len(row_map)} rows, x has {R}")
-        base = (row_map[:, None] * T + torch.arange(T, dtype=torch.int32)[None, :]).to(dev, non_blocking=True)
+        # image -> row of the pose cache (constant over the steps of a window: built and uploaded once per row map)
+        map_key = (tuple(row_map), T, str(dev))
+        if self._img_base.get("key") != map_key:
+            rm = torch.tensor(row_map, dtype=torch.int32)
+            self._img_base = {"key": map_key,
+                              "base": (rm[:, None] * T + torch.arange(T, dtype=torch.int32)[None, :]).to(dev)}
+        base = self._img_base["base"]
         levels = noise_levels if noise_levels.dtype in (torch.int64, torch.float32) else noise_levels.float()
         graph_ok = self.use_cuda_graph and x.is_cuda and isinstance(external_cond, PoseCondition) and \
             not torch.cuda.is_current_stream_capturing()

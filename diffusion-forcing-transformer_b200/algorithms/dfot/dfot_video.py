@@ -587,7 +587,10 @@ class _WindowRun:
         self.noise_state = None
 
         # ---- RNG (1): initial noise (:607-612)
-        if dm.noise_source is None and algo.generator is not None:
+        if dry and not (dm.noise_source is None and algo.generator is not None):
+            dm.skip_randn((B, horizon, *x_shape), dev)      # a dry run wants the stream position, not the values
+            x = torch.zeros((B, horizon, *x_shape), device=dev)
+        elif dm.noise_source is None and algo.generator is not None:
             x = torch.randn((B, horizon, *x_shape), device=dev, generator=algo.generator)
         else:
             x = dm.randn((B, horizon, *x_shape), dev)
@@ -628,6 +631,12 @@ class _WindowRun:
     def _draw_prepare_noise(self, p: sp.StepPlan):
         # RNG (2): q_sample noise, then (full manager only) the excluded-token noise — always drawn
         shape = (self.T, *self.algo.x_shape)
+        if self.dry:
+            if p.n_hist_rows:
+                self.dm.skip_randn((p.n_hist_rows, *shape), self.dev)
+            if p.draws_excluded_noise:
+                self.dm.skip_randn((self.B * p.nfe, *shape), self.dev)
+            return None, None
         nh = self.dm.clipped_noise((p.n_hist_rows, *shape), self.dev) if p.n_hist_rows else None
         ne = self.dm.randn((self.B * p.nfe, *shape), self.dev) if p.draws_excluded_noise else None
         return nh, ne
@@ -657,8 +666,11 @@ class _WindowRun:
         if self.return_all:
             self.record.append(self.x.clone())
         # RNG (3): the step's noise (DDIM sigma / DDPM) — drawn even when eta == 0, to stay aligned with the reference
-        nd = dm.clipped_noise((B * p.nfe, T, *algo.x_shape), self.dev)
-        nd = nd if dm.host_tables.uses_step_noise else None
+        nd = None
+        if dm.host_tables.uses_step_noise and not self.dry:
+            nd = dm.clipped_noise((B * p.nfe, T, *algo.x_shape), self.dev)
+        else:               # sigma == 0 everywhere (or a dry run): advance the stream, skip the values
+            dm.skip_randn((B * p.nfe, T, *algo.x_shape), self.dev)
         tracing = algo.trace is not None and not self.dry
         trace_in = self.model_in.float().clone() if tracing else None
         nxt = self.plans[m + 1] if m + 1 < self.n_steps else None

@@ -48,6 +48,7 @@ class DiscreteDiffusion(nn.Module):
         self.use_causal_mask = cfg.use_causal_mask
         self.noise_source: Optional[Callable] = None   # test hook: callable(shape, device) -> standard normal tensor
         self.generator: Optional[torch.Generator] = None   # per-shard noise stream (DFoTVideo.sample_sharded); None = global
+        self._skip_increment = {}
         self._build_model()
         self._build_buffer()
 
@@ -117,6 +118,24 @@ class DiscreteDiffusion(nn.Module):
 
     def clipped_noise(self, shape, device) -> torch.Tensor:
         return torch.clamp(self.randn(shape, device), -self.clip_noise, self.clip_noise)
+
+    def skip_randn(self, shape, device) -> None:
+        """Advance the noise stream exactly as `randn(shape, device)` would, without producing the values.  The reference
+        draws the per-step update noise even when it is multiplied by sigma = 0 (DDIM, eta = 0: discrete_diffusion.py:525),
+        and the lockstep rounds replay whole windows only to find stream positions; both want the position, not the numbers.
+        CUDA generators are counter based: the Philox offset a draw of a given size consumes is measured once and re-applied."""
+        if self.noise_source is not None or torch.device(device).type != "cuda":
+            self.randn(shape, device)
+            return
+        g = self._torch_generator(device)
+        key = (int(np.prod(shape)), str(device))
+        inc = self._skip_increment.get(key)
+        if inc is None:
+            before = g.get_offset()
+            torch.randn(tuple(shape), device=device, generator=self.generator)
+            self._skip_increment[key] = g.get_offset() - before
+        else:
+            g.set_offset(g.get_offset() + inc)
 
     def _torch_generator(self, device) -> torch.Generator:
         if self.generator is not None:

@@ -69,6 +69,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and is_current():
         return LIB
     os.makedirs(OBJ, exist_ok=True)
+    # one builder at a time: the ranks of a torchrun launch all load the library at once, and every one of them would
+    # otherwise rebuild a stale library into the same files
+    import fcntl
+    with open(os.path.join(OBJ, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():       # another process finished the build while this one waited
+                return LIB
+            return _build_locked(srcs, headers, force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(srcs, headers, force: bool, verbose: bool) -> str:
     nvcc = _nvcc()
 
     def compile_one(src):
@@ -84,10 +98,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC", "-cudart", "static"]
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-Xcompiler", "-fPIC", "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)                         # atomic: a concurrent loader sees the old or the new file, never half of one
     with open(HASH_FILE, "w") as fh:
         fh.write(source_hash() + "\n")
     return LIB
