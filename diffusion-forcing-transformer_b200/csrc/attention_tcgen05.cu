@@ -259,6 +259,8 @@ struct Params {
   int no_max;       // scores are bounded (|s| <= ~96 in log2 units, e.g. QK-normalised attention): p = 2^s needs no running
                     // maximum, no subtraction and no rescaling — mathematically identical softmax, a third fewer instructions
   int R, Ntok, heads, q_tiles, kv_tiles, num_items;
+  int pair_items;   // kernel 2: items [0, pair_items) are query-tile PAIRS; the rest are SINGLE tiles, two per pair of the
+                    // last (partial) wave — the tail of the persistent loop then costs half a wave instead of a whole one
 };
 
 // DH: true head dim; DP: head dim padded to a multiple of 16 (MMA K / N granularity)
@@ -577,6 +579,13 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
 #define DFOT_ATTN_POLYB_SECOND 0x55
 #endif
   constexpr uint32_t kPolyFirstB = SEP_P ? DFOT_ATTN_POLYB_FIRST : 0u, kPolySecondB = SEP_P ? DFOT_ATTN_POLYB_SECOND : 0u;
+#ifndef DFOT_ATTN_PV_WAIT_CHUNK
+#define DFOT_ATTN_PV_WAIT_CHUNK -1
+#endif
+  // 32-score chunk (0..3) after whose exps PV_DONE is awaited.  Measured on B200 (d = 64, N = 8192, R = 8), chunk 0 / 1 /
+  // 2 / 3: bounded-score path 903 / 901 / 900 / 824 TFLOP/s (its exp2 phase is short enough that the stores at the end
+  // lengthen the tile), running-max path 788 / 775 / 761 / 844 (there the wait at the very end never stalls).
+  constexpr int kPvWaitChunk = DFOT_ATTN_PV_WAIT_CHUNK >= 0 ? DFOT_ATTN_PV_WAIT_CHUNK : (NOMAX ? 0 : 3);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
@@ -619,9 +628,18 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
 
   const int n_kv = p.kv_tiles;
   const int q_pairs = (p.q_tiles + 1) >> 1;
-  auto item_coord = [&](int item, int& r, int& h, int& qp) {
-    qp = item % q_pairs;                             // consecutive items share (r, h): K/V stay hot in L2
-    const int rh = item / q_pairs;
+  // item -> (sample r, head h, first query tile q0, number of query tiles nt in {1, 2})
+  auto item_coord = [&](int item, int& r, int& h, int& q0, int& nt) {
+    int pair = item, sel = 0;
+    nt = 2;
+    if (item >= p.pair_items) {                      // split tail: two single-tile items per pair
+      const int k = item - p.pair_items;
+      pair = p.pair_items + (k >> 1);
+      sel = k & 1;
+      nt = 1;
+    }
+    q0 = 2 * (pair % q_pairs) + sel;                 // consecutive items share (r, h): K/V stay hot in L2
+    const int rh = pair / q_pairs;
     h = rh % p.heads;
     r = rh / p.heads;
   };
@@ -633,16 +651,16 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
     if (lane == 0) {
       uint32_t g = 0, it = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-        int r, h, qp;
-        item_coord(item, r, h, qp);
+        int r, h, q0, nt;
+        item_coord(item, r, h, q0, nt);
         const int row0 = r * p.Ntok;
         mbar_wait(bar(Q_EMPTY), (it & 1u) ^ 1u);
         mbar_expect_tx(bar(Q_FULL), 2 * TILE_BYTES);
 #pragma unroll
-        for (int t = 0; t < 2; ++t)
+        for (int t = 0; t < 2; ++t)     // (the second slot of a single-tile item is loaded too and simply not used)
 #pragma unroll
           for (int a = 0; a < ATOMS; ++a)
-            tma_load_3d(sQ + t * TILE_BYTES + a * kAtomBytes, &tmap, bar(Q_FULL), a * 64, h, row0 + (2 * qp + t) * BQ);
+            tma_load_3d(sQ + t * TILE_BYTES + a * kAtomBytes, &tmap, bar(Q_FULL), a * 64, h, row0 + (q0 + t) * BQ);
         for (int j = 0; j < n_kv; ++j, ++g) {
           const uint32_t st = g & 1u, ph = (g >> 1) & 1u;
           mbar_wait(bar(K_EMPTY + st), ph ^ 1u);
@@ -673,9 +691,9 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
       const int t = warp - 1;
       uint32_t g = 0, it = 0, n_p = 0, n_f = 0, n_o = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-        int r, h, qp;
-        item_coord(item, r, h, qp);
-        const bool active = (2 * qp + t) * BQ < p.Ntok;   // (tile 1 of the last pair may lie outside the sample)
+        int r, h, q0, nt;
+        item_coord(item, r, h, q0, nt);
+        const bool active = t < nt && (q0 + t) * BQ < p.Ntok;   // (tile 1 of the last pair may lie outside the sample)
         mbar_wait(bar(Q_FULL), it & 1u);
         if (!active) {                                 // keep the shared rings moving
           for (int j = 0; j < n_kv; ++j) {
@@ -751,9 +769,9 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
       uint32_t n_f[2] = {0, 0};                      // S_FREE phases consumed per tile (SEP_P)
       uint32_t n_o[2] = {0, 0};                      // items in which tile t was active (O_FREE phases)
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-        int r, h, qp;
-        item_coord(item, r, h, qp);
-        const bool has1 = (2 * qp + 1) * BQ < p.Ntok;     // second query tile holds rows of this sample
+        int r, h, q0, nt;
+        item_coord(item, r, h, q0, nt);
+        const bool has1 = nt == 2 && (q0 + 1) * BQ < p.Ntok;     // second query tile holds rows of this sample
         auto issue_s = [&](int t, uint32_t st) {          // S_t = Q_t · K^T (K stage st)
           const uint32_t d = tmem_base + TMEM_S + (uint32_t)t * 128u;
 #pragma unroll
@@ -853,10 +871,10 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
     const uint32_t t_o = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_O + (uint32_t)t * O_STRIDE;
     uint32_t n_s = 0, n_items = 0, n_pv = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      int r, h, qp;
-      item_coord(item, r, h, qp);
-      const int qt = 2 * qp + t;
-      if (qt * BQ >= p.Ntok) continue;               // (only t == 1 of the last pair) tile lies outside the sample
+      int r, h, q0, nt;
+      item_coord(item, r, h, q0, nt);
+      const int qt = q0 + t;
+      if (t >= nt || qt * BQ >= p.Ntok) continue;    // single-tile item, or tile 1 of the last pair outside the sample
       float m_used = 0.f, l_run = 0.f;
       uint32_t v[4][32];                             // the 128 scores of this row stay in registers
       // pull S_t(jj) into registers (all four 32-column loads in flight), hand the buffer back, mask, row maximum
@@ -919,9 +937,10 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
           // TFLOP/s at d = 64, N = 8192).  A partial last tile carries -inf masks the polynomial cannot take: MUFU only.
           auto exp_tile = [&](auto poly_tag) {
             constexpr bool POLY = decltype(poly_tag)::value;
+            uint32_t pka[4][16];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              uint32_t pk[16];
+              uint32_t (&pk)[16] = pka[c];
 #pragma unroll
               for (int e = 0; e < 16; e += 2) {
                 float p0, p1, p2, p3;
@@ -936,13 +955,22 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
                 pk[e] = pack_bf16x2(p0, p1);
                 pk[e + 1] = pack_bf16x2(p2, p3);
               }
+              // PV_t(j-1) still reads P_t(j-1) from these very columns: it must have retired before the first store of
+              // P_t(j).  The wait sits after chunk kPvWaitChunk's exps (the packed P of the earlier chunks stays in
+              // registers until then), so that the MMA's latency hides under exp2 work instead of stalling the warp.
               if constexpr (SEP_P) {
-                if (c == 0 && j > 0) {               // PV_t(j-1) still reads P_t(j-1) from these columns
-                  mbar_wait_fast(bar(PV_DONE + t), n_pv++ & 1u);
-                  tc_fence_after();
+                if (c == kPvWaitChunk) {
+                  if (j > 0) {
+                    mbar_wait_fast(bar(PV_DONE + t), n_pv++ & 1u);
+                    tc_fence_after();
+                  }
+#pragma unroll
+                  for (int cc = 0; cc < kPvWaitChunk; ++cc) tmem_st_x16(t_p + 16 * cc, pka[cc]);
                 }
+                if (c >= kPvWaitChunk) tmem_st_x16(t_p + 16 * c, pk);
+              } else {
+                tmem_st_x16(t_p + 16 * c, pk);
               }
-              tmem_st_x16(t_p + 16 * c, pk);
             }
           };
           if (p.Ntok - j * BKV >= BKV) exp_tile(std::true_type{});
@@ -975,9 +1003,10 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
         // p = exp2(s - m) → packed bf16 pairs into P_t (the PV MMA's A operand); fp32x2 packed sub / row sum
         const uint64_t neg_m2 = pack_f32x2(-m_used, -m_used);
         uint64_t sum_a = 0ull, sum_b = 0ull;         // (+0.f, +0.f)
+        uint32_t pka[4][16];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
+          uint32_t (&pk)[16] = pka[c];
 #pragma unroll
           for (int e = 0; e < 16; e += 2) {
             float x0, x1, x2, x3;
@@ -999,13 +1028,19 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
           }
           if constexpr (SEP_P) {
             // PV_t(j-1) reads P_t(j-1) from these very columns (and writes O_t): it must have retired before the first
-            // store of P_t(j).  Waiting here — after the first 32 exps — instead of before them hides its latency.
-            if (c == 0 && j > 0) {
-              mbar_wait_fast(bar(PV_DONE + t), n_pv++ & 1u);
-              tc_fence_after();
+            // store of P_t(j) — see the bounded-score path above for the placement of the wait.
+            if (c == kPvWaitChunk) {
+              if (j > 0) {
+                mbar_wait_fast(bar(PV_DONE + t), n_pv++ & 1u);
+                tc_fence_after();
+              }
+#pragma unroll
+              for (int cc = 0; cc < kPvWaitChunk; ++cc) tmem_st_x16(t_p + 16 * cc, pka[cc]);
             }
+            if (c >= kPvWaitChunk) tmem_st_x16(t_p + 16 * c, pk);
+          } else {
+            tmem_st_x16(t_p + 16 * c, pk);
           }
-          tmem_st_x16(t_p + 16 * c, pk);
           if constexpr (PREFETCH) {                  // S_t(j+1) into the registers the exp2 loop has finished with
             if (more) {
               if (c == 2) {                          // late enough for S_t(j+1) to be complete: the wait is free
@@ -1105,308 +1140,6 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
   }
 }
 
-// =====================================================================================================================
-// Kernel 3 — head_dim 64 only: kernel 2's two query tiles, with every tile's keys split into two INDEPENDENT online-
-// softmax streams (keys 0-63 / 64-127 of each 128-key tile), merged once per work item (flash-decoding style):
-//   * 16 softmax warps = 4 per scheduler instead of 2: the exp2 rate (16/clk/SM MUFU) bounds head_dim-64 attention, and
-//     with two warps per scheduler the MUFU sat idle ~30 % of the time (both warps in their load / max / hand-off phases);
-//   * a thread owns (query row, 64 keys): 64 scores in registers, its own running maximum / sum / O accumulator —
-//     streams never exchange anything inside the KV loop;
-//   * S_t = Q_t·Kᵀ is still ONE 128x128 MMA per tile; stream u reads columns [64u, 64u+64), writes its packed bf16 P over
-//     the first 32 of them, and the PV MMA of the stream (A from TMEM, K = 64) accumulates into its own O_tu (64 columns):
-//     TMEM = 2 x 128 (S/P) + 4 x 64 (O) = 512 columns; tensor work is identical to kernel 2;
-//   * epilogue: out = (a0·O_t0 + a1·O_t1) / (a0·l0 + a1·l1), a_u = 2^(m_u − max(m0, m1)); the two threads of a row swap
-//     (m, l) through shared memory once per item and each writes half of the row's columns.
-// MEASURED (B200, d = 64, N = 8192): 585 TFLOP/s against kernel 2's 788 — with P aliased into S (no TMEM left for a
-// separate P) S_t(j+1) has to wait for both streams' PV(j), and that per-tile bubble costs more than the extra warps
-// hide.  Kept selectable (DFOT_ATTENTION_IMPL=3) as the record of the experiment; kernel 2 is the default.
-constexpr int kThreads3 = 640;   // warp 0 TMA, warps 1-2 MMA issuers (tile 0 / 1), warp 3 idle, warps 4-19 softmax
-__global__ void __launch_bounds__(kThreads3, 1)
-attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
-  pdl_trigger();   // programmatic dependent launch: see common.cuh (pdl_wait() follows the prologue)
-  constexpr int DH = 64;
-  constexpr int TILE_BYTES = kAtomBytes;             // 128 rows x 64 bf16
-  constexpr uint32_t IDESC_S = make_idesc(BKV, false);
-  constexpr uint32_t IDESC_PV = make_idesc(DH, true);
-  constexpr uint32_t TMEM_O = 256;                   // S_t at 128*t (stream u: +64u; P_tu aliases its first 32 columns)
-  constexpr float kRescaleThreshold = 8.0f;
-
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const uint32_t base = smem_u32(smem_raw);
-  if ((base & 1023u) != 0) {
-    if (threadIdx.x == 0) printf("dfot_attention: dynamic shared memory is not 1024-byte aligned\n");
-    __trap();
-  }
-  const uint32_t sQ = base;                          // 2 tiles
-  const uint32_t sK = sQ + 2 * TILE_BYTES;           // 2 stages
-  const uint32_t sV = sK + 2 * TILE_BYTES;           // 2 stages
-  const uint32_t bars = sV + 2 * TILE_BYTES;
-  enum { Q_FULL = 0, Q_EMPTY = 1, K_FULL = 2, K_EMPTY = 4, V_FULL = 6, V_EMPTY = 8, S_FULL = 10, P_FULL = 12,
-         O_DONE = 14, O_FREE = 16, N_BARS = 18 };
-  auto bar = [&](int id) { return bars + 8u * id; };
-  const uint32_t tmem_slot = bars + 8u * N_BARS;
-  const uint32_t s_merge = bars + 256u;              // float2 [2 tiles][2 streams][128 rows]: (m, l) of each stream
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-    for (int i = 0; i < N_BARS; ++i) {
-      const bool from_softmax = (i >= P_FULL && i < P_FULL + 2) || (i >= O_FREE && i < O_FREE + 2);
-      const bool from_both_issuers = i == Q_EMPTY || (i >= K_EMPTY && i < K_EMPTY + 2) || (i >= V_EMPTY && i < V_EMPTY + 2);
-      mbar_init(bar(i), from_softmax ? 8 : (from_both_issuers ? 2 : 1));   // 8 = both streams' warps of a tile
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  pdl_wait();   // barriers and tensor memory are set up; global memory is only touched from here on
-
-  const int n_kv = p.kv_tiles;
-  const int q_pairs = (p.q_tiles + 1) >> 1;
-  auto item_coord = [&](int item, int& r, int& h, int& qp) {
-    qp = item % q_pairs;
-    const int rh = item / q_pairs;
-    h = rh % p.heads;
-    r = rh / p.heads;
-  };
-
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (warp == 0) {
-      // ===================== TMA producer =====================
-      if (lane == 0) {
-        uint32_t g = 0, it = 0;
-        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-          int r, h, qp;
-          item_coord(item, r, h, qp);
-          const int row0 = r * p.Ntok;
-          mbar_wait(bar(Q_EMPTY), (it & 1u) ^ 1u);
-          mbar_expect_tx(bar(Q_FULL), 2 * TILE_BYTES);
-          tma_load_3d(sQ, &tmap, bar(Q_FULL), 0, h, row0 + (2 * qp) * BQ);
-          tma_load_3d(sQ + TILE_BYTES, &tmap, bar(Q_FULL), 0, h, row0 + (2 * qp + 1) * BQ);
-          for (int j = 0; j < n_kv; ++j, ++g) {
-            const uint32_t st = g & 1u, ph = (g >> 1) & 1u;
-            mbar_wait(bar(K_EMPTY + st), ph ^ 1u);
-            mbar_expect_tx(bar(K_FULL + st), TILE_BYTES);
-            tma_load_3d(sK + st * TILE_BYTES, &tmap, bar(K_FULL + st), 0, p.heads + h, row0 + j * BKV);
-            mbar_wait(bar(V_EMPTY + st), ph ^ 1u);
-            mbar_expect_tx(bar(V_FULL + st), TILE_BYTES);
-            tma_load_3d(sV + st * TILE_BYTES, &tmap, bar(V_FULL + st), 0, 2 * p.heads + h, row0 + j * BKV);
-          }
-        }
-      }
-    } else if (warp <= 2) {
-      // ===================== MMA issuers: warp 1 drives query tile 0, warp 2 drives query tile 1 =====================
-      // per tile t:  S_t(0) | PV_t0(j) PV_t1(j) S_t(j+1) ...  (P_tu lives inside S_t: issue order makes the aliasing safe)
-      if (lane == 0) {
-        const int t = warp - 1;
-        uint32_t g = 0, it = 0, n_p = 0, n_o = 0;
-        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-          int r, h, qp;
-          item_coord(item, r, h, qp);
-          const bool active = (2 * qp + t) * BQ < p.Ntok;
-          mbar_wait(bar(Q_FULL), it & 1u);
-          if (!active) {                               // keep the shared rings moving
-            for (int j = 0; j < n_kv; ++j) {
-              const uint32_t gt = g + j, st = gt & 1u, ph = (gt >> 1) & 1u;
-              mbar_wait(bar(K_FULL + st), ph);
-              mbar_arrive(bar(K_EMPTY + st));
-              mbar_wait(bar(V_FULL + st), ph);
-              mbar_arrive(bar(V_EMPTY + st));
-            }
-            mbar_arrive(bar(Q_EMPTY));
-            g += n_kv;
-            continue;
-          }
-          auto issue_s = [&](uint32_t st) {
-            const uint32_t d = tmem_base + (uint32_t)t * 128u;
-#pragma unroll
-            for (int s = 0; s < DH / 16; ++s)
-              umma_bf16(d, desc_kmajor(sQ + t * TILE_BYTES + (uint32_t)s * 32u), desc_kmajor(sK + st * TILE_BYTES + (uint32_t)s * 32u),
-                        IDESC_S, s > 0 ? 1u : 0u);
-            umma_commit(bar(S_FULL + t));
-            umma_commit(bar(K_EMPTY + st));
-          };
-          {
-            const uint32_t st = g & 1u, ph = (g >> 1) & 1u;
-            mbar_wait(bar(K_FULL + st), ph);
-            tc_fence_after();
-            issue_s(st);
-          }
-          if (n_o > 0) mbar_wait(bar(O_FREE + t), (n_o - 1) & 1u);
-          for (int j = 0; j < n_kv; ++j) {
-            const uint32_t gt = g + j, st = gt & 1u, ph = (gt >> 1) & 1u;
-            const uint32_t gn = gt + 1, stn = gn & 1u, phn = (gn >> 1) & 1u;
-            mbar_wait(bar(V_FULL + st), ph);
-            mbar_wait_fast(bar(P_FULL + t), n_p++ & 1u);   // both streams stored P(j) (and rescaled O if they had to)
-            tc_fence_after();
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const uint32_t d = tmem_base + TMEM_O + (uint32_t)t * 128u + (uint32_t)u * 64u;
-              const uint32_t a = tmem_base + (uint32_t)t * 128u + (uint32_t)u * 64u;
-#pragma unroll
-              for (int s = 0; s < 4; ++s)              // 64 keys of the stream = 4 k-steps of 16
-                umma_bf16_ts(d, a + (uint32_t)(8 * s),
-                             desc_mnmajor(sV + st * TILE_BYTES + (uint32_t)(4 * u + s) * 2048u, kAtomBytes), IDESC_PV,
-                             (j == 0 && s == 0) ? 0u : 1u);
-            }
-            umma_commit(bar(V_EMPTY + st));
-            if (j + 1 < n_kv) {
-              mbar_wait(bar(K_FULL + stn), phn);
-              tc_fence_after();
-              issue_s(stn);
-            } else {
-              umma_commit(bar(O_DONE + t));
-            }
-          }
-          umma_commit(bar(Q_EMPTY));
-          ++n_o;
-          g += n_kv;
-        }
-      }
-    }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    // ===================== softmax streams: thread = (query row of tile t, key half u) =====================
-    const int grp = (warp - 4) >> 2;                 // 0..3
-    const int t = grp >> 1, u = grp & 1;
-    const int q = warp & 3;                          // TMEM lane quarter (hardware rule: warp_id % 4)
-    const int row = q * 32 + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t t_s = lane_base + (uint32_t)t * 128u + (uint32_t)u * 64u;     // scores; P aliases the first 32 columns
-    const uint32_t t_o = lane_base + TMEM_O + (uint32_t)t * 128u + (uint32_t)u * 64u;
-    uint32_t n_s = 0, n_items = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      int r, h, qp;
-      item_coord(item, r, h, qp);
-      const int qt = 2 * qp + t;
-      if (qt * BQ >= p.Ntok) continue;
-      float m_used = 0.f, l_run = 0.f;
-      for (int j = 0; j < n_kv; ++j) {
-        mbar_wait_fast(bar(S_FULL + t), n_s++ & 1u);
-        tc_fence_after();
-        uint32_t v[2][32];
-        tmem_ld_x32(t_s, v[0]);
-        tmem_ld_x32(t_s + 32, v[1]);
-        tmem_ld_wait();
-        const int valid = p.Ntok - j * BKV - u * 64;   // keys of this half-tile that exist (<= 0: none — only j > 0)
-        if (valid < 64) {
-#pragma unroll
-          for (int c = 0; c < 64; ++c)
-            if (c >= valid) v[c >> 5][c & 31] = 0xff800000u;   // -inf
-        }
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          mx0 = fmaxf(mx0, __uint_as_float(v[0][c]));
-          mx1 = fmaxf(mx1, __uint_as_float(v[0][16 + c]));
-          mx2 = fmaxf(mx2, __uint_as_float(v[1][c]));
-          mx3 = fmaxf(mx3, __uint_as_float(v[1][16 + c]));
-        }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        float alpha = 1.f;
-        bool rescale = false;
-        if (j == 0) {
-          m_used = mx;                               // first tile always holds valid keys (Ntok > 128); O is overwritten
-        } else {
-          const bool raise = mx > m_used + kRescaleThreshold;
-          rescale = __any_sync(0xffffffffu, raise);
-          if (raise) {
-            alpha = ex2(m_used - mx);
-            l_run *= alpha;
-            m_used = mx;
-          }
-        }
-        const uint64_t neg_m2 = pack_f32x2(-m_used, -m_used);
-        uint64_t sum_a = 0ull, sum_b = 0ull;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            float x0, x1, x2, x3;
-            unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[c][2 * e]), __uint_as_float(v[c][2 * e + 1])), neg_m2), x0, x1);
-            unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[c][2 * e + 2]), __uint_as_float(v[c][2 * e + 3])), neg_m2), x2, x3);
-            const float p0 = ex2(x0), p1 = ex2(x1), p2 = ex2(x2), p3 = ex2(x3);
-            sum_a = add_f32x2(sum_a, pack_f32x2(p0, p1));
-            sum_b = add_f32x2(sum_b, pack_f32x2(p2, p3));
-            pk[e] = pack_bf16x2(p0, p1);
-            pk[e + 1] = pack_bf16x2(p2, p3);
-          }
-          tmem_st_x16(t_s + 16 * c, pk);             // all 64 scores are in registers: safe to overwrite
-        }
-        float sum0, sum1, sum2, sum3;
-        unpack_f32x2(sum_a, sum0, sum1);
-        unpack_f32x2(sum_b, sum2, sum3);
-        if (rescale) {   // S_FULL(j) was committed after PV(j-1): O_tu is complete and idle until P_FULL(j)
-#pragma unroll
-          for (int c0 = 0; c0 < 64; c0 += 32) {
-            uint32_t o[32];
-            tmem_ld_x32(t_o + c0, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-            tmem_st_x32(t_o + c0, o);
-          }
-        }
-        l_run += (sum0 + sum1) + (sum2 + sum3);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(P_FULL + t));
-      }
-      // ---- merge the two streams of the row and write half of its columns
-      mbar_wait_fast(bar(O_DONE + t), n_items++ & 1u);
-      tc_fence_after();
-      const uint32_t mine = s_merge + 8u * (uint32_t)((t * 2 + u) * 128 + row);
-      const uint32_t other = s_merge + 8u * (uint32_t)((t * 2 + (u ^ 1)) * 128 + row);
-      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(mine), "f"(m_used), "f"(l_run) : "memory");
-      asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
-      float m_o, l_o;
-      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_o), "=f"(l_o) : "r"(other));
-      const float m_all = fmaxf(m_used, m_o);
-      const float a_me = ex2(m_used - m_all), a_ot = ex2(m_o - m_all);
-      const float inv = 1.f / (a_me * l_run + a_ot * l_o);
-      const float w_me = a_me * inv, w_ot = a_ot * inv;
-      uint32_t o_me[32], o_ot[32];                   // columns [32u, 32u+32) of both streams' accumulators
-      tmem_ld_x32(t_o + 32 * u, o_me);
-      tmem_ld_x32(lane_base + TMEM_O + (uint32_t)t * 128u + (uint32_t)(u ^ 1) * 64u + 32 * u, o_ot);
-      tmem_ld_wait();
-      const int qrow = qt * BQ + row;
-      if (qrow < p.Ntok) {
-        __nv_bfloat16* dst = p.out + ((int64_t)r * p.Ntok + qrow) * p.ld_out + (int64_t)h * DH + 32 * u;
-#pragma unroll
-        for (int c = 0; c < 32; c += 8) {
-          float y[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(o_me[c + e]) * w_me + __uint_as_float(o_ot[c + e]) * w_ot;
-          *reinterpret_cast<uint4*>(dst + c) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
-                                                          pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-        }
-      }
-      asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");   // partner has read my (m, l) before the next item overwrites it
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(O_FREE + t));
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-  }
-}
-
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1429,9 +1162,17 @@ static int attention_impl_override() {   // DFOT_ATTENTION_IMPL=1|2 pins the ker
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("DFOT_ATTENTION_IMPL");
-    v = (e != nullptr && (e[0] == '1' || e[0] == '2' || e[0] == '3')) ? e[0] - '0' : 0;
+    v = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
   }
   return v;
+}
+static bool attention_split_tail() {     // DFOT_ATTENTION_SPLIT_TAIL=0 keeps whole pairs in the last wave (benchmarking)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DFOT_ATTENTION_SPLIT_TAIL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 template <int DH, int DP>
@@ -1442,10 +1183,8 @@ static int launch(const void* qkv, void* out, int64_t ld_out, int64_t R, int64_t
   constexpr int smem2 = 6 * ATOMS * kAtomBytes + 512 /*barriers*/;
   static_assert(smem1 <= 232448 && smem2 <= 232448, "attention: shared memory budget exceeded");
   const int ov = attention_impl_override();
-  const bool split = DH == 64 && Ntok > BQ && ov == 3;   // kernel 3 (two key streams per query tile): opt-in, see below
-  const bool paired = split || ov == 2 || (ov == 0 && Ntok > BQ);      // more than one query tile per sample
-  constexpr int smem3 = 6 * kAtomBytes + 256 + 4096 + 64;
-  const int smem_bytes = split ? smem3 : (paired ? smem2 : smem1);
+  const bool paired = ov == 2 || (ov == 0 && Ntok > BQ);      // more than one query tile per sample
+  const int smem_bytes = paired ? smem2 : smem1;
   EncodeTiledFn enc = get_encode_fn();
   DFOT_REQUIRE(enc != nullptr, DFOT_ERR_DRIVER, "attention: cuTensorMapEncodeTiled unavailable from the driver");
   // qkv viewed as [tokens][3*heads][DH]: box = 64 (d) x 1 x 128 (tokens); d beyond DH is zero-filled by TMA
@@ -1458,19 +1197,21 @@ static int launch(const void* qkv, void* out, int64_t ld_out, int64_t R, int64_t
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DFOT_REQUIRE(cr == CUDA_SUCCESS, DFOT_ERR_DRIVER, "attention: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
-  const bool nomax = paired && !split && score_bound > 0.f && score_bound <= 96.f;   // kernel 2 only
+  const bool nomax = paired && score_bound > 0.f && score_bound <= 96.f;   // kernel 2 only
   void (*kern)(const CUtensorMap, const Params) =
-      split ? attention3_tcgen05_kernel
-            : (paired ? (nomax ? attention2_tcgen05_kernel<DH, DP, true> : attention2_tcgen05_kernel<DH, DP, false>)
-                      : attention_tcgen05_kernel<DH, DP>);
-  const int which = split ? 2 : (paired ? (nomax ? 3 : 1) : 0);
-  static bool configured[4] = {false, false, false, false};
+      paired ? (nomax ? attention2_tcgen05_kernel<DH, DP, true> : attention2_tcgen05_kernel<DH, DP, false>)
+             : attention_tcgen05_kernel<DH, DP>;
+  const int which = paired ? (nomax ? 2 : 1) : 0;
+  static bool configured[3] = {false, false, false};
   if (!configured[which]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     DFOT_REQUIRE(e == cudaSuccess, DFOT_ERR_CUDA, "attention: cannot reserve %d B shared memory: %s", smem_bytes,
                  cudaGetErrorString(e));
     configured[which] = true;
   }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   Params p;
   p.out = (__nv_bfloat16*)out;
   p.ld_out = ld_out;
@@ -1479,11 +1220,21 @@ static int launch(const void* qkv, void* out, int64_t ld_out, int64_t R, int64_t
   p.q_tiles = (int)ceil_div(Ntok, BQ);
   p.kv_tiles = (int)ceil_div(Ntok, BKV);
   p.num_items = (int)(R * heads * (paired ? (p.q_tiles + 1) / 2 : p.q_tiles));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  p.pair_items = p.num_items;
+  if (paired && attention_split_tail() && p.q_tiles % 2 == 0 && p.num_items > sms) {
+    // Persistent CTAs take items round-robin, so the last wave holds num_items % sms pairs on as many SMs while the
+    // others idle for the length of a whole item.  Those pairs are handed out as single query tiles instead (twice the
+    // items, half the work each) when they still fit one wave: the tail then costs about half a wave.  (With more than
+    // sms / 2 pairs left the singles would need two rounds, and a single costs more than half a pair — K / V tiles are
+    // shared inside a pair — so those tails stay whole: measured 866 vs 1000 TFLOP/s at d = 128, R = 8, N = 2048.)
+    const int rem = p.num_items % sms;
+    if (rem > 0 && 2 * rem <= sms) {
+      p.pair_items = p.num_items - rem;
+      p.num_items = p.pair_items + 2 * rem;
+    }
+  }
   const int grid = p.num_items < sms ? p.num_items : sms;
-  launch_pdl(kern, dim3(grid), dim3(split ? kThreads3 : (paired ? kThreads2 : kThreads)), smem_bytes, s, tmap, p);
+  launch_pdl(kern, dim3(grid), dim3(paired ? kThreads2 : kThreads), smem_bytes, s, tmap, p);
   DFOT_CHECK_LAUNCH("attention_tcgen05");
   return DFOT_OK;
 }

@@ -102,7 +102,10 @@ def test_gemm_qkv_rope_epilogue(heads, dh, T, gh, gw):
 @pytest.mark.parametrize("R,heads,dh,N", [(2, 4, 64, 512), (1, 1, 64, 64), (2, 16, 72, 1280), (1, 12, 64, 576),
                                           (1, 9, 128, 2048), (3, 2, 72, 200), (1, 2, 64, 1), (2, 3, 72, 128),
                                           (3, 2, 128, 129), (1, 2, 64, 256), (5, 7, 72, 384), (1, 2, 64, 8192),
-                                          (8, 16, 72, 1280)])
+                                          (8, 16, 72, 1280),
+                                          # more pair items than SMs with an even tile count: the last wave is handed
+                                          # out as single query tiles (split tail) — dual-issuer, single-issuer, d = 128
+                                          (4, 12, 64, 1024), (3, 9, 128, 2048), (5, 16, 72, 512)])
 def test_attention_matches_sdpa(R, heads, dh, N):
     D = heads * dh
     g = torch.Generator().manual_seed(N + dh)
@@ -119,7 +122,7 @@ def test_attention_matches_sdpa(R, heads, dh, N):
 
 
 @pytest.mark.parametrize("R,heads,dh,N", [(2, 9, 64, 1024), (1, 9, 128, 512), (2, 3, 64, 200), (1, 2, 128, 129),
-                                          (1, 2, 64, 100), (3, 4, 72, 384)])
+                                          (1, 2, 64, 100), (3, 4, 72, 384), (4, 12, 64, 1024), (3, 9, 128, 2048)])
 def test_attention_bounded_scores_matches_sdpa(R, heads, dh, N):
     """QK-normalised operands with a declared score bound: the kernel may drop the running maximum (p = 2^s); the
     result must still be the softmax attention.  Scores reach the declared bound on the diagonal (q == k direction)."""
@@ -140,7 +143,8 @@ def test_attention_bounded_scores_matches_sdpa(R, heads, dh, N):
     out = torch.full((R * N, D), float("nan"), device=DEV, dtype=torch.bfloat16)
     ops.attention(qkv, out, R, N, heads, dh, score_bound=bound)
     assert torch.isfinite(out.float()).all()
-    assert (out.float() - ref).abs().max().item() < 3e-2 and rel_err(out, ref) < 1e-2
+    # (absolute 3e-2 for |ref| <= 1, relative above: one bf16 ulp of an output in [4, 8) is already 3.1e-2)
+    assert ((out.float() - ref).abs() <= 3e-2 * ref.abs().clamp(min=1.0)).all() and rel_err(out, ref) < 1e-2
 
 
 @pytest.mark.parametrize("heads,dh,N", [(3, 64, 2048), (2, 128, 1024), (2, 72, 640)])
