@@ -579,6 +579,10 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
 #define DFOT_ATTN_POLYB_SECOND 0x55
 #endif
   constexpr uint32_t kPolyFirstB = SEP_P ? DFOT_ATTN_POLYB_FIRST : 0u, kPolySecondB = SEP_P ? DFOT_ATTN_POLYB_SECOND : 0u;
+  // Measured and dropped (aliased layout, d = 72 / 128): starting tile 1 one softmax phase behind tile 0, so that one
+  // warpgroup exponentiates while the other tile's PV + S MMAs run — 505 vs 522 TFLOP/s at d = 72 (N = 1280), 958 vs 1003
+  // at d = 128 (N = 2048): the hand-off latencies, not the phase of the two tiles, bound these shapes
+  // (profiles/r02_ncu_attn72.txt: 44 % of the softmax warps' samples wait for S_FULL with the tensor pipe 27 % busy).
 #ifndef DFOT_ATTN_PV_WAIT_CHUNK
 #define DFOT_ATTN_PV_WAIT_CHUNK -1
 #endif
