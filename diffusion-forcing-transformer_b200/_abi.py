@@ -17,6 +17,7 @@ SYMBOLS = [
     "dfot_rmsnorm_film_bf16", "dfot_qk_norm_rope", "dfot_avgpool2x2", "dfot_sub_bf16", "dfot_upsample2x_add",
     "dfot_pose_ray_patches", "dfot_groupnorm_stats_strided", "dfot_groupnorm_apply_bf16", "dfot_vae_upsample2x_bf16",
     "dfot_vae_fill_pad_frames", "dfot_softmax_rows_bf16", "dfot_upsample2x_nearest_bf16",
+    "dfot_relu_bf16", "dfot_pixel_shuffle2x", "dfot_linear_attention_relu", "dfot_dwconv3x3_glu_bf16", "dfot_rmsnorm_affine",
 ]
 
 
@@ -90,6 +91,11 @@ def lib() -> ctypes.CDLL:
     L.dfot_sub_bf16.argtypes = [vp, vp, vp, i64, vp]
     L.dfot_upsample2x_add.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp]
     L.dfot_pose_ray_patches.argtypes = [vp, vp, i64, vp, i64, i64, i64, i64, vp]
+    L.dfot_relu_bf16.argtypes = [vp, i64, vp]
+    L.dfot_pixel_shuffle2x.argtypes = [vp, i64, vp, i64, i64, vp, vp, i64, i64, i64, i64, vp]
+    L.dfot_linear_attention_relu.argtypes = [vp, i64, vp, i64, i64, i64, i64, i64, c_float, vp]
+    L.dfot_dwconv3x3_glu_bf16.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp]
+    L.dfot_rmsnorm_affine.argtypes = [vp, i64, vp, vp, c_float, vp, i, vp, vp, i64, i64, vp]
     for name in SYMBOLS:
         if name not in ("dfot_last_error", "dfot_launch_count"):
             getattr(L, name).restype = c_int

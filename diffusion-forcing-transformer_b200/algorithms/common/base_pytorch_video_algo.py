@@ -99,12 +99,20 @@ class BaseVideoAlgo(nn.Module):
 
     # ------------------------------------------------------------------ latent decode (:507-629)
     def _load_vae(self) -> None:
-        """(:507-551) — the reference's own VAEs on the B200 kernels: the causal VideoVAE when latents are temporally
-        compressed, else the ImageVAE; the external image VAEs (DC-AE, diffusers KL, TiTok) are not built."""
+        """(:507-551) — VAEs on the B200 kernels: the DC-AE image autoencoder when `vae.name` names it (DMLab / Minecraft),
+        else the reference's causal VideoVAE (temporally compressed latents) or its ImageVAE; the diffusers KL autoencoder
+        and TiTok tokenizer (external model code no shipped configuration of the sampling path selects) are not built."""
         name = self.cfg.vae.get("name")
+        if name is not None and "dc_ae" in name:
+            from ..vae import MyAutoencoderDC
+            self.vae = MyAutoencoderDC.from_pretrained(cfg=self.cfg.vae, **dict(self.cfg.vae.get("pretrained_kwargs") or {}))
+            self.vae = self.vae.to(self.device)
+            for p in self.vae.parameters():
+                p.requires_grad_(False)
+            return
         if name is not None:
-            raise NotImplementedError(f"vae.name={name!r} (DC-AE / KL / TiTok: external model code) is not decoded by "
-                                      "dfot_b200; only the reference's VideoVAE and ImageVAE are")
+            raise NotImplementedError(f"vae.name={name!r} (diffusers AutoencoderKL / TiTok: external model code) is not "
+                                      "decoded by dfot_b200; DC-AE and the reference's VideoVAE / ImageVAE are")
         from ..vae import ImageVAE, VideoVAE
         vae_cls = VideoVAE if self.is_latent_video_vae else ImageVAE
         self.vae = vae_cls.from_pretrained(path=self.cfg.vae.pretrained_path,

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdfot_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["abi.cu", "sampler.cu", "norm.cu", "embed.cu", "uvit.cu", "vae.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu"]
+SOURCES = ["abi.cu", "sampler.cu", "norm.cu", "embed.cu", "uvit.cu", "vae.cu", "dcae.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

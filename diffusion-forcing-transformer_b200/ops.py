@@ -431,3 +431,66 @@ def pose_ray_patches(cams, freq_scale, out, frames, res, p):
     rc = _abi.lib().dfot_pose_ray_patches(cams.data_ptr(), freq_scale.data_ptr(), freq_scale.numel(), out.data_ptr(),
                                           out.stride(0), frames, res, p, _stream())
     _abi.check(rc, "pose_ray_patches")
+
+
+# ---------------------------------------------------------------- DC-AE decoder glue (include/dfot_b200.h)
+def relu_bf16(x):
+    _need(x, torch.bfloat16, "x")
+    rc = _abi.lib().dfot_relu_bf16(x.data_ptr(), x.numel(), _stream())
+    _abi.check(rc, "relu_bf16")
+
+
+def pixel_shuffle2x(conv, C, n_img, H, W, shortcut=None, repeats=1, out_f32=None, out_bf16=None):
+    """conv [n*H*W, >= 4C] f32 (+ shortcut [n*H*W, 4C / repeats] f32) -> [n, 2H, 2W, C] f32 and / or bf16."""
+    if not conv.is_cuda or conv.dtype != torch.float32 or conv.stride(-1) != 1 or conv.shape[0] != n_img * H * W:
+        raise RuntimeError("dfot_b200: `conv` must be a CUDA f32 [n*H*W, >=4C] matrix with unit inner stride")
+    Cx = 0
+    if shortcut is not None:
+        _need(shortcut, torch.float32, "shortcut")
+        Cx = shortcut.shape[-1]
+    for t, dt, n in ((out_f32, torch.float32, "out_f32"), (out_bf16, torch.bfloat16, "out_bf16")):
+        if t is not None:
+            _need(t, dt, n)
+            if t.numel() != n_img * 4 * H * W * C:
+                raise RuntimeError(f"dfot_b200: `{n}` must hold n*2H*2W*C elements")
+    rc = _abi.lib().dfot_pixel_shuffle2x(conv.data_ptr(), conv.stride(0), _ptr(shortcut), Cx, repeats, _ptr(out_f32),
+                                         _ptr(out_bf16), n_img, H, W, C, _stream())
+    _abi.check(rc, "pixel_shuffle2x")
+
+
+def linear_attention_relu(qkv, out, n_img, HW, heads, head_dim, eps=1e-15):
+    _need(qkv, torch.float32, "qkv")
+    _need(out, torch.float32, "out")
+    if qkv.shape[0] != n_img * HW or out.shape[0] != n_img * HW:
+        raise RuntimeError("dfot_b200: linear_attention_relu expects [n_img*HW, ...] matrices")
+    rc = _abi.lib().dfot_linear_attention_relu(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), n_img, HW, heads,
+                                               head_dim, float(eps), _stream())
+    _abi.check(rc, "linear_attention_relu")
+
+
+def dwconv3x3_glu_bf16(x, w, b, out, n_img, H, W, Ch):
+    _need(x, torch.bfloat16, "x")
+    _need(w, torch.float32, "w")
+    _need(b, torch.float32, "b")
+    _need(out, torch.bfloat16, "out")
+    if x.numel() != n_img * H * W * 2 * Ch or out.numel() != n_img * H * W * Ch or w.numel() != 18 * Ch or b.numel() != 2 * Ch:
+        raise RuntimeError("dfot_b200: dwconv3x3_glu shape mismatch")
+    rc = _abi.lib().dfot_dwconv3x3_glu_bf16(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), n_img, H, W, Ch, _stream())
+    _abi.check(rc, "dwconv3x3_glu_bf16")
+
+
+def rmsnorm_affine(x, w, b, eps, resid=None, relu=False, out_f32=None, out_bf16=None):
+    if not x.is_cuda or x.dtype != torch.float32 or x.stride(-1) != 1:
+        raise RuntimeError("dfot_b200: `x` must be a CUDA f32 matrix with unit inner stride")
+    _need(w, torch.float32, "w")
+    _need(b, torch.float32, "b")
+    M, C = x.shape
+    if resid is not None:
+        _need(resid, torch.float32, "resid")
+    if out_f32 is not None:
+        _need(out_f32, torch.float32, "out_f32")
+    if out_bf16 is not None:
+        _need(out_bf16, torch.bfloat16, "out_bf16")
+    rc = _abi.lib().dfot_rmsnorm_affine(x.data_ptr(), x.stride(0), w.data_ptr(), b.data_ptr(), float(eps), _ptr(resid),
+                                        1 if relu else 0, _ptr(out_f32), _ptr(out_bf16), M, C, _stream())
+    _abi.check(rc, "rmsnorm_affine")

@@ -298,6 +298,32 @@ DFOT_API int dfot_upsample2x_add(const float* low, const float* skip, float* out
 DFOT_API int dfot_pose_ray_patches(const float* cams, const float* freq_scale, int64_t n_freq, void* out_bf16, int64_t ld,
                           int64_t frames, int64_t res, int64_t p, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * DC-AE image decoder (the VAE of the DMLab / Minecraft latent configurations): glue kernels around
+ * the GEMM / implicit-GEMM calls.  Reference: algorithms/vae/dc_ae/autoencoder_dc_model.py (Decoder :383-470,
+ * DCUpBlock2d :222-260, ResBlock :109-136, EfficientViTBlock :139-172, SanaMultiscaleLinearAttention :46-106) and the
+ * diffusers==0.32.2 modules it imports (GLUMBConv, RMSNorm, SanaMultiscaleAttnProcessor2_0).  Channel-last [n, H, W, C].
+ *   dfot_relu_bf16            — max(x, 0) in place (ResBlock nonlinearity; n % 8 == 0).
+ *   dfot_pixel_shuffle2x      — out[n, 2h+i, 2w+j, c] = conv[n, h, w, 4c+2i+j] (+ x[n, h, w, (4c+2i+j)/repeats], the
+ *                               channel-repeat shortcut of DCUpBlock2d; x NULL: none) -> f32 and / or bf16.
+ *   dfot_linear_attention_relu— ReLU linear attention over the tokens of an image: a token's [q|k|v] row is read as
+ *                               `heads` groups of 3*head_dim channels (query, key, value of the group), per group
+ *                               out = (relu(q) KV) / (relu(q) KV[:, d] + eps), KV = relu(k)^T [v | 1]; fp32, head_dim <= 32.
+ *   dfot_dwconv3x3_glu_bf16   — GLUMBConv middle: y = depthwise3x3(x) + b over 2*Ch channels; out = y[:Ch] * silu(y[Ch:]).
+ *   dfot_rmsnorm_affine       — y = x * rsqrt(mean_c(x^2) + eps) * w + b (+ resid) (ReLU if relu) -> f32 and / or bf16.
+ */
+DFOT_API int dfot_relu_bf16(void* x_bf16, int64_t n, void* stream);
+DFOT_API int dfot_pixel_shuffle2x(const float* conv, int64_t ld_conv, const float* x, int64_t Cx, int64_t repeats,
+                                  float* out_f32, void* out_bf16, int64_t n_img, int64_t H, int64_t W, int64_t C,
+                                  void* stream);
+DFOT_API int dfot_linear_attention_relu(const float* qkv, int64_t ld_qkv, float* out, int64_t ld_out, int64_t n_img,
+                                        int64_t HW, int64_t heads, int64_t head_dim, float eps, void* stream);
+DFOT_API int dfot_dwconv3x3_glu_bf16(const void* x_bf16, const float* w, const float* b, void* out_bf16, int64_t n_img,
+                                     int64_t H, int64_t W, int64_t Ch, void* stream);
+DFOT_API int dfot_rmsnorm_affine(const float* x, int64_t ld_x, const float* w, const float* b, float eps,
+                                 const float* resid, int relu, float* out_f32, void* out_bf16, int64_t M, int64_t C,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

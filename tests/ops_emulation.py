@@ -271,7 +271,52 @@ def softmax_rows_bf16(s, p, scale=1.0):
     p.copy_(torch.softmax(s.float() * scale, -1).to(BF))
 
 
-ALL = ["cast_bf16", "patchify_bf16", "unpatchify", "gemm_bf16", "conv3x3_bf16", "groupnorm_stats", "groupnorm_silu_bf16",
+# ---------------------------------------------------------------- DC-AE decoder glue (csrc/dcae.cu)
+def relu_bf16(x):
+    x.copy_(F.relu(x.float()).to(BF))
+
+
+def pixel_shuffle2x(conv, C, n_img, H, W, shortcut=None, repeats=1, out_f32=None, out_bf16=None):
+    y = conv[:, : 4 * C].reshape(n_img, H, W, 4 * C).float()
+    if shortcut is not None:
+        y = y + shortcut.reshape(n_img, H, W, -1).repeat_interleave(repeats, dim=-1)
+    y = F.pixel_shuffle(y.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)          # [n, 2H, 2W, C]
+    if out_f32 is not None:
+        out_f32.copy_(y.reshape(out_f32.shape))
+    if out_bf16 is not None:
+        out_bf16.copy_(y.reshape(out_bf16.shape).to(BF))
+
+
+def linear_attention_relu(qkv, out, n_img, HW, heads, head_dim, eps=1e-15):
+    d = head_dim
+    t = qkv[:, : 3 * heads * d].float().reshape(n_img, HW, heads, 3 * d)
+    q, k, v = F.relu(t[..., :d]), F.relu(t[..., d:2 * d]), t[..., 2 * d:]
+    v1 = torch.cat([v, torch.ones_like(v[..., :1])], -1)
+    kv = torch.einsum("ntha,nthb->nhab", k, v1)
+    o = torch.einsum("ntha,nhab->nthb", q, kv)
+    out[:, : heads * d] = (o[..., :d] / (o[..., d:] + eps)).reshape(n_img * HW, heads * d)
+
+
+def dwconv3x3_glu_bf16(x, w, b, out, n_img, H, W, Ch):
+    xi = x.float().reshape(n_img, H, W, 2 * Ch).permute(0, 3, 1, 2)
+    y = F.conv2d(xi, w.reshape(2 * Ch, 1, 3, 3), b, padding=1, groups=2 * Ch)
+    h, gate = torch.chunk(y, 2, dim=1)
+    out.copy_((h * F.silu(gate)).permute(0, 2, 3, 1).reshape(out.shape).to(BF))
+
+
+def rmsnorm_affine(x, w, b, eps, resid=None, relu=False, out_f32=None, out_bf16=None):
+    y = x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + eps) * w + b
+    if resid is not None:
+        y = y + resid
+    if relu:
+        y = F.relu(y)
+    if out_f32 is not None:
+        out_f32.copy_(y)
+    if out_bf16 is not None:
+        out_bf16.copy_(y.to(BF))
+
+
+ALL = ["relu_bf16", "pixel_shuffle2x", "linear_attention_relu", "dwconv3x3_glu_bf16", "rmsnorm_affine", "cast_bf16", "patchify_bf16", "unpatchify", "gemm_bf16", "conv3x3_bf16", "groupnorm_stats", "groupnorm_silu_bf16",
        "rmsnorm_film_bf16", "qk_norm_rope", "attention", "avgpool2x2", "sub_bf16", "upsample2x_add", "pose_ray_patches",
        "noise_features", "conv3d_causal_bf16", "groupnorm_stats_strided", "groupnorm_apply_bf16",
        "vae_upsample2x_bf16", "upsample2x_nearest_bf16", "vae_fill_pad_frames", "softmax_rows_bf16", "adaln_layernorm",
