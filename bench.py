@@ -86,6 +86,15 @@ def dmlab_cfg(sampling_timesteps=50, frames=36, guidance_scale=None):
     return cfg
 
 
+# configurations/algorithm/dc_ae_preprocessor.yaml (the `vae` node of dmlab_video_generation.yaml), decode side
+DCAE_DMLAB_CFG = dict(in_channels=3, latent_channels=32, attention_head_dim=32, scaling_factor=0.2889,
+                      decoder_block_types=["ResBlock", "ResBlock", "ResBlock", "EfficientViTBlock"],
+                      decoder_block_out_channels=[128, 256, 512, 512], decoder_layers_per_block=[0, 5, 10, 2],
+                      decoder_norm_types=["batch_norm", "batch_norm", "batch_norm", "rms_norm"],
+                      decoder_act_fns=["relu", "relu", "relu", "silu"], decoder_qkv_multiscales=[[], [], [], []],
+                      upsample_block_type="pixel_shuffle")
+
+
 def re10k_cfg(sampling_timesteps=50, guidance_scale=4.0):
     """`dataset=realestate10k_mini algorithm=dfot_video_pose @diffusion/continuous dataset.context_length=1
     dataset.n_frames=8 ...history_guidance.name=vanilla +guidance_scale=4.0` (README.md:74) resolved by hand from
@@ -541,8 +550,9 @@ def main():
                     help="force the running-maximum attention path (what trained q/k-norm weights with a score bound > 96 "
                          "would select) instead of the bounded-score path the random-init weights allow")
     ap.add_argument("--decode", action="store_true",
-                    help="k600: VideoVAE-decode the sampled latents to 128x128 frames inside the e2e region (random-init "
-                         "decoder, hidden 128, z 16) and report the decode on its own; `value` stays sampling-only (SURVEY 8d)")
+                    help="k600 / dmlab: decode the sampled latents to frames inside the e2e region (random-init VideoVAE: "
+                         "hidden 128, z 16 / DC-AE: dc_ae_preprocessor.yaml) and report the decode on its own; `value` stays "
+                         "sampling-only (SURVEY 8d)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -594,10 +604,14 @@ def main():
     algo = make_weights(cfg, 0).to(dev).eval()
     B = wl.batch
     if args.decode:
-        assert wl.name == "k600", "--decode applies to the latent-video workload (k600)"
-        from dfot_b200.algorithms.vae import VideoVAE
+        assert wl.name in ("k600", "dmlab"), "--decode applies to the latent workloads (k600: VideoVAE, dmlab: DC-AE)"
         torch.manual_seed(1)
-        algo.vae = VideoVAE(hidden_size=128, z_channels=16, embed_dim=16, hidden_size_mult=(1, 2, 4, 4)).to(dev)
+        if wl.name == "k600":
+            from dfot_b200.algorithms.vae import VideoVAE
+            algo.vae = VideoVAE(hidden_size=128, z_channels=16, embed_dim=16, hidden_size_mult=(1, 2, 4, 4)).to(dev)
+        else:
+            from dfot_b200.algorithms.vae import MyAutoencoderDC
+            algo.vae = MyAutoencoderDC(DCAE_DMLAB_CFG).to(dev)
     xs_host, conds_host = wl.inputs(rank)
     if strong and world > 1:
         from dfot_b200 import distributed as D
@@ -783,8 +797,10 @@ def main():
             n_fr = B * world * vids_host.shape[1]
             line["vae_decode"] = dict(ms_per_batch=ms_decode, decoded_frames_per_sec=n_fr / ms_decode * 1e3,
                                       video_shape=list(vids_host.shape), vae_batch_size=cfg["vae"]["batch_size"],
-                                      note="VideoVAE decoder (hidden 128, mult 1-2-4-4, z 16, random init); e2e includes "
-                                           "it, `value` does not (SURVEY 8d excludes the decode)")
+                                      note=("VideoVAE decoder (hidden 128, mult 1-2-4-4, z 16, random init)" if wl.name == "k600"
+                                            else "DC-AE decoder (dc_ae_preprocessor.yaml: 128/256/512/512 channels, 17 blocks, "
+                                                 "random init)") + "; e2e includes it, `value` does not (SURVEY 8d excludes "
+                                           "the decode)")
         assert bool(algo.diffusion_model.model.use_cuda_graph) == config["cuda_graph"]
         if not args.skip_parity and world == 1 and wl.name != "re10k_long":
             line["parity"] = parity_check(wl, dev)

@@ -459,8 +459,9 @@ def pixel_shuffle2x(conv, C, n_img, H, W, shortcut=None, repeats=1, out_f32=None
 
 
 def linear_attention_relu(qkv, out, n_img, HW, heads, head_dim, eps=1e-15):
-    _need(qkv, torch.float32, "qkv")
-    _need(out, torch.float32, "out")
+    for t, n in ((qkv, "qkv"), (out, "out")):
+        if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2 or t.stride(-1) != 1:
+            raise RuntimeError(f"dfot_b200: `{n}` must be a CUDA f32 matrix with unit inner stride")
     if qkv.shape[0] != n_img * HW or out.shape[0] != n_img * HW:
         raise RuntimeError("dfot_b200: linear_attention_relu expects [n_img*HW, ...] matrices")
     rc = _abi.lib().dfot_linear_attention_relu(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), n_img, HW, heads,
