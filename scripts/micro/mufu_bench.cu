@@ -1,4 +1,4 @@
-// Micro-benchmark: exp2 throughput per SM — MUFU.EX2 (f32), packed bf16x2 ex2, and an FMA-pipe polynomial emulation.
+// Micro-benchmark: exp2 throughput per SM — MUFU.EX2 (f32), packed bf16x2 / f16x2 ex2, and an FMA-pipe polynomial emulation.
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mufu_bench mufu_bench.cu
 #include <cstdio>
 #include <cstdint>
@@ -8,6 +8,7 @@
 constexpr int ITERS = 4096, UNROLL = 8;
 
 __device__ __forceinline__ float ex2f(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t ex2h2(uint32_t x) { uint32_t y; asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
 __device__ __forceinline__ uint32_t ex2bf2(uint32_t x) { uint32_t y; asm volatile("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
 // 2^x for x <= 0 on the FMA/ALU pipes: round-to-nearest split + degree-3 minimax on [-0.5, 0.5] + exponent add
 __device__ __forceinline__ float ex2poly(float x) {
@@ -30,6 +31,7 @@ __global__ void k(float* out, float seed) {
     for (int i = 0; i < UNROLL; ++i) {
       if (MODE == 0) v[i] = ex2f(v[i]) - 1.0f;
       else if (MODE == 1) u[i] = ex2bf2(u[i]) ^ 0x80008000u;
+      else if (MODE == 3) u[i] = ex2h2(u[i]) ^ 0x80008000u;
       else v[i] = ex2poly(v[i]) - 1.0f;
     }
   }
@@ -58,5 +60,6 @@ int main() {
   run<0>("ex2.approx.ftz.f32", 1);
   run<1>("ex2.approx.ftz.bf16x2", 2);
   run<2>("poly3 on FMA/ALU pipes", 1);
+  run<3>("ex2.approx.f16x2", 2);
   return 0;
 }
