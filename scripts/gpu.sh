@@ -30,7 +30,7 @@ prof_cmd() { # name -> kernel regex + command
     gemm)           RX="gemm2?_bf16"; CMD="python scripts/bench_one.py gemm 3" ;;
     gemm_l2)        RX="gemm2?_bf16"; CMD="python scripts/bench_one.py gemm_l2 3" ;;
     gn_silu)        RX=gn_silu; CMD="python scripts/bench_one.py gn_silu 3" ;;
-    gn_stats)       RX=groupnorm_stats; CMD="python scripts/bench_one.py gn_stats 3" ;;
+    gn_stats)       RX=gn_stats; CMD="python scripts/bench_one.py gn_stats 3" ;;
     sampler)        RX=sampler; CMD="python scripts/bench_one.py sampler 3" ;;
     rmsnorm)        RX=rmsnorm_film; CMD="python scripts/bench_one.py rmsnorm 3" ;;
     rmsnorm1152)    RX=rmsnorm_film; CMD="python scripts/bench_one.py rmsnorm1152 3" ;;
