@@ -30,6 +30,20 @@ constexpr int kThreads = 64 + 32 * kSoftmaxWarps;   // TMA warp, MMA warp, 2 sof
 constexpr int kAtomBytes = 128 * 128;   // one 128-row x 128-byte swizzle plane (64 bf16 wide)
 constexpr uint32_t kSuspendHintNs = 2000;
 
+// Debug build only (-DDFOT_ATTN_TRACE, scripts/attn_trace.py): per-warp clock64 stamps of the phase boundaries of CTA 0
+#ifdef DFOT_ATTN_TRACE
+__device__ unsigned long long g_trace[16 * 2048];
+#define DFOT_TRACE_DECL uint32_t tr_n = 0
+#define DFOT_TRACE(tag)                                                                                    \
+  do {                                                                                                     \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && tr_n < 2048)                                         \
+      g_trace[(threadIdx.x >> 5) * 2048 + tr_n++] = ((unsigned long long)clock64() << 8) | (unsigned)(tag); \
+  } while (0)
+#else
+#define DFOT_TRACE_DECL
+#define DFOT_TRACE(tag)
+#endif
+
 // ------------------------------------------------------------------ PTX wrappers (same idioms as the GEMM)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -293,7 +307,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params 
   const uint32_t tmem_slot = bars + 8u * N_BARS;
   const uint32_t s_xchg = bars + 160u;               // float [2 (parity)][2 (warpgroup)][128 rows]: max / sum exchange
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;   // (uniform for the compiler: see elect_one_sync)
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     for (int i = 0; i < N_BARS; ++i) {
@@ -323,51 +337,63 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params 
   };
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (all lanes walk the loop; the copies are issued under elect.sync) ===========
+    {
       uint32_t g = 0, it = 0;                        // global KV-tile counter, item counter
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
         int r, h, qt;
         item_coord(item, r, h, qt);
         const int row0 = r * p.Ntok;
         mbar_wait(bar(Q_EMPTY), (it & 1u) ^ 1u);
-        mbar_expect_tx(bar(Q_FULL), TILE_BYTES);
+        if (elect_one_sync()) {
+          mbar_expect_tx(bar(Q_FULL), TILE_BYTES);
 #pragma unroll
-        for (int a = 0; a < ATOMS; ++a) tma_load_3d(sQ + a * kAtomBytes, &tmap, bar(Q_FULL), a * 64, h, row0 + qt * BQ);
+          for (int a = 0; a < ATOMS; ++a) tma_load_3d(sQ + a * kAtomBytes, &tmap, bar(Q_FULL), a * 64, h, row0 + qt * BQ);
+        }
+        __syncwarp();
         for (int j = 0; j < n_kv; ++j, ++g) {
           const uint32_t st = g & 1u, ph = (g >> 1) & 1u;
           mbar_wait(bar(K_EMPTY + st), ph ^ 1u);
-          mbar_expect_tx(bar(K_FULL + st), TILE_BYTES);
+          if (elect_one_sync()) {
+            mbar_expect_tx(bar(K_FULL + st), TILE_BYTES);
 #pragma unroll
-          for (int a = 0; a < ATOMS; ++a)
-            tma_load_3d(sK + st * TILE_BYTES + a * kAtomBytes, &tmap, bar(K_FULL + st), a * 64, p.heads + h,
-                        row0 + j * BKV);
+            for (int a = 0; a < ATOMS; ++a)
+              tma_load_3d(sK + st * TILE_BYTES + a * kAtomBytes, &tmap, bar(K_FULL + st), a * 64, p.heads + h,
+                          row0 + j * BKV);
+          }
+          __syncwarp();
           mbar_wait(bar(V_EMPTY + st), ph ^ 1u);
-          mbar_expect_tx(bar(V_FULL + st), TILE_BYTES);
+          if (elect_one_sync()) {
+            mbar_expect_tx(bar(V_FULL + st), TILE_BYTES);
 #pragma unroll
-          for (int a = 0; a < ATOMS; ++a)
-            tma_load_3d(sV + st * TILE_BYTES + a * kAtomBytes, &tmap, bar(V_FULL + st), a * 64, 2 * p.heads + h,
-                        row0 + j * BKV);
+            for (int a = 0; a < ATOMS; ++a)
+              tma_load_3d(sV + st * TILE_BYTES + a * kAtomBytes, &tmap, bar(V_FULL + st), a * 64, 2 * p.heads + h,
+                          row0 + j * BKV);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, tcgen05 instructions under elect.sync) =====================
+    {
       uint32_t g = 0, it = 0;
       auto issue_s = [&](uint32_t gt, bool last_of_item) {       // S = Q · K^T for global tile gt
         const uint32_t st = gt & 1u, ph = (gt >> 1) & 1u;
         mbar_wait(bar(K_FULL + st), ph);
         tc_fence_after();
-        const uint32_t d = tmem_base + TMEM_S0 + st * 128u;
+        if (elect_one_sync()) {
+          const uint32_t d = tmem_base + TMEM_S0 + st * 128u;
 #pragma unroll
-        for (int s = 0; s < KS_QK; ++s) {
-          const uint32_t off = (uint32_t)(s >> 2) * kAtomBytes + (uint32_t)(s & 3) * 32u;
-          umma_bf16(d, desc_kmajor(sQ + off), desc_kmajor(sK + st * TILE_BYTES + off), IDESC_S, s > 0 ? 1u : 0u);
+          for (int s = 0; s < KS_QK; ++s) {
+            const uint32_t off = (uint32_t)(s >> 2) * kAtomBytes + (uint32_t)(s & 3) * 32u;
+            umma_bf16(d, desc_kmajor(sQ + off), desc_kmajor(sK + st * TILE_BYTES + off), IDESC_S, s > 0 ? 1u : 0u);
+          }
+          umma_commit(bar(K_EMPTY + st));
+          umma_commit(bar(S_FULL + st));
+          if (last_of_item) umma_commit(bar(Q_EMPTY));
         }
-        umma_commit(bar(K_EMPTY + st));
-        umma_commit(bar(S_FULL + st));
-        if (last_of_item) umma_commit(bar(Q_EMPTY));
+        __syncwarp();
       };
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
         mbar_wait(bar(Q_FULL), it & 1u);
@@ -381,15 +407,18 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params 
           mbar_wait(bar(O_EMPTY + st), ph ^ 1u);     // softmax consumed PV of tile gt-2
           mbar_wait(bar(P_FULL + st), ph);           // P_j is in shared memory (and S_j has been read)
           tc_fence_after();
-          const uint32_t d = tmem_base + TMEM_PV0 + st * 128u;
+          if (elect_one_sync()) {
+            const uint32_t d = tmem_base + TMEM_PV0 + st * 128u;
 #pragma unroll
-          for (int s = 0; s < KS_PV; ++s) {
-            const uint32_t a_off = (uint32_t)(s >> 2) * kAtomBytes + (uint32_t)(s & 3) * 32u;   // 16 keys along K
-            umma_bf16(d, desc_kmajor(sP + st * P_BYTES + a_off),
-                      desc_mnmajor(sV + st * TILE_BYTES + (uint32_t)s * 2048u, kAtomBytes), IDESC_PV, s > 0 ? 1u : 0u);
+            for (int s = 0; s < KS_PV; ++s) {
+              const uint32_t a_off = (uint32_t)(s >> 2) * kAtomBytes + (uint32_t)(s & 3) * 32u;   // 16 keys along K
+              umma_bf16(d, desc_kmajor(sP + st * P_BYTES + a_off),
+                        desc_mnmajor(sV + st * TILE_BYTES + (uint32_t)s * 2048u, kAtomBytes), IDESC_PV, s > 0 ? 1u : 0u);
+            }
+            umma_commit(bar(V_EMPTY + st));
+            umma_commit(bar(PV_DONE + st));
           }
-          umma_commit(bar(V_EMPTY + st));
-          umma_commit(bar(PV_DONE + st));
+          __syncwarp();
           if (j + 2 < n_kv) issue_s(gt + 2, j + 3 == n_kv);
         }
         g += n_kv;
@@ -565,7 +594,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
   // issue/latency-bound before it is MUFU-bound (XU pipe 70 % busy), so extra FMA-pipe instructions do not pay: off.
 #ifndef DFOT_ATTN_POLY_FIRST
 #define DFOT_ATTN_POLY_FIRST 0x00
-#define DFOT_ATTN_POLY_SECOND 0x00
+#define DFOT_ATTN_POLY_SECOND 0x55
 #endif
   constexpr uint32_t kPolyFirst = SEP_P ? DFOT_ATTN_POLY_FIRST : 0u, kPolySecond = SEP_P ? DFOT_ATTN_POLY_SECOND : 0u;
   // bounded-score path (2 instead of 3 base instructions per score): polynomial share of the score pairs.  Measured
@@ -590,6 +619,15 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
   // 2 / 3: bounded-score path 903 / 901 / 900 / 824 TFLOP/s (its exp2 phase is short enough that the stores at the end
   // lengthen the tile), running-max path 788 / 775 / 761 / 844 (there the wait at the very end never stalls).
   constexpr int kPvWaitChunk = DFOT_ATTN_PV_WAIT_CHUNK >= 0 ? DFOT_ATTN_PV_WAIT_CHUNK : (NOMAX ? 0 : 3);
+  // Phase stagger of the two query tiles (SEP_P only).  The warps of tile 0 and tile 1 that share a scheduler also share
+  // its MUFU; started together they stay in lockstep — both in the exp2 phase (each at half the MUFU rate), then both in
+  // the MUFU-free phase (TMEM load, barrier hand-offs, P stores) — and an offset between them, once there, persists
+  // (profiles/r02_ncu_attn64_stalls.txt: exp2 phase = 2 x its solo length, XU pipe idle a third of the time).  So tile 1
+  // starts every work item one exp2 phase late: its first tile waits until tile 0 has published its first P.
+#ifndef DFOT_ATTN_STAGGER
+#define DFOT_ATTN_STAGGER 0
+#endif
+  constexpr int kStagger = SEP_P ? DFOT_ATTN_STAGGER : 0;   // 0 off, 1 after tile 0's first P, 2 after half of it
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
@@ -602,16 +640,16 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
   const uint32_t sV = sK + 2 * TILE_BYTES;           // 2 stages
   const uint32_t bars = sV + 2 * TILE_BYTES;
   enum { Q_FULL = 0, Q_EMPTY = 1, K_FULL = 2, K_EMPTY = 4, V_FULL = 6, V_EMPTY = 8, S_FULL = 10, P_FULL = 12,
-         O_DONE = 14, O_FREE = 16, S_FREE = 18, PV_DONE = 20, N_BARS = 22 };
+         O_DONE = 14, O_FREE = 16, S_FREE = 18, PV_DONE = 20, STAGGER = 22, N_BARS = 23 };
   auto bar = [&](int id) { return bars + 8u * id; };
   const uint32_t tmem_slot = bars + 8u * N_BARS;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;   // (uniform for the compiler: see elect_one_sync)
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     for (int i = 0; i < N_BARS; ++i) {
       const bool from_softmax = (i >= P_FULL && i < P_FULL + 2) || (i >= O_FREE && i < O_FREE + 2) ||
-                                (i >= S_FREE && i < S_FREE + 2);
+                                (i >= S_FREE && i < S_FREE + 2) || i == STAGGER;
       const bool from_both_issuers = i == Q_EMPTY || (i >= K_EMPTY && i < K_EMPTY + 2) || (i >= V_EMPTY && i < V_EMPTY + 2);
       // softmax → one arrival per warp of the tile's warpgroup; ring slots → one per MMA issuer; else one producer
       mbar_init(bar(i), from_softmax ? 4 : ((DUAL && from_both_issuers) ? 2 : 1));
@@ -651,34 +689,43 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (all lanes walk the loop; the copies are issued under elect.sync) ===========
+    {
       uint32_t g = 0, it = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
         int r, h, q0, nt;
         item_coord(item, r, h, q0, nt);
         const int row0 = r * p.Ntok;
         mbar_wait(bar(Q_EMPTY), (it & 1u) ^ 1u);
-        mbar_expect_tx(bar(Q_FULL), 2 * TILE_BYTES);
+        if (elect_one_sync()) {
+          mbar_expect_tx(bar(Q_FULL), 2 * TILE_BYTES);
 #pragma unroll
-        for (int t = 0; t < 2; ++t)     // (the second slot of a single-tile item is loaded too and simply not used)
+          for (int t = 0; t < 2; ++t)   // (the second slot of a single-tile item is loaded too and simply not used)
 #pragma unroll
-          for (int a = 0; a < ATOMS; ++a)
-            tma_load_3d(sQ + t * TILE_BYTES + a * kAtomBytes, &tmap, bar(Q_FULL), a * 64, h, row0 + (q0 + t) * BQ);
+            for (int a = 0; a < ATOMS; ++a)
+              tma_load_3d(sQ + t * TILE_BYTES + a * kAtomBytes, &tmap, bar(Q_FULL), a * 64, h, row0 + (q0 + t) * BQ);
+        }
+        __syncwarp();
         for (int j = 0; j < n_kv; ++j, ++g) {
           const uint32_t st = g & 1u, ph = (g >> 1) & 1u;
           mbar_wait(bar(K_EMPTY + st), ph ^ 1u);
-          mbar_expect_tx(bar(K_FULL + st), TILE_BYTES);
+          if (elect_one_sync()) {
+            mbar_expect_tx(bar(K_FULL + st), TILE_BYTES);
 #pragma unroll
-          for (int a = 0; a < ATOMS; ++a)
-            tma_load_3d(sK + st * TILE_BYTES + a * kAtomBytes, &tmap, bar(K_FULL + st), a * 64, p.heads + h,
-                        row0 + j * BKV);
+            for (int a = 0; a < ATOMS; ++a)
+              tma_load_3d(sK + st * TILE_BYTES + a * kAtomBytes, &tmap, bar(K_FULL + st), a * 64, p.heads + h,
+                          row0 + j * BKV);
+          }
+          __syncwarp();
           mbar_wait(bar(V_EMPTY + st), ph ^ 1u);
-          mbar_expect_tx(bar(V_FULL + st), TILE_BYTES);
+          if (elect_one_sync()) {
+            mbar_expect_tx(bar(V_FULL + st), TILE_BYTES);
 #pragma unroll
-          for (int a = 0; a < ATOMS; ++a)
-            tma_load_3d(sV + st * TILE_BYTES + a * kAtomBytes, &tmap, bar(V_FULL + st), a * 64, 2 * p.heads + h,
-                        row0 + j * BKV);
+            for (int a = 0; a < ATOMS; ++a)
+              tma_load_3d(sV + st * TILE_BYTES + a * kAtomBytes, &tmap, bar(V_FULL + st), a * 64, 2 * p.heads + h,
+                          row0 + j * BKV);
+          }
+          __syncwarp();
         }
       }
     }
@@ -691,9 +738,10 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
     //            aliased: it is issued right after PV_t(j) (tensor-core ops of one thread execute in issue order);
     //   PV_t(j)  needs V(j), P_t(j) (P_FULL) and, for j == 0, the previous item's epilogue to have drained O_t (O_FREE).
     // K / V / Q ring slots are released by BOTH issuers (barrier count 2).
-    if (lane == 0) {
+    {
       const int t = warp - 1;
       uint32_t g = 0, it = 0, n_p = 0, n_f = 0, n_o = 0;
+      DFOT_TRACE_DECL;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
         int r, h, q0, nt;
         item_coord(item, r, h, q0, nt);
@@ -703,33 +751,43 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
           for (int j = 0; j < n_kv; ++j) {
             const uint32_t gt = g + j, st = gt & 1u, ph = (gt >> 1) & 1u;
             mbar_wait(bar(K_FULL + st), ph);
-            mbar_arrive(bar(K_EMPTY + st));
+            if (lane == 0) mbar_arrive(bar(K_EMPTY + st));
             mbar_wait(bar(V_FULL + st), ph);
-            mbar_arrive(bar(V_EMPTY + st));
+            if (lane == 0) mbar_arrive(bar(V_EMPTY + st));
           }
-          mbar_arrive(bar(Q_EMPTY));
+          if (lane == 0) mbar_arrive(bar(Q_EMPTY));
           g += n_kv;
           continue;
         }
         auto issue_s = [&](uint32_t st) {              // S_t = Q_t · K^T (K stage st)
-          const uint32_t d = tmem_base + TMEM_S + (uint32_t)t * 128u;
+          if (elect_one_sync()) {
+            const uint32_t d = tmem_base + TMEM_S + (uint32_t)t * 128u;
 #pragma unroll
-          for (int s = 0; s < KS_QK; ++s) {
-            const uint32_t off = (uint32_t)(s >> 2) * kAtomBytes + (uint32_t)(s & 3) * 32u;
-            umma_bf16(d, desc_kmajor(sQ + t * TILE_BYTES + off), desc_kmajor(sK + st * TILE_BYTES + off), IDESC_S,
-                      s > 0 ? 1u : 0u);
+            for (int s = 0; s < KS_QK; ++s) {
+              const uint32_t off = (uint32_t)(s >> 2) * kAtomBytes + (uint32_t)(s & 3) * 32u;
+              umma_bf16(d, desc_kmajor(sQ + t * TILE_BYTES + off), desc_kmajor(sK + st * TILE_BYTES + off), IDESC_S,
+                        s > 0 ? 1u : 0u);
+            }
+            umma_commit(bar(S_FULL + t));
+            umma_commit(bar(K_EMPTY + st));
           }
-          umma_commit(bar(S_FULL + t));
-          umma_commit(bar(K_EMPTY + st));
+          __syncwarp();
         };
-        auto issue_pv = [&](uint32_t st, bool first) {  // O_t (+)= P_t · V (V stage st), A operand from TMEM
-          const uint32_t d = tmem_base + TMEM_O + (uint32_t)t * O_STRIDE;
-          const uint32_t a = tmem_base + TMEM_P + (uint32_t)t * P_STRIDE;
+        // O_t (+)= P_t · V (V stage st), A operand from TMEM; then the step's commits
+        auto issue_pv = [&](uint32_t st, bool first, bool more, bool last_of_item) {
+          if (elect_one_sync()) {
+            const uint32_t d = tmem_base + TMEM_O + (uint32_t)t * O_STRIDE;
+            const uint32_t a = tmem_base + TMEM_P + (uint32_t)t * P_STRIDE;
 #pragma unroll
-          for (int s = 0; s < KS_PV; ++s)
-            umma_bf16_ts(d, a + (uint32_t)(8 * s), desc_mnmajor(sV + st * TILE_BYTES + (uint32_t)s * 2048u, kAtomBytes),
-                         IDESC_PV, (first && s == 0) ? 0u : 1u);
-          umma_commit(bar(V_EMPTY + st));
+            for (int s = 0; s < KS_PV; ++s)
+              umma_bf16_ts(d, a + (uint32_t)(8 * s), desc_mnmajor(sV + st * TILE_BYTES + (uint32_t)s * 2048u, kAtomBytes),
+                           IDESC_PV, (first && s == 0) ? 0u : 1u);
+            umma_commit(bar(V_EMPTY + st));
+            if (!more) umma_commit(bar(O_DONE + t));
+            else if constexpr (SEP_P) umma_commit(bar(PV_DONE + t));
+            if (last_of_item) umma_commit(bar(Q_EMPTY));
+          }
+          __syncwarp();
         };
         {
           const uint32_t st = g & 1u, ph = (g >> 1) & 1u;
@@ -744,34 +802,42 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
           const bool more = j + 1 < n_kv;
           if (SEP_P && more) {
             mbar_wait(bar(K_FULL + stn), phn);
+            DFOT_TRACE(10);
             mbar_wait_fast(bar(S_FREE + t), n_f++ & 1u);
             tc_fence_after();
+            DFOT_TRACE(11);
             issue_s(stn);
+            DFOT_TRACE(12);
           }
           mbar_wait(bar(V_FULL + st), ph);
+          DFOT_TRACE(13);
           mbar_wait_fast(bar(P_FULL + t), n_p++ & 1u);
           tc_fence_after();
-          issue_pv(st, j == 0);
-          if (!more) umma_commit(bar(O_DONE + t));
-          else if constexpr (SEP_P) umma_commit(bar(PV_DONE + t));
+          DFOT_TRACE(14);
+          issue_pv(st, j == 0, more, !more);
+          DFOT_TRACE(15);
           if (!SEP_P && more) {
             mbar_wait(bar(K_FULL + stn), phn);
             tc_fence_after();
             issue_s(stn);
           }
         }
-        umma_commit(bar(Q_EMPTY));
         ++n_o;
         g += n_kv;
       }
     }
     } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer of the aliased layout (head_dim > 64): one warp drives both query tiles ==========
+    // Issue order  S0(0) S1(0) | PV0(j) S0(j+1) PV1(j) S1(j+1) ...: tensor-core ops of one thread execute in issue order,
+    // which is what makes the S/P aliasing safe without extra barriers.
+    {
       uint32_t g = 0, it = 0;
       uint32_t n_p[2] = {0, 0};                      // P_FULL phases consumed per tile
-      uint32_t n_f[2] = {0, 0};                      // S_FREE phases consumed per tile (SEP_P)
       uint32_t n_o[2] = {0, 0};                      // items in which tile t was active (O_FREE phases)
+      auto one = [&](auto&& f) {                     // f() by one elected lane, warp-uniform control flow around it
+        if (elect_one_sync()) f();
+        __syncwarp();
+      };
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
         int r, h, q0, nt;
         item_coord(item, r, h, q0, nt);
@@ -799,9 +865,11 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
           const uint32_t st = g & 1u, ph = (g >> 1) & 1u;
           mbar_wait(bar(K_FULL + st), ph);
           tc_fence_after();
-          issue_s(0, st);
-          if (has1) issue_s(1, st);
-          umma_commit(bar(K_EMPTY + st));
+          one([&] {
+            issue_s(0, st);
+            if (has1) issue_s(1, st);
+            umma_commit(bar(K_EMPTY + st));
+          });
         }
         // the epilogue of the previous item must have drained O_t before the first (overwriting) PV
         if (n_o[0] > 0) mbar_wait(bar(O_FREE + 0), (n_o[0] - 1) & 1u);
@@ -810,53 +878,29 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
           const uint32_t gt = g + j, st = gt & 1u, ph = (gt >> 1) & 1u;
           const uint32_t gn = gt + 1, stn = gn & 1u, phn = (gn >> 1) & 1u;
           const bool more = j + 1 < n_kv;
-          if constexpr (SEP_P) {
-            // S_t(j+1) only needs the S_t buffer back (softmax holds S_t(j) in registers): it runs under the exp2 phase
-            if (more) {
-              mbar_wait(bar(K_FULL + stn), phn);
-              mbar_wait_fast(bar(S_FREE + 0), n_f[0]++ & 1u);
-              tc_fence_after();
-              issue_s(0, stn);
-            }
-            mbar_wait(bar(V_FULL + st), ph);
-            mbar_wait_fast(bar(P_FULL + 0), n_p[0]++ & 1u);
-            tc_fence_after();
+          mbar_wait(bar(V_FULL + st), ph);
+          if (more) mbar_wait(bar(K_FULL + stn), phn);         // (loaded long ago: K runs a whole step ahead)
+          mbar_wait_fast(bar(P_FULL + 0), n_p[0]++ & 1u);      // P_0(j) is in TMEM (O_0 rescaled if it had to be)
+          tc_fence_after();
+          one([&] {
             issue_pv(0, st, j == 0);
-            umma_commit(bar((more ? PV_DONE : O_DONE) + 0));
-            if (has1) {
-              if (more) {
-                mbar_wait_fast(bar(S_FREE + 1), n_f[1]++ & 1u);
-                tc_fence_after();
-                issue_s(1, stn);
-              }
-              mbar_wait_fast(bar(P_FULL + 1), n_p[1]++ & 1u);
-              tc_fence_after();
-              issue_pv(1, st, j == 0);
-              umma_commit(bar((more ? PV_DONE : O_DONE) + 1));
+            if (more) issue_s(0, stn); else umma_commit(bar(O_DONE + 0));
+            if (!has1) {
+              umma_commit(bar(V_EMPTY + st));
+              if (more) umma_commit(bar(K_EMPTY + stn)); else umma_commit(bar(Q_EMPTY));
             }
-          } else {
-            mbar_wait(bar(V_FULL + st), ph);
-            mbar_wait_fast(bar(P_FULL + 0), n_p[0]++ & 1u);  // P_0(j) is in TMEM (O_0 rescaled if it had to be)
+          });
+          if (has1) {
+            mbar_wait_fast(bar(P_FULL + 1), n_p[1]++ & 1u);
             tc_fence_after();
-            issue_pv(0, st, j == 0);
-            if (more) {
-              mbar_wait(bar(K_FULL + stn), phn);
-              tc_fence_after();
-              issue_s(0, stn);
-            } else {
-              umma_commit(bar(O_DONE + 0));
-            }
-            if (has1) {
-              mbar_wait_fast(bar(P_FULL + 1), n_p[1]++ & 1u);
-              tc_fence_after();
+            one([&] {
               issue_pv(1, st, j == 0);
               if (more) issue_s(1, stn); else umma_commit(bar(O_DONE + 1));
-            }
+              umma_commit(bar(V_EMPTY + st));
+              if (more) umma_commit(bar(K_EMPTY + stn)); else umma_commit(bar(Q_EMPTY));
+            });
           }
-          umma_commit(bar(V_EMPTY + st));
-          if (more) umma_commit(bar(K_EMPTY + stn));
         }
-        umma_commit(bar(Q_EMPTY));
         ++n_o[0];
         if (has1) ++n_o[1];
         g += n_kv;
@@ -873,21 +917,26 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
     const uint32_t t_s = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_S + (uint32_t)t * 128u;
     const uint32_t t_p = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_P + (uint32_t)t * P_STRIDE;
     const uint32_t t_o = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_O + (uint32_t)t * O_STRIDE;
-    uint32_t n_s = 0, n_items = 0, n_pv = 0;
+    uint32_t n_s = 0, n_items = 0, n_pv = 0, it_all = 0;
+    DFOT_TRACE_DECL;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       int r, h, q0, nt;
       item_coord(item, r, h, q0, nt);
       const int qt = q0 + t;
+      const uint32_t it_cur = it_all++;              // tile 0 is active in every item: one STAGGER phase per item
       if (t >= nt || qt * BQ >= p.Ntok) continue;    // single-tile item, or tile 1 of the last pair outside the sample
+      if (kStagger != 0 && t == 1) mbar_wait_fast(bar(STAGGER), it_cur & 1u);
       float m_used = 0.f, l_run = 0.f;
       uint32_t v[4][32];                             // the 128 scores of this row stay in registers
       // pull S_t(jj) into registers (all four 32-column loads in flight), hand the buffer back, mask, row maximum
       auto load_begin = [&]() {
         mbar_wait_fast(bar(S_FULL + t), n_s++ & 1u);
         tc_fence_after();
+        DFOT_TRACE(1);
       };
       auto load_end = [&](int jj) -> float {
         tmem_ld_wait();
+        DFOT_TRACE(2);
         if constexpr (SEP_P) {                       // hand the S_t buffer back: S_t(jj+1) may be computed now
           if (jj + 1 < n_kv) {
             tc_fence_before();
@@ -965,8 +1014,10 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
               if constexpr (SEP_P) {
                 if (c == kPvWaitChunk) {
                   if (j > 0) {
+                    DFOT_TRACE(3);
                     mbar_wait_fast(bar(PV_DONE + t), n_pv++ & 1u);
                     tc_fence_after();
+                    DFOT_TRACE(4);
                   }
 #pragma unroll
                   for (int cc = 0; cc < kPvWaitChunk; ++cc) tmem_st_x16(t_p + 16 * cc, pka[cc]);
@@ -975,6 +1026,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
               } else {
                 tmem_st_x16(t_p + 16 * c, pk);
               }
+              if (kStagger == 2 && t == 0 && j == 0 && c == 1 && lane == 0) mbar_arrive(bar(STAGGER));
             }
           };
           if (p.Ntok - j * BKV >= BKV) exp_tile(std::true_type{});
@@ -986,7 +1038,11 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar(P_FULL + t));
+          if (lane == 0) {
+            mbar_arrive(bar(P_FULL + t));
+            if (kStagger == 1 && t == 0 && j == 0) mbar_arrive(bar(STAGGER));
+          }
+          DFOT_TRACE(5);
           continue;
         }
         // Lazy rescaling decision now (the exps below already use the new maximum); the O_t tile itself is rescaled
@@ -1035,8 +1091,10 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
             // store of P_t(j) — see the bounded-score path above for the placement of the wait.
             if (c == kPvWaitChunk) {
               if (j > 0) {
+                DFOT_TRACE(3);
                 mbar_wait_fast(bar(PV_DONE + t), n_pv++ & 1u);
                 tc_fence_after();
+                DFOT_TRACE(4);
               }
 #pragma unroll
               for (int cc = 0; cc < kPvWaitChunk; ++cc) tmem_st_x16(t_p + 16 * cc, pka[cc]);
@@ -1045,6 +1103,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
           } else {
             tmem_st_x16(t_p + 16 * c, pk);
           }
+          if (kStagger == 2 && t == 0 && j == 0 && c == 1 && lane == 0) mbar_arrive(bar(STAGGER));
           if constexpr (PREFETCH) {                  // S_t(j+1) into the registers the exp2 loop has finished with
             if (more) {
               if (c == 2) {                          // late enough for S_t(j+1) to be complete: the wait is free
@@ -1094,7 +1153,10 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(P_FULL + t));
+        if (lane == 0) {
+          mbar_arrive(bar(P_FULL + t));
+          if (kStagger == 1 && t == 0 && j == 0) mbar_arrive(bar(STAGGER));
+        }
         if constexpr (PREFETCH) mx = mx_next;
       }
       // ---- epilogue: O_t / l → bf16 rows
@@ -1245,6 +1307,13 @@ static int launch(const void* qkv, void* out, int64_t ld_out, int64_t R, int64_t
 
 }  // namespace fattn
 }  // namespace dfot
+
+#ifdef DFOT_ATTN_TRACE
+extern "C" __attribute__((visibility("default"))) int dfot_debug_attn_trace(void* dst, int64_t bytes) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(dst, dfot::fattn::g_trace, (size_t)bytes);
+}
+#endif
 
 extern "C" int dfot_attention(const void* qkv, void* out, int64_t R, int64_t Ntok, int64_t heads, int64_t head_dim,
                               void* stream) {

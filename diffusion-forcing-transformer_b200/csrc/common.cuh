@@ -129,6 +129,24 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
   (void)cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);   // a launch error is picked up by DFOT_CHECK_LAUNCH
 }
 
+// ---------------------------------------------------------------- warp-uniform issue of tcgen05 / TMA instructions
+// UTCHMMA / UTMALDG / UTCBAR take their operands from UNIFORM registers.  Issued under `if (lane == 0)` they sit in
+// divergent control flow, and ptxas wraps every one of them in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop whose R2URs wait
+// for the previous instruction's operand read: ~16 instructions and a serialising scoreboard per MMA (measured in the
+// attention kernel: 700 cycles to issue four MMAs).  The issuing warps therefore run their loops with all 32 lanes
+// (warp-uniform control flow, warp index made uniform with a shuffle as CUTLASS does) and only the instruction itself
+// sits under elect.sync, which ptxas recognises.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

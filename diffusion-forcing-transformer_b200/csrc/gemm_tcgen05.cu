@@ -621,6 +621,53 @@ __device__ __forceinline__ void epilogue_head_qknorm(const Params& p, uint32_t t
   }
 }
 
+// chunk with its side inputs already in flight (see epilogue_tile_resid)
+template <int EPI, bool FULL>
+__device__ __forceinline__ void epilogue_chunk_f32_side(const Params& p, const ChunkSide<EPI>& side, uint32_t t_addr,
+                                                        uint32_t stage_buf, int lane, int m0, int n0) {
+  uint32_t r[32];
+  tmem_ld_x32(t_addr, r);
+  stage_chunk(stage_buf, lane, r);
+  __syncwarp();
+  epilogue_rows_f32<EPI, FULL>(p, side, stage_buf, lane, m0, n0);
+  __syncwarp();
+}
+
+// Residual epilogues (RESID_F32, GATE_RESID_F32) are bound by HBM, not by the tensor pipe, whenever K is small (a
+// 128 x 256 fp32 tile reads and writes 256 KB for 1-5 k cycles of MMA work), and the eight epilogue warps are all the
+// memory-level parallelism a CTA has: with the residual of ONE chunk in flight per warp (8 x 16 B per lane, 32 KB per SM
+// at best) these launches ran at ~60 % of the copy bandwidth.  The residual rows do not depend on the accumulator, so
+// the warp's chunks are software-pipelined: chunk c+1's residual is requested before chunk c is transposed and stored,
+// and the first chunk's before the wait for the accumulator — i.e. under the main loop of the tile.
+template <int EPI, int BN_>
+__device__ __forceinline__ void epilogue_tile_resid(const Params& p, uint32_t t_row, uint32_t stage_buf, int lane, int m0,
+                                                    int n_base, int half, uint32_t full_bar, uint32_t parity) {
+  auto valid = [&](int c) { return c < BN_ / 32 && n_base + c * 32 < p.N && m0 < p.M; };   // warp-uniform
+  auto full = [&](int c) { return m0 + 32 <= p.M && n_base + c * 32 + 32 <= p.N; };
+  auto fetch = [&](ChunkSide<EPI>& sd, int c) {
+    if (full(c)) prefetch_side<EPI, true>(p, sd, lane, m0, n_base + c * 32);
+    else prefetch_side<EPI, false>(p, sd, lane, m0, n_base + c * 32);
+  };
+  ChunkSide<EPI> cur, nxt;
+  int c = half;
+  bool v = valid(c);
+  if (v) fetch(cur, c);
+  mbar_wait(full_bar, parity);
+  tc_fence_after();
+#pragma unroll 1
+  while (v) {
+    const int cn = c + 2;
+    const bool vn = valid(cn);
+    if (vn) fetch(nxt, cn);
+    if (full(c)) epilogue_chunk_f32_side<EPI, true>(p, cur, t_row + (uint32_t)(c * 32), stage_buf, lane, m0, n_base + c * 32);
+    else epilogue_chunk_f32_side<EPI, false>(p, cur, t_row + (uint32_t)(c * 32), stage_buf, lane, m0, n_base + c * 32);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cur.r[i] = nxt.r[i];
+    c = cn;
+    v = vn;
+  }
+}
+
 template <int EPI, bool FULL>
 __device__ __forceinline__ void epilogue_chunk(const Params& p, uint32_t t_addr, uint32_t stage_buf, int lane, int m0,
                                                int n0) {
@@ -657,7 +704,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   const uint32_t tmem_slot = bars + 8u * (2 * C::kStages + 4);
   const uint32_t epi_stage0 = bars + 256u;  // 8 x 4 KB transpose buffers (16-byte aligned)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;   // (uniform for the compiler: common.cuh)
   const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = p.conv_cblks > 0 ? p.conv_taps * p.conv_cblks : (p.K + BK - 1) / BK;
@@ -694,8 +741,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   pdl_wait();   // barriers, tensor memory and tensor maps are set up; global memory is only touched from here on
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (all lanes walk the loop, the copies sit under elect.sync: common.cuh) ========
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -704,10 +751,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         if (p.conv_cblks == 0) {
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), C::kStageBytes);
-            const uint32_t sa = smem_base + stage * C::kStageBytes;
-            tma_load_2d(sa, &tma_a, full_bar(stage), kb * BK, m_blk * BM);
-            tma_load_2d(sa + C::kStageBytesA, &tma_b, full_bar(stage), kb * BK, n_blk * BN);
+            if (elect_one_sync()) {
+              mbar_expect_tx(full_bar(stage), C::kStageBytes);
+              const uint32_t sa = smem_base + stage * C::kStageBytes;
+              tma_load_2d(sa, &tma_a, full_bar(stage), kb * BK, m_blk * BM);
+              tma_load_2d(sa + C::kStageBytesA, &tma_b, full_bar(stage), kb * BK, n_blk * BN);
+            }
+            __syncwarp();
             if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
           }
         } else {
@@ -717,12 +767,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           int tap = 0, cb = 0;
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), C::kStageBytes);
-            const uint32_t sa = smem_base + stage * C::kStageBytes;
-            const int dt = tap / 9, sp = tap - dt * 9;
-            const int dy = sp / 3 - 1, dx = sp - (sp / 3) * 3 - 1;
-            tma_load_4d(sa, &tma_a, full_bar(stage), cb * BK, x0 + dx, y0 + dy, img0 + dt);
-            tma_load_3d(sa + C::kStageBytesA, &tma_b, full_bar(stage), cb * BK, tap, n_blk * BN);
+            if (elect_one_sync()) {
+              mbar_expect_tx(full_bar(stage), C::kStageBytes);
+              const uint32_t sa = smem_base + stage * C::kStageBytes;
+              const int dt = tap / 9, sp = tap - dt * 9;
+              const int dy = sp / 3 - 1, dx = sp - (sp / 3) * 3 - 1;
+              tma_load_4d(sa, &tma_a, full_bar(stage), cb * BK, x0 + dx, y0 + dy, img0 + dt);
+              tma_load_3d(sa + C::kStageBytesA, &tma_b, full_bar(stage), cb * BK, tap, n_blk * BN);
+            }
+            __syncwarp();
             if (++cb == p.conv_cblks) { cb = 0; ++tap; }
             if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
           }
@@ -730,8 +783,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, tcgen05 instructions under elect.sync) =====================
+    {
       constexpr uint32_t idesc = make_idesc<BN>();
       int stage = 0;
       uint32_t phase = 0;
@@ -745,19 +798,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);               // TMA bytes have landed
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * C::kStageBytes;
-          const uint64_t a_desc = make_smem_desc_sw128(sa);
-          const uint64_t b_desc = make_smem_desc_sw128(sa + C::kStageBytesA);
+          if (elect_one_sync()) {
+            const uint32_t sa = smem_base + stage * C::kStageBytes;
+            const uint64_t a_desc = make_smem_desc_sw128(sa);
+            const uint64_t b_desc = make_smem_desc_sw128(sa + C::kStageBytesA);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
+              umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));                 // ring slot reusable once these MMAs retire
+            if (kb + 1 == num_kb) umma_commit(tmem_full_bar(acc));   // accumulator complete → epilogue
           }
-          umma_commit(empty_bar(stage));                   // ring slot reusable once these MMAs retire
+          __syncwarp();
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tmem_full_bar(acc));                   // accumulator complete → epilogue
       }
     }
   } else {
@@ -771,10 +827,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       tile_coord(tile, m_blk, n_blk);
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(tmem_full_bar(acc), acc_phase);
-      tc_fence_after();
       const int m0 = m_blk * BM + q * 32;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      if constexpr (EPI == DFOT_EPI_RESID_F32 || EPI == DFOT_EPI_GATE_RESID_F32) {
+        epilogue_tile_resid<EPI, BN>(p, t_row, stage_buf, lane, m0, n_blk * BN, half, tmem_full_bar(acc), acc_phase);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        continue;
+      }
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tc_fence_after();
       if constexpr (EPI == DFOT_EPI_QKNORM_ROPE_BF16) {
         // head-wise: the two warps of a lane quarter alternate over the heads of the 256-column tile
         const int dh = (int)p.e.head_dim;               // 64 or 128 (host-checked), N % dh == 0
@@ -854,7 +917,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
   const uint32_t tmem_slot = bars + 8u * (2 * C::kStages + 4);
   const uint32_t epi_stage0 = bars + 256u;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;   // (uniform for the compiler: common.cuh)
   const int rank = (int)cluster_ctarank();              // 0 = leader
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int num_m = (p.M + 2 * BM - 1) / (2 * BM), num_n = (p.N + BN - 1) / BN;
@@ -893,7 +956,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs: own A rows, own half of B) =====================
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -905,25 +968,28 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
         int tap = 0, cb = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::kStageBytes);
-          const uint32_t sa = smem_base + stage * C::kStageBytes;
-          if (p.conv_cblks == 0) {
-            tma2_load_2d(sa, &tma_a, full_bar(stage), kb * BK, m0);
-            tma2_load_2d(sa + C::kStageBytesA, &tma_b, full_bar(stage), kb * BK, nb0);
-          } else {
-            const int dt = tap / 9, sp = tap - dt * 9;
-            const int dy = sp / 3 - 1, dx = sp - (sp / 3) * 3 - 1;
-            tma2_load_4d(sa, &tma_a, full_bar(stage), cb * BK, x0 + dx, y0 + dy, img0 + dt);
-            tma2_load_3d(sa + C::kStageBytesA, &tma_b, full_bar(stage), cb * BK, tap, nb0);
-            if (++cb == p.conv_cblks) { cb = 0; ++tap; }
+          if (elect_one_sync()) {
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::kStageBytes);
+            const uint32_t sa = smem_base + stage * C::kStageBytes;
+            if (p.conv_cblks == 0) {
+              tma2_load_2d(sa, &tma_a, full_bar(stage), kb * BK, m0);
+              tma2_load_2d(sa + C::kStageBytesA, &tma_b, full_bar(stage), kb * BK, nb0);
+            } else {
+              const int dt = tap / 9, sp = tap - dt * 9;
+              const int dy = sp / 3 - 1, dx = sp - (sp / 3) * 3 - 1;
+              tma2_load_4d(sa, &tma_a, full_bar(stage), cb * BK, x0 + dx, y0 + dy, img0 + dt);
+              tma2_load_3d(sa + C::kStageBytesA, &tma_b, full_bar(stage), cb * BK, tap, nb0);
+            }
           }
+          __syncwarp();
+          if (p.conv_cblks != 0 && ++cb == p.conv_cblks) { cb = 0; ++tap; }
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {                                     // warp-uniform loop, tcgen05 instructions under elect.sync
       constexpr uint32_t idesc = make_idesc_pair<BN>();
       int stage = 0;
       uint32_t phase = 0;
@@ -937,16 +1003,20 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);                 // both CTAs' TMA bytes have landed
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * C::kStageBytes;
-          const uint64_t a_desc = make_smem_desc_sw128(sa);
-          const uint64_t b_desc = make_smem_desc_sw128(sa + C::kStageBytesA);
+          if (elect_one_sync()) {
+            const uint32_t sa = smem_base + stage * C::kStageBytes;
+            const uint64_t a_desc = make_smem_desc_sw128(sa);
+            const uint64_t b_desc = make_smem_desc_sw128(sa + C::kStageBytesA);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma2_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma2_commit_both(empty_bar(stage));               // ring slot reusable in BOTH CTAs
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma2_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                         (kb > 0 || k > 0) ? 1u : 0u);
+            umma2_commit_both(empty_bar(stage));             // ring slot reusable in BOTH CTAs
+            if (kb + 1 == num_kb) umma2_commit_both(tmem_full_bar(acc));   // accumulator complete → both epilogues
+          }
+          __syncwarp();
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
-        umma2_commit_both(tmem_full_bar(acc));               // accumulator complete → both epilogues
       }
     }
   } else {
@@ -960,10 +1030,17 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
       tile_coord(tile, m_blk, n_blk);
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(tmem_full_bar(acc), acc_phase);
-      tc_fence_after();
       const int m0 = m_blk * 2 * BM + rank * BM + q * 32;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      if constexpr (EPI == DFOT_EPI_RESID_F32 || EPI == DFOT_EPI_GATE_RESID_F32) {
+        epilogue_tile_resid<EPI, BN>(p, t_row, stage_buf, lane, m0, n_blk * BN, half, tmem_full_bar(acc), acc_phase);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(tmem_empty_bar(acc));
+        continue;
+      }
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tc_fence_after();
       if constexpr (EPI == DFOT_EPI_QKNORM_ROPE_BF16) {
         const int dh = (int)p.e.head_dim;               // 64 or 128 (host-checked), N % dh == 0, BN % dh == 0
 #pragma unroll 1
