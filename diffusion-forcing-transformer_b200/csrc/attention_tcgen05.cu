@@ -81,6 +81,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 // Latency-critical hand-offs (softmax <-> MMA issuer): plain try_wait polling, no suspend-time hint.
 __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
+#ifdef DFOT_ATTN_SUSPEND_WAITS
+  mbar_wait(bar, parity);
+  return;
+#endif
   uint32_t done = 0;
   for (uint32_t spin = 0;; ++spin) {
     asm volatile(
@@ -176,6 +180,11 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (P, bf16 pairs packed in 32-bit columns, lane = row) is read
@@ -574,20 +583,34 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params 
 // With head_dim 64 the kernel is bound by the 16/clk/SM MUFU (exp2) rate, not the tensor pipe: 128x128 exps = 1024
 // cycles vs 512 cycles of MMA per tile — the roofline is ~50 % of the bf16 tensor peak.
 constexpr int kThreads2 = 384;
-template <int DH, int DP, bool NOMAX>   // NOMAX: bounded scores, p = 2^s without a running maximum (Params::no_max)
+// Keys per KV tile of kernel 2.  The separate-P pipeline needs 2 x (KV + KV/2 + DP) <= 512 tensor-memory columns: 128
+// keys fit for head_dim 64; head_dim 72 (padded to 80) takes 112-key tiles (496 columns) — 12 instead of 10 tiles at
+// N = 1280, but S_t(j+1) no longer waits for PV_t(j) (the aliased layout spent 44 % of its softmax time waiting for S);
+// head_dim 128 has no room for it at any useful width and keeps the aliased layout.
+template <int DP> struct KvTile { static constexpr int value = DP == 80 ? 112 : 128; };
+// NOMAX: bounded scores, p = 2^s without a running maximum (Params::no_max); KV: keys per tile (KvTile<DP>)
+template <int DH, int DP, bool NOMAX, int KV>
 __global__ void __launch_bounds__(kThreads2, 1)
-attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_kv,
+                          const Params p) {
   pdl_trigger();   // programmatic dependent launch: see common.cuh (pdl_wait() follows the prologue)
+  constexpr int BKV = KV;                            // (shadows the 128 of kernel 1)
+  static_assert(KV % 16 == 0 && KV <= 128 && KV > 96, "KV tile: three full 32-score chunks plus a 16- or 32-wide one");
+  constexpr int NCH = (KV + 31) / 32;                // 32-score chunks of a row; the last one may hold 16
   constexpr int ATOMS = (DP + 63) / 64;
-  constexpr int TILE_BYTES = ATOMS * kAtomBytes;
+  constexpr int TILE_BYTES = ATOMS * kAtomBytes;     // smem slot of a Q / K / V tile (K / V fill KV of its 128 rows)
+  constexpr int KV_BYTES = ATOMS * KV * 128;         // bytes one K or V tile brings in
   constexpr int KS_QK = DP / 16, KS_PV = BKV / 16;
   constexpr uint32_t IDESC_S = make_idesc(BKV, false);
   constexpr uint32_t IDESC_PV = make_idesc(DP, true);
-  constexpr bool SEP_P = DP <= 64;                   // P_t has its own TMEM columns
+  constexpr bool SEP_P = 2 * (KV + KV / 2 + DP) <= 512;   // P_t has its own TMEM columns
   constexpr bool DUAL = SEP_P;                       // one MMA issuer warp per query tile (measured: helps only SEP_P)
-  // aliased: S_t at 128*t (P_t = its first 64 columns), O_t at 256 + 128*t;  separate: S 128*t, P 256 + 64*t, O 384 + 64*t
-  constexpr uint32_t TMEM_S = 0, TMEM_P = SEP_P ? 256 : 0, P_STRIDE = SEP_P ? 64 : 128;
-  constexpr uint32_t TMEM_O = SEP_P ? 384 : 256, O_STRIDE = SEP_P ? 64 : 128;
+  // aliased: S_t at 128*t (P_t = its first 64 columns), O_t at 256 + 128*t;
+  // separate: S_t at KV*t, P_t at 2*KV + (KV/2)*t, O_t at 3*KV + DP*t
+  constexpr uint32_t TMEM_S = 0, S_STRIDE = SEP_P ? KV : 128;
+  constexpr uint32_t TMEM_P = SEP_P ? 2 * KV : 0, P_STRIDE = SEP_P ? KV / 2 : 128;
+  constexpr uint32_t TMEM_O = SEP_P ? 3 * KV : 256, O_STRIDE = SEP_P ? DP : 128;
+  static_assert(SEP_P || KV == 128, "the aliased layout is written for 128-key tiles");
   constexpr float kRescaleThreshold = 8.0f;
   // which of the 16 score pairs of every 32-score group go through the polynomial exp2 (bit i: iteration i of 8).
   // Measured on B200 (d = 64, N = 8192): 0 % poly 786 TFLOP/s, 25 % 753, 31 % 774, 37.5 % 746, 50 % 693 — the kernel is
@@ -596,7 +619,11 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
 #define DFOT_ATTN_POLY_FIRST 0x00
 #define DFOT_ATTN_POLY_SECOND 0x55
 #endif
-  constexpr uint32_t kPolyFirst = SEP_P ? DFOT_ATTN_POLY_FIRST : 0u, kPolySecond = SEP_P ? DFOT_ATTN_POLY_SECOND : 0u;
+#ifndef DFOT_ATTN_POLY_ALIASED
+#define DFOT_ATTN_POLY_ALIASED 1
+#endif
+  constexpr bool kPolyOn = SEP_P || DFOT_ATTN_POLY_ALIASED;
+  constexpr uint32_t kPolyFirst = kPolyOn ? DFOT_ATTN_POLY_FIRST : 0u, kPolySecond = kPolyOn ? DFOT_ATTN_POLY_SECOND : 0u;
   // bounded-score path (2 instead of 3 base instructions per score): polynomial share of the score pairs.  Measured
   // on B200 (d = 64, N = 8192, R = 8; run-to-run spread of one box ~3 %): 0 % 824, 12.5 % 853, 19 % 874, 25 % 884-918,
   // 31 % 857, 37.5 % 886, 44 % 874, 50 % 864-877, 62.5 % 867, 75 % 813 TFLOP/s — flat between 25 % and 50 %, so the
@@ -607,7 +634,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
 #define DFOT_ATTN_POLYB_FIRST 0x00
 #define DFOT_ATTN_POLYB_SECOND 0x55
 #endif
-  constexpr uint32_t kPolyFirstB = SEP_P ? DFOT_ATTN_POLYB_FIRST : 0u, kPolySecondB = SEP_P ? DFOT_ATTN_POLYB_SECOND : 0u;
+  constexpr uint32_t kPolyFirstB = kPolyOn ? DFOT_ATTN_POLYB_FIRST : 0u, kPolySecondB = kPolyOn ? DFOT_ATTN_POLYB_SECOND : 0u;
   // Measured and dropped (aliased layout, d = 72 / 128): starting tile 1 one softmax phase behind tile 0, so that one
   // warpgroup exponentiates while the other tile's PV + S MMAs run — 505 vs 522 TFLOP/s at d = 72 (N = 1280), 958 vs 1003
   // at d = 128 (N = 2048): the hand-off latencies, not the phase of the two tiles, bound these shapes
@@ -647,6 +674,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;   // (uniform for the compiler: see elect_one_sync)
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_kv) : "memory");
     for (int i = 0; i < N_BARS; ++i) {
       const bool from_softmax = (i >= P_FULL && i < P_FULL + 2) || (i >= O_FREE && i < O_FREE + 2) ||
                                 (i >= S_FREE && i < S_FREE + 2) || i == STAGGER;
@@ -710,19 +738,19 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
           const uint32_t st = g & 1u, ph = (g >> 1) & 1u;
           mbar_wait(bar(K_EMPTY + st), ph ^ 1u);
           if (elect_one_sync()) {
-            mbar_expect_tx(bar(K_FULL + st), TILE_BYTES);
+            mbar_expect_tx(bar(K_FULL + st), KV_BYTES);
 #pragma unroll
             for (int a = 0; a < ATOMS; ++a)
-              tma_load_3d(sK + st * TILE_BYTES + a * kAtomBytes, &tmap, bar(K_FULL + st), a * 64, p.heads + h,
+              tma_load_3d(sK + st * TILE_BYTES + a * kAtomBytes, &tmap_kv, bar(K_FULL + st), a * 64, p.heads + h,
                           row0 + j * BKV);
           }
           __syncwarp();
           mbar_wait(bar(V_EMPTY + st), ph ^ 1u);
           if (elect_one_sync()) {
-            mbar_expect_tx(bar(V_FULL + st), TILE_BYTES);
+            mbar_expect_tx(bar(V_FULL + st), KV_BYTES);
 #pragma unroll
             for (int a = 0; a < ATOMS; ++a)
-              tma_load_3d(sV + st * TILE_BYTES + a * kAtomBytes, &tmap, bar(V_FULL + st), a * 64, 2 * p.heads + h,
+              tma_load_3d(sV + st * TILE_BYTES + a * kAtomBytes, &tmap_kv, bar(V_FULL + st), a * 64, 2 * p.heads + h,
                           row0 + j * BKV);
           }
           __syncwarp();
@@ -759,9 +787,11 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
           g += n_kv;
           continue;
         }
-        auto issue_s = [&](uint32_t st) {              // S_t = Q_t · K^T (K stage st)
+        // S_t = Q_t · K^T (K stage st).  The item's last S releases the Q tiles: the next item's Q (and its first K / V
+        // tiles behind it in the producer's queue) then load under the last KV step instead of after it.
+        auto issue_s = [&](uint32_t st, bool last_s) {
           if (elect_one_sync()) {
-            const uint32_t d = tmem_base + TMEM_S + (uint32_t)t * 128u;
+            const uint32_t d = tmem_base + TMEM_S + (uint32_t)t * S_STRIDE;
 #pragma unroll
             for (int s = 0; s < KS_QK; ++s) {
               const uint32_t off = (uint32_t)(s >> 2) * kAtomBytes + (uint32_t)(s & 3) * 32u;
@@ -770,11 +800,12 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
             }
             umma_commit(bar(S_FULL + t));
             umma_commit(bar(K_EMPTY + st));
+            if (last_s) umma_commit(bar(Q_EMPTY));
           }
           __syncwarp();
         };
         // O_t (+)= P_t · V (V stage st), A operand from TMEM; then the step's commits
-        auto issue_pv = [&](uint32_t st, bool first, bool more, bool last_of_item) {
+        auto issue_pv = [&](uint32_t st, bool first, bool more) {
           if (elect_one_sync()) {
             const uint32_t d = tmem_base + TMEM_O + (uint32_t)t * O_STRIDE;
             const uint32_t a = tmem_base + TMEM_P + (uint32_t)t * P_STRIDE;
@@ -785,7 +816,6 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
             umma_commit(bar(V_EMPTY + st));
             if (!more) umma_commit(bar(O_DONE + t));
             else if constexpr (SEP_P) umma_commit(bar(PV_DONE + t));
-            if (last_of_item) umma_commit(bar(Q_EMPTY));
           }
           __syncwarp();
         };
@@ -793,7 +823,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
           const uint32_t st = g & 1u, ph = (g >> 1) & 1u;
           mbar_wait(bar(K_FULL + st), ph);
           tc_fence_after();
-          issue_s(st);
+          issue_s(st, n_kv == 1);
         }
         if (n_o > 0) mbar_wait(bar(O_FREE + t), (n_o - 1) & 1u);
         for (int j = 0; j < n_kv; ++j) {
@@ -806,7 +836,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
             mbar_wait_fast(bar(S_FREE + t), n_f++ & 1u);
             tc_fence_after();
             DFOT_TRACE(11);
-            issue_s(stn);
+            issue_s(stn, j + 2 == n_kv);
             DFOT_TRACE(12);
           }
           mbar_wait(bar(V_FULL + st), ph);
@@ -814,12 +844,12 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
           mbar_wait_fast(bar(P_FULL + t), n_p++ & 1u);
           tc_fence_after();
           DFOT_TRACE(14);
-          issue_pv(st, j == 0, more, !more);
+          issue_pv(st, j == 0, more);
           DFOT_TRACE(15);
           if (!SEP_P && more) {
             mbar_wait(bar(K_FULL + stn), phn);
             tc_fence_after();
-            issue_s(stn);
+            issue_s(stn, j + 2 == n_kv);
           }
         }
         ++n_o;
@@ -843,7 +873,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
         item_coord(item, r, h, q0, nt);
         const bool has1 = nt == 2 && (q0 + 1) * BQ < p.Ntok;     // second query tile holds rows of this sample
         auto issue_s = [&](int t, uint32_t st) {          // S_t = Q_t · K^T (K stage st)
-          const uint32_t d = tmem_base + TMEM_S + (uint32_t)t * 128u;
+          const uint32_t d = tmem_base + TMEM_S + (uint32_t)t * S_STRIDE;
 #pragma unroll
           for (int s = 0; s < KS_QK; ++s) {
             const uint32_t off = (uint32_t)(s >> 2) * kAtomBytes + (uint32_t)(s & 3) * 32u;
@@ -869,6 +899,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
             issue_s(0, st);
             if (has1) issue_s(1, st);
             umma_commit(bar(K_EMPTY + st));
+            if (n_kv == 1) umma_commit(bar(Q_EMPTY));   // the item's last S releases the Q tiles (see the dual path)
           });
         }
         // the epilogue of the previous item must have drained O_t before the first (overwriting) PV
@@ -887,7 +918,8 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
             if (more) issue_s(0, stn); else umma_commit(bar(O_DONE + 0));
             if (!has1) {
               umma_commit(bar(V_EMPTY + st));
-              if (more) umma_commit(bar(K_EMPTY + stn)); else umma_commit(bar(Q_EMPTY));
+              if (more) umma_commit(bar(K_EMPTY + stn));
+              if (j + 2 == n_kv) umma_commit(bar(Q_EMPTY));
             }
           });
           if (has1) {
@@ -897,7 +929,8 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
               issue_pv(1, st, j == 0);
               if (more) issue_s(1, stn); else umma_commit(bar(O_DONE + 1));
               umma_commit(bar(V_EMPTY + st));
-              if (more) umma_commit(bar(K_EMPTY + stn)); else umma_commit(bar(Q_EMPTY));
+              if (more) umma_commit(bar(K_EMPTY + stn));
+              if (j + 2 == n_kv) umma_commit(bar(Q_EMPTY));
             });
           }
         }
@@ -914,7 +947,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
     const int t = (warp - 4) >> 2;                   // which query tile of the pair
     const int q = warp & 3;                          // TMEM lane quarter (hardware rule: warp_id % 4)
     const int row = q * 32 + lane;
-    const uint32_t t_s = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_S + (uint32_t)t * 128u;
+    const uint32_t t_s = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_S + (uint32_t)t * S_STRIDE;
     const uint32_t t_p = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_P + (uint32_t)t * P_STRIDE;
     const uint32_t t_o = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_O + (uint32_t)t * O_STRIDE;
     uint32_t n_s = 0, n_items = 0, n_pv = 0, it_all = 0;
@@ -927,12 +960,20 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
       if (t >= nt || qt * BQ >= p.Ntok) continue;    // single-tile item, or tile 1 of the last pair outside the sample
       if (kStagger != 0 && t == 1) mbar_wait_fast(bar(STAGGER), it_cur & 1u);
       float m_used = 0.f, l_run = 0.f;
-      uint32_t v[4][32];                             // the 128 scores of this row stay in registers
+      uint32_t v[NCH][32];                           // the KV scores of this row stay in registers
       // pull S_t(jj) into registers (all four 32-column loads in flight), hand the buffer back, mask, row maximum
       auto load_begin = [&]() {
         mbar_wait_fast(bar(S_FULL + t), n_s++ & 1u);
         tc_fence_after();
         DFOT_TRACE(1);
+      };
+      auto load_chunk = [&](int c) {                 // (the last chunk of a 112-key tile holds 16 scores)
+        if (32 * c + 32 <= BKV) tmem_ld_x32(t_s + 32 * c, v[c]);
+        else tmem_ld_x16(t_s + 32 * c, *reinterpret_cast<uint32_t(*)[16]>(&v[c][0]));
+      };
+      auto store_chunk = [&](int c, const uint32_t (&pk)[16]) {   // 32 (16) scores = 16 (8) packed bf16 pairs
+        if (32 * c + 32 <= BKV) tmem_st_x16(t_p + 16 * c, pk);
+        else tmem_st_x8(t_p + 16 * c, *reinterpret_cast<const uint32_t(*)[8]>(&pk[0]));
       };
       auto load_end = [&](int jj) -> float {
         tmem_ld_wait();
@@ -957,31 +998,17 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
           mx0 = fmaxf(mx0, __uint_as_float(v[0][c]));
           mx1 = fmaxf(mx1, __uint_as_float(v[1][c]));
           mx2 = fmaxf(mx2, __uint_as_float(v[2][c]));
-          mx3 = fmaxf(mx3, __uint_as_float(v[3][c]));
+          if (96 + c < BKV) mx3 = fmaxf(mx3, __uint_as_float(v[3][c]));
         }
         return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       };
-      // Experiment kept for reference (off): with SEP_P, S_t(j+1) is ready while this warpgroup works on tile j, so its
-      // scores could be PREFETCHED chunk by chunk into the registers the exp2 loop has just finished with.  Measured on
-      // B200 (d = 64, N = 8192): 559 TFLOP/s (prefetch chunk by chunk from the first chunk on) and 623 TFLOP/s (prefetch
-      // after the third chunk, when S_t(j+1) is certainly complete) against 762-786 without — a tcgen05.ld in flight
-      // slows the exp2 loop of the same warp down more than its hidden latency gains; the plain order stays.
-      constexpr bool PREFETCH = false;
-      float mx = 0.f;
-      if constexpr (PREFETCH) {
+      // (Measured and dropped, r02: prefetching S_t(j+1) chunk by chunk into the registers the exp2 loop has finished with —
+      // 559-623 against 762-786 TFLOP/s at d = 64: a tcgen05.ld in flight slows the exp2 loop of the same warp down.)
+      for (int j = 0; j < n_kv; ++j) {
         load_begin();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_x32(t_s + 32 * c, v[c]);
-        mx = load_end(0);
-      }
-      for (int j = 0; j < n_kv; ++j) {
-        const bool more = j + 1 < n_kv;
-        if constexpr (!PREFETCH) {
-          load_begin();
-#pragma unroll
-          for (int c = 0; c < 4; ++c) tmem_ld_x32(t_s + 32 * c, v[c]);
-          mx = load_end(j);
-        }
+        for (int c = 0; c < NCH; ++c) load_chunk(c);
+        const float mx = load_end(j);
         if constexpr (NOMAX) {
           // Bounded scores: p = 2^s directly (reference maximum 0 for every row and tile) — no row maximum, no
           // subtraction, no O rescaling; everything else (P in TMEM, PV, row sums) is unchanged.
@@ -990,12 +1017,13 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
           // TFLOP/s at d = 64, N = 8192).  A partial last tile carries -inf masks the polynomial cannot take: MUFU only.
           auto exp_tile = [&](auto poly_tag) {
             constexpr bool POLY = decltype(poly_tag)::value;
-            uint32_t pka[4][16];
+            uint32_t pka[NCH][16];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < NCH; ++c) {
               uint32_t (&pk)[16] = pka[c];
 #pragma unroll
               for (int e = 0; e < 16; e += 2) {
+                if (32 * c + 2 * e >= BKV) continue;   // (the last chunk of a 112-key tile holds 16 scores)
                 float p0, p1, p2, p3;
                 if (POLY && ((kPolyFirstB >> (e >> 1)) & 1))
                   ex2_poly_x2_bounded(__uint_as_float(v[c][2 * e]), __uint_as_float(v[c][2 * e + 1]), p0, p1);
@@ -1020,11 +1048,11 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
                     DFOT_TRACE(4);
                   }
 #pragma unroll
-                  for (int cc = 0; cc < kPvWaitChunk; ++cc) tmem_st_x16(t_p + 16 * cc, pka[cc]);
+                  for (int cc = 0; cc < kPvWaitChunk; ++cc) store_chunk(cc, pka[cc]);
                 }
-                if (c >= kPvWaitChunk) tmem_st_x16(t_p + 16 * c, pk);
+                if (c >= kPvWaitChunk) store_chunk(c, pk);
               } else {
-                tmem_st_x16(t_p + 16 * c, pk);
+                store_chunk(c, pk);
               }
               if (kStagger == 2 && t == 0 && j == 0 && c == 1 && lane == 0) mbar_arrive(bar(STAGGER));
             }
@@ -1063,12 +1091,13 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
         // p = exp2(s - m) → packed bf16 pairs into P_t (the PV MMA's A operand); fp32x2 packed sub / row sum
         const uint64_t neg_m2 = pack_f32x2(-m_used, -m_used);
         uint64_t sum_a = 0ull, sum_b = 0ull;         // (+0.f, +0.f)
-        uint32_t pka[4][16];
+        uint32_t pka[NCH][16];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NCH; ++c) {
           uint32_t (&pk)[16] = pka[c];
 #pragma unroll
           for (int e = 0; e < 16; e += 2) {
+            if (32 * c + 2 * e >= BKV) continue;     // (the last chunk of a 112-key tile holds 16 scores)
             float x0, x1, x2, x3;
 #ifndef DFOT_ATTN_NO_PACKED
             unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[c][2 * e]), __uint_as_float(v[c][2 * e + 1])), neg_m2), x0, x1);
@@ -1097,28 +1126,13 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
                 DFOT_TRACE(4);
               }
 #pragma unroll
-              for (int cc = 0; cc < kPvWaitChunk; ++cc) tmem_st_x16(t_p + 16 * cc, pka[cc]);
+              for (int cc = 0; cc < kPvWaitChunk; ++cc) store_chunk(cc, pka[cc]);
             }
-            if (c >= kPvWaitChunk) tmem_st_x16(t_p + 16 * c, pk);
+            if (c >= kPvWaitChunk) store_chunk(c, pk);
           } else {
-            tmem_st_x16(t_p + 16 * c, pk);
+            store_chunk(c, pk);
           }
           if (kStagger == 2 && t == 0 && j == 0 && c == 1 && lane == 0) mbar_arrive(bar(STAGGER));
-          if constexpr (PREFETCH) {                  // S_t(j+1) into the registers the exp2 loop has finished with
-            if (more) {
-              if (c == 2) {                          // late enough for S_t(j+1) to be complete: the wait is free
-                load_begin();
-                tmem_ld_x32(t_s, v[0]);
-                tmem_ld_x32(t_s + 32, v[1]);
-                tmem_ld_x32(t_s + 64, v[2]);
-              }
-              if (c == 3) tmem_ld_x32(t_s + 96, v[3]);
-            }
-          }
-        }
-        float mx_next = 0.f;
-        if constexpr (PREFETCH) {
-          if (more) mx_next = load_end(j + 1);
         }
         float sum0, sum1, sum2, sum3;
         unpack_f32x2(sum_a, sum0, sum1);
@@ -1157,7 +1171,6 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params
           mbar_arrive(bar(P_FULL + t));
           if (kStagger == 1 && t == 0 && j == 0) mbar_arrive(bar(STAGGER));
         }
-        if constexpr (PREFETCH) mx = mx_next;
       }
       // ---- epilogue: O_t / l → bf16 rows
       mbar_wait_fast(bar(O_DONE + t), n_items++ & 1u);
@@ -1251,26 +1264,31 @@ static int launch(const void* qkv, void* out, int64_t ld_out, int64_t R, int64_t
   const int ov = attention_impl_override();
   const bool paired = ov == 2 || (ov == 0 && Ntok > BQ);      // more than one query tile per sample
   const int smem_bytes = paired ? smem2 : smem1;
+  constexpr int KV2 = KvTile<DP>::value;                      // keys per KV tile of kernel 2
   EncodeTiledFn enc = get_encode_fn();
   DFOT_REQUIRE(enc != nullptr, DFOT_ERR_DRIVER, "attention: cuTensorMapEncodeTiled unavailable from the driver");
-  // qkv viewed as [tokens][3*heads][DH]: box = 64 (d) x 1 x 128 (tokens); d beyond DH is zero-filled by TMA
-  CUtensorMap tmap;
+  // qkv viewed as [tokens][3*heads][DH]: box = 64 (d) x 1 x rows (tokens); d beyond DH is zero-filled by TMA.  Query
+  // tiles are 128 rows; the K / V tiles of kernel 2 may be narrower (KvTile), hence a second map.
+  CUtensorMap tmap, tmap_kv;
   cuuint64_t gdim[3] = {(cuuint64_t)DH, (cuuint64_t)(3 * heads), (cuuint64_t)(R * Ntok)};
   cuuint64_t gstr[2] = {(cuuint64_t)DH * 2, (cuuint64_t)(3 * heads * DH) * 2};
-  cuuint32_t box[3] = {64, 1, 128};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), gdim, gstr, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  DFOT_REQUIRE(cr == CUDA_SUCCESS, DFOT_ERR_DRIVER, "attention: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+  for (int m = 0; m < 2; ++m) {
+    cuuint32_t box[3] = {64, 1, (cuuint32_t)(m == 0 ? 128 : KV2)};
+    CUresult cr = enc(m == 0 ? &tmap : &tmap_kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), gdim, gstr,
+                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DFOT_REQUIRE(cr == CUDA_SUCCESS, DFOT_ERR_DRIVER, "attention: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+  }
   const bool nomax = paired && score_bound > 0.f && score_bound <= 96.f;   // kernel 2 only
-  void (*kern)(const CUtensorMap, const Params) =
-      paired ? (nomax ? attention2_tcgen05_kernel<DH, DP, true> : attention2_tcgen05_kernel<DH, DP, false>)
-             : attention_tcgen05_kernel<DH, DP>;
+  void (*kern1)(const CUtensorMap, const Params) = attention_tcgen05_kernel<DH, DP>;
+  void (*kern2)(const CUtensorMap, const CUtensorMap, const Params) =
+      nomax ? attention2_tcgen05_kernel<DH, DP, true, KV2> : attention2_tcgen05_kernel<DH, DP, false, KV2>;
   const int which = paired ? (nomax ? 2 : 1) : 0;
   static bool configured[3] = {false, false, false};
   if (!configured[which]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = paired ? cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
+                           : cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     DFOT_REQUIRE(e == cudaSuccess, DFOT_ERR_CUDA, "attention: cannot reserve %d B shared memory: %s", smem_bytes,
                  cudaGetErrorString(e));
     configured[which] = true;
@@ -1284,7 +1302,7 @@ static int launch(const void* qkv, void* out, int64_t ld_out, int64_t R, int64_t
   p.no_max = nomax ? 1 : 0;
   p.R = (int)R; p.Ntok = (int)Ntok; p.heads = (int)heads;
   p.q_tiles = (int)ceil_div(Ntok, BQ);
-  p.kv_tiles = (int)ceil_div(Ntok, BKV);
+  p.kv_tiles = (int)ceil_div(Ntok, paired ? KV2 : BKV);
   p.num_items = (int)(R * heads * (paired ? (p.q_tiles + 1) / 2 : p.q_tiles));
   p.pair_items = p.num_items;
   if (paired && attention_split_tail() && p.q_tiles % 2 == 0 && p.num_items > sms) {
@@ -1300,7 +1318,8 @@ static int launch(const void* qkv, void* out, int64_t ld_out, int64_t R, int64_t
     }
   }
   const int grid = p.num_items < sms ? p.num_items : sms;
-  launch_pdl(kern, dim3(grid), dim3(paired ? kThreads2 : kThreads), smem_bytes, s, tmap, p);
+  if (paired) launch_pdl(kern2, dim3(grid), dim3(kThreads2), smem_bytes, s, tmap, tmap_kv, p);
+  else launch_pdl(kern1, dim3(grid), dim3(kThreads), smem_bytes, s, tmap, p);
   DFOT_CHECK_LAUNCH("attention_tcgen05");
   return DFOT_OK;
 }

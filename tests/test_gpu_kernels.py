@@ -105,7 +105,9 @@ def test_gemm_qkv_rope_epilogue(heads, dh, T, gh, gw):
                                           (8, 16, 72, 1280),
                                           # more pair items than SMs with an even tile count: the last wave is handed
                                           # out as single query tiles (split tail) — dual-issuer, single-issuer, d = 128
-                                          (4, 12, 64, 1024), (3, 9, 128, 2048), (5, 16, 72, 512)])
+                                          (4, 12, 64, 1024), (3, 9, 128, 2048), (5, 16, 72, 512),
+                                          # head_dim 72 runs 112-key KV tiles: whole tiles, one key over, T = 17 stress
+                                          (2, 2, 72, 224), (1, 2, 72, 225), (2, 3, 72, 337), (1, 4, 72, 4352)])
 def test_attention_matches_sdpa(R, heads, dh, N):
     D = heads * dh
     g = torch.Generator().manual_seed(N + dh)
@@ -122,7 +124,7 @@ def test_attention_matches_sdpa(R, heads, dh, N):
 
 
 @pytest.mark.parametrize("R,heads,dh,N", [(2, 9, 64, 1024), (1, 9, 128, 512), (2, 3, 64, 200), (1, 2, 128, 129),
-                                          (1, 2, 64, 100), (3, 4, 72, 384), (4, 12, 64, 1024), (3, 9, 128, 2048)])
+                                          (1, 2, 64, 100), (3, 4, 72, 384), (4, 12, 64, 1024), (3, 9, 128, 2048), (2, 3, 72, 1233)])
 def test_attention_bounded_scores_matches_sdpa(R, heads, dh, N):
     """QK-normalised operands with a declared score bound: the kernel may drop the running maximum (p = 2^s); the
     result must still be the softmax attention.  Scores reach the declared bound on the diagonal (q == k direction)."""
