@@ -228,7 +228,12 @@ class DFoTVideo(BaseVideoAlgo):
             cur = xs.shape[1]
         return xs, record
 
-    def _window_conditions(self, conditions: Tensor, nfe: int):
+    def _conditions_follow_levels(self) -> bool:
+        """True when `_process_conditions` reads the step's noise levels (pose conditioning under `temporal` history
+        guidance); the window then caches one conditioning per distinct mask of top-level frames instead of one."""
+        return False
+
+    def _window_conditions(self, conditions: Tensor, nfe: int, levels_from=None):
         """Conditioning of all branch rows `(b h g)` of one window (rows of a sample share its conditions)."""
         return self._process_conditions(conditions.repeat_interleave(nfe, dim=0).clone(), None)
 
@@ -612,7 +617,7 @@ class _WindowRun:
             self.lvl_dev = [torch.from_numpy(p.levels).to(dev, non_blocking=True) for p in self.plans]
             self.cm_dev = [None if p.cond_mask is None else torch.from_numpy(p.cond_mask).to(dev, non_blocking=True)
                            for p in self.plans]
-        self.cond_cache: Dict[int, Tensor] = {}
+        self.cond_cache: Dict[object, Tensor] = {}
         self.record = [] if return_all else None
         self.model_in = None
         self.m = 0
@@ -621,12 +626,16 @@ class _WindowRun:
     def done(self) -> bool:
         return self.m >= self.n_steps
 
-    def _cond_for(self, nfe: int):
+    def _cond_for(self, p: sp.StepPlan):
         if self.conditions is None or self.dry:
             return None
-        if nfe not in self.cond_cache:   # constant over the window (the reference recomputes it every step, :732-743)
-            self.cond_cache[nfe] = self.algo._window_conditions(self.conditions.to(self.dev), nfe)
-        return self.cond_cache[nfe]
+        nfe, key, levels = p.nfe, p.nfe, None
+        if self.algo._conditions_follow_levels():   # `temporal` HG + poses: depends on which frames sit at the top level
+            levels = p.levels_from
+            key = (nfe, (levels == self.algo.timesteps - 1).tobytes())
+        if key not in self.cond_cache:   # constant over the window (the reference recomputes it every step, :732-743)
+            self.cond_cache[key] = self.algo._window_conditions(self.conditions.to(self.dev), nfe, levels_from=levels)
+        return self.cond_cache[key]
 
     def _draw_prepare_noise(self, p: sp.StepPlan):
         # RNG (2): q_sample noise, then (full manager only) the excluded-token noise — always drawn
@@ -657,7 +666,7 @@ class _WindowRun:
 
     def step_inputs(self) -> dict:
         p = self.plans[self.m]
-        return dict(model_in=self.model_in, levels=self.lvl_dev[self.m], cond=self._cond_for(p.nfe),
+        return dict(model_in=self.model_in, levels=self.lvl_dev[self.m], cond=self._cond_for(p),
                     cond_mask=self.cm_dev[self.m])
 
     def advance(self, out: Optional[Tensor]) -> None:

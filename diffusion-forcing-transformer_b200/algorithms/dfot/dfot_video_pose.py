@@ -14,6 +14,7 @@ import torch
 from torch import Tensor
 
 from dfot_b200 import ops
+from . import pose_math
 from dfot_b200.config import to_config
 from .backbones.u_vit.u_vit3d_pose import PoseCondition
 from .dfot_video import DFoTVideo
@@ -24,26 +25,31 @@ def ray_freq_scale(n_freq: int = 15) -> Tensor:
     return 2 ** torch.linspace(0, n_freq - 1, n_freq, dtype=torch.float32) * math.pi
 
 
-def camera_table(conditions: Tensor, resolution: int, normalize_by: str = "first", bound=None) -> Tensor:
+def camera_table(conditions: Tensor, resolution: int, normalize_by: str = "first", bound=None,
+                 interp_mask: Optional[Tensor] = None) -> Tensor:
     """(B, T, 16) raw poses (fx, fy, px, py, row-major [R | t]) → (B, T, 16) per-frame camera table
     (fx, fy, px, py in pixels | R^-1 row-major | ray origin -R^-1 t) after the reference's normalisation
-    (geometry_utils.py:102-168: left-normalise by frame 0, optional bound scaling).  16 floats per frame: host-side
-    plumbing, fp32 like the reference (its autocast is disabled for this part, dfot_video_pose.py:64-67)."""
+    (geometry_utils.py:102-168: left-normalise by frame 0 or by the mean camera, optional bound scaling).  `interp_mask`
+    (B, T) bool marks frames whose pose is first rebuilt by interpolation (`temporal` history guidance,
+    dfot_video_pose.py:73-81).  16 floats per frame: host-side plumbing, fp32 like the reference (its autocast is
+    disabled for this part, dfot_video_pose.py:64-67)."""
     c = conditions.float()
     K, RT = c[..., :4], c[..., 4:].reshape(*c.shape[:2], 3, 4)
     R, t = RT[..., :3], RT[..., 3]
+    if interp_mask is not None:
+        R, t = pose_math.interpolate_masked_poses(R, t, interp_mask)
     if normalize_by == "first":
-        R0_inv = R[:, 0].transpose(-1, -2)
-        R = torch.einsum("btij,bjk->btik", R, R0_inv)
-        t = t - torch.einsum("btij,bj->bti", R, t[:, 0])
-    elif normalize_by == "mean":
-        raise NotImplementedError("camera_pose_conditioning.normalize_by='mean' needs quaternion averaging (roma) and "
-                                  "is outside the dfot_b200 scope; the shipped RE10K configs use 'first'")
+        R_ref, t_ref = R[:, 0], t[:, 0]
+    elif normalize_by == "mean":   # geometry_utils.py:137-155: mean quaternion (not re-normalised), mean world position
+        R_ref = pose_math.quat_to_rotmat(pose_math.rotmat_to_quat(R).mean(dim=1))
+        t_ref = torch.einsum("bij,bj->bi", R_ref, torch.einsum("btji,btj->bti", R, t).mean(dim=1))
     else:
         raise ValueError(f"Unknown camera pose normalization method: {normalize_by}")
+    R = torch.einsum("btij,bjk->btik", R, R_ref.transpose(-1, -2))     # (the reference "inverts" by transposing, :124)
+    t = t - torch.einsum("btij,bj->bti", R, t_ref)
     if bound is not None:
         t = t * (bound / t.abs().amax(dim=1, keepdim=True).clamp(min=1e-6))
-    R_inv = R.transpose(-1, -2)
+    R_inv = R.transpose(-1, -2)   # geometry_utils.py:283: the transpose, also for the scaled rotations of "mean"
     origin = -torch.einsum("btij,btj->bti", R_inv, t)
     return torch.cat([K * resolution, R_inv.reshape(*c.shape[:2], 9), origin], dim=-1).contiguous()
 
@@ -82,14 +88,23 @@ class DFoTVideoPose(DFoTVideo):
         """Reference signature; returns the lightweight handle the UViT3DPose backbone consumes."""
         return self._window_conditions(conditions, 1)
 
-    def _window_conditions(self, conditions: Optional[Tensor], nfe: int):
+    def _conditions_follow_levels(self) -> bool:
+        """`temporal` history guidance: frames at the top noise level are 'fully masked' and their camera poses are
+        rebuilt by interpolation (dfot_video_pose.py:73-81) — the conditioning then depends on the step's noise levels."""
+        return self.cfg.tasks.prediction.history_guidance.name == "temporal"
+
+    def _window_conditions(self, conditions: Optional[Tensor], nfe: int, levels_from=None):
         if conditions is None:
             return None
-        if self.cfg.tasks.prediction.history_guidance.name == "temporal":
-            raise NotImplementedError("`temporal` history guidance interpolates camera poses with roma "
-                                      "(dfot_video_pose.py:73-81), outside the dfot_b200 scope")
         cp = self.camera_pose_conditioning
-        cams = camera_table(conditions.to(self.device), self.x_shape[1], cp.normalize_by, cp.bound)
+        conditions = conditions.to(self.device)
+        if self._conditions_follow_levels() and levels_from is not None:
+            # one camera table per backbone row: rows are ordered (b nfe) like the reference's repeat (dfot_video.py:733-738)
+            mask = torch.as_tensor(levels_from == self.timesteps - 1, device=conditions.device)
+            rows = conditions.repeat_interleave(nfe, dim=0)
+            cams = camera_table(rows, self.x_shape[1], cp.normalize_by, cp.bound, interp_mask=mask)
+            return PoseCondition(cams, list(range(rows.shape[0])))
+        cams = camera_table(conditions, self.x_shape[1], cp.normalize_by, cp.bound)
         rows = [b for b in range(conditions.shape[0]) for _ in range(nfe)]
         return PoseCondition(cams, rows)
 

@@ -255,7 +255,8 @@ def install():
         RESET = ""
 
     col.Fore = _F
-    _mod("roma")
+    from . import roma_restatement           # roma 1.5.2.1 is absent: its three functions on the pose path, restated
+    roma_restatement.install(_mod("roma"))   # (pinned against scipy, tests/test_pose_quaternions.py)
     if "wandb" not in sys.modules:
         try:
             import wandb  # noqa: F401

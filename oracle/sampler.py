@@ -74,8 +74,10 @@ class SamplerOracle:
         if cond is not None and "camera_pose_conditioning" in self.cfg:   # dfot_video_pose.py:64-110
             from .pose import ray_encoding
             cp = self.cfg["camera_pose_conditioning"]
-            assert self.cfg["tasks"]["prediction"]["history_guidance"]["name"] != "temporal"
-            return ray_encoding(cond, self.x_shape[1], cp["normalize_by"], cp["bound"], cp["type"])
+            interp = None                                         # dfot_video_pose.py:73-81
+            if self.cfg["tasks"]["prediction"]["history_guidance"]["name"] == "temporal":
+                interp = noise_levels == self.timesteps - 1
+            return ray_encoding(cond, self.x_shape[1], cp["normalize_by"], cp["bound"], cp["type"], interp_mask=interp)
         if cond is None or self.cfg["external_cond_processing"] is None:
             return cond
         assert self.cfg["external_cond_processing"] == "mask_first"

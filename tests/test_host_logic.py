@@ -114,7 +114,8 @@ def test_ops_fail_loudly_without_cuda():
         pose.diffusion_model.model(torch.zeros(1, 4, 3, 32, 32), torch.zeros(1, 4), cond)
 
 
-@pytest.mark.parametrize("name", ["uvit_pose_vanilla", "uvit_pose_stabilized_interp"])
+@pytest.mark.parametrize("name", ["uvit_pose_vanilla", "uvit_pose_stabilized_interp", "uvit_pose_mean_vanilla",
+                                  "uvit_pose_temporal"])
 def test_uvit_host_orchestration_with_emulated_kernels(name, monkeypatch):
     """The product's U-ViT3DPose host side (weight packing, channel-last buffer flow, FiLM column offsets, per-window
     pose cache, row maps, K4 tables) driven by CPU restatements of the kernel contracts must reproduce the
@@ -157,8 +158,10 @@ def test_planner_end_to_end_on_cpu(name, monkeypatch):
     if "camera_pose_conditioning" in cfg:   # the oracle backbone consumes the reference's dense ray encoding
         from oracle.pose import ray_encoding
         cp = cfg["camera_pose_conditioning"]
-        algo._window_conditions = lambda c, nfe: ray_encoding(c.repeat_interleave(nfe, 0), cfg["x_shape"][1],
-                                                              cp["normalize_by"], cp["bound"], cp["type"])
+        temporal = cfg["tasks"]["prediction"]["history_guidance"]["name"] == "temporal"
+        algo._window_conditions = lambda c, nfe, levels_from=None: ray_encoding(
+            c.repeat_interleave(nfe, 0), cfg["x_shape"][1], cp["normalize_by"], cp["bound"], cp["type"],
+            interp_mask=torch.from_numpy(levels_from == cfg["diffusion"]["timesteps"] - 1) if temporal else None)
     _, backbone = build_oracle(cfg, weights)
 
     class OracleBackbone(torch.nn.Module):
