@@ -639,6 +639,9 @@ __device__ __forceinline__ void epilogue_chunk_f32_side(const Params& p, const C
 // at best) these launches ran at ~60 % of the copy bandwidth.  The residual rows do not depend on the accumulator, so
 // the warp's chunks are software-pipelined: chunk c+1's residual is requested before chunk c is transposed and stored,
 // and the first chunk's before the wait for the accumulator — i.e. under the main loop of the tile.
+#ifndef DFOT_GEMM_L2_PREFETCH_MAX_K
+#define DFOT_GEMM_L2_PREFETCH_MAX_K 1536
+#endif
 template <int EPI, int BN_>
 __device__ __forceinline__ void epilogue_tile_resid(const Params& p, uint32_t t_row, uint32_t stage_buf, int lane, int m0,
                                                     int n_base, int half, uint32_t full_bar, uint32_t parity) {
@@ -648,6 +651,29 @@ __device__ __forceinline__ void epilogue_tile_resid(const Params& p, uint32_t t_
     if (full(c)) prefetch_side<EPI, true>(p, sd, lane, m0, n_base + c * 32);
     else prefetch_side<EPI, false>(p, sd, lane, m0, n_base + c * 32);
   };
+  // ... and all of the warp's residual rows of this tile are pulled into L2 first (prefetch.global.L2 needs no
+  // scoreboard, unlike a register prefetch, whose completion the loads of the chunk in hand wait for as well): the
+  // register loads below then see L2 latency, and up to 16 KB per warp (128 KB per SM) of DRAM requests are in flight.
+  // (scripts/micro/rowpiece_bench.cu: 8 warps x 4 KB in flight top out at 2.7-3.7 TB/s of the 6.5 TB/s copy peak.)
+  // Measured on one box, M = 65536, N = K = 576: 93.8 -> 75-83 us; N = K = 1152: 58.4 -> 55-58 us; no gain for K >= 2304
+  // (tensor-bound) and -2 % on the 128-channel convolutions, which are bound by L2 -> SM operand traffic (9 taps re-read
+  // the input tile: 64 B/clk/SM of A alone against ~43 B/clk/SM of L2 bandwidth) — so small-K plain GEMMs only.
+#ifndef DFOT_GEMM_NO_L2_PREFETCH
+  if (p.K <= DFOT_GEMM_L2_PREFETCH_MAX_K && p.conv_cblks == 0) {   // (measured: see the comment above)
+    const int col = n_base + ((lane & 7) << 2), rsub = lane >> 3;
+#pragma unroll 1
+    for (int cc = half; valid(cc); cc += 2) {
+      const int cn0 = col + cc * 32;
+      if (cn0 < p.N) {
+        const float* res = p.e.resid + (int64_t)(m0 + rsub) * p.e.ld_resid + cn0;
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          if (m0 + 4 * it + rsub < p.M)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(res + (int64_t)(4 * it) * p.e.ld_resid));
+      }
+    }
+  }
+#endif
   ChunkSide<EPI> cur, nxt;
   int c = half;
   bool v = valid(c);
