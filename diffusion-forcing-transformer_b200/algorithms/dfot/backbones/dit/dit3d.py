@@ -1,4 +1,6 @@
-"""DiT3D backbone (variant=full, pos_emb_type=rope_3d) on hand-written sm_100a kernels.
+"""DiT3D backbone on hand-written sm_100a kernels: variant=full (pos_emb_type rope_3d — the shipped dit3d.yaml — learned_1d,
+sinusoidal_1d) and the factorized variants (factorized_encoder / factorized_attention, dit3d_factorized_attention.yaml:
+per layer a spatial block over the patches of a frame and a temporal block over the frames of a patch position).
 
 Drop-in for the reference class
     algorithms/dfot/backbones/dit/dit3d.py:11-192  (DiT3D),
@@ -15,6 +17,10 @@ Per forward (R rows, T frames, P patches/frame, M = R*T*P tokens, D hidden):
     per block: K1 adaLN-LN → GEMM qkv (+bias, RoPE-3D, q-scale fused in the epilogue) → K3 attention →
                GEMM proj (+bias, gate, residual fused) → K1 → GEMM fc1 (+bias, GELU) → GEMM fc2 (+gate, residual)
     K1 (final) → GEMM final → unpatchify
+Factorized variants reuse the same kernels: a spatial block is the block above with R*T "samples" of P tokens; for a
+temporal block the fp32 token stream is transposed to (row, patch, frame) order (data movement), the block runs with
+R*P "samples" of T tokens and a per-token copy of its modulation columns (the frame of a token is no longer m / P), and
+the stream is transposed back.
 """
 import math
 from typing import Optional
@@ -123,6 +129,27 @@ def sincos_1d_table(dim: int, n: int) -> torch.Tensor:
     return torch.from_numpy(np.concatenate([np.sin(out), np.cos(out)], axis=1)).float()
 
 
+def sincos_nd_table(dim: int, shape) -> torch.Tensor:
+    """dit_base.py:528-580 for an n-D grid: the per-axis tables side by side, dim/n columns each.  The reference builds the
+    grid with `np.meshgrid` and its default "xy" indexing — the first block of columns encodes the coordinate that varies
+    fastest along the flattened grid (quirk Q5) — so the same call is made here."""
+    assert dim % (2 * len(shape)) == 0
+    grid = np.meshgrid(*[np.arange(n, dtype=np.float32) for n in shape])
+    return torch.cat([sincos_1d_table_at(dim // len(shape), g.reshape(-1)) for g in grid], dim=1)
+
+
+def sincos_1d_table_at(dim: int, pos: np.ndarray) -> torch.Tensor:
+    omega = 1.0 / 10000 ** (np.arange(dim // 2, dtype=np.float64) / (dim / 2.0))
+    out = np.einsum("m,d->md", pos.astype(np.float64), omega)
+    return torch.from_numpy(np.concatenate([np.sin(out), np.cos(out)], axis=1)).float()
+
+
+class _FixedTable(nn.Module):           # SinusoidalPositionalEmbedding with a fixed n-D table (non-persistent buffer)
+    def __init__(self, dim: int, shape):
+        super().__init__()
+        self.register_buffer("pos_emb", sincos_nd_table(dim, shape).unsqueeze(0), persistent=False)
+
+
 class _AbsPosEmb(nn.Module):            # dit_base.py:504-525 (SinusoidalPositionalEmbedding, learnable or fixed)
     def __init__(self, dim: int, n_tokens: int, learnable: bool):
         super().__init__()
@@ -134,13 +161,19 @@ class _AbsPosEmb(nn.Module):            # dit_base.py:504-525 (SinusoidalPositio
 
 class _DiTBase(nn.Module):
     def __init__(self, dim: int, depth: int, spatial_mlp_ratio: Optional[float], out_channels: int,
-                 pos_emb_type: str = "rope_3d", n_tokens: int = 0):
+                 pos_emb_type: str = "rope_3d", n_tokens: int = 0, factorized: bool = False,
+                 mlp_ratio: Optional[float] = 4.0, grid=(1, 1), max_frames: int = 1):
         super().__init__()
         # dit_base.py:156: the positional embedding is registered BEFORE the blocks (named_parameters() order)
         if pos_emb_type in ("learned_1d", "sinusoidal_1d"):
             self.pos_emb = _AbsPosEmb(dim, n_tokens, pos_emb_type == "learned_1d")
-        # dit_base.py:185,192 — "full" blocks take spatial_mlp_ratio (None ⇒ no MLP; fork quirk Q2)
+        elif pos_emb_type == "sinusoidal_factorized":      # dit_base.py:265-274
+            self.spatial_pos_emb = _FixedTable(dim, tuple(grid))
+            self.temporal_pos_emb = _FixedTable(dim, (max_frames,))
+        # dit_base.py:185,192 — "full" and spatial blocks take spatial_mlp_ratio (None ⇒ no MLP; fork quirk Q2)
         self.blocks = nn.ModuleList([_Block(dim, spatial_mlp_ratio) for _ in range(depth)])
+        if factorized:                                     # dit_base.py:196-222: temporal blocks take mlp_ratio, no RoPE
+            self.temporal_blocks = nn.ModuleList([_Block(dim, mlp_ratio) for _ in range(depth)])
         self.final_layer = _FinalLayer(dim, out_channels)
 
 
@@ -180,10 +213,16 @@ class DiT3D(nn.Module):
         super().__init__()
         cfg = to_config(cfg)
         self.pos_emb_type = cfg.get("pos_emb_type", "rope_3d")
-        if cfg.get("variant", "full") != "full" or self.pos_emb_type not in ("rope_3d", "learned_1d", "sinusoidal_1d"):
-            raise NotImplementedError("dfot_b200 DiT3D supports variant=full with pos_emb_type rope_3d (the default "
-                                      "dit3d.yaml), learned_1d or sinusoidal_1d; the factorized / matrix-attention variants "
-                                      "and sinusoidal_3d (which asserts in the fork itself) are fork-only ablations")
+        self.variant = cfg.get("variant", "full")
+        self.factorized = self.variant in ("factorized_encoder", "factorized_attention")   # one code path in the fork
+        allowed = ("learned_1d", "sinusoidal_1d", "sinusoidal_factorized") if self.factorized else \
+            ("rope_3d", "learned_1d", "sinusoidal_1d")
+        if not (self.variant == "full" or self.factorized) or self.pos_emb_type not in allowed:
+            raise NotImplementedError(
+                "dfot_b200 DiT3D supports variant=full with pos_emb_type rope_3d (the default dit3d.yaml), learned_1d or "
+                "sinusoidal_1d, and the factorized_encoder / factorized_attention variants with sinusoidal_factorized "
+                "(dit3d_factorized_attention.yaml), learned_1d or sinusoidal_1d; the matrix-attention variants, rope with a "
+                "factorized variant and sinusoidal_3d (both assert in the fork itself) are not built")
         self.cfg = cfg
         self.x_shape = list(x_shape)
         self.max_tokens = max_tokens
@@ -218,9 +257,13 @@ class DiT3D(nn.Module):
             self.external_cond_embedding = None
         self.patch_embedder = _PatchEmbed(C, D, self.patch_size)
         self.dit_base = _DiTBase(D, self.depth, cfg.get("spatial_mlp_ratio", None), self.patch_size ** 2 * C,
-                                 self.pos_emb_type, max_tokens * self.num_patches)
+                                 self.pos_emb_type, max_tokens * self.num_patches, factorized=self.factorized,
+                                 mlp_ratio=cfg.get("mlp_ratio", 4.0), grid=(self.num_patches_h, self.num_patches_w),
+                                 max_frames=max_tokens)
         self.use_rope = self.pos_emb_type == "rope_3d"
         self.use_mlp = self.dit_base.blocks[0].use_mlp
+        if self.factorized and max_tokens > 128:
+            raise NotImplementedError("factorized DiT3D: temporal attention over more than 128 frames is not built")
         self._init_embedders()
         self._packed = None
         self._packed_key = None
@@ -247,6 +290,15 @@ class DiT3D(nn.Module):
     @property
     def n_tokens_per_frame(self) -> int:
         return self.num_patches
+
+    def _ordered_blocks(self):
+        """Blocks in execution order with their kind: "full" (all tokens of a row), or per layer "spatial" then "temporal"."""
+        if not self.factorized:
+            return [("full", b) for b in self.dit_base.blocks]
+        out = []
+        for sb, tb in zip(self.dit_base.blocks, self.dit_base.temporal_blocks):
+            out += [("spatial", sb), ("temporal", tb)]
+        return out
 
     # ------------------------------------------------------------------ weight packing
     def _version_key(self):
@@ -283,7 +335,7 @@ class DiT3D(nn.Module):
         wp[:, : C * p * p] = self.patch_embedder.proj.weight.detach().float().reshape(D, -1)
         P["pe_w"], P["pe_b"] = bf(wp), f32(self.patch_embedder.proj.bias)
         mods_w, mods_b = [], []
-        for blk in self.dit_base.blocks:
+        for _, blk in self._ordered_blocks():
             mods_w.append(blk.norm1.modulation[-1].weight)
             mods_b.append(blk.norm1.modulation[-1].bias)
             if blk.use_mlp:
@@ -298,14 +350,18 @@ class DiT3D(nn.Module):
         if not self.use_rope:
             # absolute position table: the residual operand of the patch-embed GEMM; without RoPE the QKV epilogue is a plain
             # bf16 store, so the softmax scale (x log2 e: the attention kernel exponentiates in base 2) is folded into W_q, b_q
-            P["pos"] = f32(self.dit_base.pos_emb.pos_emb[0])
+            if self.pos_emb_type == "sinusoidal_factorized":   # spatial table per frame now, temporal table before the
+                P["pos"] = f32(self.dit_base.spatial_pos_emb.pos_emb[0]).repeat(self.max_tokens, 1)   # first temporal block
+                P["tpos"] = f32(self.dit_base.temporal_pos_emb.pos_emb[0])
+            else:
+                P["pos"] = f32(self.dit_base.pos_emb.pos_emb[0])
             qs = torch.ones((3 * D, 1), device=dev)
             qs[:D] = LOG2E / math.sqrt(self.head_dim)
-        for blk in self.dit_base.blocks:
+        for kind, blk in self._ordered_blocks():
             qw, qb = blk.attn.qkv.weight.detach().float(), blk.attn.qkv.bias.detach().float()
             if not self.use_rope:
                 qw, qb = qw * qs, qb * qs[:, 0]
-            d = dict(qkv_w=bf(qw), qkv_b=f32(qb), proj_w=bf(blk.attn.proj.weight),
+            d = dict(kind=kind, qkv_w=bf(qw), qkv_b=f32(qb), proj_w=bf(blk.attn.proj.weight),
                      proj_b=f32(blk.attn.proj.bias))
             if blk.use_mlp:
                 d.update(fc1_w=bf(blk.mlp.fc1.weight), fc1_b=f32(blk.mlp.fc1.bias), fc2_w=bf(blk.mlp.fc2.weight),
@@ -329,15 +385,24 @@ class DiT3D(nn.Module):
             return ws
         D, C, p = self.hidden_size, self.x_shape[0], self.patch_size
         M, RT = R * T * self.num_patches, R * T
-        n_mod = (6 if self.use_mlp else 3) * self.depth + 2
+        blocks = self._ordered_blocks()
+        n_mod = sum(6 if b.use_mlp else 3 for _, b in blocks) + 2
         e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
         bf, f32 = torch.bfloat16, torch.float32
         ws = dict(feat=e((RT, 256), bf), e1=e((RT, D), bf), emb=e((RT, D), f32), cact=e((RT, D), bf),
                   mod=e((RT, n_mod * D), f32), patches=torch.zeros((M, _pad8(C * p * p)), dtype=bf, device=dev),
                   x=e((M, D), f32), y=e((M, D), f32), y16=e((M, D), bf), qkv=e((M, 3 * D), bf), att=e((M, D), bf),
                   tok=e((M, _pad8(p * p * C)), f32), out=e((R, T, *self.x_shape), out_dtype))
-        if self.use_mlp:
-            ws["h"] = e((M, self.dit_base.blocks[0].mlp.fc1.out_features), bf)
+        hidden = max([b.mlp.fc1.out_features for _, b in blocks if b.use_mlp], default=0)
+        if hidden:
+            ws["h"] = e((M, hidden), bf)
+        if self.factorized:
+            # temporal blocks: the token stream in (row, patch, frame) order, the block's modulation columns per token and the
+            # frame index of every token of that order (m = (r*P + p)*T + t  ->  frame r*T + t)
+            Pn = self.num_patches
+            m = torch.arange(M, device=dev)
+            ncol_t = (6 if self.dit_base.temporal_blocks[0].use_mlp else 3) * D
+            ws.update(xt=e((M, D), f32), mod_tok=e((M, ncol_t), f32), frame_of_tok=(m // (Pn * T)) * T + m % T)
         if not self.use_rope:
             ws["pos_rows"], ws["pos_key"] = e((M, D), f32), None     # the table repeated per row (filled lazily)
         if self.external_cond_embedding is not None:
@@ -468,25 +533,41 @@ class DiT3D(nn.Module):
         q_scale = LOG2E / math.sqrt(self.head_dim)
         col = 0
         xa, xb = ws["x"], ws["y"]
+        first_temporal = True
         for bw in Pk["blocks"]:
-            ops.adaln_layernorm(xa, mod, col, col + D, Pn, y_f32=xb, y_bf16=ws["y16"])
+            kind, ncol = bw["kind"], (6 if "fc1_w" in bw else 3) * D
+            xs, bmod, bld, bcol, tpf, n_seq, seq_len = xa, mod, ldm, col, Pn, R, Ntok
+            if kind == "spatial":            # attention inside a frame: R*T sequences of P tokens, same token order
+                n_seq, seq_len = RT, Pn
+            elif kind == "temporal":         # dit_base.py:403-410: "(b t) p c -> (b p) t c", block, and back
+                xs = ws["xt"]
+                xs.view(R, Pn, T, D).copy_(xa.view(R, T, Pn, D).permute(0, 2, 1, 3))
+                if first_temporal and "tpos" in Pk:      # temporal table, once, before the first temporal block
+                    xs.view(R * Pn, T, D).add_(Pk["tpos"][:T])
+                first_temporal = False
+                torch.index_select(mod[:, col: col + ncol], 0, ws["frame_of_tok"], out=ws["mod_tok"])
+                bmod, bld, bcol, tpf, n_seq, seq_len = ws["mod_tok"], ws["mod_tok"].shape[1], 0, 1, R * Pn, T
+            ops.adaln_layernorm(xs, bmod, bcol, bcol + D, tpf, y_f32=xb, y_bf16=ws["y16"])
             if self.use_rope:
                 ops.gemm_bf16(ws["y16"], bw["qkv_w"], ws["qkv"], ops.EPI_QKV_ROPE_BF16, bias=bw["qkv_b"],
                               rope_cs=Pk["rope"], tokens_per_sample=Ntok, model_dim=D, head_dim=self.head_dim,
                               q_scale=q_scale)
             else:
                 ops.gemm_bf16(ws["y16"], bw["qkv_w"], ws["qkv"], ops.EPI_BF16, bias=bw["qkv_b"])
-            ops.attention(ws["qkv"], ws["att"], R, Ntok, self.num_heads, self.head_dim)
+            ops.attention(ws["qkv"], ws["att"], n_seq, seq_len, self.num_heads, self.head_dim)
             # x1 = y + gate1 * proj(att)   (residual base is the modulated tensor — reference quirk Q1)
-            ops.gemm_bf16(ws["att"], bw["proj_w"], xa, ops.EPI_GATE_RESID_F32, bias=bw["proj_b"], resid=xb,
-                          gate=mod[:, col + 2 * D:], ld_gate=ldm, tokens_per_frame=Pn)
-            col += 3 * D
-            if self.use_mlp:
-                ops.adaln_layernorm(xa, mod, col, col + D, Pn, y_f32=xb, y_bf16=ws["y16"])
-                ops.gemm_bf16(ws["y16"], bw["fc1_w"], ws["h"], ops.EPI_GELU_BF16, bias=bw["fc1_b"])
-                ops.gemm_bf16(ws["h"], bw["fc2_w"], xa, ops.EPI_GATE_RESID_F32, bias=bw["fc2_b"], resid=xb,
-                              gate=mod[:, col + 2 * D:], ld_gate=ldm, tokens_per_frame=Pn)
-                col += 3 * D
+            ops.gemm_bf16(ws["att"], bw["proj_w"], xs, ops.EPI_GATE_RESID_F32, bias=bw["proj_b"], resid=xb,
+                          gate=bmod[:, bcol + 2 * D:], ld_gate=bld, tokens_per_frame=tpf)
+            if "fc1_w" in bw:
+                bcol += 3 * D
+                hbuf = ws["h"][:, : bw["fc1_w"].shape[0]]
+                ops.adaln_layernorm(xs, bmod, bcol, bcol + D, tpf, y_f32=xb, y_bf16=ws["y16"])
+                ops.gemm_bf16(ws["y16"], bw["fc1_w"], hbuf, ops.EPI_GELU_BF16, bias=bw["fc1_b"])
+                ops.gemm_bf16(hbuf, bw["fc2_w"], xs, ops.EPI_GATE_RESID_F32, bias=bw["fc2_b"], resid=xb,
+                              gate=bmod[:, bcol + 2 * D:], ld_gate=bld, tokens_per_frame=tpf)
+            col += ncol
+            if kind == "temporal":
+                xa.view(R, T, Pn, D).copy_(xs.view(R, Pn, T, D).permute(0, 2, 1, 3))
         # --- final layer + unpatchify
         ops.adaln_layernorm(xa, mod, col, col + D, Pn, y_bf16=ws["y16"])
         ops.gemm_bf16(ws["y16"], Pk["fin_w"], ws["tok"], ops.EPI_F32, bias=Pk["fin_b"])

@@ -1,4 +1,6 @@
-"""ORACLE (test infrastructure): DiT3D backbone forward (variant=full; rope_3d, learned_1d or sinusoidal_1d positions),
+"""ORACLE (test infrastructure): DiT3D backbone forward — variant=full (rope_3d, learned_1d or sinusoidal_1d positions) and
+the factorized variants (factorized_encoder / factorized_attention: per layer a spatial block over the patches of a frame,
+then a temporal block over the frames of a patch position; sinusoidal_factorized, learned_1d or sinusoidal_1d positions) —
 functional over a reference-keyed state dict.
 
 Restates
@@ -61,6 +63,21 @@ def apply_rope(x: torch.Tensor, angles: torch.Tensor) -> torch.Tensor:
     return x * a.cos() + rot * a.sin()
 
 
+def sincos_nd_table(dim: int, shape) -> torch.Tensor:
+    """dit_base.py:528-580 (get_nd_sincos_pos_embed): [prod(shape), dim]; `np.meshgrid` with its default "xy" indexing, so
+    for a 2-D grid the FIRST dim/2 columns encode the coordinate that varies fastest (quirk Q5)."""
+    import numpy as np
+    assert dim % (2 * len(shape)) == 0
+    grid = np.stack(np.meshgrid(*[np.arange(n, dtype=np.float32) for n in shape]), axis=0)
+    d = dim // len(shape)
+    omega = 1.0 / 10000 ** (np.arange(d // 2, dtype=np.float64) / (d / 2.0))
+    parts = []
+    for i in range(len(shape)):
+        ang = np.einsum("m,d->md", grid[i].reshape(-1), omega)
+        parts.append(np.concatenate([np.sin(ang), np.cos(ang)], axis=1))
+    return torch.from_numpy(np.concatenate(parts, axis=1)).float()
+
+
 def _linear(x, sd, prefix):
     return F.linear(x, sd[prefix + ".weight"], sd.get(prefix + ".bias"))
 
@@ -79,7 +96,10 @@ class DiT3DOracle:
                  external_cond_dim: int = 0):
         cfg = backbone_cfg
         self.pos_emb_type = cfg.get("pos_emb_type", "rope_3d")
-        assert cfg.get("variant", "full") == "full" and self.pos_emb_type in ("rope_3d", "learned_1d", "sinusoidal_1d")
+        self.factorized = cfg.get("variant", "full") in ("factorized_encoder", "factorized_attention")
+        assert cfg.get("variant", "full") == "full" or self.factorized
+        assert self.pos_emb_type in (("learned_1d", "sinusoidal_1d", "sinusoidal_factorized") if self.factorized
+                                     else ("rope_3d", "learned_1d", "sinusoidal_1d"))
         self.sd = {k: v.detach().float() for k, v in state_dict.items()}
         self.p = cfg["patch_size"]
         self.C, self.H, self.W = x_shape
@@ -102,6 +122,9 @@ class DiT3DOracle:
             omega = 1.0 / 10000 ** (np.arange(self.D // 2, dtype=np.float64) / (self.D / 2.0))
             ang = np.einsum("m,d->md", np.arange(n, dtype=np.float32).astype(np.float64), omega)
             self.pos_emb = torch.from_numpy(np.concatenate([np.sin(ang), np.cos(ang)], axis=1)).float().unsqueeze(0)
+        if self.pos_emb_type == "sinusoidal_factorized":   # dit_base.py:265-274: 2-D spatial table + 1-D temporal table
+            self.spatial_pos = sincos_nd_table(self.D, (self.gh, self.gw)).unsqueeze(0)
+            self.temporal_pos = sincos_nd_table(self.D, (max_tokens,)).unsqueeze(0)
         # dit_base.py:185,192: MLP exists only if spatial_mlp_ratio is set (fork quirk Q2)
         self.use_mlp = "dit_base.blocks.0.mlp.fc1.weight" in self.sd
         self.taps = None  # optional dict filled with intermediates for kernel-level parity tests
@@ -128,9 +151,9 @@ class DiT3DOracle:
             e = torch.where(cond_mask.reshape(-1, *([1] * (e.ndim - 1))), torch.zeros_like(e), e)
         return e
 
-    def attention(self, y: torch.Tensor, i: int) -> torch.Tensor:
+    def attention(self, y: torch.Tensor, i: int, group: str = "blocks") -> torch.Tensor:
         B, N, D = y.shape
-        qkv = _linear(y, self.sd, f"dit_base.blocks.{i}.attn.qkv")
+        qkv = _linear(y, self.sd, f"dit_base.{group}.{i}.attn.qkv")
         q, k, v = qkv.reshape(B, N, 3, self.heads, self.dh).permute(2, 0, 3, 1, 4).unbind(0)
         if self.angles is not None:
             q, k = apply_rope(q, self.angles), apply_rope(k, self.angles)
@@ -138,7 +161,34 @@ class DiT3DOracle:
         o = (w @ v).transpose(1, 2).reshape(B, N, D)
         if self.taps is not None and i == 0:
             self.taps.update(q0=q, k0=k, v0=v, attn0=o)
-        return _linear(o, self.sd, f"dit_base.blocks.{i}.attn.proj")
+        return _linear(o, self.sd, f"dit_base.{group}.{i}.attn.proj")
+
+    def block(self, h, c_act, i: int, group: str):
+        """dit_blocks.py:488-510 (the MLP exists iff the block was built with a positive ratio)."""
+        sd, pre = self.sd, f"dit_base.{group}.{i}"
+        y, gate = _adaln(h, c_act, sd, pre + ".norm1", 3)
+        h = y + gate * self.attention(y, i, group)               # residual base is the modulated tensor (Q1)
+        if pre + ".mlp.fc1.weight" in sd:
+            z, gate2 = _adaln(h, c_act, sd, pre + ".norm2", 3)
+            m = _linear(F.gelu(_linear(z, sd, pre + ".mlp.fc1"), approximate="tanh"), sd, pre + ".mlp.fc2")
+            h = z + gate2 * m
+        return h
+
+    def factorized_blocks(self, tok, c_act, B: int, T: int):
+        """dit_base.py:355-412 for the factorized variants: tokens (b, t, p); every layer runs a spatial block on
+        ((b t), p) and a temporal block on ((b p), t); the temporal table is added before the first temporal block."""
+        P, D = self.P, self.D
+        h, c = tok.reshape(B, T, P, D), c_act.reshape(B, T, P, D)
+        if self.pos_emb_type == "sinusoidal_factorized":
+            h = h + self.spatial_pos[:, :P].reshape(1, 1, P, D)
+        for i in range(self.depth):
+            h = self.block(h.reshape(B * T, P, D), c.reshape(B * T, P, D), i, "blocks").reshape(B, T, P, D)
+            ht, ct = h.transpose(1, 2).reshape(B * P, T, D), c.transpose(1, 2).reshape(B * P, T, D)
+            if i == 0 and self.pos_emb_type == "sinusoidal_factorized":
+                ht = ht + self.temporal_pos[:, :T]
+            ht = self.block(ht, ct, i, "temporal_blocks")
+            h = ht.reshape(B, P, T, D).transpose(1, 2)
+        return h.reshape(B, T * P, D)
 
     def __call__(self, x, noise_levels, external_cond=None, external_cond_mask=None):
         B, T = x.shape[:2]
@@ -146,7 +196,7 @@ class DiT3DOracle:
         tok = F.conv2d(x.reshape(B * T, self.C, self.H, self.W).float(), sd["patch_embedder.proj.weight"],
                        sd["patch_embedder.proj.bias"], stride=self.p)
         tok = tok.flatten(2).transpose(1, 2).reshape(B, T * self.P, self.D)
-        if self.angles is None:
+        if self.angles is None and self.pos_emb_type != "sinusoidal_factorized":
             tok = tok + self.pos_emb[:, : tok.shape[1]]             # dit_base.py:352-353, 523-525
         emb = self.noise_embedding(noise_levels)
         if external_cond is not None:
@@ -156,7 +206,7 @@ class DiT3DOracle:
                 emb = emb + self.cond_embedding(external_cond.float(), external_cond_mask)
         c_act = F.silu(emb.repeat_interleave(self.P, dim=1))      # per-token copy of a per-frame vector
         h = tok
-        for i in range(self.depth):
+        for i in range(0 if self.factorized else self.depth):
             pre = f"dit_base.blocks.{i}"
             y, gate = _adaln(h, c_act, sd, pre + ".norm1", 3)
             h = y + gate * self.attention(y, i)                    # residual base is the modulated tensor (Q1)
@@ -166,6 +216,8 @@ class DiT3DOracle:
                 h = z + gate2 * m
             if self.taps is not None and i == 0:
                 self.taps.update(block0=h)
+        if self.factorized:
+            h = self.factorized_blocks(tok, c_act, B, T)
         h = _adaln(h, c_act, sd, "dit_base.final_layer.norm_final", 2)
         h = _linear(h, sd, "dit_base.final_layer.linear")           # [B, T*P, p*p*C]
         h = h.reshape(B, T, self.gh, self.gw, self.p, self.p, self.C)
