@@ -21,6 +21,7 @@ B200-first execution model (not a translation):
     the reference (dfot_video_pose.py:64-110) is never materialised on the fast path.
 """
 import math
+import os
 from typing import List, Optional
 
 import torch
@@ -29,6 +30,8 @@ from torch import nn
 from dfot_b200 import _abi, ops
 from dfot_b200.config import to_config
 from ..dit.dit3d import LOG2E, _Fourier, _NoiseLevelEmbedding, _PatchEmbed, _pad8, rope_cos_sin_table  # noqa: F401
+# q/k-norm + RoPE ride on the QKV GEMM's epilogue from this width on (DFOT_UVIT_FUSE_QKNORM_MIN_CH pins it: benchmarking)
+_FUSE_QKNORM_MIN_CH = int(os.environ.get("DFOT_UVIT_FUSE_QKNORM_MIN_CH", "1024"))
 
 
 # ------------------------------------------------------------------ parameter containers (reference key names)
@@ -504,7 +507,7 @@ class UViT3DPose(nn.Module):
                     dh = ch // self.num_heads
                     Ntok = T * HW
                     ops.rmsnorm_film_bf16(src, bw["norm_w"], mod, sc, sh, HW, w["a16"], mod_pix=cache, img_map=img_map)
-                    if ch >= 1024:
+                    if ch >= _FUSE_QKNORM_MIN_CH:
                         # wide levels (K >= 1024: the GEMM is MMA-bound, its epilogue has slack): q/k RMSNorm(head_dim)
                         # + RoPE-3D + softmax scale ride on the QKV GEMM's epilogue, from the fp32 accumulators
                         ops.gemm_bf16(w["a16"], bw["qkv_w"], w["qkv"], ops.EPI_QKNORM_ROPE_BF16, bias=bw["qkv_b"],
@@ -512,7 +515,8 @@ class UViT3DPose(nn.Module):
                                       q_scale=LOG2E / math.sqrt(dh), qn_w=bw["qn_w"], kn_w=bw["kn_w"])
                     else:
                         # narrow levels (K = 576 at RE10K): the GEMM is epilogue-bound, a separate HBM-bound pass is
-                        # cheaper than a heavier epilogue (measured: 134.2 vs 132.7 NFE/s)
+                        # cheaper than a heavier epilogue (measured: 134.2 vs 132.7 NFE/s in r01; 11.01 vs 10.93 frames/s
+                        # after the r02 issue fix)
                         ops.gemm_bf16(w["a16"], bw["qkv_w"], w["qkv"], ops.EPI_BF16, bias=bw["qkv_b"])
                         ops.qk_norm_rope(w["qkv"], bw["qn_w"], bw["kn_w"], Pk["rope"][i], Ntok, self.num_heads, dh,
                                          LOG2E / math.sqrt(dh))
