@@ -656,8 +656,9 @@ __device__ __forceinline__ void epilogue_tile_resid(const Params& p, uint32_t t_
   // register loads below then see L2 latency, and up to 16 KB per warp (128 KB per SM) of DRAM requests are in flight.
   // (scripts/micro/rowpiece_bench.cu: 8 warps x 4 KB in flight top out at 2.7-3.7 TB/s of the 6.5 TB/s copy peak.)
   // Measured on one box, M = 65536, N = K = 576: 93.8 -> 75-83 us; N = K = 1152: 58.4 -> 55-58 us; no gain for K >= 2304
-  // (tensor-bound) and -2 % on the 128-channel convolutions, which are bound by L2 -> SM operand traffic (9 taps re-read
-  // the input tile: 64 B/clk/SM of A alone against ~43 B/clk/SM of L2 bandwidth) — so small-K plain GEMMs only.
+  // (tensor-bound) and -2 % on the 128-channel convolutions, which are bound by the SM's TMA fill rate (9 taps re-read
+  // the input tile: 94 B/clk/SM at the full MMA rate against the 69 B/clk/SM scripts/micro/tma_fill_bench.cu measures)
+  // — so small-K plain GEMMs only.
 #ifndef DFOT_GEMM_NO_L2_PREFETCH
   if (p.K <= DFOT_GEMM_L2_PREFETCH_MAX_K && p.conv_cblks == 0) {   // (measured: see the comment above)
     const int col = n_base + ((lane & 7) << 2), rsub = lane >> 3;
