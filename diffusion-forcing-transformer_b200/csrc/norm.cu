@@ -83,7 +83,9 @@ extern "C" int dfot_adaln_layernorm(const float* x, const float* mod, int64_t mo
                                                               tokens_per_frame, eps)
   if (D <= 256) LAUNCH(2);
   else if (D <= 512) LAUNCH(4);
+  else if (D <= 768) LAUNCH(6);
   else if (D <= 1024) LAUNCH(8);
+  else if (D <= 1152) LAUNCH(9);      // (DiT-XL: 36 instead of 48 data registers per lane — more rows resident per SM)
   else if (D <= 1536) LAUNCH(12);
   else if (D <= 2048) LAUNCH(16);
   else LAUNCH(32);

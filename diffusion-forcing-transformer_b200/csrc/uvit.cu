@@ -124,9 +124,18 @@ __global__ void gn_finalize_kernel(const double* __restrict__ sums, float2* __re
 // grid (pixel slabs, images); a thread owns ONE 8-channel vector (so gamma / beta / statistics / per-image FiLM are
 // loaded once and folded into a per-channel affine) and walks kGnPix pixels of its slab with all loads issued up
 // front — no 64-bit index arithmetic, 4 independent 16/32-byte loads in flight per thread.
-constexpr int kGnPix = 2, kGnIter = 4;
+// Pixels in flight per thread and resident blocks per SM.  Measured on B200 (bf16 input + per-pixel FiLM stream, 64 x 128² x
+// 128): 2 pixels x 3 blocks 169.5 us (4.75 TB/s), 4 x 2 181, 2 x 4 186, 1 x 4 141.9 us (5.68 TB/s = 87 % of the copy peak),
+// 1 x 5 154, 1 x 6 163: many light threads beat few heavy ones; the f32 path is unchanged (123.5-124.4 us, 6.5 TB/s).
+#ifndef DFOT_GN_BLOCKS
+#define DFOT_GN_BLOCKS 4
+#endif
+#ifndef DFOT_GN_PIX
+#define DFOT_GN_PIX 1
+#endif
+constexpr int kGnPix = DFOT_GN_PIX, kGnIter = 8 / DFOT_GN_PIX;
 template <typename TX, bool SILU = true>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, DFOT_GN_BLOCKS)
 gn_silu_kernel(const TX* __restrict__ x, const float2* __restrict__ stats, const float* __restrict__ gamma,
                const float* __restrict__ beta, const float* __restrict__ mod_img, int64_t ld_img,
                int64_t scale_col, int64_t shift_col, const __nv_bfloat16* __restrict__ mod_pix,
@@ -224,8 +233,10 @@ gn_silu_kernel(const TX* __restrict__ x, const float2* __restrict__ stats, const
 
 // ------------------------------------------------------------------ RMSNorm + FiLM -> bf16 (warp per token)
 constexpr int kNormWarps = 4;
+// Resident blocks per SM (register cap): measured on B200, D = 1152 (NV = 9): 5 blocks 30.1 us, 6 31.4, 8 35.8 (spills),
+// uncapped 31.3-33.5; D = 576 (NV = 5): 8 blocks 55.0 us, uncapped 56.9.
 template <int NV>
-__global__ void __launch_bounds__(kNormWarps * 32)
+__global__ void __launch_bounds__(kNormWarps * 32, NV >= 8 ? 5 : 8)
 rmsnorm_film_kernel(const float* __restrict__ x, const float* __restrict__ weight, float eps,
                     const float* __restrict__ mod_img, int64_t ld_img, int64_t scale_col, int64_t shift_col,
                     const __nv_bfloat16* __restrict__ mod_pix, const int32_t* __restrict__ img_map,
@@ -293,6 +304,8 @@ rmsnorm_film_kernel(const float* __restrict__ x, const float* __restrict__ weigh
 // pieces: a lane owns 8 adjacent elements (4 rotation pairs) of one head, LPH = DH/8 lanes share a head and one load
 // instruction covers 32/LPH heads (512 contiguous bytes).  ALL pieces of the token are loaded before the first reduction
 // (NI loads in flight per lane, one DRAM round trip per token); head sums are xor-shuffles inside the LPH-lane group.
+// (register cap measured on B200, d = 64: uncapped = 3 blocks/SM 63.9 us, 1 block 73.3, 4 blocks 99.0 (spills); d = 128 needs
+// the uncapped allocation: 28.4 us vs 60.0 with a 3-block cap)
 template <int DH, int NI>
 __global__ void __launch_bounds__(kThreads)
 qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, const float* __restrict__ qw,
