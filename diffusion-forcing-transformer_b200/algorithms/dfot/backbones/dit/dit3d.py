@@ -1,10 +1,13 @@
 """DiT3D backbone on hand-written sm_100a kernels: variant=full (pos_emb_type rope_3d — the shipped dit3d.yaml — learned_1d,
-sinusoidal_1d) and the factorized variants (factorized_encoder / factorized_attention, dit3d_factorized_attention.yaml:
-per layer a spatial block over the patches of a frame and a temporal block over the frames of a patch position).
+sinusoidal_1d), the factorized variants (factorized_encoder / factorized_attention, dit3d_factorized_attention.yaml:
+per layer a spatial block over the patches of a frame and a temporal block over the frames of a patch position) and the
+matrix-attention variants (full_matrix_attention / factorized_matrix_attention with matrix_block=matrix,
+dit3d_full_matrix.yaml / dit3d_factorized_matrix.yaml: frames are the attention tokens of a MatrixDiTBlock).
 
 Drop-in for the reference class
     algorithms/dfot/backbones/dit/dit3d.py:11-192  (DiT3D),
-    algorithms/dfot/backbones/dit/dit_base.py:77-425 (DiTBase), dit_blocks.py:378-542 (blocks)
+    algorithms/dfot/backbones/dit/dit_base.py:77-425 (DiTBase), dit_blocks.py:378-542 (blocks),
+    dit_blocks.py:211-350 (MatrixAttention), :549-652 (MatrixDiTBlock)
 same constructor signature, same ``forward(x, noise_levels, external_cond, external_cond_mask)`` and the
 same ``state_dict()`` keys, so a reference checkpoint loads unchanged.  Parameters are kept in fp32
 under the reference's names; kernel-layout copies (bf16, concatenated modulation weights, padded
@@ -21,6 +24,12 @@ Factorized variants reuse the same kernels: a spatial block is the block above w
 temporal block the fp32 token stream is transposed to (row, patch, frame) order (data movement), the block runs with
 R*P "samples" of T tokens and a per-token copy of its modulation columns (the frame of a token is no longer m / P), and
 the stream is transposed back.
+A matrix block keeps the (row, frame, patch) token order and per-frame modulation of a full block; its attention is
+    K1 adaLN-LN → patch-mix (the `qkv_u` factor: P patch rows of a frame → Mc rows) → GEMM qkv_v on R*Mc*T rows (+ 1-D RoPE
+    over the frame index, q-scale) → K3 attention over the T frames (R*Mc sequences) → GEMM proj_v → patch-expand (the
+    `proj_u` factor back to P rows, + proj_bias, gate, residual)
+i.e. the u factor is contracted first (the reference's einsum 'nm,blnd,dk->blmk' leaves the order open), so the GEMMs see
+Mc rows per frame instead of P.
 """
 import math
 from typing import Optional
@@ -113,6 +122,43 @@ class _Block(nn.Module):                # dit_blocks.py:440-510
             nn.init.zeros_(lin.bias)
 
 
+class _MatrixAttention(nn.Module):      # dit_blocks.py:215-287 (parameters in the reference's registration order)
+    def __init__(self, col_dim: int, row_dim: int, embed_col_dim: int, embed_row_dim: int, use_bias: bool,
+                 fixed_u: Optional[str]):
+        super().__init__()
+        self.fixed_u = fixed_u
+        if fixed_u is None:
+            self.qkv_u = nn.Parameter(torch.empty(col_dim, embed_col_dim))
+            self.proj_u = nn.Parameter(torch.empty(embed_col_dim, col_dim))
+        elif fixed_u == "identity":      # plain tensors in the reference (:267-269), not part of the state dict
+            if embed_col_dim != col_dim:
+                raise ValueError("fixed_u='identity' needs embed_col_dim == the number of patches per frame")
+        else:
+            raise ValueError(f"Invalid fixed_u value: {fixed_u}. It should be 'identity', None")
+        self.qkv_v = nn.Parameter(torch.empty(row_dim, 3 * embed_row_dim))
+        self.proj_v = nn.Parameter(torch.empty(embed_row_dim, row_dim))
+        if use_bias:
+            self.qkv_bias = nn.Parameter(torch.zeros(embed_col_dim, 3 * embed_row_dim))
+            self.proj_bias = nn.Parameter(torch.zeros(col_dim, row_dim))
+        for w in [self.qkv_v, self.proj_v] + ([self.qkv_u, self.proj_u] if fixed_u is None else []):
+            nn.init.xavier_uniform_(w)                   # dit_blocks.py:604-621
+
+
+class _MatrixBlock(nn.Module):          # dit_blocks.py:549-652
+    def __init__(self, col_dim: int, dim: int, embed_col_dim: int, mlp_ratio: Optional[float], use_bias: bool,
+                 fixed_u: Optional[str]):
+        super().__init__()
+        self.norm1 = _AdaLN(dim, 3)
+        self.attn = _MatrixAttention(col_dim, dim, embed_col_dim, dim, use_bias, fixed_u)
+        self.use_mlp = mlp_ratio is not None and mlp_ratio > 0.0
+        if self.use_mlp:
+            self.norm2 = _AdaLN(dim, 3)
+            self.mlp = _Mlp(dim, int(dim * mlp_ratio))
+            for lin in (self.mlp.fc1, self.mlp.fc2):
+                nn.init.xavier_uniform_(lin.weight)
+                nn.init.zeros_(lin.bias)
+
+
 class _FinalLayer(nn.Module):           # dit_blocks.py:513-542
     def __init__(self, dim: int, out_channels: int):
         super().__init__()
@@ -162,8 +208,19 @@ class _AbsPosEmb(nn.Module):            # dit_base.py:504-525 (SinusoidalPositio
 class _DiTBase(nn.Module):
     def __init__(self, dim: int, depth: int, spatial_mlp_ratio: Optional[float], out_channels: int,
                  pos_emb_type: str = "rope_3d", n_tokens: int = 0, factorized: bool = False,
-                 mlp_ratio: Optional[float] = 4.0, grid=(1, 1), max_frames: int = 1):
+                 mlp_ratio: Optional[float] = 4.0, grid=(1, 1), max_frames: int = 1, matrix: Optional[dict] = None):
         super().__init__()
+        if matrix is not None:                             # dit_base.py:254-258 (sinusoidal_2d), :159-222
+            self.pos_emb = _FixedTable(dim, tuple(grid))
+            mk = lambda: _MatrixBlock(grid[0] * grid[1], dim, matrix["embed_col_dim"], mlp_ratio, matrix["use_bias"],
+                                      matrix["fixed_u"])
+            if matrix["full"]:
+                self.blocks = nn.ModuleList([mk() for _ in range(depth)])
+            else:
+                self.blocks = nn.ModuleList([_Block(dim, spatial_mlp_ratio) for _ in range(depth)])
+                self.temporal_blocks = nn.ModuleList([mk() for _ in range(depth)])
+            self.final_layer = _FinalLayer(dim, out_channels)
+            return
         # dit_base.py:156: the positional embedding is registered BEFORE the blocks (named_parameters() order)
         if pos_emb_type in ("learned_1d", "sinusoidal_1d"):
             self.pos_emb = _AbsPosEmb(dim, n_tokens, pos_emb_type == "learned_1d")
@@ -200,6 +257,13 @@ def rope_cos_sin_table(head_dim: int, sizes, theta: float = 10000.0) -> torch.Te
     return torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()
 
 
+def rope_1d_cos_sin_table(dim: int, n: int, theta: float = 10000.0) -> torch.Tensor:
+    """[n, dim/2, 2] (cos, sin) of RotaryEmbedding1D's pair angles (embeddings.py:218-231, 189-198)."""
+    inv = 1.0 / (theta ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim))
+    ang = torch.arange(n, dtype=torch.float32)[:, None] * inv[None, :]
+    return torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()
+
+
 def _pad8(n: int) -> int:
     return (n + 7) // 8 * 8
 
@@ -215,14 +279,19 @@ class DiT3D(nn.Module):
         self.pos_emb_type = cfg.get("pos_emb_type", "rope_3d")
         self.variant = cfg.get("variant", "full")
         self.factorized = self.variant in ("factorized_encoder", "factorized_attention")   # one code path in the fork
-        allowed = ("learned_1d", "sinusoidal_1d", "sinusoidal_factorized") if self.factorized else \
+        self.matrix = self.variant in ("full_matrix_attention", "factorized_matrix_attention")
+        allowed = ("sinusoidal_2d",) if self.matrix else \
+            ("learned_1d", "sinusoidal_1d", "sinusoidal_factorized") if self.factorized else \
             ("rope_3d", "learned_1d", "sinusoidal_1d")
-        if not (self.variant == "full" or self.factorized) or self.pos_emb_type not in allowed:
+        if not (self.variant == "full" or self.factorized or self.matrix) or self.pos_emb_type not in allowed:
             raise NotImplementedError(
                 "dfot_b200 DiT3D supports variant=full with pos_emb_type rope_3d (the default dit3d.yaml), learned_1d or "
-                "sinusoidal_1d, and the factorized_encoder / factorized_attention variants with sinusoidal_factorized "
-                "(dit3d_factorized_attention.yaml), learned_1d or sinusoidal_1d; the matrix-attention variants, rope with a "
-                "factorized variant and sinusoidal_3d (both assert in the fork itself) are not built")
+                "sinusoidal_1d, the factorized_encoder / factorized_attention variants with sinusoidal_factorized "
+                "(dit3d_factorized_attention.yaml), learned_1d or sinusoidal_1d, and the matrix-attention variants with "
+                "sinusoidal_2d (dit3d_full_matrix.yaml, dit3d_factorized_matrix.yaml); rope with a factorized variant and "
+                "sinusoidal_3d (both assert in the fork itself) are not built")
+        if self.matrix:
+            self._check_matrix_cfg(cfg)
         self.cfg = cfg
         self.x_shape = list(x_shape)
         self.max_tokens = max_tokens
@@ -234,12 +303,17 @@ class DiT3D(nn.Module):
         C, H, W = self.x_shape
         self.num_patches_h, self.num_patches_w = H // self.patch_size, W // self.patch_size
         self.num_patches = self.num_patches_h * self.num_patches_w
-        self.hidden_size = D = cfg.hidden_size
-        self.num_heads = cfg.num_heads
-        self.head_dim = D // self.num_heads
+        self.hidden_size = D = cfg.embed_row_dim if self.matrix else cfg.hidden_size      # dit3d.py:113-118
         self.depth = cfg.depth
-        if D % self.num_heads or self.head_dim not in (64, 72, 128):
-            raise NotImplementedError(f"head_dim {self.head_dim} unsupported by the attention kernel (64, 72, 128)")
+        self.has_token_attention = self.variant != "full_matrix_attention"     # plain DiT blocks somewhere in the stack
+        if self.has_token_attention:
+            self.num_heads = cfg.num_heads
+            self.head_dim = D // self.num_heads
+            assert D % self.num_heads == 0, "dim should be divisible by num_heads"      # dit_blocks.py:66
+            if self.head_dim not in (64, 72, 128):
+                raise NotImplementedError(f"head_dim {self.head_dim} unsupported by the attention kernel (64, 72, 128)")
+        else:
+            self.num_heads, self.head_dim = 0, 0
         self.external_cond_dropout = cfg.get("external_cond_dropout", 0.0)
 
         self.noise_level_pos_embedding = _NoiseLevelEmbedding(256, D, bool(cfg.get("use_fourier_noise_embedding",
@@ -256,14 +330,18 @@ class DiT3D(nn.Module):
         else:
             self.external_cond_embedding = None
         self.patch_embedder = _PatchEmbed(C, D, self.patch_size)
+        matrix = None
+        if self.matrix:
+            matrix = dict(full=self.variant == "full_matrix_attention", embed_col_dim=self.matrix_cols,
+                          use_bias=bool(cfg.use_bias), fixed_u=cfg.get("fixed_u", None))
         self.dit_base = _DiTBase(D, self.depth, cfg.get("spatial_mlp_ratio", None), self.patch_size ** 2 * C,
                                  self.pos_emb_type, max_tokens * self.num_patches, factorized=self.factorized,
                                  mlp_ratio=cfg.get("mlp_ratio", 4.0), grid=(self.num_patches_h, self.num_patches_w),
-                                 max_frames=max_tokens)
+                                 max_frames=max_tokens, matrix=matrix)
         self.use_rope = self.pos_emb_type == "rope_3d"
         self.use_mlp = self.dit_base.blocks[0].use_mlp
-        if self.factorized and max_tokens > 128:
-            raise NotImplementedError("factorized DiT3D: temporal attention over more than 128 frames is not built")
+        if (self.factorized or self.matrix) and max_tokens > 128:
+            raise NotImplementedError("factorized / matrix DiT3D: temporal attention over more than 128 frames is not built")
         self._init_embedders()
         self._packed = None
         self._packed_key = None
@@ -272,6 +350,36 @@ class DiT3D(nn.Module):
         # kernels, so replaying a captured graph removes the host launch cost from the sampling loop.
         self.use_cuda_graph = True
         self._graphs = {}
+
+    def _check_matrix_cfg(self, cfg) -> None:
+        """dit_base.py:129-149 (the reference's own assertions) + what the kernels cover: one row per column head
+        (embed_col_dim == num_col_heads — every shipped matrix configuration has both = 1), so a head's feature is one
+        [1, head_row_dim] row and `flatten_matrix_rope` / `matrix_multi_token` do not change the computation (checked
+        against the executed reference, oracle/make_goldens_matrix.py)."""
+        if cfg.get("matrix_block") != "matrix":
+            raise NotImplementedError(f"matrix_block={cfg.get('matrix_block')!r}: only MatrixDiTBlock ('matrix', the shipped "
+                                      "configurations) is built, not the matrix_self / matrix_cross ablations")
+        for k in ("embed_col_dim", "embed_row_dim", "num_col_heads", "num_row_heads", "use_bias"):
+            assert cfg.get(k) is not None, f"{k} must be specified for matrix attention"
+        if self.variant == "factorized_matrix_attention":
+            assert cfg.get("spatial_mlp_ratio") is not None, "spatial_mlp_ratio must be specified for matrix attention"
+        assert cfg.embed_row_dim % cfg.num_row_heads == 0, "embed_row_dim must be divisible by num_row_heads"
+        assert cfg.embed_col_dim % cfg.num_col_heads == 0, "embed_col_dim must be divisible by num_col_heads"
+        if cfg.embed_col_dim != cfg.num_col_heads:
+            raise NotImplementedError("matrix attention with more than one row per column head "
+                                      "(embed_col_dim > num_col_heads) is not built")
+        if cfg.get("flatten_matrix_rope") and cfg.get("matrix_multi_token"):
+            raise AssertionError("flatten_rope and multi_token cannot be used together.")      # dit_blocks.py:253
+        self.matrix_cols = cfg.embed_col_dim
+        self.matrix_heads = cfg.num_row_heads
+        self.matrix_head_dim = cfg.embed_row_dim // cfg.num_row_heads
+        self.matrix_rope = bool(cfg.get("use_temporal_rope", False))
+        if self.matrix_head_dim not in (64, 72, 128):
+            raise NotImplementedError(f"matrix head dim {self.matrix_head_dim} unsupported by the attention kernel "
+                                      "(64, 72, 128)")
+        if cfg.use_bias and self.matrix_cols != 1:
+            raise NotImplementedError("matrix attention: use_bias with embed_col_dim > 1 is not built (the bias row "
+                                      "depends on the column head)")
 
     # dit3d.py:91-108
     def _init_embedders(self):
@@ -293,11 +401,13 @@ class DiT3D(nn.Module):
 
     def _ordered_blocks(self):
         """Blocks in execution order with their kind: "full" (all tokens of a row), or per layer "spatial" then "temporal"."""
-        if not self.factorized:
+        if self.variant == "full_matrix_attention":
+            return [("matrix", b) for b in self.dit_base.blocks]
+        if not (self.factorized or self.matrix):
             return [("full", b) for b in self.dit_base.blocks]
         out = []
         for sb, tb in zip(self.dit_base.blocks, self.dit_base.temporal_blocks):
-            out += [("spatial", sb), ("temporal", tb)]
+            out += [("spatial", sb), ("matrix" if self.matrix else "temporal", tb)]
         return out
 
     # ------------------------------------------------------------------ weight packing
@@ -353,11 +463,16 @@ class DiT3D(nn.Module):
             if self.pos_emb_type == "sinusoidal_factorized":   # spatial table per frame now, temporal table before the
                 P["pos"] = f32(self.dit_base.spatial_pos_emb.pos_emb[0]).repeat(self.max_tokens, 1)   # first temporal block
                 P["tpos"] = f32(self.dit_base.temporal_pos_emb.pos_emb[0])
+            elif self.pos_emb_type == "sinusoidal_2d":         # dit_base.py:356-362: the spatial table, per frame
+                P["pos"] = f32(self.dit_base.pos_emb.pos_emb[0]).repeat(self.max_tokens, 1)
             else:
                 P["pos"] = f32(self.dit_base.pos_emb.pos_emb[0])
             qs = torch.ones((3 * D, 1), device=dev)
-            qs[:D] = LOG2E / math.sqrt(self.head_dim)
+            qs[:D] = LOG2E / math.sqrt(max(self.head_dim, 1))
         for kind, blk in self._ordered_blocks():
+            if kind == "matrix":
+                P["blocks"].append(self._pack_matrix_block(blk, bf, f32, dev))
+                continue
             qw, qb = blk.attn.qkv.weight.detach().float(), blk.attn.qkv.bias.detach().float()
             if not self.use_rope:
                 qw, qb = qw * qs, qb * qs[:, 0]
@@ -375,8 +490,31 @@ class DiT3D(nn.Module):
         P["fin_w"], P["fin_b"] = bf(wf), bfin
         if self.use_rope:
             P["rope"] = rope_cos_sin_table(self.head_dim, (self.max_tokens, self.num_patches_h, self.num_patches_w)).to(dev)
+        if self.matrix and self.matrix_rope:
+            P["mrope"] = rope_1d_cos_sin_table(self.matrix_head_dim, self.max_tokens).to(dev)
         self._packed, self._packed_key = P, key
         return P
+
+    def _pack_matrix_block(self, blk, bf, f32, dev):
+        """MatrixDiTBlock weights in kernel layout: the v factors as [N, K] bf16 GEMM weights (W = v^T), the u factors as
+        f32 tables of the two patch kernels.  Without the temporal RoPE the QKV epilogue is a plain bf16 store, so the
+        softmax scale (x log2 e) is folded into the q columns (as for the absolute-position DiT blocks)."""
+        a, E, Mc, Pn = blk.attn, self.hidden_size, self.matrix_cols, self.num_patches
+        qw = a.qkv_v.detach().float().t().contiguous()                 # [3E, D]
+        qb = a.qkv_bias.detach().float()[0].clone() if hasattr(a, "qkv_bias") else torch.zeros((3 * E,), device=dev)
+        if not self.matrix_rope:
+            scale = LOG2E / math.sqrt(self.matrix_head_dim)
+            qw[:E] *= scale
+            qb[:E] *= scale
+        eye = torch.eye(Pn, device=dev) if a.fixed_u == "identity" else None
+        d = dict(kind="matrix", qkv_w=bf(qw), qkv_b=f32(qb), proj_w=bf(a.proj_v.detach().float().t().contiguous()),
+                 qkv_u=f32(eye if eye is not None else a.qkv_u).reshape(Pn, Mc).contiguous(),
+                 proj_u=f32(eye if eye is not None else a.proj_u).reshape(Mc, Pn).contiguous(),
+                 proj_bias=f32(a.proj_bias) if hasattr(a, "proj_bias") else None)
+        if blk.use_mlp:
+            d.update(fc1_w=bf(blk.mlp.fc1.weight), fc1_b=f32(blk.mlp.fc1.bias), fc2_w=bf(blk.mlp.fc2.weight),
+                     fc2_b=f32(blk.mlp.fc2.bias))
+        return d
 
     def _workspace(self, R: int, T: int, dev, out_dtype):
         key = (R, T, str(dev), out_dtype)
@@ -403,6 +541,9 @@ class DiT3D(nn.Module):
             m = torch.arange(M, device=dev)
             ncol_t = (6 if self.dit_base.temporal_blocks[0].use_mlp else 3) * D
             ws.update(xt=e((M, D), f32), mod_tok=e((M, ncol_t), f32), frame_of_tok=(m // (Pn * T)) * T + m % T)
+        if self.matrix:      # frame-level rows (row, column head, frame) of the matrix attention
+            Mf = R * self.matrix_cols * T
+            ws.update(ms=e((Mf, D), bf), mqkv=e((Mf, 3 * D), bf), matt=e((Mf, D), bf), mz=e((Mf, D), f32))
         if not self.use_rope:
             ws["pos_rows"], ws["pos_key"] = e((M, D), f32), None     # the table repeated per row (filled lazily)
         if self.external_cond_embedding is not None:
@@ -530,7 +671,7 @@ class DiT3D(nn.Module):
         mod, ldm = ws["mod"], ws["mod"].shape[1]
 
         # --- blocks
-        q_scale = LOG2E / math.sqrt(self.head_dim)
+        q_scale = LOG2E / math.sqrt(max(self.head_dim, 1))
         col = 0
         xa, xb = ws["x"], ws["y"]
         first_temporal = True
@@ -547,17 +688,10 @@ class DiT3D(nn.Module):
                 first_temporal = False
                 torch.index_select(mod[:, col: col + ncol], 0, ws["frame_of_tok"], out=ws["mod_tok"])
                 bmod, bld, bcol, tpf, n_seq, seq_len = ws["mod_tok"], ws["mod_tok"].shape[1], 0, 1, R * Pn, T
-            ops.adaln_layernorm(xs, bmod, bcol, bcol + D, tpf, y_f32=xb, y_bf16=ws["y16"])
-            if self.use_rope:
-                ops.gemm_bf16(ws["y16"], bw["qkv_w"], ws["qkv"], ops.EPI_QKV_ROPE_BF16, bias=bw["qkv_b"],
-                              rope_cs=Pk["rope"], tokens_per_sample=Ntok, model_dim=D, head_dim=self.head_dim,
-                              q_scale=q_scale)
+            if kind == "matrix":
+                self._matrix_attention(bw, Pk, ws, xs, xb, mod, ldm, col, R, T)
             else:
-                ops.gemm_bf16(ws["y16"], bw["qkv_w"], ws["qkv"], ops.EPI_BF16, bias=bw["qkv_b"])
-            ops.attention(ws["qkv"], ws["att"], n_seq, seq_len, self.num_heads, self.head_dim)
-            # x1 = y + gate1 * proj(att)   (residual base is the modulated tensor — reference quirk Q1)
-            ops.gemm_bf16(ws["att"], bw["proj_w"], xs, ops.EPI_GATE_RESID_F32, bias=bw["proj_b"], resid=xb,
-                          gate=bmod[:, bcol + 2 * D:], ld_gate=bld, tokens_per_frame=tpf)
+                self._token_attention(bw, Pk, ws, xs, xb, bmod, bld, bcol, tpf, n_seq, seq_len, Ntok, q_scale)
             if "fc1_w" in bw:
                 bcol += 3 * D
                 hbuf = ws["h"][:, : bw["fc1_w"].shape[0]]
@@ -573,3 +707,34 @@ class DiT3D(nn.Module):
         ops.gemm_bf16(ws["y16"], Pk["fin_w"], ws["tok"], ops.EPI_F32, bias=Pk["fin_b"])
         ops.unpatchify(ws["tok"], ws["out"], RT, C, H, W, p)
         return ws["out"]
+
+    def _token_attention(self, bw, Pk, ws, xs, xb, bmod, bld, bcol, tpf, n_seq, seq_len, Ntok, q_scale):
+        """dit_blocks.py:488-507, first half of a DiTBlock: x <- y + gate * proj(attention(qkv(y))), y = modulate(LN(x))."""
+        D = self.hidden_size
+        ops.adaln_layernorm(xs, bmod, bcol, bcol + D, tpf, y_f32=xb, y_bf16=ws["y16"])
+        if self.use_rope:
+            ops.gemm_bf16(ws["y16"], bw["qkv_w"], ws["qkv"], ops.EPI_QKV_ROPE_BF16, bias=bw["qkv_b"],
+                          rope_cs=Pk["rope"], tokens_per_sample=Ntok, model_dim=D, head_dim=self.head_dim,
+                          q_scale=q_scale)
+        else:
+            ops.gemm_bf16(ws["y16"], bw["qkv_w"], ws["qkv"], ops.EPI_BF16, bias=bw["qkv_b"])
+        ops.attention(ws["qkv"], ws["att"], n_seq, seq_len, self.num_heads, self.head_dim)
+        # x1 = y + gate1 * proj(att)   (residual base is the modulated tensor — reference quirk Q1)
+        ops.gemm_bf16(ws["att"], bw["proj_w"], xs, ops.EPI_GATE_RESID_F32, bias=bw["proj_b"], resid=xb,
+                      gate=bmod[:, bcol + 2 * D:], ld_gate=bld, tokens_per_frame=tpf)
+
+    def _matrix_attention(self, bw, Pk, ws, xs, xb, mod, ldm, col, R: int, T: int):
+        """dit_blocks.py:626-644 + 289-350, first half of a MatrixDiTBlock: x <- y + gate * (proj_u^T A(u^T y v) proj_v +
+        proj_bias), attention A over the T frames of a row (see the module docstring)."""
+        D, Pn, Mc = self.hidden_size, self.num_patches, self.matrix_cols
+        ops.adaln_layernorm(xs, mod, col, col + D, Pn, y_f32=xb)
+        ops.patch_mix_bf16(xb, bw["qkv_u"], ws["ms"], R, T, Pn, Mc)
+        if self.matrix_rope:
+            ops.gemm_bf16(ws["ms"], bw["qkv_w"], ws["mqkv"], ops.EPI_QKV_ROPE_BF16, bias=bw["qkv_b"], rope_cs=Pk["mrope"],
+                          tokens_per_sample=T, model_dim=D, head_dim=self.matrix_head_dim,
+                          q_scale=LOG2E / math.sqrt(self.matrix_head_dim))
+        else:
+            ops.gemm_bf16(ws["ms"], bw["qkv_w"], ws["mqkv"], ops.EPI_BF16, bias=bw["qkv_b"])
+        ops.attention(ws["mqkv"], ws["matt"], R * Mc, T, self.matrix_heads, self.matrix_head_dim)
+        ops.gemm_bf16(ws["matt"], bw["proj_w"], ws["mz"], ops.EPI_F32)
+        ops.patch_expand_gate_resid(xs, xb, ws["mz"], bw["proj_u"], bw["proj_bias"], mod[:, col + 2 * D:], ldm, R, T, Pn, Mc)

@@ -221,6 +221,36 @@ def cast_bf16(src, out=None):
 
 
 # ------------------------------------------------------------------ U-ViT3DPose kernels
+def patch_mix_bf16(y, u, out, R, L, P, Mc):
+    """Matrix attention, `qkv_u` factor: y [R*L*P, D] f32, u [P, Mc] f32 -> out [R*Mc*L, D] bf16 (rows (r, c, l))."""
+    _need(y, torch.float32, "y")
+    _need(u, torch.float32, "u")
+    _need(out, torch.bfloat16, "out")
+    D = y.shape[-1]
+    if y.numel() != R * L * P * D or u.numel() != P * Mc or out.numel() != R * Mc * L * D:
+        raise RuntimeError(f"dfot_b200: patch_mix shape mismatch y{tuple(y.shape)} u{tuple(u.shape)} out{tuple(out.shape)}")
+    rc = _abi.lib().dfot_patch_mix_bf16(y.data_ptr(), u.data_ptr(), out.data_ptr(), R, L, P, Mc, D, _stream())
+    _abi.check(rc, "patch_mix_bf16")
+
+
+def patch_expand_gate_resid(x, y, z, pu, pb, gate, ld_gate, R, L, P, Mc):
+    """Matrix attention, `proj_u` factor + gate + residual: x = y + gate[frame] * (pu^T z + pb); y, x [R*L*P, D] f32,
+    z [R*Mc*L, D] f32, pu [Mc, P] f32, pb [P, D] f32 or None, gate a view into the per-frame modulation matrix."""
+    for t, name in ((x, "x"), (y, "y"), (z, "z"), (pu, "pu")):
+        _need(t, torch.float32, name)
+    if pb is not None:
+        _need(pb, torch.float32, "pb")
+    if gate.dtype != torch.float32 or not gate.is_cuda:
+        raise RuntimeError("dfot_b200: `gate` must be CUDA f32")
+    D = y.shape[-1]
+    if (y.numel() != R * L * P * D or x.numel() != y.numel() or z.numel() != R * Mc * L * D or pu.numel() != Mc * P
+            or (pb is not None and pb.numel() != P * D)):
+        raise RuntimeError("dfot_b200: patch_expand_gate_resid shape mismatch")
+    rc = _abi.lib().dfot_patch_expand_gate_resid(x.data_ptr(), y.data_ptr(), z.data_ptr(), pu.data_ptr(), _ptr(pb),
+                                                 gate.data_ptr(), ld_gate, R, L, P, Mc, D, _stream())
+    _abi.check(rc, "patch_expand_gate_resid")
+
+
 def conv3x3_bf16(x, w, out, epilogue, bias=None, resid=None, gn_sums=None, gn_groups=32, gn_eps=1e-6):
     """3x3 conv, stride 1, padding 1, implicit GEMM.  x [n,H,W,Cin] bf16 channel-last, w [Cout,3,3,Cin] bf16,
     out [n*H*W, Cout] f32|bf16 per epilogue (EPI_F32, EPI_BF16, EPI_SILU_BF16, EPI_RESID_F32)."""

@@ -219,6 +219,23 @@ DFOT_API int dfot_unpatchify(const float* tok, int64_t ld, void* x, int x_dtype,
 /* elementwise f32 → bf16 (weights repack / activations), n % 8 == 0 not required */
 DFOT_API int dfot_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
 
+/* Matrix-attention DiT variants (full_matrix_attention / factorized_matrix_attention; dit_blocks.py:211-350
+ * MatrixAttention, :549-652 MatrixDiTBlock): the attention tokens are FRAMES, a frame's [P patches, D] matrix is
+ * projected as u^T X v.  The u factors (over the patches) run as the two kernels below, the v factors as K2 GEMMs on
+ * R*Mc*L rows, the attention over the L frames as K3 (Mc = embed_col_dim column heads of one row each).
+ *   dfot_patch_mix_bf16:  out[((r*Mc + c)*L + l), d] = sum_n u[n*Mc + c] * y[((r*L + l)*P + n), d]     f32 -> bf16
+ *       (replaces the `qkv_u` contraction of matrix_mul, dit_blocks.py:211-212,301; y = the block's modulated tokens)
+ *   dfot_patch_expand_gate_resid:  x[((r*L + l)*P + n), d] = y[same] + gate[(r*L + l)*ld_gate + d] *
+ *           (sum_c pu[c*P + n] * z[((r*Mc + c)*L + l), d] + pb[n*D + d])                                 f32
+ *       (replaces the `proj_u` contraction + proj_bias, dit_blocks.py:345-347, and the gated residual :640-644;
+ *        z = attention output through proj_v; pb may be NULL; x may alias y).  D % 4 == 0.
+ */
+DFOT_API int dfot_patch_mix_bf16(const float* y, const float* u, void* out_bf16, int64_t R, int64_t L, int64_t P,
+                        int64_t Mc, int64_t D, void* stream);
+DFOT_API int dfot_patch_expand_gate_resid(float* x, const float* y, const float* z, const float* pu, const float* pb,
+                                 const float* gate, int64_t ld_gate, int64_t R, int64_t L, int64_t P, int64_t Mc,
+                                 int64_t D, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * U-ViT3DPose glue kernels (algorithms/dfot/backbones/u_vit/{u_vit3d_pose,u_vit3d,u_vit_blocks}.py).
  * Activations are channel-last everywhere: [n_img, H, W, C] == [tokens, C], so ResBlock levels and

@@ -1,13 +1,16 @@
-"""ORACLE (test infrastructure): DiT3D backbone forward — variant=full (rope_3d, learned_1d or sinusoidal_1d positions) and
-the factorized variants (factorized_encoder / factorized_attention: per layer a spatial block over the patches of a frame,
-then a temporal block over the frames of a patch position; sinusoidal_factorized, learned_1d or sinusoidal_1d positions) —
+"""ORACLE (test infrastructure): DiT3D backbone forward — variant=full (rope_3d, learned_1d or sinusoidal_1d positions), the
+factorized variants (factorized_encoder / factorized_attention: per layer a spatial block over the patches of a frame,
+then a temporal block over the frames of a patch position; sinusoidal_factorized, learned_1d or sinusoidal_1d positions)
+and the matrix-attention variants (full_matrix_attention / factorized_matrix_attention with matrix_block=matrix and
+sinusoidal_2d positions: frames are the attention tokens, a frame's [patches, channels] matrix is projected as u^T X v) —
 functional over a reference-keyed state dict.
 
 Restates
   algorithms/dfot/backbones/dit/dit3d.py:153-192           (patchify / unpatchify)
   algorithms/dfot/backbones/dit/dit_base.py:310-425        (block loop, final layer)
   algorithms/dfot/backbones/dit/dit_blocks.py:21-44,47-123 (attention), :408-437 (AdaLN-Zero),
-                                              :488-510 (block, residual-on-modulated quirk), :513-542
+                                              :488-510 (block, residual-on-modulated quirk), :513-542,
+                                              :211-350 (MatrixAttention), :549-652 (MatrixDiTBlock)
   algorithms/dfot/backbones/modules/embeddings.py:67-153   (noise-level embedding), :156-277 (RoPE-ND)
 Third-party pieces restated from their pinned versions (see oracle/ref_shim.py):
 timm PatchEmbed / Mlp, diffusers TimestepEmbedding.
@@ -55,6 +58,12 @@ def rope_angles(head_dim: int, sizes: Tuple[int, int, int], theta: float = 10000
     return torch.cat(parts, dim=-1).reshape(T * H * W, head_dim)
 
 
+def rope_angles_1d(dim: int, n: int, theta: float = 10000.0) -> torch.Tensor:
+    """embeddings.py:218-231 (RotaryEmbedding1D): angle table [n, dim]; each frequency repeated twice."""
+    inv = 1.0 / (theta ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim))
+    return (torch.arange(n, dtype=torch.float32)[:, None] * inv[None, :]).repeat_interleave(2, dim=-1)
+
+
 def apply_rope(x: torch.Tensor, angles: torch.Tensor) -> torch.Tensor:
     """embeddings.py:204-215 with interleaved rotate_half: (x0,x1) -> (-x1,x0)."""
     a = angles[: x.shape[-2]]
@@ -96,19 +105,32 @@ class DiT3DOracle:
                  external_cond_dim: int = 0):
         cfg = backbone_cfg
         self.pos_emb_type = cfg.get("pos_emb_type", "rope_3d")
-        self.factorized = cfg.get("variant", "full") in ("factorized_encoder", "factorized_attention")
-        assert cfg.get("variant", "full") == "full" or self.factorized
-        assert self.pos_emb_type in (("learned_1d", "sinusoidal_1d", "sinusoidal_factorized") if self.factorized
-                                     else ("rope_3d", "learned_1d", "sinusoidal_1d"))
+        self.variant = cfg.get("variant", "full")
+        self.matrix = self.variant in ("full_matrix_attention", "factorized_matrix_attention")
+        self.factorized = self.variant in ("factorized_encoder", "factorized_attention")
+        assert self.variant == "full" or self.factorized or self.matrix
+        if self.matrix:
+            assert self.pos_emb_type == "sinusoidal_2d" and cfg.get("matrix_block") == "matrix"
+        else:
+            assert self.pos_emb_type in (("learned_1d", "sinusoidal_1d", "sinusoidal_factorized") if self.factorized
+                                         else ("rope_3d", "learned_1d", "sinusoidal_1d"))
         self.sd = {k: v.detach().float() for k, v in state_dict.items()}
         self.p = cfg["patch_size"]
         self.C, self.H, self.W = x_shape
         self.gh, self.gw = self.H // self.p, self.W // self.p
         self.P = self.gh * self.gw
-        self.D = cfg["hidden_size"]
+        self.D = cfg["embed_row_dim"] if self.matrix else cfg["hidden_size"]      # dit3d.py:113-118
         self.depth = cfg["depth"]
-        self.heads = cfg["num_heads"]
+        self.heads = cfg.get("num_heads") or 1
         self.dh = self.D // self.heads
+        if self.matrix:                                                            # dit_base.py:129-149, 296-308
+            self.col_heads, self.row_heads = cfg["num_col_heads"], cfg["num_row_heads"]
+            self.hc, self.hr = cfg["embed_col_dim"] // self.col_heads, cfg["embed_row_dim"] // self.row_heads
+            self.flatten_rope, self.multi_token = bool(cfg.get("flatten_matrix_rope")), bool(cfg.get("matrix_multi_token"))
+            self.fixed_u = cfg.get("fixed_u")
+            self.matrix_angles = None
+            if cfg.get("use_temporal_rope"):
+                self.matrix_angles = rope_angles_1d(self.hc * self.hr if self.flatten_rope else self.hr, max_tokens)
         self.use_fourier = bool(cfg.get("use_fourier_noise_embedding", False))
         self.external_cond_dim = external_cond_dim
         self.cond_dropout = cfg.get("external_cond_dropout", 0.0)
@@ -125,6 +147,8 @@ class DiT3DOracle:
         if self.pos_emb_type == "sinusoidal_factorized":   # dit_base.py:265-274: 2-D spatial table + 1-D temporal table
             self.spatial_pos = sincos_nd_table(self.D, (self.gh, self.gw)).unsqueeze(0)
             self.temporal_pos = sincos_nd_table(self.D, (max_tokens,)).unsqueeze(0)
+        if self.pos_emb_type == "sinusoidal_2d":           # dit_base.py:254-258: the spatial table, added per frame (:356-362)
+            self.spatial_pos = sincos_nd_table(self.D, (self.gh, self.gw)).unsqueeze(0)
         # dit_base.py:185,192: MLP exists only if spatial_mlp_ratio is set (fork quirk Q2)
         self.use_mlp = "dit_base.blocks.0.mlp.fc1.weight" in self.sd
         self.taps = None  # optional dict filled with intermediates for kernel-level parity tests
@@ -163,11 +187,47 @@ class DiT3DOracle:
             self.taps.update(q0=q, k0=k, v0=v, attn0=o)
         return _linear(o, self.sd, f"dit_base.{group}.{i}.attn.proj")
 
-    def block(self, h, c_act, i: int, group: str):
-        """dit_blocks.py:488-510 (the MLP exists iff the block was built with a positive ratio)."""
+    def matrix_attention(self, y: torch.Tensor, pre: str) -> torch.Tensor:
+        """dit_blocks.py:289-350.  y [B, L, N, D]: L frames (the attention tokens) of N patch rows; heads = col x row heads,
+        a head's feature is its [hc, hr] sub-matrix."""
+        sd = self.sd
+        B, L, N, D = y.shape
+        eye = torch.eye(N) if self.fixed_u == "identity" else None          # :267-269 (plain tensors, not parameters)
+        qkv = torch.einsum("nm,blnd,dk->blmk", eye if eye is not None else sd[pre + ".qkv_u"], y, sd[pre + ".qkv_v"])
+        if pre + ".qkv_bias" in sd:
+            qkv = qkv + sd[pre + ".qkv_bias"]
+        C, R, hc, hr = self.col_heads, self.row_heads, self.hc, self.hr
+        q, k, v = qkv.reshape(B, L, C, hc, 3, R, hr).permute(4, 0, 2, 5, 1, 3, 6).unbind(0)   # b c r l n d
+        if self.matrix_angles is not None:
+            if self.flatten_rope:                                           # rotate the flattened (n d) feature over l
+                q = apply_rope(q.reshape(B, C, R, L, hc * hr), self.matrix_angles).reshape(q.shape)
+                k = apply_rope(k.reshape(B, C, R, L, hc * hr), self.matrix_angles).reshape(k.shape)
+            else:                                                           # every row n rotated over l with the same table
+                q = apply_rope(q.transpose(3, 4), self.matrix_angles).transpose(3, 4)
+                k = apply_rope(k.transpose(3, 4), self.matrix_angles).transpose(3, 4)
+        if self.multi_token:                                                # :324-332: one softmax per row n
+            w = torch.softmax(torch.einsum("bcrlnd,bcrknd->bcrnlk", q * hr ** -0.5, k), dim=-1)
+            o = torch.einsum("bcrnlk,bcrknd->bcrlnd", w, v)
+        else:                                                               # :333-338: the whole sub-matrix is the feature
+            w = torch.softmax(torch.einsum("bcrlnd,bcrknd->bcrlk", q * (hc * hr) ** -0.5, k), dim=-1)
+            o = torch.einsum("bcrlk,bcrknd->bcrlnd", w, v)
+        o = o.permute(0, 3, 1, 4, 2, 5).reshape(B, L, C * hc, R * hr)       # b l (c n) (r d)
+        o = torch.einsum("nm,blnd,dk->blmk", eye if eye is not None else sd[pre + ".proj_u"], o, sd[pre + ".proj_v"])
+        if pre + ".proj_bias" in sd:
+            o = o + sd[pre + ".proj_bias"]
+        return o
+
+    def block(self, h, c_act, i: int, group: str, n_frames: int = 0):
+        """dit_blocks.py:488-510 (the MLP exists iff the block was built with a positive ratio); :626-652 for a
+        MatrixDiTBlock (same block around MatrixAttention over the n_frames frames of the row)."""
         sd, pre = self.sd, f"dit_base.{group}.{i}"
         y, gate = _adaln(h, c_act, sd, pre + ".norm1", 3)
-        h = y + gate * self.attention(y, i, group)               # residual base is the modulated tensor (Q1)
+        if pre + ".attn.qkv_v" in sd:
+            B, N, D = y.shape
+            att = self.matrix_attention(y.reshape(B, n_frames, N // n_frames, D), pre + ".attn").reshape(B, N, D)
+        else:
+            att = self.attention(y, i, group)
+        h = y + gate * att                                       # residual base is the modulated tensor (Q1)
         if pre + ".mlp.fc1.weight" in sd:
             z, gate2 = _adaln(h, c_act, sd, pre + ".norm2", 3)
             m = _linear(F.gelu(_linear(z, sd, pre + ".mlp.fc1"), approximate="tanh"), sd, pre + ".mlp.fc2")
@@ -190,13 +250,27 @@ class DiT3DOracle:
             h = ht.reshape(B, P, T, D).transpose(1, 2)
         return h.reshape(B, T * P, D)
 
+    def matrix_blocks(self, tok, c_act, B: int, T: int):
+        """dit_base.py:355-416 for the matrix variants: sinusoidal_2d table per frame; full_matrix_attention runs one
+        MatrixDiTBlock per layer on the (t p) tokens, factorized_matrix_attention a spatial DiTBlock on ((b t), p) and
+        then a MatrixDiTBlock (`temporal_blocks`) on (b, (t p))."""
+        P, D = self.P, self.D
+        h = (tok.reshape(B, T, P, D) + self.spatial_pos[:, :P].reshape(1, 1, P, D)).reshape(B, T * P, D)
+        for i in range(self.depth):
+            if self.variant == "full_matrix_attention":
+                h = self.block(h, c_act, i, "blocks", T)
+            else:
+                h = self.block(h.reshape(B * T, P, D), c_act.reshape(B * T, P, D), i, "blocks").reshape(B, T * P, D)
+                h = self.block(h, c_act, i, "temporal_blocks", T)
+        return h
+
     def __call__(self, x, noise_levels, external_cond=None, external_cond_mask=None):
         B, T = x.shape[:2]
         sd = self.sd
         tok = F.conv2d(x.reshape(B * T, self.C, self.H, self.W).float(), sd["patch_embedder.proj.weight"],
                        sd["patch_embedder.proj.bias"], stride=self.p)
         tok = tok.flatten(2).transpose(1, 2).reshape(B, T * self.P, self.D)
-        if self.angles is None and self.pos_emb_type != "sinusoidal_factorized":
+        if self.angles is None and self.pos_emb_type not in ("sinusoidal_factorized", "sinusoidal_2d"):
             tok = tok + self.pos_emb[:, : tok.shape[1]]             # dit_base.py:352-353, 523-525
         emb = self.noise_embedding(noise_levels)
         if external_cond is not None:
@@ -206,7 +280,7 @@ class DiT3DOracle:
                 emb = emb + self.cond_embedding(external_cond.float(), external_cond_mask)
         c_act = F.silu(emb.repeat_interleave(self.P, dim=1))      # per-token copy of a per-frame vector
         h = tok
-        for i in range(0 if self.factorized else self.depth):
+        for i in range(0 if self.factorized or self.matrix else self.depth):
             pre = f"dit_base.blocks.{i}"
             y, gate = _adaln(h, c_act, sd, pre + ".norm1", 3)
             h = y + gate * self.attention(y, i)                    # residual base is the modulated tensor (Q1)
@@ -218,6 +292,8 @@ class DiT3DOracle:
                 self.taps.update(block0=h)
         if self.factorized:
             h = self.factorized_blocks(tok, c_act, B, T)
+        if self.matrix:
+            h = self.matrix_blocks(tok, c_act, B, T)
         h = _adaln(h, c_act, sd, "dit_base.final_layer.norm_final", 2)
         h = _linear(h, sd, "dit_base.final_layer.linear")           # [B, T*P, p*p*C]
         h = h.reshape(B, T, self.gh, self.gw, self.p, self.p, self.C)

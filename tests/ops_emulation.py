@@ -90,6 +90,21 @@ def adaln_layernorm(x, mod, shift_col, scale_col, tokens_per_frame, y_f32=None, 
         y_bf16.copy_(y.to(BF))
 
 
+def patch_mix_bf16(y, u, out, R, L, P, Mc):
+    D = y.shape[-1]
+    s = torch.einsum("nc,rlnd->rcld", u.reshape(P, Mc).float(), y.reshape(R, L, P, D).float())
+    out.copy_(s.reshape(out.shape).to(BF))
+
+
+def patch_expand_gate_resid(x, y, z, pu, pb, gate, ld_gate, R, L, P, Mc):
+    D = y.shape[-1]
+    s = torch.einsum("cn,rcld->rlnd", pu.reshape(Mc, P).float(), z.reshape(R, Mc, L, D).float())
+    if pb is not None:
+        s = s + pb.reshape(1, 1, P, D)
+    g = gate[:, :D].reshape(R, L, 1, D)
+    x.copy_((y.reshape(R, L, P, D) + g * s).reshape(x.shape))
+
+
 def silu_sum_bf16(a, b, row_mask, rows_per_mask, out):
     s = a.float()
     if b is not None:
@@ -320,7 +335,7 @@ ALL = ["relu_bf16", "pixel_shuffle2x", "linear_attention_relu", "dwconv3x3_glu_b
        "rmsnorm_film_bf16", "qk_norm_rope", "attention", "avgpool2x2", "sub_bf16", "upsample2x_add", "pose_ray_patches",
        "noise_features", "conv3d_causal_bf16", "groupnorm_stats_strided", "groupnorm_apply_bf16",
        "vae_upsample2x_bf16", "upsample2x_nearest_bf16", "vae_fill_pad_frames", "softmax_rows_bf16", "adaln_layernorm",
-       "silu_sum_bf16"]
+       "silu_sum_bf16", "patch_mix_bf16", "patch_expand_gate_resid"]
 
 
 def install(monkeypatch):

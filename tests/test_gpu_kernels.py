@@ -265,3 +265,37 @@ def test_noise_features_patchify_unpatchify_silu():
     ops.silu_sum_bf16(a.to(DEV), b.to(DEV), mask.to(DEV), 8, o)
     keep = (1 - mask.float()).repeat_interleave(8)[:, None]
     assert (o.float().cpu() - torch.nn.functional.silu(a + keep * b)).abs().max().item() < 2e-2
+
+
+# ---------------------------------------------------------------- matrix-attention patch kernels (the u factors)
+@pytest.mark.parametrize("R,L,P,Mc,D", [(2, 4, 16, 1, 64), (1, 5, 64, 2, 512), (3, 8, 256, 1, 768), (1, 3, 9, 5, 132),
+                                        (2, 16, 16, 16, 64)])
+def test_patch_mix_and_expand(R, L, P, Mc, D):
+    g = torch.Generator().manual_seed(R * 131 + P)
+    y = torch.randn((R * L * P, D), generator=g)
+    u = torch.randn((P, Mc), generator=g) / math.sqrt(P)
+    out = torch.empty((R * Mc * L, D), device=DEV, dtype=torch.bfloat16)
+    ops.patch_mix_bf16(y.to(DEV), u.to(DEV), out, R, L, P, Mc)
+    ref = torch.einsum("nc,rlnd->rcld", u.double(), y.reshape(R, L, P, D).double()).reshape(R * Mc * L, D).float()
+    assert (out.float().cpu() - ref).abs().max().item() <= 2 ** -8 * ref.abs().max().item() + 1e-6   # bf16 rounding
+    out2 = torch.empty_like(out)
+    ops.patch_mix_bf16(y.to(DEV), u.to(DEV), out2, R, L, P, Mc)
+    assert torch.equal(out, out2)                                                                  # fixed-order reduction
+    # the way back: x = y + gate[frame] * (pu^T z + pb)
+    z = torch.randn((R * Mc * L, D), generator=g)
+    pu = torch.randn((Mc, P), generator=g)
+    pb = torch.randn((P, D), generator=g)
+    mod = torch.randn((R * L, 3 * D + 8), generator=g)                 # the gate is a column slab of a wider matrix
+    for bias in (pb, None):
+        x = torch.empty((R * L * P, D), device=DEV)
+        ops.patch_expand_gate_resid(x, y.to(DEV), z.to(DEV), pu.to(DEV), None if bias is None else bias.to(DEV),
+                                    mod.to(DEV)[:, 2 * D:], mod.shape[1], R, L, P, Mc)
+        s = torch.einsum("cn,rcld->rlnd", pu.double(), z.reshape(R, Mc, L, D).double())
+        if bias is not None:
+            s = s + bias.double()
+        ref = y.reshape(R, L, P, D).double() + mod[:, 2 * D:3 * D].reshape(R, L, 1, D).double() * s
+        assert (x.cpu().double() - ref.reshape(-1, D)).abs().max().item() < 1e-4
+    # in place (x aliases y)
+    yd = y.to(DEV)
+    ops.patch_expand_gate_resid(yd, yd, z.to(DEV), pu.to(DEV), None, mod.to(DEV)[:, 2 * D:], mod.shape[1], R, L, P, Mc)
+    assert (yd.cpu().double() - ref.reshape(-1, D)).abs().max().item() < 1e-4
