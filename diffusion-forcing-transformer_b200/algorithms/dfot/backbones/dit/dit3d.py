@@ -359,10 +359,8 @@ class DiT3D(nn.Module):
         if cfg.get("matrix_block") != "matrix":
             raise NotImplementedError(f"matrix_block={cfg.get('matrix_block')!r}: only MatrixDiTBlock ('matrix', the shipped "
                                       "configurations) is built, not the matrix_self / matrix_cross ablations")
-        for k in ("embed_col_dim", "embed_row_dim", "num_col_heads", "num_row_heads", "use_bias"):
+        for k in ("embed_col_dim", "embed_row_dim", "num_col_heads", "num_row_heads", "spatial_mlp_ratio", "use_bias"):
             assert cfg.get(k) is not None, f"{k} must be specified for matrix attention"
-        if self.variant == "factorized_matrix_attention":
-            assert cfg.get("spatial_mlp_ratio") is not None, "spatial_mlp_ratio must be specified for matrix attention"
         assert cfg.embed_row_dim % cfg.num_row_heads == 0, "embed_row_dim must be divisible by num_row_heads"
         assert cfg.embed_col_dim % cfg.num_col_heads == 0, "embed_col_dim must be divisible by num_col_heads"
         if cfg.embed_col_dim != cfg.num_col_heads:

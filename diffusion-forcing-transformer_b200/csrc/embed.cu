@@ -103,84 +103,115 @@ __global__ void cast_bf16_vec8_kernel(const float* __restrict__ in, __nv_bfloat1
 // Frames are the attention tokens of the matrix variants: the P patch rows of a frame are contracted with the columns of
 // `qkv_u` BEFORE the row projection (einsum 'nm,blnd,dk->blmk' with the u factor first: P times fewer GEMM rows).
 //   out[((r*Mc + c)*L + l), d] = sum_n u[n*Mc + c] * y[((r*L + l)*P + n), d]        (bf16, the A operand of the QKV GEMM)
-// One block per (frame, 128-column slab): 8 warps stride over the patches, float4 per lane, fixed-order reduction in shared
-// memory (deterministic).  Column heads c are handled four at a time (y re-read from L1/L2 when Mc > 4).
+// A work item = (frame, 128-column slab): 8 warps stride over the patches (four rows = 2 KB per warp in flight), float4 per
+// lane, fixed-order reduction in shared memory (deterministic).  Column heads c are handled four at a time (y re-read from
+// L2 when Mc > 4).
 __global__ void __launch_bounds__(256)
 patch_mix_bf16_kernel(const float* __restrict__ y, const float* __restrict__ u, __nv_bfloat16* __restrict__ out,
-                      int L, int P, int Mc, int D) {
+                      int n_frames, int L, int P, int Mc, int D) {
   pdl_trigger();   // programmatic dependent launch: see common.cuh
   pdl_wait();
   __shared__ float4 part[8][4][32];
-  const int frame = blockIdx.x, r = frame / L, l = frame % L;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int d = blockIdx.y * 128 + lane * 4;
-  const bool live = d < D;
-  const float* yf = y + (int64_t)frame * P * D + d;
-  for (int c0 = 0; c0 < Mc; c0 += 4) {
-    float4 acc[4];
+  const int n_slabs = (D + 127) >> 7;
+  // persistent over (frame, slab) items, slab fastest: the blocks running at any moment read whole rows between them
+  for (int item = blockIdx.x; item < n_frames * n_slabs; item += gridDim.x) {
+    const int frame = item / n_slabs, r = frame / L, l = frame % L;
+    const int d = (item % n_slabs) * 128 + lane * 4;
+    const bool live = d < D;
+    const float* yf = y + (int64_t)frame * P * D + d;
+    for (int c0 = 0; c0 < Mc; c0 += 4) {
+      float4 acc[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) {
-      for (int n = warp; n < P; n += 8) {
-        const float4 v = *reinterpret_cast<const float4*>(yf + (int64_t)n * D);
+      for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        for (int n0 = warp; n0 < P; n0 += 32) {           // rows n0, n0 + 8, n0 + 16, n0 + 24 of this warp
+          uint4 v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float w = (c0 + j < Mc) ? u[n * Mc + c0 + j] : 0.f;
-          acc[j].x = fmaf(w, v.x, acc[j].x);
-          acc[j].y = fmaf(w, v.y, acc[j].y);
-          acc[j].z = fmaf(w, v.z, acc[j].z);
-          acc[j].w = fmaf(w, v.w, acc[j].w);
+          for (int k = 0; k < 4; ++k)
+            v[k] = n0 + 8 * k < P ? ld_stream_u4(yf + (int64_t)(n0 + 8 * k) * D) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int n = n0 + 8 * k;
+            if (n >= P) break;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float w = (c0 + j < Mc) ? __ldg(u + n * Mc + c0 + j) : 0.f;
+              acc[j].x = fmaf(w, __uint_as_float(v[k].x), acc[j].x);
+              acc[j].y = fmaf(w, __uint_as_float(v[k].y), acc[j].y);
+              acc[j].z = fmaf(w, __uint_as_float(v[k].z), acc[j].z);
+              acc[j].w = fmaf(w, __uint_as_float(v[k].w), acc[j].w);
+            }
+          }
         }
       }
-    }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) part[warp][j][lane] = acc[j];
-    __syncthreads();
-    if (warp < 4 && c0 + warp < Mc && live) {          // warp j finishes column head c0 + j
-      float4 s = part[0][warp][lane];
+      for (int j = 0; j < 4; ++j) part[warp][j][lane] = acc[j];
+      __syncthreads();
+      if (warp < 4 && c0 + warp < Mc && live) {          // warp j finishes column head c0 + j
+        float4 s = part[0][warp][lane];
 #pragma unroll
-      for (int w = 1; w < 8; ++w) {
-        const float4 t = part[w][warp][lane];
-        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        for (int w = 1; w < 8; ++w) {
+          const float4 t = part[w][warp][lane];
+          s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+        const int64_t row = ((int64_t)r * Mc + c0 + warp) * L + l;
+        *reinterpret_cast<uint2*>(out + row * D + d) = make_uint2(pack_bf16x2(s.x, s.y), pack_bf16x2(s.z, s.w));
       }
-      const int64_t row = ((int64_t)r * Mc + c0 + warp) * L + l;
-      *reinterpret_cast<uint2*>(out + row * D + d) = make_uint2(pack_bf16x2(s.x, s.y), pack_bf16x2(s.z, s.w));
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
 // The way back (the `proj_u` factor of the output projection, the AdaLN-Zero gate and the block's residual in one pass):
 //   x[((r*L + l)*P + n), d] = y[same] + gate[(r*L + l)*ld_gate + d] * (sum_c pu[c*P + n] * z[((r*Mc + c)*L + l), d] + pb[n*D + d])
+// One block per (frame, 32-patch chunk); a thread owns one float4 column group (two when D > 1024): the frame's gate and —
+// with one column head, every shipped configuration — its z row stay in registers, the patch rows stream through four at a
+// time.  No index arithmetic per element.
+template <bool ONE_COL>
 __global__ void __launch_bounds__(256)
 patch_expand_gate_resid_kernel(float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z,
                                const float* __restrict__ pu, const float* __restrict__ pb,
-                               const float* __restrict__ gate, int64_t ld_gate, int64_t total4, int L, int P, int Mc, int D) {
+                               const float* __restrict__ gate, int64_t ld_gate, int L, int P, int Mc, int D) {
   pdl_trigger();   // programmatic dependent launch: see common.cuh
   pdl_wait();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total4) return;
-  const int d4 = D >> 2;
-  const int d = (int)(i % d4) * 4;
-  const int64_t m = i / d4;
-  const int n = (int)(m % P);
-  const int64_t frame = m / P;
-  const int64_t r = frame / L;
-  const int l = (int)(frame % L);
-  float4 s = pb != nullptr ? *reinterpret_cast<const float4*>(pb + (int64_t)n * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int c = 0; c < Mc; ++c) {
-    const float w = pu[c * P + n];
-    const float4 t = *reinterpret_cast<const float4*>(z + ((r * Mc + c) * L + l) * D + d);
-    s.x = fmaf(w, t.x, s.x); s.y = fmaf(w, t.y, s.y); s.z = fmaf(w, t.z, s.z); s.w = fmaf(w, t.w, s.w);
+  const int frame = blockIdx.x, r = frame / L, l = frame % L;
+  const int n_begin = blockIdx.y * 32, n_end = min(P, n_begin + 32);
+  for (int d = threadIdx.x * 4; d < D; d += 1024) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gate + (int64_t)frame * ld_gate + d));
+    const float* zf = z + ((int64_t)r * Mc * L + l) * D + d;          // column head c: + c * L * D
+    float4 z0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ONE_COL) z0 = __ldg(reinterpret_cast<const float4*>(zf));
+    const int64_t row0 = (int64_t)frame * P;
+    for (int n0 = n_begin; n0 < n_end; n0 += 4) {
+      uint4 yv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        yv[k] = n0 + k < n_end ? ld_stream_u4(y + (row0 + n0 + k) * D + d) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int n = n0 + k;
+        if (n >= n_end) break;
+        float4 s = pb != nullptr ? __ldg(reinterpret_cast<const float4*>(pb + (int64_t)n * D + d))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ONE_COL) {
+          const float w = __ldg(pu + n);
+          s.x = fmaf(w, z0.x, s.x); s.y = fmaf(w, z0.y, s.y); s.z = fmaf(w, z0.z, s.z); s.w = fmaf(w, z0.w, s.w);
+        } else {
+          for (int c = 0; c < Mc; ++c) {
+            const float w = __ldg(pu + c * P + n);
+            const float4 t = __ldg(reinterpret_cast<const float4*>(zf + (int64_t)c * L * D));
+            s.x = fmaf(w, t.x, s.x); s.y = fmaf(w, t.y, s.y); s.z = fmaf(w, t.z, s.z); s.w = fmaf(w, t.w, s.w);
+          }
+        }
+        st_stream_u4(x + (row0 + n) * D + d,
+                     make_uint4(__float_as_uint(fmaf(g.x, s.x, __uint_as_float(yv[k].x))),
+                                __float_as_uint(fmaf(g.y, s.y, __uint_as_float(yv[k].y))),
+                                __float_as_uint(fmaf(g.z, s.z, __uint_as_float(yv[k].z))),
+                                __float_as_uint(fmaf(g.w, s.w, __uint_as_float(yv[k].w)))));
+      }
+    }
   }
-  const float4 g = *reinterpret_cast<const float4*>(gate + frame * ld_gate + d);
-  const uint4 yu = ld_stream_u4(y + m * D + d);
-  float4 o;
-  o.x = fmaf(g.x, s.x, __uint_as_float(yu.x));
-  o.y = fmaf(g.y, s.y, __uint_as_float(yu.y));
-  o.z = fmaf(g.z, s.z, __uint_as_float(yu.z));
-  o.w = fmaf(g.w, s.w, __uint_as_float(yu.w));
-  st_stream_u4(x + m * D + d, make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
 }
 
 static inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)ceil_div(n, threads); }
@@ -264,9 +295,10 @@ extern "C" int dfot_patch_mix_bf16(const float* y, const float* u, void* out_bf1
                "patch_mix_bf16: bad arguments");
   DFOT_REQUIRE(D % 4 == 0 && (uintptr_t)y % 16 == 0 && (uintptr_t)out_bf16 % 8 == 0, DFOT_ERR_INVALID_ARG,
                "patch_mix_bf16: D must be a multiple of 4 and the buffers 16-byte aligned");
-  DFOT_REQUIRE(R * L < (1ll << 31) && D < (1ll << 22), DFOT_ERR_INVALID_ARG, "patch_mix_bf16: too many frames");
-  launch_pdl(patch_mix_bf16_kernel, dim3((unsigned)(R * L), (unsigned)ceil_div(D, 128)), dim3(256), 0, (cudaStream_t)stream,
-             y, u, (__nv_bfloat16*)out_bf16, (int)L, (int)P, (int)Mc, (int)D);
+  DFOT_REQUIRE(R * L * ceil_div(D, 128) < (1ll << 31), DFOT_ERR_INVALID_ARG, "patch_mix_bf16: too many frames");
+  const int64_t items = R * L * ceil_div(D, 128);
+  launch_pdl(patch_mix_bf16_kernel, dim3((unsigned)(items < 148 * 8 ? items : 148 * 8)), dim3(256), 0, (cudaStream_t)stream,
+             y, u, (__nv_bfloat16*)out_bf16, (int)(R * L), (int)L, (int)P, (int)Mc, (int)D);
   DFOT_CHECK_LAUNCH("patch_mix_bf16");
   return DFOT_OK;
 }
@@ -274,15 +306,20 @@ extern "C" int dfot_patch_mix_bf16(const float* y, const float* u, void* out_bf1
 extern "C" int dfot_patch_expand_gate_resid(float* x, const float* y, const float* z, const float* pu, const float* pb,
                                             const float* gate, int64_t ld_gate, int64_t R, int64_t L, int64_t P,
                                             int64_t Mc, int64_t D, void* stream) {
-  DFOT_REQUIRE(x && y && z && pu && gate && R > 0 && L > 0 && P > 0 && Mc > 0 && D > 0, DFOT_ERR_INVALID_ARG,
-               "patch_expand_gate_resid: bad arguments");
+  DFOT_REQUIRE(x && y && z && pu && gate && x != y && R > 0 && L > 0 && P > 0 && Mc > 0 && D > 0, DFOT_ERR_INVALID_ARG,
+               "patch_expand_gate_resid: bad arguments (x must not alias y)");
   DFOT_REQUIRE(D % 4 == 0 && ld_gate % 4 == 0 && ld_gate >= D, DFOT_ERR_INVALID_ARG,
                "patch_expand_gate_resid: D and ld_gate must be multiples of 4, ld_gate >= D");
   DFOT_REQUIRE(((uintptr_t)x | (uintptr_t)y | (uintptr_t)z | (uintptr_t)gate | (uintptr_t)pb) % 16 == 0, DFOT_ERR_INVALID_ARG,
                "patch_expand_gate_resid: buffers must be 16-byte aligned");
-  const int64_t total4 = R * L * P * (D / 4);
-  launch_pdl(patch_expand_gate_resid_kernel, dim3(blocks_for(total4, 256)), dim3(256), 0, (cudaStream_t)stream,
-             x, y, z, pu, pb, gate, ld_gate, total4, (int)L, (int)P, (int)Mc, (int)D);
+  DFOT_REQUIRE(R * L < (1ll << 31) && P < (1ll << 20), DFOT_ERR_INVALID_ARG, "patch_expand_gate_resid: too many frames");
+  const dim3 grid((unsigned)(R * L), (unsigned)ceil_div(P, 32));
+  if (Mc == 1)
+    launch_pdl(patch_expand_gate_resid_kernel<true>, grid, dim3(256), 0, (cudaStream_t)stream, x, y, z, pu, pb, gate,
+               ld_gate, (int)L, (int)P, (int)Mc, (int)D);
+  else
+    launch_pdl(patch_expand_gate_resid_kernel<false>, grid, dim3(256), 0, (cudaStream_t)stream, x, y, z, pu, pb, gate,
+               ld_gate, (int)L, (int)P, (int)Mc, (int)D);
   DFOT_CHECK_LAUNCH("patch_expand_gate_resid");
   return DFOT_OK;
 }

@@ -81,6 +81,20 @@ def bench_norm(iters):
         print(f"adaln_layernorm M={M} D={D} (bf16 out):     {us:7.1f} us  {M * D * 6 / us / 1e3:7.1f} GB/s")
 
 
+def bench_matrix(iters):
+    """The u-factor kernels of the matrix-attention DiT variants (HBM-bound: one pass over the token stream each)."""
+    for R, L, P, Mc, D in [(64, 16, 256, 1, 768), (16, 36, 16, 1, 512)]:
+        y = torch.randn((R * L * P, D), device=DEV)
+        u, pu = torch.randn((P, Mc), device=DEV), torch.randn((Mc, P), device=DEV)
+        out = torch.empty((R * Mc * L, D), device=DEV, dtype=torch.bfloat16)
+        z, mod = torch.randn((R * Mc * L, D), device=DEV), torch.randn((R * L, 6 * D), device=DEV)
+        x = torch.empty_like(y)
+        us = timeit(lambda: ops.patch_mix_bf16(y, u, out, R, L, P, Mc), iters)
+        print(f"patch_mix R*L={R * L} P={P} D={D}:          {us:7.1f} us  {y.numel() * 4 / us / 1e3:7.1f} GB/s")
+        us = timeit(lambda: ops.patch_expand_gate_resid(x, y, z, pu, None, mod[:, 2 * D:], 6 * D, R, L, P, Mc), iters)
+        print(f"patch_expand_gate_resid (same shape):      {us:7.1f} us  {y.numel() * 8 / us / 1e3:7.1f} GB/s")
+
+
 def bench_gemm_ditb(iters):
     """DiT-B (DMLab) block GEMMs: D = 768, 12 heads of 64, 16 tokens per frame, M = rows x frames x 16 tokens."""
     D, P = 768, 16
@@ -228,6 +242,8 @@ if __name__ == "__main__":
         bench_gemm(a.iters)
     if a.which in ("norm", "all"):
         bench_norm(a.iters)
+    if a.which in ("matrix", "all"):
+        bench_matrix(a.iters)
     if a.which in ("gemm_ditb",):
         bench_gemm_ditb(a.iters)
     if a.which in ("sampler", "all"):

@@ -109,6 +109,17 @@ elif which == "adaln":     # K600 adaLN-LayerNorm launch: 8 x 1280 tokens, D = 1
     mod = torch.randn((M // tpf, 6 * D), device=DEV)
     y = torch.empty((M, D), device=DEV, dtype=torch.bfloat16)
     fn = lambda: ops.adaln_layernorm(x, mod, 0, D, tpf, y_bf16=y)
+elif which in ("patch_mix", "patch_expand"):   # matrix-attention u factors: 64 rows x 16 frames x 256 patches, D = 768
+    R, L, P, Mc, D = 64, 16, 256, 1, 768
+    yv = torch.randn((R * L * P, D), device=DEV)
+    if which == "patch_mix":
+        u = torch.randn((P, Mc), device=DEV)
+        o = torch.empty((R * Mc * L, D), device=DEV, dtype=torch.bfloat16)
+        fn = lambda: ops.patch_mix_bf16(yv, u, o, R, L, P, Mc)
+    else:
+        pu, z = torch.randn((Mc, P), device=DEV), torch.randn((R * Mc * L, D), device=DEV)
+        mod, xo = torch.randn((R * L, 6 * D), device=DEV), torch.empty_like(yv)
+        fn = lambda: ops.patch_expand_gate_resid(xo, yv, z, pu, None, mod[:, 2 * D:], 6 * D, R, L, P, Mc)
 else:
     raise SystemExit(f"unknown kernel {which}")
 for _ in range(2):

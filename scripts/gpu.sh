@@ -36,6 +36,8 @@ prof_cmd() { # name -> kernel regex + command
     rmsnorm1152)    RX=rmsnorm_film; CMD="python scripts/bench_one.py rmsnorm1152 3" ;;
     qknorm)         RX=qk_norm_rope; CMD="python scripts/bench_one.py qknorm 3" ;;
     adaln)          RX=adaln; CMD="python scripts/bench_one.py adaln 3" ;;
+    patch_mix)      RX=patch_mix; CMD="python scripts/bench_one.py patch_mix 3" ;;
+    patch_expand)   RX=patch_expand; CMD="python scripts/bench_one.py patch_expand 3" ;;
     *) echo "unknown profile target $1"; return 1 ;;
   esac
 }
