@@ -32,6 +32,7 @@ i.e. the u factor is contracted first (the reference's einsum 'nm,blnd,dk->blmk'
 Mc rows per frame instead of P.
 """
 import math
+import os
 from typing import Optional
 
 import numpy as np
@@ -539,6 +540,8 @@ class DiT3D(nn.Module):
             m = torch.arange(M, device=dev)
             ncol_t = (6 if self.dit_base.temporal_blocks[0].use_mlp else 3) * D
             ws.update(xt=e((M, D), f32), mod_tok=e((M, ncol_t), f32), frame_of_tok=(m // (Pn * T)) * T + m % T)
+        if self._use_splitk(M):
+            ws["parts"] = e((M, 8 * D), f32)                     # split-K partial sums (at most 8 splits, ops.splitk_factor)
         if self.matrix:      # frame-level rows (row, column head, frame) of the matrix attention
             Mf = R * self.matrix_cols * T
             ws.update(ms=e((Mf, D), bf), mqkv=e((Mf, 3 * D), bf), matt=e((Mf, D), bf), mz=e((Mf, D), f32))
@@ -670,6 +673,11 @@ class DiT3D(nn.Module):
 
         # --- blocks
         q_scale = LOG2E / math.sqrt(max(self.head_dim, 1))
+        if self._use_splitk(M):
+            self._blocks_splitk(Pk, ws, mod, R, T, q_scale)
+            ops.gemm_bf16(ws["y16"], Pk["fin_w"], ws["tok"], ops.EPI_F32, bias=Pk["fin_b"])
+            ops.unpatchify(ws["tok"], ws["out"], RT, C, H, W, p)
+            return ws["out"]
         col = 0
         xa, xb = ws["x"], ws["y"]
         first_temporal = True
@@ -705,6 +713,59 @@ class DiT3D(nn.Module):
         ops.gemm_bf16(ws["y16"], Pk["fin_w"], ws["tok"], ops.EPI_F32, bias=Pk["fin_b"])
         ops.unpatchify(ws["tok"], ws["out"], RT, C, H, W, p)
         return ws["out"]
+
+    def _use_splitk(self, M: int) -> bool:
+        """Latency regime (small-batch sampling: a few hundred token rows, e.g. DMLab batch 1 = 256): the GEMMs that end a
+        block half (proj, fc2: N = D columns — fewer tiles than SMs — and, for fc2, the longest k-loop of the block) deal
+        their k-blocks over several CTAs and the gated residual moves into the AdaLN kernel that follows
+        (ops.gemm_bf16_splitk / ops.splitk_gate_resid_adaln).  DFOT_DIT_SPLITK=0 pins the plain path (benchmarking)."""
+        return (self.variant == "full" and M <= ops.SPLITK_MAX_ROWS and self.hidden_size % 64 == 0
+                and self.hidden_size <= 2048 and os.environ.get("DFOT_DIT_SPLITK", "1") != "0")
+
+    def _blocks_splitk(self, Pk, ws, mod, R: int, T: int, q_scale: float) -> None:
+        """The block loop of variant=full in the latency regime; leaves the final layer's modulated tokens in ws["y16"].
+        Same arithmetic as the plain loop except for the summation order of the split k-loops.  The token stream x is never
+        stored: its only reader is the next AdaLN (the residual base of a block half is the modulated tensor, quirk Q1), so
+        the two fp32 buffers alternate as y (residual base) of consecutive halves."""
+        D, Pn = self.hidden_size, self.num_patches
+        Ntok, M = T * Pn, R * T * Pn
+        y_cur, y_alt = ws["y"], ws["x"]
+        parts, y16 = ws["parts"], ws["y16"]
+        pending, col = None, 0               # (splits, bias, gate column) of the GEMM whose partial sums are in `parts`
+
+        def norm(shift_col, want_f32=True):
+            nonlocal y_cur, y_alt, pending
+            if pending is None:              # first norm of the network: the patch-embed output is in ws["x"]
+                ops.adaln_layernorm(ws["x"], mod, shift_col, shift_col + D, Pn, y_f32=y_cur if want_f32 else None, y_bf16=y16)
+                return
+            S, bias, gate_col = pending
+            ops.splitk_gate_resid_adaln(parts, S, bias, y_cur, mod, gate_col, shift_col, shift_col + D, Pn,
+                                        y_f32=y_alt if want_f32 else None, y_bf16=y16)
+            y_cur, y_alt, pending = y_alt, y_cur, None
+
+        for bw in Pk["blocks"]:
+            norm(col)
+            if self.use_rope:
+                ops.gemm_bf16(y16, bw["qkv_w"], ws["qkv"], ops.EPI_QKV_ROPE_BF16, bias=bw["qkv_b"], rope_cs=Pk["rope"],
+                              tokens_per_sample=Ntok, model_dim=D, head_dim=self.head_dim, q_scale=q_scale)
+            else:
+                ops.gemm_bf16(y16, bw["qkv_w"], ws["qkv"], ops.EPI_BF16, bias=bw["qkv_b"])
+            ops.attention(ws["qkv"], ws["att"], R, Ntok, self.num_heads, self.head_dim)
+            S = ops.splitk_factor(M, D, D)
+            ops.gemm_bf16_splitk(ws["att"], bw["proj_w"], parts, S)
+            pending = (S, bw["proj_b"], col + 2 * D)
+            if "fc1_w" in bw:
+                norm(col + 3 * D)
+                hidden = bw["fc1_w"].shape[0]
+                hbuf = ws["h"][:, :hidden]
+                ops.gemm_bf16(y16, bw["fc1_w"], hbuf, ops.EPI_GELU_BF16, bias=bw["fc1_b"])
+                S = ops.splitk_factor(M, D, hidden)
+                ops.gemm_bf16_splitk(hbuf, bw["fc2_w"], parts, S)
+                pending = (S, bw["fc2_b"], col + 5 * D)
+                col += 6 * D
+            else:
+                col += 3 * D
+        norm(col, want_f32=False)            # final layer's AdaLayerNorm (dit_blocks.py:533-542)
 
     def _token_attention(self, bw, Pk, ws, xs, xb, bmod, bld, bcol, tpf, n_seq, seq_len, Ntok, q_scale):
         """dit_blocks.py:488-507, first half of a DiTBlock: x <- y + gate * proj(attention(qkv(y))), y = modulate(LN(x))."""

@@ -46,6 +46,10 @@ struct Params {
   int conv_cblks;   // ceil(Cin / 64)
   int conv_W, conv_H;
   int conv_taps;    // 9 (3x3) or 9*kt (causal kt x 3 x 3 over a frame axis: tap / 9 = frame offset of the TMA box)
+  // split-K (single-CTA kernel, plain GEMM, F32 epilogue without bias): N = split_k * (weight rows) output columns;
+  // n-block nb covers weight rows (nb % num_n_w) * BN and the k-blocks of split nb / num_n_w — the partial sums of split s
+  // land in columns [s * N_w, (s + 1) * N_w) of C (N_w % BN == 0, host-checked), so the epilogue is unchanged.
+  int split_k;      // 1 = off
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -745,6 +749,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     m_blk = band_m0 + in_band % band_h;
     n_blk = in_band / band_h;
   };
+  // split-K (Params::split_k): weight n-block and k-block range [kb0, kb1) of output n-block n_blk
+  const int num_n_w = num_n / p.split_k;
+  auto k_range = [&](int n_blk, int& n_blk_w, int& kb0, int& kb1) {
+    const int sp = n_blk / num_n_w;
+    n_blk_w = n_blk - sp * num_n_w;
+    kb0 = (int)((int64_t)sp * num_kb / p.split_k);
+    kb1 = (int)((int64_t)(sp + 1) * num_kb / p.split_k);
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tma_a);
@@ -776,13 +788,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         int m_blk, n_blk;
         tile_coord(tile, m_blk, n_blk);
         if (p.conv_cblks == 0) {
-          for (int kb = 0; kb < num_kb; ++kb) {
+          int n_blk_w, kb0, kb1;
+          k_range(n_blk, n_blk_w, kb0, kb1);
+          for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (elect_one_sync()) {
               mbar_expect_tx(full_bar(stage), C::kStageBytes);
               const uint32_t sa = smem_base + stage * C::kStageBytes;
               tma_load_2d(sa, &tma_a, full_bar(stage), kb * BK, m_blk * BM);
-              tma_load_2d(sa + C::kStageBytesA, &tma_b, full_bar(stage), kb * BK, n_blk * BN);
+              tma_load_2d(sa + C::kStageBytesA, &tma_b, full_bar(stage), kb * BK, n_blk_w * BN);
             }
             __syncwarp();
             if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
@@ -822,7 +836,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        int kb0 = 0, kb1 = num_kb;
+        if (p.split_k > 1) {                               // (conv launches never split)
+          int m_blk, n_blk, n_blk_w;
+          tile_coord(tile, m_blk, n_blk);
+          k_range(n_blk, n_blk_w, kb0, kb1);
+        }
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);               // TMA bytes have landed
           tc_fence_after();
           if (elect_one_sync()) {
@@ -833,10 +853,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
             for (int k = 0; k < BK / UMMA_K; ++k) {
               // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
               umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                        (kb > 0 || k > 0) ? 1u : 0u);
+                        (kb > kb0 || k > 0) ? 1u : 0u);
             }
             umma_commit(empty_bar(stage));                 // ring slot reusable once these MMAs retire
-            if (kb + 1 == num_kb) umma_commit(tmem_full_bar(acc));   // accumulator complete → epilogue
+            if (kb + 1 == kb1) umma_commit(tmem_full_bar(acc));   // accumulator complete → epilogue
           }
           __syncwarp();
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
@@ -1362,7 +1382,7 @@ extern "C" int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
                  DFOT_ERR_INVALID_ARG, "gemm: QKV_ROPE needs rope table, tokens_per_sample, head_dim | model_dim, N=3D");
   Params p;
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.C = Cout; p.ldc = ldc; p.e = *epi;
-  p.conv_cblks = 0; p.conv_W = p.conv_H = 1; p.conv_taps = 9;
+  p.conv_cblks = 0; p.conv_W = p.conv_H = 1; p.conv_taps = 9; p.split_k = 1;
   CUtensorMap ta, tb;
   int rc = make_tmap(&ta, A, M, K, lda, BM);
   if (rc) return rc;
@@ -1388,6 +1408,43 @@ extern "C" int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
     if (!rc) rc = dispatch_epi<64>(epilogue, ta, tb, p, s);
   }
   return rc ? rc : gn_end(p, s);
+}
+
+// Split-K for the latency regime (a few hundred rows: fewer output tiles than SMs and a long serial k-loop per CTA, e.g.
+// DiT-B fc2 at batch 1: 256 x 768 x 3072 = 24 tiles of 48 k-blocks, bound by one SM's TMA fill rate).  The k-blocks are
+// dealt to `splits` CTAs per output tile; split s writes its fp32 partial sums to columns [s*N, (s+1)*N) of
+// parts[M, splits*N] — no atomics, the consumer (dfot_splitk_gate_resid_adaln) adds them in a fixed order.
+extern "C" int dfot_gemm_bf16_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, float* parts, int64_t M,
+                                     int64_t N, int64_t K, int64_t splits, void* stream) {
+  using namespace dfot;
+  using namespace dfot::gemm;
+  DFOT_REQUIRE(A && W && parts, DFOT_ERR_INVALID_ARG, "gemm_splitk: null pointer");
+  DFOT_REQUIRE(M > 0 && N > 0 && K > 0 && splits >= 1 && M < (1ll << 31) && N * splits < (1ll << 31) && K < (1ll << 31),
+               DFOT_ERR_INVALID_ARG, "gemm_splitk: bad sizes M=%lld N=%lld K=%lld splits=%lld", (long long)M, (long long)N,
+               (long long)K, (long long)splits);
+  DFOT_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K, DFOT_ERR_UNSUPPORTED,
+               "gemm_splitk: K, lda, ldw must be multiples of 8 (16-byte TMA strides)");
+  DFOT_REQUIRE(N % 64 == 0, DFOT_ERR_UNSUPPORTED, "gemm_splitk: N must be a multiple of 64 (whole n-blocks per split)");
+  DFOT_REQUIRE(splits <= ceil_div(K, BK), DFOT_ERR_INVALID_ARG, "gemm_splitk: more splits (%lld) than k-blocks (%lld)",
+               (long long)splits, (long long)ceil_div(K, BK));
+  DFOT_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0) && ((uintptr_t)parts % 16 == 0), DFOT_ERR_UNSUPPORTED,
+               "gemm_splitk: A, W, parts must be 16-byte aligned");
+  Params p;
+  memset(&p.e, 0, sizeof(p.e));
+  p.M = (int)M; p.N = (int)(N * splits); p.K = (int)K; p.C = parts; p.ldc = N * splits;
+  p.conv_cblks = 0; p.conv_W = p.conv_H = 1; p.conv_taps = 9; p.split_k = (int)splits;
+  p.e.tokens_per_frame = 1; p.e.tokens_per_sample = 1;
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, A, M, K, lda, BM);
+  if (rc) return rc;
+  // the widest n-block that divides N and still leaves the tiles x splits grid at or under one wave
+  const int64_t m_tiles = ceil_div(M, BM);
+  int bn = 64;
+  if (N % 128 == 0 && m_tiles * (N / 64) * splits > num_sms()) bn = 128;
+  rc = make_tmap(&tb, W, N, K, ldw, bn);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  return bn == 128 ? launch<128, DFOT_EPI_F32>(ta, tb, p, s) : launch<64, DFOT_EPI_F32>(ta, tb, p, s);
 }
 
 // 3x3 convolution, stride 1, zero padding 1, over NHWC bf16 activations as an implicit GEMM on the same kernel:
@@ -1439,7 +1496,7 @@ static int conv_impl(const void* x, const void* w, void* out, int64_t ldc, int64
   }
   Params p;
   p.M = (int)(n_img * H * W); p.N = (int)Cout; p.K = (int)(9 * kt * Cin); p.C = out; p.ldc = ldc; p.e = *epi;
-  p.conv_cblks = (int)ceil_div(Cin, BK); p.conv_W = (int)W; p.conv_H = (int)H; p.conv_taps = (int)(9 * kt);
+  p.conv_cblks = (int)ceil_div(Cin, BK); p.conv_W = (int)W; p.conv_H = (int)H; p.conv_taps = (int)(9 * kt); p.split_k = 1;
   CUtensorMap ta, tb;
   {
     cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(n_img + kt - 1)};

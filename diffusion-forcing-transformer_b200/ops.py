@@ -158,6 +158,56 @@ def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, gate=None, ld_gate=0, 
     _abi.check(rc, "gemm_bf16")
 
 
+import os as _os
+
+# token rows up to which the DiT blocks take the split-K path (see splitk_factor); the environment variable pins it (benchmarking)
+SPLITK_MAX_ROWS = int(_os.environ.get("DFOT_DIT_SPLITK_MAX_ROWS", "1280"))
+
+
+def splitk_factor(M: int, N: int, K: int, sms: int = 148) -> int:
+    """How many CTAs share the k-loop of one output tile of a [M, N] x K GEMM in the latency regime: as many as keep the
+    grid within one wave of the 148 SMs, at least four 64-wide k-blocks each, at most 8.  1 = not worth splitting."""
+    tiles = -(-M // 128) * -(-N // 64)
+    return max(1, min(sms // max(tiles, 1), (K // 64) // 4, 8))
+
+
+def gemm_bf16_splitk(a, w, parts, splits, M=None):
+    """K2 split-K: a [M,K] bf16, w [N,K] bf16 -> parts [M, splits*N] f32 partial sums (no bias); N % 64 == 0."""
+    for t, name in ((a, "a"), (w, "w")):
+        if not t.is_cuda or t.dtype != torch.bfloat16 or t.stride(-1) != 1:
+            raise RuntimeError(f"dfot_b200: `{name}` must be a CUDA bf16 matrix with unit inner stride")
+    _need(parts, torch.float32, "parts")
+    M = a.shape[0] if M is None else M
+    N, K = w.shape
+    if a.shape[1] != K or parts.numel() < M * splits * N:
+        raise RuntimeError(f"dfot_b200: split-K shape mismatch a{tuple(a.shape)} w{tuple(w.shape)} parts{tuple(parts.shape)}")
+    rc = _abi.lib().dfot_gemm_bf16_splitk(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), parts.data_ptr(), M, N, K,
+                                          splits, _stream())
+    _abi.check(rc, "gemm_bf16_splitk")
+
+
+def splitk_gate_resid_adaln(parts, splits, bias, resid, mod, gate_col, shift_col, scale_col, tokens_per_frame, x_out=None,
+                            y_f32=None, y_bf16=None, eps=1e-6):
+    """x = resid + mod[f, gate_col:] * (sum of the split-K partial sums + bias), then the next AdaLN on x (shift_col < 0:
+    none).  resid [M,D] f32, parts [M, splits*D] f32, mod [frames, ld] f32."""
+    _need(parts, torch.float32, "parts")
+    _need(resid, torch.float32, "resid")
+    _need(mod, torch.float32, "mod")
+    M, D = resid.shape
+    if parts.numel() < M * splits * D:
+        raise RuntimeError("dfot_b200: `parts` is smaller than M * splits * D")
+    for t, dt, name in ((bias, torch.float32, "bias"), (x_out, torch.float32, "x_out"), (y_f32, torch.float32, "y_f32"),
+                        (y_bf16, torch.bfloat16, "y_bf16")):
+        if t is not None:
+            _need(t, dt, name)
+            if name != "bias" and (t.data_ptr() == resid.data_ptr() or tuple(t.shape) != (M, D)):
+                raise RuntimeError(f"dfot_b200: `{name}` must be a [M, D] tensor that does not alias `resid`")
+    rc = _abi.lib().dfot_splitk_gate_resid_adaln(parts.data_ptr(), splits, _ptr(bias), resid.data_ptr(), mod.data_ptr(),
+                                                 mod.shape[-1], gate_col, shift_col, scale_col, _ptr(x_out), _ptr(y_f32),
+                                                 _ptr(y_bf16), M, D, tokens_per_frame, eps, _stream())
+    _abi.check(rc, "splitk_gate_resid_adaln")
+
+
 def attention(qkv, out, R, Ntok, heads, head_dim, score_bound=0.0):
     """K3. qkv [R*Ntok, 3*D] bf16 (q rotated+scaled, k rotated), out [R*Ntok, D] bf16 (row stride may exceed D).
     score_bound > 0: an upper bound of |q.k| (pre-scaled, log2 units), e.g. from QK-normalisation — lets the kernel drop

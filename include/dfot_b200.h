@@ -178,6 +178,24 @@ DFOT_API int dfot_conv3d_causal_bf16(const void* x, const void* w, void* out, in
                             int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t kt, int epilogue,
                             const dfot_gemm_epilogue* epi, void* stream);
 
+/* Split-K pair for the latency regime of K2 (a few hundred token rows — small-batch DiT sampling: fewer output tiles than
+ * SMs and a long serial k-loop per CTA, bound by one SM's TMA fill rate):
+ *   dfot_gemm_bf16_splitk: parts[M, splits*N] f32, columns [s*N, (s+1)*N) = A[:, K_s] · W[:, K_s]^T for the s-th share of
+ *       the k-blocks (no bias, no atomics).  N % 64 == 0, splits <= ceil(K / 64); same alignment rules as dfot_gemm_bf16.
+ *   dfot_splitk_gate_resid_adaln: the consumer, fused with the AdaLN that follows a DiT block half
+ *       (dit_blocks.py:504-509 then :427-437):
+ *         x[m, :] = resid[m, :] + mod[f(m), gate_col + :] * (sum_s parts[m, s*D + :] + bias)     (fixed split order)
+ *         y[m, :] = LN_eps(x[m, :]) * (1 + mod[f(m), scale_col + :]) + mod[f(m), shift_col + :]  -> y_f32 and / or y_bf16
+ *       x_out (may be NULL) receives x; shift_col < 0: no norm (x_out is the output).  Outputs must not alias resid.
+ *       D % 4 == 0, D <= 2048.
+ */
+DFOT_API int dfot_gemm_bf16_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, float* parts, int64_t M, int64_t N,
+                          int64_t K, int64_t splits, void* stream);
+DFOT_API int dfot_splitk_gate_resid_adaln(const float* parts, int64_t splits, const float* bias, const float* resid,
+                                 const float* mod, int64_t mod_ld, int64_t gate_col, int64_t shift_col, int64_t scale_col,
+                                 float* x_out, float* y_f32, void* y_bf16, int64_t M, int64_t D, int64_t tokens_per_frame,
+                                 float eps, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K3 — attention over space-time latent tokens (non-causal, no mask: context frames are
  * expressed through per-frame noise levels, never an attention mask — SURVEY.md §8a Q9).

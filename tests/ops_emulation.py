@@ -105,6 +105,34 @@ def patch_expand_gate_resid(x, y, z, pu, pb, gate, ld_gate, R, L, P, Mc):
     x.copy_((y.reshape(R, L, P, D) + g * s).reshape(x.shape))
 
 
+def gemm_bf16_splitk(a, w, parts, splits, M=None):
+    M = a.shape[0] if M is None else M
+    N, K = w.shape
+    kb = -(-K // 64)
+    out = parts.reshape(-1)[: M * splits * N].view(M, splits, N)
+    for s in range(splits):
+        k0, k1 = 64 * (s * kb // splits), min(K, 64 * ((s + 1) * kb // splits))
+        out[:, s] = a[:M, k0:k1].float() @ w[:, k0:k1].float().t()
+
+
+def splitk_gate_resid_adaln(parts, splits, bias, resid, mod, gate_col, shift_col, scale_col, tokens_per_frame, x_out=None,
+                            y_f32=None, y_bf16=None, eps=1e-6):
+    M, D = resid.shape
+    acc = parts.reshape(-1)[: M * splits * D].view(M, splits, D).sum(1)
+    if bias is not None:
+        acc = acc + bias
+    frame = torch.arange(M) // tokens_per_frame
+    x = resid + mod[frame, gate_col:gate_col + D] * acc
+    if x_out is not None:
+        x_out.copy_(x)
+    if shift_col >= 0:
+        y = F.layer_norm(x, (D,), eps=eps) * (1 + mod[frame, scale_col:scale_col + D]) + mod[frame, shift_col:shift_col + D]
+        if y_f32 is not None:
+            y_f32.copy_(y)
+        if y_bf16 is not None:
+            y_bf16.copy_(y.to(BF))
+
+
 def silu_sum_bf16(a, b, row_mask, rows_per_mask, out):
     s = a.float()
     if b is not None:
@@ -335,7 +363,8 @@ ALL = ["relu_bf16", "pixel_shuffle2x", "linear_attention_relu", "dwconv3x3_glu_b
        "rmsnorm_film_bf16", "qk_norm_rope", "attention", "avgpool2x2", "sub_bf16", "upsample2x_add", "pose_ray_patches",
        "noise_features", "conv3d_causal_bf16", "groupnorm_stats_strided", "groupnorm_apply_bf16",
        "vae_upsample2x_bf16", "upsample2x_nearest_bf16", "vae_fill_pad_frames", "softmax_rows_bf16", "adaln_layernorm",
-       "silu_sum_bf16", "patch_mix_bf16", "patch_expand_gate_resid"]
+       "silu_sum_bf16", "patch_mix_bf16", "patch_expand_gate_resid", "gemm_bf16_splitk",
+       "splitk_gate_resid_adaln"]
 
 
 def install(monkeypatch):

@@ -93,6 +93,19 @@ def test_k600_fullsize_rollout_vs_oracle(mlp):
     _rollout(cfg, xs, None, 2, seed=43)
 
 
+@pytest.mark.parametrize("splitk", ["1", "0"])
+def test_dmlab_fullsize_rollout_vs_oracle(splitk, monkeypatch):
+    """BASELINE configs[4] at batch 1: DiT3D-B (12 x 768, 12 heads of 64, patch 2, MLP x4) on 16 frames of 32x8x8 latents
+    (256 token rows — the latency regime: split-K GEMMs + the gated residual fused into the next AdaLN) with action
+    conditioning, and the same rollout through the plain block loop (DFOT_DIT_SPLITK=0)."""
+    monkeypatch.setenv("DFOT_DIT_SPLITK", splitk)
+    cfg = bench.dmlab_cfg(sampling_timesteps=2, frames=16)
+    g = torch.Generator().manual_seed(5)
+    xs = torch.randn((1, 16, 32, 8, 8), generator=g)
+    conds = torch.randn((1, 16, 3), generator=g)
+    _rollout(cfg, xs, conds, 4, seed=53)
+
+
 def test_k600_fullsize_vanilla_hg_batch2():
     """Same backbone under vanilla history guidance (2 branch rows per sample) at batch 2: the batched-row path of the
     28-block network, not only B = 1."""

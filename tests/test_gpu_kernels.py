@@ -174,7 +174,8 @@ def test_attention_rescale_stress_is_deterministic(heads, dh, N):
 
 
 # ---------------------------------------------------------------- K1 adaLN + LayerNorm
-@pytest.mark.parametrize("M,D,P", [(512, 256, 64), (1280, 1152, 256), (100, 64, 16), (96, 768, 16), (33, 2048, 11)])
+@pytest.mark.parametrize("M,D,P", [(512, 256, 64), (1280, 1152, 256), (100, 64, 16), (96, 768, 16), (33, 2048, 11),
+                                   (4096, 1152, 256), (2304, 768, 16), (2049, 2048, 3), (300, 4096, 100)])   # (> 2048 rows or D > 2048: one warp per row)
 def test_adaln_layernorm(M, D, P):
     g = torch.Generator().manual_seed(M + D)
     x = (torch.randn((M, D), generator=g) * 3 + 0.5).to(DEV)
@@ -295,3 +296,42 @@ def test_patch_mix_and_expand(R, L, P, Mc, D):
             s = s + bias.double()
         ref = y.reshape(R, L, P, D).double() + mod[:, 2 * D:3 * D].reshape(R, L, 1, D).double() * s
         assert (x.cpu().double() - ref.reshape(-1, D)).abs().max().item() < 1e-4
+
+
+# ---------------------------------------------------------------- split-K GEMM + its fused consumer (latency regime)
+@pytest.mark.parametrize("M,N,K,S", [(256, 768, 3072, 6), (256, 768, 768, 3), (100, 64, 128, 2), (512, 1152, 4608, 2),
+                                     (128, 64, 64, 1), (300, 256, 1024, 8), (256, 1536, 520, 5)])
+def test_gemm_splitk_partials_and_fused_consumer(M, N, K, S):
+    g = torch.Generator().manual_seed(M + N + K)
+    a = bf16_round(torch.randn((M, K), generator=g))
+    w = bf16_round(torch.randn((N, K), generator=g) / math.sqrt(K))
+    parts = torch.full((M, S * N), float("nan"), device=DEV)
+    ops.gemm_bf16_splitk(a.to(DEV).to(torch.bfloat16), w.to(DEV).to(torch.bfloat16), parts, S)
+    kb = -(-K // 64)
+    p = parts.cpu().view(M, S, N)
+    for s in range(S):                                              # every split holds exactly its share of the k-blocks
+        k0, k1 = 64 * (s * kb // S), min(K, 64 * ((s + 1) * kb // S))
+        ref = a[:, k0:k1].double() @ w[:, k0:k1].double().t()
+        assert (p[:, s].double() - ref).abs().max().item() < 2e-3, s
+    full = a.double() @ w.double().t()
+    assert (p.double().sum(1) - full).abs().max().item() < 2e-3
+    # consumer: x = resid + gate * (sum + bias); y = LN(x) * (1 + scale) + shift
+    tpf = 16 if M % 16 == 0 else 1
+    frames = -(-M // tpf)
+    resid, bias = torch.randn((M, N), generator=g), torch.randn((N,), generator=g)
+    mod = torch.randn((frames, 3 * N + 8), generator=g) * 0.5
+    x = torch.empty((M, N), device=DEV)
+    y32 = torch.empty((M, N), device=DEV)
+    y16 = torch.empty((M, N), device=DEV, dtype=torch.bfloat16)
+    ops.splitk_gate_resid_adaln(parts, S, bias.to(DEV), resid.to(DEV), mod.to(DEV), 2 * N, 0, N, tpf, x_out=x, y_f32=y32,
+                                y_bf16=y16)
+    fr = torch.arange(M) // tpf
+    xr = resid.double() + mod[fr, 2 * N:3 * N].double() * (p.double().sum(1) + bias.double())
+    yr = torch.nn.functional.layer_norm(xr, (N,), eps=1e-6) * (1 + mod[fr, N:2 * N].double()) + mod[fr, :N].double()
+    assert (x.cpu().double() - xr).abs().max().item() < 1e-4
+    assert (y32.cpu().double() - yr).abs().max().item() < 1e-3
+    assert (y16.float().cpu().double() - yr).abs().max().item() < 2e-2 * max(1.0, yr.abs().max().item())
+    x2 = torch.empty((M, N), device=DEV)                            # no norm: x only, no bias
+    ops.splitk_gate_resid_adaln(parts, S, None, resid.to(DEV), mod.to(DEV), 2 * N, -1, -1, tpf, x_out=x2)
+    xr2 = resid.double() + mod[fr, 2 * N:3 * N].double() * p.double().sum(1)
+    assert (x2.cpu().double() - xr2).abs().max().item() < 1e-4

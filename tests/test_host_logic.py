@@ -266,3 +266,32 @@ def test_dit3d_host_orchestration_with_emulated_kernels(name, monkeypatch):
     ref = arr["prediction"][:, n_ctx:]
     mse = float(((out.numpy()[:, n_ctx:] - ref) ** 2).mean())
     assert 10 * np.log10((ref.max() - ref.min()) ** 2 / max(mse, 1e-30)) >= 40.0
+
+
+@pytest.mark.parametrize("pos", ["rope_3d", "learned_1d"])
+def test_dit3d_splitk_block_loop_equals_plain_loop(pos, monkeypatch):
+    """The latency-regime block loop of DiT3D (split-K GEMMs at the end of a block half + the gated residual fused into the
+    next AdaLN, x never stored) against the plain loop on the kernel-contract emulations, at a width where the k-loops
+    really split (hidden 256, MLP x4: 4 splits of fc2) — same arithmetic up to the summation order of the splits."""
+    import ops_emulation
+    from oracle.cases import _small
+    from dfot_b200.algorithms.dfot.backbones.dit.dit3d import DiT3D
+    cfg = _small(**{"backbone.hidden_size": 256, "backbone.num_heads": 4, "backbone.spatial_mlp_ratio": 4.0,
+                    "backbone.depth": 3, "backbone.pos_emb_type": pos})["backbone"]
+    torch.manual_seed(0)
+    model = DiT3D(cfg, [4, 8, 8], 4, use_causal_mask=False).eval()
+    for prm in model.parameters():                       # AdaLN-Zero / final layer are zero-initialised: redraw
+        if prm.abs().sum() == 0:
+            torch.nn.init.normal_(prm, std=0.05)
+    ops_emulation.install(monkeypatch)
+    model.use_cuda_graph = False
+    assert ops.splitk_factor(2 * 4 * 16, 256, 1024) == 4 and ops.splitk_factor(128, 256, 256) == 1
+    x, lv = torch.randn((2, 4, 4, 8, 8)), torch.randint(0, 1000, (2, 4))
+    assert model._use_splitk(2 * 4 * 16)
+    out_split = model(x, lv).clone()
+    monkeypatch.setenv("DFOT_DIT_SPLITK", "0")
+    model._ws.clear()
+    assert not model._use_splitk(2 * 4 * 16)
+    out_plain = model(x, lv).clone()
+    assert out_plain.abs().max() > 1e-2
+    assert (out_split - out_plain).abs().max().item() <= 1e-5 * max(1.0, out_plain.abs().max().item())
