@@ -549,6 +549,9 @@ def main():
     ap.add_argument("--attn-running-max", action="store_true",
                     help="force the running-maximum attention path (what trained q/k-norm weights with a score bound > 96 "
                          "would select) instead of the bounded-score path the random-init weights allow")
+    ap.add_argument("--latency-mode", action="store_true",
+                    help="small-batch DiT sampling: split-K block loop, block-per-row AdaLN, single-tile attention items "
+                         "(ops.set_latency_mode: a row's bits then depend on its batch; off by default)")
     ap.add_argument("--decode", action="store_true",
                     help="k600 / dmlab: decode the sampled latents to frames inside the e2e region (random-init VideoVAE: "
                          "hidden 128, z 16 / DC-AE: dc_ae_preprocessor.yaml) and report the decode on its own; `value` stays "
@@ -567,6 +570,8 @@ def main():
                                else f"samples sharded x{world}"), l2=wl.l2,
                   cuda_graph=True,     # this repo's arm replays the backbone forward from a CUDA graph (both arms name it)
                   attention_path="running-max (forced)" if args.attn_running_max else "by score bound")
+    if args.latency_mode:
+        config["latency_mode"] = True
 
     if args.impl == "reference":
         if rank != 0:
@@ -588,6 +593,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    ops.set_latency_mode(args.latency_mode)
 
     attn_paths = {}
     if True:      # record (and optionally force) the attention kernel variant: bounded scores vs running maximum

@@ -13,7 +13,7 @@ EPI_F32, EPI_BF16, EPI_GELU_BF16, EPI_SILU_BF16, EPI_GATE_RESID_F32, EPI_QKV_ROP
 SYMBOLS = [
     "dfot_abi_version", "dfot_last_error", "dfot_launch_count", "dfot_sampler_step_hg", "dfot_adaln_layernorm",
     "dfot_gemm_bf16", "dfot_attention", "dfot_attention_strided", "dfot_attention_bounded", "dfot_noise_features", "dfot_silu_sum_bf16", "dfot_patchify_bf16",
-    "dfot_unpatchify", "dfot_cast_bf16", "dfot_patch_mix_bf16", "dfot_patch_expand_gate_resid", "dfot_gemm_bf16_splitk", "dfot_splitk_gate_resid_adaln", "dfot_conv3x3_bf16", "dfot_conv3d_causal_bf16", "dfot_groupnorm_stats", "dfot_groupnorm_silu_bf16",
+    "dfot_unpatchify", "dfot_cast_bf16", "dfot_patch_mix_bf16", "dfot_patch_expand_gate_resid", "dfot_gemm_bf16_splitk", "dfot_splitk_gate_resid_adaln", "dfot_set_latency_mode", "dfot_get_latency_mode", "dfot_conv3x3_bf16", "dfot_conv3d_causal_bf16", "dfot_groupnorm_stats", "dfot_groupnorm_silu_bf16",
     "dfot_rmsnorm_film_bf16", "dfot_qk_norm_rope", "dfot_avgpool2x2", "dfot_sub_bf16", "dfot_upsample2x_add",
     "dfot_pose_ray_patches", "dfot_groupnorm_stats_strided", "dfot_groupnorm_apply_bf16", "dfot_vae_upsample2x_bf16",
     "dfot_vae_fill_pad_frames", "dfot_softmax_rows_bf16", "dfot_upsample2x_nearest_bf16",
@@ -75,6 +75,8 @@ def lib() -> ctypes.CDLL:
     L.dfot_patchify_bf16.argtypes = [vp, i, vp, i64, i64, i64, i64, i64, i64, vp]
     L.dfot_unpatchify.argtypes = [vp, i64, vp, i, i64, i64, i64, i64, i64, vp]
     L.dfot_cast_bf16.argtypes = [vp, vp, i64, vp]
+    L.dfot_set_latency_mode.argtypes = [i]
+    L.dfot_get_latency_mode.argtypes = []
     L.dfot_gemm_bf16_splitk.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, i64, vp]
     L.dfot_splitk_gate_resid_adaln.argtypes = [vp, i64, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, i64, i64, i64, c_float, vp]
     L.dfot_patch_mix_bf16.argtypes = [vp, vp, vp, i64, i64, i64, i64, i64, vp]

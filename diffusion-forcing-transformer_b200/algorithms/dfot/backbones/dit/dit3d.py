@@ -540,8 +540,6 @@ class DiT3D(nn.Module):
             m = torch.arange(M, device=dev)
             ncol_t = (6 if self.dit_base.temporal_blocks[0].use_mlp else 3) * D
             ws.update(xt=e((M, D), f32), mod_tok=e((M, ncol_t), f32), frame_of_tok=(m // (Pn * T)) * T + m % T)
-        if self._use_splitk(M):
-            ws["parts"] = e((M, 8 * D), f32)                     # split-K partial sums (at most 8 splits, ops.splitk_factor)
         if self.matrix:      # frame-level rows (row, column head, frame) of the matrix attention
             Mf = R * self.matrix_cols * T
             ws.update(ms=e((Mf, D), bf), mqkv=e((Mf, 3 * D), bf), matt=e((Mf, D), bf), mz=e((Mf, D), f32))
@@ -586,7 +584,8 @@ class DiT3D(nn.Module):
         R, T = x.shape[:2]
         levels = noise_levels if noise_levels.dtype in (torch.int64, torch.float32) else noise_levels.float()
         use_mask = external_cond_mask is not None and external_cond is not None and self.external_cond_dropout != 0
-        sig = (R, T, x.dtype, levels.dtype, external_cond is not None, use_mask, out_dtype, str(x.device))
+        sig = (R, T, x.dtype, levels.dtype, external_cond is not None, use_mask, out_dtype, str(x.device),
+               ops.latency_mode())
         st = self._graphs.get(sig)
         if st is None:   # first call with this signature: eager (also warms up lazy kernel attributes)
             self._graphs[sig] = {"graph": None, "key": self._version_key()}
@@ -613,19 +612,43 @@ class DiT3D(nn.Module):
                 if st.get(name + "_key") != key:
                     st[name].copy_(src)
                     st[name + "_key"] = key
+        if st["cond"] is not None:
+            # the condition embedding is constant over the sampling steps of a window: it is computed here, outside the
+            # graph, when the condition tensor (or the weights) changed — keyed on the workspace, which the graphs of
+            # different signatures share; the source tensor is kept alive so that its address cannot be re-used
+            Pk, ws = self.packed(), self._workspace(R, T, x.device, out_dtype)
+            ckey = (external_cond.data_ptr(), external_cond._version, tuple(external_cond.shape), self._packed_key)
+            if ws.get("cemb_key") != ckey:
+                self._cond_embedding(Pk, ws, st["cond"], R, T)
+                ws["cemb_key"], ws["cemb_src"] = ckey, external_cond
         if st["graph"] is None:
             g = torch.cuda.CUDAGraph()
             n0 = _abi.launch_count()
             with torch.cuda.graph(g):
-                st["out"] = self._forward_impl(xin, st["levels"], st["cond"], st["mask"], out_dtype)
+                st["out"] = self._forward_impl(xin, st["levels"], st["cond"], st["mask"], out_dtype, cond_cached=True)
             st["graph"], st["kernels"] = g, _abi.launch_count() - n0
         st["graph"].replay()
         ops.count_replayed_launches(st["kernels"])
         return st["out"]
 
+    def _cond_embedding(self, Pk, ws, external_cond: torch.Tensor, R: int, T: int) -> None:
+        """ws["cemb"] <- the per-frame embedding of the external condition (before the mask).  It does not depend on the
+        noise levels, so under a CUDA graph it is computed once per condition tensor, outside the graph (forward())."""
+        ws["cemb_key"] = None            # (whoever caches the result sets the key afterwards)
+        if self.label_cond:
+            # dit3d.py:171-173: emb + table[labels]; labels [R, 1] (one per clip, ucf_101.py:304-309) or [R, T]; the
+            # mask is not passed to the label embedding.  The row gather is data movement (torch indexing).
+            lab = external_cond.reshape(R, -1).long()
+            ws["cemb"].view(R, T, -1).copy_(Pk["label_table"][lab].expand(R, T, -1))
+        else:
+            ws["cin"][:, : self.external_cond_dim] = external_cond.reshape(R * T, -1).to(torch.bfloat16)
+            ops.gemm_bf16(ws["cin"], Pk["c1_w"], ws["c1"], ops.EPI_SILU_BF16, bias=Pk["c1_b"])
+            ops.gemm_bf16(ws["c1"], Pk["c2_w"], ws["cemb"], ops.EPI_F32, bias=Pk["c2_b"])
+
     @torch.no_grad()
     def _forward_impl(self, x: torch.Tensor, noise_levels: torch.Tensor, external_cond: Optional[torch.Tensor] = None,
-                      external_cond_mask: Optional[torch.Tensor] = None, out_dtype=torch.float32) -> torch.Tensor:
+                      external_cond_mask: Optional[torch.Tensor] = None, out_dtype=torch.float32,
+                      cond_cached: bool = False) -> torch.Tensor:
         R, T = x.shape[:2]
         C, H, W = self.x_shape
         D, p, Pn = self.hidden_size, self.patch_size, self.num_patches
@@ -655,18 +678,12 @@ class DiT3D(nn.Module):
             if self.external_cond_embedding is None:
                 raise ValueError("external_cond given but the backbone was built with external_cond_dim=0")
             cemb = ws["cemb"]
-            if self.label_cond:
-                # dit3d.py:171-173: emb + table[labels]; labels [R, 1] (one per clip, ucf_101.py:304-309) or [R, T]; the
-                # mask is not passed to the label embedding.  The row gather is data movement (torch indexing).
-                lab = external_cond.reshape(R, -1).long()
-                cemb.view(R, T, -1).copy_(Pk["label_table"][lab].expand(R, T, -1))
-            else:
-                ws["cin"][:, : self.external_cond_dim] = external_cond.reshape(RT, -1).to(torch.bfloat16)
-                ops.gemm_bf16(ws["cin"], Pk["c1_w"], ws["c1"], ops.EPI_SILU_BF16, bias=Pk["c1_b"])
-                ops.gemm_bf16(ws["c1"], Pk["c2_w"], ws["cemb"], ops.EPI_F32, bias=Pk["c2_b"])
-                # embeddings.py:364-387: with dropout_prob == 0 the embedding is a plain MLP and ignores the mask
-                if external_cond_mask is not None and self.external_cond_dropout != 0:
-                    row_mask = external_cond_mask.to(torch.uint8).contiguous()
+            if not cond_cached:
+                self._cond_embedding(Pk, ws, external_cond, R, T)
+            # embeddings.py:364-387: with dropout_prob == 0 the embedding is a plain MLP and ignores the mask; the label
+            # embedding never sees it (dit3d.py:171-173)
+            if not self.label_cond and external_cond_mask is not None and self.external_cond_dropout != 0:
+                row_mask = external_cond_mask.to(torch.uint8).contiguous()
         ops.silu_sum_bf16(ws["emb"], cemb, row_mask, T, ws["cact"])
         ops.gemm_bf16(ws["cact"], Pk["mod_w"], ws["mod"], ops.EPI_F32, bias=Pk["mod_b"])
         mod, ldm = ws["mod"], ws["mod"].shape[1]
@@ -715,12 +732,13 @@ class DiT3D(nn.Module):
         return ws["out"]
 
     def _use_splitk(self, M: int) -> bool:
-        """Latency regime (small-batch sampling: a few hundred token rows, e.g. DMLab batch 1 = 256): the GEMMs that end a
-        block half (proj, fc2: N = D columns — fewer tiles than SMs — and, for fc2, the longest k-loop of the block) deal
-        their k-blocks over several CTAs and the gated residual moves into the AdaLN kernel that follows
-        (ops.gemm_bf16_splitk / ops.splitk_gate_resid_adaln).  DFOT_DIT_SPLITK=0 pins the plain path (benchmarking)."""
-        return (self.variant == "full" and M <= ops.SPLITK_MAX_ROWS and self.hidden_size % 64 == 0
-                and self.hidden_size <= 2048 and os.environ.get("DFOT_DIT_SPLITK", "1") != "0")
+        """Latency mode (ops.set_latency_mode, off by default) in the latency regime (small-batch sampling: up to ~1k token
+        rows, e.g. DMLab batch 1 = 256): the GEMMs that end a block half (proj, fc2: N = D columns — fewer tiles than SMs —
+        and, for fc2, the longest k-loop of the block) deal their k-blocks over several CTAs and the gated residual moves
+        into the AdaLN kernel that follows (ops.gemm_bf16_splitk / ops.splitk_gate_resid_adaln).  The number of splits
+        depends on the row count, so a row's bits depend on its batch — which is why this is a mode and not the default."""
+        return (ops.latency_mode() and self.variant == "full" and M <= ops.SPLITK_MAX_ROWS and self.hidden_size % 64 == 0
+                and self.hidden_size <= 2048)
 
     def _blocks_splitk(self, Pk, ws, mod, R: int, T: int, q_scale: float) -> None:
         """The block loop of variant=full in the latency regime; leaves the final layer's modulated tokens in ws["y16"].
@@ -730,6 +748,8 @@ class DiT3D(nn.Module):
         D, Pn = self.hidden_size, self.num_patches
         Ntok, M = T * Pn, R * T * Pn
         y_cur, y_alt = ws["y"], ws["x"]
+        if "parts" not in ws:                # split-K partial sums (at most 8 splits, ops.splitk_factor)
+            ws["parts"] = torch.empty((M, 8 * D), dtype=torch.float32, device=ws["x"].device)
         parts, y16 = ws["parts"], ws["y16"]
         pending, col = None, 0               # (splits, bias, gate column) of the GEMM whose partial sums are in `parts`
 

@@ -1262,7 +1262,15 @@ static int launch(const void* qkv, void* out, int64_t ld_out, int64_t R, int64_t
   constexpr int smem2 = 6 * ATOMS * kAtomBytes + 512 /*barriers*/;
   static_assert(smem1 <= 232448 && smem2 <= 232448, "attention: shared memory budget exceeded");
   const int ov = attention_impl_override();
-  const bool paired = ov == 2 || (ov == 0 && Ntok > BQ);      // more than one query tile per sample
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // Kernel 2 (two query tiles per CTA) whenever a sample has more than one query tile — except, in latency mode (the choice
+  // depends on the batch, see dfot_set_latency_mode), in the latency regime of small-batch DiT sampling: short sequences whose single query tiles all fit one wave run as twice as many CTAs of half
+  // the serial work each (measured in the DMLab bench, profiles/r02_dmlab_attn_impl_ab.txt: T = 36 batch 1 735 -> 771
+  // frames/s, T = 16 batch 4 989 -> 1032, batch 1 332 -> 338).
+  const bool latency_regime = latency_mode() && score_bound == 0.f && Ntok <= 1024 && R * heads * ceil_div(Ntok, BQ) <= sms;
+  const bool paired = ov == 2 || (ov == 0 && Ntok > BQ && !latency_regime);
   const int smem_bytes = paired ? smem2 : smem1;
   constexpr int KV2 = KvTile<DP>::value;                      // keys per KV tile of kernel 2
   EncodeTiledFn enc = get_encode_fn();
@@ -1293,9 +1301,6 @@ static int launch(const void* qkv, void* out, int64_t ld_out, int64_t R, int64_t
                  cudaGetErrorString(e));
     configured[which] = true;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   Params p;
   p.out = (__nv_bfloat16*)out;
   p.ld_out = ld_out;

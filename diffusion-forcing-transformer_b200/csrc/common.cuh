@@ -18,6 +18,7 @@ namespace dfot {
 // ---- host-side error plumbing (thread-local message, never throws) ----
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+bool latency_mode();   // dfot_set_latency_mode / DFOT_LATENCY_MODE (abi.cu)
 
 #define DFOT_REQUIRE(cond, code, ...)          \
   do {                                         \

@@ -152,7 +152,7 @@ row_adaln_kernel(const float* __restrict__ parts, int splits, const float* __res
   }
 }
 
-constexpr int64_t kRowKernelMaxRows = 2048;   // up to here K1 runs one block per row (see row_adaln_kernel)
+constexpr int64_t kRowKernelMaxRows = 2048;   // up to here K1 runs one block per row in latency mode (see row_adaln_kernel)
 
 }  // namespace dfot
 
@@ -166,7 +166,7 @@ extern "C" int dfot_adaln_layernorm(const float* x, const float* mod, int64_t mo
                "adaln_layernorm: D, mod_ld and column offsets must be multiples of 4 (128-bit access)");
   DFOT_REQUIRE(D <= 4096, DFOT_ERR_UNSUPPORTED, "adaln_layernorm: D=%lld > 4096 unsupported", (long long)D);
   cudaStream_t s = (cudaStream_t)stream;
-  if (M <= kRowKernelMaxRows && D <= 2048 && (uintptr_t)x % 16 == 0 && (uintptr_t)mod % 16 == 0 && (uintptr_t)y_f32 % 16 == 0 &&
+  if (latency_mode() && M <= kRowKernelMaxRows && D <= 2048 && (uintptr_t)x % 16 == 0 && (uintptr_t)mod % 16 == 0 && (uintptr_t)y_f32 % 16 == 0 &&
       (uintptr_t)y_bf16 % 8 == 0) {
     if (D <= 1024)
       launch_pdl(row_adaln_kernel<1>, dim3((unsigned)M), dim3(kRowThreads), 0, s, (const float*)nullptr, 0,

@@ -160,8 +160,24 @@ def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, gate=None, ld_gate=0, 
 
 import os as _os
 
-# token rows up to which the DiT blocks take the split-K path (see splitk_factor); the environment variable pins it (benchmarking)
+# token rows up to which the DiT blocks take the split-K path in latency mode (see splitk_factor); the environment variable
+# pins it (benchmarking)
 SPLITK_MAX_ROWS = int(_os.environ.get("DFOT_DIT_SPLITK_MAX_ROWS", "1280"))
+_latency_mode = _os.environ.get("DFOT_LATENCY_MODE", "0") == "1"
+
+
+def set_latency_mode(on: bool) -> None:
+    """Latency mode (include/dfot_b200.h, off by default): small-batch DiT sampling trades the bit-level batch invariance of
+    a forward row for latency — split-K block loop, block-per-row AdaLN, single-tile attention items.  Set it before the
+    first forward of a model (CUDA graphs captured earlier keep the kernels they were captured with)."""
+    global _latency_mode
+    _latency_mode = bool(on)
+    if torch.cuda.is_available():
+        _abi.check(_abi.lib().dfot_set_latency_mode(int(_latency_mode)), "set_latency_mode")
+
+
+def latency_mode() -> bool:
+    return _latency_mode
 
 
 def splitk_factor(M: int, N: int, K: int, sms: int = 148) -> int:

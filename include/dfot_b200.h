@@ -47,6 +47,14 @@ DFOT_API int dfot_abi_version(void);
 DFOT_API const char* dfot_last_error(void);
 /* number of kernel launches issued through this library since load (all threads) */
 DFOT_API int64_t dfot_launch_count(void);
+/* Latency mode (off by default; DFOT_LATENCY_MODE=1 turns it on at load).  By default every kernel choice that affects the
+ * ARITHMETIC of a token row is independent of the batch, so a forward row is bit-identical whatever rows it is batched
+ * with (sharded rollouts == single-GPU rollouts, bit for bit).  Latency mode trades that bit-level invariance (parity with
+ * the reference is unchanged) for the latency of small-batch DiT sampling (<= ~1k token rows): K1 runs one block per row up
+ * to 2048 rows, short attention problems that fit one wave as single query tiles use kernel 1, and the host takes the
+ * split-K block loop (dfot_gemm_bf16_splitk + dfot_splitk_gate_resid_adaln) up to 1280 rows. */
+DFOT_API int dfot_set_latency_mode(int on);
+DFOT_API int dfot_get_latency_mode(void);
 
 /* ------------------------------------------------------------------------------------------
  * K4 — fused per-frame sampler step + history-guidance combine (+ next-step prepare).

@@ -93,17 +93,21 @@ def test_k600_fullsize_rollout_vs_oracle(mlp):
     _rollout(cfg, xs, None, 2, seed=43)
 
 
-@pytest.mark.parametrize("splitk", ["1", "0"])
-def test_dmlab_fullsize_rollout_vs_oracle(splitk, monkeypatch):
+@pytest.mark.parametrize("latency_mode", [False, True])
+def test_dmlab_fullsize_rollout_vs_oracle(latency_mode):
     """BASELINE configs[4] at batch 1: DiT3D-B (12 x 768, 12 heads of 64, patch 2, MLP x4) on 16 frames of 32x8x8 latents
-    (256 token rows — the latency regime: split-K GEMMs + the gated residual fused into the next AdaLN) with action
-    conditioning, and the same rollout through the plain block loop (DFOT_DIT_SPLITK=0)."""
-    monkeypatch.setenv("DFOT_DIT_SPLITK", splitk)
-    cfg = bench.dmlab_cfg(sampling_timesteps=2, frames=16)
-    g = torch.Generator().manual_seed(5)
-    xs = torch.randn((1, 16, 32, 8, 8), generator=g)
-    conds = torch.randn((1, 16, 3), generator=g)
-    _rollout(cfg, xs, conds, 4, seed=53)
+    (256 token rows) with action conditioning — through the default kernels and in latency mode (ops.set_latency_mode:
+    split-K GEMMs + the gated residual fused into the next AdaLN, block-per-row AdaLN, single-tile attention items)."""
+    from dfot_b200 import ops
+    ops.set_latency_mode(latency_mode)
+    try:
+        cfg = bench.dmlab_cfg(sampling_timesteps=2, frames=16)
+        g = torch.Generator().manual_seed(5)
+        xs = torch.randn((1, 16, 32, 8, 8), generator=g)
+        conds = torch.randn((1, 16, 3), generator=g)
+        _rollout(cfg, xs, conds, 4, seed=53)
+    finally:
+        ops.set_latency_mode(False)
 
 
 def test_k600_fullsize_vanilla_hg_batch2():

@@ -174,16 +174,21 @@ def test_attention_rescale_stress_is_deterministic(heads, dh, N):
 
 
 # ---------------------------------------------------------------- K1 adaLN + LayerNorm
+@pytest.mark.parametrize("latency_mode", [False, True])    # on: one block per row up to 2048 rows (and D <= 2048)
 @pytest.mark.parametrize("M,D,P", [(512, 256, 64), (1280, 1152, 256), (100, 64, 16), (96, 768, 16), (33, 2048, 11),
-                                   (4096, 1152, 256), (2304, 768, 16), (2049, 2048, 3), (300, 4096, 100)])   # (> 2048 rows or D > 2048: one warp per row)
-def test_adaln_layernorm(M, D, P):
+                                   (4096, 1152, 256), (2049, 2048, 3), (300, 4096, 100)])
+def test_adaln_layernorm(M, D, P, latency_mode):
     g = torch.Generator().manual_seed(M + D)
     x = (torch.randn((M, D), generator=g) * 3 + 0.5).to(DEV)
     frames = (M + P - 1) // P
     mod = torch.randn((frames, 6 * D), generator=g).to(DEV)
     y32 = torch.empty((M, D), device=DEV)
     y16 = torch.empty((M, D), device=DEV, dtype=torch.bfloat16)
-    ops.adaln_layernorm(x, mod, 3 * D, 4 * D, P, y_f32=y32, y_bf16=y16)
+    ops.set_latency_mode(latency_mode)
+    try:
+        ops.adaln_layernorm(x, mod, 3 * D, 4 * D, P, y_f32=y32, y_bf16=y16)
+    finally:
+        ops.set_latency_mode(False)
     f = torch.arange(M, device=DEV) // P
     ref = torch.nn.functional.layer_norm(x, (D,), eps=1e-6) * (1 + mod[f, 4 * D:5 * D]) + mod[f, 3 * D:4 * D]
     assert (y32 - ref).abs().max().item() < 1e-4

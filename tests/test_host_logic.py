@@ -270,7 +270,7 @@ def test_dit3d_host_orchestration_with_emulated_kernels(name, monkeypatch):
 
 @pytest.mark.parametrize("pos", ["rope_3d", "learned_1d"])
 def test_dit3d_splitk_block_loop_equals_plain_loop(pos, monkeypatch):
-    """The latency-regime block loop of DiT3D (split-K GEMMs at the end of a block half + the gated residual fused into the
+    """The latency-mode block loop of DiT3D (ops.set_latency_mode; split-K GEMMs at the end of a block half + the gated residual fused into the
     next AdaLN, x never stored) against the plain loop on the kernel-contract emulations, at a width where the k-loops
     really split (hidden 256, MLP x4: 4 splits of fc2) — same arithmetic up to the summation order of the splits."""
     import ops_emulation
@@ -287,11 +287,10 @@ def test_dit3d_splitk_block_loop_equals_plain_loop(pos, monkeypatch):
     model.use_cuda_graph = False
     assert ops.splitk_factor(2 * 4 * 16, 256, 1024) == 4 and ops.splitk_factor(128, 256, 256) == 1
     x, lv = torch.randn((2, 4, 4, 8, 8)), torch.randint(0, 1000, (2, 4))
+    assert not model._use_splitk(2 * 4 * 16)             # latency mode is off by default
+    out_plain = model(x, lv).clone()
+    monkeypatch.setattr(ops, "_latency_mode", True)
     assert model._use_splitk(2 * 4 * 16)
     out_split = model(x, lv).clone()
-    monkeypatch.setenv("DFOT_DIT_SPLITK", "0")
-    model._ws.clear()
-    assert not model._use_splitk(2 * 4 * 16)
-    out_plain = model(x, lv).clone()
     assert out_plain.abs().max() > 1e-2
     assert (out_split - out_plain).abs().max().item() <= 1e-5 * max(1.0, out_plain.abs().max().item())
