@@ -44,13 +44,25 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
 // floating-point sums are fp32 "micro-partials" over one thread's 8 channels x kGnMicro pixels of a globally aligned
 // pixel chunk, whose composition depends on (HW, C) alone.  Two forwards of the same image — alone, inside a batch, on
 // another rank — therefore see identical statistics (the r01 version used fp32 shared-memory atomics and agreed to ~1e-6).
-constexpr int kGnMicro = 8;                               // pixels per fp32 micro-partial
+#ifndef DFOT_GN_MICRO_BF16
+#define DFOT_GN_MICRO_BF16 8
+#endif
+// pixels per fp32 micro-partial (per input type: a bf16 pixel vector is one 16-byte load, an fp32 one two)
+template <typename TX> struct GnMicro { static constexpr int value = 8; };
+template <> struct GnMicro<__nv_bfloat16> { static constexpr int value = DFOT_GN_MICRO_BF16; };
 constexpr float kGnFix = 4294967296.f;                    // 2^32: |partial| < 2^31 is ample for activations
 __device__ __forceinline__ unsigned long long gn_fix(float v) { return (unsigned long long)__float2ll_rn(v * kGnFix); }
 
 // grid (slabs, n_img); a thread owns one 8-channel vector (fixed) and walks the slab's pixels; GPV = groups per vector.
+// (register cap measured on B200, 64 x 16384 x 128: with a bare __launch_bounds__(256) ptxas keeps 48 (f32) / 92 (bf16)
+// registers and serialises the micro-partial's loads — 4.1 / 3.2 TB/s; min-blocks 1 lets it keep all of them in flight with
+// 96 / 64 registers — 6.15 TB/s = 94 % of the copy peak / 4.7 TB/s; caps of 3, 4, 6 blocks: 6.2 / 3.9, 6.0 / 3.2, 4.3 / 1.7.
+// bf16 micro-partials of 16 pixels: 2.4 TB/s, of 4: 4.8 — the bf16 kernel is bound by its unpack + accumulate instructions.)
+#ifndef DFOT_GN_STATS_MIN_BLOCKS
+#define DFOT_GN_STATS_MIN_BLOCKS 1
+#endif
 template <typename TX, int GPV>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, DFOT_GN_STATS_MIN_BLOCKS)
 gn_stats_kernel(const TX* __restrict__ x, double* __restrict__ sums, int64_t HW, int64_t img_stride, int C, int G,
                 int pix_per_block) {
   pdl_trigger();   // programmatic dependent launch: see common.cuh
@@ -62,6 +74,7 @@ gn_stats_kernel(const TX* __restrict__ x, double* __restrict__ sums, int64_t HW,
   __syncthreads();
   const int v = threadIdx.x % vecs, lane_pix = threadIdx.x / vecs, pix_step = kThreads / vecs;
   constexpr int CPV = 8 / GPV;                            // channels of one group inside the vector
+  constexpr int kGnMicro = GnMicro<TX>::value;
   const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;  // multiple of kGnMicro * pix_step (host): chunks are aligned
   const int64_t p1 = min(HW, p0 + pix_per_block);
   unsigned long long as[GPV], aq[GPV];
@@ -511,7 +524,7 @@ extern "C" int dfot_groupnorm_stats_strided(const void* x, int x_dtype, double* 
   // ~8 resident blocks per SM over the whole batch; a block's pixel range is a whole number of aligned micro-partial
   // chunks (kGnMicro pixels per thread-row), so the fp32 micro-partials do not depend on how many blocks share an image
   const int pix_rows = kThreads / vecs;
-  const int64_t chunk = (int64_t)kGnMicro * pix_rows;
+  const int64_t chunk = (int64_t)(x_dtype == DFOT_BF16 ? GnMicro<__nv_bfloat16>::value : GnMicro<float>::value) * pix_rows;
   int64_t slabs = ceil_div(148 * 8, n_img);
   int64_t ppb = ceil_div(ceil_div(HW, slabs), chunk) * chunk;
   slabs = ceil_div(HW, ppb);
