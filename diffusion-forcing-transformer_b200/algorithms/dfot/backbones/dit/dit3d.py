@@ -1,13 +1,14 @@
 """DiT3D backbone on hand-written sm_100a kernels: variant=full (pos_emb_type rope_3d — the shipped dit3d.yaml — learned_1d,
 sinusoidal_1d), the factorized variants (factorized_encoder / factorized_attention, dit3d_factorized_attention.yaml:
 per layer a spatial block over the patches of a frame and a temporal block over the frames of a patch position) and the
-matrix-attention variants (full_matrix_attention / factorized_matrix_attention with matrix_block=matrix,
-dit3d_full_matrix.yaml / dit3d_factorized_matrix.yaml: frames are the attention tokens of a MatrixDiTBlock).
+matrix-attention variants (full_matrix_attention / factorized_matrix_attention, dit3d_full_matrix.yaml /
+dit3d_factorized_matrix.yaml: frames are the attention tokens of a MatrixDiTBlock; matrix_block = matrix | matrix_self |
+matrix_cross, the latter two with token attention inside every frame behind the matrix attention).
 
 Drop-in for the reference class
     algorithms/dfot/backbones/dit/dit3d.py:11-192  (DiT3D),
     algorithms/dfot/backbones/dit/dit_base.py:77-425 (DiTBase), dit_blocks.py:378-542 (blocks),
-    dit_blocks.py:211-350 (MatrixAttention), :549-652 (MatrixDiTBlock)
+    dit_blocks.py:211-350 (MatrixAttention), :549-652 (MatrixDiTBlock), :655-883 (MatrixCrossDiTBlock, MatrixSelfDiTBlock)
 same constructor signature, same ``forward(x, noise_levels, external_cond, external_cond_mask)`` and the
 same ``state_dict()`` keys, so a reference checkpoint loads unchanged.  Parameters are kept in fp32
 under the reference's names; kernel-layout copies (bf16, concatenated modulation weights, padded
@@ -122,6 +123,9 @@ class _Block(nn.Module):                # dit_blocks.py:440-510
             nn.init.xavier_uniform_(lin.weight)
             nn.init.zeros_(lin.bias)
 
+    def adaln_norms(self):              # the block's AdaLN-Zero layers in execution order
+        return [self.norm1] + ([self.norm2] if self.use_mlp else [])
+
 
 class _MatrixAttention(nn.Module):      # dit_blocks.py:215-287 (parameters in the reference's registration order)
     def __init__(self, col_dim: int, row_dim: int, embed_col_dim: int, embed_row_dim: int, use_bias: bool,
@@ -158,6 +162,47 @@ class _MatrixBlock(nn.Module):          # dit_blocks.py:549-652
             for lin in (self.mlp.fc1, self.mlp.fc2):
                 nn.init.xavier_uniform_(lin.weight)
                 nn.init.zeros_(lin.bias)
+
+    def adaln_norms(self):
+        return [self.norm1] + ([self.norm2] if self.use_mlp else [])
+
+
+class _CrossAttention(nn.Module):       # dit_blocks.py:125-160 (q from the tokens, k / v from a second stream)
+    def __init__(self, dim: int):
+        super().__init__()
+        self.q_proj = nn.Linear(dim, dim, bias=True)
+        self.kv_proj = nn.Linear(dim, 2 * dim, bias=True)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _MatrixTokenBlock(nn.Module):     # dit_blocks.py:655-769 (MatrixCrossDiTBlock), :772-883 (MatrixSelfDiTBlock)
+    """Matrix attention over the frames (attn1: never a bias or a fixed u — the two blocks drop those keyword arguments)
+    followed by token attention inside every frame (attn2: self-attention behind a second AdaLN, or cross-attention of the
+    modulated tokens to attn1's output).  Modules in the reference's registration order."""
+
+    def __init__(self, col_dim: int, dim: int, embed_col_dim: int, mlp_ratio: Optional[float], cross: bool):
+        super().__init__()
+        self.cross = cross
+        self.norm1 = _AdaLN(dim, 3)
+        self.attn1 = _MatrixAttention(col_dim, dim, embed_col_dim, dim, False, None)
+        if cross:
+            self.attn2 = _CrossAttention(dim)
+            lins = [self.attn2.q_proj, self.attn2.kv_proj, self.attn2.proj]
+        else:
+            self.norm2 = _AdaLN(dim, 3)
+            self.attn2 = _Attention(dim)
+            lins = [self.attn2.qkv, self.attn2.proj]
+        self.use_mlp = mlp_ratio is not None                  # dit_blocks.py:702, :819 (not "> 0" as in DiTBlock)
+        if self.use_mlp:
+            self.norm3 = _AdaLN(dim, 3)
+            self.mlp = _Mlp(dim, int(dim * mlp_ratio))
+            lins += [self.mlp.fc1, self.mlp.fc2]
+        for lin in lins:
+            nn.init.xavier_uniform_(lin.weight)
+            nn.init.zeros_(lin.bias)
+
+    def adaln_norms(self):
+        return [self.norm1] + ([] if self.cross else [self.norm2]) + ([self.norm3] if self.use_mlp else [])
 
 
 class _FinalLayer(nn.Module):           # dit_blocks.py:513-542
@@ -213,8 +258,12 @@ class _DiTBase(nn.Module):
         super().__init__()
         if matrix is not None:                             # dit_base.py:254-258 (sinusoidal_2d), :159-222
             self.pos_emb = _FixedTable(dim, tuple(grid))
-            mk = lambda: _MatrixBlock(grid[0] * grid[1], dim, matrix["embed_col_dim"], mlp_ratio, matrix["use_bias"],
-                                      matrix["fixed_u"])
+            if matrix["block"] == "matrix":
+                mk = lambda: _MatrixBlock(grid[0] * grid[1], dim, matrix["embed_col_dim"], mlp_ratio, matrix["use_bias"],
+                                          matrix["fixed_u"])
+            else:                                          # dit_base.py:27-31 `matrix_blocks`
+                mk = lambda: _MatrixTokenBlock(grid[0] * grid[1], dim, matrix["embed_col_dim"], mlp_ratio,
+                                               matrix["block"] == "matrix_cross")
             if matrix["full"]:
                 self.blocks = nn.ModuleList([mk() for _ in range(depth)])
             else:
@@ -334,7 +383,7 @@ class DiT3D(nn.Module):
         matrix = None
         if self.matrix:
             matrix = dict(full=self.variant == "full_matrix_attention", embed_col_dim=self.matrix_cols,
-                          use_bias=bool(cfg.use_bias), fixed_u=cfg.get("fixed_u", None))
+                          use_bias=bool(cfg.use_bias), fixed_u=cfg.get("fixed_u", None), block=self.matrix_block)
         self.dit_base = _DiTBase(D, self.depth, cfg.get("spatial_mlp_ratio", None), self.patch_size ** 2 * C,
                                  self.pos_emb_type, max_tokens * self.num_patches, factorized=self.factorized,
                                  mlp_ratio=cfg.get("mlp_ratio", 4.0), grid=(self.num_patches_h, self.num_patches_w),
@@ -357,9 +406,8 @@ class DiT3D(nn.Module):
         (embed_col_dim == num_col_heads — every shipped matrix configuration has both = 1), so a head's feature is one
         [1, head_row_dim] row and `flatten_matrix_rope` / `matrix_multi_token` do not change the computation (checked
         against the executed reference, oracle/make_goldens_matrix.py)."""
-        if cfg.get("matrix_block") != "matrix":
-            raise NotImplementedError(f"matrix_block={cfg.get('matrix_block')!r}: only MatrixDiTBlock ('matrix', the shipped "
-                                      "configurations) is built, not the matrix_self / matrix_cross ablations")
+        self.matrix_block = cfg.get("matrix_block")
+        assert self.matrix_block in ("matrix", "matrix_self", "matrix_cross"), f"Unknown matrix block {self.matrix_block}"
         for k in ("embed_col_dim", "embed_row_dim", "num_col_heads", "num_row_heads", "spatial_mlp_ratio", "use_bias"):
             assert cfg.get(k) is not None, f"{k} must be specified for matrix attention"
         assert cfg.embed_row_dim % cfg.num_row_heads == 0, "embed_row_dim must be divisible by num_row_heads"
@@ -376,7 +424,7 @@ class DiT3D(nn.Module):
         if self.matrix_head_dim not in (64, 72, 128):
             raise NotImplementedError(f"matrix head dim {self.matrix_head_dim} unsupported by the attention kernel "
                                       "(64, 72, 128)")
-        if cfg.use_bias and self.matrix_cols != 1:
+        if cfg.use_bias and self.matrix_block == "matrix" and self.matrix_cols != 1:
             raise NotImplementedError("matrix attention: use_bias with embed_col_dim > 1 is not built (the bias row "
                                       "depends on the column head)")
 
@@ -400,13 +448,14 @@ class DiT3D(nn.Module):
 
     def _ordered_blocks(self):
         """Blocks in execution order with their kind: "full" (all tokens of a row), or per layer "spatial" then "temporal"."""
+        mkind = self.matrix_block if self.matrix else None     # "matrix" | "matrix_self" | "matrix_cross"
         if self.variant == "full_matrix_attention":
-            return [("matrix", b) for b in self.dit_base.blocks]
+            return [(mkind, b) for b in self.dit_base.blocks]
         if not (self.factorized or self.matrix):
             return [("full", b) for b in self.dit_base.blocks]
         out = []
         for sb, tb in zip(self.dit_base.blocks, self.dit_base.temporal_blocks):
-            out += [("spatial", sb), ("matrix" if self.matrix else "temporal", tb)]
+            out += [("spatial", sb), (mkind if self.matrix else "temporal", tb)]
         return out
 
     # ------------------------------------------------------------------ weight packing
@@ -445,11 +494,9 @@ class DiT3D(nn.Module):
         P["pe_w"], P["pe_b"] = bf(wp), f32(self.patch_embedder.proj.bias)
         mods_w, mods_b = [], []
         for _, blk in self._ordered_blocks():
-            mods_w.append(blk.norm1.modulation[-1].weight)
-            mods_b.append(blk.norm1.modulation[-1].bias)
-            if blk.use_mlp:
-                mods_w.append(blk.norm2.modulation[-1].weight)
-                mods_b.append(blk.norm2.modulation[-1].bias)
+            for norm in blk.adaln_norms():
+                mods_w.append(norm.modulation[-1].weight)
+                mods_b.append(norm.modulation[-1].bias)
         fl = self.dit_base.final_layer
         mods_w.append(fl.norm_final.modulation[-1].weight)
         mods_b.append(fl.norm_final.modulation[-1].bias)
@@ -469,13 +516,13 @@ class DiT3D(nn.Module):
             qs = torch.ones((3 * D, 1), device=dev)
             qs[:D] = LOG2E / math.sqrt(max(self.head_dim, 1))
         for kind, blk in self._ordered_blocks():
-            if kind == "matrix":
-                P["blocks"].append(self._pack_matrix_block(blk, bf, f32, dev))
+            if kind.startswith("matrix"):
+                P["blocks"].append(self._pack_matrix_block(blk, kind, bf, f32, dev))
                 continue
             qw, qb = blk.attn.qkv.weight.detach().float(), blk.attn.qkv.bias.detach().float()
             if not self.use_rope:
                 qw, qb = qw * qs, qb * qs[:, 0]
-            d = dict(kind=kind, qkv_w=bf(qw), qkv_b=f32(qb), proj_w=bf(blk.attn.proj.weight),
+            d = dict(kind=kind, n_norms=len(blk.adaln_norms()), qkv_w=bf(qw), qkv_b=f32(qb), proj_w=bf(blk.attn.proj.weight),
                      proj_b=f32(blk.attn.proj.bias))
             if blk.use_mlp:
                 d.update(fc1_w=bf(blk.mlp.fc1.weight), fc1_b=f32(blk.mlp.fc1.bias), fc2_w=bf(blk.mlp.fc2.weight),
@@ -494,11 +541,13 @@ class DiT3D(nn.Module):
         self._packed, self._packed_key = P, key
         return P
 
-    def _pack_matrix_block(self, blk, bf, f32, dev):
+    def _pack_matrix_block(self, blk, kind, bf, f32, dev):
         """MatrixDiTBlock weights in kernel layout: the v factors as [N, K] bf16 GEMM weights (W = v^T), the u factors as
         f32 tables of the two patch kernels.  Without the temporal RoPE the QKV epilogue is a plain bf16 store, so the
-        softmax scale (x log2 e) is folded into the q columns (as for the absolute-position DiT blocks)."""
-        a, E, Mc, Pn = blk.attn, self.hidden_size, self.matrix_cols, self.num_patches
+        softmax scale (x log2 e) is folded into the q columns (as for the absolute-position DiT blocks).  The token
+        attention of a matrix_self / matrix_cross block (attn2, never rotated) gets the same folding; a cross block's
+        q_proj / kv_proj stay two GEMMs (different inputs) that write the column slabs of one [M, 3D] q|k|v buffer."""
+        a, E, Mc, Pn = blk.attn if kind == "matrix" else blk.attn1, self.hidden_size, self.matrix_cols, self.num_patches
         qw = a.qkv_v.detach().float().t().contiguous()                 # [3E, D]
         qb = a.qkv_bias.detach().float()[0].clone() if hasattr(a, "qkv_bias") else torch.zeros((3 * E,), device=dev)
         if not self.matrix_rope:
@@ -506,10 +555,21 @@ class DiT3D(nn.Module):
             qw[:E] *= scale
             qb[:E] *= scale
         eye = torch.eye(Pn, device=dev) if a.fixed_u == "identity" else None
-        d = dict(kind="matrix", qkv_w=bf(qw), qkv_b=f32(qb), proj_w=bf(a.proj_v.detach().float().t().contiguous()),
+        d = dict(kind=kind, n_norms=len(blk.adaln_norms()), qkv_w=bf(qw), qkv_b=f32(qb),
+                 proj_w=bf(a.proj_v.detach().float().t().contiguous()),
                  qkv_u=f32(eye if eye is not None else a.qkv_u).reshape(Pn, Mc).contiguous(),
                  proj_u=f32(eye if eye is not None else a.proj_u).reshape(Mc, Pn).contiguous(),
                  proj_bias=f32(a.proj_bias) if hasattr(a, "proj_bias") else None)
+        if kind != "matrix":
+            t, ts = blk.attn2, LOG2E / math.sqrt(self.matrix_head_dim)
+            if kind == "matrix_cross":
+                d.update(q2_w=bf(t.q_proj.weight.detach().float() * ts), q2_b=f32(t.q_proj.bias.detach().float() * ts),
+                         kv2_w=bf(t.kv_proj.weight), kv2_b=f32(t.kv_proj.bias))
+            else:
+                qs2 = torch.ones((3 * E, 1), device=dev)
+                qs2[:E] = ts
+                d.update(qkv2_w=bf(t.qkv.weight.detach().float() * qs2), qkv2_b=f32(t.qkv.bias.detach().float() * qs2[:, 0]))
+            d.update(proj2_w=bf(t.proj.weight), proj2_b=f32(t.proj.bias))
         if blk.use_mlp:
             d.update(fc1_w=bf(blk.mlp.fc1.weight), fc1_b=f32(blk.mlp.fc1.bias), fc2_w=bf(blk.mlp.fc2.weight),
                      fc2_b=f32(blk.mlp.fc2.bias))
@@ -523,7 +583,7 @@ class DiT3D(nn.Module):
         D, C, p = self.hidden_size, self.x_shape[0], self.patch_size
         M, RT = R * T * self.num_patches, R * T
         blocks = self._ordered_blocks()
-        n_mod = sum(6 if b.use_mlp else 3 for _, b in blocks) + 2
+        n_mod = sum(3 * len(b.adaln_norms()) for _, b in blocks) + 2
         e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
         bf, f32 = torch.bfloat16, torch.float32
         ws = dict(feat=e((RT, 256), bf), e1=e((RT, D), bf), emb=e((RT, D), f32), cact=e((RT, D), bf),
@@ -543,6 +603,8 @@ class DiT3D(nn.Module):
         if self.matrix:      # frame-level rows (row, column head, frame) of the matrix attention
             Mf = R * self.matrix_cols * T
             ws.update(ms=e((Mf, D), bf), mqkv=e((Mf, 3 * D), bf), matt=e((Mf, D), bf), mz=e((Mf, D), f32))
+            if self.matrix_block == "matrix_cross":        # attn1's output, the k / v source of attn2
+                ws.update(x1=e((M, D), f32), x1_16=e((M, D), bf))
         if not self.use_rope:
             ws["pos_rows"], ws["pos_key"] = e((M, D), f32), None     # the table repeated per row (filled lazily)
         if self.external_cond_embedding is not None:
@@ -699,7 +761,7 @@ class DiT3D(nn.Module):
         xa, xb = ws["x"], ws["y"]
         first_temporal = True
         for bw in Pk["blocks"]:
-            kind, ncol = bw["kind"], (6 if "fc1_w" in bw else 3) * D
+            kind, ncol = bw["kind"], 3 * bw["n_norms"] * D
             xs, bmod, bld, bcol, tpf, n_seq, seq_len = xa, mod, ldm, col, Pn, R, Ntok
             if kind == "spatial":            # attention inside a frame: R*T sequences of P tokens, same token order
                 n_seq, seq_len = RT, Pn
@@ -713,6 +775,12 @@ class DiT3D(nn.Module):
                 bmod, bld, bcol, tpf, n_seq, seq_len = ws["mod_tok"], ws["mod_tok"].shape[1], 0, 1, R * Pn, T
             if kind == "matrix":
                 self._matrix_attention(bw, Pk, ws, xs, xb, mod, ldm, col, R, T)
+            elif kind == "matrix_self":
+                self._matrix_attention(bw, Pk, ws, xs, xb, mod, ldm, col, R, T)
+                bcol += 3 * D
+                self._frame_self_attention(bw, ws, xs, xb, mod, ldm, bcol, RT)
+            elif kind == "matrix_cross":
+                self._matrix_cross_attention(bw, Pk, ws, xs, xb, mod, ldm, col, R, T)
             else:
                 self._token_attention(bw, Pk, ws, xs, xb, bmod, bld, bcol, tpf, n_seq, seq_len, Ntok, q_scale)
             if "fc1_w" in bw:
@@ -807,6 +875,36 @@ class DiT3D(nn.Module):
         proj_bias), attention A over the T frames of a row (see the module docstring)."""
         D, Pn, Mc = self.hidden_size, self.num_patches, self.matrix_cols
         ops.adaln_layernorm(xs, mod, col, col + D, Pn, y_f32=xb)
+        self._matrix_core(bw, Pk, ws, xb, R, T)
+        ops.patch_expand_gate_resid(xs, xb, ws["mz"], bw["proj_u"], bw["proj_bias"], mod[:, col + 2 * D:], ldm, R, T, Pn, Mc)
+
+    def _frame_self_attention(self, bw, ws, xs, xb, mod, ldm, col, RT: int):
+        """dit_blocks.py:874-877, second half of a MatrixSelfDiTBlock: x <- y + gate * proj(attention(qkv(y))) with the Pn
+        tokens of a frame as one sequence, y = modulate(LN(x)) through norm2, no rotation."""
+        D, Pn = self.hidden_size, self.num_patches
+        ops.adaln_layernorm(xs, mod, col, col + D, Pn, y_f32=xb, y_bf16=ws["y16"])
+        ops.gemm_bf16(ws["y16"], bw["qkv2_w"], ws["qkv"], ops.EPI_BF16, bias=bw["qkv2_b"])
+        ops.attention(ws["qkv"], ws["att"], RT, Pn, self.matrix_heads, self.matrix_head_dim)
+        ops.gemm_bf16(ws["att"], bw["proj2_w"], xs, ops.EPI_GATE_RESID_F32, bias=bw["proj2_b"], resid=xb,
+                      gate=mod[:, col + 2 * D:], ld_gate=ldm, tokens_per_frame=Pn)
+
+    def _matrix_cross_attention(self, bw, Pk, ws, xs, xb, mod, ldm, col, R: int, T: int):
+        """dit_blocks.py:752-763, first half of a MatrixCrossDiTBlock: x1 = matrix attention of y (bare: no gate, no
+        residual), then per frame x <- y + gate * proj(attention(q(y), k(x1), v(x1)))."""
+        D, Pn, Mc = self.hidden_size, self.num_patches, self.matrix_cols
+        ops.adaln_layernorm(xs, mod, col, col + D, Pn, y_f32=xb, y_bf16=ws["y16"])
+        self._matrix_core(bw, Pk, ws, xb, R, T)
+        ops.patch_expand_gate_resid(ws["x1"], None, ws["mz"], bw["proj_u"], bw["proj_bias"], None, 0, R, T, Pn, Mc)
+        ops.cast_bf16(ws["x1"], ws["x1_16"])
+        ops.gemm_bf16(ws["y16"], bw["q2_w"], ws["qkv"][:, :D], ops.EPI_BF16, bias=bw["q2_b"])
+        ops.gemm_bf16(ws["x1_16"], bw["kv2_w"], ws["qkv"][:, D:], ops.EPI_BF16, bias=bw["kv2_b"])
+        ops.attention(ws["qkv"], ws["att"], R * T, Pn, self.matrix_heads, self.matrix_head_dim)
+        ops.gemm_bf16(ws["att"], bw["proj2_w"], xs, ops.EPI_GATE_RESID_F32, bias=bw["proj2_b"], resid=xb,
+                      gate=mod[:, col + 2 * D:], ld_gate=ldm, tokens_per_frame=Pn)
+
+    def _matrix_core(self, bw, Pk, ws, xb, R: int, T: int):
+        """ws["mz"] <- A(u^T y v) proj_v for y = xb: MatrixAttention up to its `proj_u` factor (dit_blocks.py:289-344)."""
+        D, Pn, Mc = self.hidden_size, self.num_patches, self.matrix_cols
         ops.patch_mix_bf16(xb, bw["qkv_u"], ws["ms"], R, T, Pn, Mc)
         if self.matrix_rope:
             ops.gemm_bf16(ws["ms"], bw["qkv_w"], ws["mqkv"], ops.EPI_QKV_ROPE_BF16, bias=bw["qkv_b"], rope_cs=Pk["mrope"],
@@ -816,4 +914,3 @@ class DiT3D(nn.Module):
             ops.gemm_bf16(ws["ms"], bw["qkv_w"], ws["mqkv"], ops.EPI_BF16, bias=bw["qkv_b"])
         ops.attention(ws["mqkv"], ws["matt"], R * Mc, T, self.matrix_heads, self.matrix_head_dim)
         ops.gemm_bf16(ws["matt"], bw["proj_w"], ws["mz"], ops.EPI_F32)
-        ops.patch_expand_gate_resid(xs, xb, ws["mz"], bw["proj_u"], bw["proj_bias"], mod[:, col + 2 * D:], ldm, R, T, Pn, Mc)

@@ -165,6 +165,7 @@ patch_mix_bf16_kernel(const float* __restrict__ y, const float* __restrict__ u, 
 
 // The way back (the `proj_u` factor of the output projection, the AdaLN-Zero gate and the block's residual in one pass):
 //   x[((r*L + l)*P + n), d] = y[same] + gate[(r*L + l)*ld_gate + d] * (sum_c pu[c*P + n] * z[((r*Mc + c)*L + l), d] + pb[n*D + d])
+// (y == NULL: no residual, gate == NULL: gate 1 — the bare attention output a MatrixCrossDiTBlock attends to.)
 // One block per (frame, 32-patch chunk); a thread owns one float4 column group (two when D > 1024): the frame's gate and —
 // with one column head, every shipped configuration — its z row stay in registers, the patch rows stream through four at a
 // time.  No index arithmetic per element.
@@ -178,7 +179,8 @@ patch_expand_gate_resid_kernel(float* __restrict__ x, const float* __restrict__ 
   const int frame = blockIdx.x, r = frame / L, l = frame % L;
   const int n_begin = blockIdx.y * 32, n_end = min(P, n_begin + 32);
   for (int d = threadIdx.x * 4; d < D; d += 1024) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gate + (int64_t)frame * ld_gate + d));
+    const float4 g = gate != nullptr ? __ldg(reinterpret_cast<const float4*>(gate + (int64_t)frame * ld_gate + d))
+                                     : make_float4(1.f, 1.f, 1.f, 1.f);
     const float* zf = z + ((int64_t)r * Mc * L + l) * D + d;          // column head c: + c * L * D
     float4 z0 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ONE_COL) z0 = __ldg(reinterpret_cast<const float4*>(zf));
@@ -187,7 +189,7 @@ patch_expand_gate_resid_kernel(float* __restrict__ x, const float* __restrict__ 
       uint4 yv[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        yv[k] = n0 + k < n_end ? ld_stream_u4(y + (row0 + n0 + k) * D + d) : make_uint4(0u, 0u, 0u, 0u);
+        yv[k] = (y != nullptr && n0 + k < n_end) ? ld_stream_u4(y + (row0 + n0 + k) * D + d) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int n = n0 + k;
@@ -306,9 +308,9 @@ extern "C" int dfot_patch_mix_bf16(const float* y, const float* u, void* out_bf1
 extern "C" int dfot_patch_expand_gate_resid(float* x, const float* y, const float* z, const float* pu, const float* pb,
                                             const float* gate, int64_t ld_gate, int64_t R, int64_t L, int64_t P,
                                             int64_t Mc, int64_t D, void* stream) {
-  DFOT_REQUIRE(x && y && z && pu && gate && x != y && R > 0 && L > 0 && P > 0 && Mc > 0 && D > 0, DFOT_ERR_INVALID_ARG,
+  DFOT_REQUIRE(x && z && pu && x != y && R > 0 && L > 0 && P > 0 && Mc > 0 && D > 0, DFOT_ERR_INVALID_ARG,
                "patch_expand_gate_resid: bad arguments (x must not alias y)");
-  DFOT_REQUIRE(D % 4 == 0 && ld_gate % 4 == 0 && ld_gate >= D, DFOT_ERR_INVALID_ARG,
+  DFOT_REQUIRE(D % 4 == 0 && (gate == nullptr || (ld_gate % 4 == 0 && ld_gate >= D)), DFOT_ERR_INVALID_ARG,
                "patch_expand_gate_resid: D and ld_gate must be multiples of 4, ld_gate >= D");
   DFOT_REQUIRE(((uintptr_t)x | (uintptr_t)y | (uintptr_t)z | (uintptr_t)gate | (uintptr_t)pb) % 16 == 0, DFOT_ERR_INVALID_ARG,
                "patch_expand_gate_resid: buffers must be 16-byte aligned");

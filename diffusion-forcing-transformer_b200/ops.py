@@ -300,20 +300,21 @@ def patch_mix_bf16(y, u, out, R, L, P, Mc):
 
 
 def patch_expand_gate_resid(x, y, z, pu, pb, gate, ld_gate, R, L, P, Mc):
-    """Matrix attention, `proj_u` factor + gate + residual: x = y + gate[frame] * (pu^T z + pb); y, x [R*L*P, D] f32,
-    z [R*Mc*L, D] f32, pu [Mc, P] f32, pb [P, D] f32 or None, gate a view into the per-frame modulation matrix."""
-    for t, name in ((x, "x"), (y, "y"), (z, "z"), (pu, "pu")):
+    """Matrix attention, `proj_u` factor + gate + residual: x = y + gate[frame] * (pu^T z + pb); x [R*L*P, D] f32,
+    z [R*Mc*L, D] f32, pu [Mc, P] f32, pb [P, D] f32 or None, gate a view into the per-frame modulation matrix;
+    y None: no residual, gate None: gate 1."""
+    for t, name in ((x, "x"), (z, "z"), (pu, "pu")) + (((y, "y"),) if y is not None else ()):
         _need(t, torch.float32, name)
     if pb is not None:
         _need(pb, torch.float32, "pb")
-    if gate.dtype != torch.float32 or not gate.is_cuda:
+    if gate is not None and (gate.dtype != torch.float32 or not gate.is_cuda):
         raise RuntimeError("dfot_b200: `gate` must be CUDA f32")
-    D = y.shape[-1]
-    if (y.numel() != R * L * P * D or x.numel() != y.numel() or z.numel() != R * Mc * L * D or pu.numel() != Mc * P
-            or (pb is not None and pb.numel() != P * D)):
+    D = x.shape[-1]
+    if (x.numel() != R * L * P * D or (y is not None and y.numel() != x.numel()) or z.numel() != R * Mc * L * D
+            or pu.numel() != Mc * P or (pb is not None and pb.numel() != P * D)):
         raise RuntimeError("dfot_b200: patch_expand_gate_resid shape mismatch")
-    rc = _abi.lib().dfot_patch_expand_gate_resid(x.data_ptr(), y.data_ptr(), z.data_ptr(), pu.data_ptr(), _ptr(pb),
-                                                 gate.data_ptr(), ld_gate, R, L, P, Mc, D, _stream())
+    rc = _abi.lib().dfot_patch_expand_gate_resid(x.data_ptr(), _ptr(y), z.data_ptr(), pu.data_ptr(), _ptr(pb), _ptr(gate),
+                                                 ld_gate, R, L, P, Mc, D, _stream())
     _abi.check(rc, "patch_expand_gate_resid")
 
 

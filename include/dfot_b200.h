@@ -254,7 +254,8 @@ DFOT_API int dfot_cast_bf16(const float* in, void* out_bf16, int64_t n, void* st
  *   dfot_patch_expand_gate_resid:  x[((r*L + l)*P + n), d] = y[same] + gate[(r*L + l)*ld_gate + d] *
  *           (sum_c pu[c*P + n] * z[((r*Mc + c)*L + l), d] + pb[n*D + d])                                 f32
  *       (replaces the `proj_u` contraction + proj_bias, dit_blocks.py:345-347, and the gated residual :640-644;
- *        z = attention output through proj_v; pb may be NULL; x must not alias y).  D % 4 == 0.
+ *        z = attention output through proj_v; pb may be NULL; y NULL = no residual and gate NULL = gate 1 (the bare attention
+ *        output a MatrixCrossDiTBlock attends to, :752-761); x must not alias y).  D % 4 == 0.
  */
 DFOT_API int dfot_patch_mix_bf16(const float* y, const float* u, void* out_bf16, int64_t R, int64_t L, int64_t P,
                         int64_t Mc, int64_t D, void* stream);

@@ -110,7 +110,7 @@ class DiT3DOracle:
         self.factorized = self.variant in ("factorized_encoder", "factorized_attention")
         assert self.variant == "full" or self.factorized or self.matrix
         if self.matrix:
-            assert self.pos_emb_type == "sinusoidal_2d" and cfg.get("matrix_block") == "matrix"
+            assert self.pos_emb_type == "sinusoidal_2d" and cfg.get("matrix_block") in ("matrix", "matrix_self", "matrix_cross")
         else:
             assert self.pos_emb_type in (("learned_1d", "sinusoidal_1d", "sinusoidal_factorized") if self.factorized
                                          else ("rope_3d", "learned_1d", "sinusoidal_1d"))
@@ -217,19 +217,49 @@ class DiT3DOracle:
             o = o + sd[pre + ".proj_bias"]
         return o
 
+    def token_attention(self, y: torch.Tensor, pre: str, heads: int, kv_src: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """dit_blocks.py:81-123 (Attention) / :162-208 (CrossAttention: q from y, k / v from kv_src) without RoPE, before the
+        output projection's residual: returns proj(softmax(q k^T / sqrt(d)) v)."""
+        sd = self.sd
+        B, N, D = y.shape
+        dh = D // heads
+        if kv_src is None:
+            q, k, v = _linear(y, sd, pre + ".qkv").reshape(B, N, 3, heads, dh).permute(2, 0, 3, 1, 4).unbind(0)
+        else:
+            q = _linear(y, sd, pre + ".q_proj").reshape(B, N, heads, dh).permute(0, 2, 1, 3)
+            k, v = _linear(kv_src, sd, pre + ".kv_proj").reshape(B, N, 2, heads, dh).permute(2, 0, 3, 1, 4).unbind(0)
+        w = torch.softmax(q @ k.transpose(-2, -1) * (1 / math.sqrt(dh)), dim=-1)
+        return _linear((w @ v).transpose(1, 2).reshape(B, N, D), sd, pre + ".proj")
+
     def block(self, h, c_act, i: int, group: str, n_frames: int = 0):
         """dit_blocks.py:488-510 (the MLP exists iff the block was built with a positive ratio); :626-652 for a
-        MatrixDiTBlock (same block around MatrixAttention over the n_frames frames of the row)."""
+        MatrixDiTBlock (same block around MatrixAttention over the n_frames frames of the row); :734-769 MatrixCrossDiTBlock
+        (per frame, the modulated tokens attend to the matrix attention's output); :852-883 MatrixSelfDiTBlock (matrix
+        attention, then self-attention inside every frame, then the MLP)."""
         sd, pre = self.sd, f"dit_base.{group}.{i}"
         y, gate = _adaln(h, c_act, sd, pre + ".norm1", 3)
-        if pre + ".attn.qkv_v" in sd:
-            B, N, D = y.shape
+        B, N, D = y.shape
+        mlp_norm = ".norm2"
+        if pre + ".attn1.qkv_v" in sd:                               # matrix_self / matrix_cross (attn1 never has a bias)
+            T, P = n_frames, N // n_frames
+            x1 = self.matrix_attention(y.reshape(B, T, P, D), pre + ".attn1").reshape(B, N, D)
+            mlp_norm = ".norm3"
+            if pre + ".attn2.q_proj.weight" in sd:                   # cross: q from y, k / v from x1, inside every frame
+                att = self.token_attention(y.reshape(B * T, P, D), pre + ".attn2", self.row_heads,
+                                           x1.reshape(B * T, P, D)).reshape(B, N, D)
+                h = y + gate * att
+            else:                                                    # self: two gated halves
+                h = y + gate * x1
+                y2, gate2 = _adaln(h, c_act, sd, pre + ".norm2", 3)
+                att = self.token_attention(y2.reshape(B * T, P, D), pre + ".attn2", self.row_heads).reshape(B, N, D)
+                h = y2 + gate2 * att
+        elif pre + ".attn.qkv_v" in sd:
             att = self.matrix_attention(y.reshape(B, n_frames, N // n_frames, D), pre + ".attn").reshape(B, N, D)
+            h = y + gate * att
         else:
-            att = self.attention(y, i, group)
-        h = y + gate * att                                       # residual base is the modulated tensor (Q1)
+            h = y + gate * self.attention(y, i, group)               # residual base is the modulated tensor (Q1)
         if pre + ".mlp.fc1.weight" in sd:
-            z, gate2 = _adaln(h, c_act, sd, pre + ".norm2", 3)
+            z, gate2 = _adaln(h, c_act, sd, pre + mlp_norm, 3)
             m = _linear(F.gelu(_linear(z, sd, pre + ".mlp.fc1"), approximate="tanh"), sd, pre + ".mlp.fc2")
             h = z + gate2 * m
         return h

@@ -42,6 +42,12 @@ def cases():
                                             "backbone.hidden_size": 64}),
         "matrix_factorized_bias": matrix_case("factorized_matrix_attention", "matrix_factorized_bias", 1, None,
                                               **{"backbone.use_bias": True, "backbone.use_temporal_rope": False}),
+        # the other two entries of dit_base.py:27-31 `matrix_blocks`
+        "matrix_self_factorized": matrix_case("factorized_matrix_attention", "matrix_self", 1, None,
+                                              **{"backbone.matrix_block": "matrix_self"}),
+        "matrix_cross_full": matrix_case("full_matrix_attention", "matrix_cross", 1, vanilla,
+                                         **{"backbone.matrix_block": "matrix_cross", "backbone.hidden_size": 64,
+                                            "backbone.embed_col_dim": 2, "backbone.num_col_heads": 2}),
     }
 
 

@@ -97,12 +97,15 @@ def patch_mix_bf16(y, u, out, R, L, P, Mc):
 
 
 def patch_expand_gate_resid(x, y, z, pu, pb, gate, ld_gate, R, L, P, Mc):
-    D = y.shape[-1]
+    D = x.shape[-1]
     s = torch.einsum("cn,rcld->rlnd", pu.reshape(Mc, P).float(), z.reshape(R, Mc, L, D).float())
     if pb is not None:
         s = s + pb.reshape(1, 1, P, D)
-    g = gate[:, :D].reshape(R, L, 1, D)
-    x.copy_((y.reshape(R, L, P, D) + g * s).reshape(x.shape))
+    if gate is not None:
+        s = gate[:, :D].reshape(R, L, 1, D) * s
+    if y is not None:
+        s = y.reshape(R, L, P, D) + s
+    x.copy_(s.reshape(x.shape))
 
 
 def gemm_bf16_splitk(a, w, parts, splits, M=None):

@@ -301,6 +301,11 @@ def test_patch_mix_and_expand(R, L, P, Mc, D):
             s = s + bias.double()
         ref = y.reshape(R, L, P, D).double() + mod[:, 2 * D:3 * D].reshape(R, L, 1, D).double() * s
         assert (x.cpu().double() - ref.reshape(-1, D)).abs().max().item() < 1e-4
+    # bare form (a MatrixCrossDiTBlock's attn1 output): no residual, gate 1
+    x = torch.full((R * L * P, D), float("nan"), device=DEV)
+    ops.patch_expand_gate_resid(x, None, z.to(DEV), pu.to(DEV), pb.to(DEV), None, 0, R, L, P, Mc)
+    ref = torch.einsum("cn,rcld->rlnd", pu.double(), z.reshape(R, Mc, L, D).double()) + pb.double()
+    assert (x.cpu().double() - ref.reshape(-1, D)).abs().max().item() < 1e-4
 
 
 # ---------------------------------------------------------------- split-K GEMM + its fused consumer (latency regime)
