@@ -402,27 +402,34 @@ class DiT3D(nn.Module):
         self._graphs = {}
 
     def _check_matrix_cfg(self, cfg) -> None:
-        """dit_base.py:129-149 (the reference's own assertions) + what the kernels cover: one row per column head
-        (embed_col_dim == num_col_heads — every shipped matrix configuration has both = 1), so a head's feature is one
+        """dit_base.py:129-149 (the reference's own assertions) + what the kernels cover.  With one row per column head
+        (embed_col_dim == num_col_heads — every shipped matrix configuration has both = 1) a head's feature is one
         [1, head_row_dim] row and `flatten_matrix_rope` / `matrix_multi_token` do not change the computation (checked
-        against the executed reference, oracle/make_goldens_matrix.py)."""
+        against the executed reference, oracle/make_goldens_matrix.py).  With n = embed_col_dim / num_col_heads > 1 rows per
+        column head (dit_blocks.py:312-340): `matrix_multi_token` makes every one of the embed_col_dim rows its own sequence
+        (scale head_row_dim^-1/2) — the same kernel sequence as n = 1; otherwise a head's feature is the flattened
+        [n, head_row_dim] block (scale (n * head_row_dim)^-1/2), reached by regrouping the frame-level q | k | v rows
+        (_matrix_core), rotated per row or — `flatten_matrix_rope` — as one n * head_row_dim wide vector."""
         self.matrix_block = cfg.get("matrix_block")
         assert self.matrix_block in ("matrix", "matrix_self", "matrix_cross"), f"Unknown matrix block {self.matrix_block}"
         for k in ("embed_col_dim", "embed_row_dim", "num_col_heads", "num_row_heads", "spatial_mlp_ratio", "use_bias"):
             assert cfg.get(k) is not None, f"{k} must be specified for matrix attention"
         assert cfg.embed_row_dim % cfg.num_row_heads == 0, "embed_row_dim must be divisible by num_row_heads"
         assert cfg.embed_col_dim % cfg.num_col_heads == 0, "embed_col_dim must be divisible by num_col_heads"
-        if cfg.embed_col_dim != cfg.num_col_heads:
-            raise NotImplementedError("matrix attention with more than one row per column head "
-                                      "(embed_col_dim > num_col_heads) is not built")
         if cfg.get("flatten_matrix_rope") and cfg.get("matrix_multi_token"):
             raise AssertionError("flatten_rope and multi_token cannot be used together.")      # dit_blocks.py:253
         self.matrix_cols = cfg.embed_col_dim
         self.matrix_heads = cfg.num_row_heads
         self.matrix_head_dim = cfg.embed_row_dim // cfg.num_row_heads
         self.matrix_rope = bool(cfg.get("use_temporal_rope", False))
-        if self.matrix_head_dim not in (64, 72, 128):
-            raise NotImplementedError(f"matrix head dim {self.matrix_head_dim} unsupported by the attention kernel "
+        n = cfg.embed_col_dim // cfg.num_col_heads
+        # rows of a column head that one attention head's feature spans (1: every row is a sequence of its own)
+        self.matrix_group = 1 if cfg.get("matrix_multi_token") else n
+        self.matrix_flatten_rope = bool(cfg.get("flatten_matrix_rope")) and self.matrix_group > 1
+        self.matrix_feature_dim = self.matrix_group * self.matrix_head_dim      # the attention kernel's head_dim
+        if self.matrix_feature_dim not in (64, 72, 128) or self.matrix_head_dim % 8:
+            raise NotImplementedError(f"matrix attention feature width {self.matrix_feature_dim} (rows per head x "
+                                      f"head_row_dim {self.matrix_head_dim}) unsupported by the attention kernel "
                                       "(64, 72, 128)")
         if cfg.use_bias and self.matrix_block == "matrix" and self.matrix_cols != 1:
             raise NotImplementedError("matrix attention: use_bias with embed_col_dim > 1 is not built (the bias row "
@@ -537,7 +544,8 @@ class DiT3D(nn.Module):
         if self.use_rope:
             P["rope"] = rope_cos_sin_table(self.head_dim, (self.max_tokens, self.num_patches_h, self.num_patches_w)).to(dev)
         if self.matrix and self.matrix_rope:
-            P["mrope"] = rope_1d_cos_sin_table(self.matrix_head_dim, self.max_tokens).to(dev)
+            if not self.matrix_flatten_rope:         # (the flattened table depends on T: built with the workspace)
+                P["mrope"] = rope_1d_cos_sin_table(self.matrix_head_dim, self.max_tokens).to(dev)
         self._packed, self._packed_key = P, key
         return P
 
@@ -551,7 +559,7 @@ class DiT3D(nn.Module):
         qw = a.qkv_v.detach().float().t().contiguous()                 # [3E, D]
         qb = a.qkv_bias.detach().float()[0].clone() if hasattr(a, "qkv_bias") else torch.zeros((3 * E,), device=dev)
         if not self.matrix_rope:
-            scale = LOG2E / math.sqrt(self.matrix_head_dim)
+            scale = LOG2E / math.sqrt(self.matrix_feature_dim)
             qw[:E] *= scale
             qb[:E] *= scale
         eye = torch.eye(Pn, device=dev) if a.fixed_u == "identity" else None
@@ -603,6 +611,16 @@ class DiT3D(nn.Module):
         if self.matrix:      # frame-level rows (row, column head, frame) of the matrix attention
             Mf = R * self.matrix_cols * T
             ws.update(ms=e((Mf, D), bf), mqkv=e((Mf, 3 * D), bf), matt=e((Mf, D), bf), mz=e((Mf, D), f32))
+            if self.matrix_group > 1:                      # q | k | v and the attention output regrouped per column head
+                ws.update(mqkv_g=e((Mf // self.matrix_group, 3 * D * self.matrix_group), bf),
+                          matt_g=e((Mf // self.matrix_group, D * self.matrix_group), bf))
+            if self.matrix_flatten_rope:
+                # dit_blocks.py:316-318: the flattened [g, d] feature of a head rotates as one g*d wide vector, i.e. row j of
+                # a column head takes the pair angles j*d/2 .. (j+1)*d/2 of the wider table: one table row per (column row,
+                # frame), addressed by the QKV epilogue as row % (Mc * T)
+                g, d2 = self.matrix_group, self.matrix_head_dim // 2
+                t = rope_1d_cos_sin_table(self.matrix_feature_dim, T).view(T, g, d2, 2)
+                ws["mrope"] = t.permute(1, 0, 2, 3).repeat(self.matrix_cols // g, 1, 1, 1).reshape(-1, d2, 2).contiguous().to(dev)
             if self.matrix_block == "matrix_cross":        # attn1's output, the k / v source of attn2
                 ws.update(x1=e((M, D), f32), x1_16=e((M, D), bf))
         if not self.use_rope:
@@ -904,13 +922,24 @@ class DiT3D(nn.Module):
 
     def _matrix_core(self, bw, Pk, ws, xb, R: int, T: int):
         """ws["mz"] <- A(u^T y v) proj_v for y = xb: MatrixAttention up to its `proj_u` factor (dit_blocks.py:289-344)."""
-        D, Pn, Mc = self.hidden_size, self.num_patches, self.matrix_cols
+        D, Pn, Mc, g = self.hidden_size, self.num_patches, self.matrix_cols, self.matrix_group
+        H, d = self.matrix_heads, self.matrix_head_dim
         ops.patch_mix_bf16(xb, bw["qkv_u"], ws["ms"], R, T, Pn, Mc)
         if self.matrix_rope:
-            ops.gemm_bf16(ws["ms"], bw["qkv_w"], ws["mqkv"], ops.EPI_QKV_ROPE_BF16, bias=bw["qkv_b"], rope_cs=Pk["mrope"],
-                          tokens_per_sample=T, model_dim=D, head_dim=self.matrix_head_dim,
-                          q_scale=LOG2E / math.sqrt(self.matrix_head_dim))
+            flat = self.matrix_flatten_rope
+            ops.gemm_bf16(ws["ms"], bw["qkv_w"], ws["mqkv"], ops.EPI_QKV_ROPE_BF16, bias=bw["qkv_b"],
+                          rope_cs=ws["mrope"] if flat else Pk["mrope"], tokens_per_sample=Mc * T if flat else T,
+                          model_dim=D, head_dim=d, q_scale=LOG2E / math.sqrt(self.matrix_feature_dim))
         else:
             ops.gemm_bf16(ws["ms"], bw["qkv_w"], ws["mqkv"], ops.EPI_BF16, bias=bw["qkv_b"])
-        ops.attention(ws["mqkv"], ws["matt"], R * Mc, T, self.matrix_heads, self.matrix_head_dim)
+        if g == 1:
+            ops.attention(ws["mqkv"], ws["matt"], R * Mc, T, H, d)
+        else:
+            # dit_blocks.py:334-340: the g rows of a column head form one [g, d] feature per row head — regroup the frame-level
+            # rows (row, column head, row j, frame) x (q|k|v, row head, d) into (row, column head, frame) x (q|k|v, row head,
+            # j, d) (data movement on R*Mc*T rows), attend with g*d wide heads, and back
+            C = Mc // g
+            ws["mqkv_g"].view(R * C, T, 3, H, g, d).copy_(ws["mqkv"].view(R * C, g, T, 3, H, d).permute(0, 2, 3, 4, 1, 5))
+            ops.attention(ws["mqkv_g"], ws["matt_g"], R * C, T, H, g * d)
+            ws["matt"].view(R * C, g, T, H, d).copy_(ws["matt_g"].view(R * C, T, H, g, d).permute(0, 3, 1, 2, 4))
         ops.gemm_bf16(ws["matt"], bw["proj_w"], ws["mz"], ops.EPI_F32)

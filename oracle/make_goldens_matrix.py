@@ -48,6 +48,17 @@ def cases():
         "matrix_cross_full": matrix_case("full_matrix_attention", "matrix_cross", 1, vanilla,
                                          **{"backbone.matrix_block": "matrix_cross", "backbone.hidden_size": 64,
                                             "backbone.embed_col_dim": 2, "backbone.num_col_heads": 2}),
+        # more than one row per column head (dit_blocks.py:312-340): every row its own sequence (multi-token), the flattened
+        # [n, d] feature rotated as one vector, and — with two row heads of 32 — rotated row by row
+        "matrix_rows2_multi_token": matrix_case("full_matrix_attention", "matrix_rows4", 1, None,
+                                                **{"backbone.embed_col_dim": 4, "backbone.num_col_heads": 2,
+                                                   "backbone.hidden_size": 64, "backbone.matrix_multi_token": True}),
+        "matrix_rows2_flatten": matrix_case("full_matrix_attention", "matrix_rows4", 1, None,
+                                            **{"backbone.embed_col_dim": 4, "backbone.num_col_heads": 2,
+                                               "backbone.hidden_size": 64, "backbone.flatten_matrix_rope": True}),
+        "matrix_rows2_grouped": matrix_case("factorized_matrix_attention", "matrix_rows2_grouped", 1, vanilla,
+                                            **{"backbone.embed_col_dim": 2, "backbone.num_col_heads": 1,
+                                               "backbone.num_row_heads": 2}),
     }
 
 
