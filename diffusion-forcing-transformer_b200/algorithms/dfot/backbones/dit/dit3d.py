@@ -431,9 +431,10 @@ class DiT3D(nn.Module):
             raise NotImplementedError(f"matrix attention feature width {self.matrix_feature_dim} (rows per head x "
                                       f"head_row_dim {self.matrix_head_dim}) unsupported by the attention kernel "
                                       "(64, 72, 128)")
-        if cfg.use_bias and self.matrix_block == "matrix" and self.matrix_cols != 1:
-            raise NotImplementedError("matrix attention: use_bias with embed_col_dim > 1 is not built (the bias row "
-                                      "depends on the column head)")
+        # qkv_bias [embed_col_dim, 3E]: one bias row per column row.  One column row: the GEMM's bias vector; more: Mc extra
+        # one-hot input columns select the row's bias out of Mc extra weight columns (_pack_matrix_block)
+        self.matrix_bias_cols = _pad8(self.matrix_cols) if (cfg.use_bias and self.matrix_block == "matrix"
+                                                            and self.matrix_cols > 1) else 0
 
     # dit3d.py:91-108
     def _init_embedders(self):
@@ -557,7 +558,12 @@ class DiT3D(nn.Module):
         q_proj / kv_proj stay two GEMMs (different inputs) that write the column slabs of one [M, 3D] q|k|v buffer."""
         a, E, Mc, Pn = blk.attn if kind == "matrix" else blk.attn1, self.hidden_size, self.matrix_cols, self.num_patches
         qw = a.qkv_v.detach().float().t().contiguous()                 # [3E, D]
-        qb = a.qkv_bias.detach().float()[0].clone() if hasattr(a, "qkv_bias") else torch.zeros((3 * E,), device=dev)
+        qb = torch.zeros((3 * E,), device=dev)
+        if hasattr(a, "qkv_bias") and self.matrix_bias_cols:      # [Mc, 3E] -> weight columns D .. D+Mc (bf16 like the weights)
+            qw = torch.cat([qw, a.qkv_bias.detach().float().t(),
+                            torch.zeros((3 * E, self.matrix_bias_cols - Mc), device=dev)], dim=1)
+        elif hasattr(a, "qkv_bias"):
+            qb = a.qkv_bias.detach().float()[0].clone()
         if not self.matrix_rope:
             scale = LOG2E / math.sqrt(self.matrix_feature_dim)
             qw[:E] *= scale
@@ -611,6 +617,12 @@ class DiT3D(nn.Module):
         if self.matrix:      # frame-level rows (row, column head, frame) of the matrix attention
             Mf = R * self.matrix_cols * T
             ws.update(ms=e((Mf, D), bf), mqkv=e((Mf, 3 * D), bf), matt=e((Mf, D), bf), mz=e((Mf, D), f32))
+            if self.matrix_bias_cols:                      # [u^T y | one-hot(column row)]: the QKV GEMM's input with bias columns
+                msb = torch.zeros((Mf, D + self.matrix_bias_cols), dtype=bf, device=dev)
+                hot = msb.view(R, self.matrix_cols, T, -1)
+                for mc in range(self.matrix_cols):
+                    hot[:, mc, :, D + mc] = 1.0
+                ws["ms_b"] = msb
             if self.matrix_group > 1:                      # q | k | v and the attention output regrouped per column head
                 ws.update(mqkv_g=e((Mf // self.matrix_group, 3 * D * self.matrix_group), bf),
                           matt_g=e((Mf // self.matrix_group, D * self.matrix_group), bf))
@@ -925,13 +937,17 @@ class DiT3D(nn.Module):
         D, Pn, Mc, g = self.hidden_size, self.num_patches, self.matrix_cols, self.matrix_group
         H, d = self.matrix_heads, self.matrix_head_dim
         ops.patch_mix_bf16(xb, bw["qkv_u"], ws["ms"], R, T, Pn, Mc)
+        ms = ws["ms"]
+        if self.matrix_bias_cols and bw["qkv_w"].shape[1] > D:
+            ms = ws["ms_b"]
+            ms[:, :D].copy_(ws["ms"])                      # (frame-level rows: R*Mc*T x D)
         if self.matrix_rope:
             flat = self.matrix_flatten_rope
-            ops.gemm_bf16(ws["ms"], bw["qkv_w"], ws["mqkv"], ops.EPI_QKV_ROPE_BF16, bias=bw["qkv_b"],
+            ops.gemm_bf16(ms, bw["qkv_w"], ws["mqkv"], ops.EPI_QKV_ROPE_BF16, bias=bw["qkv_b"],
                           rope_cs=ws["mrope"] if flat else Pk["mrope"], tokens_per_sample=Mc * T if flat else T,
                           model_dim=D, head_dim=d, q_scale=LOG2E / math.sqrt(self.matrix_feature_dim))
         else:
-            ops.gemm_bf16(ws["ms"], bw["qkv_w"], ws["mqkv"], ops.EPI_BF16, bias=bw["qkv_b"])
+            ops.gemm_bf16(ms, bw["qkv_w"], ws["mqkv"], ops.EPI_BF16, bias=bw["qkv_b"])
         if g == 1:
             ops.attention(ws["mqkv"], ws["matt"], R * Mc, T, H, d)
         else:

@@ -56,6 +56,10 @@ def cases():
         "matrix_rows2_flatten": matrix_case("full_matrix_attention", "matrix_rows4", 1, None,
                                             **{"backbone.embed_col_dim": 4, "backbone.num_col_heads": 2,
                                                "backbone.hidden_size": 64, "backbone.flatten_matrix_rope": True}),
+        # one bias row per column row (qkv_bias [embed_col_dim, 3E], dit_blocks.py:283-286, 303-304)
+        "matrix_bias_cols2": matrix_case("full_matrix_attention", "matrix_bias_cols2", 1, None,
+                                         **{"backbone.embed_col_dim": 2, "backbone.num_col_heads": 2,
+                                            "backbone.hidden_size": 64, "backbone.use_bias": True}),
         "matrix_rows2_grouped": matrix_case("factorized_matrix_attention", "matrix_rows2_grouped", 1, vanilla,
                                             **{"backbone.embed_col_dim": 2, "backbone.num_col_heads": 1,
                                                "backbone.num_row_heads": 2}),
