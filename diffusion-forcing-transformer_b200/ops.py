@@ -524,7 +524,10 @@ def upsample2x_add(low, skip, out, n_img, H, W, C):
 def pose_ray_patches(cams, freq_scale, out, frames, res, p):
     _need(cams, torch.float32, "cams")
     _need(freq_scale, torch.float32, "freq_scale")
-    _need(out, torch.bfloat16, "out")
+    if not out.is_cuda or out.dtype != torch.bfloat16 or out.dim() != 2 or out.stride(1) != 1:
+        raise RuntimeError("dfot_b200: `out` must be a CUDA bf16 matrix with unit inner stride (rows may be padded)")
+    if out.shape[0] != frames * (res // p) ** 2 or out.shape[1] != p * p * 12 * freq_scale.numel():
+        raise RuntimeError(f"dfot_b200: pose_ray_patches `out` has shape {tuple(out.shape)}")
     rc = _abi.lib().dfot_pose_ray_patches(cams.data_ptr(), freq_scale.data_ptr(), freq_scale.numel(), out.data_ptr(),
                                           out.stride(0), frames, res, p, _stream())
     _abi.check(rc, "pose_ray_patches")

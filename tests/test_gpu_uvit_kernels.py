@@ -334,3 +334,7 @@ def test_pose_ray_patches_vs_oracle(res, p, B, T):
     lo = (ch < 10).repeat(p * p)
     assert err[:, lo].max().item() < 1e-2, err[:, lo].max()
     assert err[:, ~lo].max().item() < 0.25, err[:, ~lo].max()
+    # rows with padding (ld > p*p*180) take the element-wise write-out: same values, padding untouched
+    wide = torch.full((B * T * g * g, p * p * 180 + 8), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.pose_ray_patches(cams.reshape(B * T, 16).contiguous(), ray_freq_scale().to(DEV), wide[:, : p * p * 180], B * T, res, p)
+    assert torch.equal(wide[:, : p * p * 180], out) and bool((wide[:, p * p * 180:] == 7.0).all())
