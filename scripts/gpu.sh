@@ -38,6 +38,7 @@ prof_cmd() { # name -> kernel regex + command
     adaln)          RX=adaln; CMD="python scripts/bench_one.py adaln 3" ;;
     patch_mix)      RX=patch_mix; CMD="python scripts/bench_one.py patch_mix 3" ;;
     patch_expand)   RX=patch_expand; CMD="python scripts/bench_one.py patch_expand 3" ;;
+    pose_rays)      RX=pose_ray; CMD="python scripts/bench_pose_rays.py" ;;
     *) echo "unknown profile target $1"; return 1 ;;
   esac
 }
