@@ -12,7 +12,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from dfot_b200.algorithms.dfot import DFoTVideo  # noqa: E402
-from helpers import NoiseBank, build_oracle, build_product, case_names, load_case  # noqa: E402
+from helpers import MATRIX_COMBOS, NoiseBank, build_oracle, build_product, case_names, load_case, matrix_combo_model  # noqa: E402
 from oracle.cases import algorithm_cfg, continuous_overrides  # noqa: E402
 
 DEV = "cuda"
@@ -345,6 +345,18 @@ def test_dit_forward_rows_do_not_depend_on_the_batch():
     for i in range(4):
         one = model(x[i:i + 1].contiguous(), k[i:i + 1].contiguous())
         assert torch.equal(one[0], full[i]), f"row {i}: max diff {(one[0] - full[i]).abs().max().item()}"
+
+
+@pytest.mark.parametrize("combo", range(len(MATRIX_COMBOS)))
+def test_matrix_attention_combinations_vs_oracle(combo):
+    """tests/test_host_logic.py's matrix-attention combinations (block type x head grouping x RoPE mode x bias) on the
+    kernels: one forward against the CPU oracle, eager and through the captured graph."""
+    model, oracle, x, lv = matrix_combo_model(MATRIX_COMBOS[combo])
+    model = model.to(DEV)
+    want = oracle(x, lv)
+    for _ in range(3):                                   # eager, capture, replay
+        got = model(x.to(DEV), lv.to(DEV)).float().cpu()
+        assert (got - want).abs().max().item() <= 2e-2, (got - want).abs().max().item()
 
 
 def test_lockstep_rounds_reproduce_the_sequential_rollout_on_gpu():

@@ -12,7 +12,7 @@ from dfot_b200 import ops
 from dfot_b200.algorithms.dfot import DFoTVideo
 from dfot_b200.algorithms.dfot.dfot_video import interpolation_plan
 from dfot_b200.algorithms.dfot.history_guidance import HistoryGuidance
-from helpers import GOLDEN, NoiseBank, build_oracle, build_product, case_names, load_case
+from helpers import GOLDEN, MATRIX_COMBOS, NoiseBank, build_oracle, build_product, case_names, load_case, matrix_combo_model
 from oracle.cases import algorithm_cfg, continuous_overrides
 import k4_emulation
 
@@ -266,6 +266,20 @@ def test_dit3d_host_orchestration_with_emulated_kernels(name, monkeypatch):
     ref = arr["prediction"][:, n_ctx:]
     mse = float(((out.numpy()[:, n_ctx:] - ref) ** 2).mean())
     assert 10 * np.log10((ref.max() - ref.min()) ** 2 / max(mse, 1e-30)) >= 40.0
+
+
+@pytest.mark.parametrize("combo", range(len(MATRIX_COMBOS)))
+def test_matrix_attention_combinations_vs_oracle_with_emulated_kernels(combo, monkeypatch):
+    """Matrix-attention block types x head groupings x RoPE modes x bias that no golden rollout covers: one forward of the
+    product's host side on the kernel-contract emulations against the oracle (which the goldens pin, general in all of these)."""
+    import ops_emulation
+    model, oracle, x, lv = matrix_combo_model(MATRIX_COMBOS[combo])
+    ops_emulation.install(monkeypatch)
+    model.use_cuda_graph = False
+    want = oracle(x, lv)
+    got = model(x, lv)
+    assert want.abs().max() > 1e-2
+    assert (got - want).abs().max().item() <= 2e-2, (got - want).abs().max().item()
 
 
 @pytest.mark.parametrize("pos", ["rope_3d", "learned_1d"])
