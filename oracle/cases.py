@@ -158,3 +158,28 @@ def synthetic_poses(batch: int, n_frames: int):
             rows.append(torch.cat([torch.tensor([0.5, 0.9, 0.5, 0.5]), torch.cat([R, tv[:, None]], 1).flatten()]))
         out.append(torch.stack(rows))
     return torch.stack(out).float()
+
+
+# matrix-attention configurations beyond the golden rollouts: (variant, matrix_block, embed_col_dim, num_col_heads,
+# num_row_heads, embed_row_dim, use_temporal_rope, flatten_matrix_rope, matrix_multi_token, use_bias, fixed_u)
+MATRIX_COMBOS = [
+    ("full_matrix_attention", "matrix_self", 2, 2, 1, 64, True, False, False, False, None),
+    ("factorized_matrix_attention", "matrix_cross", 1, 1, 1, 64, False, False, False, False, None),
+    ("full_matrix_attention", "matrix", 4, 2, 1, 64, True, True, False, True, None),         # grouped + flatten + bias rows
+    ("factorized_matrix_attention", "matrix", 4, 1, 2, 64, False, False, False, True, None),  # 4 rows x 32 = 128 wide, no RoPE
+    ("full_matrix_attention", "matrix", 3, 3, 2, 128, True, False, True, True, None),        # odd column count, two row heads
+    ("full_matrix_attention", "matrix_cross", 4, 2, 1, 64, True, False, True, False, None),
+    ("factorized_matrix_attention", "matrix_self", 2, 1, 1, 64, True, True, False, False, None),
+    ("full_matrix_attention", "matrix", 16, 16, 1, 64, True, False, False, False, "identity"),
+]
+
+
+def matrix_combo_cfg(combo) -> dict:
+    """Backbone config of one MATRIX_COMBOS entry at golden size (8x8 latents, patch 2, 4 frames, depth 2)."""
+    variant, block, ecd, nch, nrh, erd, rope, flat, multi, bias, fixed_u = combo
+    return _small(**{"backbone.variant": variant, "backbone.pos_emb_type": "sinusoidal_2d", "backbone.use_temporal_rope": rope,
+                     "backbone.hidden_size": erd, "backbone.embed_col_dim": ecd, "backbone.embed_row_dim": erd,
+                     "backbone.num_col_heads": nch, "backbone.num_row_heads": nrh, "backbone.num_heads": erd // 64,
+                     "backbone.mlp_ratio": 2.0, "backbone.spatial_mlp_ratio": 2.0, "backbone.use_bias": bias,
+                     "backbone.matrix_block": block, "backbone.flatten_matrix_rope": flat,
+                     "backbone.matrix_multi_token": multi, "backbone.fixed_u": fixed_u})["backbone"]

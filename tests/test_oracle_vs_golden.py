@@ -123,3 +123,19 @@ def test_rollout_matches_reference(name):
             assert err <= 1e-5, (name, i, k, err)
     err = np.abs(out.numpy() - arr["prediction"]).max()
     assert err <= 1e-5, (name, err)
+
+
+def test_oracle_matrix_combinations_against_the_executed_reference():
+    """The matrix-attention combinations the product is tested on beyond the goldens (oracle/cases.py MATRIX_COMBOS) pin the
+    oracle LIVE against the executed reference backbone wherever the reference is present (/root/reference here, its unmodified
+    copy oracle/_ref/reference elsewhere) — in a subprocess, because oracle/ref_shim.py installs stand-in modules."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    probe = subprocess.run([sys.executable, "-c", "from oracle import ref_shim; print(ref_shim.available())"], cwd=root,
+                           capture_output=True, text=True, timeout=300)
+    if probe.stdout.strip() != "True":
+        pytest.skip("reference not present (run oracle/build_ref.py in the authoring container)")
+    run = subprocess.run([sys.executable, "-m", "oracle.check_matrix_combos"], cwd=root, capture_output=True, text=True,
+                         timeout=600)
+    assert run.returncode == 0 and "OK:" in run.stdout, run.stdout[-2000:] + run.stderr[-2000:]
