@@ -4,7 +4,7 @@ a one-DDIM-step rollout through the reference's public `_predict_videos` and thr
 weights (the PRODUCT's state dict, loaded strictly into the reference: its keys are the reference's), inputs and torch seed.
 Closes the chain GPU == oracle (tests/test_gpu_fullsize_parity.py) == reference at the sizes the numbers are quoted on.
 Runs wherever the reference is present (/root/reference, or oracle/_ref/reference), in a process of its own:
-    python -m oracle.check_fullsize [re10k] [k600]"""
+    python -m oracle.check_fullsize [re10k] [k600] [dmlab]"""
 import json
 import os
 import sys
@@ -32,6 +32,9 @@ def check(name: str) -> float:
         mean = torch.tensor(cfg["data_mean"]).reshape(1, 1, 3, 1, 1)
         xs = (xs - mean) / torch.tensor(cfg["data_std"]).reshape(1, 1, 3, 1, 1)
         conds, n_ctx = bench.synthetic_poses(1, 8), 1
+    elif name == "dmlab":                                          # BASELINE configs[4]: DiT-B, action-conditioned, T = 16
+        cfg = bench.dmlab_cfg(sampling_timesteps=1, frames=16)
+        xs, conds, n_ctx = torch.randn((1, 16, 32, 8, 8), generator=g), torch.randn((1, 16, 3), generator=g), 4
     else:
         cfg = bench.k600_cfg(sampling_timesteps=1)
         xs, conds, n_ctx = torch.randn((1, 5, 16, 16, 16), generator=g), None, 2
@@ -61,7 +64,7 @@ def check(name: str) -> float:
 def main() -> int:
     torch.set_num_threads(os.cpu_count() or 1)
     ref_shim.install()
-    for name in (sys.argv[1:] or ["k600", "re10k"]):
+    for name in (sys.argv[1:] or ["k600", "dmlab", "re10k"]):
         check(name)
     print("OK")
     return 0

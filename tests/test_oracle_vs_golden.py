@@ -141,9 +141,9 @@ def test_oracle_matrix_combinations_against_the_executed_reference():
     assert run.returncode == 0 and "OK:" in run.stdout, run.stdout[-2000:] + run.stderr[-2000:]
 
 
-@pytest.mark.parametrize("name", ["k600", "re10k"])
+@pytest.mark.parametrize("name", ["k600", "dmlab", "re10k"])
 def test_oracle_fullsize_rollout_against_the_executed_reference(name):
-    """oracle/check_fullsize.py: one DDIM step of the FULL-SIZE benchmarked models (bench.k600_cfg / bench.re10k_cfg) through
+    """oracle/check_fullsize.py: one DDIM step of the FULL-SIZE benchmarked models (bench.k600_cfg / bench.dmlab_cfg / bench.re10k_cfg) through
     the executed reference's `_predict_videos` and through the oracle, on the product's own state dict loaded strictly into
     the reference.  K600 takes ~45 s of CPU; RE10K (~2 min on 4 cores) runs when DFOT_SLOW_TESTS=1 — its last output is
     committed as profiles/r02_fullsize_oracle_vs_reference.txt."""
