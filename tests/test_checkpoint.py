@@ -72,7 +72,12 @@ def test_uvit3d_pose_parameter_order_matches_the_reference():
     import os
     from helpers import GOLDEN
     for case, wfile in [("uvit_pose_vanilla", "weights_uvit_pose.npz"), ("vanilla", "weights_plain.npz"),
-                        ("continuous_action", "weights_action.npz"), ("label_vanilla", "weights_label.npz")]:
+                        ("continuous_action", "weights_action.npz"), ("label_vanilla", "weights_label.npz"),
+                        ("factorized_vanilla", "weights_factorized.npz"), ("learned_1d_vanilla", "weights_learned_1d.npz"),
+                        ("matrix_factorized_bias", "weights_matrix_factorized_bias.npz"),
+                        ("matrix_self_factorized", "weights_matrix_self.npz"),
+                        ("matrix_cross_full", "weights_matrix_cross.npz"),
+                        ("matrix_bias_cols2", "weights_matrix_bias_cols2.npz")]:
         algo, _, _ = _algo_and_weights(case)
         ref_keys = list(np.load(os.path.join(GOLDEN, wfile)).files)
         model = algo.diffusion_model.model
