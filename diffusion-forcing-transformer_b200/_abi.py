@@ -8,10 +8,11 @@ LIB_PATH = os.environ.get("DFOT_B200_LIB") or os.path.join(HERE, "libdfot_b200.s
 
 F32, BF16, I64 = 0, 1, 2
 EPI_F32, EPI_BF16, EPI_GELU_BF16, EPI_SILU_BF16, EPI_GATE_RESID_F32, EPI_QKV_ROPE_BF16, EPI_RESID_F32, \
-    EPI_QKNORM_ROPE_BF16 = range(8)
+    EPI_QKNORM_ROPE_BF16, EPI_GATE_LNRESID_F32 = range(9)
 
 SYMBOLS = [
     "dfot_abi_version", "dfot_last_error", "dfot_launch_count", "dfot_sampler_step_hg", "dfot_adaln_layernorm",
+    "dfot_adaln_layernorm_stats",
     "dfot_gemm_bf16", "dfot_attention", "dfot_attention_strided", "dfot_attention_bounded", "dfot_noise_features", "dfot_silu_sum_bf16", "dfot_patchify_bf16",
     "dfot_unpatchify", "dfot_cast_bf16", "dfot_patch_mix_bf16", "dfot_patch_expand_gate_resid", "dfot_gemm_bf16_splitk", "dfot_splitk_gate_resid_adaln", "dfot_set_latency_mode", "dfot_get_latency_mode", "dfot_conv3x3_bf16", "dfot_conv3d_causal_bf16", "dfot_groupnorm_stats", "dfot_groupnorm_silu_bf16",
     "dfot_rmsnorm_film_bf16", "dfot_qk_norm_rope", "dfot_avgpool2x2", "dfot_sub_bf16", "dfot_upsample2x_add",
@@ -36,7 +37,7 @@ class GemmEpilogue(Structure):
                 ("tokens_per_sample", c_int64), ("model_dim", c_int64), ("head_dim", c_int64),
                 ("q_scale", c_float), ("qn_w", c_void_p), ("kn_w", c_void_p), ("qk_eps", c_float),
                 ("gn_sums", c_void_p), ("gn_rows_per_img", c_int64), ("gn_groups", c_int64),
-                ("gn_eps", c_float)]
+                ("gn_eps", c_float), ("ln_stats", c_void_p), ("ln_shift", c_void_p), ("ln_scale", c_void_p)]
 
 
 _lib = None
@@ -66,6 +67,7 @@ def lib() -> ctypes.CDLL:
     vp, i64, i = c_void_p, c_int64, c_int
     L.dfot_sampler_step_hg.argtypes = [vp, vp, i, vp, i, vp, vp, vp, vp, vp, i64, i64, i64, i64, vp]
     L.dfot_adaln_layernorm.argtypes = [vp, vp, i64, i64, i64, vp, vp, i64, i64, i64, c_float, vp]
+    L.dfot_adaln_layernorm_stats.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp, i64, i64, i64, c_float, vp]
     L.dfot_gemm_bf16.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, i64, i, POINTER(GemmEpilogue), vp]
     L.dfot_attention.argtypes = [vp, vp, i64, i64, i64, i64, vp]
     L.dfot_attention_strided.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp]

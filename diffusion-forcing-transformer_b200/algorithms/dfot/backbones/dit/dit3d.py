@@ -400,6 +400,10 @@ class DiT3D(nn.Module):
         # kernels, so replaying a captured graph removes the host launch cost from the sampling loop.
         self.use_cuda_graph = True
         self._graphs = {}
+        # K1 writes only the bf16 copy of the modulated tokens plus the rows' (mean, rstd); the gated-residual GEMM epilogue
+        # rebuilds the fp32 residual base from x in place (118 -> 71 MB per K1 launch at K600).  DFOT_DIT_REBUILD_BASE=0: the
+        # round-1 path (K1 stores the fp32 copy) — same bits.
+        self.rebuild_residual_base = os.environ.get("DFOT_DIT_REBUILD_BASE", "1") != "0"
 
     def _check_matrix_cfg(self, cfg) -> None:
         """dit_base.py:129-149 (the reference's own assertions) + what the kernels cover.  With one row per column head
@@ -603,7 +607,7 @@ class DiT3D(nn.Module):
         ws = dict(feat=e((RT, 256), bf), e1=e((RT, D), bf), emb=e((RT, D), f32), cact=e((RT, D), bf),
                   mod=e((RT, n_mod * D), f32), patches=torch.zeros((M, _pad8(C * p * p)), dtype=bf, device=dev),
                   x=e((M, D), f32), y=e((M, D), f32), y16=e((M, D), bf), qkv=e((M, 3 * D), bf), att=e((M, D), bf),
-                  tok=e((M, _pad8(p * p * C)), f32), out=e((R, T, *self.x_shape), out_dtype))
+                  tok=e((M, _pad8(p * p * C)), f32), out=e((R, T, *self.x_shape), out_dtype), stats=e((M, 2), f32))
         hidden = max([b.mlp.fc1.out_features for _, b in blocks if b.use_mlp], default=0)
         if hidden:
             ws["h"] = e((M, hidden), bf)
@@ -816,10 +820,15 @@ class DiT3D(nn.Module):
             if "fc1_w" in bw:
                 bcol += 3 * D
                 hbuf = ws["h"][:, : bw["fc1_w"].shape[0]]
-                ops.adaln_layernorm(xs, bmod, bcol, bcol + D, tpf, y_f32=xb, y_bf16=ws["y16"])
-                ops.gemm_bf16(ws["y16"], bw["fc1_w"], hbuf, ops.EPI_GELU_BF16, bias=bw["fc1_b"])
-                ops.gemm_bf16(hbuf, bw["fc2_w"], xs, ops.EPI_GATE_RESID_F32, bias=bw["fc2_b"], resid=xb,
-                              gate=bmod[:, bcol + 2 * D:], ld_gate=bld, tokens_per_frame=tpf)
+                if self.rebuild_residual_base:
+                    ops.adaln_layernorm(xs, bmod, bcol, bcol + D, tpf, y_bf16=ws["y16"], stats=ws["stats"])
+                    ops.gemm_bf16(ws["y16"], bw["fc1_w"], hbuf, ops.EPI_GELU_BF16, bias=bw["fc1_b"])
+                    self._gate_lnresid_gemm(hbuf, bw["fc2_w"], bw["fc2_b"], xs, ws["stats"], bmod, bld, bcol, tpf)
+                else:
+                    ops.adaln_layernorm(xs, bmod, bcol, bcol + D, tpf, y_f32=xb, y_bf16=ws["y16"])
+                    ops.gemm_bf16(ws["y16"], bw["fc1_w"], hbuf, ops.EPI_GELU_BF16, bias=bw["fc1_b"])
+                    ops.gemm_bf16(hbuf, bw["fc2_w"], xs, ops.EPI_GATE_RESID_F32, bias=bw["fc2_b"], resid=xb,
+                                  gate=bmod[:, bcol + 2 * D:], ld_gate=bld, tokens_per_frame=tpf)
             col += ncol
             if kind == "temporal":
                 xa.view(R, T, Pn, D).copy_(xs.view(R, Pn, T, D).permute(0, 2, 1, 3))
@@ -888,7 +897,11 @@ class DiT3D(nn.Module):
     def _token_attention(self, bw, Pk, ws, xs, xb, bmod, bld, bcol, tpf, n_seq, seq_len, Ntok, q_scale):
         """dit_blocks.py:488-507, first half of a DiTBlock: x <- y + gate * proj(attention(qkv(y))), y = modulate(LN(x))."""
         D = self.hidden_size
-        ops.adaln_layernorm(xs, bmod, bcol, bcol + D, tpf, y_f32=xb, y_bf16=ws["y16"])
+        rebuild = self.rebuild_residual_base
+        if rebuild:
+            ops.adaln_layernorm(xs, bmod, bcol, bcol + D, tpf, y_bf16=ws["y16"], stats=ws["stats"])
+        else:
+            ops.adaln_layernorm(xs, bmod, bcol, bcol + D, tpf, y_f32=xb, y_bf16=ws["y16"])
         if self.use_rope:
             ops.gemm_bf16(ws["y16"], bw["qkv_w"], ws["qkv"], ops.EPI_QKV_ROPE_BF16, bias=bw["qkv_b"],
                           rope_cs=Pk["rope"], tokens_per_sample=Ntok, model_dim=D, head_dim=self.head_dim,
@@ -897,8 +910,19 @@ class DiT3D(nn.Module):
             ops.gemm_bf16(ws["y16"], bw["qkv_w"], ws["qkv"], ops.EPI_BF16, bias=bw["qkv_b"])
         ops.attention(ws["qkv"], ws["att"], n_seq, seq_len, self.num_heads, self.head_dim)
         # x1 = y + gate1 * proj(att)   (residual base is the modulated tensor — reference quirk Q1)
-        ops.gemm_bf16(ws["att"], bw["proj_w"], xs, ops.EPI_GATE_RESID_F32, bias=bw["proj_b"], resid=xb,
-                      gate=bmod[:, bcol + 2 * D:], ld_gate=bld, tokens_per_frame=tpf)
+        if rebuild:
+            self._gate_lnresid_gemm(ws["att"], bw["proj_w"], bw["proj_b"], xs, ws["stats"], bmod, bld, bcol, tpf)
+        else:
+            ops.gemm_bf16(ws["att"], bw["proj_w"], xs, ops.EPI_GATE_RESID_F32, bias=bw["proj_b"], resid=xb,
+                          gate=bmod[:, bcol + 2 * D:], ld_gate=bld, tokens_per_frame=tpf)
+
+    def _gate_lnresid_gemm(self, a, w, b, xs, stats, bmod, bld, bcol, tpf):
+        """x <- modulate(LN(x)) + gate * (a w^T + b), in place: the residual base of a block half is the modulated tensor
+        (quirk Q1), which K1 did not store in fp32 — the epilogue rebuilds it from x, the rows' (mean, rstd) and the frame's
+        shift / scale vectors with K1's own expression (bit-identical to the stored copy: DFOT_EPI_GATE_LNRESID_F32)."""
+        D = self.hidden_size
+        ops.gemm_bf16(a, w, xs, ops.EPI_GATE_LNRESID_F32, bias=b, resid=xs, gate=bmod[:, bcol + 2 * D:], ld_gate=bld,
+                      tokens_per_frame=tpf, ln_stats=stats, ln_shift=bmod[:, bcol:], ln_scale=bmod[:, bcol + D:])
 
     def _matrix_attention(self, bw, Pk, ws, xs, xb, mod, ldm, col, R: int, T: int):
         """dit_blocks.py:626-644 + 289-350, first half of a MatrixDiTBlock: x <- y + gate * (proj_u^T A(u^T y v) proj_v +

@@ -114,6 +114,12 @@ inline bool pdl_enabled() {
   return v == 1;
 }
 
+// One element of AdaLayerNorm[Zero]'s output, with the rounding of every step pinned: the GATE_LNRESID GEMM epilogue rebuilds
+// the value dfot_adaln_layernorm produced (its bf16 copy fed the GEMM) and must match it bit for bit.
+__device__ __forceinline__ float adaln_value(float x, float mean, float rstd, float scale, float shift) {
+  return __fmaf_rn(__fmul_rn(__fsub_rn(x, mean), rstd), __fadd_rn(1.f, scale), shift);
+}
+
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
   cudaLaunchConfig_t cfg;

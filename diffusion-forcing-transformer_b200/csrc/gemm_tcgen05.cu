@@ -351,6 +351,12 @@ __device__ __forceinline__ void gn_flush(const Params& p, int lane, int m0, int 
   else gn_flush_impl<NC, LPR, NC>(p, lane, m0, col0, cpg, s, q, col_ok);       // one channel per group
 }
 
+// epilogue families: a residual operand (fetched ahead of the accumulator), a per-frame gate
+__host__ __device__ constexpr bool epi_has_resid(int epi) {
+  return epi == DFOT_EPI_RESID_F32 || epi == DFOT_EPI_GATE_RESID_F32 || epi == DFOT_EPI_GATE_LNRESID_F32;
+}
+__host__ __device__ constexpr bool epi_has_gate(int epi) { return epi == DFOT_EPI_GATE_RESID_F32 || epi == DFOT_EPI_GATE_LNRESID_F32; }
+
 template <int EPI> struct ChunkSide {
   float4 r[8];   // *_RESID_F32: residual of (row 4*it + lane/8, columns 4*(lane%8)..+3), it = 0..7
   float v[32];   // QKV_ROPE: (cos, sin) of row 2k + (lane>>4) for the lane's rotation pair
@@ -358,7 +364,7 @@ template <int EPI> struct ChunkSide {
 
 template <int EPI, bool FULL>
 __device__ __forceinline__ void prefetch_side(const Params& p, ChunkSide<EPI>& sd, int lane, int m0, int n0) {
-  if constexpr (EPI == DFOT_EPI_GATE_RESID_F32 || EPI == DFOT_EPI_RESID_F32) {
+  if constexpr (epi_has_resid(EPI)) {
     const int col = n0 + ((lane & 7) << 2), rsub = lane >> 3;
     const float* res = p.e.resid + (int64_t)(m0 + rsub) * p.e.ld_resid + col;
     const int64_t step = 4 * p.e.ld_resid;
@@ -405,7 +411,10 @@ __device__ __forceinline__ void prefetch_side(const Params& p, ChunkSide<EPI>& s
   }
 }
 
-// fp32 outputs (F32, RESID_F32, GATE_RESID_F32): lane = (row 4*it + lane/8, columns 4*(lane%8)..+3), 8 steps.
+// fp32 outputs (F32, RESID_F32, GATE_RESID_F32, GATE_LNRESID_F32): lane = (row 4*it + lane/8, columns 4*(lane%8)..+3), 8 steps.
+// GATE_LNRESID: the residual base is not the stored tensor r but its modulated LayerNorm, rebuilt here from the row's
+// (mean, rstd) and the frame's shift / scale vectors with the expression dfot_adaln_layernorm uses — so that kernel need not
+// store the fp32 copy of its output; the output may overwrite r (every element is read and written by the same lane).
 template <int EPI, bool FULL>
 __device__ __forceinline__ void epilogue_rows_f32(const Params& p, const ChunkSide<EPI>& sd, uint32_t stage, int lane,
                                                   int m0, int n0) {
@@ -418,12 +427,13 @@ __device__ __forceinline__ void epilogue_rows_f32(const Params& p, const ChunkSi
   float* out = reinterpret_cast<float*>(p.C) + (int64_t)(m0 + rsub) * p.ldc + col;
   const int64_t step = 4 * p.ldc;
   float4 gate0 = make_float4(0.f, 0.f, 0.f, 0.f), gate1 = gate0;
+  float4 sc0 = gate0, sc1 = gate0, sh0 = gate0, sh1 = gate0;   // GATE_LNRESID: scale / shift of the chunk's two frames
   // tokens_per_frame >= 32: rows [0, split) of the chunk belong to frame f0, the rest to f0 + 1 — two gate vectors per
   // lane.  Smaller frames (8x8 latents with patch 2: 16 tokens, the DMLab / Minecraft DiT configurations): a chunk spans
   // several frames and every row looks its (L1-resident) gate vector up.
   int split = 32, P = 1, f0 = 0, rem0 = 0;
   bool small_frames = false;     // warp-uniform
-  if constexpr (EPI == DFOT_EPI_GATE_RESID_F32) {
+  if constexpr (epi_has_gate(EPI)) {
     P = (int)p.e.tokens_per_frame;
     f0 = m0 / P;
     rem0 = m0 - f0 * P;
@@ -432,6 +442,14 @@ __device__ __forceinline__ void epilogue_rows_f32(const Params& p, const ChunkSi
     if (col_ok && !small_frames) {
       gate0 = __ldg(reinterpret_cast<const float4*>(p.e.gate + (int64_t)f0 * p.e.ld_gate + col));
       if (split < 32) gate1 = __ldg(reinterpret_cast<const float4*>(p.e.gate + (int64_t)(f0 + 1) * p.e.ld_gate + col));
+      if constexpr (EPI == DFOT_EPI_GATE_LNRESID_F32) {
+        sc0 = __ldg(reinterpret_cast<const float4*>(p.e.ln_scale + (int64_t)f0 * p.e.ld_gate + col));
+        sh0 = __ldg(reinterpret_cast<const float4*>(p.e.ln_shift + (int64_t)f0 * p.e.ld_gate + col));
+        if (split < 32) {
+          sc1 = __ldg(reinterpret_cast<const float4*>(p.e.ln_scale + (int64_t)(f0 + 1) * p.e.ld_gate + col));
+          sh1 = __ldg(reinterpret_cast<const float4*>(p.e.ln_shift + (int64_t)(f0 + 1) * p.e.ld_gate + col));
+        }
+      }
     }
   }
   const bool gn = p.e.gn_sums != nullptr;   // warp-uniform
@@ -447,6 +465,24 @@ __device__ __forceinline__ void epilogue_rows_f32(const Params& p, const ChunkSi
         g = __ldg(reinterpret_cast<const float4*>(p.e.gate + (int64_t)(f0 + (rem0 + i) / P) * p.e.ld_gate + col));
       y.x = fmaf(g.x, y.x, sd.r[it].x); y.y = fmaf(g.y, y.y, sd.r[it].y);
       y.z = fmaf(g.z, y.z, sd.r[it].z); y.w = fmaf(g.w, y.w, sd.r[it].w);
+    }
+    if constexpr (EPI == DFOT_EPI_GATE_LNRESID_F32) {
+      float4 g = i < split ? gate0 : gate1, sc = i < split ? sc0 : sc1, sh = i < split ? sh0 : sh1;
+      float2 st = make_float2(0.f, 0.f);                       // (mean, rstd) of row m0 + i
+      if (col_ok && (FULL || i < rows)) {
+        st = __ldg(reinterpret_cast<const float2*>(p.e.ln_stats) + m0 + i);
+        if (small_frames) {
+          const int64_t fo = (int64_t)(f0 + (rem0 + i) / P) * p.e.ld_gate + col;
+          g = __ldg(reinterpret_cast<const float4*>(p.e.gate + fo));
+          sc = __ldg(reinterpret_cast<const float4*>(p.e.ln_scale + fo));
+          sh = __ldg(reinterpret_cast<const float4*>(p.e.ln_shift + fo));
+        }
+      }
+      const float4 r = sd.r[it];
+      // the residual base, bit for bit what adaln_layernorm_kernel computes: ((x - mean) * rstd) * (1 + scale) + shift
+      const float bx = adaln_value(r.x, st.x, st.y, sc.x, sh.x), by = adaln_value(r.y, st.x, st.y, sc.y, sh.y);
+      const float bz = adaln_value(r.z, st.x, st.y, sc.z, sh.z), bw = adaln_value(r.w, st.x, st.y, sc.w, sh.w);
+      y.x = fmaf(g.x, y.x, bx); y.y = fmaf(g.y, y.y, by); y.z = fmaf(g.z, y.z, bz); y.w = fmaf(g.w, y.w, bw);
     }
     if constexpr (EPI == DFOT_EPI_RESID_F32) {
       y.x += sd.r[it].x; y.y += sd.r[it].y; y.z += sd.r[it].z; y.w += sd.r[it].w;
@@ -708,7 +744,7 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, uint32_t t_addr,
   tmem_ld_x32(t_addr, r);
   stage_chunk(stage_buf, lane, r);
   __syncwarp();
-  if constexpr (EPI == DFOT_EPI_F32 || EPI == DFOT_EPI_GATE_RESID_F32 || EPI == DFOT_EPI_RESID_F32)
+  if constexpr (EPI == DFOT_EPI_F32 || epi_has_resid(EPI))
     epilogue_rows_f32<EPI, FULL>(p, side, stage_buf, lane, m0, n0);
   else if constexpr (EPI == DFOT_EPI_QKV_ROPE_BF16)
     epilogue_rows_rope<FULL>(p, side, stage_buf, lane, m0, n0);
@@ -876,7 +912,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int m0 = m_blk * BM + q * 32;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      if constexpr (EPI == DFOT_EPI_RESID_F32 || EPI == DFOT_EPI_GATE_RESID_F32) {
+      if constexpr (epi_has_resid(EPI)) {
         epilogue_tile_resid<EPI, BN>(p, t_row, stage_buf, lane, m0, n_blk * BN, half, tmem_full_bar(acc), acc_phase);
         tc_fence_before();
         __syncwarp();
@@ -1079,7 +1115,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int m0 = m_blk * 2 * BM + rank * BM + q * 32;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      if constexpr (EPI == DFOT_EPI_RESID_F32 || EPI == DFOT_EPI_GATE_RESID_F32) {
+      if constexpr (epi_has_resid(EPI)) {
         epilogue_tile_resid<EPI, BN>(p, t_row, stage_buf, lane, m0, n_blk * BN, half, tmem_full_bar(acc), acc_phase);
         tc_fence_before();
         __syncwarp();
@@ -1230,6 +1266,7 @@ static int dispatch_pair(int epi, const CUtensorMap& ta, const CUtensorMap& tb, 
     case DFOT_EPI_GELU_BF16: return launch_pair<BN, DFOT_EPI_GELU_BF16>(ta, tb, p, s);
     case DFOT_EPI_SILU_BF16: return launch_pair<BN, DFOT_EPI_SILU_BF16>(ta, tb, p, s);
     case DFOT_EPI_GATE_RESID_F32: return launch_pair<BN, DFOT_EPI_GATE_RESID_F32>(ta, tb, p, s);
+    case DFOT_EPI_GATE_LNRESID_F32: return launch_pair<BN, DFOT_EPI_GATE_LNRESID_F32>(ta, tb, p, s);
     case DFOT_EPI_QKV_ROPE_BF16: return launch_pair<BN, DFOT_EPI_QKV_ROPE_BF16>(ta, tb, p, s);
     case DFOT_EPI_RESID_F32: return launch_pair<BN, DFOT_EPI_RESID_F32>(ta, tb, p, s);
     case DFOT_EPI_QKNORM_ROPE_BF16:
@@ -1326,6 +1363,7 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
     case DFOT_EPI_GELU_BF16: return launch<BN, DFOT_EPI_GELU_BF16>(ta, tb, p, s);
     case DFOT_EPI_SILU_BF16: return launch<BN, DFOT_EPI_SILU_BF16>(ta, tb, p, s);
     case DFOT_EPI_GATE_RESID_F32: return launch<BN, DFOT_EPI_GATE_RESID_F32>(ta, tb, p, s);
+    case DFOT_EPI_GATE_LNRESID_F32: return launch<BN, DFOT_EPI_GATE_LNRESID_F32>(ta, tb, p, s);
     case DFOT_EPI_QKV_ROPE_BF16: return launch<BN, DFOT_EPI_QKV_ROPE_BF16>(ta, tb, p, s);
     case DFOT_EPI_RESID_F32: return launch<BN, DFOT_EPI_RESID_F32>(ta, tb, p, s);
     case DFOT_EPI_QKNORM_ROPE_BF16:
@@ -1358,13 +1396,18 @@ extern "C" int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   // the epilogue reads bias / residual / gate and writes the output with 16-byte accesses
   DFOT_REQUIRE(epi->bias == nullptr || (uintptr_t)epi->bias % 16 == 0, DFOT_ERR_UNSUPPORTED,
                "gemm: bias must be 16-byte aligned");
-  if (epilogue == DFOT_EPI_GATE_RESID_F32)
+  const bool gated = epilogue == DFOT_EPI_GATE_RESID_F32 || epilogue == DFOT_EPI_GATE_LNRESID_F32;
+  if (gated)
     DFOT_REQUIRE(epi->resid && epi->gate && epi->tokens_per_frame >= 1 && epi->tokens_per_frame < (1ll << 30),
                  DFOT_ERR_INVALID_ARG, "gemm: GATE_RESID needs resid, gate and tokens_per_frame");
-  if (epilogue == DFOT_EPI_GATE_RESID_F32)
+  if (gated)
     DFOT_REQUIRE((uintptr_t)epi->gate % 16 == 0 && epi->ld_gate % 4 == 0, DFOT_ERR_UNSUPPORTED,
                  "gemm: gate must be 16-byte aligned with ld_gate %% 4 == 0");
-  if (epilogue == DFOT_EPI_GATE_RESID_F32 || epilogue == DFOT_EPI_RESID_F32)
+  if (epilogue == DFOT_EPI_GATE_LNRESID_F32)
+    DFOT_REQUIRE(epi->ln_stats && epi->ln_shift && epi->ln_scale && (uintptr_t)epi->ln_stats % 8 == 0 &&
+                     (uintptr_t)epi->ln_shift % 16 == 0 && (uintptr_t)epi->ln_scale % 16 == 0,
+                 DFOT_ERR_INVALID_ARG, "gemm: GATE_LNRESID needs ln_stats (8-byte aligned), ln_shift and ln_scale (16-byte aligned)");
+  if (gated || epilogue == DFOT_EPI_RESID_F32)
     DFOT_REQUIRE(epi->resid != nullptr && (uintptr_t)epi->resid % 16 == 0 && epi->ld_resid % 4 == 0, DFOT_ERR_UNSUPPORTED,
                  "gemm: resid must be 16-byte aligned with ld_resid %% 4 == 0");
   if (epilogue == DFOT_EPI_RESID_F32)

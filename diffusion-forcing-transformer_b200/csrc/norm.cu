@@ -13,7 +13,8 @@ template <int NV>  // NV = float4 vectors held per lane (row length D <= NV*128)
 __global__ void __launch_bounds__(kNormWarps * 32)
 adaln_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ mod, int64_t mod_ld,
                        int64_t shift_col, int64_t scale_col, float* __restrict__ y_f32,
-                       __nv_bfloat16* __restrict__ y_bf16, int64_t M, int D, int64_t tokens_per_frame, float eps) {
+                       __nv_bfloat16* __restrict__ y_bf16, float2* __restrict__ stats, int64_t M, int D,
+                       int64_t tokens_per_frame, float eps) {
   pdl_trigger();   // programmatic dependent launch: see common.cuh
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -45,6 +46,7 @@ adaln_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ mo
     }
   }
   const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+  if (stats != nullptr && lane == 0) stats[m] = make_float2(mean, rstd);   // for the GATE_LNRESID GEMM epilogue
   const int64_t f = m / tokens_per_frame;
   const float4* sh = reinterpret_cast<const float4*>(mod + f * mod_ld + shift_col);
   const float4* sc = reinterpret_cast<const float4*>(mod + f * mod_ld + scale_col);
@@ -54,10 +56,10 @@ adaln_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ mo
     if (c < nvec) {
       const float4 s = __ldg(sh + c), g = __ldg(sc + c);
       float4 y;
-      y.x = (v[i].x - mean) * rstd * (1.f + g.x) + s.x;
-      y.y = (v[i].y - mean) * rstd * (1.f + g.y) + s.y;
-      y.z = (v[i].z - mean) * rstd * (1.f + g.z) + s.z;
-      y.w = (v[i].w - mean) * rstd * (1.f + g.w) + s.w;
+      y.x = adaln_value(v[i].x, mean, rstd, g.x, s.x);
+      y.y = adaln_value(v[i].y, mean, rstd, g.y, s.y);
+      y.z = adaln_value(v[i].z, mean, rstd, g.z, s.z);
+      y.w = adaln_value(v[i].w, mean, rstd, g.w, s.w);
       if (y_f32)
         st_stream_u4(y_f32 + m * D + 4 * c, make_uint4(__float_as_uint(y.x), __float_as_uint(y.y),
                                                        __float_as_uint(y.z), __float_as_uint(y.w)));
@@ -161,14 +163,22 @@ constexpr int64_t kRowKernelMaxRows = 2048;   // up to here K1 runs one block pe
 extern "C" int dfot_adaln_layernorm(const float* x, const float* mod, int64_t mod_ld, int64_t shift_col,
                                     int64_t scale_col, float* y_f32, void* y_bf16, int64_t M, int64_t D,
                                     int64_t tokens_per_frame, float eps, void* stream) {
+  return dfot_adaln_layernorm_stats(x, mod, mod_ld, shift_col, scale_col, y_f32, y_bf16, nullptr, M, D, tokens_per_frame,
+                                    eps, stream);
+}
+
+extern "C" int dfot_adaln_layernorm_stats(const float* x, const float* mod, int64_t mod_ld, int64_t shift_col,
+                                          int64_t scale_col, float* y_f32, void* y_bf16, float* stats, int64_t M, int64_t D,
+                                          int64_t tokens_per_frame, float eps, void* stream) {
   using namespace dfot;
   DFOT_REQUIRE(x && mod && (y_f32 || y_bf16), DFOT_ERR_INVALID_ARG, "adaln_layernorm: null pointer");
+  DFOT_REQUIRE((uintptr_t)stats % 8 == 0, DFOT_ERR_UNSUPPORTED, "adaln_layernorm: stats must be 8-byte aligned");
   DFOT_REQUIRE(M > 0 && D > 0 && tokens_per_frame > 0, DFOT_ERR_INVALID_ARG, "adaln_layernorm: bad sizes");
   DFOT_REQUIRE(D % 4 == 0 && mod_ld % 4 == 0 && shift_col % 4 == 0 && scale_col % 4 == 0, DFOT_ERR_UNSUPPORTED,
                "adaln_layernorm: D, mod_ld and column offsets must be multiples of 4 (128-bit access)");
   DFOT_REQUIRE(D <= 4096, DFOT_ERR_UNSUPPORTED, "adaln_layernorm: D=%lld > 4096 unsupported", (long long)D);
   cudaStream_t s = (cudaStream_t)stream;
-  if (latency_mode() && M <= kRowKernelMaxRows && D <= 2048 && (uintptr_t)x % 16 == 0 && (uintptr_t)mod % 16 == 0 && (uintptr_t)y_f32 % 16 == 0 &&
+  if (stats == nullptr && latency_mode() && M <= kRowKernelMaxRows && D <= 2048 && (uintptr_t)x % 16 == 0 && (uintptr_t)mod % 16 == 0 && (uintptr_t)y_f32 % 16 == 0 &&
       (uintptr_t)y_bf16 % 8 == 0) {
     if (D <= 1024)
       launch_pdl(row_adaln_kernel<1>, dim3((unsigned)M), dim3(kRowThreads), 0, s, (const float*)nullptr, 0,
@@ -184,7 +194,7 @@ extern "C" int dfot_adaln_layernorm(const float* x, const float* mod, int64_t mo
   const unsigned grid = (unsigned)ceil_div(M, kNormWarps);
 #define LAUNCH(NV)                                                                                             \
   launch_pdl(adaln_layernorm_kernel<NV>, dim3(grid), dim3(kNormWarps * 32), 0, s, x, mod, mod_ld, shift_col, scale_col, y_f32,     \
-                                                              (__nv_bfloat16*)y_bf16, M, (int)D,               \
+                                                              (__nv_bfloat16*)y_bf16, (float2*)stats, M, (int)D, \
                                                               tokens_per_frame, eps)
   if (D <= 256) LAUNCH(2);
   else if (D <= 512) LAUNCH(4);

@@ -10,7 +10,7 @@ import torch
 
 from . import _abi
 from ._abi import (BF16, EPI_BF16, EPI_F32, EPI_GATE_RESID_F32, EPI_GELU_BF16, EPI_QKV_ROPE_BF16,  # noqa: F401
-                   EPI_QKNORM_ROPE_BF16, EPI_RESID_F32, EPI_SILU_BF16, F32, I64)
+                   EPI_QKNORM_ROPE_BF16, EPI_RESID_F32, EPI_SILU_BF16, EPI_GATE_LNRESID_F32, F32, I64)
 
 _DTYPE_TAG = {torch.float32: F32, torch.bfloat16: BF16, torch.int64: I64}
 
@@ -91,8 +91,8 @@ def sampler_step_hg(x, model_out, model_in_next, upd, prep, noise_ddim, noise_hi
     _abi.check(rc, "sampler_step_hg")
 
 
-def adaln_layernorm(x, mod, shift_col, scale_col, tokens_per_frame, y_f32=None, y_bf16=None, eps=1e-6):
-    """K1. x [M,D] f32, mod [frames, mod_ld] f32."""
+def adaln_layernorm(x, mod, shift_col, scale_col, tokens_per_frame, y_f32=None, y_bf16=None, eps=1e-6, stats=None):
+    """K1. x [M,D] f32, mod [frames, mod_ld] f32; stats [M,2] f32 (optional side output: mean, rstd per row)."""
     _need(x, torch.float32, "x")
     _need(mod, torch.float32, "mod")
     M, D = x.shape
@@ -100,8 +100,12 @@ def adaln_layernorm(x, mod, shift_col, scale_col, tokens_per_frame, y_f32=None, 
         _need(y_f32, torch.float32, "y_f32")
     if y_bf16 is not None:
         _need(y_bf16, torch.bfloat16, "y_bf16")
-    rc = _abi.lib().dfot_adaln_layernorm(x.data_ptr(), mod.data_ptr(), mod.shape[-1], shift_col, scale_col,
-                                         _ptr(y_f32), _ptr(y_bf16), M, D, tokens_per_frame, eps, _stream())
+    if stats is not None:
+        _need(stats, torch.float32, "stats")
+        if stats.numel() != 2 * M:
+            raise RuntimeError("dfot_b200: `stats` must hold (mean, rstd) of every row: [M, 2] f32")
+    rc = _abi.lib().dfot_adaln_layernorm_stats(x.data_ptr(), mod.data_ptr(), mod.shape[-1], shift_col, scale_col,
+                                               _ptr(y_f32), _ptr(y_bf16), _ptr(stats), M, D, tokens_per_frame, eps, _stream())
     _abi.check(rc, "adaln_layernorm")
 
 
@@ -117,15 +121,17 @@ def _gn_side_output(e, gn_sums, gn_rows_per_img, gn_groups, gn_eps, M, N):
 
 def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, gate=None, ld_gate=0, tokens_per_frame=1, rope_cs=None,
               tokens_per_sample=1, model_dim=0, head_dim=0, q_scale=1.0, M=None, gn_sums=None, gn_rows_per_img=0,
-              gn_groups=32, gn_eps=1e-6, qn_w=None, kn_w=None, qk_eps=1e-6):
-    """K2. a [M,K] bf16, w [N,K] bf16 (row strides may exceed K), out [M,N] f32|bf16 per epilogue."""
+              gn_groups=32, gn_eps=1e-6, qn_w=None, kn_w=None, qk_eps=1e-6, ln_stats=None, ln_shift=None, ln_scale=None):
+    """K2. a [M,K] bf16, w [N,K] bf16 (row strides may exceed K), out [M,N] f32|bf16 per epilogue.
+    EPI_GATE_LNRESID_F32: `resid` is x, the residual base modulate(LN(x)) is rebuilt from ln_stats [M,2] (adaln_layernorm's side
+    output) and the ln_shift / ln_scale views into the modulation matrix (same row stride as `gate`); `out` may be `resid`."""
     if not w.is_cuda or w.dtype != torch.bfloat16 or w.stride(-1) != 1:
         raise RuntimeError("dfot_b200: `w` must be a CUDA bf16 matrix with unit inner stride")
     if not a.is_cuda or a.dtype != torch.bfloat16 or a.stride(-1) != 1:
         raise RuntimeError("dfot_b200: `a` must be a CUDA bf16 matrix with unit inner stride")
     if not out.is_cuda or out.stride(-1) != 1:
         raise RuntimeError("dfot_b200: `out` must be a CUDA matrix with unit inner stride")
-    want = torch.float32 if epilogue in (EPI_F32, EPI_GATE_RESID_F32, EPI_RESID_F32) else torch.bfloat16
+    want = torch.float32 if epilogue in (EPI_F32, EPI_GATE_RESID_F32, EPI_RESID_F32, EPI_GATE_LNRESID_F32) else torch.bfloat16
     if out.dtype != want:
         raise RuntimeError(f"dfot_b200: epilogue {epilogue} writes {want}, got {out.dtype}")
     M = a.shape[0] if M is None else M
@@ -144,6 +150,14 @@ def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, gate=None, ld_gate=0, 
             raise RuntimeError("dfot_b200: `gate` must be CUDA f32")
         e.gate, e.ld_gate = gate.data_ptr(), ld_gate
     e.tokens_per_frame = tokens_per_frame
+    if epilogue == EPI_GATE_LNRESID_F32:
+        _need(ln_stats, torch.float32, "ln_stats")
+        for t, name in ((ln_shift, "ln_shift"), (ln_scale, "ln_scale")):
+            if t is None or t.dtype != torch.float32 or not t.is_cuda or t.stride(0) != gate.stride(0):
+                raise RuntimeError(f"dfot_b200: `{name}` must be a CUDA f32 view with the row stride of `gate`")
+        if ln_stats.numel() != 2 * (a.shape[0] if M is None else M):
+            raise RuntimeError("dfot_b200: `ln_stats` must be [M, 2] f32")
+        e.ln_stats, e.ln_shift, e.ln_scale = ln_stats.data_ptr(), ln_shift.data_ptr(), ln_scale.data_ptr()
     if rope_cs is not None:
         _need(rope_cs, torch.float32, "rope_cs")
         e.rope_cs = rope_cs.data_ptr()

@@ -110,6 +110,12 @@ DFOT_API int dfot_sampler_step_hg(float* x, const void* model_out, int model_out
 DFOT_API int dfot_adaln_layernorm(const float* x, const float* mod, int64_t mod_ld, int64_t shift_col, int64_t scale_col,
                          float* y_f32, void* y_bf16, int64_t M, int64_t D, int64_t tokens_per_frame, float eps,
                          void* stream);
+/* The same with a side output: stats[m] = (mean, rstd) of row m (float pairs, may be NULL).  With it the consumer of the
+ * fp32 copy — the gated-residual GEMM epilogue of a DiT block half, whose residual base is the MODULATED tensor
+ * (dit_blocks.py:504-509) — can rebuild y from x (DFOT_EPI_GATE_LNRESID_F32) and y_f32 need not be written. */
+DFOT_API int dfot_adaln_layernorm_stats(const float* x, const float* mod, int64_t mod_ld, int64_t shift_col, int64_t scale_col,
+                               float* y_f32, void* y_bf16, float* stats, int64_t M, int64_t D, int64_t tokens_per_frame,
+                               float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K2 — tcgen05/TMEM bf16 GEMM fed by TMA:  C[M,N] = epilogue(A[M,K] · W[N,K]^T + bias[N]).
@@ -128,6 +134,11 @@ DFOT_API int dfot_adaln_layernorm(const float* x, const float* mod, int64_t mod_
 #define DFOT_EPI_QKNORM_ROPE_BF16 7 /* out bf16 = [rope3d(rmsnorm_d(acc + bias) * w_q) * q_scale | rope3d(rmsnorm_d(.) * w_k) | v]:
                                      q/k RMSNorm over head_dim from the fp32 accumulators, then RoPE-3D
                                      (u_vit_blocks.py:253-259); N = 3*model_dim, head_dim in {64, 128} */
+
+#define DFOT_EPI_GATE_LNRESID_F32 8 /* out f32 = y[m, n] + gate[f(m), n] * (acc + bias), y = ((resid - mean[m]) * rstd[m]) *
+                                     (1 + ln_scale[f(m), n]) + ln_shift[f(m), n]: the residual base of a DiT block half rebuilt
+                                     from x and the (mean, rstd) side output of dfot_adaln_layernorm_stats, bit for bit the
+                                     value K1 computes; out may be resid itself (dit_blocks.py:427-437, 504-509) */
 
 typedef struct {
   const float* bias;          /* [N] or NULL */
@@ -155,6 +166,10 @@ typedef struct {
   int64_t gn_rows_per_img;
   int64_t gn_groups;
   float gn_eps;
+  /* GATE_LNRESID: stats[m] = (mean, rstd) float pairs; shift / scale vectors addressed like the gate (f * ld_gate + n) */
+  const float* ln_stats;
+  const float* ln_shift;
+  const float* ln_scale;
 } dfot_gemm_epilogue;
 
 DFOT_API int dfot_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int64_t M,

@@ -77,13 +77,24 @@ def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, M=None, **kw):
         frame = torch.arange(M) // kw["tokens_per_frame"]
         out[:M].copy_(resid[:M] + kw["gate"][frame][:, : acc.shape[1]] * (acc + bias))
         return
+    if epilogue == ops.EPI_GATE_LNRESID_F32:      # the residual base rebuilt from x = resid and the row statistics
+        N = acc.shape[1]
+        frame = torch.arange(M) // kw["tokens_per_frame"]
+        st = kw["ln_stats"].reshape(-1, 2)[:M]
+        base = ((resid[:M] - st[:, :1]) * st[:, 1:]) * (1 + kw["ln_scale"][frame][:, :N]) + kw["ln_shift"][frame][:, :N]
+        out[:M].copy_(base + kw["gate"][frame][:, :N] * (acc + bias))
+        return
     _epilogue(acc, out[:M], epilogue, bias, None if resid is None else resid[:M])
 
 
-def adaln_layernorm(x, mod, shift_col, scale_col, tokens_per_frame, y_f32=None, y_bf16=None, eps=1e-6):
+def adaln_layernorm(x, mod, shift_col, scale_col, tokens_per_frame, y_f32=None, y_bf16=None, eps=1e-6, stats=None):
     M, D = x.shape
     frame = torch.arange(M) // tokens_per_frame
-    y = F.layer_norm(x.float(), (D,), eps=eps) * (1 + mod[frame, scale_col:scale_col + D]) + mod[frame, shift_col:shift_col + D]
+    mean = x.float().mean(-1, keepdim=True)
+    rstd = torch.rsqrt(((x.float() - mean) ** 2).mean(-1, keepdim=True) + eps)
+    y = ((x.float() - mean) * rstd) * (1 + mod[frame, scale_col:scale_col + D]) + mod[frame, shift_col:shift_col + D]
+    if stats is not None:
+        stats.reshape(-1, 2).copy_(torch.cat([mean, rstd], 1))
     if y_f32 is not None:
         y_f32.copy_(y)
     if y_bf16 is not None:
@@ -129,7 +140,9 @@ def splitk_gate_resid_adaln(parts, splits, bias, resid, mod, gate_col, shift_col
     if x_out is not None:
         x_out.copy_(x)
     if shift_col >= 0:
-        y = F.layer_norm(x, (D,), eps=eps) * (1 + mod[frame, scale_col:scale_col + D]) + mod[frame, shift_col:shift_col + D]
+        mean = x.mean(-1, keepdim=True)                       # (the arithmetic of adaln_layernorm above)
+        rstd = torch.rsqrt(((x - mean) ** 2).mean(-1, keepdim=True) + eps)
+        y = ((x - mean) * rstd) * (1 + mod[frame, scale_col:scale_col + D]) + mod[frame, shift_col:shift_col + D]
         if y_f32 is not None:
             y_f32.copy_(y)
         if y_bf16 is not None:

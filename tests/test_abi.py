@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_abi.FrameUpdate) == 24
     assert ctypes.sizeof(_abi.FramePrepare) == 16
-    assert ctypes.sizeof(_abi.GemmEpilogue) == 144
+    assert ctypes.sizeof(_abi.GemmEpilogue) == 168
 
 
 def test_argument_validation_is_host_side():

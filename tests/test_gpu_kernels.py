@@ -345,3 +345,35 @@ def test_gemm_splitk_partials_and_fused_consumer(M, N, K, S):
     ops.splitk_gate_resid_adaln(parts, S, None, resid.to(DEV), mod.to(DEV), 2 * N, -1, -1, tpf, x_out=x2)
     xr2 = resid.double() + mod[fr, 2 * N:3 * N].double() * p.double().sum(1)
     assert (x2.cpu().double() - xr2).abs().max().item() < 1e-4
+
+
+# ---------------------------------------------------------------- residual base rebuilt in the gate epilogue
+@pytest.mark.parametrize("M,N,K,tpf", [(512, 768, 768, 256), (300, 1152, 320, 40), (256, 768, 3072, 16), (130, 64, 64, 1),
+                                       (10240, 1152, 1152, 256), (384, 256, 256, 32)])
+def test_gate_lnresid_epilogue_equals_the_stored_residual_base(M, N, K, tpf):
+    """DFOT_EPI_GATE_LNRESID_F32 (K1 writes bf16 + row statistics, the GEMM epilogue rebuilds modulate(LN(x)) from x in place)
+    against the two-buffer path (K1 stores the fp32 copy, DFOT_EPI_GATE_RESID_F32 reads it): bit-identical."""
+    g = torch.Generator().manual_seed(M + N + K + tpf)
+    frames = -(-M // tpf)
+    x = torch.randn((M, N), generator=g).to(DEV) * 2 + 0.3
+    mod = (torch.randn((frames, 3 * N + 8), generator=g) * 0.5).to(DEV)
+    a = torch.randn((M, K), generator=g).to(DEV).to(torch.bfloat16)
+    w = (torch.randn((N, K), generator=g) / math.sqrt(K)).to(DEV).to(torch.bfloat16)
+    bias = torch.randn((N,), generator=g).to(DEV)
+    # stored copy
+    y32, y16 = torch.empty_like(x), torch.empty((M, N), device=DEV, dtype=torch.bfloat16)
+    ops.adaln_layernorm(x, mod, 0, N, tpf, y_f32=y32, y_bf16=y16)
+    want = torch.empty_like(x)
+    ops.gemm_bf16(a, w, want, ops.EPI_GATE_RESID_F32, bias=bias, resid=y32, gate=mod[:, 2 * N:], ld_gate=mod.shape[1],
+                  tokens_per_frame=tpf)
+    # rebuilt
+    stats, y16b = torch.empty((M, 2), device=DEV), torch.empty_like(y16)
+    ops.adaln_layernorm(x, mod, 0, N, tpf, y_bf16=y16b, stats=stats)
+    assert torch.equal(y16, y16b)
+    ref_mean = x.double().mean(1)
+    assert (stats[:, 0].double() - ref_mean).abs().max().item() < 1e-5
+    assert (stats[:, 1].double() - 1 / torch.sqrt(x.double().var(1, unbiased=False) + 1e-6)).abs().max().item() < 1e-4
+    xs = x.clone()
+    ops.gemm_bf16(a, w, xs, ops.EPI_GATE_LNRESID_F32, bias=bias, resid=xs, gate=mod[:, 2 * N:], ld_gate=mod.shape[1],
+                  tokens_per_frame=tpf, ln_stats=stats, ln_shift=mod[:, 0:], ln_scale=mod[:, N:])
+    assert torch.equal(xs, want), (xs - want).abs().max().item()
