@@ -86,6 +86,56 @@ def test_random_dit3d_forward_vs_oracle(seed, monkeypatch):
     assert (got - want).abs().max().item() <= 2e-2, (cfg, (got - want).abs().max().item())
 
 
+def uvit_case(rng: random.Random):
+    """U-ViT3DPose at golden scale: channels / heads (head dims 64, 128) / blocks per level / mid blocks / resolution / frames /
+    pose normalisation drawn at random."""
+    from oracle.cases import algorithm_cfg
+    heads = rng.choice([1, 2])
+    c2 = 64 * heads * rng.choice([1, 2]) if heads == 1 else 128 * rng.choice([1, 2])
+    c3 = rng.choice([c2, 2 * c2]) if 2 * c2 // heads <= 128 else c2
+    channels = [32, rng.choice([32, 64]), c2, c3]
+    updown = [rng.choice([1, 2]), rng.choice([1, 2]), rng.choice([1, 2])]
+    res, frames = 32, rng.choice([2, 3, 4])
+    return algorithm_cfg(**{
+        **continuous_overrides(), "external_cond_type": "action", "external_cond_dim": 16,
+        "camera_pose_conditioning": dict(normalize_by=rng.choice(["first", "mean"]), bound=None, type="ray_encoding"),
+        "backbone": dict(name="u_vit3d_pose", channels=channels, emb_channels=64, patch_size=2,
+                         block_types=["ResBlock", "ResBlock", "TransformerBlock", "TransformerBlock"],
+                         block_dropouts=[0.0] * 4, num_updown_blocks=updown, num_mid_blocks=rng.choice([1, 2]),
+                         num_heads=heads, pos_emb_type="rope", use_checkpointing=[False] * 4, conditioning=dict(dim=None),
+                         external_cond_dropout=0.1, use_fourier_noise_embedding=rng.choice([True, False])),
+        "x_shape": [3, res, res], "max_frames": frames, "n_frames": frames, "context_frames": 1,
+        "data_mean": [[[0.5]]] * 3, "data_std": [[[0.5]]] * 3, "diffusion.sampling_timesteps": 3}), res, frames
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_uvit3d_pose_forward_vs_oracle(seed, monkeypatch):
+    """Cached-pose fast path and dense reference-style conditioning, one row's pose masked, vs the oracle."""
+    from oracle.cases import synthetic_poses
+    from oracle.pose import ray_encoding
+    from oracle.uvit3d_pose import UViT3DPoseOracle
+    from dfot_b200.algorithms.dfot import DFoTVideoPose
+    cfg, res, frames = uvit_case(random.Random(3000 + seed))
+    torch.manual_seed(seed)
+    algo = DFoTVideoPose(json.loads(json.dumps(cfg))).eval()
+    _redraw(algo)
+    model = algo.diffusion_model.model
+    oracle = UViT3DPoseOracle(cfg["backbone"], cfg["x_shape"], frames, {k: v.detach().clone() for k, v in model.state_dict().items()})
+    ops_emulation.install(monkeypatch)
+    model.use_cuda_graph = False
+    g = torch.Generator().manual_seed(seed)
+    x, levels = torch.randn((2, frames, 3, res, res), generator=g), torch.randn((2, frames), generator=g)
+    poses = synthetic_poses(1, frames)
+    norm = cfg["camera_pose_conditioning"]["normalize_by"]
+    enc = ray_encoding(poses.repeat_interleave(2, 0), res, norm, None, "ray_encoding")
+    mask = torch.tensor([True, False])
+    want = oracle(x, levels, enc, mask)
+    got = model(x, levels, algo._window_conditions(poses, 2), mask)
+    assert (got - want).abs().max().item() <= 2e-2, (cfg["backbone"], (got - want).abs().max().item())
+    got = model(x, levels, enc, mask)
+    assert (got - want).abs().max().item() <= 2e-2, (cfg["backbone"], "dense", (got - want).abs().max().item())
+
+
 def sampler_case(rng: random.Random):
     o = {"backbone.depth": 1}
     ctx = rng.choice([1, 2])
