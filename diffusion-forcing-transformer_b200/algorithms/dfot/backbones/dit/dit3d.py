@@ -435,6 +435,10 @@ class DiT3D(nn.Module):
             raise NotImplementedError(f"matrix attention feature width {self.matrix_feature_dim} (rows per head x "
                                       f"head_row_dim {self.matrix_head_dim}) unsupported by the attention kernel "
                                       "(64, 72, 128)")
+        if self.matrix_block != "matrix" and self.matrix_head_dim not in (64, 72, 128):
+            # attn2 of a MatrixSelf / MatrixCrossDiTBlock: num_row_heads heads of embed_row_dim / num_row_heads inside a frame
+            raise NotImplementedError(f"matrix_block={self.matrix_block}: token attention head dim {self.matrix_head_dim} "
+                                      "unsupported by the attention kernel (64, 72, 128)")
         # qkv_bias [embed_col_dim, 3E]: one bias row per column row.  One column row: the GEMM's bias vector; more: Mc extra
         # one-hot input columns select the row's bias out of Mc extra weight columns (_pack_matrix_block)
         self.matrix_bias_cols = _pad8(self.matrix_cols) if (cfg.use_bias and self.matrix_block == "matrix"

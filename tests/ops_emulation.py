@@ -225,6 +225,7 @@ def qk_norm_rope(qkv, q_weight, k_weight, rope_cs, tokens_per_sample, heads, hea
 
 
 def attention(qkv, out, R, Ntok, heads, head_dim, score_bound=0.0):
+    assert head_dim in (64, 72, 128), f"attention: head_dim {head_dim} unsupported (64, 72, 128)"      # the kernel's contract
     D = heads * head_dim
     q, k, v = qkv.float().reshape(R, Ntok, 3, heads, head_dim).permute(2, 0, 3, 1, 4).unbind(0)
     w = torch.softmax(q @ k.transpose(-1, -2) * math.log(2.0), dim=-1)       # q carries scale * log2(e)

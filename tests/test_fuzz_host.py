@@ -42,14 +42,15 @@ def dit_forward_case(rng: random.Random):
         multi = rng.choice([False, True])
         flat = (not multi) and rng.choice([False, True])
         d = erd // nrh
-        if (d if multi else n * d) not in (64, 72, 128):
-            return None
+        block = rng.choice(["matrix", "matrix_self", "matrix_cross"])
+        if (d if multi else n * d) not in (64, 72, 128) or (block != "matrix" and d not in (64, 72, 128)):
+            return None                                    # outside what the attention kernel covers (the constructor refuses)
         o.update({"backbone.pos_emb_type": "sinusoidal_2d", "backbone.hidden_size": erd, "backbone.embed_row_dim": erd,
                   "backbone.embed_col_dim": nch * n, "backbone.num_col_heads": nch, "backbone.num_row_heads": nrh,
                   "backbone.num_heads": erd // 64, "backbone.use_temporal_rope": rng.choice([False, True]),
                   "backbone.flatten_matrix_rope": flat, "backbone.matrix_multi_token": multi,
                   "backbone.use_bias": rng.choice([False, True]), "backbone.spatial_mlp_ratio": 2.0,
-                  "backbone.matrix_block": rng.choice(["matrix", "matrix_self", "matrix_cross"]), "backbone.fixed_u": None})
+                  "backbone.matrix_block": block, "backbone.fixed_u": None})
     else:
         o.update({"backbone.hidden_size": erd, "backbone.num_heads": erd // 64,
                   "backbone.pos_emb_type": rng.choice(["rope_3d", "learned_1d", "sinusoidal_1d"] if variant == "full" else

@@ -359,6 +359,36 @@ def test_matrix_attention_combinations_vs_oracle(combo):
         assert (got - want).abs().max().item() <= 2e-2, (got - want).abs().max().item()
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_random_dit3d_forward_on_gpu(seed):
+    """tests/test_fuzz_host.py's random DiT3D configurations (variant x positions x matrix block / head grouping / RoPE mode /
+    bias x conditioning x window length) on the kernels: eager forward and captured graph vs the CPU oracle."""
+    import random
+    from oracle.dit3d import DiT3DOracle
+    from dfot_b200.algorithms.dfot.backbones.dit.dit3d import DiT3D
+    from test_fuzz_host import _redraw, dit_forward_case
+    rng = random.Random(1000 + seed)
+    case = None
+    while case is None:
+        case = dit_forward_case(rng)
+    cfg, kw, T, with_mask = case
+    torch.manual_seed(seed)
+    model = DiT3D(cfg, [4, 8, 8], 4, use_causal_mask=False, **kw).eval()
+    _redraw(model)
+    oracle = DiT3DOracle(cfg, [4, 8, 8], 4, {k: v.detach().clone() for k, v in model.state_dict().items()},
+                         external_cond_dim=kw["external_cond_dim"])
+    g = torch.Generator().manual_seed(seed)
+    x, lv = torch.randn((2, T, 4, 8, 8), generator=g), torch.randint(0, 1000, (2, T), generator=g)
+    c = torch.randn((2, T, 3), generator=g) if kw["external_cond_dim"] else None
+    m = (torch.rand((2,), generator=g) < 0.5) if with_mask else None
+    want = oracle(x, lv, c, m)
+    model = model.to(DEV)
+    dev = lambda t: None if t is None else t.to(DEV)
+    for _ in range(3):                                   # eager, capture, replay
+        got = model(dev(x), dev(lv), dev(c), dev(m)).float().cpu()
+        assert (got - want).abs().max().item() <= 2e-2, (cfg, (got - want).abs().max().item())
+
+
 def test_lockstep_rounds_reproduce_the_sequential_rollout_on_gpu():
     """BASELINE configs[3] structure (keyframe windows + interpolation rounds): with a row shard the chunk batches of a
     round advance in lockstep, every batch drawing from its own position of torch's CUDA generator stream.  On one GPU

@@ -310,3 +310,17 @@ def test_dit3d_splitk_block_loop_equals_plain_loop(pos, monkeypatch):
     # the fp32 token streams differ in their last bits (summation order of the splits); where that flips the bf16 rounding of
     # a GEMM operand element the outputs move by up to ~1e-3 (seeds 0-5: 0 ... 1.2e-3), so the gate is the flip level
     assert (out_split - out_plain).abs().max().item() <= 2e-3 * max(1.0, out_plain.abs().max().item())
+
+
+def test_matrix_token_attention_head_dim_is_checked_at_construction():
+    """attn2 of a MatrixSelf / MatrixCrossDiTBlock runs num_row_heads heads of embed_row_dim / num_row_heads inside a frame: a
+    width the attention kernel does not cover is refused when the model is built, not at the first forward (found by the
+    randomised GPU test: two row heads of 32 pass the matrix-attention check — 2 rows x 32 = 64 — but not attn2's)."""
+    from oracle.cases import MATRIX_COMBOS, matrix_combo_cfg
+    from dfot_b200.algorithms.dfot.backbones.dit.dit3d import DiT3D
+    ok = ("full_matrix_attention", "matrix", 2, 1, 2, 64, True, False, False, False, None)          # 2 rows x 32 = 64
+    DiT3D(matrix_combo_cfg(ok), [4, 8, 8], 4, use_causal_mask=False)
+    for block in ("matrix_self", "matrix_cross"):
+        bad = (ok[0], block) + ok[2:]
+        with pytest.raises(NotImplementedError, match="token attention head dim 32"):
+            DiT3D(matrix_combo_cfg(bad), [4, 8, 8], 4, use_causal_mask=False)
