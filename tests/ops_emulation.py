@@ -11,6 +11,12 @@ from dfot_b200 import ops
 BF = torch.bfloat16
 
 
+def _col_offset(t):
+    """Element offset of a view's first element inside its row (0 for whole tensors): the kernels want 16-byte aligned
+    pointers, and the base allocations are, so the offset decides."""
+    return t.storage_offset() % t.stride(0) if t.dim() == 2 and t.stride(0) > 0 else 0
+
+
 def cast_bf16(src, out=None):
     if out is None:
         return src.to(BF)
@@ -44,6 +50,17 @@ def _epilogue(acc, out, epilogue, bias, resid):
 
 def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, M=None, **kw):
     assert a.dtype == BF and w.dtype == BF
+    # the kernel's contract (dfot_gemm_bf16: 16-byte TMA strides, 16-byte aligned operands and epilogue vectors)
+    assert w.shape[1] % 8 == 0 and a.stride(0) % 8 == 0 and w.stride(0) % 8 == 0, "gemm: K, lda, ldw must be multiples of 8"
+    assert w.shape[0] % 8 == 0 and out.stride(0) % 8 == 0, "gemm: N and ldc must be multiples of 8"
+    assert _col_offset(a) % 8 == 0 and _col_offset(w) % 8 == 0, "gemm: A, W must be 16-byte aligned"
+    assert _col_offset(out) % (4 if out.dtype == torch.float32 else 8) == 0, "gemm: C must be 16-byte aligned"
+    if kw.get("gate") is not None:
+        assert _col_offset(kw["gate"]) % 4 == 0 and kw.get("ld_gate", 0) % 4 == 0, "gemm: gate must be 16-byte aligned"
+    if epilogue in (ops.EPI_QKV_ROPE_BF16, ops.EPI_QKNORM_ROPE_BF16):
+        assert kw["head_dim"] % 2 == 0 and kw["model_dim"] % kw["head_dim"] == 0 and w.shape[0] == 3 * kw["model_dim"]
+    if epilogue == ops.EPI_QKNORM_ROPE_BF16:
+        assert kw["head_dim"] in (64, 128) and w.shape[0] > 128
     M = a.shape[0] if M is None else M
     acc = a[:M].float() @ w.float().t()
     if epilogue == ops.EPI_QKNORM_ROPE_BF16:      # q/k RMSNorm(head_dim) * weight, RoPE-3D, q * q_scale; v untouched
@@ -89,6 +106,7 @@ def gemm_bf16(a, w, out, epilogue, bias=None, resid=None, M=None, **kw):
 
 def adaln_layernorm(x, mod, shift_col, scale_col, tokens_per_frame, y_f32=None, y_bf16=None, eps=1e-6, stats=None):
     M, D = x.shape
+    assert D % 4 == 0 and mod.shape[-1] % 4 == 0 and shift_col % 4 == 0 and scale_col % 4 == 0 and D <= 4096, "adaln contract"
     frame = torch.arange(M) // tokens_per_frame
     mean = x.float().mean(-1, keepdim=True)
     rstd = torch.rsqrt(((x.float() - mean) ** 2).mean(-1, keepdim=True) + eps)
@@ -103,12 +121,15 @@ def adaln_layernorm(x, mod, shift_col, scale_col, tokens_per_frame, y_f32=None, 
 
 def patch_mix_bf16(y, u, out, R, L, P, Mc):
     D = y.shape[-1]
+    assert D % 4 == 0, "patch_mix: D % 4"
     s = torch.einsum("nc,rlnd->rcld", u.reshape(P, Mc).float(), y.reshape(R, L, P, D).float())
     out.copy_(s.reshape(out.shape).to(BF))
 
 
 def patch_expand_gate_resid(x, y, z, pu, pb, gate, ld_gate, R, L, P, Mc):
     D = x.shape[-1]
+    assert D % 4 == 0 and (gate is None or (ld_gate % 4 == 0 and ld_gate >= D and _col_offset(gate) % 4 == 0)), "patch_expand contract"
+    assert y is None or x.data_ptr() != y.data_ptr(), "patch_expand: x must not alias y"
     s = torch.einsum("cn,rcld->rlnd", pu.reshape(Mc, P).float(), z.reshape(R, Mc, L, D).float())
     if pb is not None:
         s = s + pb.reshape(1, 1, P, D)
@@ -210,6 +231,7 @@ def rmsnorm_film_bf16(x, weight, mod_img, scale_col, shift_col, tokens_per_img, 
 
 
 def qk_norm_rope(qkv, q_weight, k_weight, rope_cs, tokens_per_sample, heads, head_dim, q_scale, eps=1e-6):
+    assert head_dim in (64, 128) and 2 * heads * head_dim <= 4096 and qkv.stride(0) % 8 == 0, "qk_norm_rope contract"
     M = qkv.shape[0]
     D = heads * head_dim
     q, k = (qkv[:, i * D:(i + 1) * D].float().reshape(M, heads, head_dim) for i in range(2))
@@ -226,6 +248,7 @@ def qk_norm_rope(qkv, q_weight, k_weight, rope_cs, tokens_per_sample, heads, hea
 
 def attention(qkv, out, R, Ntok, heads, head_dim, score_bound=0.0):
     assert head_dim in (64, 72, 128), f"attention: head_dim {head_dim} unsupported (64, 72, 128)"      # the kernel's contract
+    assert out.stride(0) % 8 == 0 and out.stride(0) >= heads * head_dim and _col_offset(out) % 8 == 0, "attention: ld_out / alignment"
     D = heads * head_dim
     q, k, v = qkv.float().reshape(R, Ntok, 3, heads, head_dim).permute(2, 0, 3, 1, 4).unbind(0)
     w = torch.softmax(q @ k.transpose(-1, -2) * math.log(2.0), dim=-1)       # q carries scale * log2(e)
