@@ -182,6 +182,7 @@ def silu_sum_bf16(a, b, row_mask, rows_per_mask, out):
 
 def conv3x3_bf16(x, w, out, epilogue, bias=None, resid=None, gn_sums=None, gn_groups=32, gn_eps=1e-6):
     assert x.dtype == BF and w.dtype == BF
+    _conv_contract(x.shape[1], x.shape[2], x.shape[3], w.shape[0], out.stride(0) if out.dim() == 2 else w.shape[0])
     y = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), None, padding=1).permute(0, 2, 3, 1)
     _epilogue(y.reshape(-1, w.shape[0]), out, epilogue, bias, resid)
     if gn_sums is not None:      # side output: statistics of the stored output
@@ -301,8 +302,20 @@ def noise_features(levels, out, fourier_freqs=None, fourier_phases=None):
 
 
 # ------------------------------------------------------------------ VAE-decode row (clips [B, 2 + T, H, W, C])
+def _conv_contract(H, W, Cin, Cout, ldc):
+    """dfot_conv3x3_bf16 / dfot_conv3d_causal_bf16: channel counts and the image-tile rules of the 4-D TMA box."""
+    assert Cin % 8 == 0 and Cout % 8 == 0 and ldc % 8 == 0, "conv3x3: Cin, Cout, ldc must be multiples of 8"
+    pow2 = lambda n: n > 0 and n & (n - 1) == 0
+    if W >= 128:
+        assert W % 128 == 0, "conv3x3: W must be a multiple of 128 or a power of two"
+    else:
+        assert pow2(W), "conv3x3: W must be a power of two below 128"
+        assert H % (128 // W) == 0 if H * W >= 128 else pow2(H), "conv3x3: H vs the 128-pixel tile"
+
+
 def conv3d_causal_bf16(x, w, out, epilogue, bias=None, resid=None):
     assert x.dtype == BF and w.dtype == BF
+    _conv_contract(x.shape[1], x.shape[2], x.shape[3], w.shape[0], out.stride(0) if out.dim() == 2 else w.shape[0])
     kt = w.shape[1]
     xs = x.float().permute(3, 0, 1, 2)[None]                                    # [1, Cin, n_in, H, W]
     y = F.conv3d(xs, w.float().permute(0, 4, 1, 2, 3), None, padding=(0, 1, 1))[0].permute(1, 2, 3, 0)
